@@ -1,0 +1,206 @@
+/*
+ * qb200.h — plain-C ABI of the B200-native QuBLAS hot path (libqb200.so).
+ *
+ * The reference (pikapuma/QuBLAS, header-only C++23) has no FFI seam: its boundary is
+ * the template API itself.  This ABI is what a binding of that API lowers to: every
+ * `Qu<...>` type becomes a POD `qb_qdesc`, every per-level `TypeList` a `qb_levels`,
+ * every tensor a buffer of raw two's-complement words in the reference's own memory
+ * layout (`ArbiInt<N>::data`, QuBLAS.h:353 — int32 for N<=32, int64 for N<=64;
+ * tensors column-major, QuBLAS.h:2680-2692; complex elements AoS {real, imag},
+ * QuBLAS.h:2501-2617).
+ *
+ * Reference interface each entry point replaces (file:line in /root/reference):
+ *   qb200_reduce_batched   <- Qreduce<Args...>(tensor / scalars...)   include/QuBLAS.h:4903-5018
+ *   qb200_gemul_batched    <- Qgemul<QgemulAddArgs<>,QgemulMulArgs<>,QgemulTransposedA<>>(C,A,B)
+ *                             readme.md:80-87 (documented only; composed from Qmul :3980-3985,
+ *                             Qreduce :5014-5018 and the converting ctor :2398-2411)
+ *   qb200_cgemul_batched   <- the same call with Qcomplex elements and
+ *                             MulArgs = TFComplexMul<abT..BCT>       include/QuBLAS.h:3453-3535,
+ *                             accumulated with complex Qadd           include/QuBLAS.h:3549-3568
+ *   qb200_tfcmul_batched   <- tensor Qmul<TFComplexMul<...>>(x, y)    include/QuBLAS.h:3783-3811, 4080-4085
+ *   qb200_convert_batched  <- element-wise converting assignment      include/QuBLAS.h:2398-2411, 2759-2830
+ *
+ * All functions return 0 on success and a negative QB_E* code on failure; the message is
+ * available from qb200_last_error() (thread-local).  Nothing throws.  There is no CPU
+ * fallback: without a CUDA device every compute entry point fails with QB_ENODEVICE.
+ */
+#ifndef QB200_H
+#define QB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QB200_ABI_VERSION 1
+#define QB_MAX_LEVELS 64
+
+/* QuMode ids == the reference's ::value constants (QuBLAS.h:1988-1998). */
+enum qb_qumode {
+    QB_RND_POS_INF = 0, QB_RND_NEG_INF = 1, QB_RND_ZERO = 2, QB_RND_INF = 3, QB_RND_CONV = 4,
+    QB_TRN_TCPL = 5, QB_TRN_SMGN = 6
+};
+/* OfMode ids == the reference's ::value constants (QuBLAS.h:2212-2223). */
+enum qb_ofmode { QB_SAT_TCPL = 0, QB_SAT_ZERO = 1, QB_SAT_SMGN = 2, QB_WRP_TCPL = 3 };
+
+enum qb_status {
+    QB_OK = 0,
+    QB_EINVAL = -1,      /* malformed plan / null pointer                                   */
+    QB_EDOMAIN = -2,     /* plan is outside the bit-exact parity domain     */
+    QB_ENODEVICE = -3,   /* no CUDA device / driver                                         */
+    QB_ECUDA = -4,       /* a CUDA call failed                                              */
+    QB_ENOMEM = -5
+};
+
+/* Where the caller's buffers live. */
+enum qb_memkind { QB_MEM_HOST = 0, QB_MEM_DEVICE = 1 };
+
+/* Tree form for non-power-of-two counts (QuBLAS.h:4924-4957 vs :4960-4990). */
+enum qb_treeform { QB_TREE_VECTOR = 0, QB_TREE_VARIADIC = 1 };
+
+/* One fixed-point type: Qu<intBits<i>, fracBits<f>, isSigned<s>, QuMode<q>, OfMode<o>>
+ * (QuBLAS.h:2368-2385).  Stored width is always 1 + int_bits + frac_bits.
+ * word_bytes: storage word of buffers holding this type: 0 = the reference's natural word
+ * (4 if width<=32 else 8); 1/2/4/8 select a packed word (sign-extended on load). */
+typedef struct qb_qdesc {
+    int16_t int_bits;
+    int16_t frac_bits;
+    uint8_t is_signed;
+    uint8_t qu_mode;   /* enum qb_qumode */
+    uint8_t of_mode;   /* enum qb_ofmode */
+    uint8_t word_bytes;
+} qb_qdesc;
+
+/* Per-level accumulation types: level l uses lv[min(l, n-1)] (QuBLAS.h:4913).
+ * n == 0 means "no AddArgs": every level uses the default AddMerger of its operands
+ * (QuBLAS.h:3125-3140). */
+typedef struct qb_levels {
+    uint32_t n;
+    qb_qdesc lv[QB_MAX_LEVELS];
+} qb_levels;
+
+/* Qreduce over `batch` independent vectors of `len` elements each. */
+typedef struct qb_reduce_plan {
+    qb_qdesc  elem;
+    qb_levels levels;
+    uint64_t  len;
+    uint32_t  tree_form;      /* enum qb_treeform */
+    uint32_t  reserved;
+} qb_reduce_plan;
+
+/* Real Qgemul: C[i,j] = conv_c( tree_k( Qmul<mul>(opA(i,k), opB(k,j)) ) ).
+ * A is M x K (K x M when trans_a), B is K x N (N x K when trans_b), C is M x N; all column-major.
+ * stride_* are in elements between consecutive instances; 0 for A/B = shared by all instances. */
+typedef struct qb_gemul_plan {
+    qb_qdesc  a, b, mul, c;
+    qb_levels add;
+    uint32_t  M, N, K;
+    uint8_t   trans_a, trans_b, tree_form, reserved;
+    int64_t   stride_a, stride_b, stride_c;
+} qb_gemul_plan;
+
+/* Resolved types of the TFComplexMul dataflow (QuBLAS.h:3510-3535), x = a+bi, y = c+di:
+ *   ab = a+b, cd = c+d, ba = b-a, A = ab*c (abc), B = cd*b (bad), C = ba*d (cdb),
+ *   re = A-B (AB), im = B-C (BC).
+ * The reference's routing quirks (badT governs B, cdbT governs C, baT is ignored) are applied
+ * by the host lowering, not here: these are the types each node really has. */
+typedef struct qb_tfc_types {
+    qb_qdesc ab, cd, ba, abc, bad, cdb, AB, BC;
+} qb_tfc_types;
+
+/* Complex Qgemul with TFComplexMul products and component-wise tree accumulation. */
+typedef struct qb_cgemul_plan {
+    qb_qdesc     a_re, a_im, b_re, b_im;
+    qb_tfc_types tf;
+    qb_levels    add_re, add_im;
+    qb_qdesc     c_re, c_im;
+    uint32_t     M, N, K;
+    uint8_t      trans_a, trans_b, tree_form, reserved;
+    int64_t      stride_a, stride_b, stride_c;   /* in complex elements */
+} qb_cgemul_plan;
+
+/* Element-wise TFComplexMul of two complex vectors (output type = {AB, BC}). */
+typedef struct qb_tfcmul_plan {
+    qb_qdesc     x_re, x_im, y_re, y_im;
+    qb_tfc_types tf;
+    uint64_t     len;
+} qb_tfcmul_plan;
+
+/* Element-wise conversion from -> to (converting ctor, target's modes). */
+typedef struct qb_convert_plan {
+    qb_qdesc from, to;
+    uint64_t len;
+} qb_convert_plan;
+
+/* What the library decided for a plan (for tests, benchmarks and DESIGN.md tables). */
+typedef struct qb_plan_info {
+    int32_t arith_bits;        /* 32 or 64: register arithmetic class of the kernel            */
+    int32_t max_inter_bits;    /* widest intermediate (two's complement bits) the plan produces */
+    int32_t lossless;          /* 1 if every quantizer on the accumulation path is an identity  */
+    int32_t tensor_core;       /* 1 if the tcgen05 kind::i8 path is selected                    */
+    int32_t specialized;       /* 1 if a compile-time-specialised kernel is used                */
+    int32_t out_word_bytes;    /* storage word of the result buffer                             */
+    qb_qdesc out_type;         /* type of the result (reduce: last level reached)               */
+    char    kernel[96];        /* kernel variant name                                           */
+} qb_plan_info;
+
+/* Execution context: where buffers live, which device, which stream (cudaStream_t or NULL). */
+typedef struct qb_exec {
+    int32_t  mem_kind;   /* enum qb_memkind */
+    int32_t  device;     /* CUDA device ordinal; -1 = current device                           */
+    void    *stream;     /* cudaStream_t; NULL = default stream. Host-memory calls synchronise. */
+    uint32_t flags;      /* QB_F_*                                                             */
+    uint32_t reserved;
+} qb_exec;
+
+#define QB_F_NO_TENSOR_CORE 0x1u   /* force the integer-ALU path even when kind::i8 is legal  */
+#define QB_F_NO_SPECIALIZE  0x2u   /* force the runtime-descriptor kernels                    */
+
+int         qb200_abi_version(void);
+const char *qb200_last_error(void);
+int         qb200_device_count(void);
+/* Number of kernels launched by this library on this thread since the last reset. */
+uint64_t    qb200_launch_count(void);
+void        qb200_launch_count_reset(void);
+
+/* Plan validation + kernel selection without running anything (no device needed). */
+int qb200_reduce_plan_info(const qb_reduce_plan *plan, qb_plan_info *info);
+int qb200_gemul_plan_info(const qb_gemul_plan *plan, qb_plan_info *info);
+int qb200_cgemul_plan_info(const qb_cgemul_plan *plan, qb_plan_info *info);
+
+/* x: batch*len words (elem word).  out: batch words of the result type.
+ * partials (optional, may be NULL): per-vector level-`partial_level` nodes,
+ * ceil(len / 2^partial_level) words each, emitted for depth-wise parity checks. */
+int qb200_reduce_batched(const qb_reduce_plan *plan, const void *x, void *out,
+                         void *partials, uint32_t partial_level,
+                         uint64_t batch, const qb_exec *exec);
+
+int qb200_gemul_batched(const qb_gemul_plan *plan, const void *A, const void *B, void *C,
+                        uint64_t batch, const qb_exec *exec);
+
+/* Complex buffers are AoS {re, im}; both parts use the wider of the two natural words. */
+int qb200_cgemul_batched(const qb_cgemul_plan *plan, const void *A, const void *B, void *C,
+                         uint64_t batch, const qb_exec *exec);
+
+int qb200_tfcmul_batched(const qb_tfcmul_plan *plan, const void *x, const void *y, void *out,
+                         uint64_t batch, const qb_exec *exec);
+
+int qb200_convert_batched(const qb_convert_plan *plan, const void *in, void *out,
+                          uint64_t batch, const qb_exec *exec);
+
+/* Deterministic synthetic raw words, uniform over [lo, hi], counter-based:
+ * word[i] = lo + mix64(seed, stream_id, first_index + i) mod (hi - lo + 1).
+ * Same function on host and device; buffers are device memory when
+ * exec->mem_kind == QB_MEM_DEVICE. */
+int qb200_synth_fill(void *dst, uint64_t count, uint32_t word_bytes, int64_t lo, int64_t hi,
+                     uint64_t seed, uint64_t stream_id, uint64_t first_index, const qb_exec *exec);
+
+/* Contiguous shard [first, first+count) of `total` units for `rank` of `world` (batch or M-panel). */
+int qb200_shard_range(uint64_t total, uint32_t world, uint32_t rank, uint64_t *first, uint64_t *count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QB200_H */

@@ -1,0 +1,447 @@
+#!/usr/bin/env python3
+"""Golden-vector generator: runs the UNMODIFIED reference header and records its answers.
+
+TEST INFRASTRUCTURE.  Runs only in the build container (needs /root/reference, read-only):
+
+    python oracle/ref_harness_gen.py            # regenerates tests/golden/ref_*.json
+
+What it does
+  1. builds a deterministic list of cases (seeded) over the hot path of the reference:
+       scalar   Qmul / Qadd / Qsub / converting ctor       include/QuBLAS.h:3146-3235, 2398-2411
+       reduce   Qreduce vector form and variadic form       include/QuBLAS.h:4903-5018
+       tf       Qmul<TFComplexMul<...>>(x, y)               include/QuBLAS.h:3510-3535
+       gemul    the readme.md:80-87 composition Qmul -> Qreduce -> converting assignment
+       cgemul   TFComplexMul products -> variadic complex Qreduce (QuBLAS.h:3549-3568)
+  2. emits oracle/_ref/ref_cases.cpp that instantiates every case with the reference's own
+     templates, compiles it with g++ -std=c++23 against /root/reference/include (sources are
+     compiled where they lie; nothing is copied), loads the .so and runs every case;
+  3. writes inputs, the reference's outputs AND the reference's deduced result types to
+     tests/golden/ref_*.json.  Those fixtures travel to the GPU box; the reference does not.
+
+All cases stay inside the parity domain of SURVEY.md 2.3 (every intermediate <= 64 bits, no RND
+right shift of 31/32/63/64, no unsigned WRP::TCPL target with intBits+fracBits in {32,64} — there
+ArbiInt<32>::allOnes() sign-extends and the wrap mask is a no-op, found by this generator) where
+the reference equals the ideal integer model.
+"""
+import ctypes
+import json
+import os
+import random
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_INC = os.environ.get("QUBLAS_REF_INCLUDE", "/root/reference/include")
+OUT_DIR = os.path.join(ROOT, "oracle", "_ref")
+GOLD_DIR = os.path.join(ROOT, "tests", "golden")
+
+QU = ["RND::POS_INF", "RND::NEG_INF", "RND::ZERO", "RND::INF", "RND::CONV", "TRN::TCPL", "TRN::SMGN"]
+OF = ["SAT::TCPL", "SAT::ZERO", "SAT::SMGN", "WRP::TCPL"]
+
+
+def T(i, f, s=True, q=5, o=0):
+    return {"i": i, "f": f, "s": bool(s), "q": q, "o": o}
+
+
+def cxx_type(t):
+    return "Qu<intBits<%d>, fracBits<%d>, isSigned<%s>, QuMode<%s>, OfMode<%s>>" % (
+        t["i"], t["f"], "true" if t["s"] else "false", QU[t["q"]], OF[t["o"]])
+
+
+def cxx_tags(tags):
+    """Partial tag list (merger arguments): any subset of i/f/s/q/o plus FullPrec."""
+    if tags is None:
+        return ""
+    parts = []
+    if "i" in tags: parts.append("intBits<%d>" % tags["i"])
+    if "f" in tags: parts.append("fracBits<%d>" % tags["f"])
+    if "s" in tags: parts.append("isSigned<%s>" % ("true" if tags["s"] else "false"))
+    if "q" in tags: parts.append("QuMode<%s>" % QU[tags["q"]])
+    if "o" in tags: parts.append("OfMode<%s>" % OF[tags["o"]])
+    if tags.get("full"): parts.append("FullPrec")
+    return ", ".join(parts)
+
+
+def width(t):
+    return 1 + t["i"] + t["f"]
+
+
+def raw_range(t):
+    w = width(t)
+    return -(1 << (w - 1)), (1 << (w - 1)) - 1
+
+
+def rand_raw(rng, t):
+    lo, hi = raw_range(t)
+    r = rng.random()
+    if r < 0.08: return lo
+    if r < 0.16: return hi
+    if r < 0.22: return rng.choice([0, 1, -1, 2, -2])
+    if r < 0.35: return rng.randint(max(lo, -40), min(hi, 40))
+    return rng.randint(lo, hi)
+
+
+BAD_SHIFTS = {31, 32, 63, 64}
+
+# ------------------------------------------------------------------------------------------
+# case construction
+# ------------------------------------------------------------------------------------------
+
+def scalar_cases(rng):
+    cases = []
+    for op in ("mul", "add", "sub"):
+        for q in range(7):
+            for o in range(4):
+                for rep in range(2):
+                    while True:
+                        big = rep == 1 and rng.random() < 0.6
+                        wmax = 30 if big else 15
+                        a = T(rng.randint(-2, wmax // 2 + 3), 0, rng.random() < 0.8, rng.randrange(7), rng.randrange(4))
+                        a["f"] = rng.randint(max(-a["i"], -3), wmax - a["i"])
+                        b = T(rng.randint(-2, wmax // 2 + 3), 0, rng.random() < 0.8, rng.randrange(7), rng.randrange(4))
+                        b["f"] = rng.randint(max(-b["i"], -3), wmax - b["i"])
+                        if width(a) < 2 or width(b) < 2:
+                            continue
+                        from_f = a["f"] + b["f"] if op == "mul" else max(a["f"], b["f"])
+                        s = rng.choice([-3, -1, 0, 1, 1, 2, 3, 5, 8, 12]) if rng.random() < 0.85 else rng.randint(13, 28)
+                        to_f = from_f - s
+                        if op == "mul":
+                            inter = width(a) + width(b)
+                        else:
+                            mf = max(a["f"], b["f"])
+                            inter = max(width(a) + mf - a["f"], width(b) + mf - b["f"]) + 1
+                        inter += max(0, -s) + 1
+                        if inter > 62 or s in BAD_SHIFTS:
+                            continue
+                        # result width: sometimes tight (forces overflow handling), sometimes roomy
+                        full_int = inter - from_f
+                        to_i = rng.choice([full_int - 6, full_int - 3, full_int - 1, full_int, full_int + 1])
+                        to_i = max(to_i, -to_f)
+                        if 1 + to_i + to_f < 2 or 1 + to_i + to_f > 62:
+                            continue
+                        to = T(to_i, to_f, rng.random() < 0.75, q, o)
+                        if o == 3 and not to["s"] and (to_i + to_f) in (32, 64):
+                            continue        # reference defect: unsigned WRP mask of exactly 32/64 bits is a no-op
+                        break
+                    cases.append({"kind": "scalar", "op": op, "a": a, "b": b, "to": to})
+    # merger-default and partial-tag cases (QuBLAS.h:3107-3140)
+    for op in ("mul", "add", "sub"):
+        for tags in (None, {"full": True}, {"i": 9}, {"f": 2, "q": 4}, {"o": 3, "s": False}, {"full": True, "q": 0}):
+            a = T(rng.randint(2, 7), rng.randint(0, 6), rng.random() < 0.8, rng.randrange(7), rng.randrange(4))
+            b = dict(a) if rng.random() < 0.4 else T(rng.randint(2, 7), rng.randint(0, 6), rng.random() < 0.8,
+                                                     rng.randrange(7), rng.randrange(4))
+            cases.append({"kind": "scalar", "op": op, "a": a, "b": b, "tags": tags})
+    # converting ctor
+    for q in range(7):
+        for o in range(4):
+            for rep in range(2):
+                while True:
+                    a = T(rng.randint(0, 20), rng.randint(0, 20), True, rng.randrange(7), rng.randrange(4))
+                    s = rng.choice([-4, -1, 0, 1, 2, 3, 4, 7, 9, 15])
+                    to_f = a["f"] - s
+                    to_i = rng.choice([a["i"] - 5, a["i"] - 2, a["i"], a["i"] + 2])
+                    to_i = max(to_i, -to_f)
+                    if 2 <= 1 + to_i + to_f <= 62 and width(a) + max(0, -s) <= 62 and s not in BAD_SHIFTS:
+                        break
+                cases.append({"kind": "scalar", "op": "conv", "a": a, "b": a, "to": T(to_i, to_f, rng.random() < 0.7, q, o)})
+    return cases
+
+
+def level_list(rng, elem, nlev, uniform_mode=None):
+    lv = []
+    i, f = elem["i"], elem["f"]
+    for l in range(nlev):
+        i += rng.choice([0, 1, 1, 2])
+        f -= rng.choice([0, 0, 1, 1, 2])
+        if i + f < 1:
+            f = 1 - i
+        q = uniform_mode if uniform_mode is not None else rng.randrange(7)
+        lv.append(T(i, f, rng.random() < 0.9, q, rng.randrange(4)))
+    return lv
+
+
+def reduce_cases(rng):
+    cases = []
+    vec_lens = [1, 2, 3, 4, 5, 6, 7, 8, 9, 15, 16, 17, 31, 32, 33, 63, 64, 65, 100, 127, 128, 129, 255, 256, 257, 500, 512, 1000]
+    for n in vec_lens:
+        for rep in range(2):
+            elem = T(rng.randint(3, 9), rng.randint(2, 9), rng.random() < 0.85, rng.randrange(7), rng.randrange(4))
+            nlev = rng.choice([0, 1, 2, 3, 4, 6, 12]) if rep else rng.choice([1, 3, 5])
+            cases.append({"kind": "reduce", "form": "vector", "len": n, "elem": elem,
+                          "levels": level_list(rng, elem, nlev, None if rep else rng.randrange(7))})
+    for n in [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 16, 17, 24, 31, 32, 33]:
+        for rep in range(2):
+            elem = T(rng.randint(3, 9), rng.randint(2, 9), True, rng.randrange(7), rng.randrange(4))
+            nlev = rng.choice([0, 1, 2, 3, 6])
+            cases.append({"kind": "reduce", "form": "variadic", "len": n, "elem": elem,
+                          "levels": level_list(rng, elem, nlev)})
+    # readme reductions (readme.md:57,61,64): red1 / red2 are pinned with their exact inputs below
+    return cases
+
+
+TF_TAGS = ["abT", "cdT", "baT", "abcT", "cdbT", "badT", "ABT", "BCT"]
+
+
+def tf_cases(rng):
+    cases = []
+    t44 = T(4, 4)
+    # the SURVEY 2.5 probe: distinct frac bits per tag expose the routing quirks
+    cases.append({"kind": "tf", "x_re": t44, "x_im": t44, "y_re": t44, "y_im": t44,
+                  "tags": {"abT": T(6, 3), "cdT": T(6, 2), "baT": T(6, 1), "abcT": T(10, 5), "cdbT": T(10, 6),
+                           "badT": T(10, 7), "ABT": T(11, 3, True, 4, 0), "BCT": T(12, 2, True, 3, 0)}})
+    cases.append({"kind": "tf", "x_re": t44, "x_im": t44, "y_re": t44, "y_im": t44, "tags": {}})
+    # BASELINE config 4 types
+    t = T(3, 12); P = T(6, 12); S = T(7, 12)
+    cases.append({"kind": "tf", "x_re": t, "x_im": t, "y_re": t, "y_im": t,
+                  "tags": {"abT": T(4, 12), "cdT": T(4, 11), "abcT": P, "cdbT": P, "badT": P, "ABT": S, "BCT": S}})
+    for rep in range(12):
+        def rt(lo=2, hi=8):
+            return T(rng.randint(lo, hi), rng.randint(0, 8), rng.random() < 0.85, rng.randrange(7), rng.randrange(4))
+        xr, xi, yr, yi = rt(), rt(), rt(), rt()
+        if rep % 3 == 0:
+            xi = dict(xr); yi = dict(yr)
+        tags = {}
+        for name in TF_TAGS:
+            if rng.random() < 0.7:
+                tags[name] = rt(4, 14)
+        cases.append({"kind": "tf", "x_re": xr, "x_im": xi, "y_re": yr, "y_im": yi, "tags": tags})
+    return cases
+
+
+def gemul_cases(rng):
+    cases = []
+    type1 = T(6, 3, True, 5, 1)     # readme.md:31  Qu<isSigned<true>,intBits<6>,fracBits<3>,OfMode<SAT::ZERO>>
+    type2 = T(6, -3, True, 5, 0)    # readme.md:35  Qu<intBits<6>,fracBits<-3>>
+    for ta in (True, False):
+        cases.append({"kind": "gemul", "M": 4, "N": 4, "K": 4, "a": type1, "b": type1, "mul": type1, "c": type1,
+                      "levels": [type1, type2], "trans_a": ta, "form": "vector", "readme": True})
+    for (M, N, K, form) in [(3, 2, 8, "vector"), (2, 3, 5, "vector"), (2, 3, 5, "variadic"), (5, 4, 16, "vector"),
+                            (2, 2, 7, "variadic"), (2, 2, 7, "vector"), (3, 3, 1, "vector"), (4, 2, 32, "vector")]:
+        a = T(rng.randint(3, 7), rng.randint(3, 8), True, rng.randrange(7), rng.randrange(4))
+        b = T(rng.randint(3, 7), rng.randint(3, 8), True, rng.randrange(7), rng.randrange(4))
+        mul = T(a["i"] + b["i"] - rng.randint(0, 2), max(a["f"], b["f"]) - rng.randint(0, 2), True, rng.randrange(7), rng.randrange(4))
+        lv = level_list(rng, mul, rng.choice([1, 2, 3, 5]))
+        c = T(mul["i"] + rng.randint(0, 3), mul["f"] - rng.randint(0, 4), True, rng.randrange(7), rng.randrange(4))
+        cases.append({"kind": "gemul", "M": M, "N": N, "K": K, "a": a, "b": b, "mul": mul, "c": c, "levels": lv,
+                      "trans_a": rng.random() < 0.5, "form": form})
+    return cases
+
+
+def cgemul_cases(rng):
+    cases = []
+    for (K, half) in [(4, False), (8, True), (16, False), (5, False)]:
+        t = T(3, 12); P = T(6, 12); S = T(7, 12)
+        tags = {"abT": T(4, 12), "cdT": T(4, 11), "abcT": P, "cdbT": P, "badT": P, "ABT": S, "BCT": S}
+        lv = [T(8 + l, 12 - l, True, 4, 0) for l in range(4)]
+        cases.append({"kind": "cgemul", "K": K, "x_re": t, "x_im": t, "y_re": t, "y_im": t, "tags": tags,
+                      "levels": lv, "half_range": half})
+    return cases
+
+
+# ------------------------------------------------------------------------------------------
+# C++ emission
+# ------------------------------------------------------------------------------------------
+
+PRELUDE = r'''// GENERATED by oracle/ref_harness_gen.py — do not commit. Includes the unmodified reference header.
+#include "QuBLAS.h"
+#include <cstdint>
+using namespace QuBLAS;
+template <typename Q> static inline void put_type(int64_t *o, const Q &) {
+    o[0] = Q::intB; o[1] = Q::fracB; o[2] = Q::isS; o[3] = Q::QuM; o[4] = Q::OfM;
+}
+template <typename Q> static inline Q mk(int64_t raw) { Q q; q.data.data = (decltype(q.data.data))raw; return q; }
+'''
+
+
+def emit_scalar(c, idx):
+    A, B = cxx_type(c["a"]), cxx_type(c["b"])
+    if c["op"] == "conv":
+        body = "auto r = %s(mk<%s>(in[0]));" % (cxx_type(c["to"]), A)
+    else:
+        fn = {"mul": "Qmul", "add": "Qadd", "sub": "Qsub"}[c["op"]]
+        targ = cxx_type(c["to"]) if "to" in c else cxx_tags(c.get("tags"))
+        body = "auto r = %s<%s>(mk<%s>(in[0]), mk<%s>(in[1]));" % (fn, targ, A, B)
+    return "static void case_%d(const int64_t *in, int64_t *out) { %s out[0] = (int64_t)r.data.data; put_type(out + 1, r); }\n" % (idx, body)
+
+
+def emit_levels(levels):
+    if not levels:
+        return ""
+    return "TypeList<%s>" % ", ".join(cxx_type(t) for t in levels)
+
+
+def emit_reduce(c, idx):
+    E = cxx_type(c["elem"])
+    n = c["len"]
+    L = emit_levels(c["levels"])
+    if c["form"] == "vector":
+        body = ("static Qu<dim<%d>, %s> v; for (int i = 0; i < %d; i++) v[i].data.data = (decltype(v[i].data.data))in[i]; "
+                "auto r = Qreduce<%s>(v);" % (n, E, n, L))
+    else:
+        args = ", ".join("mk<%s>(in[%d])" % (E, i) for i in range(n))
+        body = "auto r = Qreduce<%s>(%s);" % (L, args)
+    return "static void case_%d(const int64_t *in, int64_t *out) { %s out[0] = (int64_t)r.data.data; put_type(out + 1, r); }\n" % (idx, body)
+
+
+def emit_tf_args(tags):
+    return ", ".join("%s<%s>" % (k, cxx_type(v)) for k, v in tags.items())
+
+
+def emit_tf(c, idx):
+    X = "Qcomplex<%s, %s>" % (cxx_type(c["x_re"]), cxx_type(c["x_im"]))
+    Y = "Qcomplex<%s, %s>" % (cxx_type(c["y_re"]), cxx_type(c["y_im"]))
+    body = ("%s x; x.real = mk<%s>(in[0]); x.imag = mk<%s>(in[1]); %s y; y.real = mk<%s>(in[2]); y.imag = mk<%s>(in[3]); "
+            "auto r = Qmul<TFComplexMul<%s>>(x, y); out[0] = (int64_t)r.real.data.data; out[1] = (int64_t)r.imag.data.data; "
+            "put_type(out + 2, r.real); put_type(out + 7, r.imag);"
+            % (X, cxx_type(c["x_re"]), cxx_type(c["x_im"]), Y, cxx_type(c["y_re"]), cxx_type(c["y_im"]), emit_tf_args(c["tags"])))
+    return "static void case_%d(const int64_t *in, int64_t *out) { %s }\n" % (idx, body)
+
+
+def emit_gemul(c, idx):
+    M, N, K = c["M"], c["N"], c["K"]
+    A, B, P, C = (cxx_type(c[k]) for k in ("a", "b", "mul", "c"))
+    L = emit_levels(c["levels"])
+    lines = ["static void case_%d(const int64_t *in, int64_t *out) {" % idx,
+             "  const int64_t *Ain = in, *Bin = in + %d;" % (M * K),
+             "  for (int j = 0; j < %d; j++) for (int i = 0; i < %d; i++) {" % (N, M)]
+    a_idx = "k + i * %d" % K if c["trans_a"] else "i + k * %d" % M
+    if c["form"] == "vector":
+        lines.append("    static Qu<dim<%d>, %s> p;" % (K, P))
+        lines.append("    for (int k = 0; k < %d; k++) p[k] = Qmul<%s>(mk<%s>(Ain[%s]), mk<%s>(Bin[k + j * %d]));" % (K, P, A, a_idx, B, K))
+        lines.append("    %s cij = Qreduce<%s>(p);" % (C, L))
+    else:
+        args = ", ".join("Qmul<%s>(mk<%s>(Ain[%s]), mk<%s>(Bin[%d + j * %d]))" % (
+            P, A, a_idx.replace("k", str(k)), B, k, K) for k in range(K))
+        lines.append("    %s cij = Qreduce<%s>(%s);" % (C, L, args))
+    lines.append("    out[i + j * %d] = (int64_t)cij.data.data;" % M)
+    lines.append("  }\n}\n")
+    return "\n".join(lines)
+
+
+def emit_cgemul(c, idx):
+    """One output of a complex row dot product: variadic complex Qreduce over TF products."""
+    K = c["K"]
+    X = "Qcomplex<%s, %s>" % (cxx_type(c["x_re"]), cxx_type(c["x_im"]))
+    Y = "Qcomplex<%s, %s>" % (cxx_type(c["y_re"]), cxx_type(c["y_im"]))
+    L = emit_levels(c["levels"])
+    lines = ["static void case_%d(const int64_t *in, int64_t *out) {" % idx,
+             "  %s x[%d]; %s y[%d];" % (X, K, Y, K),
+             "  for (int k = 0; k < %d; k++) { x[k].real = mk<%s>(in[4*k]); x[k].imag = mk<%s>(in[4*k+1]); "
+             "y[k].real = mk<%s>(in[4*k+2]); y[k].imag = mk<%s>(in[4*k+3]); }" % (
+                 K, cxx_type(c["x_re"]), cxx_type(c["x_im"]), cxx_type(c["y_re"]), cxx_type(c["y_im"]))]
+    args = ", ".join("Qmul<TFComplexMul<%s>>(x[%d], y[%d])" % (emit_tf_args(c["tags"]), k, k) for k in range(K))
+    lines.append("  auto r = Qreduce<%s>(%s);" % (L, args))
+    lines.append("  out[0] = (int64_t)r.real.data.data; out[1] = (int64_t)r.imag.data.data; put_type(out + 2, r.real); put_type(out + 7, r.imag);")
+    lines.append("}\n")
+    return "\n".join(lines)
+
+
+EMIT = {"scalar": emit_scalar, "reduce": emit_reduce, "tf": emit_tf, "gemul": emit_gemul, "cgemul": emit_cgemul}
+
+
+def n_inputs(c):
+    k = c["kind"]
+    if k == "scalar": return 2
+    if k == "reduce": return c["len"]
+    if k == "tf": return 4
+    if k == "gemul": return c["M"] * c["K"] + c["K"] * c["N"]
+    if k == "cgemul": return 4 * c["K"]
+
+
+def n_outputs(c):
+    k = c["kind"]
+    if k == "scalar" or k == "reduce": return 6
+    if k == "tf" or k == "cgemul": return 12
+    if k == "gemul": return c["M"] * c["N"]
+
+
+def gen_inputs(rng, c):
+    k = c["kind"]
+    if k == "scalar":
+        return [[rand_raw(rng, c["a"]), rand_raw(rng, c["b"])] for _ in range(48)]
+    if k == "reduce":
+        reps = 6 if c["len"] <= 64 else 3
+        return [[rand_raw(rng, c["elem"]) for _ in range(c["len"])] for _ in range(reps)]
+    if k == "tf":
+        sets = [[rand_raw(rng, c["x_re"]), rand_raw(rng, c["x_im"]), rand_raw(rng, c["y_re"]), rand_raw(rng, c["y_im"])]
+                for _ in range(48)]
+        if c["x_re"] == T(4, 4) and c["tags"].get("abT") == T(6, 3):
+            sets.insert(0, [37, -22, -51, 19])          # SURVEY 2.5 golden
+        return sets
+    if k == "gemul":
+        if c.get("readme"):
+            m1 = [8 * v for v in range(1, 17)]          # readme.md:43-46, raw = value * 2^3, column-major
+            return [m1 + m1]
+        return [[rand_raw(rng, c["a"]) for _ in range(c["M"] * c["K"])] + [rand_raw(rng, c["b"]) for _ in range(c["K"] * c["N"])]
+                for _ in range(4)]
+    if k == "cgemul":
+        out = []
+        for _ in range(8):
+            row = []
+            for kk in range(c["K"]):
+                for t in (c["x_re"], c["x_im"], c["y_re"], c["y_im"]):
+                    v = rand_raw(rng, t)
+                    if c["half_range"]:
+                        v //= 2
+                    row.append(v)
+            out.append(row)
+        return out
+
+
+def main():
+    rng = random.Random(20261018)
+    cases = scalar_cases(rng) + reduce_cases(rng) + tf_cases(rng) + gemul_cases(rng) + cgemul_cases(rng)
+    os.makedirs(OUT_DIR, exist_ok=True)
+    os.makedirs(GOLD_DIR, exist_ok=True)
+    # split into a few TUs so that g++ can build them in parallel
+    n_tu = 8
+    tus = [[] for _ in range(n_tu)]
+    for idx, c in enumerate(cases):
+        tus[idx % n_tu].append(idx)
+    objs = []
+    procs = []
+    for t, idxs in enumerate(tus):
+        src = os.path.join(OUT_DIR, "ref_cases_%d.cpp" % t)
+        with open(src, "w") as f:
+            f.write(PRELUDE)
+            for idx in idxs:
+                f.write(EMIT[cases[idx]["kind"]](cases[idx], idx))
+            f.write('extern "C" int ref_run_%d(int id, const int64_t *in, int64_t *out) {\n  switch (id) {\n' % t)
+            for idx in idxs:
+                f.write("  case %d: case_%d(in, out); return 0;\n" % (idx, idx))
+            f.write("  default: return -1; }\n}\n")
+        obj = src[:-4] + ".o"
+        objs.append(obj)
+        procs.append(subprocess.Popen(["g++", "-std=c++23", "-O1", "-fPIC", "-w", "-I", REF_INC, "-c", src, "-o", obj]))
+    for p in procs:
+        if p.wait() != 0:
+            sys.exit("reference harness failed to compile")
+    so = os.path.join(OUT_DIR, "libqref_cases.so")
+    subprocess.check_call(["g++", "-shared", "-o", so] + objs)
+    lib = ctypes.CDLL(so)
+    fixtures = {}
+    for idx, c in enumerate(cases):
+        fn = getattr(lib, "ref_run_%d" % (idx % n_tu))
+        fn.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
+        ins = gen_inputs(rng, c)
+        outs = []
+        for row in ins:
+            assert len(row) == n_inputs(c)
+            a = (ctypes.c_int64 * len(row))(*row)
+            o = (ctypes.c_int64 * n_outputs(c))()
+            assert fn(idx, a, o) == 0
+            outs.append(list(o))
+        rec = dict(c)
+        rec["inputs"] = ins
+        rec["outputs"] = outs
+        fixtures.setdefault(c["kind"], []).append(rec)
+    for kind, recs in fixtures.items():
+        path = os.path.join(GOLD_DIR, "ref_%s.json" % kind)
+        with open(path, "w") as f:
+            json.dump({"generator": "oracle/ref_harness_gen.py", "reference": "pikapuma/QuBLAS include/QuBLAS.h (g++ 13.3 -std=c++23)",
+                       "cases": recs}, f, separators=(",", ":"))
+        print("wrote", path, len(recs), "cases")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,156 @@
+"""Pins the CPU oracle (oracle/qb_oracle.c) and the host type resolver (qublas_b200/qtypes.py)
+against (1) the reference's own 40 known-answer tests and (2) golden vectors produced by the
+unmodified reference header (oracle/ref_harness_gen.py).  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from qublas_b200 import abi
+from qublas_b200.qtypes import (QType, TREE_VARIADIC, TREE_VECTOR, add_merge, mul_merge, resolve_tf,
+                                tree_out_type)
+from tests.helpers import (cgemul_plan, form_id, gemul_plan, load_cases, np_words, qt, reduce_plan, tf_tags,
+                           tfcmul_plan)
+
+
+def type_tuple(t: QType):
+    return [t.i, t.f, int(t.s), t.q, t.o]
+
+
+def test_reference_known_answer_tests():
+    """test/RND/*.cpp, test/TRN/*.cpp of the reference: +-1.25 and the CONV ties."""
+    cases = load_cases("ref_kat.json")
+    assert len(cases) == 40
+    for c in cases:
+        got = oracle.conv128(int(c["raw"]), c["from"]["f"], qt(c["to"]))
+        assert got == c["expect_raw"], c
+        assert got / 2 ** c["to"]["f"] == c["expect_value"]
+
+
+def test_scalar_ops_match_reference():
+    cases = load_cases("ref_scalar.json")
+    n = 0
+    for c in cases:
+        a, b = qt(c["a"]), qt(c["b"])
+        if c["op"] == "conv":
+            to = qt(c["to"])
+        elif "to" in c:
+            to = qt(c["to"])
+        else:
+            to = (mul_merge if c["op"] == "mul" else add_merge)(a, b, c.get("tags"))
+        for inp, out in zip(c["inputs"], c["outputs"]):
+            assert out[1:6] == type_tuple(to), (c, out)          # resolver == reference's deduced type
+            if c["op"] == "conv":
+                got = oracle.conv(inp[0], a.f, to)
+            else:
+                got = {"mul": oracle.qmul, "add": oracle.qadd, "sub": oracle.qsub}[c["op"]](inp[0], a, inp[1], b, to)
+            assert got == out[0], (c["op"], c["a"], c["b"], to, inp, out[0], got)
+            n += 1
+    assert n > 10000
+
+
+def test_all_modes_covered():
+    cases = [c for c in load_cases("ref_scalar.json") if "to" in c]
+    seen = {(c["op"], c["to"]["q"], c["to"]["o"]) for c in cases}
+    for op in ("mul", "add", "sub", "conv"):
+        for q in range(7):
+            for o in range(4):
+                assert (op, q, o) in seen
+
+
+def test_reduce_matches_reference():
+    cases = load_cases("ref_reduce.json")
+    forms = set()
+    for c in cases:
+        elem = qt(c["elem"]); lv = [qt(t) for t in c["levels"]]
+        form = form_id(c["form"]); forms.add((c["form"], c["len"] & 1))
+        plan = reduce_plan(elem, lv, c["len"], form)
+        ot = tree_out_type(c["len"], elem, lv, form)
+        for inp, out in zip(c["inputs"], c["outputs"]):
+            assert out[1:6] == type_tuple(ot), (c["form"], c["len"], out, ot)
+            got, _ = oracle.reduce_batched(plan, np_words(inp, elem), 1)
+            assert int(got[0]) == out[0], (c["form"], c["len"], c["elem"], c["levels"], out[0], int(got[0]))
+    assert forms == {("vector", 0), ("vector", 1), ("variadic", 0), ("variadic", 1)}
+
+
+def test_reduce_partials_consistent():
+    """Level-p partials of the oracle, reduced again with the level list shifted by p, give the
+    same final value (tree separability)."""
+    rng = np.random.default_rng(5)
+    elem = QType(8, 8)
+    lv = [QType(9 + l, 8 - l, True, l % 7, 0) for l in range(8)]
+    for n in (512, 1000, 777):
+        x = rng.integers(elem.raw_min, elem.raw_max + 1, size=n).astype(np.int32)
+        plan = reduce_plan(elem, lv, n)
+        full, parts = oracle.reduce_batched(plan, x, 1, partial_level=3)
+        p2 = reduce_plan(lv[2], lv[3:], len(parts))
+        again, _ = oracle.reduce_batched(p2, parts.astype(np.int32), 1)
+        assert int(full[0]) == int(again[0])
+
+
+def test_tfcmul_matches_reference():
+    cases = load_cases("ref_tf.json")
+    for c in cases:
+        xr, xi, yr, yi = (qt(c[k]) for k in ("x_re", "x_im", "y_re", "y_im"))
+        tags = tf_tags(c["tags"])
+        r = resolve_tf(xr, xi, yr, yi, tags)
+        plan = tfcmul_plan(xr, xi, yr, yi, tags, 1)
+        wx = max(xr.word_bytes, xi.word_bytes); wy = max(yr.word_bytes, yi.word_bytes)
+        for inp, out in zip(c["inputs"], c["outputs"]):
+            assert out[2:7] == type_tuple(r["AB"]) and out[7:12] == type_tuple(r["BC"]), (c, out)
+            x = np.array(inp[0:2], dtype=oracle.np_dtype(wx)); y = np.array(inp[2:4], dtype=oracle.np_dtype(wy))
+            got = oracle.tfcmul_batched(plan, x, y, 1)
+            assert [int(got[0]), int(got[1])] == out[0:2], (c["tags"], inp, out, got)
+    # SURVEY 2.5 golden: x=(37,-22), y=(-51,19) -> re -44 (11.3), im 29 (12.2)
+    assert cases[0]["inputs"][0] == [37, -22, -51, 19] and cases[0]["outputs"][0][0:2] == [-44, 29]
+
+
+def test_gemul_matches_reference_composition():
+    cases = load_cases("ref_gemul.json")
+    for c in cases:
+        a, b, mul, cc = (qt(c[k]) for k in ("a", "b", "mul", "c"))
+        lv = [qt(t) for t in c["levels"]]
+        M, N, K = c["M"], c["N"], c["K"]
+        plan = gemul_plan(a, b, mul, cc, lv, M, N, K, trans_a=c["trans_a"], form=form_id(c["form"]))
+        for inp, out in zip(c["inputs"], c["outputs"]):
+            A = np_words(inp[:M * K], a); B = np_words(inp[M * K:], b)
+            got = oracle.gemul_batched(plan, A, B, 1)
+            assert [int(v) for v in got] == out, (c["M"], c["N"], c["K"], c["form"])
+    # readme.md:80-87 on m1 = 1..16: SURVEY 3.5 goldens
+    assert cases[0]["outputs"][0] == [192, 448, 192, 448, 448, 448, 0, 0, 192, 0, 0, 0, 448, 0, 0, 0]
+    assert cases[1]["outputs"][0] == [64, 64, 128, 448, 448, 320, 448, 0, 448, 0, 192, 256, 64, 192, 256, 384]
+
+
+def test_cgemul_matches_reference_composition():
+    cases = load_cases("ref_cgemul.json")
+    for c in cases:
+        xr, xi, yr, yi = (qt(c[k]) for k in ("x_re", "x_im", "y_re", "y_im"))
+        tags = tf_tags(c["tags"]); lv = [qt(t) for t in c["levels"]]
+        K = c["K"]
+        r = resolve_tf(xr, xi, yr, yi, tags)
+        o_re = tree_out_type(K, r["AB"], lv, TREE_VARIADIC); o_im = tree_out_type(K, r["BC"], lv, TREE_VARIADIC)
+        # 1 x K times K x 1 complex Qgemul; C type = the reduction's own result type (identity conversion)
+        plan = cgemul_plan(xr, xi, yr, yi, tags, lv, lv, o_re, o_im, 1, 1, K, trans_a=False, form=TREE_VARIADIC)
+        for inp, out in zip(c["inputs"], c["outputs"]):
+            v = np.array(inp, dtype=np.int32).reshape(K, 4)
+            A = np.ascontiguousarray(v[:, 0:2]).reshape(-1); B = np.ascontiguousarray(v[:, 2:4]).reshape(-1)
+            assert out[2:7] == type_tuple(o_re) and out[7:12] == type_tuple(o_im)
+            got = oracle.cgemul_batched(plan, A, B, 1)
+            assert [int(got[0]), int(got[1])] == out[0:2], (K, out, got)
+
+
+def test_readme_reductions():
+    """readme.md:57,61,64 (SURVEY 8(c) goldens): red1 = 0, red2 raw 7 @ 6.-3 (=56), red3 = 34."""
+    type1 = QType(6, 3, True, 5, 1); type2 = QType(6, -3)
+    v1 = QType(4, 8)                                  # Qu<dim<4>, intBits<4>> -> fracBits default 8
+    x = np.array([int(v * 256) for v in (1.0, 2.0, 3.0, 4.0)], dtype=np.int32)
+    # values 1..4 in a 4.8 type: 4.0 saturates at construction, but raw inputs here are what the readme stores
+    x = np.minimum(x, v1.raw_max)
+    r1, _ = oracle.reduce_batched(reduce_plan(v1, [type2], 4), x, 1)
+    assert int(r1[0]) * 2 ** 3 == 0
+    m1 = np.array([8 * v for v in range(1, 17)], dtype=np.int32)
+    r2, _ = oracle.reduce_batched(reduce_plan(type1, [type1, type2], 16), m1, 1)
+    assert int(r2[0]) == 7
+    # Qreduce<type1>(q1, q2, q1, q2), q1 = 1.0 (raw 8 @ 6.3), q2 = 16 (raw 2 @ 6.-3): mixed-type variadic
+    a = oracle.qadd(8, type1, 2, type2, type1)
+    r3 = oracle.qadd(a, type1, a, type1, type1)
+    assert r3 / 8 == 34
