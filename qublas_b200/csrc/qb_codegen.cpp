@@ -1,0 +1,82 @@
+#include "qb_codegen.h"
+#include <cstdio>
+#include <sstream>
+
+namespace qb {
+
+std::string emit_qstage(const QStage &q)
+{
+    char buf[256];
+    auto lit = [](long long v, char *o) {
+        if (v == INT64_MIN) snprintf(o, 40, "(-9223372036854775807LL-1)"); else snprintf(o, 40, "%lldLL", v);
+    };
+    char lo[40], hi[40]; lit(q.lo, lo); lit(q.hi, hi);
+    snprintf(buf, sizeof(buf), "qb::QStage{%d,%u,%u,%u,%u,%u,%u,%u,%s,%s}", (int)q.shift, q.qu, q.of, q.need_lo, q.need_hi,
+             q.wrap_bits, q.wrap_signed, q.identity, lo, hi);
+    return buf;
+}
+
+std::string emit_addstage(const AddStage &a)
+{
+    char buf[64];
+    snprintf(buf, sizeof(buf), "qb::AddStage{%u,%u,%u,{0,0,0,0,0},", a.shl_a, a.shl_b, a.sub);
+    return std::string(buf) + emit_qstage(a.q) + "}";
+}
+
+static std::string emit_levels(const char *fn, const TreeProg &t, unsigned n)
+{
+    std::ostringstream o;
+    o << "  static constexpr __host__ __device__ qb::AddStage " << fn << "(int l) {\n    constexpr qb::AddStage t[" << (n ? n : 1) << "] = {\n";
+    for (unsigned l = 0; l < (n ? n : 1); l++) o << "      " << emit_addstage(t.lvl[l]) << ",\n";
+    o << "    };\n    return t[l];\n  }\n";
+    return o.str();
+}
+
+static unsigned ilog2(uint64_t n) { unsigned l = 0; while (((uint64_t)1 << (l + 1)) <= n) l++; return l; }
+
+static const char *word_t(int wb) { return wb == 1 ? "int8_t" : wb == 2 ? "int16_t" : wb == 4 ? "int32_t" : "int64_t"; }
+
+std::string emit_gemul_cfg(const std::string &name, const qb_gemul_plan &p, const GemulProg &g)
+{
+    std::ostringstream o;
+    o << "struct " << name << " {\n";
+    o << "  typedef int32_t I;\n";
+    o << "  typedef " << word_t(g.a_wb) << " WA; typedef " << word_t(g.b_wb) << " WB; typedef " << word_t(g.c_wb) << " WC;\n";
+    o << "  static constexpr int M = " << p.M << ", N = " << p.N << ", K = " << p.K << ", NLEV = " << ilog2(p.K) << ";\n";
+    o << "  static constexpr __host__ __device__ qb::QStage mul() { return " << emit_qstage(g.mul) << "; }\n";
+    o << "  static constexpr __host__ __device__ qb::QStage out() { return " << emit_qstage(g.out) << "; }\n";
+    o << emit_levels("lvl", g.tree, ilog2(p.K));
+    o << "};\n";
+    return o.str();
+}
+
+std::string emit_cgemul_cfg(const std::string &name, const qb_cgemul_plan &p, const CGemulProg &g)
+{
+    std::ostringstream o;
+    o << "struct " << name << " {\n";
+    o << "  typedef int32_t I;\n";
+    o << "  typedef " << word_t(g.a_wb) << " WA; typedef " << word_t(g.b_wb) << " WB; typedef " << word_t(g.c_wb) << " WC;\n";
+    o << "  static constexpr int M = " << p.M << ", N = " << p.N << ", K = " << p.K << ", NLEV = " << ilog2(p.K) << ";\n";
+    o << "  static constexpr __host__ __device__ qb::TfProg tf() { return qb::TfProg{" << emit_addstage(g.tf.ab) << ",\n      "
+      << emit_addstage(g.tf.cd) << ",\n      " << emit_addstage(g.tf.ba) << ",\n      " << emit_qstage(g.tf.A) << ",\n      "
+      << emit_qstage(g.tf.B) << ",\n      " << emit_qstage(g.tf.C) << ",\n      " << emit_addstage(g.tf.re) << ",\n      "
+      << emit_addstage(g.tf.im) << "}; }\n";
+    o << "  static constexpr __host__ __device__ qb::QStage out_re() { return " << emit_qstage(g.out_re) << "; }\n";
+    o << "  static constexpr __host__ __device__ qb::QStage out_im() { return " << emit_qstage(g.out_im) << "; }\n";
+    o << emit_levels("lvl_re", g.tree_re, ilog2(p.K));
+    o << emit_levels("lvl_im", g.tree_im, ilog2(p.K));
+    o << "};\n";
+    return o.str();
+}
+
+std::string emit_plan_bytes(const void *plan, size_t n)
+{
+    std::ostringstream o;
+    const unsigned char *b = (const unsigned char *)plan;
+    o << "{";
+    for (size_t i = 0; i < n; i++) { o << (unsigned)b[i]; if (i + 1 < n) o << ","; if ((i & 63) == 63) o << "\n"; }
+    o << "}";
+    return o.str();
+}
+
+}  // namespace qb

@@ -1,0 +1,19 @@
+// qb_codegen.h — emits the C++ text of a compile-time kernel configuration from a compiled plan.
+//
+// This is the step that "lowers each Qu type's compile-time parameters into kernel template
+// arguments": the POD programs of qb_prog.h are printed as constexpr initialisers inside a tag
+// struct, and the kernel templates of qb_fast_*.cuh are instantiated on that tag.  Used at build
+// time (qb_gen -> _build/qb_fast_gen.inc, the AOT-specialised BASELINE configurations).
+#pragma once
+#include <string>
+#include "qb_plan.h"
+
+namespace qb {
+
+std::string emit_qstage(const QStage &q);
+std::string emit_addstage(const AddStage &a);
+std::string emit_gemul_cfg(const std::string &name, const qb_gemul_plan &p, const GemulProg &g);
+std::string emit_cgemul_cfg(const std::string &name, const qb_cgemul_plan &p, const CGemulProg &g);
+std::string emit_plan_bytes(const void *plan, size_t n);
+
+}  // namespace qb

@@ -1,0 +1,170 @@
+// qb_device.cuh — register-level quantizer primitives (integer shift / mask / clamp only).
+//
+// Every function is bit-exact with the reference's fracConvert (QuBLAS.h:2002-2204) followed by
+// intConvert (QuBLAS.h:2227-2334) inside the parity domain checked by the host plan compiler.
+// `CT` = the program is a compile-time constant (specialised kernels): need_* flags and modes fold
+// away.  With CT=false the same code reads the program from the kernel's constant bank.
+#pragma once
+#include <stdint.h>
+#include "qb_prog.h"
+
+#define QB_DEV __device__ __forceinline__
+
+namespace qb {
+
+template <typename I> struct ITraits;
+template <> struct ITraits<int32_t> { typedef uint32_t U; static constexpr int BITS = 32; };
+template <> struct ITraits<int64_t> { typedef uint64_t U; static constexpr int BITS = 64; };
+
+template <typename I> QB_DEV I imin(I a, I b) { return a < b ? a : b; }
+template <typename I> QB_DEV I imax(I a, I b) { return a > b ? a : b; }
+
+template <typename I> QB_DEV I shl_exact(I v, int s)
+{
+    typedef typename ITraits<I>::U U;
+    return (I)((U)v << s);
+}
+
+// fracConvert: s = fromFrac - toFrac.  All modes are (v + bias) >> s with
+//   TRN::TCPL bias 0 | TRN::SMGN (2^s - 1) for v < 0 | RND::POS_INF half | RND::NEG_INF half-1
+//   RND::ZERO half-1 + (v<0) | RND::INF half - (v<0) | RND::CONV half-1 + lsb(v >> s)
+template <typename I> QB_DEV I q_round(I v, int s, int mode)
+{
+    typedef typename ITraits<I>::U U;
+    constexpr int B = ITraits<I>::BITS;
+    if (s <= 0) return shl_exact<I>(v, -s);
+    const I half = (I)((U)1 << (s - 1));
+    switch (mode) {
+    case TRN_TCPL:    return v >> s;
+    case TRN_SMGN:    return (v + ((v >> (B - 1)) & (I)(((U)1 << s) - 1))) >> s;
+    case RND_POS_INF: return (v + half) >> s;
+    case RND_NEG_INF: return (v + (half - 1)) >> s;
+    case RND_ZERO:    return (v + (half - 1) + (I)((U)v >> (B - 1))) >> s;
+    case RND_INF:     return (v + half - (I)((U)v >> (B - 1))) >> s;
+    default:          return (v + (half - 1) + ((v >> s) & 1)) >> s;      // RND_CONV
+    }
+}
+
+// intConvert.  Bounds and wrap width come from the program; clamps proven dead by the host's
+// interval analysis are skipped when the program is a compile-time constant.
+template <typename I, bool CT> QB_DEV I q_ovf(I v, const QStage &s)
+{
+    typedef typename ITraits<I>::U U;
+    constexpr int B = ITraits<I>::BITS;
+    const bool nlo = CT ? (s.need_lo != 0) : true, nhi = CT ? (s.need_hi != 0) : true;
+    switch (s.of) {
+    case SAT_TCPL: case SAT_SMGN:
+        if (nhi) v = imin<I>(v, (I)s.hi);
+        if (nlo) v = imax<I>(v, (I)s.lo);
+        return v;
+    case SAT_ZERO: {
+        bool bad = (nhi && v > (I)s.hi) || (nlo && v < (I)s.lo);
+        return bad ? (I)0 : v;
+    }
+    default:  // WRP_TCPL: a wrap that interval analysis proved unnecessary is skipped in both modes
+              // (the target may be wider than the register class)
+        if (!(s.need_lo || s.need_hi)) return v;
+        if (s.wrap_signed) { const int k = B - s.wrap_bits; return (I)(shl_exact<I>(v, k)) >> k; }
+        return v & (I)s.hi;
+    }
+}
+
+template <typename I, bool CT> QB_DEV I q_apply(I v, const QStage &s)
+{
+    return q_ovf<I, CT>(q_round<I>(v, s.shift, s.qu), s);
+}
+
+template <typename I, bool CT> QB_DEV I add_apply(I a, I b, const AddStage &s)
+{
+    I x = shl_exact<I>(a, s.shl_a), y = shl_exact<I>(b, s.shl_b);
+    return q_apply<I, CT>(s.sub ? x - y : x + y, s.q);
+}
+
+// Same-type tree merge (both operands are level-l nodes): no alignment shifts.
+template <typename I, bool CT> QB_DEV I merge_apply(I a, I b, const AddStage &s)
+{
+    return q_apply<I, CT>(a + b, s.q);
+}
+
+// TFComplexMul::mul, QuBLAS.h:3522-3534.
+template <typename I, bool CT>
+QB_DEV void tf_apply(I a, I b, I c, I d, const TfProg &t, I &re, I &im)
+{
+    I ab = add_apply<I, CT>(a, b, t.ab);
+    I cd = add_apply<I, CT>(c, d, t.cd);
+    I ba = add_apply<I, CT>(b, a, t.ba);
+    I A = q_apply<I, CT>(ab * c, t.A);
+    I Bv = q_apply<I, CT>(cd * b, t.B);
+    I Cv = q_apply<I, CT>(ba * d, t.C);
+    re = add_apply<I, CT>(A, Bv, t.re);
+    im = add_apply<I, CT>(Bv, Cv, t.im);
+}
+
+// Non-power-of-two counts: run the host-built flush program over the pending stack entries
+// (vector form QuBLAS.h:4977-4980, variadic form :4942-4949).
+template <typename I, bool CT>
+QB_DEV I flush_apply(const TreeProg &P, const I *st)
+{
+    if (P.nflush == 0) return st[P.top_slot];
+    I cur = 0;
+    for (uint32_t i = 0; i < P.nflush; ++i) {
+        const FlushStep &f = P.flush[i];
+        if (f.kind == FL_LOAD) cur = st[f.slot];
+        else if (f.kind == FL_CONV) cur = q_apply<I, CT>(cur, f.a.q);
+        else cur = add_apply<I, CT>(st[f.slot], cur, f.a);
+    }
+    return cur;
+}
+
+// Streaming adjacent-pair tree with a level-indexed stack: after leaf k, bit l of (k+1) set <=> st[l]
+// holds a pending level-l node.  Reproduces the reference's pairing order exactly.
+template <typename I, bool CT, int MAXL, class LeafFn>
+QB_DEV I tree_stream(const TreeProg &P, uint64_t count, LeafFn leaf)
+{
+    I st[MAXL];
+    for (uint64_t k = 0; k < count; ++k) {
+        I v = leaf(k);
+        unsigned l = 0;
+        uint64_t m = k;
+        while (m & 1) { v = merge_apply<I, CT>(st[l], v, P.lvl[l]); ++l; m >>= 1; }
+        st[l] = v;
+    }
+    return flush_apply<I, CT>(P, st);
+}
+
+// Sign-extending loads of raw words (ArbiInt::data) of 1/2/4/8 bytes.
+template <typename I> QB_DEV I load_word(const void *p, uint64_t idx, int wb)
+{
+    switch (wb) {
+    case 1: return (I)((const int8_t *)p)[idx];
+    case 2: return (I)((const int16_t *)p)[idx];
+    case 4: return (I)((const int32_t *)p)[idx];
+    default: return (I)((const int64_t *)p)[idx];
+    }
+}
+template <typename I> QB_DEV void store_word(void *p, uint64_t idx, int wb, I v)
+{
+    switch (wb) {
+    case 1: ((int8_t *)p)[idx] = (int8_t)v; break;
+    case 2: ((int16_t *)p)[idx] = (int16_t)v; break;
+    case 4: ((int32_t *)p)[idx] = (int32_t)v; break;
+    default: ((int64_t *)p)[idx] = (int64_t)v; break;
+    }
+}
+
+// Counter-based synthetic raw words; identical to oracle/qb_oracle.c:qbo_synth_word.
+__host__ __device__ inline uint64_t mix64(uint64_t z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ inline int64_t synth_word(uint64_t key, uint64_t index, int64_t lo, uint64_t span)
+{
+    uint64_t h = mix64(key ^ index);
+    if (span == 0) return (int64_t)h;
+    return lo + (int64_t)__umul64hi(h, span);
+}
+
+}  // namespace qb

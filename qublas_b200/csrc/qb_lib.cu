@@ -1,0 +1,429 @@
+// qb_lib.cu — C ABI of libqb200.so (include/qb200.h): plan compilation, kernel selection, launches.
+//
+// No CPU fallback lives here: every compute entry point launches CUDA kernels or fails.
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/qb200.h"
+#include "qb_plan.h"
+#include "qb_kernels.cuh"
+#include "qb_fast.h"
+
+using namespace qb;
+
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const std::string &m) { g_err = m; return code; }
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fail(e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver ? QB_ENODEVICE : QB_ECUDA, \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));                       \
+    } while (0)
+
+namespace qb { void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); } }
+
+static int post_launch(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(QB_ECUDA, std::string(what) + " launch: " + cudaGetErrorString(e));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return QB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// execution context + staging of host buffers
+// ---------------------------------------------------------------------------------------------
+struct Ctx {
+    cudaStream_t stream = nullptr;
+    bool host = false;
+    uint32_t flags = 0;
+    std::vector<void *> to_free;
+    int init(const qb_exec *ex)
+    {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0) { cudaGetLastError(); return fail(QB_ENODEVICE, "no CUDA device available (there is no CPU fallback)"); }
+        if (ex) {
+            if (ex->device >= 0) CUDA_TRY(cudaSetDevice(ex->device));
+            stream = (cudaStream_t)ex->stream;
+            host = ex->mem_kind == QB_MEM_HOST;
+            flags = ex->flags;
+        }
+        return QB_OK;
+    }
+    int alloc(void **p, size_t bytes)
+    {
+        CUDA_TRY(cudaMallocAsync(p, bytes ? bytes : 16, stream));
+        to_free.push_back(*p);
+        return QB_OK;
+    }
+    // device view of a caller input
+    int in(const void *src, size_t bytes, const void **dev)
+    {
+        if (!host) { *dev = src; return QB_OK; }
+        void *d; int rc = alloc(&d, bytes); if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, stream));
+        *dev = d; return QB_OK;
+    }
+    int out(void *dst, size_t bytes, void **dev)
+    {
+        if (!host) { *dev = dst; return QB_OK; }
+        return alloc(dev, bytes);
+    }
+    int out_done(void *dst, size_t bytes, void *dev)
+    {
+        if (host) CUDA_TRY(cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, stream));
+        return QB_OK;
+    }
+    int finish()
+    {
+        for (void *p : to_free) cudaFreeAsync(p, stream);
+        to_free.clear();
+        if (host) CUDA_TRY(cudaStreamSynchronize(stream));
+        return QB_OK;
+    }
+    ~Ctx() { for (void *p : to_free) cudaFreeAsync(p, stream); }
+};
+
+static inline unsigned grid_for(uint64_t n, unsigned block, unsigned cap = 148 * 16)
+{
+    uint64_t g = (n + block - 1) / block;
+    return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+
+static void fill_info(qb_plan_info *info, const Analysis &an, qb_qdesc out_t, int out_wb, const char *kernel, int tc, int spec)
+{
+    memset(info, 0, sizeof(*info));
+    info->arith_bits = arith_bits(an);
+    info->max_inter_bits = an.max_bits;
+    info->lossless = an.lossless;
+    info->tensor_core = tc;
+    info->specialized = spec;
+    info->out_word_bytes = out_wb;
+    info->out_type = out_t;
+    snprintf(info->kernel, sizeof(info->kernel), "%s", kernel);
+}
+
+// ---------------------------------------------------------------------------------------------
+// misc entry points
+// ---------------------------------------------------------------------------------------------
+extern "C" int qb200_abi_version(void) { return QB200_ABI_VERSION; }
+extern "C" const char *qb200_last_error(void) { return g_err.c_str(); }
+extern "C" int qb200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+extern "C" uint64_t qb200_launch_count(void) { return g_launches.load(); }
+extern "C" void qb200_launch_count_reset(void) { g_launches.store(0); }
+
+extern "C" int qb200_shard_range(uint64_t total, uint32_t world, uint32_t rank, uint64_t *first, uint64_t *count)
+{
+    if (!world || rank >= world || !first || !count) return fail(QB_EINVAL, "bad shard arguments");
+    uint64_t base = total / world, rem = total % world;
+    *first = rank * base + (rank < rem ? rank : rem);
+    *count = base + (rank < rem ? 1 : 0);
+    return QB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Qreduce
+// ---------------------------------------------------------------------------------------------
+static unsigned ceil_log2(uint64_t n) { unsigned l = 0; while (((uint64_t)1 << l) < n) l++; return l; }
+
+static const char *reduce_kernel_name(const qb_reduce_plan *p)
+{
+    if (p->len == 1) return "recast";
+    if (p->tree_form == QB_TREE_VECTOR && p->len >= 64) return "k_reduce_warp";
+    return "k_reduce_thread";
+}
+
+extern "C" int qb200_reduce_plan_info(const qb_reduce_plan *plan, qb_plan_info *info)
+{
+    if (!plan || !info) return fail(QB_EINVAL, "null argument");
+    ReduceProg rp; Analysis an;
+    if (compile_reduce(*plan, &rp, an)) return fail(an.status, an.err);
+    fill_info(info, an, rp.out.t, rp.out_wb, reduce_kernel_name(plan), 0, 0);
+    return QB_OK;
+}
+
+template <typename I>
+static int launch_reduce_warp(const void *x, int in_wb, void *out, int out_wb, uint64_t n_in, uint64_t batch, uint32_t lev0,
+                              uint32_t pw, uint32_t rmax, const TreeProg &P, cudaStream_t s)
+{
+    const uint64_t per_vec = (n_in + ((uint64_t)1 << pw) - 1) >> pw;
+    const uint64_t warps = batch * per_vec;
+    const unsigned block = 256;
+    const uint64_t blocks = (warps + 7) / 8;
+    if (blocks > 0x7fffffffull) return fail(QB_EINVAL, "reduction too large for one launch");
+    const int vec_ok = ((uintptr_t)x % 16 == 0) && (batch == 1 || (n_in * in_wb) % 16 == 0);
+    switch (in_wb) {
+    case 1: k_reduce_warp<int8_t, I><<<(unsigned)blocks, block, 0, s>>>((const int8_t *)x, out, out_wb, n_in, batch, lev0, pw, rmax, 0, P); break;
+    case 2: k_reduce_warp<int16_t, I><<<(unsigned)blocks, block, 0, s>>>((const int16_t *)x, out, out_wb, n_in, batch, lev0, pw, rmax, vec_ok, P); break;
+    case 4: k_reduce_warp<int32_t, I><<<(unsigned)blocks, block, 0, s>>>((const int32_t *)x, out, out_wb, n_in, batch, lev0, pw, rmax, vec_ok, P); break;
+    default: k_reduce_warp<int64_t, I><<<(unsigned)blocks, block, 0, s>>>((const int64_t *)x, out, out_wb, n_in, batch, lev0, pw, rmax, vec_ok, P); break;
+    }
+    return post_launch("k_reduce_warp");
+}
+
+template <typename I>
+static int run_reduce(const qb_reduce_plan *plan, const ReduceProg &rp, const void *dx, void *dout, void *dpart,
+                      uint32_t partial_level, uint64_t batch, Ctx &cx)
+{
+    const uint64_t len = plan->len;
+    cudaStream_t s = cx.stream;
+    if (len == 1) {
+        k_recast<<<grid_for(batch, 256), 256, 0, s>>>(dx, rp.elem_wb, dout, rp.out_wb, batch);
+        int rc = post_launch("k_recast"); if (rc) return rc;
+        if (dpart) { k_recast<<<grid_for(batch, 256), 256, 0, s>>>(dx, rp.elem_wb, dpart, 8, batch); return post_launch("k_recast"); }
+        return QB_OK;
+    }
+    const bool warp_path = plan->tree_form == QB_TREE_VECTOR && (len >= 64 || dpart);
+    if (!warp_path) {
+        k_reduce_thread<I><<<(unsigned)((batch + 127) / 128), 128, 0, s>>>(dx, rp.elem_wb, dout, rp.out_wb, len, batch, rp.tree);
+        return post_launch("k_reduce_thread");
+    }
+    if (dpart && partial_level == 0) {
+        k_recast<<<grid_for(batch * len, 256), 256, 0, s>>>(dx, rp.elem_wb, dpart, 8, batch * len);
+        int rc = post_launch("k_recast"); if (rc) return rc;
+    }
+    const void *in = dx; int in_wb = rp.elem_wb; uint64_t n = len; uint32_t lev = 0;
+    while (true) {
+        const unsigned stop = ceil_log2(n);
+        uint32_t pw = stop < 8 ? 8 : (stop > 12 ? 12 : stop);
+        bool part_pass = dpart && partial_level > 0 && lev == 0 && partial_level < stop;
+        if (part_pass) pw = partial_level;
+        const bool final = n <= ((uint64_t)1 << pw);
+        if (final) {
+            int rc = launch_reduce_warp<I>(in, in_wb, dout, rp.out_wb, n, batch, lev, pw, stop, rp.tree, s);
+            if (rc) return rc;
+            if (dpart && partial_level > 0 && lev == 0) {            // requested level is the root itself
+                k_recast<<<grid_for(batch, 256), 256, 0, s>>>(dout, rp.out_wb, dpart, 8, batch);
+                rc = post_launch("k_recast"); if (rc) return rc;
+            }
+            return QB_OK;
+        }
+        const uint64_t n_out = (n + ((uint64_t)1 << pw) - 1) >> pw;
+        void *scratch; int rc = cx.alloc(&scratch, batch * n_out * sizeof(I)); if (rc) return rc;
+        rc = launch_reduce_warp<I>(in, in_wb, scratch, (int)sizeof(I), n, batch, lev, pw, pw, rp.tree, s);
+        if (rc) return rc;
+        if (part_pass) {
+            k_recast<<<grid_for(batch * n_out, 256), 256, 0, s>>>(scratch, (int)sizeof(I), dpart, 8, batch * n_out);
+            rc = post_launch("k_recast"); if (rc) return rc;
+        }
+        in = scratch; in_wb = (int)sizeof(I); n = n_out; lev += pw;
+    }
+}
+
+extern "C" int qb200_reduce_batched(const qb_reduce_plan *plan, const void *x, void *out, void *partials,
+                                    uint32_t partial_level, uint64_t batch, const qb_exec *exec)
+{
+    if (!plan || !x || !out) return fail(QB_EINVAL, "null argument");
+    ReduceProg rp; Analysis an;
+    if (compile_reduce(*plan, &rp, an)) return fail(an.status, an.err);
+    if (partials) {
+        if (plan->tree_form != QB_TREE_VECTOR) return fail(QB_EINVAL, "partials are defined for the vector form only");
+        if (partial_level != 0 && partial_level < 8) return fail(QB_EINVAL, "partial_level must be 0 or >= 8");
+        if (partial_level > ceil_log2(plan->len)) return fail(QB_EINVAL, "partial_level above the root");
+    }
+    if (batch == 0) return QB_OK;
+    if (arith_bits(an) == 32) sanitize32(rp.tree);
+    Ctx cx; int rc = cx.init(exec); if (rc) return rc;
+    uint64_t per = plan->len; for (uint32_t l = 0; l < partial_level; l++) per = (per + 1) / 2;
+    const void *dx; void *dout, *dpart = nullptr;
+    if ((rc = cx.in(x, batch * plan->len * rp.elem_wb, &dx))) return rc;
+    if ((rc = cx.out(out, batch * rp.out_wb, &dout))) return rc;
+    if (partials && (rc = cx.out(partials, batch * per * 8, &dpart))) return rc;
+    rc = arith_bits(an) == 32 ? run_reduce<int32_t>(plan, rp, dx, dout, dpart, partial_level, batch, cx)
+                              : run_reduce<int64_t>(plan, rp, dx, dout, dpart, partial_level, batch, cx);
+    if (rc) return rc;
+    if ((rc = cx.out_done(out, batch * rp.out_wb, dout))) return rc;
+    if (partials && (rc = cx.out_done(partials, batch * per * 8, dpart))) return rc;
+    return cx.finish();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Qgemul (real)
+// ---------------------------------------------------------------------------------------------
+static GemulShape shape_of(uint32_t M, uint32_t N, uint32_t K, int ta, int tb, int a_wb, int b_wb, int c_wb,
+                           int64_t sa, int64_t sb, int64_t sc)
+{
+    GemulShape S; S.M = M; S.N = N; S.K = K; S.trans_a = ta; S.trans_b = tb;
+    S.a_wb = a_wb; S.b_wb = b_wb; S.c_wb = c_wb; S.stride_a = sa; S.stride_b = sb; S.stride_c = sc;
+    return S;
+}
+
+static size_t span_elems(uint64_t batch, int64_t stride, uint64_t per)
+{
+    return batch == 0 ? 0 : (size_t)((batch - 1) * (uint64_t)stride + per);
+}
+
+extern "C" int qb200_gemul_plan_info(const qb_gemul_plan *plan, qb_plan_info *info)
+{
+    if (!plan || !info) return fail(QB_EINVAL, "null argument");
+    GemulProg gp; Analysis an;
+    if (compile_gemul(*plan, &gp, an)) return fail(an.status, an.err);
+    const FastGemul *f = find_fast_gemul(*plan, gp, arith_bits(an));
+    qb_qdesc ct = plan->c; ct.word_bytes = 0;
+    fill_info(info, an, ct, gp.c_wb, f ? f->name : "k_gemul_thread", gemul_tensor_core_ok(*plan, gp, an), f != nullptr);
+    return QB_OK;
+}
+
+extern "C" int qb200_gemul_batched(const qb_gemul_plan *plan, const void *A, const void *B, void *C, uint64_t batch,
+                                   const qb_exec *exec)
+{
+    if (!plan || !A || !B || !C) return fail(QB_EINVAL, "null argument");
+    GemulProg gp; Analysis an;
+    if (compile_gemul(*plan, &gp, an)) return fail(an.status, an.err);
+    if (plan->stride_a < 0 || plan->stride_b < 0 || plan->stride_c < (int64_t)((uint64_t)plan->M * plan->N))
+        return fail(QB_EINVAL, "bad batch strides");
+    if (batch == 0) return QB_OK;
+    Ctx cx; int rc = cx.init(exec); if (rc) return rc;
+    const uint64_t ea = (uint64_t)plan->M * plan->K, eb = (uint64_t)plan->K * plan->N, ec = (uint64_t)plan->M * plan->N;
+    const size_t bytes_a = span_elems(batch, plan->stride_a, ea) * gp.a_wb, bytes_b = span_elems(batch, plan->stride_b, eb) * gp.b_wb,
+                 bytes_c = span_elems(batch, plan->stride_c, ec) * gp.c_wb;
+    const void *dA, *dB; void *dC;
+    if ((rc = cx.in(A, bytes_a, &dA)) || (rc = cx.in(B, bytes_b, &dB)) || (rc = cx.out(C, bytes_c, &dC))) return rc;
+    const int bits = arith_bits(an);
+    if (bits == 32) { sanitize32_stage(gp.mul); sanitize32(gp.tree); sanitize32_stage(gp.out); }
+    const FastGemul *f = (cx.flags & QB_F_NO_SPECIALIZE) ? nullptr : find_fast_gemul(*plan, gp, bits);
+    if (f) {
+        rc = f->launch(dA, dB, dC, batch, cx.stream);
+        if (rc) return fail(QB_ECUDA, std::string(f->name) + " launch failed: " + cudaGetErrorString((cudaError_t)rc));
+    } else {
+        GemulShape S = shape_of(plan->M, plan->N, plan->K, plan->trans_a, plan->trans_b, gp.a_wb, gp.b_wb, gp.c_wb,
+                                plan->stride_a, plan->stride_b, plan->stride_c);
+        const uint64_t threads = batch * ec;
+        const uint64_t blocks = (threads + 127) / 128;
+        if (blocks > 0x7fffffffull) return fail(QB_EINVAL, "too many outputs for one launch");
+        if (bits == 32) k_gemul_thread<int32_t><<<(unsigned)blocks, 128, 0, cx.stream>>>(dA, dB, dC, batch, S, gp.mul, gp.tree, gp.out);
+        else            k_gemul_thread<int64_t><<<(unsigned)blocks, 128, 0, cx.stream>>>(dA, dB, dC, batch, S, gp.mul, gp.tree, gp.out);
+        if ((rc = post_launch("k_gemul_thread"))) return rc;
+    }
+    if ((rc = cx.out_done(C, bytes_c, dC))) return rc;
+    return cx.finish();
+}
+
+// ---------------------------------------------------------------------------------------------
+// complex Qgemul with TFComplexMul products
+// ---------------------------------------------------------------------------------------------
+extern "C" int qb200_cgemul_plan_info(const qb_cgemul_plan *plan, qb_plan_info *info)
+{
+    if (!plan || !info) return fail(QB_EINVAL, "null argument");
+    CGemulProg gp; Analysis an;
+    if (compile_cgemul(*plan, &gp, an)) return fail(an.status, an.err);
+    const FastCGemul *f = find_fast_cgemul(*plan, gp, arith_bits(an));
+    qb_qdesc ct = plan->c_re; ct.word_bytes = 0;
+    fill_info(info, an, ct, gp.c_wb, f ? f->name : "k_cgemul_thread", 0, f != nullptr);
+    return QB_OK;
+}
+
+extern "C" int qb200_cgemul_batched(const qb_cgemul_plan *plan, const void *A, const void *B, void *C, uint64_t batch,
+                                    const qb_exec *exec)
+{
+    if (!plan || !A || !B || !C) return fail(QB_EINVAL, "null argument");
+    CGemulProg gp; Analysis an;
+    if (compile_cgemul(*plan, &gp, an)) return fail(an.status, an.err);
+    if (plan->stride_a < 0 || plan->stride_b < 0 || plan->stride_c < (int64_t)((uint64_t)plan->M * plan->N))
+        return fail(QB_EINVAL, "bad batch strides");
+    if (batch == 0) return QB_OK;
+    Ctx cx; int rc = cx.init(exec); if (rc) return rc;
+    const uint64_t ea = (uint64_t)plan->M * plan->K, eb = (uint64_t)plan->K * plan->N, ec = (uint64_t)plan->M * plan->N;
+    const size_t bytes_a = 2 * span_elems(batch, plan->stride_a, ea) * gp.a_wb, bytes_b = 2 * span_elems(batch, plan->stride_b, eb) * gp.b_wb,
+                 bytes_c = 2 * span_elems(batch, plan->stride_c, ec) * gp.c_wb;
+    const void *dA, *dB; void *dC;
+    if ((rc = cx.in(A, bytes_a, &dA)) || (rc = cx.in(B, bytes_b, &dB)) || (rc = cx.out(C, bytes_c, &dC))) return rc;
+    const int bits = arith_bits(an);
+    if (bits == 32) { sanitize32(gp.tf); sanitize32(gp.tree_re); sanitize32(gp.tree_im); sanitize32_stage(gp.out_re); sanitize32_stage(gp.out_im); }
+    const FastCGemul *f = (cx.flags & QB_F_NO_SPECIALIZE) ? nullptr : find_fast_cgemul(*plan, gp, bits);
+    if (f) {
+        rc = f->launch(dA, dB, dC, batch, cx.stream);
+        if (rc) return fail(QB_ECUDA, std::string(f->name) + " launch failed: " + cudaGetErrorString((cudaError_t)rc));
+    } else {
+        GemulShape S = shape_of(plan->M, plan->N, plan->K, plan->trans_a, plan->trans_b, gp.a_wb, gp.b_wb, gp.c_wb,
+                                plan->stride_a, plan->stride_b, plan->stride_c);
+        const uint64_t threads = batch * ec;
+        const uint64_t blocks = (threads + 127) / 128;
+        if (blocks > 0x7fffffffull) return fail(QB_EINVAL, "too many outputs for one launch");
+        if (bits == 32) k_cgemul_thread<int32_t><<<(unsigned)blocks, 128, 0, cx.stream>>>(dA, dB, dC, batch, S, gp.tf, gp.tree_re, gp.tree_im, gp.out_re, gp.out_im);
+        else            k_cgemul_thread<int64_t><<<(unsigned)blocks, 128, 0, cx.stream>>>(dA, dB, dC, batch, S, gp.tf, gp.tree_re, gp.tree_im, gp.out_re, gp.out_im);
+        if ((rc = post_launch("k_cgemul_thread"))) return rc;
+    }
+    if ((rc = cx.out_done(C, bytes_c, dC))) return rc;
+    return cx.finish();
+}
+
+// ---------------------------------------------------------------------------------------------
+// element-wise TFComplexMul, conversion, synthetic fill
+// ---------------------------------------------------------------------------------------------
+extern "C" int qb200_tfcmul_batched(const qb_tfcmul_plan *plan, const void *x, const void *y, void *out, uint64_t batch,
+                                    const qb_exec *exec)
+{
+    if (!plan || !x || !y || !out) return fail(QB_EINVAL, "null argument");
+    TfProg tf; TVal re, im; Analysis an;
+    if (compile_tfcmul(*plan, &tf, &re, &im, an)) return fail(an.status, an.err);
+    const uint64_t n = plan->len * batch;
+    if (n == 0) return QB_OK;
+    Ctx cx; int rc = cx.init(exec); if (rc) return rc;
+    const int xw = std::max(word_bytes(plan->x_re), word_bytes(plan->x_im)), yw = std::max(word_bytes(plan->y_re), word_bytes(plan->y_im));
+    const int ow = std::max(natural_word(plan->tf.AB), natural_word(plan->tf.BC));
+    const void *dx, *dy; void *dout;
+    if ((rc = cx.in(x, 2 * n * xw, &dx)) || (rc = cx.in(y, 2 * n * yw, &dy)) || (rc = cx.out(out, 2 * n * ow, &dout))) return rc;
+    if (arith_bits(an) == 32) sanitize32(tf);
+    if (arith_bits(an) == 32) k_tfcmul<int32_t><<<grid_for(n, 256), 256, 0, cx.stream>>>(dx, dy, dout, n, xw, yw, ow, tf);
+    else                      k_tfcmul<int64_t><<<grid_for(n, 256), 256, 0, cx.stream>>>(dx, dy, dout, n, xw, yw, ow, tf);
+    if ((rc = post_launch("k_tfcmul"))) return rc;
+    if ((rc = cx.out_done(out, 2 * n * ow, dout))) return rc;
+    return cx.finish();
+}
+
+extern "C" int qb200_convert_batched(const qb_convert_plan *plan, const void *in, void *out, uint64_t batch, const qb_exec *exec)
+{
+    if (!plan || !in || !out) return fail(QB_EINVAL, "null argument");
+    Analysis an;
+    if (!check_type(plan->from, an, "from type") || !check_type(plan->to, an, "to type")) return fail(an.status, an.err);
+    TVal o;
+    QStage q = make_stage(plan->from.frac_bits, type_range(plan->from), width(plan->from), plan->to, &o, an);
+    if (an.status) return fail(an.status, an.err);
+    if (an.max_bits > 64) return fail(QB_EDOMAIN, "conversion intermediate wider than 64 bits");
+    const uint64_t n = plan->len * batch;
+    if (n == 0) return QB_OK;
+    Ctx cx; int rc = cx.init(exec); if (rc) return rc;
+    const int iw = word_bytes(plan->from), ow = word_bytes(plan->to);
+    const void *din; void *dout;
+    if ((rc = cx.in(in, n * iw, &din)) || (rc = cx.out(out, n * ow, &dout))) return rc;
+    if (arith_bits(an) == 32) sanitize32_stage(q);
+    if (arith_bits(an) == 32) k_convert<int32_t><<<grid_for(n, 256), 256, 0, cx.stream>>>(din, dout, n, iw, ow, q);
+    else                      k_convert<int64_t><<<grid_for(n, 256), 256, 0, cx.stream>>>(din, dout, n, iw, ow, q);
+    if ((rc = post_launch("k_convert"))) return rc;
+    if ((rc = cx.out_done(out, n * ow, dout))) return rc;
+    return cx.finish();
+}
+
+extern "C" int qb200_synth_fill(void *dst, uint64_t count, uint32_t wb, int64_t lo, int64_t hi, uint64_t seed,
+                                uint64_t stream_id, uint64_t first_index, const qb_exec *exec)
+{
+    if (!dst) return fail(QB_EINVAL, "null argument");
+    if (wb != 1 && wb != 2 && wb != 4 && wb != 8) return fail(QB_EINVAL, "word_bytes must be 1/2/4/8");
+    if (hi < lo) return fail(QB_EINVAL, "hi < lo");
+    if (count == 0) return QB_OK;
+    Ctx cx; int rc = cx.init(exec); if (rc) return rc;
+    void *d;
+    if ((rc = cx.out(dst, count * wb, &d))) return rc;
+    const uint64_t key = mix64(seed * 0xD1342543DE82EF95ull + stream_id);
+    const uint64_t span = (uint64_t)(hi - lo) + 1;
+    k_synth_fill<<<grid_for(count, 256), 256, 0, cx.stream>>>(d, count, (int)wb, lo, span, key, first_index);
+    if ((rc = post_launch("k_synth_fill"))) return rc;
+    if ((rc = cx.out_done(dst, count * wb, d))) return rc;
+    return cx.finish();
+}

@@ -1,0 +1,217 @@
+"""Host-side mirror of the reference's operator interface for the hot path, over the C ABI.
+
+Same names and argument meaning as the reference's template API:
+
+    Qreduce<Args...>(tensor)                                   QuBLAS.h:5014-5018
+    Qgemul<QgemulAddArgs<..>, QgemulMulArgs<..>, QgemulTransposedA<..>>(C, A, B)   readme.md:80-87
+    Qmul<TFComplexMul<...>>(x, y) on complex tensors           QuBLAS.h:3510-3535, 4080-4085
+
+Types are `QType`s instead of template arguments; tensors are raw two's-complement words in the
+reference's layout (column-major, int32 for width <= 32 else int64, complex = AoS pairs), held
+either in numpy arrays (host memory; the library stages them through the GPU) or in torch CUDA
+tensors (device memory; runs on torch's current stream).  Errors surface as QbError, like the
+reference's std::runtime_error.  Everything executes in libqb200.so's CUDA kernels — there is no
+CPU path here.
+"""
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import abi
+from .qtypes import (QType, TREE_VARIADIC, TREE_VECTOR, mul_merge, resolve_tf, tree_out_type)
+
+try:  # torch is plumbing (device memory, streams); host-only use works without it
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+_NP = {1: np.int8, 2: np.int16, 4: np.int32, 8: np.int64}
+
+
+def _is_torch(x):
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+def _tdtype(wb):
+    return {1: torch.int8, 2: torch.int16, 4: torch.int32, 8: torch.int64}[wb]
+
+
+def _exec_for(*tensors, flags=0) -> abi.qb_exec:
+    dev = [t for t in tensors if _is_torch(t)]
+    if dev:
+        if len(dev) != len([t for t in tensors if t is not None]):
+            raise ValueError("mix of host and device buffers")
+        d = dev[0].device
+        if d.type != "cuda" or any(t.device != d for t in dev):
+            raise ValueError("all tensors must live on one CUDA device")
+        return abi.qb_exec(abi.QB_MEM_DEVICE, d.index if d.index is not None else torch.cuda.current_device(),
+                           torch.cuda.current_stream(d).cuda_stream, flags, 0)
+    return abi.qb_exec(abi.QB_MEM_HOST, -1, None, flags, 0)
+
+
+def _ptr(x):
+    if _is_torch(x):
+        if not x.is_contiguous():
+            raise ValueError("tensors must be contiguous")
+        return C.c_void_p(x.data_ptr())
+    if not x.flags["C_CONTIGUOUS"]:
+        raise ValueError("arrays must be contiguous")
+    return x.ctypes.data_as(C.c_void_p)
+
+
+def _check_words(x, wb, what):
+    isz = x.element_size() if _is_torch(x) else x.dtype.itemsize
+    kind_ok = (not x.dtype.is_floating_point) if _is_torch(x) else (x.dtype.kind == "i")
+    if isz != wb or not kind_ok:
+        raise ValueError("%s: expected %d-byte signed integer raw words" % (what, wb))
+
+
+def _new_like(ref, n, wb):
+    if _is_torch(ref):
+        return torch.empty(n, dtype=_tdtype(wb), device=ref.device)
+    return np.empty(n, dtype=_NP[wb])
+
+
+def _wb(t: QType, word_bytes: int = 0):
+    return word_bytes or t.word_bytes
+
+
+def plan_info_reduce(plan):
+    info = abi.qb_plan_info()
+    abi.check(abi.load().qb200_reduce_plan_info(C.byref(plan), C.byref(info)))
+    return info
+
+
+def plan_info_gemul(plan):
+    info = abi.qb_plan_info()
+    abi.check(abi.load().qb200_gemul_plan_info(C.byref(plan), C.byref(info)))
+    return info
+
+
+def plan_info_cgemul(plan):
+    info = abi.qb_plan_info()
+    abi.check(abi.load().qb200_cgemul_plan_info(C.byref(plan), C.byref(info)))
+    return info
+
+
+# --------------------------------------------------------------------------------------------
+def make_reduce_plan(elem: QType, levels: Optional[Sequence[QType]], length: int, form: int = TREE_VECTOR,
+                     word_bytes: int = 0) -> abi.qb_reduce_plan:
+    p = abi.qb_reduce_plan()
+    p.elem = abi.desc(elem, word_bytes)
+    p.levels = abi.levels(levels)
+    p.len = length
+    p.tree_form = form
+    return p
+
+
+def Qreduce(x, elem: QType, levels: Optional[Sequence[QType]] = None, *, length: Optional[int] = None, batch: int = 1,
+            form: int = TREE_VECTOR, partial_level: Optional[int] = None, word_bytes: int = 0, flags: int = 0):
+    """Tree reduction of `batch` vectors of `length` elements (default: the whole buffer is one vector).
+
+    Returns (out, out_type) or (out, out_type, partials) when partial_level is given.
+    """
+    total = x.numel() if _is_torch(x) else x.size
+    if length is None:
+        length = total // batch
+    if length * batch != total:
+        raise ValueError("buffer size does not match batch * length")
+    _check_words(x, _wb(elem, word_bytes), "x")
+    plan = make_reduce_plan(elem, levels, length, form, word_bytes)
+    ot = tree_out_type(length, elem, list(levels or []), form)
+    out = _new_like(x, batch, ot.word_bytes)
+    parts = None
+    if partial_level is not None:
+        per = length
+        for _ in range(partial_level):
+            per = (per + 1) // 2
+        parts = _new_like(x, batch * per, 8)
+    ex = _exec_for(x, flags=flags)
+    abi.check(abi.load().qb200_reduce_batched(C.byref(plan), _ptr(x), _ptr(out), _ptr(parts) if parts is not None else None,
+                                              partial_level or 0, batch, C.byref(ex)))
+    return (out, ot) if parts is None else (out, ot, parts)
+
+
+# --------------------------------------------------------------------------------------------
+def make_gemul_plan(a: QType, b: QType, c: QType, M: int, N: int, K: int, *, mul=None, add: Optional[Sequence[QType]] = None,
+                    trans_a: bool = False, trans_b: bool = False, form: int = TREE_VECTOR,
+                    word_bytes=(0, 0, 0)) -> abi.qb_gemul_plan:
+    """mul: QgemulMulArgs — a full QType, a dict of partial tags (i/f/s/q/o/full) or None (MulMerger defaults)."""
+    p = abi.qb_gemul_plan()
+    mt = mul if isinstance(mul, QType) else mul_merge(a, b, mul)
+    p.a, p.b, p.c = abi.desc(a, word_bytes[0]), abi.desc(b, word_bytes[1]), abi.desc(c, word_bytes[2])
+    p.mul = abi.desc(mt)
+    p.add = abi.levels(add)
+    p.M, p.N, p.K = M, N, K
+    p.trans_a, p.trans_b, p.tree_form = int(trans_a), int(trans_b), form
+    p.stride_a, p.stride_b, p.stride_c = M * K, K * N, M * N
+    return p
+
+
+def Qgemul(Cbuf, A, B, plan: abi.qb_gemul_plan, batch: int = 1, flags: int = 0):
+    """Qgemul<AddArgs, MulArgs, TransposedA>(C, A, B): out-parameter first, like the reference."""
+    lib = abi.load()
+    ex = _exec_for(Cbuf, A, B, flags=flags)
+    abi.check(lib.qb200_gemul_batched(C.byref(plan), _ptr(A), _ptr(B), _ptr(Cbuf), batch, C.byref(ex)))
+    return Cbuf
+
+
+def make_cgemul_plan(a_re: QType, a_im: QType, b_re: QType, b_im: QType, c_re: QType, c_im: QType, M: int, N: int, K: int, *,
+                     tf_tags=None, add_re: Optional[Sequence[QType]] = None, add_im: Optional[Sequence[QType]] = None,
+                     trans_a=False, trans_b=False, form: int = TREE_VARIADIC) -> abi.qb_cgemul_plan:
+    p = abi.qb_cgemul_plan()
+    p.a_re, p.a_im, p.b_re, p.b_im = (abi.desc(t) for t in (a_re, a_im, b_re, b_im))
+    p.tf = abi.tfc_types(resolve_tf(a_re, a_im, b_re, b_im, tf_tags))
+    p.add_re, p.add_im = abi.levels(add_re), abi.levels(add_im if add_im is not None else add_re)
+    p.c_re, p.c_im = abi.desc(c_re), abi.desc(c_im)
+    p.M, p.N, p.K = M, N, K
+    p.trans_a, p.trans_b, p.tree_form = int(trans_a), int(trans_b), form
+    p.stride_a, p.stride_b, p.stride_c = M * K, K * N, M * N
+    return p
+
+
+def Qcgemul(Cbuf, A, B, plan: abi.qb_cgemul_plan, batch: int = 1, flags: int = 0):
+    lib = abi.load()
+    ex = _exec_for(Cbuf, A, B, flags=flags)
+    abi.check(lib.qb200_cgemul_batched(C.byref(plan), _ptr(A), _ptr(B), _ptr(Cbuf), batch, C.byref(ex)))
+    return Cbuf
+
+
+def tfcmul(x, y, x_re: QType, x_im: QType, y_re: QType, y_im: QType, tf_tags=None, batch: int = 1):
+    """Element-wise Qmul<TFComplexMul<tags...>>(x, y) on complex vectors (AoS pairs)."""
+    n = (x.numel() if _is_torch(x) else x.size) // 2
+    p = abi.qb_tfcmul_plan()
+    p.x_re, p.x_im, p.y_re, p.y_im = (abi.desc(t) for t in (x_re, x_im, y_re, y_im))
+    r = resolve_tf(x_re, x_im, y_re, y_im, tf_tags)
+    p.tf = abi.tfc_types(r)
+    p.len = n // batch
+    out = _new_like(x, 2 * n, max(r["AB"].word_bytes, r["BC"].word_bytes))
+    ex = _exec_for(x, y)
+    abi.check(abi.load().qb200_tfcmul_batched(C.byref(p), _ptr(x), _ptr(y), _ptr(out), batch, C.byref(ex)))
+    return out, (r["AB"], r["BC"])
+
+
+def convert(x, src: QType, dst: QType):
+    n = x.numel() if _is_torch(x) else x.size
+    p = abi.qb_convert_plan()
+    p.from_, p.to, p.len = abi.desc(src), abi.desc(dst), n
+    out = _new_like(x, n, dst.word_bytes)
+    ex = _exec_for(x)
+    abi.check(abi.load().qb200_convert_batched(C.byref(p), _ptr(x), _ptr(out), 1, C.byref(ex)))
+    return out
+
+
+def synth_fill(out, lo: int, hi: int, seed: int, stream_id: int, first_index: int = 0):
+    """Counter-based synthetic raw words, uniform over [lo, hi]."""
+    n = out.numel() if _is_torch(out) else out.size
+    wb = out.element_size() if _is_torch(out) else out.dtype.itemsize
+    ex = _exec_for(out)
+    abi.check(abi.load().qb200_synth_fill(_ptr(out), n, wb, lo, hi, seed, stream_id, first_index, C.byref(ex)))
+    return out
+
+
+def shard_range(total: int, world: int, rank: int):
+    f, c = C.c_uint64(), C.c_uint64()
+    abi.check(abi.load().qb200_shard_range(total, world, rank, C.byref(f), C.byref(c)))
+    return f.value, c.value

@@ -1,0 +1,114 @@
+"""CPU-side checks of the C ABI: the library loads, exports every symbol include/qb200.h declares,
+validates plans without a device, fences the parity domain, and refuses to compute without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from qublas_b200 import abi, ops
+from qublas_b200.qtypes import QType, RND_CONV, RND_POS_INF, SAT_TCPL, TREE_VARIADIC, TREE_VECTOR, WRP_TCPL
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "qb200.h")).read()
+    declared = set(re.findall(r"\b(qb200_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(abi.ABI_SYMBOLS), declared ^ set(abi.ABI_SYMBOLS)
+    lib = abi.load()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.qb200_abi_version() == 1
+
+
+def test_struct_layout_matches_header(tmp_path):
+    """ctypes mirrors == the C compiler's view of include/qb200.h."""
+    import subprocess
+    names = ["qb_qdesc", "qb_levels", "qb_reduce_plan", "qb_gemul_plan", "qb_tfc_types", "qb_cgemul_plan",
+             "qb_tfcmul_plan", "qb_convert_plan", "qb_plan_info", "qb_exec"]
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "qb200.h"\nint main(void){' +
+                   "".join('printf("%%zu\\n", sizeof(%s));' % n for n in names) + "return 0;}\n")
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    sizes = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    for n, sz in zip(names, sizes):
+        assert C.sizeof(getattr(abi, n)) == sz, n
+
+
+def test_plan_info_reduce_c2():
+    lv = [QType(9 + l, 8 - l, True, RND_POS_INF, SAT_TCPL) for l in range(8)]
+    info = ops.plan_info_reduce(ops.make_reduce_plan(QType(8, 8), lv, 1 << 24))
+    assert info.arith_bits == 32 and info.kernel == b"k_reduce_warp"
+    assert abi.qtype_of(info.out_type) == lv[-1] and info.out_word_bytes == 4
+    assert not info.lossless
+
+
+def test_plan_info_gemul_c3_interval_analysis():
+    a = QType(7, 8)
+    mul = QType(14, 8, True, RND_CONV, SAT_TCPL)
+    lv = [QType(15 + l, 8 - l, True, RND_POS_INF, SAT_TCPL) for l in range(6)]
+    c = QType(17, 4, True, RND_POS_INF, SAT_TCPL)
+    info = ops.plan_info_gemul(ops.make_gemul_plan(a, a, c, 64, 64, 64, mul=mul, add=lv))
+    assert info.arith_bits == 32 and info.max_inter_bits == 32 and not info.lossless and not info.tensor_core
+
+
+def test_plan_info_gemul_c5_lossless_predicate():
+    a = QType(7, 0)
+    acc = QType(30, 0)
+    p = ops.make_gemul_plan(a, a, acc, 256, 256, 256, mul=QType(15, 0), add=[acc])
+    info = ops.plan_info_gemul(p)
+    assert info.lossless and info.tensor_core and info.arith_bits == 32
+    # FullPrec product type 14.0 loses min*min -> a clamp is live -> not lossless
+    p2 = ops.make_gemul_plan(a, a, acc, 256, 256, 256, mul={"full": True}, add=[acc])
+    info2 = ops.plan_info_gemul(p2)
+    assert not info2.lossless and not info2.tensor_core
+
+
+@pytest.mark.parametrize("shift,mode,ok", [(32, RND_POS_INF, False), (31, RND_CONV, False), (31, RND_POS_INF, True),
+                                           (32, 5, True), (33, RND_CONV, True)])
+def test_parity_domain_fence_shifts(shift, mode, ok):
+    """SURVEY.md 2.3 defects 1-2: RND shifts of 32/64 and CONV shifts of 31/63 are outside the domain."""
+    elem = QType(10, 40)
+    lv = [QType(12, 40 - shift, True, mode, SAT_TCPL)]
+    plan = ops.make_reduce_plan(elem, lv, 2)
+    info = abi.qb_plan_info()
+    rc = abi.load().qb200_reduce_plan_info(C.byref(plan), C.byref(info))
+    assert (rc == 0) == ok, abi.load().qb200_last_error()
+    if not ok:
+        assert rc == abi.QB_EDOMAIN
+
+
+def test_parity_domain_fence_width_and_wrap():
+    lib = abi.load()
+    info = abi.qb_plan_info()
+    # product of two 40-bit types is an 80-bit ArbiInt in the reference -> fenced
+    p = ops.make_gemul_plan(QType(19, 20), QType(19, 20), QType(20, 20), 2, 2, 2, mul=QType(20, 20))
+    assert lib.qb200_gemul_plan_info(C.byref(p), C.byref(info)) == abi.QB_EDOMAIN
+    # unsigned WRP::TCPL with int+frac == 32 (reference mask is a no-op)
+    r = ops.make_reduce_plan(QType(20, 14), [QType(20, 12, False, 5, WRP_TCPL)], 4)
+    assert lib.qb200_reduce_plan_info(C.byref(r), C.byref(info)) == abi.QB_EDOMAIN
+    # malformed
+    bad = ops.make_reduce_plan(QType(8, 8), None, 0)
+    assert lib.qb200_reduce_plan_info(C.byref(bad), C.byref(info)) == abi.QB_EINVAL
+
+
+def test_shard_range_partitions_exactly():
+    for total in (0, 1, 7, 1000000, 8192):
+        for world in (1, 2, 3, 8):
+            got = [ops.shard_range(total, world, r) for r in range(world)]
+            assert got[0][0] == 0 and sum(c for _, c in got) == total
+            for (f0, c0), (f1, _) in zip(got, got[1:]):
+                assert f0 + c0 == f1
+
+
+def test_compute_fails_loudly_without_gpu():
+    lib = abi.load()
+    if lib.qb200_device_count() > 0:
+        pytest.skip("a GPU is present")
+    x = np.arange(8, dtype=np.int32)
+    with pytest.raises(abi.QbError) as e:
+        ops.Qreduce(x, QType(8, 8), [QType(9, 8)])
+    assert e.value.code == abi.QB_ENODEVICE and "no CPU fallback" in str(e.value)

@@ -1,0 +1,307 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libqb200.so) against the CPU oracle and the
+reference-generated golden fixtures.  Integer work => bit-exact, no tolerance anywhere."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from qublas_b200 import abi, ops
+from qublas_b200.qtypes import (QType, RND_CONV, RND_POS_INF, SAT_TCPL, TREE_VARIADIC, TREE_VECTOR, mul_merge,
+                                resolve_tf, tree_out_type)
+from tests.helpers import (cgemul_plan, form_id, gemul_plan, load_cases, np_words, qt, reduce_plan, tf_tags,
+                           tfcmul_plan)
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if abi.load().qb200_device_count() < 1:
+        pytest.fail("no CUDA device: the GPU tests must run on the B200 box")
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def rand_words(rng, t: QType, n):
+    return rng.integers(t.raw_min, t.raw_max + 1, size=n, dtype=np.int64).astype(oracle.np_dtype(t.word_bytes))
+
+
+# ------------------------------------------------------------------------------------------------
+# golden fixtures produced by the unmodified reference header
+# ------------------------------------------------------------------------------------------------
+def test_golden_converting_ctor_and_qmul():
+    """Scalar goldens on the GPU: conv cases through qb200_convert, mul cases through a 1x1x1 Qgemul."""
+    n = 0
+    for c in load_cases("ref_scalar.json"):
+        a, b = qt(c["a"]), qt(c["b"])
+        if c["op"] == "conv":
+            to = qt(c["to"])
+            x = np_words([i[0] for i in c["inputs"]], a)
+            got = ops.convert(dev(x), a, to).cpu().numpy()
+            assert [int(v) for v in got] == [o[0] for o in c["outputs"]], c
+            n += len(x)
+        elif c["op"] == "mul":
+            to = qt(c["to"]) if "to" in c else mul_merge(a, b, c.get("tags"))
+            plan = ops.make_gemul_plan(a, b, to, 1, 1, 1, mul=to)
+            A = np_words([i[0] for i in c["inputs"]], a); B = np_words([i[1] for i in c["inputs"]], b)
+            Cd = torch.empty(len(A), dtype=torch.int32 if to.word_bytes == 4 else torch.int64, device="cuda")
+            ops.Qgemul(Cd, dev(A), dev(B), plan, batch=len(A))
+            assert [int(v) for v in Cd.cpu().numpy()] == [o[0] for o in c["outputs"]], c
+            n += len(A)
+    assert n > 5000
+
+
+@pytest.mark.parametrize("mem", ["device", "host"])
+def test_golden_reduce(mem):
+    for c in load_cases("ref_reduce.json"):
+        elem = qt(c["elem"]); lv = [qt(t) for t in c["levels"]]
+        x = np_words(sum(c["inputs"], []), elem)
+        batch = len(c["inputs"])
+        xin = dev(x) if mem == "device" else x
+        out, ot = ops.Qreduce(xin, elem, lv, length=c["len"], batch=batch, form=form_id(c["form"]))
+        got = out.cpu().numpy() if mem == "device" else out
+        assert [int(v) for v in got] == [o[0] for o in c["outputs"]], (c["form"], c["len"], c["elem"], c["levels"])
+        assert [ot.i, ot.f, int(ot.s), ot.q, ot.o] == c["outputs"][0][1:6]
+
+
+def test_golden_tfcmul():
+    for c in load_cases("ref_tf.json"):
+        xr, xi, yr, yi = (qt(c[k]) for k in ("x_re", "x_im", "y_re", "y_im"))
+        wx = max(xr.word_bytes, xi.word_bytes); wy = max(yr.word_bytes, yi.word_bytes)
+        x = np.array([i[0:2] for i in c["inputs"]], dtype=oracle.np_dtype(wx)).reshape(-1)
+        y = np.array([i[2:4] for i in c["inputs"]], dtype=oracle.np_dtype(wy)).reshape(-1)
+        out, _ = ops.tfcmul(dev(x), dev(y), xr, xi, yr, yi, tf_tags(c["tags"]))
+        got = out.cpu().numpy().reshape(-1, 2)
+        assert [[int(a), int(b)] for a, b in got] == [o[0:2] for o in c["outputs"]], c["tags"]
+
+
+@pytest.mark.parametrize("mem", ["device", "host"])
+def test_golden_gemul_readme_and_random(mem):
+    for c in load_cases("ref_gemul.json"):
+        a, b, mul, cc = (qt(c[k]) for k in ("a", "b", "mul", "c"))
+        lv = [qt(t) for t in c["levels"]]
+        M, N, K = c["M"], c["N"], c["K"]
+        plan = gemul_plan(a, b, mul, cc, lv, M, N, K, trans_a=c["trans_a"], form=form_id(c["form"]))
+        batch = len(c["inputs"])
+        A = np_words(sum([i[:M * K] for i in c["inputs"]], []), a)
+        B = np_words(sum([i[M * K:] for i in c["inputs"]], []), b)
+        if mem == "device":
+            Cd = torch.empty(batch * M * N, dtype=torch.int32 if cc.word_bytes == 4 else torch.int64, device="cuda")
+            ops.Qgemul(Cd, dev(A), dev(B), plan, batch=batch)
+            got = Cd.cpu().numpy()
+        else:
+            got = np.empty(batch * M * N, dtype=oracle.np_dtype(cc.word_bytes))
+            ops.Qgemul(got, A, B, plan, batch=batch)
+        assert [int(v) for v in got] == sum(c["outputs"], []), (M, N, K, c["form"])
+
+
+def test_golden_cgemul():
+    for c in load_cases("ref_cgemul.json"):
+        xr, xi, yr, yi = (qt(c[k]) for k in ("x_re", "x_im", "y_re", "y_im"))
+        tags = tf_tags(c["tags"]); lv = [qt(t) for t in c["levels"]]
+        K = c["K"]
+        r = resolve_tf(xr, xi, yr, yi, tags)
+        o_re = tree_out_type(K, r["AB"], lv, TREE_VARIADIC); o_im = tree_out_type(K, r["BC"], lv, TREE_VARIADIC)
+        plan = cgemul_plan(xr, xi, yr, yi, tags, lv, lv, o_re, o_im, 1, 1, K, form=TREE_VARIADIC)
+        batch = len(c["inputs"])
+        v = np.array(c["inputs"], dtype=np.int32).reshape(batch, K, 4)
+        A = np.ascontiguousarray(v[:, :, 0:2]).reshape(-1); B = np.ascontiguousarray(v[:, :, 2:4]).reshape(-1)
+        Cd = torch.empty(batch * 2, dtype=torch.int32, device="cuda")
+        ops.Qcgemul(Cd, dev(A), dev(B), plan, batch=batch)
+        got = Cd.cpu().numpy().reshape(-1, 2)
+        assert [[int(a), int(b)] for a, b in got] == [o[0:2] for o in c["outputs"]]
+
+
+# ------------------------------------------------------------------------------------------------
+# randomized plans against the oracle
+# ------------------------------------------------------------------------------------------------
+def _rand_levels(rng, elem: QType, n, wide=False):
+    lv = []
+    i, f = elem.i, elem.f
+    for _ in range(n):
+        i += int(rng.integers(0, 3)); f -= int(rng.integers(0, 3))
+        if i + f < 1:
+            f = 1 - i
+        lv.append(QType(i, f, bool(rng.random() < 0.9), int(rng.integers(0, 7)), int(rng.integers(0, 4))))
+    return lv
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_reduce_vs_oracle(seed):
+    rng = np.random.default_rng(1000 + seed)
+    for n in [2, 63, 64, 65, 255, 256, 257, 1000, 4095, 4096, 4097, 5000, 65536 + 1, 70001, 1 << 17]:
+        wide = rng.random() < 0.3
+        elem = QType(int(rng.integers(3, 10)) + (20 if wide else 0), int(rng.integers(2, 9)), True, int(rng.integers(0, 7)),
+                     int(rng.integers(0, 4)))
+        lv = _rand_levels(rng, elem, int(rng.choice([0, 1, 3, 8, 20])))
+        batch = int(rng.choice([1, 3])) if n > 4096 else int(rng.choice([1, 5, 17]))
+        x = rand_words(rng, elem, n * batch)
+        plan = reduce_plan(elem, lv, n)
+        want, _ = oracle.reduce_batched(plan, x, batch)
+        out, _ = ops.Qreduce(dev(x), elem, lv, length=n, batch=batch)
+        assert np.array_equal(out.cpu().numpy(), want), (n, elem, lv)
+    # variadic form goes through the per-vector streaming kernel
+    for n in [3, 5, 6, 7, 11, 100, 1001]:
+        elem = QType(6, 6, True, int(rng.integers(0, 7)), int(rng.integers(0, 4)))
+        lv = _rand_levels(rng, elem, 3)
+        x = rand_words(rng, elem, n * 9)
+        plan = reduce_plan(elem, lv, n, TREE_VARIADIC)
+        want, _ = oracle.reduce_batched(plan, x, 9)
+        out, _ = ops.Qreduce(dev(x), elem, lv, length=n, batch=9, form=TREE_VARIADIC)
+        assert np.array_equal(out.cpu().numpy(), want), (n, elem, lv)
+
+
+@pytest.mark.parametrize("n,level", [(1 << 16, 9), (70001, 8), (5000, 12), (300, 8), (256, 8), (1 << 14, 0)])
+def test_reduce_partials_depthwise(n, level):
+    """low-level errors are masked in the final scalar, so intermediate levels are compared too."""
+    rng = np.random.default_rng(n)
+    elem = QType(8, 8)
+    lv = [QType(9 + l, 8 - l, True, l % 7, SAT_TCPL) for l in range(8)]
+    x = rand_words(rng, elem, n * 2)
+    plan = reduce_plan(elem, lv, n)
+    want, wparts = oracle.reduce_batched(plan, x, 2, partial_level=level)
+    out, _, parts = ops.Qreduce(dev(x), elem, lv, length=n, batch=2, partial_level=level)
+    assert np.array_equal(parts.cpu().numpy(), wparts)
+    assert np.array_equal(out.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_gemul_vs_oracle(seed):
+    rng = np.random.default_rng(2000 + seed)
+    for (M, N, K) in [(1, 1, 1), (3, 5, 7), (8, 8, 8), (16, 4, 33), (5, 5, 64), (64, 64, 64), (33, 17, 100)]:
+        big = rng.random() < 0.35          # forces the 64-bit arithmetic class
+        a = QType(int(rng.integers(2, 8)) + (14 if big else 0), int(rng.integers(2, 9)), True, 5, 0)
+        b = QType(int(rng.integers(2, 8)), int(rng.integers(2, 9)) + (8 if big else 0), True, 5, 0)
+        mul = QType(a.i + b.i - int(rng.integers(0, 3)), max(a.f, b.f) - int(rng.integers(0, 3)), True,
+                    int(rng.integers(0, 7)), int(rng.integers(0, 4)))
+        lv = _rand_levels(rng, mul, int(rng.choice([0, 1, 2, 6])))
+        last = lv[-1] if lv else mul
+        cc = QType(last.i + int(rng.integers(-2, 3)), max(last.f - int(rng.integers(0, 4)), 1 - last.i + 2), True,
+                   int(rng.integers(0, 7)), int(rng.integers(0, 4)))
+        form = int(rng.integers(0, 2))
+        ta, tb = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        plan = gemul_plan(a, b, mul, cc, lv, M, N, K, trans_a=ta, trans_b=tb, form=form)
+        batch = 3
+        A = rand_words(rng, a, batch * M * K); B = rand_words(rng, b, batch * K * N)
+        want = oracle.gemul_batched(plan, A, B, batch)
+        Cd = torch.empty(batch * M * N, dtype=torch.int32 if cc.word_bytes == 4 else torch.int64, device="cuda")
+        try:
+            ops.Qgemul(Cd, dev(A), dev(B), plan, batch=batch)
+        except abi.QbError as e:
+            assert e.code == abi.QB_EDOMAIN
+            continue
+        assert np.array_equal(Cd.cpu().numpy(), want), (M, N, K, a, b, mul, lv, cc, form, ta, tb)
+
+
+def _c4_plan(M, N, K):
+    t = QType(3, 12); P = QType(6, 12); S = QType(7, 12)
+    tags = {"abT": QType(4, 12), "cdT": QType(4, 11), "abcT": P, "cdbT": P, "badT": P, "ABT": S, "BCT": S}
+    lv = [QType(8 + l, 12 - l, True, RND_CONV, SAT_TCPL) for l in range(8)]
+    out_t = tree_out_type(K, S, lv, TREE_VARIADIC)
+    return t, cgemul_plan(t, t, t, t, tags, lv, lv, out_t, out_t, M, N, K, form=TREE_VARIADIC)
+
+
+@pytest.mark.parametrize("half_range", [True, False])
+def test_cgemul_c4_matvec_vs_oracle(half_range):
+    """BASELINE config 4: 256x256 complex mat-vec, TFComplexMul 3-mult/5-add, 8-level CONV tree.
+    Full-range inputs saturate the un-taggable b-a node in ~1/4 of the products."""
+    rng = np.random.default_rng(7)
+    t, plan = _c4_plan(256, 1, 256)
+    batch = 4
+    lo, hi = (-(1 << 14), (1 << 14) - 1) if half_range else (t.raw_min, t.raw_max)
+    H = rng.integers(lo, hi + 1, size=batch * 256 * 256 * 2).astype(np.int32)
+    x = rng.integers(lo, hi + 1, size=batch * 256 * 2).astype(np.int32)
+    want = oracle.cgemul_batched(plan, H, x, batch)
+    y = torch.empty(batch * 256 * 2, dtype=torch.int32, device="cuda")
+    ops.Qcgemul(y, dev(H), dev(x), plan, batch=batch)
+    assert np.array_equal(y.cpu().numpy(), want)
+
+
+def test_random_cgemul_vs_oracle():
+    rng = np.random.default_rng(11)
+    for (M, N, K, form) in [(2, 3, 5, TREE_VARIADIC), (4, 4, 16, TREE_VECTOR), (3, 1, 7, TREE_VECTOR), (5, 2, 12, TREE_VARIADIC)]:
+        def rt():
+            return QType(int(rng.integers(2, 7)), int(rng.integers(1, 8)), True, int(rng.integers(0, 7)), int(rng.integers(0, 4)))
+        ar, ai, br, bi = rt(), rt(), rt(), rt()
+        tags = {k: QType(int(rng.integers(5, 12)), int(rng.integers(2, 10)), True, int(rng.integers(0, 7)), int(rng.integers(0, 4)))
+                for k in ("abT", "cdT", "abcT", "cdbT", "badT", "ABT", "BCT") if rng.random() < 0.8}
+        r = resolve_tf(ar, ai, br, bi, tags)
+        lre = _rand_levels(rng, r["AB"], 3); lim = _rand_levels(rng, r["BC"], 2)
+        cre, cim = QType(10, 4, True, 4, 0), QType(9, 3, True, 2, 2)
+        plan = cgemul_plan(ar, ai, br, bi, tags, lre, lim, cre, cim, M, N, K, form=form)
+        batch = 3
+        wa = max(ar.word_bytes, ai.word_bytes); wb = max(br.word_bytes, bi.word_bytes)
+        A = np.stack([rand_words(rng, ar, batch * M * K), rand_words(rng, ai, batch * M * K)], axis=1).astype(oracle.np_dtype(wa)).reshape(-1)
+        B = np.stack([rand_words(rng, br, batch * K * N), rand_words(rng, bi, batch * K * N)], axis=1).astype(oracle.np_dtype(wb)).reshape(-1)
+        want = oracle.cgemul_batched(plan, A, B, batch)
+        Cd = torch.empty(batch * M * N * 2, dtype=torch.int32, device="cuda")
+        ops.Qcgemul(Cd, dev(A), dev(B), plan, batch=batch)
+        assert np.array_equal(Cd.cpu().numpy(), want), (M, N, K, form)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE configs at (or near) full size
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", range(7))
+def test_c2_reduce_2p24_all_modes(mode):
+    """Config 2: Qreduce of 2^24 x Qu<8,8>, C2a (8-entry list, last reused) and C2b (24-entry list)."""
+    n = 1 << 24
+    elem = QType(8, 8)
+    x = torch.empty(n, dtype=torch.int32, device="cuda")
+    ops.synth_fill(x, elem.raw_min, elem.raw_max, seed=1, stream_id=mode)
+    xh = x.cpu().numpy()
+    assert np.array_equal(xh[:4096], oracle.synth_fill(4096, 4, elem.raw_min, elem.raw_max, 1, mode))
+    c2a = [QType(9 + l, 8 - l, True, mode, SAT_TCPL) for l in range(8)]
+    c2b = c2a + [QType(17 + (l - 7 + 1) // 2, 0, True, mode, SAT_TCPL) for l in range(8, 24)]
+    for lv, level in ((c2a, 9), (c2b, 17)):
+        plan = reduce_plan(elem, lv, n)
+        want, wparts = oracle.reduce_batched(plan, xh, 1, partial_level=level)
+        out, ot, parts = ops.Qreduce(x, elem, lv, partial_level=level)
+        assert np.array_equal(parts.cpu().numpy(), wparts)
+        assert int(out.cpu()[0]) == int(want[0])
+        assert ot == lv[-1]
+
+
+def test_c3_batched_64cubed_vs_oracle_and_shard_edges():
+    """Config 3 at reduced batch against the oracle (first/last instances of a shard), full types."""
+    a = QType(7, 8)
+    mul = QType(14, 8, True, RND_CONV, SAT_TCPL)
+    lv = [QType(15 + l, 8 - l, True, RND_POS_INF, SAT_TCPL) for l in range(6)]
+    c = QType(17, 4, True, RND_POS_INF, SAT_TCPL)
+    plan = ops.make_gemul_plan(a, a, c, 64, 64, 64, mul=mul, add=lv)
+    batch = 96
+    A = torch.empty(batch * 4096, dtype=torch.int32, device="cuda"); B = torch.empty_like(A)
+    ops.synth_fill(A, a.raw_min, a.raw_max, 1, 0); ops.synth_fill(B, a.raw_min, a.raw_max, 1, 1)
+    Cd = torch.empty(batch * 4096, dtype=torch.int32, device="cuda")
+    ops.Qgemul(Cd, A, B, plan, batch=batch)
+    want = oracle.gemul_batched(plan, A.cpu().numpy(), B.cpu().numpy(), batch)
+    assert np.array_equal(Cd.cpu().numpy(), want)
+    # the runtime-descriptor kernel and the specialised kernel must agree bit for bit
+    C2 = torch.empty_like(Cd)
+    ops.Qgemul(C2, A, B, plan, batch=batch, flags=abi.QB_F_NO_SPECIALIZE)
+    assert torch.equal(Cd, C2)
+    # saturation corner: min x min products (the only product the 14.8 MulArgs type cannot hold)
+    A.fill_(a.raw_min); B.fill_(a.raw_min)
+    ops.Qgemul(Cd, A, B, plan, batch=2)
+    want = oracle.gemul_batched(plan, A[:8192].cpu().numpy(), B[:8192].cpu().numpy(), 2)
+    assert np.array_equal(Cd[:8192].cpu().numpy(), want)
+
+
+def test_synth_fill_matches_oracle_all_word_sizes():
+    for wb, lo, hi in [(1, -127, 127), (2, -(1 << 15), (1 << 15) - 1), (4, -65536, 65535), (8, -(1 << 40), (1 << 40))]:
+        t = torch.empty(10007, dtype={1: torch.int8, 2: torch.int16, 4: torch.int32, 8: torch.int64}[wb], device="cuda")
+        ops.synth_fill(t, lo, hi, seed=3, stream_id=9, first_index=12345)
+        assert np.array_equal(t.cpu().numpy(), oracle.synth_fill(10007, wb, lo, hi, 3, 9, 12345))
+        assert int(t.min()) >= lo and int(t.max()) <= hi
+
+
+def test_launch_counter_counts_kernels():
+    lib = abi.load()
+    lib.qb200_launch_count_reset()
+    x = torch.zeros(1 << 16, dtype=torch.int32, device="cuda")
+    ops.Qreduce(x, QType(8, 8), [QType(9, 8)])
+    assert lib.qb200_launch_count() == 2          # 2^16 -> 16 partials -> root
