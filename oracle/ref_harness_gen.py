@@ -12,7 +12,7 @@ What it does
        tf       Qmul<TFComplexMul<...>>(x, y)               include/QuBLAS.h:3510-3535
        gemul    the readme.md:80-87 composition Qmul -> Qreduce -> converting assignment
        cgemul   TFComplexMul products -> variadic complex Qreduce (QuBLAS.h:3549-3568)
-  2. emits oracle/_ref/ref_cases.cpp that instantiates every case with the reference's own
+  2. emits oracle/_ref/ref_cases_*.cpp that instantiates every case with the reference's own
      templates, compiles it with g++ -std=c++23 against /root/reference/include (sources are
      compiled where they lie; nothing is copied), loads the .so and runs every case;
   3. writes inputs, the reference's outputs AND the reference's deduced result types to
@@ -194,6 +194,10 @@ def tf_cases(rng):
     t = T(3, 12); P = T(6, 12); S = T(7, 12)
     cases.append({"kind": "tf", "x_re": t, "x_im": t, "y_re": t, "y_im": t,
                   "tags": {"abT": T(4, 12), "cdT": T(4, 11), "abcT": P, "cdbT": P, "badT": P, "ABT": S, "BCT": S}})
+    # readme.md:92-109: Qcomplex<type1,type2> operands with the readme's TFComplexMul tags
+    type1 = T(6, 3, True, 5, 1); type2 = T(6, -3)
+    cases.append({"kind": "tf", "x_re": type1, "x_im": type2, "y_re": type1, "y_im": type2, "readme": True,
+                  "tags": {"abT": type2, "cdT": type1, "baT": type2, "badT": type2, "ABT": type2, "BCT": type2}})
     for rep in range(12):
         def rt(lo=2, hi=8):
             return T(rng.randint(lo, hi), rng.randint(0, 8), rng.random() < 0.85, rng.randrange(7), rng.randrange(4))
@@ -367,6 +371,9 @@ def gen_inputs(rng, c):
                 for _ in range(48)]
         if c["x_re"] == T(4, 4) and c["tags"].get("abT") == T(6, 3):
             sets.insert(0, [37, -22, -51, 19])          # SURVEY 2.5 golden
+        if c.get("readme"):
+            sets.insert(0, [8, 0, 8, 0])                # complex_vec = {a, a, a}, a = 1.0
+            sets.insert(0, [8, 0, 24, 0])               # complex1 = {1, 2}, complex2 = {3, 4}
         return sets
     if k == "gemul":
         if c.get("readme"):
@@ -388,20 +395,15 @@ def gen_inputs(rng, c):
         return out
 
 
-def main():
-    rng = random.Random(20261018)
-    cases = scalar_cases(rng) + reduce_cases(rng) + tf_cases(rng) + gemul_cases(rng) + cgemul_cases(rng)
-    os.makedirs(OUT_DIR, exist_ok=True)
-    os.makedirs(GOLD_DIR, exist_ok=True)
-    # split into a few TUs so that g++ can build them in parallel
-    n_tu = 8
+def build_harness(cases, include_dir, out_dir, tag, n_tu=8, extra_flags=()):
+    """Emit + compile the case table against the QuBLAS.h found in include_dir; returns run(idx, inputs)."""
+    os.makedirs(out_dir, exist_ok=True)
     tus = [[] for _ in range(n_tu)]
     for idx, c in enumerate(cases):
         tus[idx % n_tu].append(idx)
-    objs = []
-    procs = []
+    objs, procs = [], []
     for t, idxs in enumerate(tus):
-        src = os.path.join(OUT_DIR, "ref_cases_%d.cpp" % t)
+        src = os.path.join(out_dir, "%s_cases_%d.cpp" % (tag, t))
         with open(src, "w") as f:
             f.write(PRELUDE)
             for idx in idxs:
@@ -412,25 +414,42 @@ def main():
             f.write("  default: return -1; }\n}\n")
         obj = src[:-4] + ".o"
         objs.append(obj)
-        procs.append(subprocess.Popen(["g++", "-std=c++23", "-O1", "-fPIC", "-w", "-I", REF_INC, "-c", src, "-o", obj]))
+        procs.append(subprocess.Popen(["g++", "-std=c++23", "-O1", "-fPIC", "-w", "-I", include_dir, "-c", src, "-o", obj]))
     for p in procs:
         if p.wait() != 0:
-            sys.exit("reference harness failed to compile")
-    so = os.path.join(OUT_DIR, "libqref_cases.so")
-    subprocess.check_call(["g++", "-shared", "-o", so] + objs)
+            raise RuntimeError("harness failed to compile against " + include_dir)
+    so = os.path.join(out_dir, "libq%s_cases.so" % tag)
+    subprocess.check_call(["g++", "-shared", "-o", so] + objs + list(extra_flags))
     lib = ctypes.CDLL(so)
-    fixtures = {}
-    for idx, c in enumerate(cases):
+
+    def run(idx, row):
         fn = getattr(lib, "ref_run_%d" % (idx % n_tu))
         fn.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
+        a = (ctypes.c_int64 * len(row))(*row)
+        o = (ctypes.c_int64 * n_outputs(cases[idx]))()
+        rc = fn(idx, a, o)
+        if rc != 0:
+            raise RuntimeError("case %d failed" % idx)
+        return list(o)
+    return run
+
+
+def all_cases(rng):
+    return scalar_cases(rng) + reduce_cases(rng) + tf_cases(rng) + gemul_cases(rng) + cgemul_cases(rng)
+
+
+def main():
+    rng = random.Random(20261018)
+    cases = all_cases(rng)
+    os.makedirs(GOLD_DIR, exist_ok=True)
+    run = build_harness(cases, REF_INC, OUT_DIR, "ref")
+    fixtures = {}
+    for idx, c in enumerate(cases):
         ins = gen_inputs(rng, c)
         outs = []
         for row in ins:
             assert len(row) == n_inputs(c)
-            a = (ctypes.c_int64 * len(row))(*row)
-            o = (ctypes.c_int64 * n_outputs(c))()
-            assert fn(idx, a, o) == 0
-            outs.append(list(o))
+            outs.append(run(idx, row))
         rec = dict(c)
         rec["inputs"] = ins
         rec["outputs"] = outs

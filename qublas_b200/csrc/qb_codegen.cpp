@@ -11,8 +11,8 @@ std::string emit_qstage(const QStage &q)
         if (v == INT64_MIN) snprintf(o, 40, "(-9223372036854775807LL-1)"); else snprintf(o, 40, "%lldLL", v);
     };
     char lo[40], hi[40]; lit(q.lo, lo); lit(q.hi, hi);
-    snprintf(buf, sizeof(buf), "qb::QStage{%d,%u,%u,%u,%u,%u,%u,%u,%s,%s}", (int)q.shift, q.qu, q.of, q.need_lo, q.need_hi,
-             q.wrap_bits, q.wrap_signed, q.identity, lo, hi);
+    snprintf(buf, sizeof(buf), "qb::QStage{%d,%u,%u,%u,%u,%u,%u,%u,%u,{0,0,0,0,0,0,0},%s,%s}", (int)q.shift, q.qu, q.of, q.need_lo, q.need_hi,
+             q.wrap_bits, q.wrap_signed, q.identity, q.wide, lo, hi);
     return buf;
 }
 

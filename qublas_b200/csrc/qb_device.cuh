@@ -74,8 +74,30 @@ template <typename I, bool CT> QB_DEV I q_apply(I v, const QStage &s)
     return q_ovf<I, CT>(q_round<I>(v, s.shift, s.qu), s);
 }
 
+// A value held in a register of the kernel's class I, converted by stage s (converting ctor).
+// `wide` stages (exact input wider than 32 bits) are evaluated in 64 bits inside a 32-bit kernel.
+template <typename I, bool CT> QB_DEV I conv_apply(I v, const QStage &s)
+{
+    if constexpr (sizeof(I) == 4) { if (s.wide) return (I)q_apply<int64_t, CT>((int64_t)v, s); }
+    return q_apply<I, CT>(v, s);
+}
+
+// Qmul_s::mul, QuBLAS.h:3146-3171: exact product, then the stage.
+template <typename I, bool CT> QB_DEV I mul_apply(I a, I b, const QStage &s)
+{
+    if constexpr (sizeof(I) == 4) { if (s.wide) return (I)q_apply<int64_t, CT>((int64_t)a * (int64_t)b, s); }
+    return q_apply<I, CT>(a * b, s);
+}
+
+// Qadd_s::add / Qsub_s::sub, QuBLAS.h:3177-3235: align, exact sum, then the stage.
 template <typename I, bool CT> QB_DEV I add_apply(I a, I b, const AddStage &s)
 {
+    if constexpr (sizeof(I) == 4) {
+        if (s.q.wide) {
+            int64_t x = shl_exact<int64_t>((int64_t)a, s.shl_a), y = shl_exact<int64_t>((int64_t)b, s.shl_b);
+            return (I)q_apply<int64_t, CT>(s.sub ? x - y : x + y, s.q);
+        }
+    }
     I x = shl_exact<I>(a, s.shl_a), y = shl_exact<I>(b, s.shl_b);
     return q_apply<I, CT>(s.sub ? x - y : x + y, s.q);
 }
@@ -83,6 +105,7 @@ template <typename I, bool CT> QB_DEV I add_apply(I a, I b, const AddStage &s)
 // Same-type tree merge (both operands are level-l nodes): no alignment shifts.
 template <typename I, bool CT> QB_DEV I merge_apply(I a, I b, const AddStage &s)
 {
+    if constexpr (sizeof(I) == 4) { if (s.q.wide) return (I)q_apply<int64_t, CT>((int64_t)a + (int64_t)b, s.q); }
     return q_apply<I, CT>(a + b, s.q);
 }
 
@@ -93,9 +116,9 @@ QB_DEV void tf_apply(I a, I b, I c, I d, const TfProg &t, I &re, I &im)
     I ab = add_apply<I, CT>(a, b, t.ab);
     I cd = add_apply<I, CT>(c, d, t.cd);
     I ba = add_apply<I, CT>(b, a, t.ba);
-    I A = q_apply<I, CT>(ab * c, t.A);
-    I Bv = q_apply<I, CT>(cd * b, t.B);
-    I Cv = q_apply<I, CT>(ba * d, t.C);
+    I A = mul_apply<I, CT>(ab, c, t.A);
+    I Bv = mul_apply<I, CT>(cd, b, t.B);
+    I Cv = mul_apply<I, CT>(ba, d, t.C);
     re = add_apply<I, CT>(A, Bv, t.re);
     im = add_apply<I, CT>(Bv, Cv, t.im);
 }
@@ -110,7 +133,7 @@ QB_DEV I flush_apply(const TreeProg &P, const I *st)
     for (uint32_t i = 0; i < P.nflush; ++i) {
         const FlushStep &f = P.flush[i];
         if (f.kind == FL_LOAD) cur = st[f.slot];
-        else if (f.kind == FL_CONV) cur = q_apply<I, CT>(cur, f.a.q);
+        else if (f.kind == FL_CONV) cur = conv_apply<I, CT>(cur, f.a.q);
         else cur = add_apply<I, CT>(st[f.slot], cur, f.a);
     }
     return cur;

@@ -1,0 +1,203 @@
+// qb_fast_gemul.cuh — compile-time-specialised batched Qgemul for small dense instances
+// (BASELINE config 3: 10^6 x 64x64x64, 16-bit operands) on the integer ALU.
+//
+//   * one CTA = one instance at a time, persistent over the batch (grid = resident CTAs x SMs);
+//   * A and B instances (contiguous column-major arrays) are staged in shared memory by 1-D TMA
+//     bulk copies (cp.async.bulk ... mbarrier::complete_tx) into a 2-stage ring, so the next
+//     instance streams in from HBM while the current one is computed;
+//   * each thread owns a TM x TN register tile of C and consumes k in order: 8 products are
+//     reduced by a fully unrolled 3-level adjacent-pair tree, the resulting level-3 nodes go
+//     through a level-indexed register stack (uniform branches on the chunk counter), which is
+//     exactly the reference's pairwise order (QuBLAS.h:4936-4941) with its per-level quantizer;
+//   * every shift / bound / mode of Qmul<MulArgs> (QuBLAS.h:3146-3171), of the per-level
+//     Qadd (QuBLAS.h:3177-3204) and of the final converting assignment (QuBLAS.h:2398-2411) is an
+//     immediate; clamps the host's interval analysis proved dead are not emitted.
+#pragma once
+#include "qb_device.cuh"
+
+namespace qb {
+
+QB_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+QB_DEV void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+QB_DEV void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+QB_DEV void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+QB_DEV void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <class Cfg, int TM, int TN>
+struct GemulTile {
+    typedef typename Cfg::I I;
+    static constexpr int M = Cfg::M, N = Cfg::N, K = Cfg::K;
+    static constexpr int KC = 8;                               // products reduced in registers per chunk
+    static constexpr int NCH = K / KC;
+    static constexpr int NTOP = Cfg::NLEV - 3;                 // stack levels above a chunk
+    static constexpr int THREADS = (M / TM) * (N / TN);
+    static constexpr int A_WORDS = M * K, B_WORDS = K * N;
+    static constexpr uint32_t STAGE_BYTES = (A_WORDS + B_WORDS) * 4;
+    static constexpr uint32_t SMEM_BYTES = 2 * STAGE_BYTES + 64;
+    static_assert(M % TM == 0 && N % TN == 0 && TM == 4 && TN == 4, "tile shape");
+    static_assert(K % KC == 0 && (K & (K - 1)) == 0 && K >= KC, "K must be a power of two >= 8");
+    static_assert(sizeof(typename Cfg::WA) == 4 && sizeof(typename Cfg::WB) == 4 && sizeof(typename Cfg::WC) == 4, "int32 words");
+};
+
+// level-indexed register stack above the 8-product chunks; c = chunk counter (uniform)
+template <class Cfg, int L, int NTOP, typename I>
+QB_DEV void stack_push(I (&st)[NTOP > 0 ? NTOP : 1], uint32_t c, I v, I &result)
+{
+    if constexpr (L >= NTOP) {
+        result = v;
+    } else {
+        if ((c >> L) & 1) {
+            constexpr AddStage lv = Cfg::lvl(3 + L);
+            I m = merge_apply<I, true>(st[L], v, lv);
+            stack_push<Cfg, L + 1, NTOP, I>(st, c, m, result);
+        } else {
+            st[L] = v;
+        }
+    }
+}
+
+template <class Cfg>
+__global__ void __launch_bounds__(GemulTile<Cfg, 4, 4>::THREADS, 2)
+k_gemul_tile(const int32_t *__restrict__ A, const int32_t *__restrict__ B, int32_t *__restrict__ C, uint64_t batch)
+{
+    typedef GemulTile<Cfg, 4, 4> T;
+    typedef typename T::I I;
+    constexpr int M = T::M, N = T::N, K = T::K, NTOP = T::NTOP;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    int32_t *stage0 = (int32_t *)smem_raw;
+    uint64_t *bars = (uint64_t *)(smem_raw + 2 * T::STAGE_BYTES);
+
+    const int tid = threadIdx.x;
+    const int tx = tid % (M / 4), ty = tid / (M / 4);
+    const int i0 = tx * 4, j0 = ty * 4;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](uint64_t inst, int s) {
+        int32_t *dst = stage0 + (size_t)s * (T::STAGE_BYTES / 4);
+        mbar_expect_tx(&bars[s], T::STAGE_BYTES);
+        tma_load_1d(dst, A + inst * T::A_WORDS, T::A_WORDS * 4, &bars[s]);
+        tma_load_1d(dst + T::A_WORDS, B + inst * T::B_WORDS, T::B_WORDS * 4, &bars[s]);
+    };
+
+    uint64_t inst = blockIdx.x;
+    if (inst < batch && tid == 0) issue(inst, 0);
+
+    constexpr QStage mulq = Cfg::mul();
+    constexpr QStage outq = Cfg::out();
+    constexpr AddStage l0 = Cfg::lvl(0), l1 = Cfg::lvl(1), l2 = Cfg::lvl(2);
+
+    for (uint32_t it = 0; inst < batch; inst += gridDim.x, ++it) {
+        const int s = it & 1;
+        const uint64_t next = inst + gridDim.x;
+        if (tid == 0 && next < batch) issue(next, s ^ 1);        // stage s^1 was released by the barrier below
+        mbar_wait(&bars[s], (it >> 1) & 1);
+
+        const int32_t *As = stage0 + (size_t)s * (T::STAGE_BYTES / 4);
+        const int32_t *Bs = As + T::A_WORDS;
+        const int4 *As4 = (const int4 *)As;
+        const int4 *Bs4 = (const int4 *)Bs;
+
+        I st[4][4][NTOP > 0 ? NTOP : 1];
+        I res[4][4];
+#pragma unroll 1
+        for (uint32_t c = 0; c < (uint32_t)T::NCH; ++c) {
+            I half[2][4][4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k0 = c * 8 + h * 4;
+                int4 bq[4], aq[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) bq[jj] = Bs4[((j0 + jj) * K + k0) >> 2];      // B[k0..k0+3, j]
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) aq[kk] = As4[((k0 + kk) * M + i0) >> 2];      // A[i0..i0+3, k]
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const I b0 = bq[jj].x, b1 = bq[jj].y, b2 = bq[jj].z, b3 = bq[jj].w;
+#pragma unroll
+                    for (int ii = 0; ii < 4; ++ii) {
+                        const I a0 = (&aq[0].x)[ii], a1 = (&aq[1].x)[ii], a2 = (&aq[2].x)[ii], a3 = (&aq[3].x)[ii];
+                        I p0 = mul_apply<I, true>(a0, b0, mulq);
+                        I p1 = mul_apply<I, true>(a1, b1, mulq);
+                        I p2 = mul_apply<I, true>(a2, b2, mulq);
+                        I p3 = mul_apply<I, true>(a3, b3, mulq);
+                        I s01 = merge_apply<I, true>(p0, p1, l0);
+                        I s23 = merge_apply<I, true>(p2, p3, l0);
+                        half[h][ii][jj] = merge_apply<I, true>(s01, s23, l1);
+                    }
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) {
+                    I v = merge_apply<I, true>(half[0][ii][jj], half[1][ii][jj], l2);
+                    stack_push<Cfg, 0, NTOP, I>(st[ii][jj], c, v, res[ii][jj]);
+                }
+        }
+        // converting assignment into C's element type, column-major 128-bit stores
+        int32_t *Ci = C + inst * (uint64_t)(M * N);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            int4 o;
+            o.x = (int32_t)conv_apply<I, true>(res[0][jj], outq);
+            o.y = (int32_t)conv_apply<I, true>(res[1][jj], outq);
+            o.z = (int32_t)conv_apply<I, true>(res[2][jj], outq);
+            o.w = (int32_t)conv_apply<I, true>(res[3][jj], outq);
+            *(int4 *)(Ci + (j0 + jj) * M + i0) = o;
+        }
+        __syncthreads();      // everyone is done reading stage s before it is refilled
+    }
+}
+
+template <class Cfg>
+static int launch_gemul_tile(const void *A, const void *B, void *C, uint64_t batch, cudaStream_t s)
+{
+    typedef GemulTile<Cfg, 4, 4> T;
+    static int grid_cap = 0;
+    if (!grid_cap) {
+        cudaError_t e = cudaFuncSetAttribute(k_gemul_tile<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gemul_tile<Cfg>, T::THREADS, T::SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        grid_cap = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    const unsigned grid = (unsigned)(batch < (uint64_t)grid_cap ? batch : (uint64_t)grid_cap);
+    k_gemul_tile<Cfg><<<grid, T::THREADS, T::SMEM_BYTES, s>>>((const int32_t *)A, (const int32_t *)B, (int32_t *)C, batch);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) count_launch(1);
+    return (int)e;
+}
+
+}  // namespace qb

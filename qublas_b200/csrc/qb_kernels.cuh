@@ -54,7 +54,7 @@ QB_DEV void comb(I &lv, bool &lp, I rv, bool rp, uint32_t r, uint32_t rmax, uint
 {
     if (r >= rmax || !lp) return;                       // above the root, or nothing here
     if (rp) lv = merge_apply<I, false>(lv, rv, P.lvl[lev0 + r]);
-    else    lv = q_apply<I, false>(lv, P.carry[lev0 + r]);
+    else    lv = conv_apply<I, false>(lv, P.carry[lev0 + r]);
 }
 
 template <typename WT, typename I>
@@ -180,9 +180,9 @@ k_gemul_thread(const void *__restrict__ A, const void *__restrict__ B, void *__r
         const uint64_t ia = S.trans_a ? (k + (uint64_t)i * S.K) : (i + k * S.M);      // column-major, QuBLAS.h:2680-2692
         const uint64_t ib = S.trans_b ? (j + k * S.N) : (k + (uint64_t)j * S.K);
         I a = load_word<I>(A, oa + ia, S.a_wb), b = load_word<I>(B, ob + ib, S.b_wb);
-        return q_apply<I, false>(a * b, mul);
+        return mul_apply<I, false>(a, b, mul);
     });
-    store_word<I>(C, inst * (uint64_t)S.stride_c + ij, S.c_wb, q_apply<I, false>(r, outq));
+    store_word<I>(C, inst * (uint64_t)S.stride_c + ij, S.c_wb, conv_apply<I, false>(r, outq));
 }
 
 // Complex Qgemul with TFComplexMul products: two level-indexed stacks (real / imaginary part),
@@ -218,8 +218,8 @@ k_cgemul_thread(const void *__restrict__ A, const void *__restrict__ B, void *__
     }
     I rr = flush_apply<I, false>(Pre, sr), ri = flush_apply<I, false>(Pim, si);
     const uint64_t ic = inst * (uint64_t)S.stride_c + ij;
-    store_word<I>(C, 2 * ic, S.c_wb, q_apply<I, false>(rr, out_re));
-    store_word<I>(C, 2 * ic + 1, S.c_wb, q_apply<I, false>(ri, out_im));
+    store_word<I>(C, 2 * ic, S.c_wb, conv_apply<I, false>(rr, out_re));
+    store_word<I>(C, 2 * ic + 1, S.c_wb, conv_apply<I, false>(ri, out_im));
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -244,7 +244,7 @@ __global__ void k_convert(const void *__restrict__ in, void *__restrict__ out, u
                           const __grid_constant__ QStage q)
 {
     for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x)
-        store_word<I>(out, e, out_wb, q_apply<I, false>(load_word<I>(in, e, in_wb), q));
+        store_word<I>(out, e, out_wb, conv_apply<I, false>(load_word<I>(in, e, in_wb), q));
 }
 
 __global__ void k_synth_fill(void *__restrict__ dst, uint64_t count, int wb, int64_t lo, uint64_t span, uint64_t key,

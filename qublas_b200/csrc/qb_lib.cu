@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -92,6 +93,90 @@ struct Ctx {
     }
     ~Ctx() { for (void *p : to_free) cudaFreeAsync(p, stream); }
 };
+
+// ---------------------------------------------------------------------------------------------
+// Host-buffer calls on large batches: a 3-slot pipeline over internal streams so that the H2D copy
+// of chunk i+1, the kernel of chunk i and the D2H copy of chunk i-1 overlap (copy engines + SMs).
+// Staging buffers are persistent per device.  With pinned caller memory the copies are truly
+// asynchronous; with pageable memory the runtime stages them and the overlap is partial.
+// ---------------------------------------------------------------------------------------------
+struct HostPipe {
+    static constexpr int NS = 3;
+    std::mutex mu;
+    bool ready = false;
+    cudaStream_t st[NS];
+    cudaEvent_t done[NS];
+    char *buf[NS] = { nullptr, nullptr, nullptr };
+    size_t cap[NS] = { 0, 0, 0 };
+    char *shared = nullptr; size_t shared_cap = 0;
+    int init()
+    {
+        if (ready) return QB_OK;
+        for (int i = 0; i < NS; i++) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+        }
+        ready = true;
+        return QB_OK;
+    }
+    int ensure(char **b, size_t *c, size_t bytes)
+    {
+        if (*c >= bytes) return QB_OK;
+        if (*b) CUDA_TRY(cudaFree(*b));
+        *b = nullptr; *c = 0;
+        CUDA_TRY(cudaMalloc((void **)b, bytes));
+        *c = bytes;
+        return QB_OK;
+    }
+};
+static HostPipe g_pipes[64];
+
+struct PipeIn { const char *src; size_t unit_bytes; bool shared; size_t shared_bytes; };
+
+template <class LaunchFn>
+static int host_pipeline(int nin, const PipeIn *ins, char *out, size_t out_unit_bytes, uint64_t units, LaunchFn launch)
+{
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    HostPipe &hp = g_pipes[dev & 63];
+    std::lock_guard<std::mutex> lock(hp.mu);
+    int rc = hp.init(); if (rc) return rc;
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    size_t unit_total = out_unit_bytes, shared_total = 0;
+    for (int i = 0; i < nin; i++) { if (ins[i].shared) shared_total += al(ins[i].shared_bytes); else unit_total += ins[i].unit_bytes; }
+    uint64_t cu = (48u << 20) / (unit_total ? unit_total : 1);
+    if (cu < 1) cu = 1;
+    if (cu > units) cu = units;
+    size_t slot_bytes = al(cu * out_unit_bytes);
+    for (int i = 0; i < nin; i++) if (!ins[i].shared) slot_bytes += al(cu * ins[i].unit_bytes);
+    for (int s = 0; s < HostPipe::NS; s++) if ((rc = hp.ensure(&hp.buf[s], &hp.cap[s], slot_bytes))) return rc;
+    const void *dins[8];
+    if (shared_total) {
+        if ((rc = hp.ensure(&hp.shared, &hp.shared_cap, shared_total))) return rc;
+        size_t off = 0;
+        for (int i = 0; i < nin; i++) if (ins[i].shared) {
+            CUDA_TRY(cudaMemcpyAsync(hp.shared + off, ins[i].src, ins[i].shared_bytes, cudaMemcpyHostToDevice, hp.st[0]));
+            dins[i] = hp.shared + off; off += al(ins[i].shared_bytes);
+        }
+        CUDA_TRY(cudaStreamSynchronize(hp.st[0]));
+    }
+    uint64_t first = 0;
+    for (uint64_t it = 0; first < units; ++it, first += cu) {
+        const int s = (int)(it % HostPipe::NS);
+        const uint64_t n = units - first < cu ? units - first : cu;
+        cudaStream_t st = hp.st[s];
+        size_t off = 0;
+        for (int i = 0; i < nin; i++) if (!ins[i].shared) {
+            CUDA_TRY(cudaMemcpyAsync(hp.buf[s] + off, ins[i].src + first * ins[i].unit_bytes, n * ins[i].unit_bytes, cudaMemcpyHostToDevice, st));
+            dins[i] = hp.buf[s] + off; off += al(cu * ins[i].unit_bytes);
+        }
+        void *dout = hp.buf[s] + off;
+        if ((rc = launch(dins, dout, n, st))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(out + first * out_unit_bytes, dout, n * out_unit_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < HostPipe::NS; s++) CUDA_TRY(cudaStreamSynchronize(hp.st[s]));
+    return QB_OK;
+}
 
 static inline unsigned grid_for(uint64_t n, unsigned block, unsigned cap = 148 * 16)
 {
@@ -290,26 +375,36 @@ extern "C" int qb200_gemul_batched(const qb_gemul_plan *plan, const void *A, con
     if (batch == 0) return QB_OK;
     Ctx cx; int rc = cx.init(exec); if (rc) return rc;
     const uint64_t ea = (uint64_t)plan->M * plan->K, eb = (uint64_t)plan->K * plan->N, ec = (uint64_t)plan->M * plan->N;
+    const int bits = arith_bits(an);
+    if (bits == 32) { sanitize32_stage(gp.mul); sanitize32(gp.tree); sanitize32_stage(gp.out); }
+    const FastGemul *f = (cx.flags & QB_F_NO_SPECIALIZE) ? nullptr : find_fast_gemul(*plan, gp, bits);
+    // one launch over n instances laid out with the given strides
+    auto launch = [&](const void *dA, const void *dB, void *dC, uint64_t n, int64_t sa, int64_t sb, int64_t sc, cudaStream_t st) -> int {
+        if (f && sa == (int64_t)ea && sb == (int64_t)eb && sc == (int64_t)ec) {
+            int e = f->launch(dA, dB, dC, n, st);
+            if (e) return fail(QB_ECUDA, std::string(f->name) + " launch failed: " + cudaGetErrorString((cudaError_t)e));
+            return QB_OK;
+        }
+        GemulShape S = shape_of(plan->M, plan->N, plan->K, plan->trans_a, plan->trans_b, gp.a_wb, gp.b_wb, gp.c_wb, sa, sb, sc);
+        const uint64_t blocks = (n * ec + 127) / 128;
+        if (blocks > 0x7fffffffull) return fail(QB_EINVAL, "too many outputs for one launch");
+        if (bits == 32) k_gemul_thread<int32_t><<<(unsigned)blocks, 128, 0, st>>>(dA, dB, dC, n, S, gp.mul, gp.tree, gp.out);
+        else            k_gemul_thread<int64_t><<<(unsigned)blocks, 128, 0, st>>>(dA, dB, dC, n, S, gp.mul, gp.tree, gp.out);
+        return post_launch("k_gemul_thread");
+    };
+    const bool dense = (plan->stride_a == (int64_t)ea || plan->stride_a == 0) && (plan->stride_b == (int64_t)eb || plan->stride_b == 0) &&
+                       plan->stride_c == (int64_t)ec;
+    if (cx.host && dense && batch >= 64) {
+        PipeIn ins[2] = { { (const char *)A, ea * gp.a_wb, plan->stride_a == 0, ea * gp.a_wb }, { (const char *)B, eb * gp.b_wb, plan->stride_b == 0, eb * gp.b_wb } };
+        return host_pipeline(2, ins, (char *)C, ec * gp.c_wb, batch, [&](const void *const *d, void *dC, uint64_t n, cudaStream_t st) {
+            return launch(d[0], d[1], dC, n, plan->stride_a, plan->stride_b, plan->stride_c, st);
+        });
+    }
     const size_t bytes_a = span_elems(batch, plan->stride_a, ea) * gp.a_wb, bytes_b = span_elems(batch, plan->stride_b, eb) * gp.b_wb,
                  bytes_c = span_elems(batch, plan->stride_c, ec) * gp.c_wb;
     const void *dA, *dB; void *dC;
     if ((rc = cx.in(A, bytes_a, &dA)) || (rc = cx.in(B, bytes_b, &dB)) || (rc = cx.out(C, bytes_c, &dC))) return rc;
-    const int bits = arith_bits(an);
-    if (bits == 32) { sanitize32_stage(gp.mul); sanitize32(gp.tree); sanitize32_stage(gp.out); }
-    const FastGemul *f = (cx.flags & QB_F_NO_SPECIALIZE) ? nullptr : find_fast_gemul(*plan, gp, bits);
-    if (f) {
-        rc = f->launch(dA, dB, dC, batch, cx.stream);
-        if (rc) return fail(QB_ECUDA, std::string(f->name) + " launch failed: " + cudaGetErrorString((cudaError_t)rc));
-    } else {
-        GemulShape S = shape_of(plan->M, plan->N, plan->K, plan->trans_a, plan->trans_b, gp.a_wb, gp.b_wb, gp.c_wb,
-                                plan->stride_a, plan->stride_b, plan->stride_c);
-        const uint64_t threads = batch * ec;
-        const uint64_t blocks = (threads + 127) / 128;
-        if (blocks > 0x7fffffffull) return fail(QB_EINVAL, "too many outputs for one launch");
-        if (bits == 32) k_gemul_thread<int32_t><<<(unsigned)blocks, 128, 0, cx.stream>>>(dA, dB, dC, batch, S, gp.mul, gp.tree, gp.out);
-        else            k_gemul_thread<int64_t><<<(unsigned)blocks, 128, 0, cx.stream>>>(dA, dB, dC, batch, S, gp.mul, gp.tree, gp.out);
-        if ((rc = post_launch("k_gemul_thread"))) return rc;
-    }
+    if ((rc = launch(dA, dB, dC, batch, plan->stride_a, plan->stride_b, plan->stride_c, cx.stream))) return rc;
     if ((rc = cx.out_done(C, bytes_c, dC))) return rc;
     return cx.finish();
 }
@@ -396,6 +491,7 @@ extern "C" int qb200_convert_batched(const qb_convert_plan *plan, const void *in
     QStage q = make_stage(plan->from.frac_bits, type_range(plan->from), width(plan->from), plan->to, &o, an);
     if (an.status) return fail(an.status, an.err);
     if (an.max_bits > 64) return fail(QB_EDOMAIN, "conversion intermediate wider than 64 bits");
+    an.max_reg_bits = std::max(an.max_reg_bits, width(plan->from));      // the input word itself lives in a register
     const uint64_t n = plan->len * batch;
     if (n == 0) return QB_OK;
     Ctx cx; int rc = cx.init(exec); if (rc) return rc;

@@ -82,10 +82,12 @@ QStage make_stage(int from_frac, Ival in, int in_width, qb_qdesc to, TVal *out, 
     an.max_shift = std::max(an.max_shift, s < 0 ? -s : s);
     an.max_bits = std::max(an.max_bits, bits_for(in));
     an.ref_width = std::max(an.ref_width, in_width);
+    int stage_bits = bits_for(in);
     Ival r;
     if (s <= 0) {
         r = { shl(in.lo, -s), shl(in.hi, -s) };
         an.max_bits = std::max(an.max_bits, bits_for(r));
+        stage_bits = std::max(stage_bits, bits_for(r));
         an.ref_width = std::max(an.ref_width, in_width - s);
     } else {
         bool rnd = to.qu_mode <= RND_CONV;
@@ -100,6 +102,7 @@ QStage make_stage(int from_frac, Ival in, int in_width, qb_qdesc to, TVal *out, 
         i128 bias = rnd ? ((i128)1 << (s - 1)) : 0;                       // device computes (v + bias) >> s
         Ival biased = { in.lo, in.hi + bias };
         an.max_bits = std::max(an.max_bits, bits_for(biased));
+        stage_bits = std::max(stage_bits, bits_for(biased));
         an.lossless = false;
     }
     // intConvert, QuBLAS.h:2227-2334
@@ -143,6 +146,8 @@ QStage make_stage(int from_frac, Ival in, int in_width, qb_qdesc to, TVal *out, 
     }
     if (st.need_lo || st.need_hi) an.lossless = false;
     an.max_bits = std::max(an.max_bits, bits_for(o));
+    an.max_reg_bits = std::max(an.max_reg_bits, bits_for(o));
+    st.wide = stage_bits > 32 || s > 30 || s < -30;
     st.identity = (s <= 0 && !st.need_lo && !st.need_hi);
     if (out) { out->t = to; out->t.word_bytes = 0; out->r = o; }
     return st;
@@ -152,6 +157,7 @@ QStage make_mul(TVal a, TVal b, qb_qdesc to, TVal *out, Analysis &an)      // Qm
 {
     i128 c[4] = { a.r.lo * b.r.lo, a.r.lo * b.r.hi, a.r.hi * b.r.lo, a.r.hi * b.r.hi };
     Ival p = { *std::min_element(c, c + 4), *std::max_element(c, c + 4) };
+    an.max_reg_bits = std::max(an.max_reg_bits, std::max(bits_for(a.r), bits_for(b.r)));
     return make_stage(a.frac() + b.frac(), p, width(a.t) + width(b.t), to, out, an);
 }
 
@@ -166,9 +172,11 @@ AddStage make_add(TVal a, TVal b, qb_qdesc to, bool sub, TVal *out, Analysis &an
     an.max_shift = std::max(an.max_shift, std::max(sa, sb));
     Ival x = { shl(a.r.lo, sa), shl(a.r.hi, sa) }, y = { shl(b.r.lo, sb), shl(b.r.hi, sb) };
     an.max_bits = std::max(an.max_bits, std::max(bits_for(x), bits_for(y)));
+    an.max_reg_bits = std::max(an.max_reg_bits, std::max(bits_for(a.r), bits_for(b.r)));
     Ival e = sub ? Ival{ x.lo - y.hi, x.hi - y.lo } : Ival{ x.lo + y.lo, x.hi + y.hi };
     int w = std::max(width(a.t) + sa, width(b.t) + sb) + 1;
     s.q = make_stage(mf, e, w, to, out, an);
+    if (std::max(bits_for(x), bits_for(y)) > 32 || sa > 30 || sb > 30) s.q.wide = 1;
     return s;
 }
 

@@ -18,6 +18,7 @@ struct TVal { qb_qdesc t; Ival r; int frac() const { return t.frac_bits; } };
 
 struct Analysis {
     int  max_bits = 1;        // widest exact intermediate incl. rounding bias (two's complement bits)
+    int  max_reg_bits = 1;    // widest value that lives BETWEEN stages (leaves and stage outputs)
     int  ref_width = 1;       // widest STATIC ArbiInt width the reference would instantiate
     int  max_shift = 0;       // largest shift amount any stage uses (left, right or alignment)
     bool lossless = true;     // every quantizer so far is an identity
@@ -66,9 +67,10 @@ int compile_gemul(const qb_gemul_plan &p, GemulProg *out, Analysis &an);
 int compile_cgemul(const qb_cgemul_plan &p, CGemulProg *out, Analysis &an);
 int compile_tfcmul(const qb_tfcmul_plan &p, TfProg *out, TVal *re, TVal *im, Analysis &an);
 
-// Register class of a compiled plan: 32 iff every exact intermediate and every stage output fits
-// int32 and no shift amount reaches the word size; else 64.
-inline int arith_bits(const Analysis &an) { return (an.max_bits <= 32 && an.max_shift <= 30) ? 32 : 64; }
+// Register class of a compiled plan: 32 iff every leaf and every stage output fits int32; else 64.
+// Stages whose exact input is wider than 32 bits (e.g. a 17x16-bit product) are marked `wide` and
+// evaluated in 64 bits inside an otherwise 32-bit kernel.
+inline int arith_bits(const Analysis &an) { return an.max_reg_bits <= 32 ? 32 : 64; }
 void sanitize32(TreeProg &t);
 void sanitize32(TfProg &t);
 void sanitize32_stage(QStage &q);

@@ -29,6 +29,8 @@ struct QStage {
     uint8_t wrap_bits;   // WRP::TCPL: signed -> keep W bits sign-extended; unsigned -> keep W-1 bits
     uint8_t wrap_signed;
     uint8_t identity;    // 1 if the whole stage is provably v' = v << -shift with shift <= 0 and no clamp
+    uint8_t wide;        // the exact input of this stage needs more than 32 bits (its output may still fit 32)
+    uint8_t pad[7];
     int64_t lo, hi;      // SAT bounds of the target type (SMGN: symmetric lower bound)
 };
 

@@ -142,7 +142,11 @@ def test_random_reduce_vs_oracle(seed):
         x = rand_words(rng, elem, n * batch)
         plan = reduce_plan(elem, lv, n)
         want, _ = oracle.reduce_batched(plan, x, batch)
-        out, _ = ops.Qreduce(dev(x), elem, lv, length=n, batch=batch)
+        try:
+            out, _ = ops.Qreduce(dev(x), elem, lv, length=n, batch=batch)
+        except abi.QbError as e:
+            assert e.code == abi.QB_EDOMAIN        # a random plan may land on a fenced reference defect
+            continue
         assert np.array_equal(out.cpu().numpy(), want), (n, elem, lv)
     # variadic form goes through the per-vector streaming kernel
     for n in [3, 5, 6, 7, 11, 100, 1001]:
