@@ -197,6 +197,12 @@ int qb200_convert_batched(const qb_convert_plan *plan, const void *in, void *out
 int qb200_synth_fill(void *dst, uint64_t count, uint32_t word_bytes, int64_t lo, int64_t hi,
                      uint64_t seed, uint64_t stream_id, uint64_t first_index, const qb_exec *exec);
 
+/* Diagnostic: measured INT32 issue peak of the current device in tera thread-operations per second
+ * (dependent-chain-free mix of IMAD on the FMA pipe and IADD3/LOP3 on the ALU pipe, all SMs busy).
+ * This is the roofline denominator for the integer-ALU-bound kernels (MEASURED_PEAKS.json has no
+ * integer figure).  fma_share in [0,1] = fraction of IMAD instructions in the mix. */
+int qb200_measure_int_peak(double fma_share, double *tera_ops_per_s, const qb_exec *exec);
+
 /* Contiguous shard [first, first+count) of `total` units for `rank` of `world` (batch or M-panel). */
 int qb200_shard_range(uint64_t total, uint32_t world, uint32_t rank, uint64_t *first, uint64_t *count);
 

@@ -1,0 +1,341 @@
+// qb_i8gemm.cu — tcgen05 kind::i8 tensor-core path of Qgemul (BASELINE config 5).
+//
+// Used ONLY when the host's interval analysis proves the whole accumulation lossless
+// (qb_plan.cpp:gemul_tensor_core_ok): operand raws fit int8, every Qmul<MulArgs> and every tree
+// level is an identity, so the reference's tree result IS the exact integer dot product (sum order
+// is irrelevant) and fits int32.  The tensor core computes that dot product exactly; the only
+// quantizer left is the converting assignment into C's element type (QuBLAS.h:2398-2411), applied
+// once in the epilogue.
+//
+// Pipeline (one CTA per SM, persistent over 128x256 output tiles, warp-specialised):
+//   pack   : ABI words (int32/int64, column-major) -> int8, both operands K-major (separate kernels)
+//   warp 0 : TMA producer, 2-D tiled loads with 128B swizzle into a 4-stage smem ring (UTMALDG)
+//   warp 1 : allocates TMEM (512 columns = two 128x256 int32 accumulators), issues
+//            tcgen05.mma.cta_group::1.kind::i8 (M=128, N=256, K=32), commits to mbarriers (UTCQMMA/UTCIMMA)
+//   warps 2-5: epilogue, tcgen05.ld 32x32b.x32 (LDTM) -> C's quantizer -> coalesced column-major stores,
+//            overlapped with the next tile's MMAs through the second accumulator.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include "qb_device.cuh"
+#include "qb_fast.h"
+#include "qb_i8gemm.h"
+
+namespace qb {
+
+static constexpr int BM = 128, BN = 256, BK = 128;            // BK in int8 elements = one 128-byte swizzle row
+static constexpr int STAGES = 4;
+static constexpr int A_STAGE = BM * BK, B_STAGE = BN * BK;    // bytes
+static constexpr int STAGE_BYTES = A_STAGE + B_STAGE;
+static constexpr int TMEM_COLS = 512;
+static constexpr int I8_THREADS = 192;
+static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bar_init(uint64_t *b, uint32_t n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(n)); }
+__device__ __forceinline__ void bar_expect_tx(uint64_t *b, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint64_t *b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory"); }
+__device__ __forceinline__ void bar_wait(uint64_t *b, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(s32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(s32(dst)), "l"(map), "r"(s32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], int8 x int8 -> int32
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart
+// (cute::UMMA::SmemDescriptor: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version=1 <<46 | SWIZZLE_128B=2 <<61).
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major), 16-byte units
+    d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+    return d;
+}
+// cute::UMMA::InstrDescriptor for kind::i8: S32 accumulator, signed int8 A and B, both K-major.
+__host__ __device__ constexpr uint32_t umma_idesc_i8(int m, int n)
+{
+    return (2u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct I8Params {
+    uint32_t M, N, K;             // multiples of BM, BN, BK
+    uint32_t tiles_m, tiles_n;
+    int32_t  c_wb;
+    uint32_t group_m;             // rasterisation: group_m m-tiles share each B panel while it is hot in L2
+};
+
+__global__ void __launch_bounds__(I8_THREADS, 1)
+k_i8gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, void *__restrict__ C,
+         const __grid_constant__ I8Params P, const __grid_constant__ QStage outq)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // SWIZZLE_128B atoms need 1024-byte alignment
+    unsigned char *sA = smem, *sB = smem + STAGES * A_STAGE;
+    uint64_t *bars = (uint64_t *)(smem + STAGES * STAGE_BYTES);
+    uint64_t *full = bars, *empty = bars + STAGES, *tfull = bars + 2 * STAGES, *tempty = bars + 2 * STAGES + 2;
+    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t ntiles = P.tiles_m * P.tiles_n;
+    const uint32_t nkb = P.K / BK;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; s++) { bar_init(&full[s], 1); bar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; a++) { bar_init(&tfull[a], 1); bar_init(&tempty[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto tile_coords = [&](uint32_t t, uint32_t &tm, uint32_t &tn) {
+        const uint32_t per_group = P.group_m * P.tiles_n;
+        const uint32_t g = t / per_group, r = t - g * per_group;
+        const uint32_t gm = (P.tiles_m - g * P.group_m) < P.group_m ? (P.tiles_m - g * P.group_m) : P.group_m;
+        tm = g * P.group_m + r % gm;
+        tn = r / gm;
+    };
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                uint32_t tm, tn; tile_coords(t, tm, tn);
+                for (uint32_t kb = 0; kb < nkb; kb++) {
+                    bar_wait(&empty[stage], phase ^ 1);
+                    bar_expect_tx(&full[stage], STAGE_BYTES);
+                    tma_load_2d(sA + stage * A_STAGE, &mapA, &full[stage], (int)(kb * BK), (int)(tm * BM));
+                    tma_load_2d(sB + stage * B_STAGE, &mapB, &full[stage], (int)(kb * BK), (int)(tn * BN));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_i8(BM, BN);
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                bar_wait(&tempty[acc], acc_phase ^ 1);                 // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (uint32_t kb = 0; kb < nkb; kb++) {
+                    bar_wait(&full[stage], phase);                     // TMA bytes have landed
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_k_sw128(s32(sA + stage * A_STAGE));
+                    const uint64_t db = umma_desc_k_sw128(s32(sB + stage * B_STAGE));
+#pragma unroll
+                    for (uint32_t k = 0; k < BK / 32; k++)             // UMMA_K = 32 int8 = 32 bytes = +2 in 16-byte units
+                        tc_mma_i8(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    tc_commit(&empty[stage]);                          // frees the smem slot when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tfull[acc]);                                // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue warps 2..5: TMEM lane quadrant = warp % 4 =====
+        const uint32_t quad = warp & 3;
+        uint32_t acc = 0, acc_phase = 0;
+        for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            uint32_t tm, tn; tile_coords(t, tm, tn);
+            bar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint64_t row = (uint64_t)tm * BM + quad * 32 + lane;          // m index of this thread's TMEM lane
+#pragma unroll 1
+            for (uint32_t c0 = 0; c0 < (uint32_t)BN; c0 += 32) {
+                uint32_t v[32];
+                tc_ld32(tmem_base + ((quad * 32) << 16) + acc * BN + c0, v);
+#pragma unroll
+                for (int c = 0; c < 32; c++) {
+                    const uint64_t col = (uint64_t)tn * BN + c0 + c;
+                    const int32_t q = conv_apply<int32_t, false>((int32_t)v[c], outq);   // converting assignment into C's type
+                    if (P.c_wb == 4) ((int32_t *)C)[col * P.M + row] = q;                // column-major: 32 lanes = 128 contiguous bytes
+                    else             ((int64_t *)C)[col * P.M + row] = (int64_t)q;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) bar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+}
+
+// ---------------------------------------------------------------------------------------------
+// pack: raw ABI words -> int8, K-major.  src is column-major R x Cn (R contiguous).
+//   straight : dst[c][r] = src[r + c*R]     (K is already the contiguous index)
+//   transpose: dst[r][c] = src[r + c*R]     (the contiguous index must become the row)
+// ---------------------------------------------------------------------------------------------
+template <typename W>
+__global__ void k_pack_i8_straight(const W *__restrict__ src, int8_t *__restrict__ dst, uint64_t n)
+{
+    uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    for (; i + 3 < n; i += (uint64_t)gridDim.x * blockDim.x * 4) {
+        char4 o;
+        o.x = (signed char)src[i]; o.y = (signed char)src[i + 1]; o.z = (signed char)src[i + 2]; o.w = (signed char)src[i + 3];
+        *(char4 *)(dst + i) = o;
+    }
+}
+template <typename W>
+__global__ void k_pack_i8_transpose(const W *__restrict__ src, int8_t *__restrict__ dst, uint32_t R, uint32_t Cn)
+{
+    __shared__ int8_t tile[64][65];
+    const uint32_t r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+    for (uint32_t i = threadIdx.y; i < 64; i += blockDim.y)          // coalesced read along r
+        tile[i][threadIdx.x] = (int8_t)src[(uint64_t)(c0 + i) * R + r0 + threadIdx.x];
+    __syncthreads();
+    for (uint32_t i = threadIdx.y; i < 64; i += blockDim.y)          // coalesced write along c
+        dst[(uint64_t)(r0 + i) * Cn + c0 + threadIdx.x] = tile[threadIdx.x][i];
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// rows x K int8 matrix, K contiguous; box = 128 bytes of K x box_rows rows, 128B swizzle
+static int make_map(CUtensorMap *m, const int8_t *base, uint64_t rows, uint64_t K, uint32_t box_rows)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return -1;
+    cuuint64_t dims[2] = { K, rows };
+    cuuint64_t strides[1] = { K };
+    cuuint32_t box[2] = { (cuuint32_t)BK, box_rows };
+    cuuint32_t estr[2] = { 1, 1 };
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+bool i8gemm_shape_ok(uint32_t M, uint32_t N, uint32_t K) { return M % BM == 0 && N % BN == 0 && K % BK == 0 && M && N && K; }
+
+template <typename W>
+static void pack_operand(const void *src, int8_t *dst, uint32_t rows_contig, uint32_t cols, bool transpose, cudaStream_t s)
+{
+    // src is column-major rows_contig x cols
+    if (!transpose) {
+        const uint64_t n = (uint64_t)rows_contig * cols;
+        k_pack_i8_straight<W><<<(unsigned)std::min<uint64_t>((n / 4 + 255) / 256, 148 * 32), 256, 0, s>>>((const W *)src, dst, n);
+    } else {
+        dim3 grid(rows_contig / 64, cols / 64), block(64, 4);
+        k_pack_i8_transpose<W><<<grid, block, 0, s>>>((const W *)src, dst, rows_contig, cols);
+    }
+    count_launch(1);
+}
+
+// One instance.  A, B: device pointers to raw ABI words (a_wb / b_wb bytes each), column-major as in the plan.
+int i8gemm_run(const void *A, const void *B, void *C, uint32_t M, uint32_t N, uint32_t K, bool trans_a, bool trans_b, int a_wb,
+               int b_wb, int c_wb, const QStage &outq, int8_t *Ap, int8_t *Bp, cudaStream_t s, const char **err)
+{
+    // A operand must become M rows x K (K contiguous).  Stored M x K column-major (M contiguous) unless trans_a (K x M, K contiguous).
+    const bool a_tr = !trans_a;
+    // B operand must become N rows x K.  Stored K x N column-major (K contiguous) unless trans_b (N x K, N contiguous).
+    const bool b_tr = trans_b;
+    const uint32_t a_r = trans_a ? K : M, a_c = trans_a ? M : K;
+    const uint32_t b_r = trans_b ? N : K, b_c = trans_b ? K : N;
+    switch (a_wb) {
+    case 1: pack_operand<int8_t>(A, Ap, a_r, a_c, a_tr, s); break;
+    case 2: pack_operand<int16_t>(A, Ap, a_r, a_c, a_tr, s); break;
+    case 4: pack_operand<int32_t>(A, Ap, a_r, a_c, a_tr, s); break;
+    default: pack_operand<int64_t>(A, Ap, a_r, a_c, a_tr, s); break;
+    }
+    switch (b_wb) {
+    case 1: pack_operand<int8_t>(B, Bp, b_r, b_c, b_tr, s); break;
+    case 2: pack_operand<int16_t>(B, Bp, b_r, b_c, b_tr, s); break;
+    case 4: pack_operand<int32_t>(B, Bp, b_r, b_c, b_tr, s); break;
+    default: pack_operand<int64_t>(B, Bp, b_r, b_c, b_tr, s); break;
+    }
+    CUtensorMap mapA, mapB;
+    if (make_map(&mapA, Ap, M, K, BM) || make_map(&mapB, Bp, N, K, BN)) { *err = "cuTensorMapEncodeTiled failed"; return -1; }
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_i8gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) { *err = "cannot raise dynamic smem"; return -1; }
+        attr_set = true;
+    }
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    I8Params P;
+    P.M = M; P.N = N; P.K = K; P.tiles_m = M / BM; P.tiles_n = N / BN; P.c_wb = c_wb; P.group_m = 16;
+    const uint32_t ntiles = P.tiles_m * P.tiles_n;
+    const unsigned grid = ntiles < (uint32_t)sms ? ntiles : (unsigned)sms;
+    k_i8gemm<<<grid, I8_THREADS, SMEM_BYTES, s>>>(mapA, mapB, C, P, outq);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
+    count_launch(1);
+    return 0;
+}
+
+}  // namespace qb

@@ -1,0 +1,11 @@
+// qb_i8gemm.h — tcgen05 kind::i8 tensor-core path (qb_i8gemm.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "qb_prog.h"
+
+namespace qb {
+bool i8gemm_shape_ok(uint32_t M, uint32_t N, uint32_t K);
+int  i8gemm_run(const void *A, const void *B, void *C, uint32_t M, uint32_t N, uint32_t K, bool trans_a, bool trans_b, int a_wb,
+                int b_wb, int c_wb, const QStage &outq, int8_t *Ap, int8_t *Bp, cudaStream_t s, const char **err);
+}

@@ -13,6 +13,7 @@
 #include "qb_plan.h"
 #include "qb_kernels.cuh"
 #include "qb_fast.h"
+#include "qb_i8gemm.h"
 
 using namespace qb;
 
@@ -360,7 +361,8 @@ extern "C" int qb200_gemul_plan_info(const qb_gemul_plan *plan, qb_plan_info *in
     if (compile_gemul(*plan, &gp, an)) return fail(an.status, an.err);
     const FastGemul *f = find_fast_gemul(*plan, gp, arith_bits(an));
     qb_qdesc ct = plan->c; ct.word_bytes = 0;
-    fill_info(info, an, ct, gp.c_wb, f ? f->name : "k_gemul_thread", gemul_tensor_core_ok(*plan, gp, an), f != nullptr);
+    const bool tc = gemul_tensor_core_ok(*plan, gp, an) && i8gemm_shape_ok(plan->M, plan->N, plan->K);
+    fill_info(info, an, ct, gp.c_wb, tc ? "k_i8gemm (tcgen05 kind::i8)" : (f ? f->name : "k_gemul_thread"), tc, f != nullptr);
     return QB_OK;
 }
 
@@ -392,6 +394,24 @@ extern "C" int qb200_gemul_batched(const qb_gemul_plan *plan, const void *A, con
         else            k_gemul_thread<int64_t><<<(unsigned)blocks, 128, 0, st>>>(dA, dB, dC, n, S, gp.mul, gp.tree, gp.out);
         return post_launch("k_gemul_thread");
     };
+    const bool tc = !(cx.flags & QB_F_NO_TENSOR_CORE) && gemul_tensor_core_ok(*plan, gp, an) && i8gemm_shape_ok(plan->M, plan->N, plan->K);
+    if (tc) {
+        // lossless accumulation: exact int8 x int8 -> int32 dot products on the tensor cores, C's quantizer in the epilogue
+        const size_t bytes_a = span_elems(batch, plan->stride_a, ea) * gp.a_wb, bytes_b = span_elems(batch, plan->stride_b, eb) * gp.b_wb,
+                     bytes_c = span_elems(batch, plan->stride_c, ec) * gp.c_wb;
+        const void *dA, *dB; void *dC; void *Ap, *Bp;
+        if ((rc = cx.in(A, bytes_a, &dA)) || (rc = cx.in(B, bytes_b, &dB)) || (rc = cx.out(C, bytes_c, &dC))) return rc;
+        if ((rc = cx.alloc(&Ap, ea)) || (rc = cx.alloc(&Bp, eb))) return rc;
+        for (uint64_t i = 0; i < batch; i++) {
+            const char *err = "";
+            if (i8gemm_run((const char *)dA + i * plan->stride_a * gp.a_wb, (const char *)dB + i * plan->stride_b * gp.b_wb,
+                           (char *)dC + i * plan->stride_c * gp.c_wb, plan->M, plan->N, plan->K, plan->trans_a, plan->trans_b, gp.a_wb, gp.b_wb,
+                           gp.c_wb, gp.out, (int8_t *)Ap, (int8_t *)Bp, cx.stream, &err))
+                return fail(QB_ECUDA, std::string("k_i8gemm: ") + err);
+        }
+        if ((rc = cx.out_done(C, bytes_c, dC))) return rc;
+        return cx.finish();
+    }
     const bool dense = (plan->stride_a == (int64_t)ea || plan->stride_a == 0) && (plan->stride_b == (int64_t)eb || plan->stride_b == 0) &&
                        plan->stride_c == (int64_t)ec;
     if (cx.host && dense && batch >= 64) {
@@ -521,5 +541,65 @@ extern "C" int qb200_synth_fill(void *dst, uint64_t count, uint32_t wb, int64_t 
     k_synth_fill<<<grid_for(count, 256), 256, 0, cx.stream>>>(d, count, (int)wb, lo, span, key, first_index);
     if ((rc = post_launch("k_synth_fill"))) return rc;
     if ((rc = cx.out_done(dst, count * wb, d))) return rc;
+    return cx.finish();
+}
+
+// ---------------------------------------------------------------------------------------------
+// diagnostic: INT32 issue-rate peak (roofline denominator of the integer-ALU-bound kernels)
+// ---------------------------------------------------------------------------------------------
+template <int NFMA>   // of 8 chains, NFMA are IMAD chains, the rest IADD3+LOP3 chains
+__global__ void __launch_bounds__(256) k_int_peak(int *out, int a, int b, int iters)
+{
+    int x[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) x[c] = threadIdx.x + c * 7 + a;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                if (c < NFMA) x[c] = x[c] * a + b;                 // IMAD
+                else x[c] = ((x[c] + a) ^ b) + it;                 // IADD3 + LOP3 (2 ALU ops)
+            }
+        }
+    }
+    int s = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) s ^= x[c];
+    if (s == 0x7fffffff) out[0] = s;
+}
+
+extern "C" int qb200_measure_int_peak(double fma_share, double *tops, const qb_exec *exec)
+{
+    if (!tops) return fail(QB_EINVAL, "null argument");
+    Ctx cx; int rc = cx.init(exec); if (rc) return rc;
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int *d; if ((rc = cx.alloc((void **)&d, 64))) return rc;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    const int nfma = fma_share <= 0.0 ? 0 : (fma_share >= 1.0 ? 8 : (fma_share < 0.4 ? 2 : (fma_share < 0.6 ? 4 : 6)));
+    const int iters = 2048, grid = sms * 8;
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        CUDA_TRY(cudaEventRecord(e0, cx.stream));
+        switch (nfma) {
+        case 0: k_int_peak<0><<<grid, 256, 0, cx.stream>>>(d, 3, 5, iters); break;
+        case 2: k_int_peak<2><<<grid, 256, 0, cx.stream>>>(d, 3, 5, iters); break;
+        case 4: k_int_peak<4><<<grid, 256, 0, cx.stream>>>(d, 3, 5, iters); break;
+        case 6: k_int_peak<6><<<grid, 256, 0, cx.stream>>>(d, 3, 5, iters); break;
+        default: k_int_peak<8><<<grid, 256, 0, cx.stream>>>(d, 3, 5, iters); break;
+        }
+        if ((rc = post_launch("k_int_peak"))) return rc;
+        CUDA_TRY(cudaEventRecord(e1, cx.stream));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0; CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double ops_per_thread = (double)iters * 8 * (nfma + 2 * (8 - nfma));
+        const double t = ops_per_thread * grid * 256 / (ms * 1e-3) / 1e12;
+        if (t > best) best = t;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *tops = best;
     return cx.finish();
 }

@@ -1,0 +1,81 @@
+"""BASELINE config 5: Qgemul with int8-range operands and lossless wide accumulators on the
+tcgen05 kind::i8 tensor-core path.  Bit-exact against the oracle (small shapes), against the
+integer-ALU kernel (same ABI call with QB_F_NO_TENSOR_CORE) and against an exact float64 GEMM."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from qublas_b200 import abi, ops
+from qublas_b200.qtypes import QType, RND_POS_INF, SAT_TCPL
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def c5_plan(M, N, K, c=None, trans_a=False, trans_b=False, full_prec=False):
+    a = QType(7, 0)
+    acc = QType(30, 0)
+    mul = {"full": True} if full_prec else QType(15, 0)
+    return a, ops.make_gemul_plan(a, a, c or acc, M, N, K, mul=mul, add=[acc], trans_a=trans_a, trans_b=trans_b)
+
+
+@pytest.mark.parametrize("M,N,K,ta,tb", [(128, 256, 128, False, False), (256, 512, 256, False, False), (128, 256, 384, True, False),
+                                         (256, 256, 128, False, True), (384, 256, 256, True, True)])
+def test_i8_tensor_core_vs_oracle(M, N, K, ta, tb):
+    rng = np.random.default_rng(M + N + K)
+    a, plan = c5_plan(M, N, K, trans_a=ta, trans_b=tb)
+    info = ops.plan_info_gemul(plan)
+    assert info.tensor_core == 1 and info.lossless == 1 and b"tcgen05" in info.kernel
+    A = rng.integers(-128, 128, size=M * K).astype(np.int32)
+    B = rng.integers(-128, 128, size=K * N).astype(np.int32)
+    A[:7] = -128; B[:7] = -128                                  # min x min products
+    want = oracle.gemul_batched(plan, A, B, 1)
+    Cd = torch.empty(M * N, dtype=torch.int32, device="cuda")
+    ops.Qgemul(Cd, torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda(), plan)
+    assert np.array_equal(Cd.cpu().numpy(), want)
+    C2 = torch.empty_like(Cd)
+    ops.Qgemul(C2, torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda(), plan, flags=abi.QB_F_NO_TENSOR_CORE)
+    assert torch.equal(Cd, C2)
+
+
+def test_i8_epilogue_quantizes_once_into_c_type():
+    """C narrower than the accumulator: the single quantizer left is the converting assignment."""
+    rng = np.random.default_rng(3)
+    M, N, K = 128, 256, 256
+    c = QType(12, -2, True, RND_POS_INF, SAT_TCPL)              # drops 2 integer LSBs and saturates
+    a, plan = c5_plan(M, N, K, c=c)
+    assert ops.plan_info_gemul(plan).tensor_core == 1
+    A = rng.integers(-128, 128, size=M * K).astype(np.int32)
+    B = rng.integers(-128, 128, size=K * N).astype(np.int32)
+    want = oracle.gemul_batched(plan, A, B, 1)
+    Cd = torch.empty(M * N, dtype=torch.int32, device="cuda")
+    ops.Qgemul(Cd, torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda(), plan)
+    assert np.array_equal(Cd.cpu().numpy(), want)
+    assert (np.abs(want) == c.raw_max).any() or (want == c.raw_min).any()      # saturation was exercised
+
+
+def test_fullprec_product_is_not_lossless_and_stays_on_alu():
+    """Qmul<FullPrec> of two 7.0 types is 14.0 and cannot hold (-128)*(-128): the predicate
+    must refuse the tensor-core path and the ALU path must reproduce the saturated product."""
+    M, N, K = 128, 256, 128
+    a, plan = c5_plan(M, N, K, full_prec=True)
+    info = ops.plan_info_gemul(plan)
+    assert info.tensor_core == 0 and info.lossless == 0
+    A = np.full(M * K, -128, dtype=np.int32); B = np.full(K * N, -128, dtype=np.int32)
+    want = oracle.gemul_batched(plan, A, B, 1)
+    Cd = torch.empty(M * N, dtype=torch.int32, device="cuda")
+    ops.Qgemul(Cd, torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda(), plan)
+    assert np.array_equal(Cd.cpu().numpy(), want) and int(want[0]) == K * 16383
+
+
+def test_i8_large_vs_exact_float64_gemm():
+    """2048^3 (full tiles, many k-blocks, several waves): all partial sums < 2^53, so a float64 GEMM is exact."""
+    M = N = K = 2048
+    a, plan = c5_plan(M, N, K)
+    A = torch.empty(M * K, dtype=torch.int32, device="cuda"); B = torch.empty(K * N, dtype=torch.int32, device="cuda")
+    ops.synth_fill(A, -128, 127, 5, 0); ops.synth_fill(B, -128, 127, 5, 1)
+    Cd = torch.empty(M * N, dtype=torch.int32, device="cuda")
+    ops.Qgemul(Cd, A, B, plan)
+    Am = A.view(K, M).t().double(); Bm = B.view(N, K).t().double()         # column-major views
+    ref = (Am @ Bm).t().contiguous().view(-1)                               # back to column-major
+    assert torch.equal(Cd.double(), ref)
