@@ -309,6 +309,180 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+
+# ------------------------------------------------------------------------------------------------
+# secondary workloads (BASELINE configs 2, 4, 5): same timing discipline, one JSON line each
+# ------------------------------------------------------------------------------------------------
+def run_secondary(args):
+    import numpy as np
+    import torch
+    from oracle import oracle
+    from qublas_b200 import abi, ops
+    from qublas_b200.qtypes import QType, RND_CONV, RND_POS_INF, SAT_TCPL, TREE_VARIADIC, tree_out_type, resolve_tf
+
+    lib = abi.load()
+    if lib.qb200_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    w = args.workload
+
+    def timed(fn):
+        for _ in range(args.warmup):
+            fn()
+        torch.cuda.synchronize()
+        lib.qb200_launch_count_reset()
+        sampler = ClockSampler(0); sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # a step of these kernels lasts ~1 ms: repeat the K-step block so that the clock sampler sees the load
+        t_probe0 = time.perf_counter(); fn(); torch.cuda.synchronize(); probe = max(time.perf_counter() - t_probe0, 1e-5)
+        reps = max(1, int(1.2 / (probe * args.steps)))
+        lib.qb200_launch_count_reset()
+        e0.record()
+        for _ in range(args.steps * reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (args.steps * reps), int(lib.qb200_launch_count()) // reps, sampler.stop()
+
+    def wall(fn, n=2):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / n
+
+    if w == "c2":
+        n, batch = 1 << 24, 16
+        elem = QType(8, 8)
+        lv = [QType(9 + l, 8 - l, True, RND_POS_INF, SAT_TCPL) for l in range(8)]
+        lv += [QType(17 + (l - 7 + 1) // 2, 0, True, RND_POS_INF, SAT_TCPL) for l in range(8, 24)]      # C2b: 24-entry list
+        x = torch.empty(batch * n, dtype=torch.int32, device=dev)
+        ops.synth_fill(x, elem.raw_min, elem.raw_max, 1, 0)
+        out, _ = ops.Qreduce(x, elem, lv, length=n, batch=batch)
+        want, _ = oracle.reduce_batched(ops.make_reduce_plan(elem, lv, n), x[:n].cpu().numpy(), 1)
+        assert int(out.cpu()[0]) == int(want[0]), "Qreduce differs from the oracle"
+        rplan = ops.make_reduce_plan(elem, lv, n)
+        rout = torch.empty(batch, dtype=torch.int32, device=dev)
+        ms, launches, clocks = timed(lambda: ops.Qreduce(x, elem, lv, length=n, batch=batch, plan=rplan, out=rout))
+        units = batch * n
+        value, unit, metric = units / (ms * 1e-3) / 1e9, "Gelem/s", "bit-exact Qreduce throughput, 2^24-element Qu<8,8> vectors, 24-level TypeList (RND::POS_INF)"
+        bytes_alg = units * 4 + batch * 4
+        roof = {"bound": "hbm", "achieved": bytes_alg / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s"}
+        hx = torch.empty(n, dtype=torch.int32).pin_memory(); hx.copy_(x[:n]); hxn = hx.numpy()
+        e2e_s = wall(lambda: ops.Qreduce(hxn, elem, lv))
+        e2e = {"value": n / e2e_s / 1e9, "unit": unit, "h2d_bytes_per_step": n * 4, "d2h_bytes_per_step": 4}
+        cfg = {"workload": "BASELINE config 2 (C2b): Qreduce of 2^24 x Qu<8,8>, per-level TypeList, batch of 16 vectors (1 GiB, > L2)",
+               "kernel": ops.plan_info_reduce(ops.make_reduce_plan(elem, lv, n)).kernel.decode() + " (2 chained passes)"}
+
+        def cpu():
+            libr = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libqref_bench.so"))
+            nb = 1 << 15
+            xs = x[:nb * 512].cpu().numpy(); o = np.zeros(nb, dtype=np.int32)
+            vp = ctypes.c_void_p
+            t0 = time.perf_counter(); libr.qref_c2_reduce512(xs.ctypes.data_as(vp), o.ctypes.data_as(vp), nb); dt = time.perf_counter() - t0
+            return {"value": nb * 512 / dt / 1e9, "unit": unit, "cores": 1, "kind": "reference",
+                    "sample": "2^15 blocks of 512 elements through the header's vector-form Qreduce (levels 0-8 = 99.8% of the adds), 1 core"}
+    elif w == "c4":
+        Mm = Kk = 256
+        batch = args.batch if args.batch != 1000000 else 8192
+        t = QType(3, 12); P = QType(6, 12); S = QType(7, 12)
+        tags = {"abT": QType(4, 12), "cdT": QType(4, 11), "abcT": P, "cdbT": P, "badT": P, "ABT": S, "BCT": S}
+        lv = [QType(8 + l, 12 - l, True, RND_CONV, SAT_TCPL) for l in range(8)]
+        plan = ops.make_cgemul_plan(t, t, t, t, lv[-1], lv[-1], Mm, 1, Kk, tf_tags=tags, add_re=lv, form=TREE_VARIADIC)
+        info = ops.plan_info_cgemul(plan)
+        H = torch.empty(batch * Mm * Kk * 2, dtype=torch.int32, device=dev); xv = torch.empty(batch * Kk * 2, dtype=torch.int32, device=dev)
+        ops.synth_fill(H, -(1 << 14), (1 << 14) - 1, 1, 0); ops.synth_fill(xv, -(1 << 14), (1 << 14) - 1, 1, 1)   # half range
+        y = torch.empty(batch * Mm * 2, dtype=torch.int32, device=dev)
+        ops.Qcgemul(y, H, xv, plan, batch=batch)
+        want = oracle.cgemul_batched(plan, H[:Mm * Kk * 2].cpu().numpy(), xv[:Kk * 2].cpu().numpy(), 1)
+        assert np.array_equal(y[:Mm * 2].cpu().numpy(), want), "complex mat-vec differs from the oracle"
+        ms, launches, clocks = timed(lambda: ops.Qcgemul(y, H, xv, plan, batch=batch))
+        units = batch * Mm * Kk
+        value, unit, metric = units / (ms * 1e-3) / 1e9, "G complex-MAC/s", "bit-exact TFComplexMul (3-mult/5-add) complex mat-vec throughput, batched 256x256"
+        bytes_alg = batch * (Mm * Kk + Kk + Mm) * 8
+        roof = {"bound": "hbm", "achieved": bytes_alg / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "note": "near the HBM / integer-ALU balance point (8 B and ~25 integer ops per complex MAC)"}
+        nb = min(batch, 512)
+        hH = torch.empty(nb * Mm * Kk * 2, dtype=torch.int32).pin_memory(); hH.copy_(H[:nb * Mm * Kk * 2])
+        hx = torch.empty(nb * Kk * 2, dtype=torch.int32).pin_memory(); hx.copy_(xv[:nb * Kk * 2])
+        hy = torch.empty(nb * Mm * 2, dtype=torch.int32).pin_memory()
+        e2e_s = wall(lambda: ops.Qcgemul(hy.numpy(), hH.numpy(), hx.numpy(), plan, batch=nb))
+        e2e = {"value": nb * Mm * Kk / e2e_s / 1e9, "unit": unit, "h2d_bytes_per_step": nb * (Mm * Kk + Kk) * 8, "d2h_bytes_per_step": nb * Mm * 8}
+        cfg = {"workload": "BASELINE config 4: batched 256x256 complex mat-vec, TFComplexMul with mixed abT/cdT types, 8-level RND::CONV tree",
+               "batch": batch, "kernel": info.kernel.decode()}
+
+        def cpu():
+            t0 = time.perf_counter(); oracle.cgemul_batched(plan, H[:4 * Mm * Kk * 2].cpu().numpy(), xv[:4 * Kk * 2].cpu().numpy(), 4); dt = time.perf_counter() - t0
+            return {"value": 4 * Mm * Kk / dt / 1e9, "unit": unit, "cores": 1, "kind": "port", "sample": "4 instances through the C oracle, 1 core"}
+    else:  # c5
+        Mm = Nn = Kk = 8192
+        a = QType(7, 0); acc = QType(30, 0)
+        plan = ops.make_gemul_plan(a, a, acc, Mm, Nn, Kk, mul=QType(15, 0), add=[acc])
+        info = ops.plan_info_gemul(plan)
+        assert info.tensor_core == 1
+        A = torch.empty(Mm * Kk, dtype=torch.int32, device=dev); B = torch.empty(Kk * Nn, dtype=torch.int32, device=dev)
+        ops.synth_fill(A, -128, 127, 1, 0); ops.synth_fill(B, -128, 127, 1, 1)
+        Cd = torch.empty(Mm * Nn, dtype=torch.int32, device=dev)
+        ops.Qgemul(Cd, A, B, plan)
+        rows = torch.arange(0, Mm, 127, device=dev)                                  # exact float64 cross-check on 65 sampled rows
+        ref = (A.view(Kk, Mm).t()[rows].double() @ B.view(Nn, Kk).t().double())
+        assert torch.equal(Cd.view(Nn, Mm).t()[rows].double(), ref), "tensor-core Qgemul differs from the exact float64 GEMM"
+        ms, launches, clocks = timed(lambda: ops.Qgemul(Cd, A, B, plan))
+        ops_total = 2.0 * Mm * Nn * Kk
+        value, unit, metric = ops_total / (ms * 1e-3) / 1e12, "TOP/s", "bit-exact Qgemul 8192^3, int8-range operands, lossless accumulators (tcgen05 kind::i8), incl. int32->int8 pack"
+        # library int8 GEMM on the same box = the measured tensor peak for this dtype
+        A8 = torch.randint(-128, 128, (Mm, Kk), dtype=torch.int8, device=dev); B8 = torch.randint(-128, 128, (Kk, Nn), dtype=torch.int8, device=dev)
+        best = 0.0
+        try:
+            for _ in range(3):
+                torch._int_mm(A8, B8)
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); torch._int_mm(A8, B8); e1.record(); torch.cuda.synchronize()
+                best = max(best, ops_total / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        except Exception:
+            best = 0.0
+        nominal = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
+        roof = {"bound": "tensor", "achieved": value, "peak": best if best > 0 else nominal, "unit": "TOP/s",
+                "peak_source": "torch._int_mm (cuBLASLt int8) 8192^3 on this box" if best > 0 else "2 x measured bf16 (nominal i8:bf16 ratio)",
+                "peak_2x_bf16": nominal}
+        hA = torch.empty(Mm * Kk, dtype=torch.int32).pin_memory(); hA.copy_(A)
+        hB = torch.empty(Kk * Nn, dtype=torch.int32).pin_memory(); hB.copy_(B)
+        hC = torch.empty(Mm * Nn, dtype=torch.int32).pin_memory()
+        e2e_s = wall(lambda: ops.Qgemul(hC.numpy(), hA.numpy(), hB.numpy(), plan))
+        e2e = {"value": ops_total / e2e_s / 1e12, "unit": unit, "h2d_bytes_per_step": 2 * Mm * Kk * 4, "d2h_bytes_per_step": Mm * Nn * 4}
+        cfg = {"workload": "BASELINE config 5: 8192^3 Qgemul, A,B Qu<7,0> raws in [-128,127], MulArgs Qu<15,0>, AddArgs Qu<30,0>, C Qu<30,0>",
+               "kernel": info.kernel.decode()}
+
+        def cpu():
+            pl = ops.make_gemul_plan(a, a, acc, 16, 16, Kk, mul=QType(15, 0), add=[acc])
+            Ah = np.ascontiguousarray(A.view(Kk, Mm)[:, :16].cpu().numpy()).reshape(-1); Bh = B[:16 * Kk].cpu().numpy()
+            t0 = time.perf_counter(); oracle.gemul_batched(pl, Ah, Bh, 1); dt = time.perf_counter() - t0
+            return {"value": 2.0 * 16 * 16 * Kk / dt / 1e12, "unit": unit, "cores": 1, "kind": "port", "sample": "a 16x16x8192 corner through the C oracle, 1 core"}
+
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["traffic"] = None
+    roof.setdefault("peak_source", "MEASURED_PEAKS.json" if peaks else "fallback")
+    line = {"metric": metric, "value": value, "unit": unit, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32" if w != "c5" else "int8 x int8 -> int32",
+            "data": "synthetic", "config": cfg, "roofline": roof, "clocks": clocks, "e2e": e2e, "gpu_launches": launches}
+    if not args.no_cpu:
+        try:
+            line["cpu_baseline"] = cpu()
+        except Exception as ex:      # e.g. oracle/_ref absent
+            line["cpu_baseline"] = {"unavailable": str(ex)}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -319,13 +493,17 @@ def main():
     ap.add_argument("--e2e-chunk", type=int, default=8192, help="instances per host-buffer API call")
     ap.add_argument("--e2e-instances", type=int, default=1000000, help="instances per end-to-end step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5"],
+                    help="c3 = headline (batched 64^3 Qgemul); c2 = Qreduce 2^24; c4 = TFComplexMul 256x256 mat-vec; c5 = 8192^3 tcgen05 i8")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
-    else:
+    elif args.workload == "c3":
         run_ours(args)
+    else:
+        run_secondary(args)
 
 
 if __name__ == "__main__":

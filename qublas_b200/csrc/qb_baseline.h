@@ -45,4 +45,18 @@ inline qb_cgemul_plan baseline_c4()
     return p;
 }
 
+// Config 2: Qreduce of 2^24 x Qu<8,8>; list "a" = 8 entries Qu<9+l,8-l,M,SAT::TCPL> (last reused for levels 8..23),
+// list "b" = 24 entries, Qu<17+ceil((l-7)/2),0,M,SAT::TCPL> for l = 8..23; M = any of the 7 QuModes.
+inline qb_reduce_plan baseline_c2(bool list_b, int mode)
+{
+    qb_reduce_plan p; memset(&p, 0, sizeof(p));
+    p.elem = qd(8, 8);
+    p.levels.n = list_b ? 24 : 8;
+    for (int l = 0; l < 8; l++) p.levels.lv[l] = qd(9 + l, 8 - l, true, mode, QB_SAT_TCPL);
+    if (list_b) for (int l = 8; l < 24; l++) p.levels.lv[l] = qd(17 + (l - 7 + 1) / 2, 0, true, mode, QB_SAT_TCPL);
+    p.len = 1ull << 24;
+    p.tree_form = QB_TREE_VECTOR;
+    return p;
+}
+
 }  // namespace qb

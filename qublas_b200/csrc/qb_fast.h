@@ -24,6 +24,12 @@ struct FastCGemul {
     int (*launch)(const void *A, const void *B, void *C, uint64_t batch, cudaStream_t s);
 };
 
+struct FastReduce {
+    const char *name;
+    qb_reduce_plan plan;
+    int (*launch)(const void *x, void *out, void *scratch, uint64_t batch, cudaStream_t s);      // scratch: batch * 4096 int32
+};
+const FastReduce *find_fast_reduce(const qb_reduce_plan &p, const ReduceProg &r, int arith_bits);
 const FastGemul  *find_fast_gemul(const qb_gemul_plan &p, const GemulProg &g, int arith_bits);
 const FastCGemul *find_fast_cgemul(const qb_cgemul_plan &p, const CGemulProg &g, int arith_bits);
 

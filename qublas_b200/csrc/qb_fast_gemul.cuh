@@ -79,6 +79,24 @@ QB_DEV void stack_push(I (&st)[NTOP > 0 ? NTOP : 1], uint32_t c, I v, I &result)
     }
 }
 
+// Qmul<MulArgs> through the FP32 FMA pipe (see qb_codegen.cpp): returns the quantized product BIASED by
+// the bit pattern of the magic constant; unbias by subtracting fp_kbits<S>() (folded into the first tree add).
+template <int S> __host__ __device__ constexpr int fp_kbits() { return ((150 + S) << 23) | 0x400000; }   // bits of 1.5 * 2^(23+S)
+template <int S, bool CT> QB_DEV int fp_mul_apply(float a, float b, const QStage &q)
+{
+    constexpr float Cm = (float)(3ull << (22 + S));                    // 1.5 * 2^(23+S), exact
+    constexpr float Hf = (float)(1ull << (S - 1));
+    float t;
+    if (q.qu == RND_CONV) t = __fmaf_rn(a, b, Cm);
+    else if (q.qu == RND_POS_INF) t = __fmaf_rd(a, b, Cm + Hf);
+    else if (q.qu == RND_NEG_INF) t = __fmaf_ru(a, b, Cm - Hf);
+    else t = __fmaf_rd(a, b, Cm);                                      // TRN::TCPL
+    int bits = __float_as_int(t);                                      // = fp_kbits + round(a*b / 2^S), monotone in the value
+    if (q.need_hi) bits = imin<int>(bits, (int)q.hi + fp_kbits<S>());
+    if (q.need_lo) bits = imax<int>(bits, (int)q.lo + fp_kbits<S>());
+    return bits;
+}
+
 template <class Cfg>
 __global__ void __launch_bounds__(GemulTile<Cfg, 4, 4>::THREADS, 2)
 k_gemul_tile(const int32_t *__restrict__ A, const int32_t *__restrict__ B, int32_t *__restrict__ C, uint64_t batch)
@@ -118,8 +136,22 @@ k_gemul_tile(const int32_t *__restrict__ A, const int32_t *__restrict__ B, int32
     for (uint32_t it = 0; inst < batch; inst += gridDim.x, ++it) {
         const int s = it & 1;
         const uint64_t next = inst + gridDim.x;
-        if (tid == 0 && next < batch) issue(next, s ^ 1);        // stage s^1 was released by the barrier below
+        if (tid == 0 && next < batch) {
+            if constexpr (Cfg::FP_MUL) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes (int->float) before TMA refill
+            issue(next, s ^ 1);                                   // stage s^1 was released by the barrier below
+        }
         mbar_wait(&bars[s], (it >> 1) & 1);
+        if constexpr (Cfg::FP_MUL) {
+            // operands become exact floats once per instance (1 conversion per 32 MACs)
+            int4 *w = (int4 *)(stage0 + (size_t)s * (T::STAGE_BYTES / 4));
+#pragma unroll
+            for (int i = tid; i < (T::A_WORDS + T::B_WORDS) / 4; i += T::THREADS) {
+                int4 v = w[i];
+                float4 f = make_float4(__int2float_rn(v.x), __int2float_rn(v.y), __int2float_rn(v.z), __int2float_rn(v.w));
+                ((float4 *)w)[i] = f;
+            }
+            __syncthreads();
+        }
 
         const int32_t *As = stage0 + (size_t)s * (T::STAGE_BYTES / 4);
         const int32_t *Bs = As + T::A_WORDS;
@@ -145,12 +177,24 @@ k_gemul_tile(const int32_t *__restrict__ A, const int32_t *__restrict__ B, int32
 #pragma unroll
                     for (int ii = 0; ii < 4; ++ii) {
                         const I a0 = (&aq[0].x)[ii], a1 = (&aq[1].x)[ii], a2 = (&aq[2].x)[ii], a3 = (&aq[3].x)[ii];
-                        I p0 = mul_apply<I, true>(a0, b0, mulq);
-                        I p1 = mul_apply<I, true>(a1, b1, mulq);
-                        I p2 = mul_apply<I, true>(a2, b2, mulq);
-                        I p3 = mul_apply<I, true>(a3, b3, mulq);
-                        I s01 = merge_apply<I, true>(p0, p1, l0);
-                        I s23 = merge_apply<I, true>(p2, p3, l0);
+                        I s01, s23;
+                        if constexpr (Cfg::FP_MUL) {
+                            constexpr int S = Cfg::FP_SHIFT;
+                            constexpr uint32_t KB2 = 2u * (uint32_t)fp_kbits<S>();
+                            const int p0 = fp_mul_apply<S, true>(__int_as_float(a0), __int_as_float(b0), mulq);
+                            const int p1 = fp_mul_apply<S, true>(__int_as_float(a1), __int_as_float(b1), mulq);
+                            const int p2 = fp_mul_apply<S, true>(__int_as_float(a2), __int_as_float(b2), mulq);
+                            const int p3 = fp_mul_apply<S, true>(__int_as_float(a3), __int_as_float(b3), mulq);
+                            s01 = q_apply<I, true>((I)((uint32_t)p0 + (uint32_t)p1 - KB2), l0.q);       // unbias folded into the level-0 add
+                            s23 = q_apply<I, true>((I)((uint32_t)p2 + (uint32_t)p3 - KB2), l0.q);
+                        } else {
+                            I p0 = mul_apply<I, true>(a0, b0, mulq);
+                            I p1 = mul_apply<I, true>(a1, b1, mulq);
+                            I p2 = mul_apply<I, true>(a2, b2, mulq);
+                            I p3 = mul_apply<I, true>(a3, b3, mulq);
+                            s01 = merge_apply<I, true>(p0, p1, l0);
+                            s23 = merge_apply<I, true>(p2, p3, l0);
+                        }
                         half[h][ii][jj] = merge_apply<I, true>(s01, s23, l1);
                     }
                 }

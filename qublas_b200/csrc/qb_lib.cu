@@ -6,7 +6,9 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <memory>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/qb200.h"
@@ -50,9 +52,13 @@ struct Ctx {
     std::vector<void *> to_free;
     int init(const qb_exec *ex)
     {
-        int n = 0;
-        cudaError_t e = cudaGetDeviceCount(&n);
-        if (e != cudaSuccess || n == 0) { cudaGetLastError(); return fail(QB_ENODEVICE, "no CUDA device available (there is no CPU fallback)"); }
+        static int n_dev = -1;
+        if (n_dev <= 0) {
+            int n = 0;
+            cudaError_t e = cudaGetDeviceCount(&n);
+            if (e != cudaSuccess || n == 0) { cudaGetLastError(); return fail(QB_ENODEVICE, "no CUDA device available (there is no CPU fallback)"); }
+            n_dev = n;
+        }
         if (ex) {
             if (ex->device >= 0) CUDA_TRY(cudaSetDevice(ex->device));
             stream = (cudaStream_t)ex->stream;
@@ -200,6 +206,65 @@ static void fill_info(qb_plan_info *info, const Analysis &an, qb_qdesc out_t, in
 }
 
 // ---------------------------------------------------------------------------------------------
+// compiled-plan cache: a plan is compiled (types resolved, intervals analysed, kernel selected) once
+// per process; later calls with the same plan bytes cost one hash lookup.
+// ---------------------------------------------------------------------------------------------
+struct ReduceC { ReduceProg prog; Analysis an; int bits; const FastReduce *fast; };
+struct GemulC  { GemulProg prog; Analysis an; int bits; const FastGemul *fast; bool tc; };
+struct CGemulC { CGemulProg prog; Analysis an; int bits; const FastCGemul *fast; };
+
+template <class Plan, class Entry, class Build>
+static std::shared_ptr<Entry> cached(const Plan &p, Build build)
+{
+    static std::mutex mu;
+    static std::unordered_map<std::string, std::shared_ptr<Entry>> map;
+    std::string key((const char *)&p, sizeof(Plan));
+    {
+        std::lock_guard<std::mutex> l(mu);
+        auto it = map.find(key);
+        if (it != map.end()) return it->second;
+    }
+    auto e = std::make_shared<Entry>();
+    build(*e);
+    std::lock_guard<std::mutex> l(mu);
+    if (map.size() > 4096) map.clear();
+    map[key] = e;
+    return e;
+}
+
+static std::shared_ptr<ReduceC> get_reduce(const qb_reduce_plan &p)
+{
+    return cached<qb_reduce_plan, ReduceC>(p, [&](ReduceC &e) {
+        compile_reduce(p, &e.prog, e.an);
+        e.bits = arith_bits(e.an); e.fast = nullptr;
+        if (!e.an.status) { if (e.bits == 32) sanitize32(e.prog.tree); e.fast = find_fast_reduce(p, e.prog, e.bits); }
+    });
+}
+static std::shared_ptr<GemulC> get_gemul(const qb_gemul_plan &p)
+{
+    return cached<qb_gemul_plan, GemulC>(p, [&](GemulC &e) {
+        compile_gemul(p, &e.prog, e.an);
+        e.bits = arith_bits(e.an); e.fast = nullptr; e.tc = false;
+        if (!e.an.status) {
+            if (e.bits == 32) { sanitize32_stage(e.prog.mul); sanitize32(e.prog.tree); sanitize32_stage(e.prog.out); }
+            e.fast = find_fast_gemul(p, e.prog, e.bits);
+            e.tc = gemul_tensor_core_ok(p, e.prog, e.an) && i8gemm_shape_ok(p.M, p.N, p.K);
+        }
+    });
+}
+static std::shared_ptr<CGemulC> get_cgemul(const qb_cgemul_plan &p)
+{
+    return cached<qb_cgemul_plan, CGemulC>(p, [&](CGemulC &e) {
+        compile_cgemul(p, &e.prog, e.an);
+        e.bits = arith_bits(e.an); e.fast = nullptr;
+        if (!e.an.status) {
+            if (e.bits == 32) { sanitize32(e.prog.tf); sanitize32(e.prog.tree_re); sanitize32(e.prog.tree_im); sanitize32_stage(e.prog.out_re); sanitize32_stage(e.prog.out_im); }
+            e.fast = find_fast_cgemul(p, e.prog, e.bits);
+        }
+    });
+}
+
+// ---------------------------------------------------------------------------------------------
 // misc entry points
 // ---------------------------------------------------------------------------------------------
 extern "C" int qb200_abi_version(void) { return QB200_ABI_VERSION; }
@@ -237,9 +302,10 @@ static const char *reduce_kernel_name(const qb_reduce_plan *p)
 extern "C" int qb200_reduce_plan_info(const qb_reduce_plan *plan, qb_plan_info *info)
 {
     if (!plan || !info) return fail(QB_EINVAL, "null argument");
-    ReduceProg rp; Analysis an;
-    if (compile_reduce(*plan, &rp, an)) return fail(an.status, an.err);
-    fill_info(info, an, rp.out.t, rp.out_wb, reduce_kernel_name(plan), 0, 0);
+    auto ce = get_reduce(*plan);
+    if (ce->an.status) return fail(ce->an.status, ce->an.err);
+    const ReduceProg &rp = ce->prog; const Analysis &an = ce->an; const FastReduce *fr = ce->fast;
+    fill_info(info, an, rp.out.t, rp.out_wb, fr ? fr->name : reduce_kernel_name(plan), 0, fr != nullptr);
     return QB_OK;
 }
 
@@ -315,23 +381,31 @@ extern "C" int qb200_reduce_batched(const qb_reduce_plan *plan, const void *x, v
                                     uint32_t partial_level, uint64_t batch, const qb_exec *exec)
 {
     if (!plan || !x || !out) return fail(QB_EINVAL, "null argument");
-    ReduceProg rp; Analysis an;
-    if (compile_reduce(*plan, &rp, an)) return fail(an.status, an.err);
+    auto ce = get_reduce(*plan);
+    if (ce->an.status) return fail(ce->an.status, ce->an.err);
+    const ReduceProg &rp = ce->prog; const Analysis &an = ce->an;
     if (partials) {
         if (plan->tree_form != QB_TREE_VECTOR) return fail(QB_EINVAL, "partials are defined for the vector form only");
         if (partial_level != 0 && partial_level < 8) return fail(QB_EINVAL, "partial_level must be 0 or >= 8");
         if (partial_level > ceil_log2(plan->len)) return fail(QB_EINVAL, "partial_level above the root");
     }
     if (batch == 0) return QB_OK;
-    if (arith_bits(an) == 32) sanitize32(rp.tree);
     Ctx cx; int rc = cx.init(exec); if (rc) return rc;
     uint64_t per = plan->len; for (uint32_t l = 0; l < partial_level; l++) per = (per + 1) / 2;
     const void *dx; void *dout, *dpart = nullptr;
     if ((rc = cx.in(x, batch * plan->len * rp.elem_wb, &dx))) return rc;
     if ((rc = cx.out(out, batch * rp.out_wb, &dout))) return rc;
     if (partials && (rc = cx.out(partials, batch * per * 8, &dpart))) return rc;
-    rc = arith_bits(an) == 32 ? run_reduce<int32_t>(plan, rp, dx, dout, dpart, partial_level, batch, cx)
-                              : run_reduce<int64_t>(plan, rp, dx, dout, dpart, partial_level, batch, cx);
+    const FastReduce *fr = (partials || (cx.flags & QB_F_NO_SPECIALIZE) || ((uintptr_t)dx & 15)) ? nullptr : ce->fast;
+    if (fr) {
+        void *scratch;
+        if ((rc = cx.alloc(&scratch, batch * 4096 * sizeof(int32_t)))) return rc;
+        int e = fr->launch(dx, dout, scratch, batch, cx.stream);
+        rc = e ? fail(QB_ECUDA, std::string(fr->name) + " launch failed: " + cudaGetErrorString((cudaError_t)e)) : QB_OK;
+    } else {
+        rc = arith_bits(an) == 32 ? run_reduce<int32_t>(plan, rp, dx, dout, dpart, partial_level, batch, cx)
+                                  : run_reduce<int64_t>(plan, rp, dx, dout, dpart, partial_level, batch, cx);
+    }
     if (rc) return rc;
     if ((rc = cx.out_done(out, batch * rp.out_wb, dout))) return rc;
     if (partials && (rc = cx.out_done(partials, batch * per * 8, dpart))) return rc;
@@ -357,11 +431,11 @@ static size_t span_elems(uint64_t batch, int64_t stride, uint64_t per)
 extern "C" int qb200_gemul_plan_info(const qb_gemul_plan *plan, qb_plan_info *info)
 {
     if (!plan || !info) return fail(QB_EINVAL, "null argument");
-    GemulProg gp; Analysis an;
-    if (compile_gemul(*plan, &gp, an)) return fail(an.status, an.err);
-    const FastGemul *f = find_fast_gemul(*plan, gp, arith_bits(an));
+    auto ce = get_gemul(*plan);
+    if (ce->an.status) return fail(ce->an.status, ce->an.err);
+    const GemulProg &gp = ce->prog; const Analysis &an = ce->an; const FastGemul *f = ce->fast;
     qb_qdesc ct = plan->c; ct.word_bytes = 0;
-    const bool tc = gemul_tensor_core_ok(*plan, gp, an) && i8gemm_shape_ok(plan->M, plan->N, plan->K);
+    const bool tc = ce->tc;
     fill_info(info, an, ct, gp.c_wb, tc ? "k_i8gemm (tcgen05 kind::i8)" : (f ? f->name : "k_gemul_thread"), tc, f != nullptr);
     return QB_OK;
 }
@@ -370,16 +444,16 @@ extern "C" int qb200_gemul_batched(const qb_gemul_plan *plan, const void *A, con
                                    const qb_exec *exec)
 {
     if (!plan || !A || !B || !C) return fail(QB_EINVAL, "null argument");
-    GemulProg gp; Analysis an;
-    if (compile_gemul(*plan, &gp, an)) return fail(an.status, an.err);
+    auto ce = get_gemul(*plan);
+    if (ce->an.status) return fail(ce->an.status, ce->an.err);
+    const GemulProg &gp = ce->prog;
     if (plan->stride_a < 0 || plan->stride_b < 0 || plan->stride_c < (int64_t)((uint64_t)plan->M * plan->N))
         return fail(QB_EINVAL, "bad batch strides");
     if (batch == 0) return QB_OK;
     Ctx cx; int rc = cx.init(exec); if (rc) return rc;
     const uint64_t ea = (uint64_t)plan->M * plan->K, eb = (uint64_t)plan->K * plan->N, ec = (uint64_t)plan->M * plan->N;
-    const int bits = arith_bits(an);
-    if (bits == 32) { sanitize32_stage(gp.mul); sanitize32(gp.tree); sanitize32_stage(gp.out); }
-    const FastGemul *f = (cx.flags & QB_F_NO_SPECIALIZE) ? nullptr : find_fast_gemul(*plan, gp, bits);
+    const int bits = ce->bits;
+    const FastGemul *f = (cx.flags & QB_F_NO_SPECIALIZE) ? nullptr : ce->fast;
     // one launch over n instances laid out with the given strides
     auto launch = [&](const void *dA, const void *dB, void *dC, uint64_t n, int64_t sa, int64_t sb, int64_t sc, cudaStream_t st) -> int {
         if (f && sa == (int64_t)ea && sb == (int64_t)eb && sc == (int64_t)ec) {
@@ -394,7 +468,7 @@ extern "C" int qb200_gemul_batched(const qb_gemul_plan *plan, const void *A, con
         else            k_gemul_thread<int64_t><<<(unsigned)blocks, 128, 0, st>>>(dA, dB, dC, n, S, gp.mul, gp.tree, gp.out);
         return post_launch("k_gemul_thread");
     };
-    const bool tc = !(cx.flags & QB_F_NO_TENSOR_CORE) && gemul_tensor_core_ok(*plan, gp, an) && i8gemm_shape_ok(plan->M, plan->N, plan->K);
+    const bool tc = !(cx.flags & QB_F_NO_TENSOR_CORE) && ce->tc;
     if (tc) {
         // lossless accumulation: exact int8 x int8 -> int32 dot products on the tensor cores, C's quantizer in the epilogue
         const size_t bytes_a = span_elems(batch, plan->stride_a, ea) * gp.a_wb, bytes_b = span_elems(batch, plan->stride_b, eb) * gp.b_wb,
@@ -435,9 +509,9 @@ extern "C" int qb200_gemul_batched(const qb_gemul_plan *plan, const void *A, con
 extern "C" int qb200_cgemul_plan_info(const qb_cgemul_plan *plan, qb_plan_info *info)
 {
     if (!plan || !info) return fail(QB_EINVAL, "null argument");
-    CGemulProg gp; Analysis an;
-    if (compile_cgemul(*plan, &gp, an)) return fail(an.status, an.err);
-    const FastCGemul *f = find_fast_cgemul(*plan, gp, arith_bits(an));
+    auto ce = get_cgemul(*plan);
+    if (ce->an.status) return fail(ce->an.status, ce->an.err);
+    const CGemulProg &gp = ce->prog; const Analysis &an = ce->an; const FastCGemul *f = ce->fast;
     qb_qdesc ct = plan->c_re; ct.word_bytes = 0;
     fill_info(info, an, ct, gp.c_wb, f ? f->name : "k_cgemul_thread", 0, f != nullptr);
     return QB_OK;
@@ -447,8 +521,9 @@ extern "C" int qb200_cgemul_batched(const qb_cgemul_plan *plan, const void *A, c
                                     const qb_exec *exec)
 {
     if (!plan || !A || !B || !C) return fail(QB_EINVAL, "null argument");
-    CGemulProg gp; Analysis an;
-    if (compile_cgemul(*plan, &gp, an)) return fail(an.status, an.err);
+    auto ce = get_cgemul(*plan);
+    if (ce->an.status) return fail(ce->an.status, ce->an.err);
+    const CGemulProg &gp = ce->prog;
     if (plan->stride_a < 0 || plan->stride_b < 0 || plan->stride_c < (int64_t)((uint64_t)plan->M * plan->N))
         return fail(QB_EINVAL, "bad batch strides");
     if (batch == 0) return QB_OK;
@@ -458,9 +533,8 @@ extern "C" int qb200_cgemul_batched(const qb_cgemul_plan *plan, const void *A, c
                  bytes_c = 2 * span_elems(batch, plan->stride_c, ec) * gp.c_wb;
     const void *dA, *dB; void *dC;
     if ((rc = cx.in(A, bytes_a, &dA)) || (rc = cx.in(B, bytes_b, &dB)) || (rc = cx.out(C, bytes_c, &dC))) return rc;
-    const int bits = arith_bits(an);
-    if (bits == 32) { sanitize32(gp.tf); sanitize32(gp.tree_re); sanitize32(gp.tree_im); sanitize32_stage(gp.out_re); sanitize32_stage(gp.out_im); }
-    const FastCGemul *f = (cx.flags & QB_F_NO_SPECIALIZE) ? nullptr : find_fast_cgemul(*plan, gp, bits);
+    const int bits = ce->bits;
+    const FastCGemul *f = (cx.flags & QB_F_NO_SPECIALIZE) ? nullptr : ce->fast;
     if (f) {
         rc = f->launch(dA, dB, dC, batch, cx.stream);
         if (rc) return fail(QB_ECUDA, std::string(f->name) + " launch failed: " + cudaGetErrorString((cudaError_t)rc));

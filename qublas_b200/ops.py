@@ -107,10 +107,12 @@ def make_reduce_plan(elem: QType, levels: Optional[Sequence[QType]], length: int
 
 
 def Qreduce(x, elem: QType, levels: Optional[Sequence[QType]] = None, *, length: Optional[int] = None, batch: int = 1,
-            form: int = TREE_VECTOR, partial_level: Optional[int] = None, word_bytes: int = 0, flags: int = 0):
+            form: int = TREE_VECTOR, partial_level: Optional[int] = None, word_bytes: int = 0, flags: int = 0,
+            plan: Optional[abi.qb_reduce_plan] = None, out=None):
     """Tree reduction of `batch` vectors of `length` elements (default: the whole buffer is one vector).
 
-    Returns (out, out_type) or (out, out_type, partials) when partial_level is given.
+    Returns (out, out_type) or (out, out_type, partials) when partial_level is given.  `plan` (from
+    make_reduce_plan) and `out` may be passed in to keep repeated calls allocation-free.
     """
     total = x.numel() if _is_torch(x) else x.size
     if length is None:
@@ -118,9 +120,11 @@ def Qreduce(x, elem: QType, levels: Optional[Sequence[QType]] = None, *, length:
     if length * batch != total:
         raise ValueError("buffer size does not match batch * length")
     _check_words(x, _wb(elem, word_bytes), "x")
-    plan = make_reduce_plan(elem, levels, length, form, word_bytes)
+    if plan is None:
+        plan = make_reduce_plan(elem, levels, length, form, word_bytes)
     ot = tree_out_type(length, elem, list(levels or []), form)
-    out = _new_like(x, batch, ot.word_bytes)
+    if out is None:
+        out = _new_like(x, batch, ot.word_bytes)
     parts = None
     if partial_level is not None:
         per = length

@@ -41,7 +41,9 @@ def test_struct_layout_matches_header(tmp_path):
 def test_plan_info_reduce_c2():
     lv = [QType(9 + l, 8 - l, True, RND_POS_INF, SAT_TCPL) for l in range(8)]
     info = ops.plan_info_reduce(ops.make_reduce_plan(QType(8, 8), lv, 1 << 24))
-    assert info.arith_bits == 32 and info.kernel == b"k_reduce_warp"
+    assert info.arith_bits == 32 and info.kernel == b"k_reduce_ct<C2a,POS_INF>" and info.specialized == 1
+    other = ops.plan_info_reduce(ops.make_reduce_plan(QType(8, 8), lv, (1 << 24) - 1))
+    assert other.kernel == b"k_reduce_warp" and other.specialized == 0
     assert abi.qtype_of(info.out_type) == lv[-1] and info.out_word_bytes == 4
     assert not info.lossless
 

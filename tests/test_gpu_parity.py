@@ -270,6 +270,25 @@ def test_c2_reduce_2p24_all_modes(mode):
         assert ot == lv[-1]
 
 
+@pytest.mark.parametrize("mode", range(7))
+def test_c2_specialised_kernel_matches_oracle_and_generic(mode):
+    """The compile-time-specialised Qreduce (no partials requested) against the oracle and against the
+    runtime-descriptor kernel, batch of 3 vectors, both level lists."""
+    n, batch = 1 << 24, 3
+    elem = QType(8, 8)
+    x = torch.empty(batch * n, dtype=torch.int32, device="cuda")
+    ops.synth_fill(x, elem.raw_min, elem.raw_max, seed=2, stream_id=mode)
+    c2a = [QType(9 + l, 8 - l, True, mode, SAT_TCPL) for l in range(8)]
+    c2b = c2a + [QType(17 + (l - 7 + 1) // 2, 0, True, mode, SAT_TCPL) for l in range(8, 24)]
+    for lv in (c2a, c2b):
+        assert ops.plan_info_reduce(ops.make_reduce_plan(elem, lv, n)).specialized == 1
+        out, _ = ops.Qreduce(x, elem, lv, length=n, batch=batch)
+        gen, _ = ops.Qreduce(x, elem, lv, length=n, batch=batch, flags=abi.QB_F_NO_SPECIALIZE)
+        assert torch.equal(out, gen)
+        want, _ = oracle.reduce_batched(reduce_plan(elem, lv, n), x[n:2 * n].cpu().numpy(), 1)
+        assert int(out.cpu()[1]) == int(want[0])
+
+
 def test_c3_batched_64cubed_vs_oracle_and_shard_edges():
     """Config 3 at reduced batch against the oracle (first/last instances of a shard), full types."""
     a = QType(7, 8)
