@@ -203,6 +203,11 @@ int qb200_synth_fill(void *dst, uint64_t count, uint32_t word_bytes, int64_t lo,
  * integer figure).  fma_share in [0,1] = fraction of IMAD instructions in the mix. */
 int qb200_measure_int_peak(double fma_share, double *tera_ops_per_s, const qb_exec *exec);
 
+/* Diagnostic: run-time specialisation (NVRTC) of a Qgemul plan, compile step only (no device needed).
+ * Returns 0 if a cubin was produced, 1 if the plan does not fit the specialised kernel template,
+ * -1 if NVRTC is unavailable or compilation failed (message in `log`). */
+int qb200_jit_check_gemul(const qb_gemul_plan *plan, char *log, uint64_t log_cap);
+
 /* Contiguous shard [first, first+count) of `total` units for `rank` of `world` (batch or M-panel). */
 int qb200_shard_range(uint64_t total, uint32_t world, uint32_t rank, uint64_t *first, uint64_t *count);
 

@@ -100,7 +100,7 @@ ABI_SYMBOLS = [
     "qb200_abi_version", "qb200_last_error", "qb200_device_count", "qb200_launch_count",
     "qb200_launch_count_reset", "qb200_reduce_plan_info", "qb200_gemul_plan_info", "qb200_cgemul_plan_info",
     "qb200_reduce_batched", "qb200_gemul_batched", "qb200_cgemul_batched", "qb200_tfcmul_batched",
-    "qb200_convert_batched", "qb200_synth_fill", "qb200_shard_range", "qb200_measure_int_peak",
+    "qb200_convert_batched", "qb200_synth_fill", "qb200_shard_range", "qb200_measure_int_peak", "qb200_jit_check_gemul",
 ]
 
 _LIB = None
@@ -136,6 +136,7 @@ def load() -> C.CDLL:
     L.qb200_convert_batched.argtypes = [C.POINTER(qb_convert_plan), vp, vp, u64, C.POINTER(qb_exec)]
     L.qb200_synth_fill.argtypes = [vp, u64, u32, i64, i64, u64, u64, u64, C.POINTER(qb_exec)]
     L.qb200_shard_range.argtypes = [u64, u32, u32, C.POINTER(u64), C.POINTER(u64)]
+    L.qb200_jit_check_gemul.argtypes = [C.POINTER(qb_gemul_plan), C.c_char_p, u64]
     L.qb200_measure_int_peak.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(qb_exec)]
     for name in ABI_SYMBOLS:
         getattr(L, name)

@@ -48,19 +48,18 @@ std::string emit_gemul_cfg(const std::string &name, const qb_gemul_plan &p, cons
     o << emit_levels("lvl", g.tree, ilog2(p.K));
     // FP32-FMA product quantizer: fma(a, b, 1.5 * 2^(23+s)) is exact-product-plus-one-IEEE-rounding at a
     // granularity of 2^s, i.e. Qmul's rounded right shift by s in ONE instruction on the FMA pipe
-    // (round-to-nearest-even == RND::CONV, toward -inf with +half == RND::POS_INF, toward +inf with
-    // -half == RND::NEG_INF, toward -inf == TRN::TCPL).  Legal iff the operands are exact floats and
-    // |a*b| (+half) stays within the binade [2^(23+s), 2^(24+s)] around the magic constant.
+    // (round-to-nearest-even == RND::CONV, round toward -inf == TRN::TCPL; the half-up / half-down modes
+    // would need C +- 2^(s-1), which is below the ulp of C and not representable, so they stay on the
+    // integer path).  Legal iff the operands are exact floats and |a*b| stays within the binade
+    // [2^(23+s), 2^(24+s)] around the magic constant.
     {
         const int s = g.mul.shift;
         const Ival ra = type_range(p.a), rb = type_range(p.b);
         const i128 c4[4] = { ra.lo * rb.lo, ra.lo * rb.hi, ra.hi * rb.lo, ra.hi * rb.hi };
         i128 lo = c4[0], hi = c4[0];
         for (int i = 1; i < 4; i++) { if (c4[i] < lo) lo = c4[i]; if (c4[i] > hi) hi = c4[i]; }
-        const bool mode_ok = g.mul.qu == RND_CONV || g.mul.qu == RND_POS_INF || g.mul.qu == RND_NEG_INF || g.mul.qu == TRN_TCPL;
-        const i128 half = s > 0 ? ((i128)1 << (s - 1)) : 0;
-        const i128 adj = (g.mul.qu == RND_POS_INF || g.mul.qu == RND_NEG_INF) ? half : 0;
-        const i128 mag = (hi > -lo ? hi : -lo) + adj;
+        const bool mode_ok = g.mul.qu == RND_CONV || g.mul.qu == TRN_TCPL;
+        const i128 mag = (hi > -lo ? hi : -lo);
         const bool ops_ok = width(p.a) <= 24 && width(p.b) <= 24;
         const bool of_ok = g.mul.of == SAT_TCPL || g.mul.of == SAT_SMGN;
         const bool fp = s >= 1 && s <= 30 && mode_ok && ops_ok && of_ok && !g.mul.wide && mag <= ((i128)1 << (22 + s));

@@ -34,8 +34,7 @@ QB_DEV void cstack_push(I (&sr)[NTOP > 0 ? NTOP : 1], I (&si)[NTOP > 0 ? NTOP : 
 }
 
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::M)
-k_cgemv_rows(const int2 *__restrict__ H, const int2 *__restrict__ X, int2 *__restrict__ Y, uint64_t batch)
+QB_DEV void cgemv_rows_body(const int2 *__restrict__ H, const int2 *__restrict__ X, int2 *__restrict__ Y, uint64_t batch)
 {
     typedef typename Cfg::I I;
     constexpr int M = Cfg::M, K = Cfg::K, NTOP = Cfg::NLEV - 3;
@@ -92,6 +91,14 @@ k_cgemv_rows(const int2 *__restrict__ H, const int2 *__restrict__ X, int2 *__res
 }
 
 template <class Cfg>
+__global__ void __launch_bounds__(Cfg::M)
+k_cgemv_rows(const int2 *__restrict__ H, const int2 *__restrict__ X, int2 *__restrict__ Y, uint64_t batch)
+{
+    cgemv_rows_body<Cfg>(H, X, Y, batch);
+}
+
+#ifndef QB_JIT
+template <class Cfg>
 static int launch_cgemv_rows(const void *A, const void *B, void *C, uint64_t batch, cudaStream_t s)
 {
     static int grid_cap = 0;
@@ -109,5 +116,7 @@ static int launch_cgemv_rows(const void *A, const void *B, void *C, uint64_t bat
     if (e == cudaSuccess) count_launch(1);
     return (int)e;
 }
+
+#endif  // QB_JIT
 
 }  // namespace qb

@@ -85,12 +85,8 @@ template <int S> __host__ __device__ constexpr int fp_kbits() { return ((150 + S
 template <int S, bool CT> QB_DEV int fp_mul_apply(float a, float b, const QStage &q)
 {
     constexpr float Cm = (float)(3ull << (22 + S));                    // 1.5 * 2^(23+S), exact
-    constexpr float Hf = (float)(1ull << (S - 1));
-    float t;
-    if (q.qu == RND_CONV) t = __fmaf_rn(a, b, Cm);
-    else if (q.qu == RND_POS_INF) t = __fmaf_rd(a, b, Cm + Hf);
-    else if (q.qu == RND_NEG_INF) t = __fmaf_ru(a, b, Cm - Hf);
-    else t = __fmaf_rd(a, b, Cm);                                      // TRN::TCPL
+    const float t = q.qu == RND_CONV ? __fmaf_rn(a, b, Cm)             // one IEEE round-to-nearest-even at ulp 2^S
+                                     : __fmaf_rd(a, b, Cm);            // TRN::TCPL: round toward -inf
     int bits = __float_as_int(t);                                      // = fp_kbits + round(a*b / 2^S), monotone in the value
     if (q.need_hi) bits = imin<int>(bits, (int)q.hi + fp_kbits<S>());
     if (q.need_lo) bits = imax<int>(bits, (int)q.lo + fp_kbits<S>());
@@ -98,8 +94,7 @@ template <int S, bool CT> QB_DEV int fp_mul_apply(float a, float b, const QStage
 }
 
 template <class Cfg>
-__global__ void __launch_bounds__(GemulTile<Cfg, 4, 4>::THREADS, 2)
-k_gemul_tile(const int32_t *__restrict__ A, const int32_t *__restrict__ B, int32_t *__restrict__ C, uint64_t batch)
+QB_DEV void gemul_tile_body(const int32_t *__restrict__ A, const int32_t *__restrict__ B, int32_t *__restrict__ C, uint64_t batch)
 {
     typedef GemulTile<Cfg, 4, 4> T;
     typedef typename T::I I;
@@ -223,6 +218,14 @@ k_gemul_tile(const int32_t *__restrict__ A, const int32_t *__restrict__ B, int32
 }
 
 template <class Cfg>
+__global__ void __launch_bounds__(GemulTile<Cfg, 4, 4>::THREADS, (GemulTile<Cfg, 4, 4>::THREADS <= 256 ? 2 : 1))
+k_gemul_tile(const int32_t *__restrict__ A, const int32_t *__restrict__ B, int32_t *__restrict__ C, uint64_t batch)
+{
+    gemul_tile_body<Cfg>(A, B, C, batch);
+}
+
+#ifndef QB_JIT
+template <class Cfg>
 static int launch_gemul_tile(const void *A, const void *B, void *C, uint64_t batch, cudaStream_t s)
 {
     typedef GemulTile<Cfg, 4, 4> T;
@@ -243,5 +246,7 @@ static int launch_gemul_tile(const void *A, const void *B, void *C, uint64_t bat
     if (e == cudaSuccess) count_launch(1);
     return (int)e;
 }
+
+#endif  // QB_JIT
 
 }  // namespace qb

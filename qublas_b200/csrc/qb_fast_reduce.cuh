@@ -36,8 +36,7 @@ template <typename I> QB_DEV I shfl_xor_ct(I v, int m)
 
 // x: batch * n_in words (int32), n_in a multiple of 2^PW.  out: one node per chunk (int32).
 template <class Cfg, int LEV0, int PW>
-__global__ void __launch_bounds__(256)
-k_reduce_ct(const int32_t *__restrict__ x, int32_t *__restrict__ out, uint64_t total_chunks)
+QB_DEV void reduce_ct_body(const int32_t *__restrict__ x, int32_t *__restrict__ out, uint64_t total_chunks)
 {
     typedef typename Cfg::I I;
     constexpr int NSUB = 1 << (PW - 8), NTOP = PW - 8, U = NSUB < 4 ? NSUB : 4;
@@ -77,6 +76,14 @@ k_reduce_ct(const int32_t *__restrict__ x, int32_t *__restrict__ out, uint64_t t
     }
 }
 
+template <class Cfg, int LEV0, int PW>
+__global__ void __launch_bounds__(256)
+k_reduce_ct(const int32_t *__restrict__ x, int32_t *__restrict__ out, uint64_t total_chunks)
+{
+    reduce_ct_body<Cfg, LEV0, PW>(x, out, total_chunks);
+}
+
+#ifndef QB_JIT
 // Two chained passes for len = 2^LOGN (LOGN in [16, 24]): pass 1 PW1 = 12, pass 2 covers the rest.
 template <class Cfg>
 static int launch_reduce_ct(const void *x, void *out, void *scratch, uint64_t batch, cudaStream_t s)
@@ -95,5 +102,7 @@ static int launch_reduce_ct(const void *x, void *out, void *scratch, uint64_t ba
     if (e == cudaSuccess) count_launch(2);
     return (int)e;
 }
+
+#endif  // QB_JIT
 
 }  // namespace qb

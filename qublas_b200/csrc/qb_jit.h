@@ -1,0 +1,39 @@
+// qb_jit.h — run-time specialisation of the kernel templates with NVRTC.
+//
+// The AOT registry (qb_fast.cu) covers the BASELINE configurations; every other plan whose shape
+// fits a specialised kernel template gets its own instantiation at first use: qb_codegen prints the
+// compiled program as a tag struct, NVRTC compiles `kernel<Tag>` for sm_100a, the cubin is loaded
+// through the driver API and cached with the compiled plan.  This is the literal form of "the host
+// side lowers each Qu type's compile-time parameters into kernel template arguments".
+// If NVRTC is not available the library falls back to the runtime-descriptor CUDA kernels
+// (still the GPU — never a CPU path).  QB200_NO_JIT=1 disables it.
+#pragma once
+#include <cuda_runtime.h>
+#include <memory>
+#include <string>
+#include "qb_plan.h"
+
+namespace qb {
+
+struct JitKernel {
+    void *module = nullptr;        // CUmodule
+    void *func[2] = { nullptr, nullptr };   // CUfunction(s)
+    unsigned threads = 0, smem = 0;
+    int blocks_per_sm = 1, sms = 0;
+    std::string name, log;
+    bool ok = false;
+};
+
+bool jit_enabled();
+// Each returns nullptr when the plan does not fit the template or when compilation fails.
+std::shared_ptr<JitKernel> jit_gemul(const qb_gemul_plan &p, const GemulProg &g, int arith_bits);
+std::shared_ptr<JitKernel> jit_cgemul(const qb_cgemul_plan &p, const CGemulProg &g, int arith_bits);
+std::shared_ptr<JitKernel> jit_reduce(const qb_reduce_plan &p, const ReduceProg &r, int arith_bits);
+
+int jit_check_gemul(const qb_gemul_plan &p, const GemulProg &g, int arith_bits, std::string &log);
+
+// launches; return 0 or a CUresult / cudaError code
+int jit_launch_gemul(const JitKernel &k, const void *A, const void *B, void *C, uint64_t batch, cudaStream_t s);
+int jit_launch_reduce(const JitKernel &k, unsigned logn, const void *x, void *out, void *scratch, uint64_t batch, cudaStream_t s);
+
+}  // namespace qb

@@ -16,6 +16,7 @@
 #include "qb_kernels.cuh"
 #include "qb_fast.h"
 #include "qb_i8gemm.h"
+#include "qb_jit.h"
 
 using namespace qb;
 
@@ -209,9 +210,9 @@ static void fill_info(qb_plan_info *info, const Analysis &an, qb_qdesc out_t, in
 // compiled-plan cache: a plan is compiled (types resolved, intervals analysed, kernel selected) once
 // per process; later calls with the same plan bytes cost one hash lookup.
 // ---------------------------------------------------------------------------------------------
-struct ReduceC { ReduceProg prog; Analysis an; int bits; const FastReduce *fast; };
-struct GemulC  { GemulProg prog; Analysis an; int bits; const FastGemul *fast; bool tc; };
-struct CGemulC { CGemulProg prog; Analysis an; int bits; const FastCGemul *fast; };
+struct ReduceC { ReduceProg prog; Analysis an; int bits; const FastReduce *fast; std::once_flag jit_once; std::shared_ptr<JitKernel> jit; };
+struct GemulC  { GemulProg prog; Analysis an; int bits; const FastGemul *fast; bool tc; std::once_flag jit_once; std::shared_ptr<JitKernel> jit; };
+struct CGemulC { CGemulProg prog; Analysis an; int bits; const FastCGemul *fast; std::once_flag jit_once; std::shared_ptr<JitKernel> jit; };
 
 template <class Plan, class Entry, class Build>
 static std::shared_ptr<Entry> cached(const Plan &p, Build build)
@@ -397,11 +398,22 @@ extern "C" int qb200_reduce_batched(const qb_reduce_plan *plan, const void *x, v
     if ((rc = cx.out(out, batch * rp.out_wb, &dout))) return rc;
     if (partials && (rc = cx.out(partials, batch * per * 8, &dpart))) return rc;
     const FastReduce *fr = (partials || (cx.flags & QB_F_NO_SPECIALIZE) || ((uintptr_t)dx & 15)) ? nullptr : ce->fast;
+    JitKernel *jk = nullptr;
+    if (!fr && !partials && !(cx.flags & QB_F_NO_SPECIALIZE) && !((uintptr_t)dx & 15)) {
+        std::call_once(ce->jit_once, [&] { ce->jit = jit_reduce(*plan, rp, arith_bits(an)); });
+        if (ce->jit && ce->jit->ok) jk = ce->jit.get();
+    }
     if (fr) {
         void *scratch;
         if ((rc = cx.alloc(&scratch, batch * 4096 * sizeof(int32_t)))) return rc;
         int e = fr->launch(dx, dout, scratch, batch, cx.stream);
         rc = e ? fail(QB_ECUDA, std::string(fr->name) + " launch failed: " + cudaGetErrorString((cudaError_t)e)) : QB_OK;
+    } else if (jk) {
+        void *scratch;
+        if ((rc = cx.alloc(&scratch, batch * 4096 * sizeof(int32_t)))) return rc;
+        unsigned logn = 0; while ((1ull << logn) < plan->len) logn++;
+        int e = jit_launch_reduce(*jk, logn, dx, dout, scratch, batch, cx.stream);
+        rc = e ? fail(QB_ECUDA, "k_reduce_ct<jit> launch failed (CUresult " + std::to_string(e) + ")") : QB_OK;
     } else {
         rc = arith_bits(an) == 32 ? run_reduce<int32_t>(plan, rp, dx, dout, dpart, partial_level, batch, cx)
                                   : run_reduce<int64_t>(plan, rp, dx, dout, dpart, partial_level, batch, cx);
@@ -436,7 +448,9 @@ extern "C" int qb200_gemul_plan_info(const qb_gemul_plan *plan, qb_plan_info *in
     const GemulProg &gp = ce->prog; const Analysis &an = ce->an; const FastGemul *f = ce->fast;
     qb_qdesc ct = plan->c; ct.word_bytes = 0;
     const bool tc = ce->tc;
-    fill_info(info, an, ct, gp.c_wb, tc ? "k_i8gemm (tcgen05 kind::i8)" : (f ? f->name : "k_gemul_thread"), tc, f != nullptr);
+    const bool jit_built = ce->jit && ce->jit->ok;
+    fill_info(info, an, ct, gp.c_wb, tc ? "k_i8gemm (tcgen05 kind::i8)" : (f ? f->name : (jit_built ? "k_gemul_tile<jit>" : "k_gemul_thread")), tc,
+              f != nullptr || jit_built);
     return QB_OK;
 }
 
@@ -454,11 +468,21 @@ extern "C" int qb200_gemul_batched(const qb_gemul_plan *plan, const void *A, con
     const uint64_t ea = (uint64_t)plan->M * plan->K, eb = (uint64_t)plan->K * plan->N, ec = (uint64_t)plan->M * plan->N;
     const int bits = ce->bits;
     const FastGemul *f = (cx.flags & QB_F_NO_SPECIALIZE) ? nullptr : ce->fast;
+    JitKernel *jk = nullptr;
+    if (!f && !ce->tc && !(cx.flags & QB_F_NO_SPECIALIZE) && plan->stride_a == (int64_t)ea && plan->stride_b == (int64_t)eb && plan->stride_c == (int64_t)ec) {
+        std::call_once(ce->jit_once, [&] { ce->jit = jit_gemul(*plan, gp, bits); });
+        if (ce->jit && ce->jit->ok) jk = ce->jit.get();
+    }
     // one launch over n instances laid out with the given strides
     auto launch = [&](const void *dA, const void *dB, void *dC, uint64_t n, int64_t sa, int64_t sb, int64_t sc, cudaStream_t st) -> int {
         if (f && sa == (int64_t)ea && sb == (int64_t)eb && sc == (int64_t)ec) {
             int e = f->launch(dA, dB, dC, n, st);
             if (e) return fail(QB_ECUDA, std::string(f->name) + " launch failed: " + cudaGetErrorString((cudaError_t)e));
+            return QB_OK;
+        }
+        if (jk && sa == (int64_t)ea && sb == (int64_t)eb && sc == (int64_t)ec && !((uintptr_t)dA & 15) && !((uintptr_t)dB & 15) && !((uintptr_t)dC & 15)) {
+            int e = jit_launch_gemul(*jk, dA, dB, dC, n, st);
+            if (e) return fail(QB_ECUDA, "k_gemul_tile<jit> launch failed (CUresult " + std::to_string(e) + ")");
             return QB_OK;
         }
         GemulShape S = shape_of(plan->M, plan->N, plan->K, plan->trans_a, plan->trans_b, gp.a_wb, gp.b_wb, gp.c_wb, sa, sb, sc);
@@ -535,9 +559,17 @@ extern "C" int qb200_cgemul_batched(const qb_cgemul_plan *plan, const void *A, c
     if ((rc = cx.in(A, bytes_a, &dA)) || (rc = cx.in(B, bytes_b, &dB)) || (rc = cx.out(C, bytes_c, &dC))) return rc;
     const int bits = ce->bits;
     const FastCGemul *f = (cx.flags & QB_F_NO_SPECIALIZE) ? nullptr : ce->fast;
+    JitKernel *jk = nullptr;
+    if (!f && !(cx.flags & QB_F_NO_SPECIALIZE) && plan->stride_a == (int64_t)ea && plan->stride_b == (int64_t)eb && plan->stride_c == (int64_t)ec) {
+        std::call_once(ce->jit_once, [&] { ce->jit = jit_cgemul(*plan, gp, bits); });
+        if (ce->jit && ce->jit->ok) jk = ce->jit.get();
+    }
     if (f) {
         rc = f->launch(dA, dB, dC, batch, cx.stream);
         if (rc) return fail(QB_ECUDA, std::string(f->name) + " launch failed: " + cudaGetErrorString((cudaError_t)rc));
+    } else if (jk) {
+        int e = jit_launch_gemul(*jk, dA, dB, dC, batch, cx.stream);
+        if (e) return fail(QB_ECUDA, "k_cgemv_rows<jit> launch failed (CUresult " + std::to_string(e) + ")");
     } else {
         GemulShape S = shape_of(plan->M, plan->N, plan->K, plan->trans_a, plan->trans_b, gp.a_wb, gp.b_wb, gp.c_wb,
                                 plan->stride_a, plan->stride_b, plan->stride_c);
@@ -676,4 +708,18 @@ extern "C" int qb200_measure_int_peak(double fma_share, double *tops, const qb_e
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     *tops = best;
     return cx.finish();
+}
+
+// ---------------------------------------------------------------------------------------------
+// diagnostic: compile (NVRTC only, no device needed) the run-time specialisation of a Qgemul plan
+// ---------------------------------------------------------------------------------------------
+extern "C" int qb200_jit_check_gemul(const qb_gemul_plan *plan, char *log, uint64_t log_cap)
+{
+    if (!plan) return fail(QB_EINVAL, "null argument");
+    auto ce = get_gemul(*plan);
+    if (ce->an.status) return fail(ce->an.status, ce->an.err);
+    std::string l;
+    int rc = jit_check_gemul(*plan, ce->prog, ce->bits, l);
+    if (log && log_cap) { snprintf(log, (size_t)log_cap, "%s", l.c_str()); }
+    return rc;
 }

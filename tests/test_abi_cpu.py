@@ -114,3 +114,21 @@ def test_compute_fails_loudly_without_gpu():
     with pytest.raises(abi.QbError) as e:
         ops.Qreduce(x, QType(8, 8), [QType(9, 8)])
     assert e.value.code == abi.QB_ENODEVICE and "no CPU fallback" in str(e.value)
+
+
+def test_jit_specialisation_compiles_without_a_device():
+    """Run-time specialisation: codegen + NVRTC produce an sm_100a cubin for arbitrary plans (no GPU needed)."""
+    import ctypes
+    lib = abi.load()
+    log = ctypes.create_string_buffer(8192)
+    rng = np.random.default_rng(0)
+    for (M, N, K) in [(32, 16, 32), (64, 64, 64), (16, 32, 8)]:
+        a = QType(int(rng.integers(3, 8)), int(rng.integers(2, 8)), True, int(rng.integers(0, 7)), int(rng.integers(0, 4)))
+        mul = QType(a.i * 2, a.f, True, int(rng.integers(0, 7)), int(rng.integers(0, 4)))
+        lv = [QType(mul.i + l, max(mul.f - l, 0), True, int(rng.integers(0, 7)), int(rng.integers(0, 4))) for l in range(4)]
+        plan = ops.make_gemul_plan(a, a, lv[-1], M, N, K, mul=mul, add=lv)
+        rc = lib.qb200_jit_check_gemul(ctypes.byref(plan), log, 8192)
+        assert rc == 0, log.value.decode()
+    # shapes the tile template cannot take are reported as "not applicable", not as errors
+    plan = ops.make_gemul_plan(QType(7, 8), QType(7, 8), QType(17, 4), 5, 7, 12, mul=QType(14, 8))
+    assert lib.qb200_jit_check_gemul(ctypes.byref(plan), log, 8192) == 1

@@ -314,6 +314,65 @@ def test_c3_batched_64cubed_vs_oracle_and_shard_edges():
     assert np.array_equal(Cd[:8192].cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("seed", range(3))
+def test_jit_specialised_kernels_vs_oracle(seed):
+    """Plans outside the AOT registry get an NVRTC-specialised kernel at first use: Qgemul tiles,
+    complex mat-vec and power-of-two Qreduce, each against the oracle and the runtime-descriptor kernel."""
+    rng = np.random.default_rng(4000 + seed)
+    # Qgemul
+    for (M, N, K) in [(32, 32, 16), (64, 32, 64), (16, 64, 128)]:
+        a = QType(int(rng.integers(3, 8)), int(rng.integers(3, 9)), True, 5, 0)
+        b = QType(int(rng.integers(3, 8)), int(rng.integers(3, 9)), True, 5, 0)
+        mul = QType(a.i + b.i - 1, max(a.f, b.f), True, int(rng.integers(0, 7)), int(rng.integers(0, 4)))
+        lv = _rand_levels(rng, mul, int(rng.choice([1, 3, 7])))
+        cc = QType(lv[-1].i, max(lv[-1].f - 1, 1 - lv[-1].i), True, int(rng.integers(0, 7)), int(rng.integers(0, 4)))
+        plan = gemul_plan(a, b, mul, cc, lv, M, N, K)
+        batch = 5
+        A = rand_words(rng, a, batch * M * K); B = rand_words(rng, b, batch * K * N)
+        want = oracle.gemul_batched(plan, A, B, batch)
+        Cd = torch.empty(batch * M * N, dtype=torch.int32 if cc.word_bytes == 4 else torch.int64, device="cuda")
+        try:
+            ops.Qgemul(Cd, dev(A), dev(B), plan, batch=batch)
+        except abi.QbError as e:
+            assert e.code == abi.QB_EDOMAIN
+            continue
+        assert np.array_equal(Cd.cpu().numpy(), want), (M, N, K, a, b, mul, lv, cc)
+        if cc.word_bytes == 4 and ops.plan_info_gemul(plan).arith_bits == 32:
+            assert b"jit" in ops.plan_info_gemul(plan).kernel
+    # Qreduce, power-of-two lengths
+    for n in (1 << 16, 1 << 18, 1 << 20):
+        elem = QType(int(rng.integers(4, 9)), int(rng.integers(3, 9)), True, int(rng.integers(0, 7)), int(rng.integers(0, 4)))
+        lv = _rand_levels(rng, elem, int(rng.choice([2, 6, 20])))
+        x = rand_words(rng, elem, n * 2)
+        want, _ = oracle.reduce_batched(reduce_plan(elem, lv, n), x, 2)
+        try:
+            out, _ = ops.Qreduce(dev(x), elem, lv, length=n, batch=2)
+            gen, _ = ops.Qreduce(dev(x), elem, lv, length=n, batch=2, flags=abi.QB_F_NO_SPECIALIZE)
+        except abi.QbError as e:
+            assert e.code == abi.QB_EDOMAIN
+            continue
+        assert np.array_equal(out.cpu().numpy(), want) and torch.equal(out, gen), (n, elem, lv)
+    # complex mat-vec with random TF tags
+    def rt():
+        return QType(int(rng.integers(2, 6)), int(rng.integers(4, 10)), True, int(rng.integers(0, 7)), int(rng.integers(0, 4)))
+    ar, br = rt(), rt()
+    tags = {k: QType(int(rng.integers(6, 12)), int(rng.integers(4, 10)), True, int(rng.integers(0, 7)), int(rng.integers(0, 4)))
+            for k in ("abT", "cdT", "abcT", "cdbT", "badT", "ABT", "BCT")}
+    r = resolve_tf(ar, ar, br, br, tags)
+    lre = _rand_levels(rng, r["AB"], 6); lim = _rand_levels(rng, r["BC"], 6)
+    M, K, batch = 64, 32, 3
+    plan = cgemul_plan(ar, ar, br, br, tags, lre, lim, QType(12, 3, True, 4, 0), QType(12, 3, True, 1, 2), M, 1, K, form=TREE_VARIADIC)
+    A = np.stack([rand_words(rng, ar, batch * M * K), rand_words(rng, ar, batch * M * K)], axis=1).astype(np.int32).reshape(-1)
+    B = np.stack([rand_words(rng, br, batch * K), rand_words(rng, br, batch * K)], axis=1).astype(np.int32).reshape(-1)
+    want = oracle.cgemul_batched(plan, A, B, batch)
+    Cd = torch.empty(batch * M * 2, dtype=torch.int32, device="cuda")
+    try:
+        ops.Qcgemul(Cd, dev(A), dev(B), plan, batch=batch)
+        assert np.array_equal(Cd.cpu().numpy(), want)
+    except abi.QbError as e:
+        assert e.code == abi.QB_EDOMAIN
+
+
 def test_synth_fill_matches_oracle_all_word_sizes():
     for wb, lo, hi in [(1, -127, 127), (2, -(1 << 15), (1 << 15) - 1), (4, -65536, 65535), (8, -(1 << 40), (1 << 40))]:
         t = torch.empty(10007, dtype={1: torch.int8, 2: torch.int16, 4: torch.int32, 8: torch.int64}[wb], device="cuda")
