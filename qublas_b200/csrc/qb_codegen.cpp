@@ -63,6 +63,12 @@ std::string emit_gemul_cfg(const std::string &name, const qb_gemul_plan &p, cons
         const bool ops_ok = width(p.a) <= 24 && width(p.b) <= 24;
         const bool of_ok = g.mul.of == SAT_TCPL || g.mul.of == SAT_SMGN;
         const bool fp = s >= 1 && s <= 30 && mode_ok && ops_ok && of_ok && !g.mul.wide && mag <= ((i128)1 << (22 + s));
+        // conservative product thresholds for the per-instance clamp elision (qb_fast_gemul.cuh):
+        // round(p) <= floor(p / 2^s) + 1 and round(p) >= floor(p / 2^s)
+        long long p_hi, p_lo;
+        if (s > 0) { p_hi = (long long)(((i128)g.mul.hi << s) - 1); p_lo = (long long)((i128)g.mul.lo << s); }
+        else       { p_hi = g.mul.hi >> (-s); p_lo = -((-(g.mul.lo)) >> (-s)); }
+        o << "  static constexpr long long P_HI = " << p_hi << "LL, P_LO = " << p_lo << "LL;\n";
         o << "  static constexpr bool FP_MUL = " << (fp ? "true" : "false") << ";\n";
         o << "  static constexpr int FP_SHIFT = " << (s > 0 ? s : 1) << ";\n";
     }

@@ -93,15 +93,79 @@ template <int S, bool CT> QB_DEV int fp_mul_apply(float a, float b, const QStage
     return bits;
 }
 
+constexpr QStage stage_without_clamps(QStage q) { q.need_lo = 0; q.need_hi = 0; return q; }
+
+// One instance's 4x4 register tile.  CLAMP = false is the same arithmetic with Qmul's saturation removed;
+// it is selected per instance when the instance's own operand ranges prove that no product can saturate.
+template <class Cfg, bool CLAMP>
+QB_DEV void tile_compute(const int32_t *As, const int32_t *Bs, int i0, int j0, typename Cfg::I (&res)[4][4])
+{
+    typedef GemulTile<Cfg, 4, 4> T;
+    typedef typename T::I I;
+    constexpr int M = T::M, K = T::K, NTOP = T::NTOP;
+    constexpr QStage mulq = CLAMP ? Cfg::mul() : stage_without_clamps(Cfg::mul());
+    constexpr AddStage l0 = Cfg::lvl(0), l1 = Cfg::lvl(1), l2 = Cfg::lvl(2);
+    const int4 *As4 = (const int4 *)As;
+    const int4 *Bs4 = (const int4 *)Bs;
+    I st[4][4][NTOP > 0 ? NTOP : 1];
+#pragma unroll 1
+    for (uint32_t c = 0; c < (uint32_t)T::NCH; ++c) {
+        I half0[4][4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k0 = c * 8 + h * 4;
+            int4 bq[4], aq[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) bq[jj] = Bs4[((j0 + jj) * K + k0) >> 2];      // B[k0..k0+3, j]
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) aq[kk] = As4[((k0 + kk) * M + i0) >> 2];      // A[i0..i0+3, k]
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const I b0 = bq[jj].x, b1 = bq[jj].y, b2 = bq[jj].z, b3 = bq[jj].w;
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) {
+                    const I a0 = (&aq[0].x)[ii], a1 = (&aq[1].x)[ii], a2 = (&aq[2].x)[ii], a3 = (&aq[3].x)[ii];
+                    I s01, s23;
+                    if constexpr (Cfg::FP_MUL) {
+                        constexpr int S = Cfg::FP_SHIFT;
+                        constexpr uint32_t KB2 = 2u * (uint32_t)fp_kbits<S>();
+                        const int p0 = fp_mul_apply<S, true>(__int_as_float(a0), __int_as_float(b0), mulq);
+                        const int p1 = fp_mul_apply<S, true>(__int_as_float(a1), __int_as_float(b1), mulq);
+                        const int p2 = fp_mul_apply<S, true>(__int_as_float(a2), __int_as_float(b2), mulq);
+                        const int p3 = fp_mul_apply<S, true>(__int_as_float(a3), __int_as_float(b3), mulq);
+                        s01 = q_apply<I, true>((I)((uint32_t)p0 + (uint32_t)p1 - KB2), l0.q);       // unbias folded into the level-0 add
+                        s23 = q_apply<I, true>((I)((uint32_t)p2 + (uint32_t)p3 - KB2), l0.q);
+                    } else {
+                        I p0 = mul_apply<I, true>(a0, b0, mulq);
+                        I p1 = mul_apply<I, true>(a1, b1, mulq);
+                        I p2 = mul_apply<I, true>(a2, b2, mulq);
+                        I p3 = mul_apply<I, true>(a3, b3, mulq);
+                        s01 = merge_apply<I, true>(p0, p1, l0);
+                        s23 = merge_apply<I, true>(p2, p3, l0);
+                    }
+                    const I hv = merge_apply<I, true>(s01, s23, l1);
+                    if (h == 0) {
+                        half0[ii][jj] = hv;
+                    } else {
+                        const I v = merge_apply<I, true>(half0[ii][jj], hv, l2);
+                        stack_push<Cfg, 0, NTOP, I>(st[ii][jj], c, v, res[ii][jj]);
+                    }
+                }
+            }
+        }
+    }
+}
+
 template <class Cfg>
 QB_DEV void gemul_tile_body(const int32_t *__restrict__ A, const int32_t *__restrict__ B, int32_t *__restrict__ C, uint64_t batch)
 {
     typedef GemulTile<Cfg, 4, 4> T;
     typedef typename T::I I;
-    constexpr int M = T::M, N = T::N, K = T::K, NTOP = T::NTOP;
+    constexpr int M = T::M, N = T::N;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     int32_t *stage0 = (int32_t *)smem_raw;
     uint64_t *bars = (uint64_t *)(smem_raw + 2 * T::STAGE_BYTES);
+    __shared__ int range_smem[32][4];
 
     const int tid = threadIdx.x;
     const int tx = tid % (M / 4), ty = tid / (M / 4);
@@ -126,7 +190,12 @@ QB_DEV void gemul_tile_body(const int32_t *__restrict__ A, const int32_t *__rest
 
     constexpr QStage mulq = Cfg::mul();
     constexpr QStage outq = Cfg::out();
-    constexpr AddStage l0 = Cfg::lvl(0), l1 = Cfg::lvl(1), l2 = Cfg::lvl(2);
+    // Dynamic clamp elision: Qmul's SAT clamp survives the static interval analysis only because of extreme
+    // operand values (config 3: min x min).  One pass over the staged instance finds its actual operand
+    // ranges; if even the extreme corner products stay inside [P_LO, P_HI] (host-computed, conservative),
+    // the clamp-free instantiation runs.  Same bits either way.
+    constexpr bool DYN = (mulq.need_lo || mulq.need_hi) && (mulq.of == SAT_TCPL || mulq.of == SAT_SMGN);
+    constexpr bool PASS = DYN || Cfg::FP_MUL;
 
     for (uint32_t it = 0; inst < batch; inst += gridDim.x, ++it) {
         const int s = it & 1;
@@ -136,71 +205,55 @@ QB_DEV void gemul_tile_body(const int32_t *__restrict__ A, const int32_t *__rest
             issue(next, s ^ 1);                                   // stage s^1 was released by the barrier below
         }
         mbar_wait(&bars[s], (it >> 1) & 1);
-        if constexpr (Cfg::FP_MUL) {
-            // operands become exact floats once per instance (1 conversion per 32 MACs)
-            int4 *w = (int4 *)(stage0 + (size_t)s * (T::STAGE_BYTES / 4));
+        int32_t *As = stage0 + (size_t)s * (T::STAGE_BYTES / 4);
+        int32_t *Bs = As + T::A_WORDS;
+        bool clamp = true;
+        if constexpr (PASS) {
+            // one pass over the staged operands: exact int->float conversion (FP_MUL) and per-instance ranges (DYN)
+            int lo[2] = { 0x7fffffff, 0x7fffffff }, hi[2] = { (int)0x80000000, (int)0x80000000 };
 #pragma unroll
-            for (int i = tid; i < (T::A_WORDS + T::B_WORDS) / 4; i += T::THREADS) {
-                int4 v = w[i];
-                float4 f = make_float4(__int2float_rn(v.x), __int2float_rn(v.y), __int2float_rn(v.z), __int2float_rn(v.w));
-                ((float4 *)w)[i] = f;
+            for (int part = 0; part < 2; ++part) {
+                int4 *w = (int4 *)(part ? Bs : As);
+                const int n4 = (part ? T::B_WORDS : T::A_WORDS) / 4;
+                for (int i = tid; i < n4; i += T::THREADS) {
+                    const int4 v = w[i];
+                    if constexpr (DYN) {
+                        lo[part] = imin<int>(imin<int>(imin<int>(lo[part], v.x), imin<int>(v.y, v.z)), v.w);
+                        hi[part] = imax<int>(imax<int>(imax<int>(hi[part], v.x), imax<int>(v.y, v.z)), v.w);
+                    }
+                    if constexpr (Cfg::FP_MUL)
+                        ((float4 *)w)[i] = make_float4(__int2float_rn(v.x), __int2float_rn(v.y), __int2float_rn(v.z), __int2float_rn(v.w));
+                }
+            }
+            if constexpr (DYN) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    lo[0] = imin<int>(lo[0], __shfl_xor_sync(0xffffffffu, lo[0], o)); hi[0] = imax<int>(hi[0], __shfl_xor_sync(0xffffffffu, hi[0], o));
+                    lo[1] = imin<int>(lo[1], __shfl_xor_sync(0xffffffffu, lo[1], o)); hi[1] = imax<int>(hi[1], __shfl_xor_sync(0xffffffffu, hi[1], o));
+                }
+                if ((tid & 31) == 0) { range_smem[tid >> 5][0] = lo[0]; range_smem[tid >> 5][1] = hi[0]; range_smem[tid >> 5][2] = lo[1]; range_smem[tid >> 5][3] = hi[1]; }
             }
             __syncthreads();
+            if constexpr (DYN) {
+                int alo = 0x7fffffff, ahi = (int)0x80000000, blo = 0x7fffffff, bhi = (int)0x80000000;
+#pragma unroll
+                for (int wv = 0; wv < T::THREADS / 32; ++wv) {
+                    alo = imin<int>(alo, range_smem[wv][0]); ahi = imax<int>(ahi, range_smem[wv][1]);
+                    blo = imin<int>(blo, range_smem[wv][2]); bhi = imax<int>(bhi, range_smem[wv][3]);
+                }
+                const long long c0 = (long long)alo * blo, c1 = (long long)alo * bhi, c2 = (long long)ahi * blo, c3 = (long long)ahi * bhi;
+                const long long pmax = imax<long long>(imax<long long>(c0, c1), imax<long long>(c2, c3));
+                const long long pmin = imin<long long>(imin<long long>(c0, c1), imin<long long>(c2, c3));
+                clamp = (mulq.need_hi && pmax > Cfg::P_HI) || (mulq.need_lo && pmin < Cfg::P_LO);
+            }
         }
 
-        const int32_t *As = stage0 + (size_t)s * (T::STAGE_BYTES / 4);
-        const int32_t *Bs = As + T::A_WORDS;
-        const int4 *As4 = (const int4 *)As;
-        const int4 *Bs4 = (const int4 *)Bs;
-
-        I st[4][4][NTOP > 0 ? NTOP : 1];
         I res[4][4];
-#pragma unroll 1
-        for (uint32_t c = 0; c < (uint32_t)T::NCH; ++c) {
-            I half[2][4][4];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int k0 = c * 8 + h * 4;
-                int4 bq[4], aq[4];
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) bq[jj] = Bs4[((j0 + jj) * K + k0) >> 2];      // B[k0..k0+3, j]
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) aq[kk] = As4[((k0 + kk) * M + i0) >> 2];      // A[i0..i0+3, k]
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    const I b0 = bq[jj].x, b1 = bq[jj].y, b2 = bq[jj].z, b3 = bq[jj].w;
-#pragma unroll
-                    for (int ii = 0; ii < 4; ++ii) {
-                        const I a0 = (&aq[0].x)[ii], a1 = (&aq[1].x)[ii], a2 = (&aq[2].x)[ii], a3 = (&aq[3].x)[ii];
-                        I s01, s23;
-                        if constexpr (Cfg::FP_MUL) {
-                            constexpr int S = Cfg::FP_SHIFT;
-                            constexpr uint32_t KB2 = 2u * (uint32_t)fp_kbits<S>();
-                            const int p0 = fp_mul_apply<S, true>(__int_as_float(a0), __int_as_float(b0), mulq);
-                            const int p1 = fp_mul_apply<S, true>(__int_as_float(a1), __int_as_float(b1), mulq);
-                            const int p2 = fp_mul_apply<S, true>(__int_as_float(a2), __int_as_float(b2), mulq);
-                            const int p3 = fp_mul_apply<S, true>(__int_as_float(a3), __int_as_float(b3), mulq);
-                            s01 = q_apply<I, true>((I)((uint32_t)p0 + (uint32_t)p1 - KB2), l0.q);       // unbias folded into the level-0 add
-                            s23 = q_apply<I, true>((I)((uint32_t)p2 + (uint32_t)p3 - KB2), l0.q);
-                        } else {
-                            I p0 = mul_apply<I, true>(a0, b0, mulq);
-                            I p1 = mul_apply<I, true>(a1, b1, mulq);
-                            I p2 = mul_apply<I, true>(a2, b2, mulq);
-                            I p3 = mul_apply<I, true>(a3, b3, mulq);
-                            s01 = merge_apply<I, true>(p0, p1, l0);
-                            s23 = merge_apply<I, true>(p2, p3, l0);
-                        }
-                        half[h][ii][jj] = merge_apply<I, true>(s01, s23, l1);
-                    }
-                }
-            }
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-                for (int ii = 0; ii < 4; ++ii) {
-                    I v = merge_apply<I, true>(half[0][ii][jj], half[1][ii][jj], l2);
-                    stack_push<Cfg, 0, NTOP, I>(st[ii][jj], c, v, res[ii][jj]);
-                }
+        if constexpr (DYN) {
+            if (clamp) tile_compute<Cfg, true>(As, Bs, i0, j0, res);
+            else       tile_compute<Cfg, false>(As, Bs, i0, j0, res);
+        } else {
+            tile_compute<Cfg, true>(As, Bs, i0, j0, res);
         }
         // converting assignment into C's element type, column-major 128-bit stores
         int32_t *Ci = C + inst * (uint64_t)(M * N);
@@ -213,7 +266,7 @@ QB_DEV void gemul_tile_body(const int32_t *__restrict__ A, const int32_t *__rest
             o.w = (int32_t)conv_apply<I, true>(res[3][jj], outq);
             *(int4 *)(Ci + (j0 + jj) * M + i0) = o;
         }
-        __syncthreads();      // everyone is done reading stage s before it is refilled
+        __syncthreads();      // everyone is done reading stage s (and range_smem) before it is refilled
     }
 }
 

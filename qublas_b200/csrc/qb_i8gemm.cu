@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include "qb_device.cuh"
 #include "qb_fast.h"
 #include "qb_i8gemm.h"
@@ -56,6 +57,23 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
 {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(s32(dst)), "l"(map), "r"(s32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, uint16_t mask)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+                 ::"r"(s32(dst)), "l"(map), "r"(s32(bar)), "h"(mask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t n_clusters_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(s32(bar)), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -112,9 +130,12 @@ struct I8Params {
     uint32_t group_m;             // rasterisation: group_m m-tiles share each B panel while it is hot in L2
 };
 
-__global__ void __launch_bounds__(I8_THREADS, 1)
-k_i8gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, void *__restrict__ C,
-         const __grid_constant__ I8Params P, const __grid_constant__ QStage outq)
+// MC = false: one CTA per tile, plain TMA.
+// MC = true : clusters of two CTAs that work on vertically adjacent tiles (same n-tile): each CTA loads its own
+//             A tile and ONE HALF of the shared B tile, multicast into both CTAs' shared memory, which cuts the
+//             L2->SM traffic per MMA by a third (48 KB -> 32 KB per 128x256x128 block).
+template <bool MC>
+__device__ __forceinline__ void i8gemm_body(const CUtensorMap &mapA, const CUtensorMap &mapB, void *__restrict__ C, const I8Params &P, const QStage &outq)
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // SWIZZLE_128B atoms need 1024-byte alignment
@@ -124,11 +145,12 @@ k_i8gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUten
     uint32_t *tmem_slot = (uint32_t *)(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t ntiles = P.tiles_m * P.tiles_n;
     const uint32_t nkb = P.K / BK;
 
+    const uint32_t rank = MC ? cluster_ctarank() : 0;
+    const uint32_t worker = MC ? cluster_id_x() : blockIdx.x, n_workers = MC ? n_clusters_x() : gridDim.x;
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < STAGES; s++) { bar_init(&full[s], 1); bar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; s++) { bar_init(&full[s], 1); bar_init(&empty[s], MC ? 2 : 1); }
         for (int a = 0; a < 2; a++) { bar_init(&tfull[a], 1); bar_init(&tempty[a], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -140,14 +162,20 @@ k_i8gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUten
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (MC) cluster_sync_all();          // peer barriers are initialised before any multicast / remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // work items: tiles (MC = false) or vertical tile pairs (MC = true); rows of work items are grouped so that a
+    // B panel stays hot in L2 while `group_m` rows use it
+    const uint32_t rows = MC ? P.tiles_m / 2 : P.tiles_m;
+    const uint32_t nwork = rows * P.tiles_n;
     auto tile_coords = [&](uint32_t t, uint32_t &tm, uint32_t &tn) {
         const uint32_t per_group = P.group_m * P.tiles_n;
         const uint32_t g = t / per_group, r = t - g * per_group;
-        const uint32_t gm = (P.tiles_m - g * P.group_m) < P.group_m ? (P.tiles_m - g * P.group_m) : P.group_m;
-        tm = g * P.group_m + r % gm;
+        const uint32_t gm = (rows - g * P.group_m) < P.group_m ? (rows - g * P.group_m) : P.group_m;
+        const uint32_t row = g * P.group_m + r % gm;
+        tm = MC ? 2 * row + rank : row;
         tn = r / gm;
     };
 
@@ -155,13 +183,17 @@ k_i8gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUten
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            for (uint32_t t = worker; t < nwork; t += n_workers) {
                 uint32_t tm, tn; tile_coords(t, tm, tn);
                 for (uint32_t kb = 0; kb < nkb; kb++) {
-                    bar_wait(&empty[stage], phase ^ 1);
+                    bar_wait(&empty[stage], phase ^ 1);                // MC: both CTAs of the cluster have released this slot
                     bar_expect_tx(&full[stage], STAGE_BYTES);
                     tma_load_2d(sA + stage * A_STAGE, &mapA, &full[stage], (int)(kb * BK), (int)(tm * BM));
-                    tma_load_2d(sB + stage * B_STAGE, &mapB, &full[stage], (int)(kb * BK), (int)(tn * BN));
+                    if constexpr (MC)                                  // my half of the B tile goes to both CTAs
+                        tma_load_2d_mc(sB + stage * B_STAGE + rank * (B_STAGE / 2), &mapB, &full[stage], (int)(kb * BK),
+                                       (int)(tn * BN + rank * (BN / 2)), (uint16_t)3);
+                    else
+                        tma_load_2d(sB + stage * B_STAGE, &mapB, &full[stage], (int)(kb * BK), (int)(tn * BN));
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -171,7 +203,7 @@ k_i8gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUten
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_i8(BM, BN);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            for (uint32_t t = worker; t < nwork; t += n_workers) {
                 bar_wait(&tempty[acc], acc_phase ^ 1);                 // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
@@ -183,7 +215,8 @@ k_i8gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUten
 #pragma unroll
                     for (uint32_t k = 0; k < BK / 32; k++)             // UMMA_K = 32 int8 = 32 bytes = +2 in 16-byte units
                         tc_mma_i8(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                    tc_commit(&empty[stage]);                          // frees the smem slot when these MMAs retire
+                    if constexpr (MC) tc_commit_mc(&empty[stage], (uint16_t)3);   // the slot is shared: release it in both CTAs
+                    else tc_commit(&empty[stage]);                     // frees the smem slot when these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(&tfull[acc]);                                // accumulator complete -> epilogue
@@ -194,7 +227,8 @@ k_i8gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUten
         // ===== epilogue warps 2..5: TMEM lane quadrant = warp % 4 =====
         const uint32_t quad = warp & 3;
         uint32_t acc = 0, acc_phase = 0;
-        for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const bool plain = outq.identity && outq.shift == 0;            // C's type holds the exact sum: no quantizer left
+        for (uint32_t t = worker; t < nwork; t += n_workers) {
             uint32_t tm, tn; tile_coords(t, tm, tn);
             bar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
@@ -206,7 +240,7 @@ k_i8gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUten
 #pragma unroll
                 for (int c = 0; c < 32; c++) {
                     const uint64_t col = (uint64_t)tn * BN + c0 + c;
-                    const int32_t q = conv_apply<int32_t, false>((int32_t)v[c], outq);   // converting assignment into C's type
+                    const int32_t q = plain ? (int32_t)v[c] : conv_apply<int32_t, false>((int32_t)v[c], outq);   // converting assignment into C's type
                     if (P.c_wb == 4) ((int32_t *)C)[col * P.M + row] = q;                // column-major: 32 lanes = 128 contiguous bytes
                     else             ((int64_t *)C)[col * P.M + row] = (int64_t)q;
                 }
@@ -219,7 +253,22 @@ k_i8gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUten
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (MC) cluster_sync_all();          // no CTA leaves while its peer may still multicast into it
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+}
+
+__global__ void __launch_bounds__(I8_THREADS, 1)
+k_i8gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, void *__restrict__ C,
+         const __grid_constant__ I8Params P, const __grid_constant__ QStage outq)
+{
+    i8gemm_body<false>(mapA, mapB, C, P, outq);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1)
+k_i8gemm_mc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, void *__restrict__ C,
+            const __grid_constant__ I8Params P, const __grid_constant__ QStage outq)
+{
+    i8gemm_body<true>(mapA, mapB, C, P, outq);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -317,11 +366,15 @@ int i8gemm_run(const void *A, const void *B, void *C, uint32_t M, uint32_t N, ui
     case 4: pack_operand<int32_t>(B, Bp, b_r, b_c, b_tr, s); break;
     default: pack_operand<int64_t>(B, Bp, b_r, b_c, b_tr, s); break;
     }
+    static int variant = -1;                       // QB200_I8_VARIANT=0 forces the single-CTA kernel
+    if (variant < 0) { const char *e = getenv("QB200_I8_VARIANT"); variant = (e && e[0] == '0') ? 0 : 1; }
+    const bool mc = variant == 1 && (M / BM) % 2 == 0;
     CUtensorMap mapA, mapB;
-    if (make_map(&mapA, Ap, M, K, BM) || make_map(&mapB, Bp, N, K, BN)) { *err = "cuTensorMapEncodeTiled failed"; return -1; }
+    if (make_map(&mapA, Ap, M, K, BM) || make_map(&mapB, Bp, N, K, mc ? BN / 2 : BN)) { *err = "cuTensorMapEncodeTiled failed"; return -1; }
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(k_i8gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) { *err = "cannot raise dynamic smem"; return -1; }
+        if (cudaFuncSetAttribute(k_i8gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(k_i8gemm_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) { *err = "cannot raise dynamic smem"; return -1; }
         attr_set = true;
     }
     int dev = 0, sms = 0;
@@ -330,8 +383,14 @@ int i8gemm_run(const void *A, const void *B, void *C, uint32_t M, uint32_t N, ui
     I8Params P;
     P.M = M; P.N = N; P.K = K; P.tiles_m = M / BM; P.tiles_n = N / BN; P.c_wb = c_wb; P.group_m = 16;
     const uint32_t ntiles = P.tiles_m * P.tiles_n;
-    const unsigned grid = ntiles < (uint32_t)sms ? ntiles : (unsigned)sms;
-    k_i8gemm<<<grid, I8_THREADS, SMEM_BYTES, s>>>(mapA, mapB, C, P, outq);
+    if (mc) {
+        P.group_m = 8;                                                     // 8 tile pairs = 16 m-tiles per group
+        const uint32_t npairs = ntiles / 2, clusters = npairs < (uint32_t)(sms / 2) ? npairs : (uint32_t)(sms / 2);
+        k_i8gemm_mc<<<clusters * 2, I8_THREADS, SMEM_BYTES, s>>>(mapA, mapB, C, P, outq);
+    } else {
+        const unsigned grid = ntiles < (uint32_t)sms ? ntiles : (unsigned)sms;
+        k_i8gemm<<<grid, I8_THREADS, SMEM_BYTES, s>>>(mapA, mapB, C, P, outq);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
     count_launch(1);

@@ -373,6 +373,37 @@ def test_jit_specialised_kernels_vs_oracle(seed):
         assert e.code == abi.QB_EDOMAIN
 
 
+def test_c3_dynamic_clamp_elision_mixed_batch():
+    """The tile kernel drops Qmul's saturation per instance when the instance's operand ranges allow it.
+    A batch that mixes ordinary instances, instances where the two extreme operands meet in one product
+    (min x min, the only saturating product of config 3) and instances where they exist but never meet
+    must equal the oracle bit for bit."""
+    a = QType(7, 8)
+    mul = QType(14, 8, True, RND_CONV, SAT_TCPL)
+    lv = [QType(15 + l, 8 - l, True, RND_POS_INF, SAT_TCPL) for l in range(6)]
+    c = QType(17, 4, True, RND_POS_INF, SAT_TCPL)
+    plan = ops.make_gemul_plan(a, a, c, 64, 64, 64, mul=mul, add=lv)
+    batch = 6
+    rng = np.random.default_rng(99)
+    A = rng.integers(-32767, 32768, size=batch * 4096).astype(np.int32)
+    B = rng.integers(-32767, 32768, size=batch * 4096).astype(np.int32)
+    # instance 1: A[5,9] and B[9,3] are both the minimum -> product (5,3,k=9) saturates
+    A[1 * 4096 + 5 + 9 * 64] = -32768; B[1 * 4096 + 9 + 3 * 64] = -32768
+    # instance 3: minima present on different k -> never multiplied together
+    A[3 * 4096 + 7 + 2 * 64] = -32768; B[3 * 4096 + 11 + 8 * 64] = -32768
+    # instance 4: only A has the minimum
+    A[4 * 4096 + 0] = -32768
+    # instance 5: a whole column/row of minima
+    A[5 * 4096 + 10 * 64: 5 * 4096 + 11 * 64] = -32768; B[5 * 4096 + 10: 5 * 4096 + 4096: 64] = -32768
+    want = oracle.gemul_batched(plan, A, B, batch)
+    Cd = torch.empty(batch * 4096, dtype=torch.int32, device="cuda")
+    ops.Qgemul(Cd, dev(A), dev(B), plan, batch=batch)
+    assert np.array_equal(Cd.cpu().numpy(), want)
+    gen = torch.empty_like(Cd)
+    ops.Qgemul(gen, dev(A), dev(B), plan, batch=batch, flags=abi.QB_F_NO_SPECIALIZE)
+    assert torch.equal(Cd, gen)
+
+
 def test_synth_fill_matches_oracle_all_word_sizes():
     for wb, lo, hi in [(1, -127, 127), (2, -(1 << 15), (1 << 15) - 1), (4, -65536, 65535), (8, -(1 << 40), (1 << 40))]:
         t = torch.empty(10007, dtype={1: torch.int8, 2: torch.int16, 4: torch.int32, 8: torch.int64}[wb], device="cuda")
