@@ -190,6 +190,19 @@ int qb200_tfcmul_batched(const qb_tfcmul_plan *plan, const void *x, const void *
 int qb200_convert_batched(const qb_convert_plan *plan, const void *in, void *out,
                           uint64_t batch, const qb_exec *exec);
 
+/* ---- the steps on either side of the path in an accuracy sweep ----
+ * qb200_quantize_f64  <- Qu_s(double)  include/QuBLAS.h:2387-2393 (exact value, the type's QuMode, then its OfMode)
+ * qb200_dequantize_f64 <- toDouble()   include/QuBLAS.h:2413-2416
+ * qb200_error_stats: sums for SQNR (10 log10(sum_sq_ref / sum_sq_err)) and the max abs error of a fixed-point
+ * buffer against a float64 reference, reduced on the device in a fixed order (deterministic). */
+typedef struct qb_err_stats {
+    double   sum_sq_err, sum_sq_ref, max_abs_err;
+    uint64_t n;
+} qb_err_stats;
+int qb200_quantize_f64(const qb_qdesc *to, const double *in, void *out, uint64_t n, const qb_exec *exec);
+int qb200_dequantize_f64(const qb_qdesc *from, const void *in, double *out, uint64_t n, const qb_exec *exec);
+int qb200_error_stats(const qb_qdesc *type, const void *words, const double *ref, uint64_t n, qb_err_stats *stats, const qb_exec *exec);
+
 /* Deterministic synthetic raw words, uniform over [lo, hi], counter-based:
  * word[i] = lo + mix64(seed, stream_id, first_index + i) mod (hi - lo + 1).
  * Same function on host and device; buffers are device memory when

@@ -23,7 +23,7 @@ def build():
     src = os.path.join(HERE, "qb_oracle.c")
     if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
         os.makedirs(os.path.dirname(so), exist_ok=True)
-        subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", so, src])
+        subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", so, src, "-lm"])
     return so
 
 
@@ -43,6 +43,11 @@ def load():
         L.qbo_tfcmul_batched.argtypes = [C.POINTER(abi.qb_tfcmul_plan), vp, vp, vp, u64]
         L.qbo_convert_batched.argtypes = [C.POINTER(abi.qb_convert_plan), vp, vp, u64]
         L.qbo_synth_fill.argtypes = [vp, u64, u32, i64, i64, u64, u64, u64]
+        dp = C.POINTER(C.c_double)
+        L.qbo_from_double.restype = i64; L.qbo_from_double.argtypes = [C.c_double, qd]
+        L.qbo_quantize_f64.argtypes = [qd, vp, vp, u64]
+        L.qbo_dequantize_f64.argtypes = [qd, vp, vp, u64]
+        L.qbo_error_stats.argtypes = [qd, vp, vp, u64, dp, dp, dp]
         L.qbo_synth_word.restype = i64; L.qbo_synth_word.argtypes = [u64, u64, u64, i64, i64]
         _LIB = L
     return _LIB
@@ -147,3 +152,28 @@ def synth_fill(count, word_bytes, lo, hi, seed, stream_id, first_index=0):
     rc = load().qbo_synth_fill(_ptr(out), count, word_bytes, lo, hi, seed, stream_id, first_index)
     assert rc == 0
     return out
+
+
+def from_double(v, t: QType):
+    return load().qbo_from_double(float(v), C.byref(abi.desc(t)))
+
+
+def quantize_f64(t: QType, x):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.zeros(x.size, dtype=np_dtype(t.word_bytes))
+    assert load().qbo_quantize_f64(C.byref(abi.desc(t)), _ptr(x), _ptr(out), x.size) == 0
+    return out
+
+
+def dequantize_f64(t: QType, w):
+    w = np.ascontiguousarray(w)
+    out = np.zeros(w.size, dtype=np.float64)
+    assert load().qbo_dequantize_f64(C.byref(abi.desc(t)), _ptr(w), _ptr(out), w.size) == 0
+    return out
+
+
+def error_stats(t: QType, w, ref):
+    w = np.ascontiguousarray(w); ref = np.ascontiguousarray(ref, dtype=np.float64)
+    a, b, c = C.c_double(), C.c_double(), C.c_double()
+    assert load().qbo_error_stats(C.byref(abi.desc(t)), _ptr(w), _ptr(ref), w.size, C.byref(a), C.byref(b), C.byref(c)) == 0
+    return a.value, b.value, c.value

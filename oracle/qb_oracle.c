@@ -401,3 +401,52 @@ int qbo_synth_fill(void *dst, uint64_t count, uint32_t word_bytes, int64_t lo, i
         store_word(dst, (size_t)i, (int)word_bytes, qbo_synth_word(seed, stream_id, first_index + i, lo, hi));
     return QB_OK;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * the steps on either side of the path in an accuracy sweep.
+ * double -> Qu: Qu_s(double), QuBLAS.h:2387-2393 = the exact value (loadFromDouble into a 2400-bit
+ * buffer, :664) rounded by the type's QuMode (fracConvert<1200+frac -> frac>) and overflowed by its
+ * OfMode.  Restated on the 53-bit mantissa: raw = ovf(round(m * 2^e * 2^frac)).
+ * ------------------------------------------------------------------------------------------- */
+#include <math.h>
+int64_t qbo_from_double(double v, const qb_qdesc *t)
+{
+    if (v == 0.0 || v != v || isinf(v)) return 0;                            /* :667-671 */
+    int e = 0;
+    double m = frexp(v, &e);                                                  /* v = m * 2^e, 0.5 <= |m| < 1 */
+    i128 mi = (i128)(long long)ldexp(m, 53);                                  /* exact 53-bit signed mantissa */
+    int sh = 53 - e - t->frac_bits;                                           /* raw = mi * 2^-sh */
+    i128 r;
+    if (sh >= 0) r = sh > 120 ? ((t->qu_mode == QB_TRN_TCPL && mi < 0) ? -1 : 0) : qbo_round(mi, sh, t->qu_mode);
+    else if (-sh > 60) r = mi > 0 ? ((i128)1 << 120) : -((i128)1 << 120);
+    else r = shl128(mi, -sh);
+    return (int64_t)qbo_ovf(r, *t);
+}
+int qbo_quantize_f64(const qb_qdesc *t, const double *in, void *out, uint64_t n)
+{
+    int wb = word_bytes_of(*t);
+    for (uint64_t i = 0; i < n; i++) store_word(out, (size_t)i, wb, qbo_from_double(in[i], t));
+    return QB_OK;
+}
+/* toDouble, QuBLAS.h:2413-2416 */
+int qbo_dequantize_f64(const qb_qdesc *t, const void *in, double *out, uint64_t n)
+{
+    int wb = word_bytes_of(*t);
+    for (uint64_t i = 0; i < n; i++) out[i] = ldexp((double)(int64_t)load_word(in, (size_t)i, wb), -t->frac_bits);
+    return QB_OK;
+}
+/* error of a fixed-point result against a float64 reference: sums for SQNR and the max abs error */
+int qbo_error_stats(const qb_qdesc *t, const void *words, const double *ref, uint64_t n, double *sum_sq_err, double *sum_sq_ref,
+                    double *max_abs_err)
+{
+    int wb = word_bytes_of(*t);
+    double se = 0, sr = 0, mx = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        double v = ldexp((double)(int64_t)load_word(words, (size_t)i, wb), -t->frac_bits);
+        double d = v - ref[i];
+        se += d * d; sr += ref[i] * ref[i];
+        if (fabs(d) > mx) mx = fabs(d);
+    }
+    *sum_sq_err = se; *sum_sq_ref = sr; *max_abs_err = mx;
+    return QB_OK;
+}

@@ -231,6 +231,18 @@ def gemul_cases(rng):
     return cases
 
 
+def fromdouble_cases(rng):
+    """Qu_s(double) (QuBLAS.h:2387-2393).  RND::CONV is excluded: the reference rounds the 2400-bit load
+    buffer through its wide path, where CONV is defective."""
+    cases = []
+    for q in (0, 1, 2, 3, 5, 6):
+        for o in range(4):
+            i, f = rng.randint(2, 12), rng.randint(0, 14)
+            cases.append({"kind": "fromdouble", "to": T(i, f, rng.random() < 0.8, q, o)})
+    cases.append({"kind": "fromdouble", "to": T(6, -3)})        # readme.md:35  type2 q2 = 16
+    return cases
+
+
 def cgemul_cases(rng):
     cases = []
     for (K, half) in [(4, False), (8, True), (16, False), (5, False)]:
@@ -340,12 +352,18 @@ def emit_cgemul(c, idx):
     return "\n".join(lines)
 
 
-EMIT = {"scalar": emit_scalar, "reduce": emit_reduce, "tf": emit_tf, "gemul": emit_gemul, "cgemul": emit_cgemul}
+def emit_fromdouble(c, idx):
+    body = ("double d; __builtin_memcpy(&d, &in[0], 8); %s r = d;" % cxx_type(c["to"]))
+    return "static void case_%d(const int64_t *in, int64_t *out) { %s out[0] = (int64_t)r.data.data; put_type(out + 1, r); }\n" % (idx, body)
+
+
+EMIT = {"fromdouble": emit_fromdouble, "scalar": emit_scalar, "reduce": emit_reduce, "tf": emit_tf, "gemul": emit_gemul, "cgemul": emit_cgemul}
 
 
 def n_inputs(c):
     k = c["kind"]
     if k == "scalar": return 2
+    if k == "fromdouble": return 1
     if k == "reduce": return c["len"]
     if k == "tf": return 4
     if k == "gemul": return c["M"] * c["K"] + c["K"] * c["N"]
@@ -354,13 +372,27 @@ def n_inputs(c):
 
 def n_outputs(c):
     k = c["kind"]
-    if k == "scalar" or k == "reduce": return 6
+    if k == "scalar" or k == "reduce" or k == "fromdouble": return 6
     if k == "tf" or k == "cgemul": return 12
     if k == "gemul": return c["M"] * c["N"]
 
 
+def _dbits(x):
+    import struct
+    return struct.unpack("<q", struct.pack("<d", float(x)))[0]
+
+
 def gen_inputs(rng, c):
     k = c["kind"]
+    if k == "fromdouble":
+        t = c["to"]
+        ulp = 2.0 ** (-t["f"])
+        top = 2.0 ** t["i"]
+        vals = [0.0, 1.0, -1.0, 1.25, -1.25, 16.0, 0.5 * ulp, -0.5 * ulp, 1.5 * ulp, -1.5 * ulp, 2.5 * ulp, -2.5 * ulp, 0.49999 * ulp,
+                -0.50001 * ulp, top, -top, top - ulp, -top - ulp, top * 3.7, -top * 5.1, 1e-9, -1e-9, 3.141592653589793, -2.718281828459045]
+        vals += [rng.uniform(-1.3 * top, 1.3 * top) for _ in range(20)]
+        vals += [(rng.randint(-2 ** 10, 2 ** 10) + 0.5) * ulp for _ in range(8)]        # exact ties
+        return [[_dbits(v)] for v in vals]
     if k == "scalar":
         return [[rand_raw(rng, c["a"]), rand_raw(rng, c["b"])] for _ in range(48)]
     if k == "reduce":
@@ -435,7 +467,7 @@ def build_harness(cases, include_dir, out_dir, tag, n_tu=8, extra_flags=()):
 
 
 def all_cases(rng):
-    return scalar_cases(rng) + reduce_cases(rng) + tf_cases(rng) + gemul_cases(rng) + cgemul_cases(rng)
+    return scalar_cases(rng) + reduce_cases(rng) + tf_cases(rng) + gemul_cases(rng) + cgemul_cases(rng) + fromdouble_cases(rng)
 
 
 def main():

@@ -64,6 +64,10 @@ class qb_plan_info(C.Structure):
                 ("out_type", qb_qdesc), ("kernel", C.c_char * 96)]
 
 
+class qb_err_stats(C.Structure):
+    _fields_ = [("sum_sq_err", C.c_double), ("sum_sq_ref", C.c_double), ("max_abs_err", C.c_double), ("n", C.c_uint64)]
+
+
 class qb_exec(C.Structure):
     _fields_ = [("mem_kind", C.c_int32), ("device", C.c_int32), ("stream", C.c_void_p),
                 ("flags", C.c_uint32), ("reserved", C.c_uint32)]
@@ -100,7 +104,7 @@ ABI_SYMBOLS = [
     "qb200_abi_version", "qb200_last_error", "qb200_device_count", "qb200_launch_count",
     "qb200_launch_count_reset", "qb200_reduce_plan_info", "qb200_gemul_plan_info", "qb200_cgemul_plan_info",
     "qb200_reduce_batched", "qb200_gemul_batched", "qb200_cgemul_batched", "qb200_tfcmul_batched",
-    "qb200_convert_batched", "qb200_synth_fill", "qb200_shard_range", "qb200_measure_int_peak", "qb200_jit_check_gemul",
+    "qb200_convert_batched", "qb200_synth_fill", "qb200_shard_range", "qb200_measure_int_peak", "qb200_jit_check_gemul", "qb200_quantize_f64", "qb200_dequantize_f64", "qb200_error_stats",
 ]
 
 _LIB = None
@@ -136,6 +140,9 @@ def load() -> C.CDLL:
     L.qb200_convert_batched.argtypes = [C.POINTER(qb_convert_plan), vp, vp, u64, C.POINTER(qb_exec)]
     L.qb200_synth_fill.argtypes = [vp, u64, u32, i64, i64, u64, u64, u64, C.POINTER(qb_exec)]
     L.qb200_shard_range.argtypes = [u64, u32, u32, C.POINTER(u64), C.POINTER(u64)]
+    L.qb200_quantize_f64.argtypes = [C.POINTER(qb_qdesc), vp, vp, u64, C.POINTER(qb_exec)]
+    L.qb200_dequantize_f64.argtypes = [C.POINTER(qb_qdesc), vp, vp, u64, C.POINTER(qb_exec)]
+    L.qb200_error_stats.argtypes = [C.POINTER(qb_qdesc), vp, vp, u64, C.POINTER(qb_err_stats), C.POINTER(qb_exec)]
     L.qb200_jit_check_gemul.argtypes = [C.POINTER(qb_gemul_plan), C.c_char_p, u64]
     L.qb200_measure_int_peak.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(qb_exec)]
     for name in ABI_SYMBOLS:

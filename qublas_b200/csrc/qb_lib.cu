@@ -723,3 +723,126 @@ extern "C" int qb200_jit_check_gemul(const qb_gemul_plan *plan, char *log, uint6
     if (log && log_cap) { snprintf(log, (size_t)log_cap, "%s", l.c_str()); }
     return rc;
 }
+
+// ---------------------------------------------------------------------------------------------
+// double -> Qu, Qu -> double, on-device error statistics
+// ---------------------------------------------------------------------------------------------
+// Qu_s(double) (QuBLAS.h:2387-2393) on the 53-bit mantissa: raw = ovf(round(m * 2^(e + frac))).
+__device__ __forceinline__ int64_t from_double_dev(double v, int frac, const QStage &q)
+{
+    const uint64_t b = (uint64_t)__double_as_longlong(v);
+    const int ef = (int)((b >> 52) & 0x7FF);
+    if (ef == 0x7FF || (b << 1) == 0) return 0;                         // NaN / inf / zero load as 0 (QuBLAS.h:667-671)
+    uint64_t m = b & 0xFFFFFFFFFFFFFull;
+    int e;                                                              // value = m * 2^e
+    if (ef == 0) e = -1074; else { m |= 0x10000000000000ull; e = ef - 1075; }
+    int64_t mi = (b >> 63) ? -(int64_t)m : (int64_t)m;
+    const int sh = -(e + frac);                                         // raw = mi * 2^-sh
+    int64_t r;
+    if (sh > 0) {
+        if (sh >= 62) {                                                  // |mi| < 2^53 << 2^(sh-1): everything but floor of a negative gives 0
+            r = (q.qu == TRN_TCPL && mi < 0) ? -1 : 0;
+        } else r = q_round<int64_t>(mi, sh, q.qu);
+    } else if (-sh > 9) {                                                // far outside any <= 64-bit type: saturate before the shift can overflow
+        r = mi > 0 ? INT64_MAX : INT64_MIN;
+        if (q.of == WRP_TCPL) r = (-sh >= 64) ? 0 : (int64_t)((uint64_t)mi << (-sh));   // wrap keeps the low bits
+    } else r = (int64_t)((uint64_t)mi << (-sh));
+    QStage o = q; o.need_lo = 1; o.need_hi = 1;
+    return q_ovf<int64_t, false>(r, o);
+}
+
+__global__ void k_quantize_f64(const double *__restrict__ in, void *__restrict__ out, uint64_t n, int wb, int frac, const __grid_constant__ QStage q)
+{
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x)
+        store_word<int64_t>(out, e, wb, from_double_dev(in[e], frac, q));
+}
+__global__ void k_dequantize_f64(const void *__restrict__ in, double *__restrict__ out, uint64_t n, int wb, int frac)
+{
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x)
+        out[e] = scalbn((double)load_word<int64_t>(in, e, wb), -frac);
+}
+// fixed grid, fixed per-thread order, fixed tree: the sums are reproducible run to run
+__global__ void __launch_bounds__(256) k_err_stats(const void *__restrict__ w, const double *__restrict__ ref, uint64_t n, int wb, int frac, double *__restrict__ part)
+{
+    __shared__ double s0[256], s1[256], s2[256];
+    double se = 0, sr = 0, mx = 0;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) {
+        const double v = scalbn((double)load_word<int64_t>(w, e, wb), -frac), r = ref[e], d = v - r;
+        se += d * d; sr += r * r; mx = fmax(mx, fabs(d));
+    }
+    s0[threadIdx.x] = se; s1[threadIdx.x] = sr; s2[threadIdx.x] = mx;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { s0[threadIdx.x] += s0[threadIdx.x + o]; s1[threadIdx.x] += s1[threadIdx.x + o]; s2[threadIdx.x] = fmax(s2[threadIdx.x], s2[threadIdx.x + o]); }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { part[3 * blockIdx.x] = s0[0]; part[3 * blockIdx.x + 1] = s1[0]; part[3 * blockIdx.x + 2] = s2[0]; }
+}
+__global__ void k_err_final(const double *__restrict__ part, int nblocks, double *__restrict__ out)
+{
+    double se = 0, sr = 0, mx = 0;
+    for (int i = 0; i < nblocks; i++) { se += part[3 * i]; sr += part[3 * i + 1]; mx = fmax(mx, part[3 * i + 2]); }
+    out[0] = se; out[1] = sr; out[2] = mx;
+}
+
+static int stage_for_type(const qb_qdesc &t, QStage *q, const char *what)
+{
+    Analysis an;
+    if (!check_type(t, an, what)) return fail(an.status, an.err);
+    TVal o;
+    Ival full = { -((i128)1 << 62), ((i128)1 << 62) };
+    *q = make_stage(t.frac_bits, full, 64, t, &o, an);                 // bounds / wrap fields of the target type; shift unused
+    return QB_OK;
+}
+
+extern "C" int qb200_quantize_f64(const qb_qdesc *to, const double *in, void *out, uint64_t n, const qb_exec *exec)
+{
+    if (!to || !in || !out) return fail(QB_EINVAL, "null argument");
+    QStage q; int rc = stage_for_type(*to, &q, "target type"); if (rc) return rc;
+    if (n == 0) return QB_OK;
+    Ctx cx; if ((rc = cx.init(exec))) return rc;
+    const int wb = word_bytes(*to);
+    const void *din; void *dout;
+    if ((rc = cx.in(in, n * 8, &din)) || (rc = cx.out(out, n * wb, &dout))) return rc;
+    k_quantize_f64<<<grid_for(n, 256), 256, 0, cx.stream>>>((const double *)din, dout, n, wb, to->frac_bits, q);
+    if ((rc = post_launch("k_quantize_f64"))) return rc;
+    if ((rc = cx.out_done(out, n * wb, dout))) return rc;
+    return cx.finish();
+}
+
+extern "C" int qb200_dequantize_f64(const qb_qdesc *from, const void *in, double *out, uint64_t n, const qb_exec *exec)
+{
+    if (!from || !in || !out) return fail(QB_EINVAL, "null argument");
+    Analysis an; if (!check_type(*from, an, "source type")) return fail(an.status, an.err);
+    if (n == 0) return QB_OK;
+    Ctx cx; int rc = cx.init(exec); if (rc) return rc;
+    const int wb = word_bytes(*from);
+    const void *din; void *dout;
+    if ((rc = cx.in(in, n * wb, &din)) || (rc = cx.out(out, n * 8, &dout))) return rc;
+    k_dequantize_f64<<<grid_for(n, 256), 256, 0, cx.stream>>>(din, (double *)dout, n, wb, from->frac_bits);
+    if ((rc = post_launch("k_dequantize_f64"))) return rc;
+    if ((rc = cx.out_done(out, n * 8, dout))) return rc;
+    return cx.finish();
+}
+
+extern "C" int qb200_error_stats(const qb_qdesc *type, const void *words, const double *ref, uint64_t n, qb_err_stats *stats, const qb_exec *exec)
+{
+    if (!type || !words || !ref || !stats) return fail(QB_EINVAL, "null argument");
+    Analysis an; if (!check_type(*type, an, "type")) return fail(an.status, an.err);
+    memset(stats, 0, sizeof(*stats));
+    stats->n = n;
+    if (n == 0) return QB_OK;
+    Ctx cx; int rc = cx.init(exec); if (rc) return rc;
+    const int wb = word_bytes(*type), nblocks = 592;
+    const void *dw, *dr; void *part, *res;
+    if ((rc = cx.in(words, n * wb, &dw)) || (rc = cx.in(ref, n * 8, &dr)) || (rc = cx.alloc(&part, 3 * nblocks * 8)) || (rc = cx.alloc(&res, 3 * 8))) return rc;
+    k_err_stats<<<nblocks, 256, 0, cx.stream>>>(dw, (const double *)dr, n, wb, type->frac_bits, (double *)part);
+    if ((rc = post_launch("k_err_stats"))) return rc;
+    k_err_final<<<1, 1, 0, cx.stream>>>((const double *)part, nblocks, (double *)res);
+    if ((rc = post_launch("k_err_final"))) return rc;
+    double h[3];
+    CUDA_TRY(cudaMemcpyAsync(h, res, sizeof(h), cudaMemcpyDeviceToHost, cx.stream));
+    CUDA_TRY(cudaStreamSynchronize(cx.stream));
+    stats->sum_sq_err = h[0]; stats->sum_sq_ref = h[1]; stats->max_abs_err = h[2];
+    return cx.finish();
+}

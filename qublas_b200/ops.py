@@ -206,6 +206,38 @@ def convert(x, src: QType, dst: QType):
     return out
 
 
+def quantize(x, t: QType):
+    """double -> Qu<t> raw words on the GPU: exact value, t's QuMode, t's OfMode (Qu_s(double), QuBLAS.h:2387-2393)."""
+    n = x.numel() if _is_torch(x) else x.size
+    out = _new_like(x, n, t.word_bytes)
+    d = abi.desc(t)
+    ex = _exec_for(x)
+    abi.check(abi.load().qb200_quantize_f64(C.byref(d), _ptr(x), _ptr(out), n, C.byref(ex)))
+    return out
+
+
+def dequantize(w, t: QType):
+    """raw words -> double (toDouble, QuBLAS.h:2413-2416)."""
+    n = w.numel() if _is_torch(w) else w.size
+    out = torch.empty(n, dtype=torch.float64, device=w.device) if _is_torch(w) else np.empty(n, dtype=np.float64)
+    d = abi.desc(t)
+    ex = _exec_for(w)
+    abi.check(abi.load().qb200_dequantize_f64(C.byref(d), _ptr(w), _ptr(out), n, C.byref(ex)))
+    return out
+
+
+def error_stats(w, ref, t: QType):
+    """SQNR (dB) and max abs error of a fixed-point buffer against a float64 reference, computed on the device."""
+    import math
+    n = w.numel() if _is_torch(w) else w.size
+    st = abi.qb_err_stats()
+    d = abi.desc(t)
+    ex = _exec_for(w, ref)
+    abi.check(abi.load().qb200_error_stats(C.byref(d), _ptr(w), _ptr(ref), n, C.byref(st), C.byref(ex)))
+    sqnr = float("inf") if st.sum_sq_err == 0 else 10.0 * math.log10(st.sum_sq_ref / st.sum_sq_err)
+    return {"sqnr_db": sqnr, "max_abs_err": st.max_abs_err, "sum_sq_err": st.sum_sq_err, "sum_sq_ref": st.sum_sq_ref, "n": st.n}
+
+
 def synth_fill(out, lo: int, hi: int, seed: int, stream_id: int, first_index: int = 0):
     """Counter-based synthetic raw words, uniform over [lo, hi]."""
     n = out.numel() if _is_torch(out) else out.size

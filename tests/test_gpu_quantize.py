@@ -1,0 +1,73 @@
+"""SURVEY.md 8(f) rank 1 — the steps on either side of the path in an accuracy sweep, on the GPU:
+double -> Qu (bit-exact vs the reference's Qu_s(double) goldens and the oracle), Qu -> double (exact),
+and SQNR / max-abs error statistics against a float64 reference."""
+import json
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from qublas_b200 import ops
+from qublas_b200.qtypes import QType, RND_CONV, RND_POS_INF, SAT_TCPL
+from tests.helpers import load_cases, qt
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def test_quantize_matches_reference_goldens():
+    n = 0
+    for c in load_cases("ref_fromdouble.json"):
+        t = qt(c["to"])
+        x = np.array([struct.unpack("<d", struct.pack("<q", i[0]))[0] for i in c["inputs"]], dtype=np.float64)
+        got = ops.quantize(torch.from_numpy(x).cuda(), t).cpu().numpy()
+        assert [int(v) for v in got] == [o[0] for o in c["outputs"]], c["to"]
+        n += len(x)
+    assert n >= 1200
+
+
+@pytest.mark.parametrize("mem", ["device", "host"])
+def test_quantize_dequantize_vs_oracle_all_modes(mem):
+    rng = np.random.default_rng(12)
+    for q in range(7):
+        for o in range(4):
+            t = QType(int(rng.integers(2, 20)), int(rng.integers(-2, 24)), bool(rng.random() < 0.8), q, o)
+            if t.i + t.f < 1:
+                continue
+            scale = 2.0 ** t.i
+            x = np.concatenate([rng.uniform(-1.5 * scale, 1.5 * scale, 4000), rng.normal(0, scale / 8, 4000),
+                                (rng.integers(-4096, 4096, 500) + 0.5) * 2.0 ** (-t.f), [0.0, -0.0, 1e300, -1e300, 1e-300, np.inf, np.nan]])
+            want = oracle.quantize_f64(t, x)
+            xin = torch.from_numpy(x).cuda() if mem == "device" else x
+            got = ops.quantize(xin, t)
+            gotn = got.cpu().numpy() if mem == "device" else got
+            assert np.array_equal(gotn, want), (t,)
+            back = ops.dequantize(got, t)
+            backn = back.cpu().numpy() if mem == "device" else back
+            assert np.array_equal(backn, oracle.dequantize_f64(t, want))
+
+
+def test_error_stats_of_a_quantized_gemul_vs_float64():
+    """A 64x64x64 config-3 Qgemul against the float64 GEMM of the dequantized operands: SQNR and max error
+    computed on the device equal the oracle's (summation order differs: 1e-12 relative tolerance)."""
+    from qublas_b200.qtypes import RND_CONV, RND_POS_INF
+    a = QType(7, 8); mul = QType(14, 8, True, RND_CONV, SAT_TCPL)
+    lv = [QType(15 + l, 8 - l, True, RND_POS_INF, SAT_TCPL) for l in range(6)]
+    c = QType(17, 4, True, RND_POS_INF, SAT_TCPL)
+    plan = ops.make_gemul_plan(a, a, c, 64, 64, 64, mul=mul, add=lv)
+    batch = 32
+    rng = np.random.default_rng(1)
+    Ad = torch.from_numpy(rng.normal(0, 20, batch * 4096)).cuda(); Bd = torch.from_numpy(rng.normal(0, 20, batch * 4096)).cuda()
+    A = ops.quantize(Ad, a); B = ops.quantize(Bd, a)
+    Cq = torch.empty(batch * 4096, dtype=torch.int32, device="cuda")
+    ops.Qgemul(Cq, A, B, plan, batch=batch)
+    Af = ops.dequantize(A, a).view(batch, 64, 64).transpose(1, 2); Bf = ops.dequantize(B, a).view(batch, 64, 64).transpose(1, 2)
+    ref = torch.bmm(Af, Bf).transpose(1, 2).contiguous().view(-1)        # column-major like C
+    st = ops.error_stats(Cq, ref, c)
+    se, sr, mx = oracle.error_stats(c, Cq.cpu().numpy(), ref.cpu().numpy())
+    assert abs(st["sum_sq_err"] - se) <= 1e-12 * se and abs(st["sum_sq_ref"] - sr) <= 1e-12 * sr and st["max_abs_err"] == mx
+    assert 40.0 < st["sqnr_db"] < 120.0 and st["n"] == batch * 4096
+    again = ops.error_stats(Cq, ref, c)
+    assert again["sum_sq_err"] == st["sum_sq_err"]                         # fixed reduction order: reproducible
