@@ -160,6 +160,29 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm)}
 
 
+def roofline_alu(lib, gmacs, device):
+    """The headline kernel is bound by instruction issue on the INT32/FP32 pipes, not by HBM: compare its
+    achieved thread-instruction rate (instructions per MAC from the committed ncu capture,
+    profiles/r1_c3_ncu_summary.json) with the issue peak measured live by qb200_measure_int_peak."""
+    from qublas_b200 import abi
+    out = {"bound": "issue (INT32 ALU + FP32 FMA pipes)", "unit": "T thread-instr/s"}
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_c3_ncu_summary.json")))[0]
+        ipm = float(prof["thread_instructions_per_unit"])
+        out.update({"instr_per_mac": ipm, "ncu_pipe_alu_pct": prof.get("pipe_alu_pct"), "ncu_pipe_fma_pct": prof.get("pipe_fma_pct"),
+                    "ncu_issue_active_pct": prof.get("issue_active_pct"), "source": "profiles/r1_c3_ncu_summary.json"})
+    except Exception:
+        return out
+    t = ctypes.c_double()
+    ex = abi.qb_exec(abi.QB_MEM_DEVICE, device, None, 0, 0)
+    if lib.qb200_measure_int_peak(0.25, ctypes.byref(t), ctypes.byref(ex)) == 0 and t.value > 0:
+        out["achieved"] = gmacs * 1e9 * ipm / 1e12
+        out["peak"] = t.value
+        out["frac"] = out["achieved"] / out["peak"]
+        out["peak_source"] = "qb200_measure_int_peak (IMAD + IADD3/LOP3 mix, all SMs), this run"
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
     import numpy as np
@@ -288,6 +311,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                          "note": "this kernel is bound by the INT32 issue rate, not HBM: see roofline_alu"},
+            "roofline_alu": roofline_alu(lib, value, local),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "GMAC/s", "h2d_bytes_per_step": e2e_instances * 2 * WORDS * 4,
                     "d2h_bytes_per_step": e2e_instances * WORDS * 4},

@@ -60,8 +60,26 @@ struct Ctx {
             if (e != cudaSuccess || n == 0) { cudaGetLastError(); return fail(QB_ENODEVICE, "no CUDA device available (there is no CPU fallback)"); }
             n_dev = n;
         }
+        if (ex && ex->device >= 0) CUDA_TRY(cudaSetDevice(ex->device));
+        {
+            // keep stream-ordered scratch (cudaMallocAsync) cached in the pool instead of returning it to the
+            // driver at every synchronisation: the default release threshold of 0 makes short calls jitter by 2x
+            static std::mutex pool_mu;
+            static bool pool_done[64] = { false };
+            int dev = 0;
+            CUDA_TRY(cudaGetDevice(&dev));
+            std::lock_guard<std::mutex> l(pool_mu);
+            if (!pool_done[dev & 63]) {
+                cudaMemPool_t pool;
+                if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                    uint64_t thr = UINT64_MAX;
+                    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+                }
+                cudaGetLastError();
+                pool_done[dev & 63] = true;
+            }
+        }
         if (ex) {
-            if (ex->device >= 0) CUDA_TRY(cudaSetDevice(ex->device));
             stream = (cudaStream_t)ex->stream;
             host = ex->mem_kind == QB_MEM_HOST;
             flags = ex->flags;
