@@ -76,6 +76,22 @@ std::string emit_gemul_cfg(const std::string &name, const qb_gemul_plan &p, cons
     return o.str();
 }
 
+// Is fma(x, y, 1.5 * 2^(23+s)) an exact implementation of stage q on operands with these ranges?
+static bool fp_mul_ok(const QStage &q, const TVal &x, const TVal &y)
+{
+    const int s = q.shift;
+    if (s < 1 || s > 30) return false;
+    if (!(q.qu == RND_CONV || q.qu == TRN_TCPL) || !(q.of == SAT_TCPL || q.of == SAT_SMGN)) return false;
+    auto fits24 = [](const Ival &r) { return r.lo >= -((i128)1 << 24) && r.hi <= ((i128)1 << 24); };
+    if (!fits24(x.r) || !fits24(y.r)) return false;                                   // exact floats
+    const i128 c4[4] = { x.r.lo * y.r.lo, x.r.lo * y.r.hi, x.r.hi * y.r.lo, x.r.hi * y.r.hi };
+    i128 mag = 0;
+    for (i128 c : c4) { i128 a = c < 0 ? -c : c; if (a > mag) mag = a; }
+    if (mag > ((i128)1 << (22 + s))) return false;                                    // stays in the binade of the constant
+    const i128 lo = (i128)q.lo, hi = (i128)q.hi;                                       // biased clamp bounds must be ints
+    return lo >= -((i128)1 << 30) && hi <= ((i128)1 << 30);
+}
+
 std::string emit_cgemul_cfg(const std::string &name, const qb_cgemul_plan &p, const CGemulProg &g)
 {
     std::ostringstream o;
@@ -91,6 +107,15 @@ std::string emit_cgemul_cfg(const std::string &name, const qb_cgemul_plan &p, co
     o << "  static constexpr __host__ __device__ qb::QStage out_im() { return " << emit_qstage(g.out_im) << "; }\n";
     o << emit_levels("lvl_re", g.tree_re, ilog2(p.K));
     o << emit_levels("lvl_im", g.tree_im, ilog2(p.K));
+    {
+        // FP32-FMA quantizer for the three TF products where it is exact
+        Analysis an; TVal re, im, mid[3];
+        TVal a = { p.a_re, type_range(p.a_re) }, b = { p.a_im, type_range(p.a_im) }, c = { p.b_re, type_range(p.b_re) }, d = { p.b_im, type_range(p.b_im) };
+        build_tf(a, b, c, d, p.tf, &re, &im, an, mid);
+        const bool fa = fp_mul_ok(g.tf.A, mid[0], c), fb = fp_mul_ok(g.tf.B, mid[1], b), fc = fp_mul_ok(g.tf.C, mid[2], d);
+        o << "  static constexpr bool FP_A = " << (fa ? "true" : "false") << ", FP_B = " << (fb ? "true" : "false") << ", FP_C = " << (fc ? "true" : "false") << ";\n";
+        o << "  static constexpr int SH_A = " << (fa ? (int)g.tf.A.shift : 1) << ", SH_B = " << (fb ? (int)g.tf.B.shift : 1) << ", SH_C = " << (fc ? (int)g.tf.C.shift : 1) << ";\n";
+    }
     o << "};\n";
     return o.str();
 }

@@ -41,7 +41,9 @@ template <typename I> QB_DEV I q_round(I v, int s, int mode)
     case RND_NEG_INF: return (v + (half - 1)) >> s;
     case RND_ZERO:    return (v + (half - 1) + (I)((U)v >> (B - 1))) >> s;
     case RND_INF:     return (v + half - (I)((U)v >> (B - 1))) >> s;
-    default:          return (v + (half - 1) + ((v >> s) & 1)) >> s;      // RND_CONV
+    default:                                                              // RND_CONV
+        if (s == 1) { const I q = v >> 1; return q + (v & q & 1); }       // halves tie to the even neighbour: one op fewer
+        return (v + (half - 1) + ((v >> s) & 1)) >> s;
     }
 }
 
@@ -121,6 +123,21 @@ QB_DEV void tf_apply(I a, I b, I c, I d, const TfProg &t, I &re, I &im)
     I Cv = mul_apply<I, CT>(ba, d, t.C);
     re = add_apply<I, CT>(A, Bv, t.re);
     im = add_apply<I, CT>(Bv, Cv, t.im);
+}
+
+// Qmul through the FP32 FMA pipe (see qb_codegen.cpp:fp_mul_ok): fma(a, b, 1.5 * 2^(23+S)) is the exact product
+// plus ONE IEEE rounding at ulp 2^S, i.e. the rounded right shift by S (round-to-nearest-even == RND::CONV,
+// round toward -inf == TRN::TCPL).  Returns the quantized product BIASED by the constant's bit pattern
+// fp_kbits<S>(); clamps are applied on the biased bits (monotone).
+template <int S> __host__ __device__ constexpr int fp_kbits() { return ((150 + S) << 23) | 0x400000; }   // bits of 1.5 * 2^(23+S)
+template <int S, bool CT> QB_DEV int fp_mul_apply(float a, float b, const QStage &q)
+{
+    constexpr float Cm = (float)(3ull << (22 + S));                    // 1.5 * 2^(23+S), exact
+    const float t = q.qu == RND_CONV ? __fmaf_rn(a, b, Cm) : __fmaf_rd(a, b, Cm);
+    int bits = __float_as_int(t);
+    if (q.need_hi) bits = imin<int>(bits, (int)q.hi + fp_kbits<S>());
+    if (q.need_lo) bits = imax<int>(bits, (int)q.lo + fp_kbits<S>());
+    return bits;
 }
 
 // Non-power-of-two counts: run the host-built flush program over the pending stack entries

@@ -39,7 +39,7 @@ QB_DEV void cgemv_rows_body(const int2 *__restrict__ H, const int2 *__restrict__
     typedef typename Cfg::I I;
     constexpr int M = Cfg::M, K = Cfg::K, NTOP = Cfg::NLEV - 3;
     static_assert(Cfg::N == 1 && (K & (K - 1)) == 0 && K >= 8, "mat-vec with power-of-two K");
-    __shared__ int xc[K], xd[K], xcd[K];
+    __shared__ int xc[K], xd[K], xcd[K];          // c, d, c+d: raw ints, or exact floats where the product runs on the FMA pipe
     constexpr TfProg tf = Cfg::tf();
     constexpr AddStage r0 = Cfg::lvl_re(0), r1 = Cfg::lvl_re(1), r2 = Cfg::lvl_re(2);
     constexpr AddStage i0 = Cfg::lvl_im(0), i1 = Cfg::lvl_im(1), i2 = Cfg::lvl_im(2);
@@ -50,8 +50,10 @@ QB_DEV void cgemv_rows_body(const int2 *__restrict__ H, const int2 *__restrict__
         __syncthreads();                                   // previous instance finished with xc/xd/xcd
         for (int k = i; k < K; k += M) {
             const int2 x = __ldg(X + inst * K + k);
-            xc[k] = x.x; xd[k] = x.y;
-            xcd[k] = (int)add_apply<I, true>((I)x.x, (I)x.y, tf.cd);     // Qadd<cdT>(c, d), QuBLAS.h:3525
+            const int cdv = (int)add_apply<I, true>((I)x.x, (I)x.y, tf.cd);       // Qadd<cdT>(c, d), QuBLAS.h:3525
+            xc[k] = Cfg::FP_A ? __float_as_int(__int2float_rn(x.x)) : x.x;
+            xd[k] = Cfg::FP_C ? __float_as_int(__int2float_rn(x.y)) : x.y;
+            xcd[k] = Cfg::FP_B ? __float_as_int(__int2float_rn(cdv)) : cdv;
         }
         __syncthreads();
         const int2 *Hi = H + inst * (uint64_t)M * K + i;
@@ -69,9 +71,13 @@ QB_DEV void cgemv_rows_body(const int2 *__restrict__ H, const int2 *__restrict__
                 const I a = h[u].x, b = h[u].y, cc = xc[k], d = xd[k], cd = xcd[k];
                 const I ab = add_apply<I, true>(a, b, tf.ab);            // :3524
                 const I ba = add_apply<I, true>(b, a, tf.ba);            // :3526 (default merger: baT is ignored upstream)
-                const I A = mul_apply<I, true>(ab, cc, tf.A);
-                const I Bv = mul_apply<I, true>(cd, b, tf.B);
-                const I Cv = mul_apply<I, true>(ba, d, tf.C);
+                I A, Bv, Cv;
+                if constexpr (Cfg::FP_A) A = (I)(fp_mul_apply<Cfg::SH_A, true>(__int2float_rn((int)ab), __int_as_float((int)cc), tf.A) - fp_kbits<Cfg::SH_A>());
+                else A = mul_apply<I, true>(ab, cc, tf.A);
+                if constexpr (Cfg::FP_B) Bv = (I)(fp_mul_apply<Cfg::SH_B, true>(__int_as_float((int)cd), __int2float_rn((int)b), tf.B) - fp_kbits<Cfg::SH_B>());
+                else Bv = mul_apply<I, true>(cd, b, tf.B);
+                if constexpr (Cfg::FP_C) Cv = (I)(fp_mul_apply<Cfg::SH_C, true>(__int2float_rn((int)ba), __int_as_float((int)d), tf.C) - fp_kbits<Cfg::SH_C>());
+                else Cv = mul_apply<I, true>(ba, d, tf.C);
                 pr[u] = add_apply<I, true>(A, Bv, tf.re);                // :3528
                 pi[u] = add_apply<I, true>(Bv, Cv, tf.im);               // :3529
             }

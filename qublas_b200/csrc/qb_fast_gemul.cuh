@@ -79,20 +79,6 @@ QB_DEV void stack_push(I (&st)[NTOP > 0 ? NTOP : 1], uint32_t c, I v, I &result)
     }
 }
 
-// Qmul<MulArgs> through the FP32 FMA pipe (see qb_codegen.cpp): returns the quantized product BIASED by
-// the bit pattern of the magic constant; unbias by subtracting fp_kbits<S>() (folded into the first tree add).
-template <int S> __host__ __device__ constexpr int fp_kbits() { return ((150 + S) << 23) | 0x400000; }   // bits of 1.5 * 2^(23+S)
-template <int S, bool CT> QB_DEV int fp_mul_apply(float a, float b, const QStage &q)
-{
-    constexpr float Cm = (float)(3ull << (22 + S));                    // 1.5 * 2^(23+S), exact
-    const float t = q.qu == RND_CONV ? __fmaf_rn(a, b, Cm)             // one IEEE round-to-nearest-even at ulp 2^S
-                                     : __fmaf_rd(a, b, Cm);            // TRN::TCPL: round toward -inf
-    int bits = __float_as_int(t);                                      // = fp_kbits + round(a*b / 2^S), monotone in the value
-    if (q.need_hi) bits = imin<int>(bits, (int)q.hi + fp_kbits<S>());
-    if (q.need_lo) bits = imax<int>(bits, (int)q.lo + fp_kbits<S>());
-    return bits;
-}
-
 constexpr QStage stage_without_clamps(QStage q) { q.need_lo = 0; q.need_hi = 0; return q; }
 
 // One instance's 4x4 register tile.  CLAMP = false is the same arithmetic with Qmul's saturation removed;

@@ -269,7 +269,7 @@ TVal build_tree(uint64_t count, TVal leaf, const qb_levels &L, int form, TreePro
     return cur;
 }
 
-TfProg build_tf(TVal a, TVal b, TVal c, TVal d, const qb_tfc_types &t, TVal *re, TVal *im, Analysis &an)
+TfProg build_tf(TVal a, TVal b, TVal c, TVal d, const qb_tfc_types &t, TVal *re, TVal *im, Analysis &an, TVal *mid)
 {
     TfProg p;
     memset(&p, 0, sizeof(p));
@@ -279,6 +279,7 @@ TfProg build_tf(TVal a, TVal b, TVal c, TVal d, const qb_tfc_types &t, TVal *re,
     p.ab = make_add(a, b, t.ab, false, &ab, an);          // QuBLAS.h:3524 Qadd<abT>(a, b)
     p.cd = make_add(c, d, t.cd, false, &cd, an);          // :3525 Qadd<cdT>(c, d)
     p.ba = make_add(b, a, t.ba, true, &ba, an);           // :3526 Qsub(b, a)
+    if (mid) { mid[0] = ab; mid[1] = cd; mid[2] = ba; }
     p.A = make_mul(ab, c, t.abc, &A, an);                 // :3524
     p.B = make_mul(cd, b, t.bad, &B, an);                 // :3525
     p.C = make_mul(ba, d, t.cdb, &C, an);                 // :3526

@@ -41,7 +41,7 @@ AddStage make_add(TVal a, TVal b, qb_qdesc to, bool sub, TVal *out, Analysis &an
 // Tree over `count` leaves of type/interval `leaf`.  Returns the result's type/interval.
 TVal build_tree(uint64_t count, TVal leaf, const qb_levels &L, int form, TreeProg *prog, Analysis &an);
 
-TfProg build_tf(TVal a, TVal b, TVal c, TVal d, const qb_tfc_types &t, TVal *re, TVal *im, Analysis &an);
+TfProg build_tf(TVal a, TVal b, TVal c, TVal d, const qb_tfc_types &t, TVal *re, TVal *im, Analysis &an, TVal *mid = nullptr /* [3]: ab, cd, ba */);
 
 struct ReduceProg {
     TreeProg tree;
