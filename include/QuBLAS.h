@@ -14,6 +14,7 @@
 //   FullPrec, MulMerger / AddMerger result types             :3079-3140    detail::merge_*
 //   Qmul / Qadd / Qsub on scalars                            :3142-3235, :3980-3999  constexpr, header-only
 //   TFComplexMul<abT,cdT,baT,abcT,cdbT,badT,ABT,BCT>         :3453-3535    incl. its routing quirks
+//   BasicComplexMul<acT,bdT,adT,bcT,acbdT,adbcT>, Qmul(c1,c2) :3376-3446    4 mult / 2 add (default complex product)
 //   Qreduce<Args...>(tensor) / (scalars...)                  :4903-5018    tensor form -> GPU
 //   Qgemul<QgemulAddArgs<>,QgemulMulArgs<>,QgemulTransposedA<>>(C,A,B)   readme.md:80-87 -> GPU
 //
@@ -381,6 +382,12 @@ public:
 // ------------------------------------------------------------------------------------------------
 template <class... Args> struct TFComplexMul {};
 template <class... Args> struct BasicComplexMul {};
+template <class... Args> struct acT {};
+template <class... Args> struct bdT {};
+template <class... Args> struct adT {};
+template <class... Args> struct bcT {};
+template <class... Args> struct acbdT {};
+template <class... Args> struct adbcT {};
 template <class... Args> struct abT {};
 template <class... Args> struct cdT {};
 template <class... Args> struct baT {};
@@ -439,6 +446,28 @@ template <class... Pack> constexpr TfSpec tf_resolve(const Spec &a, const Spec &
     r.BC = merge(r.bad, r.cdb, tf_partial<BCT, Pack...>(), false);
     return r;
 }
+struct BcmSpec { Spec ac, bd, ad, bc, acbd, adbc; };
+// Resolved node types of BasicComplexMul (QuBLAS.h:3426-3446): re = ac - bd, im = ad + bc.
+template <class... Pack> constexpr BcmSpec bcm_resolve(const Spec &a, const Spec &b, const Spec &c, const Spec &d)
+{
+    BcmSpec r{};
+    r.ac = merge(a, c, tf_partial<acT, Pack...>(), true);
+    r.bd = merge(b, d, tf_partial<bdT, Pack...>(), true);
+    r.ad = merge(a, d, tf_partial<adT, Pack...>(), true);
+    r.bc = merge(b, c, tf_partial<bcT, Pack...>(), true);
+    r.acbd = merge(r.ac, r.bd, tf_partial<acbdT, Pack...>(), false);
+    r.adbc = merge(r.ad, r.bc, tf_partial<adbcT, Pack...>(), false);
+    return r;
+}
+constexpr qb_bcm_types lower(const BcmSpec &t)
+{
+    return qb_bcm_types{ lower(t.ac), lower(t.bd), lower(t.ad), lower(t.bc), lower(t.acbd), lower(t.adbc) };
+}
+template <class T> struct bcm_pack { static constexpr bool is_bcm = false; };
+template <class... P> struct bcm_pack<BasicComplexMul<P...>> {
+    static constexpr bool is_bcm = true;
+    static constexpr BcmSpec resolve(const Spec &a, const Spec &b, const Spec &c, const Spec &d) { return bcm_resolve<P...>(a, b, c, d); }
+};
 constexpr qb_tfc_types lower(const TfSpec &t)
 {
     return qb_tfc_types{ lower(t.ab), lower(t.cd), lower(t.ba), lower(t.abc), lower(t.bad), lower(t.cdb), lower(t.AB), lower(t.BC) };
@@ -474,6 +503,21 @@ constexpr auto Qmul(const X x, const Y y)
     auto C = Qmul<detail::scalar_of<t.cdb>>(ba, y.imag);
     auto re = Qsub<detail::scalar_of<t.AB>>(A, B);
     auto im = Qsub<detail::scalar_of<t.BC>>(B, C);
+    return Qcomplex<decltype(re), decltype(im)>(re, im);
+}
+// complex scalar product with BasicComplexMul: 4 multipliers / 2 adders (QuBLAS.h:3437-3445);
+// Qmul(c1, c2) without a method uses it with default types (QuBLAS.h:3422-3424)
+template <class BCM = BasicComplexMul<>, class X, class Y>
+    requires(detail::bcm_pack<BCM>::is_bcm && detail::is_complex<X>::value && detail::is_complex<Y>::value)
+constexpr auto Qmul(const X x, const Y y)
+{
+    constexpr detail::BcmSpec t = detail::bcm_pack<BCM>::resolve(X::realType::spec, X::imagType::spec, Y::realType::spec, Y::imagType::spec);
+    auto ac = Qmul<detail::scalar_of<t.ac>>(x.real, y.real);
+    auto bd = Qmul<detail::scalar_of<t.bd>>(x.imag, y.imag);
+    auto ad = Qmul<detail::scalar_of<t.ad>>(x.real, y.imag);
+    auto bc = Qmul<detail::scalar_of<t.bc>>(x.imag, y.real);
+    auto re = Qsub<detail::scalar_of<t.acbd>>(ac, bd);
+    auto im = Qadd<detail::scalar_of<t.adbc>>(ad, bc);
     return Qcomplex<decltype(re), decltype(im)>(re, im);
 }
 // component-wise complex add with one level type for both parts (QuBLAS.h:3549-3563)
@@ -624,6 +668,16 @@ template <bool V, class... Rest> struct gemul_tags<QgemulTransposedB<V>, Rest...
 template <class L> struct first_is_tf { static constexpr bool value = false; using type = void; };
 template <class... P, class... R> struct first_is_tf<TypeList<TFComplexMul<P...>, R...>> { static constexpr bool value = true; using type = TFComplexMul<P...>; };
 
+template <class L> struct first_is_bcm { using type = BasicComplexMul<>; };
+template <class... P, class... R> struct first_is_bcm<TypeList<BasicComplexMul<P...>, R...>> { using type = BasicComplexMul<P...>; };
+template <class TFL> struct tf_or_default {
+    static constexpr TfSpec resolve(const Spec &a, const Spec &b, const Spec &c, const Spec &d)
+    {
+        if constexpr (TFL::value) return tf_pack<typename TFL::type>::resolve(a, b, c, d);
+        else return tf_resolve<>(a, b, c, d);
+    }
+};
+
 template <class T> struct dims_of;
 template <std::size_t R, std::size_t C, class E> struct dims_of<Qu_s<dim<R, C>, E>> { static constexpr std::size_t rows = R, cols = C; using elem = E; };
 template <std::size_t R, class E> struct dims_of<Qu_s<dim<R>, E>> { static constexpr std::size_t rows = R, cols = 1; using elem = E; };   // vector = R x 1
@@ -693,6 +747,31 @@ auto Qmul(const Qu_s<dim<D...>, EX> &x, const Qu_s<dim<D...>, EY> &y)
         p.x_re = detail::lower(EX::realType::spec); p.x_im = detail::lower(EX::imagType::spec);
         p.y_re = detail::lower(EY::realType::spec); p.y_im = detail::lower(EY::imagType::spec);
         p.tf = detail::lower(t);
+        p.len = dim<D...>::elemSize;
+        return p;
+    }();
+    Qu_s<dim<D...>, R> out;
+    qb_exec ex{ QB_MEM_HOST, -1, nullptr, 0, 0 };
+    detail::check(qb200_tfcmul_batched(&plan, x.raw(), y.raw(), out.raw(), 1, &ex));
+    return out;
+}
+
+// tensor Qmul<BasicComplexMul<...>>(x, y) / Qmul(x, y): element-wise 4-mult/2-add complex product on the GPU
+template <class BCM = BasicComplexMul<>, std::size_t... D, class EX, class EY>
+    requires(detail::bcm_pack<BCM>::is_bcm && detail::is_complex<EX>::value && detail::is_complex<EY>::value)
+auto Qmul(const Qu_s<dim<D...>, EX> &x, const Qu_s<dim<D...>, EY> &y)
+{
+    static constexpr detail::BcmSpec t = detail::bcm_pack<BCM>::resolve(EX::realType::spec, EX::imagType::spec, EY::realType::spec, EY::imagType::spec);
+    using R = Qcomplex<detail::scalar_of<t.acbd>, detail::scalar_of<t.adbc>>;
+    static_assert(sizeof(typename EX::realType) == sizeof(typename EX::imagType) && sizeof(typename EY::realType) == sizeof(typename EY::imagType) &&
+                  sizeof(detail::scalar_of<t.acbd>) == sizeof(detail::scalar_of<t.adbc>),
+                  "complex parts with different storage words are not supported on the GPU path");
+    static constexpr qb_tfcmul_plan plan = [] {
+        qb_tfcmul_plan p{};
+        p.x_re = detail::lower(EX::realType::spec); p.x_im = detail::lower(EX::imagType::spec);
+        p.y_re = detail::lower(EY::realType::spec); p.y_im = detail::lower(EY::imagType::spec);
+        p.bcm = detail::lower(t);
+        p.product = QB_CPROD_BASIC;
         p.len = dim<D...>::elemSize;
         return p;
     }();

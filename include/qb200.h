@@ -17,7 +17,8 @@
  *   qb200_cgemul_batched   <- the same call with Qcomplex elements and
  *                             MulArgs = TFComplexMul<abT..BCT>       include/QuBLAS.h:3453-3535,
  *                             accumulated with complex Qadd           include/QuBLAS.h:3549-3568
- *   qb200_tfcmul_batched   <- tensor Qmul<TFComplexMul<...>>(x, y)    include/QuBLAS.h:3783-3811, 4080-4085
+ *   qb200_tfcmul_batched   <- tensor Qmul<TFComplexMul<...>>(x, y) / Qmul<BasicComplexMul<...>>(x, y)
+ *                             include/QuBLAS.h:3783-3811, 4080-4085, 3426-3446
  *   qb200_convert_batched  <- element-wise converting assignment      include/QuBLAS.h:2398-2411, 2759-2830
  *
  * All functions return 0 on success and a negative QB_E* code on failure; the message is
@@ -34,7 +35,7 @@
 extern "C" {
 #endif
 
-#define QB200_ABI_VERSION 1
+#define QB200_ABI_VERSION 2
 #define QB_MAX_LEVELS 64
 
 /* QuMode ids == the reference's ::value constants (QuBLAS.h:1988-1998). */
@@ -110,22 +111,36 @@ typedef struct qb_tfc_types {
     qb_qdesc ab, cd, ba, abc, bad, cdb, AB, BC;
 } qb_tfc_types;
 
-/* Complex Qgemul with TFComplexMul products and component-wise tree accumulation. */
+/* Resolved types of the BasicComplexMul dataflow (QuBLAS.h:3426-3446), x = a+bi, y = c+di:
+ *   ac, bd, ad, bc = the four products; re = ac - bd (acbd), im = ad + bc (adbc). */
+typedef struct qb_bcm_types {
+    qb_qdesc ac, bd, ad, bc, acbd, adbc;
+} qb_bcm_types;
+
+enum qb_cproduct { QB_CPROD_TF = 0, QB_CPROD_BASIC = 1 };
+
+/* Complex Qgemul with TFComplexMul (product == QB_CPROD_TF, uses .tf) or BasicComplexMul
+ * (product == QB_CPROD_BASIC, uses .bcm) products and component-wise tree accumulation. */
 typedef struct qb_cgemul_plan {
     qb_qdesc     a_re, a_im, b_re, b_im;
     qb_tfc_types tf;
+    qb_bcm_types bcm;
     qb_levels    add_re, add_im;
     qb_qdesc     c_re, c_im;
     uint32_t     M, N, K;
-    uint8_t      trans_a, trans_b, tree_form, reserved;
+    uint8_t      trans_a, trans_b, tree_form, product;   /* product: enum qb_cproduct */
     int64_t      stride_a, stride_b, stride_c;   /* in complex elements */
 } qb_cgemul_plan;
 
-/* Element-wise TFComplexMul of two complex vectors (output type = {AB, BC}). */
+/* Element-wise complex product of two complex vectors: TFComplexMul (output type {AB, BC}) or
+ * BasicComplexMul (output type {acbd, adbc}). */
 typedef struct qb_tfcmul_plan {
     qb_qdesc     x_re, x_im, y_re, y_im;
     qb_tfc_types tf;
+    qb_bcm_types bcm;
     uint64_t     len;
+    uint32_t     product;     /* enum qb_cproduct */
+    uint32_t     reserved;
 } qb_tfcmul_plan;
 
 /* Element-wise conversion from -> to (converting ctor, target's modes). */

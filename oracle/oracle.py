@@ -130,7 +130,7 @@ def cgemul_batched(plan: abi.qb_cgemul_plan, A, B, batch):
 
 
 def tfcmul_batched(plan: abi.qb_tfcmul_plan, x, y, batch):
-    wb = cword_bytes(plan.tf.AB, plan.tf.BC)
+    wb = cword_bytes(plan.bcm.acbd, plan.bcm.adbc) if plan.product == abi.QB_CPROD_BASIC else cword_bytes(plan.tf.AB, plan.tf.BC)
     out = np.zeros(2 * batch * plan.len, dtype=np_dtype(wb))
     x = np.ascontiguousarray(x); y = np.ascontiguousarray(y)
     rc = load().qbo_tfcmul_batched(C.byref(plan), _ptr(x), _ptr(y), _ptr(out), batch)

@@ -321,14 +321,25 @@ static cval tfcmul(cval x, cval y, const qb_tfc_types *t)
     return r;
 }
 
+/* BasicComplexMul::mul, QuBLAS.h:3437-3445, on resolved node types. */
+static cval bcmul(cval x, cval y, const qb_bcm_types *t)
+{
+    qval a = x.re, b = x.im, c = y.re, d = y.im;
+    cval r;
+    r.re = qbo_qsub(qbo_qmul(a, c, t->ac), qbo_qmul(b, d, t->bd), t->acbd);      /* :3439 */
+    r.im = qbo_qadd(qbo_qmul(a, d, t->ad), qbo_qmul(b, c, t->bc), t->adbc);      /* :3440 */
+    return r;
+}
+
 int qbo_tfcmul_batched(const qb_tfcmul_plan *p, const void *x, const void *y, void *out, uint64_t batch)
 {
-    int wx = cword_bytes(p->x_re, p->x_im), wy = cword_bytes(p->y_re, p->y_im), wo = cword_bytes(p->tf.AB, p->tf.BC);
+    int wx = cword_bytes(p->x_re, p->x_im), wy = cword_bytes(p->y_re, p->y_im);
+    int wo = p->product == QB_CPROD_BASIC ? cword_bytes(p->bcm.acbd, p->bcm.adbc) : cword_bytes(p->tf.AB, p->tf.BC);
     size_t n = (size_t)(p->len * batch);
     for (size_t i = 0; i < n; i++) {
         cval X = { { load_word(x, 2 * i, wx), p->x_re }, { load_word(x, 2 * i + 1, wx), p->x_im } };
         cval Y = { { load_word(y, 2 * i, wy), p->y_re }, { load_word(y, 2 * i + 1, wy), p->y_im } };
-        cval r = tfcmul(X, Y, &p->tf);
+        cval r = p->product == QB_CPROD_BASIC ? bcmul(X, Y, &p->bcm) : tfcmul(X, Y, &p->tf);
         store_word(out, 2 * i, wo, r.re.raw);
         store_word(out, 2 * i + 1, wo, r.im.raw);
     }
@@ -354,11 +365,11 @@ int qbo_cgemul_batched(const qb_cgemul_plan *p, const void *A, const void *B, vo
                     size_t ib = ob + (p->trans_b ? (j + k * N) : (k + j * K));
                     cval X = { { load_word(A, 2 * ia, wa), p->a_re }, { load_word(A, 2 * ia + 1, wa), p->a_im } };
                     cval Y = { { load_word(B, 2 * ib, wbb), p->b_re }, { load_word(B, 2 * ib + 1, wbb), p->b_im } };
-                    cval r = tfcmul(X, Y, &p->tf);
+                    cval r = p->product == QB_CPROD_BASIC ? bcmul(X, Y, &p->bcm) : tfcmul(X, Y, &p->tf);
                     xr[k] = (int64_t)r.re.raw; xi[k] = (int64_t)r.im.raw;
                 }
-                qval rr = tree(xr, K, p->tf.AB, &p->add_re, p->tree_form);
-                qval ri = tree(xi, K, p->tf.BC, &p->add_im, p->tree_form);
+                qval rr = tree(xr, K, p->product == QB_CPROD_BASIC ? p->bcm.acbd : p->tf.AB, &p->add_re, p->tree_form);
+                qval ri = tree(xi, K, p->product == QB_CPROD_BASIC ? p->bcm.adbc : p->tf.BC, &p->add_im, p->tree_form);
                 size_t ic = oc + i + j * M;
                 store_word(C, 2 * ic, wc, qbo_conv(rr.raw, rr.t.frac_bits, p->c_re));
                 store_word(C, 2 * ic + 1, wc, qbo_conv(ri.raw, ri.t.frac_bits, p->c_im));

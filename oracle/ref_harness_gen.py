@@ -212,6 +212,28 @@ def tf_cases(rng):
     return cases
 
 
+BCM_TAGS = ["acT", "bdT", "adT", "bcT", "acbdT", "adbcT"]
+
+
+def bcm_cases(rng):
+    """Qmul<BasicComplexMul<...>>(x, y) and the default Qmul(x, y) on complex scalars (QuBLAS.h:3422-3446)."""
+    cases = []
+    t44 = T(4, 4)
+    cases.append({"kind": "bcm", "x_re": t44, "x_im": t44, "y_re": t44, "y_im": t44, "tags": {}, "default": True})
+    for rep in range(10):
+        def rt(lo=2, hi=8):
+            return T(rng.randint(lo, hi), rng.randint(0, 8), rng.random() < 0.85, rng.randrange(7), rng.randrange(4))
+        xr, xi, yr, yi = rt(), rt(), rt(), rt()
+        tags = {}
+        for name in BCM_TAGS:
+            if rng.random() < 0.7:
+                tags[name] = rt(4, 14)
+        if len(tags) == 1:      # a pack of exactly ONE tag does not compile upstream (tagExtractor's single-argument
+            tags = {}           # specialisation strips the wrapper, QuBLAS.h:158-162,173-177), so it cannot occur in user code
+        cases.append({"kind": "bcm", "x_re": xr, "x_im": xi, "y_re": yr, "y_im": yi, "tags": tags, "default": False})
+    return cases
+
+
 def gemul_cases(rng):
     cases = []
     type1 = T(6, 3, True, 5, 1)     # readme.md:31  Qu<isSigned<true>,intBits<6>,fracBits<3>,OfMode<SAT::ZERO>>
@@ -313,6 +335,17 @@ def emit_tf(c, idx):
     return "static void case_%d(const int64_t *in, int64_t *out) { %s }\n" % (idx, body)
 
 
+def emit_bcm(c, idx):
+    X = "Qcomplex<%s, %s>" % (cxx_type(c["x_re"]), cxx_type(c["x_im"]))
+    Y = "Qcomplex<%s, %s>" % (cxx_type(c["y_re"]), cxx_type(c["y_im"]))
+    call = "Qmul(x, y)" if c["default"] else "Qmul<BasicComplexMul<%s>>(x, y)" % emit_tf_args(c["tags"])
+    body = ("%s x; x.real = mk<%s>(in[0]); x.imag = mk<%s>(in[1]); %s y; y.real = mk<%s>(in[2]); y.imag = mk<%s>(in[3]); "
+            "auto r = %s; out[0] = (int64_t)r.real.data.data; out[1] = (int64_t)r.imag.data.data; "
+            "put_type(out + 2, r.real); put_type(out + 7, r.imag);"
+            % (X, cxx_type(c["x_re"]), cxx_type(c["x_im"]), Y, cxx_type(c["y_re"]), cxx_type(c["y_im"]), call))
+    return "static void case_%d(const int64_t *in, int64_t *out) { %s }\n" % (idx, body)
+
+
 def emit_gemul(c, idx):
     M, N, K = c["M"], c["N"], c["K"]
     A, B, P, C = (cxx_type(c[k]) for k in ("a", "b", "mul", "c"))
@@ -357,7 +390,7 @@ def emit_fromdouble(c, idx):
     return "static void case_%d(const int64_t *in, int64_t *out) { %s out[0] = (int64_t)r.data.data; put_type(out + 1, r); }\n" % (idx, body)
 
 
-EMIT = {"fromdouble": emit_fromdouble, "scalar": emit_scalar, "reduce": emit_reduce, "tf": emit_tf, "gemul": emit_gemul, "cgemul": emit_cgemul}
+EMIT = {"bcm": emit_bcm, "fromdouble": emit_fromdouble, "scalar": emit_scalar, "reduce": emit_reduce, "tf": emit_tf, "gemul": emit_gemul, "cgemul": emit_cgemul}
 
 
 def n_inputs(c):
@@ -365,7 +398,7 @@ def n_inputs(c):
     if k == "scalar": return 2
     if k == "fromdouble": return 1
     if k == "reduce": return c["len"]
-    if k == "tf": return 4
+    if k == "tf" or k == "bcm": return 4
     if k == "gemul": return c["M"] * c["K"] + c["K"] * c["N"]
     if k == "cgemul": return 4 * c["K"]
 
@@ -373,7 +406,7 @@ def n_inputs(c):
 def n_outputs(c):
     k = c["kind"]
     if k == "scalar" or k == "reduce" or k == "fromdouble": return 6
-    if k == "tf" or k == "cgemul": return 12
+    if k == "tf" or k == "cgemul" or k == "bcm": return 12
     if k == "gemul": return c["M"] * c["N"]
 
 
@@ -398,6 +431,8 @@ def gen_inputs(rng, c):
     if k == "reduce":
         reps = 6 if c["len"] <= 64 else 3
         return [[rand_raw(rng, c["elem"]) for _ in range(c["len"])] for _ in range(reps)]
+    if k == "bcm":
+        return [[rand_raw(rng, c["x_re"]), rand_raw(rng, c["x_im"]), rand_raw(rng, c["y_re"]), rand_raw(rng, c["y_im"])] for _ in range(48)]
     if k == "tf":
         sets = [[rand_raw(rng, c["x_re"]), rand_raw(rng, c["x_im"]), rand_raw(rng, c["y_re"]), rand_raw(rng, c["y_im"])]
                 for _ in range(48)]
@@ -467,7 +502,7 @@ def build_harness(cases, include_dir, out_dir, tag, n_tu=8, extra_flags=()):
 
 
 def all_cases(rng):
-    return scalar_cases(rng) + reduce_cases(rng) + tf_cases(rng) + gemul_cases(rng) + cgemul_cases(rng) + fromdouble_cases(rng)
+    return scalar_cases(rng) + reduce_cases(rng) + tf_cases(rng) + gemul_cases(rng) + cgemul_cases(rng) + fromdouble_cases(rng) + bcm_cases(rng)
 
 
 def main():

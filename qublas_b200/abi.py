@@ -40,18 +40,25 @@ class qb_tfc_types(C.Structure):
     _fields_ = [(k, qb_qdesc) for k in ("ab", "cd", "ba", "abc", "bad", "cdb", "AB", "BC")]
 
 
+class qb_bcm_types(C.Structure):
+    _fields_ = [(k, qb_qdesc) for k in ("ac", "bd", "ad", "bc", "acbd", "adbc")]
+
+
+QB_CPROD_TF, QB_CPROD_BASIC = 0, 1
+
+
 class qb_cgemul_plan(C.Structure):
     _fields_ = [("a_re", qb_qdesc), ("a_im", qb_qdesc), ("b_re", qb_qdesc), ("b_im", qb_qdesc),
-                ("tf", qb_tfc_types), ("add_re", qb_levels), ("add_im", qb_levels),
+                ("tf", qb_tfc_types), ("bcm", qb_bcm_types), ("add_re", qb_levels), ("add_im", qb_levels),
                 ("c_re", qb_qdesc), ("c_im", qb_qdesc),
                 ("M", C.c_uint32), ("N", C.c_uint32), ("K", C.c_uint32),
-                ("trans_a", C.c_uint8), ("trans_b", C.c_uint8), ("tree_form", C.c_uint8), ("reserved", C.c_uint8),
+                ("trans_a", C.c_uint8), ("trans_b", C.c_uint8), ("tree_form", C.c_uint8), ("product", C.c_uint8),
                 ("stride_a", C.c_int64), ("stride_b", C.c_int64), ("stride_c", C.c_int64)]
 
 
 class qb_tfcmul_plan(C.Structure):
     _fields_ = [("x_re", qb_qdesc), ("x_im", qb_qdesc), ("y_re", qb_qdesc), ("y_im", qb_qdesc),
-                ("tf", qb_tfc_types), ("len", C.c_uint64)]
+                ("tf", qb_tfc_types), ("bcm", qb_bcm_types), ("len", C.c_uint64), ("product", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class qb_convert_plan(C.Structure):
@@ -90,6 +97,13 @@ def levels(ts: Optional[Sequence[QType]]) -> qb_levels:
     for k, t in enumerate(ts):
         L.lv[k] = desc(t)
     return L
+
+
+def bcm_types(r) -> qb_bcm_types:
+    t = qb_bcm_types()
+    for k in ("ac", "bd", "ad", "bc", "acbd", "adbc"):
+        setattr(t, k, desc(r[k]))
+    return t
 
 
 def tfc_types(r) -> qb_tfc_types:

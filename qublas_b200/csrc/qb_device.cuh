@@ -125,6 +125,16 @@ QB_DEV void tf_apply(I a, I b, I c, I d, const TfProg &t, I &re, I &im)
     im = add_apply<I, CT>(Bv, Cv, t.im);
 }
 
+// BasicComplexMul::mul, QuBLAS.h:3437-3445.
+template <typename I, bool CT>
+QB_DEV void bcm_apply(I a, I b, I c, I d, const BcmProg &t, I &re, I &im)
+{
+    I ac = mul_apply<I, CT>(a, c, t.ac), bd = mul_apply<I, CT>(b, d, t.bd);
+    I ad = mul_apply<I, CT>(a, d, t.ad), bc = mul_apply<I, CT>(b, c, t.bc);
+    re = add_apply<I, CT>(ac, bd, t.re);
+    im = add_apply<I, CT>(ad, bc, t.im);
+}
+
 // Qmul through the FP32 FMA pipe (see qb_codegen.cpp:fp_mul_ok): fma(a, b, 1.5 * 2^(23+S)) is the exact product
 // plus ONE IEEE rounding at ulp 2^S, i.e. the rounded right shift by S (round-to-nearest-even == RND::CONV,
 // round toward -inf == TRN::TCPL).  Returns the quantized product BIASED by the constant's bit pattern

@@ -190,7 +190,7 @@ k_gemul_thread(const void *__restrict__ A, const void *__restrict__ B, void *__r
 template <typename I>
 __global__ void __launch_bounds__(128)
 k_cgemul_thread(const void *__restrict__ A, const void *__restrict__ B, void *__restrict__ C, uint64_t batch,
-                const __grid_constant__ GemulShape S, const __grid_constant__ TfProg tf,
+                const __grid_constant__ GemulShape S, const int kind, const __grid_constant__ TfProg tf, const __grid_constant__ BcmProg bcm,
                 const __grid_constant__ TreeProg Pre, const __grid_constant__ TreeProg Pim,
                 const __grid_constant__ QStage out_re, const __grid_constant__ QStage out_im)
 {
@@ -207,7 +207,8 @@ k_cgemul_thread(const void *__restrict__ A, const void *__restrict__ B, void *__
         I a = load_word<I>(A, 2 * ia, S.a_wb), b = load_word<I>(A, 2 * ia + 1, S.a_wb);
         I c = load_word<I>(B, 2 * ib, S.b_wb), d = load_word<I>(B, 2 * ib + 1, S.b_wb);
         I vr, vi;
-        tf_apply<I, false>(a, b, c, d, tf, vr, vi);
+        if (kind == 1) bcm_apply<I, false>(a, b, c, d, bcm, vr, vi);
+        else tf_apply<I, false>(a, b, c, d, tf, vr, vi);
         unsigned l = 0; uint64_t m = k;
         while (m & 1) {
             vr = merge_apply<I, false>(sr[l], vr, Pre.lvl[l]);
@@ -227,13 +228,14 @@ k_cgemul_thread(const void *__restrict__ A, const void *__restrict__ B, void *__
 // ----------------------------------------------------------------------------------------------
 template <typename I>
 __global__ void k_tfcmul(const void *__restrict__ x, const void *__restrict__ y, void *__restrict__ out, uint64_t n,
-                         int x_wb, int y_wb, int o_wb, const __grid_constant__ TfProg tf)
+                         int x_wb, int y_wb, int o_wb, const int kind, const __grid_constant__ TfProg tf, const __grid_constant__ BcmProg bcm)
 {
     for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) {
         I a = load_word<I>(x, 2 * e, x_wb), b = load_word<I>(x, 2 * e + 1, x_wb);
         I c = load_word<I>(y, 2 * e, y_wb), d = load_word<I>(y, 2 * e + 1, y_wb);
         I re, im;
-        tf_apply<I, false>(a, b, c, d, tf, re, im);
+        if (kind == 1) bcm_apply<I, false>(a, b, c, d, bcm, re, im);
+        else tf_apply<I, false>(a, b, c, d, tf, re, im);
         store_word<I>(out, 2 * e, o_wb, re);
         store_word<I>(out, 2 * e + 1, o_wb, im);
     }

@@ -277,7 +277,7 @@ static std::shared_ptr<CGemulC> get_cgemul(const qb_cgemul_plan &p)
         compile_cgemul(p, &e.prog, e.an);
         e.bits = arith_bits(e.an); e.fast = nullptr;
         if (!e.an.status) {
-            if (e.bits == 32) { sanitize32(e.prog.tf); sanitize32(e.prog.tree_re); sanitize32(e.prog.tree_im); sanitize32_stage(e.prog.out_re); sanitize32_stage(e.prog.out_im); }
+            if (e.bits == 32) { sanitize32(e.prog.tf); sanitize32(e.prog.bcm); sanitize32(e.prog.tree_re); sanitize32(e.prog.tree_im); sanitize32_stage(e.prog.out_re); sanitize32_stage(e.prog.out_im); }
             e.fast = find_fast_cgemul(p, e.prog, e.bits);
         }
     });
@@ -594,8 +594,8 @@ extern "C" int qb200_cgemul_batched(const qb_cgemul_plan *plan, const void *A, c
         const uint64_t threads = batch * ec;
         const uint64_t blocks = (threads + 127) / 128;
         if (blocks > 0x7fffffffull) return fail(QB_EINVAL, "too many outputs for one launch");
-        if (bits == 32) k_cgemul_thread<int32_t><<<(unsigned)blocks, 128, 0, cx.stream>>>(dA, dB, dC, batch, S, gp.tf, gp.tree_re, gp.tree_im, gp.out_re, gp.out_im);
-        else            k_cgemul_thread<int64_t><<<(unsigned)blocks, 128, 0, cx.stream>>>(dA, dB, dC, batch, S, gp.tf, gp.tree_re, gp.tree_im, gp.out_re, gp.out_im);
+        if (bits == 32) k_cgemul_thread<int32_t><<<(unsigned)blocks, 128, 0, cx.stream>>>(dA, dB, dC, batch, S, gp.kind, gp.tf, gp.bcm, gp.tree_re, gp.tree_im, gp.out_re, gp.out_im);
+        else            k_cgemul_thread<int64_t><<<(unsigned)blocks, 128, 0, cx.stream>>>(dA, dB, dC, batch, S, gp.kind, gp.tf, gp.bcm, gp.tree_re, gp.tree_im, gp.out_re, gp.out_im);
         if ((rc = post_launch("k_cgemul_thread"))) return rc;
     }
     if ((rc = cx.out_done(C, bytes_c, dC))) return rc;
@@ -609,18 +609,19 @@ extern "C" int qb200_tfcmul_batched(const qb_tfcmul_plan *plan, const void *x, c
                                     const qb_exec *exec)
 {
     if (!plan || !x || !y || !out) return fail(QB_EINVAL, "null argument");
-    TfProg tf; TVal re, im; Analysis an;
-    if (compile_tfcmul(*plan, &tf, &re, &im, an)) return fail(an.status, an.err);
+    TfProg tf; BcmProg bcm; TVal re, im; Analysis an;
+    if (compile_tfcmul(*plan, &tf, &bcm, &re, &im, an)) return fail(an.status, an.err);
     const uint64_t n = plan->len * batch;
     if (n == 0) return QB_OK;
     Ctx cx; int rc = cx.init(exec); if (rc) return rc;
     const int xw = std::max(word_bytes(plan->x_re), word_bytes(plan->x_im)), yw = std::max(word_bytes(plan->y_re), word_bytes(plan->y_im));
-    const int ow = std::max(natural_word(plan->tf.AB), natural_word(plan->tf.BC));
+    const int ow = plan->product == QB_CPROD_BASIC ? std::max(natural_word(plan->bcm.acbd), natural_word(plan->bcm.adbc))
+                                                   : std::max(natural_word(plan->tf.AB), natural_word(plan->tf.BC));
     const void *dx, *dy; void *dout;
     if ((rc = cx.in(x, 2 * n * xw, &dx)) || (rc = cx.in(y, 2 * n * yw, &dy)) || (rc = cx.out(out, 2 * n * ow, &dout))) return rc;
-    if (arith_bits(an) == 32) sanitize32(tf);
-    if (arith_bits(an) == 32) k_tfcmul<int32_t><<<grid_for(n, 256), 256, 0, cx.stream>>>(dx, dy, dout, n, xw, yw, ow, tf);
-    else                      k_tfcmul<int64_t><<<grid_for(n, 256), 256, 0, cx.stream>>>(dx, dy, dout, n, xw, yw, ow, tf);
+    if (arith_bits(an) == 32) { sanitize32(tf); sanitize32(bcm); }
+    if (arith_bits(an) == 32) k_tfcmul<int32_t><<<grid_for(n, 256), 256, 0, cx.stream>>>(dx, dy, dout, n, xw, yw, ow, (int)plan->product, tf, bcm);
+    else                      k_tfcmul<int64_t><<<grid_for(n, 256), 256, 0, cx.stream>>>(dx, dy, dout, n, xw, yw, ow, (int)plan->product, tf, bcm);
     if ((rc = post_launch("k_tfcmul"))) return rc;
     if ((rc = cx.out_done(out, 2 * n * ow, dout))) return rc;
     return cx.finish();

@@ -307,6 +307,27 @@ void sanitize32(TfProg &t)
 }
 void sanitize32_stage(QStage &q) { sanitize32(q); }
 
+void sanitize32(BcmProg &t)
+{
+    sanitize32(t.ac); sanitize32(t.bd); sanitize32(t.ad); sanitize32(t.bc); sanitize32(t.re.q); sanitize32(t.im.q);
+}
+
+BcmProg build_bcm(TVal a, TVal b, TVal c, TVal d, const qb_bcm_types &t, TVal *re, TVal *im, Analysis &an)
+{
+    BcmProg p;
+    memset(&p, 0, sizeof(p));
+    const qb_qdesc *all[6] = { &t.ac, &t.bd, &t.ad, &t.bc, &t.acbd, &t.adbc };
+    for (auto q : all) if (!check_type(*q, an, "BasicComplexMul node type")) return p;
+    TVal ac, bd, ad, bc;
+    p.ac = make_mul(a, c, t.ac, &ac, an);                 // QuBLAS.h:3439 Qmul<acT>(a, c)
+    p.bd = make_mul(b, d, t.bd, &bd, an);                 //               Qmul<bdT>(b, d)
+    p.ad = make_mul(a, d, t.ad, &ad, an);                 // :3440        Qmul<adT>(a, d)
+    p.bc = make_mul(b, c, t.bc, &bc, an);                 //               Qmul<bcT>(b, c)
+    p.re = make_add(ac, bd, t.acbd, true, re, an);        // :3439 Qsub<acbdT>
+    p.im = make_add(ad, bc, t.adbc, false, im, an);       // :3440 Qadd<adbcT>
+    return p;
+}
+
 static void finish(Analysis &an)
 {
     if (an.status) return;
@@ -357,7 +378,11 @@ int compile_cgemul(const qb_cgemul_plan &p, CGemulProg *out, Analysis &an)
     TVal a = { p.a_re, type_range(p.a_re) }, b = { p.a_im, type_range(p.a_im) };
     TVal c = { p.b_re, type_range(p.b_re) }, d = { p.b_im, type_range(p.b_im) };
     TVal re, im;
-    out->tf = build_tf(a, b, c, d, p.tf, &re, &im, an);
+    if (p.product > 1) { an.fail(QB_EINVAL, "bad complex product kind"); return an.status; }
+    out->kind = p.product;
+    memset(&out->tf, 0, sizeof(out->tf)); memset(&out->bcm, 0, sizeof(out->bcm));
+    if (p.product == QB_CPROD_BASIC) out->bcm = build_bcm(a, b, c, d, p.bcm, &re, &im, an);
+    else out->tf = build_tf(a, b, c, d, p.tf, &re, &im, an);
     if (an.status) return an.status;
     TVal ar = build_tree(p.K, re, p.add_re, p.tree_form, &out->tree_re, an);
     TVal ai = build_tree(p.K, im, p.add_im, p.tree_form, &out->tree_im, an);
@@ -369,13 +394,16 @@ int compile_cgemul(const qb_cgemul_plan &p, CGemulProg *out, Analysis &an)
     return an.status;
 }
 
-int compile_tfcmul(const qb_tfcmul_plan &p, TfProg *out, TVal *re, TVal *im, Analysis &an)
+int compile_tfcmul(const qb_tfcmul_plan &p, TfProg *out, BcmProg *bout, TVal *re, TVal *im, Analysis &an)
 {
+    memset(out, 0, sizeof(*out)); memset(bout, 0, sizeof(*bout));
+    if (p.product > 1) { an.fail(QB_EINVAL, "bad complex product kind"); return an.status; }
     const qb_qdesc *ts[4] = { &p.x_re, &p.x_im, &p.y_re, &p.y_im };
     for (auto t : ts) if (!check_type(*t, an, "complex element type")) return an.status;
     TVal a = { p.x_re, type_range(p.x_re) }, b = { p.x_im, type_range(p.x_im) };
     TVal c = { p.y_re, type_range(p.y_re) }, d = { p.y_im, type_range(p.y_im) };
-    *out = build_tf(a, b, c, d, p.tf, re, im, an);
+    if (p.product == QB_CPROD_BASIC) *bout = build_bcm(a, b, c, d, p.bcm, re, im, an);
+    else *out = build_tf(a, b, c, d, p.tf, re, im, an);
     finish(an);
     return an.status;
 }

@@ -55,8 +55,12 @@ struct GemulProg {
     int      a_wb, b_wb, c_wb;
     TVal     prod, acc;
 };
+BcmProg build_bcm(TVal a, TVal b, TVal c, TVal d, const qb_bcm_types &t, TVal *re, TVal *im, Analysis &an);
+
 struct CGemulProg {
+    int      kind;         // QB_CPROD_TF / QB_CPROD_BASIC
     TfProg   tf;
+    BcmProg  bcm;
     TreeProg tree_re, tree_im;
     QStage   out_re, out_im;
     int      a_wb, b_wb, c_wb;
@@ -65,7 +69,7 @@ struct CGemulProg {
 int compile_reduce(const qb_reduce_plan &p, ReduceProg *out, Analysis &an);
 int compile_gemul(const qb_gemul_plan &p, GemulProg *out, Analysis &an);
 int compile_cgemul(const qb_cgemul_plan &p, CGemulProg *out, Analysis &an);
-int compile_tfcmul(const qb_tfcmul_plan &p, TfProg *out, TVal *re, TVal *im, Analysis &an);
+int compile_tfcmul(const qb_tfcmul_plan &p, TfProg *out, BcmProg *bout, TVal *re, TVal *im, Analysis &an);
 
 // Register class of a compiled plan: 32 iff every leaf and every stage output fits int32; else 64.
 // Stages whose exact input is wider than 32 bits (e.g. a 17x16-bit product) are marked `wide` and
@@ -73,6 +77,7 @@ int compile_tfcmul(const qb_tfcmul_plan &p, TfProg *out, TVal *re, TVal *im, Ana
 inline int arith_bits(const Analysis &an) { return an.max_reg_bits <= 32 ? 32 : 64; }
 void sanitize32(TreeProg &t);
 void sanitize32(TfProg &t);
+void sanitize32(BcmProg &t);
 void sanitize32_stage(QStage &q);
 
 // tcgen05 kind::i8 legality: operands fit int8, the whole accumulation is an exact integer sum.

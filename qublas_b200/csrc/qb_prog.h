@@ -69,4 +69,10 @@ struct TfProg {
     AddStage re, im;         // A-B, B-C
 };
 
+// BasicComplexMul dataflow (QuBLAS.h:3437-3445): re = ac - bd, im = ad + bc
+struct BcmProg {
+    QStage   ac, bd, ad, bc;
+    AddStage re, im;
+};
+
 }  // namespace qb

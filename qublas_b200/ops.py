@@ -19,7 +19,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import abi
-from .qtypes import (QType, TREE_VARIADIC, TREE_VECTOR, mul_merge, resolve_tf, tree_out_type)
+from .qtypes import (QType, TREE_VARIADIC, TREE_VECTOR, mul_merge, resolve_bcm, resolve_tf, tree_out_type)
 
 try:  # torch is plumbing (device memory, streams); host-only use works without it
     import torch
@@ -163,10 +163,15 @@ def Qgemul(Cbuf, A, B, plan: abi.qb_gemul_plan, batch: int = 1, flags: int = 0):
 
 def make_cgemul_plan(a_re: QType, a_im: QType, b_re: QType, b_im: QType, c_re: QType, c_im: QType, M: int, N: int, K: int, *,
                      tf_tags=None, add_re: Optional[Sequence[QType]] = None, add_im: Optional[Sequence[QType]] = None,
-                     trans_a=False, trans_b=False, form: int = TREE_VARIADIC) -> abi.qb_cgemul_plan:
+                     trans_a=False, trans_b=False, form: int = TREE_VARIADIC, product: str = "tf") -> abi.qb_cgemul_plan:
+    """product: "tf" = TFComplexMul<tf_tags> (3 mult / 5 add), "basic" = BasicComplexMul<tf_tags> (4 mult / 2 add)."""
     p = abi.qb_cgemul_plan()
     p.a_re, p.a_im, p.b_re, p.b_im = (abi.desc(t) for t in (a_re, a_im, b_re, b_im))
-    p.tf = abi.tfc_types(resolve_tf(a_re, a_im, b_re, b_im, tf_tags))
+    if product == "basic":
+        p.product = abi.QB_CPROD_BASIC
+        p.bcm = abi.bcm_types(resolve_bcm(a_re, a_im, b_re, b_im, tf_tags))
+    else:
+        p.tf = abi.tfc_types(resolve_tf(a_re, a_im, b_re, b_im, tf_tags))
     p.add_re, p.add_im = abi.levels(add_re), abi.levels(add_im if add_im is not None else add_re)
     p.c_re, p.c_im = abi.desc(c_re), abi.desc(c_im)
     p.M, p.N, p.K = M, N, K
@@ -182,18 +187,24 @@ def Qcgemul(Cbuf, A, B, plan: abi.qb_cgemul_plan, batch: int = 1, flags: int = 0
     return Cbuf
 
 
-def tfcmul(x, y, x_re: QType, x_im: QType, y_re: QType, y_im: QType, tf_tags=None, batch: int = 1):
-    """Element-wise Qmul<TFComplexMul<tags...>>(x, y) on complex vectors (AoS pairs)."""
+def tfcmul(x, y, x_re: QType, x_im: QType, y_re: QType, y_im: QType, tf_tags=None, batch: int = 1, product: str = "tf"):
+    """Element-wise Qmul<TFComplexMul<tags...>>(x, y) (or BasicComplexMul with product="basic") on complex vectors (AoS pairs)."""
     n = (x.numel() if _is_torch(x) else x.size) // 2
     p = abi.qb_tfcmul_plan()
     p.x_re, p.x_im, p.y_re, p.y_im = (abi.desc(t) for t in (x_re, x_im, y_re, y_im))
-    r = resolve_tf(x_re, x_im, y_re, y_im, tf_tags)
-    p.tf = abi.tfc_types(r)
+    if product == "basic":
+        r = resolve_bcm(x_re, x_im, y_re, y_im, tf_tags)
+        p.bcm = abi.bcm_types(r); p.product = abi.QB_CPROD_BASIC
+        o_re, o_im = r["acbd"], r["adbc"]
+    else:
+        r = resolve_tf(x_re, x_im, y_re, y_im, tf_tags)
+        p.tf = abi.tfc_types(r)
+        o_re, o_im = r["AB"], r["BC"]
     p.len = n // batch
-    out = _new_like(x, 2 * n, max(r["AB"].word_bytes, r["BC"].word_bytes))
+    out = _new_like(x, 2 * n, max(o_re.word_bytes, o_im.word_bytes))
     ex = _exec_for(x, y)
     abi.check(abi.load().qb200_tfcmul_batched(C.byref(p), _ptr(x), _ptr(y), _ptr(out), batch, C.byref(ex)))
-    return out, (r["AB"], r["BC"])
+    return out, (o_re, o_im)
 
 
 def convert(x, src: QType, dst: QType):

@@ -120,6 +120,26 @@ def resolve_tf(x_re: QType, x_im: QType, y_re: QType, y_im: QType, tags: Optiona
     return r
 
 
+BCM_TAGS = ("acT", "bdT", "adT", "bcT", "acbdT", "adbcT")
+
+
+def resolve_bcm(x_re: QType, x_im: QType, y_re: QType, y_im: QType, tags: Optional[Dict] = None) -> Dict[str, QType]:
+    """Types of the six BasicComplexMul nodes (QuBLAS.h:3426-3446): re = ac - bd, im = ad + bc.  This is the
+    product `Qmul(c1, c2)` uses when no method is named (:3422-3424)."""
+    tags = dict(tags or {})
+    top_full = {"full": True} if tags.get("FullPrec") or tags.get("full") else None
+    g = lambda k: tags[k] if k in tags else top_full
+    a, b, c, d = x_re, x_im, y_re, y_im
+    r = {}
+    r["ac"] = mul_merge(a, c, g("acT"))
+    r["bd"] = mul_merge(b, d, g("bdT"))
+    r["ad"] = mul_merge(a, d, g("adT"))
+    r["bc"] = mul_merge(b, c, g("bcT"))
+    r["acbd"] = add_merge(r["ac"], r["bd"], g("acbdT"))
+    r["adbc"] = add_merge(r["ad"], r["bc"], g("adbcT"))
+    return r
+
+
 def level_type(levels: Sequence[QType], layer: int, a: QType, b: QType) -> QType:
     """TypeAt<min(layer, n-1)> (QuBLAS.h:4913); no levels -> default AddMerger (:4917-4921)."""
     if not levels:

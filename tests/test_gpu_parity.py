@@ -404,6 +404,36 @@ def test_c3_dynamic_clamp_elision_mixed_batch():
     assert torch.equal(Cd, gen)
 
 
+def test_basic_complex_mul_gpu():
+    """BasicComplexMul (4 mult / 2 add, the default complex product): element-wise goldens from the reference and a
+    random complex Qgemul against the oracle."""
+    from qublas_b200.qtypes import resolve_bcm
+    for c in load_cases("ref_bcm.json"):
+        xr, xi, yr, yi = (qt(c[k]) for k in ("x_re", "x_im", "y_re", "y_im"))
+        wx = max(xr.word_bytes, xi.word_bytes); wy = max(yr.word_bytes, yi.word_bytes)
+        x = np.array([i[0:2] for i in c["inputs"]], dtype=oracle.np_dtype(wx)).reshape(-1)
+        y = np.array([i[2:4] for i in c["inputs"]], dtype=oracle.np_dtype(wy)).reshape(-1)
+        out, _ = ops.tfcmul(dev(x), dev(y), xr, xi, yr, yi, tf_tags(c["tags"]), product="basic")
+        got = out.cpu().numpy().reshape(-1, 2)
+        assert [[int(a), int(b)] for a, b in got] == [o[0:2] for o in c["outputs"]], c["tags"]
+    rng = np.random.default_rng(21)
+    ar, ai, br, bi = QType(4, 7), QType(3, 8), QType(5, 6, True, 4, 2), QType(4, 6)
+    tags = {"acT": QType(9, 8, True, 4, 0), "bdT": QType(8, 9, True, 0, 1), "adT": QType(9, 7), "bcT": QType(9, 8, True, 6, 3),
+            "acbdT": QType(10, 6, True, 3, 0), "adbcT": QType(10, 7, True, 2, 2)}
+    r = resolve_bcm(ar, ai, br, bi, tags)
+    lre = _rand_levels(rng, r["acbd"], 4); lim = _rand_levels(rng, r["adbc"], 4)
+    for (M, N, K, form) in [(4, 3, 16, TREE_VARIADIC), (8, 2, 7, TREE_VECTOR)]:
+        plan = ops.make_cgemul_plan(ar, ai, br, bi, QType(12, 4, True, 4, 0), QType(12, 3), M, N, K, tf_tags=tags, add_re=lre, add_im=lim,
+                                    form=form, product="basic")
+        batch = 4
+        A = np.stack([rand_words(rng, ar, batch * M * K), rand_words(rng, ai, batch * M * K)], axis=1).astype(np.int32).reshape(-1)
+        B = np.stack([rand_words(rng, br, batch * K * N), rand_words(rng, bi, batch * K * N)], axis=1).astype(np.int32).reshape(-1)
+        want = oracle.cgemul_batched(plan, A, B, batch)
+        Cd = torch.empty(batch * M * N * 2, dtype=torch.int32, device="cuda")
+        ops.Qcgemul(Cd, dev(A), dev(B), plan, batch=batch)
+        assert np.array_equal(Cd.cpu().numpy(), want), (M, N, K, form)
+
+
 def test_synth_fill_matches_oracle_all_word_sizes():
     for wb, lo, hi in [(1, -127, 127), (2, -(1 << 15), (1 << 15) - 1), (4, -65536, 65535), (8, -(1 << 40), (1 << 40))]:
         t = torch.empty(10007, dtype={1: torch.int8, 2: torch.int16, 4: torch.int32, 8: torch.int64}[wb], device="cuda")

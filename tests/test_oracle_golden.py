@@ -6,7 +6,7 @@ import pytest
 
 from oracle import oracle
 from qublas_b200 import abi
-from qublas_b200.qtypes import (QType, TREE_VARIADIC, TREE_VECTOR, add_merge, mul_merge, resolve_tf,
+from qublas_b200.qtypes import (QType, TREE_VARIADIC, TREE_VECTOR, add_merge, mul_merge, resolve_bcm, resolve_tf,
                                 tree_out_type)
 from tests.helpers import (cgemul_plan, form_id, gemul_plan, load_cases, np_words, qt, reduce_plan, tf_tags,
                            tfcmul_plan)
@@ -102,6 +102,30 @@ def test_tfcmul_matches_reference():
             assert [int(got[0]), int(got[1])] == out[0:2], (c["tags"], inp, out, got)
     # SURVEY 2.5 golden: x=(37,-22), y=(-51,19) -> re -44 (11.3), im 29 (12.2)
     assert cases[0]["inputs"][0] == [37, -22, -51, 19] and cases[0]["outputs"][0][0:2] == [-44, 29]
+
+
+def test_basic_complex_mul_matches_reference():
+    """Qmul<BasicComplexMul<...>>(x, y) and the default Qmul(x, y) on complex scalars (QuBLAS.h:3422-3446)."""
+    import struct
+    cases = load_cases("ref_bcm.json")
+    for c in cases:
+        xr, xi, yr, yi = (qt(c[k]) for k in ("x_re", "x_im", "y_re", "y_im"))
+        r = resolve_bcm(xr, xi, yr, yi, tf_tags(c["tags"]))
+        p = abi.qb_tfcmul_plan()
+        p.x_re, p.x_im, p.y_re, p.y_im = (abi.desc(t) for t in (xr, xi, yr, yi))
+        p.bcm = abi.bcm_types(r); p.product = abi.QB_CPROD_BASIC; p.len = 1
+        wx = max(xr.word_bytes, xi.word_bytes); wy = max(yr.word_bytes, yi.word_bytes)
+        for inp, out in zip(c["inputs"], c["outputs"]):
+            assert out[2:7] == type_tuple(r["acbd"]) and out[7:12] == type_tuple(r["adbc"])
+            got = oracle.tfcmul_batched(p, np.array(inp[:2], dtype=oracle.np_dtype(wx)), np.array(inp[2:], dtype=oracle.np_dtype(wy)), 1)
+            assert [int(got[0]), int(got[1])] == out[:2], (c["tags"], inp)
+    # SURVEY 2.5: BasicComplexMul of x=(37,-22), y=(-51,19) in 4.4 types -> re -91, im 113
+    t44 = QType(4, 4)
+    r = resolve_bcm(t44, t44, t44, t44, None)
+    p = abi.qb_tfcmul_plan()
+    p.x_re = p.x_im = p.y_re = p.y_im = abi.desc(t44); p.bcm = abi.bcm_types(r); p.product = abi.QB_CPROD_BASIC; p.len = 1
+    got = oracle.tfcmul_batched(p, np.array([37, -22], dtype=np.int32), np.array([-51, 19], dtype=np.int32), 1)
+    assert [int(got[0]), int(got[1])] == [-91, 113]
 
 
 def test_gemul_matches_reference_composition():
