@@ -165,7 +165,7 @@ def roofline_alu(lib, gmacs, device):
     achieved thread-instruction rate (instructions per MAC from the committed ncu capture,
     profiles/r1_c3_ncu_summary.json) with the issue peak measured live by qb200_measure_int_peak."""
     from qublas_b200 import abi
-    out = {"bound": "issue (INT32 ALU + FP32 FMA pipes)", "unit": "T thread-instr/s"}
+    out = {"bound": "issue (INT32 ALU + FP32 FMA pipes)", "unit": "T thread-instr/s", "scope": "per GPU"}
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "r1_c3_ncu_summary.json")))[0]
         ipm = float(prof["thread_instructions_per_unit"])
@@ -311,7 +311,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                          "note": "this kernel is bound by the INT32 issue rate, not HBM: see roofline_alu"},
-            "roofline_alu": roofline_alu(lib, value, local),
+            "roofline_alu": roofline_alu(lib, value / world, local),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "GMAC/s", "h2d_bytes_per_step": e2e_instances * 2 * WORDS * 4,
                     "d2h_bytes_per_step": e2e_instances * WORDS * 4},

@@ -710,16 +710,20 @@ void Qgemul(CT &C, const AT &A, const BT &B)
         }();
         detail::check(qb200_gemul_batched(&plan, A.raw(), B.raw(), C.raw(), 1, &ex));
     } else {
+        // complex elements: QgemulMulArgs<TFComplexMul<...>> (3 mult / 5 add) or BasicComplexMul<...> / nothing (4 mult / 2 add)
         using TFL = detail::first_is_tf<typename G::mul>;
-        static_assert(TFL::value, "Qgemul on complex tensors needs QgemulMulArgs<TFComplexMul<...>> (BasicComplexMul is not on the GPU path yet)");
-        static constexpr detail::TfSpec tf = detail::tf_pack<typename TFL::type>::resolve(EA::realType::spec, EA::imagType::spec, EB::realType::spec, EB::imagType::spec);
+        using BCL = detail::first_is_bcm<typename G::mul>;
+        static constexpr detail::TfSpec tf = detail::tf_or_default<TFL>::resolve(EA::realType::spec, EA::imagType::spec, EB::realType::spec, EB::imagType::spec);
+        static constexpr detail::BcmSpec bcm = detail::bcm_pack<typename BCL::type>::resolve(EA::realType::spec, EA::imagType::spec, EB::realType::spec, EB::imagType::spec);
+        static constexpr detail::Spec leaf_re = TFL::value ? tf.AB : bcm.acbd, leaf_im = TFL::value ? tf.BC : bcm.adbc;
         using Low = detail::reduce_lowering<typename G::add, K>;
         static constexpr qb_cgemul_plan plan = [] {
             qb_cgemul_plan p{};
             p.a_re = detail::lower(EA::realType::spec); p.a_im = detail::lower(EA::imagType::spec);
             p.b_re = detail::lower(EB::realType::spec); p.b_im = detail::lower(EB::imagType::spec);
-            p.tf = detail::lower(tf);
-            p.add_re = Low::levels(tf.AB); p.add_im = Low::levels(tf.BC);
+            if constexpr (TFL::value) { p.tf = detail::lower(tf); p.product = QB_CPROD_TF; }
+            else { p.bcm = detail::lower(bcm); p.product = QB_CPROD_BASIC; }
+            p.add_re = Low::levels(leaf_re); p.add_im = Low::levels(leaf_im);
             p.c_re = detail::lower(EC::realType::spec); p.c_im = detail::lower(EC::imagType::spec);
             p.M = (uint32_t)M; p.N = (uint32_t)N; p.K = (uint32_t)K;
             p.trans_a = G::ta; p.trans_b = G::tb; p.tree_form = QB_TREE_VARIADIC;

@@ -1,0 +1,75 @@
+// C++ drop-in boundary, batched and complex entry points: every GPU result is compared with the
+// header's own scalar (host, constexpr) arithmetic, which tests/test_host_header.py pins against the
+// reference's goldens.  Prints "OK" lines; any mismatch returns 1.  Exit code 3 = no CUDA device.
+#include "QuBLAS.h"
+#include <cstdio>
+
+using namespace QuBLAS;
+
+using in_t  = Qu<intBits<7>, fracBits<8>>;
+using mul_t = Qu<intBits<14>, fracBits<8>, QuMode<RND::CONV>, OfMode<SAT::TCPL>>;
+template <int l> using lv = Qu<intBits<15 + l>, fracBits<8 - l>, QuMode<RND::POS_INF>, OfMode<SAT::TCPL>>;
+using levels = TypeList<lv<0>, lv<1>, lv<2>, lv<3>>;
+using c_t = Qu<intBits<17>, fracBits<4>, QuMode<RND::POS_INF>, OfMode<SAT::TCPL>>;
+
+int main()
+{
+    int bad = 0;
+    try {
+        // ---- batched real Qgemul: 16x16x16, 40 instances in one call ----
+        using A_t = Qu<dim<16, 16>, in_t>; using C_t = Qu<dim<16, 16>, c_t>;
+        const std::size_t n = 40;
+        Qbatch<A_t> A(n), B(n); Qbatch<C_t> C(n);
+        A.synth(1, 0); B.synth(1, 1);
+        QgemulBatched<QgemulAddArgs<levels>, QgemulMulArgs<mul_t>>(C, A, B);
+        for (std::size_t inst : { (std::size_t)0, (std::size_t)17, n - 1 }) {
+            A_t a = A.get(inst), b = B.get(inst); C_t c = C.get(inst);
+            for (int i = 0; i < 16; i++) for (int j = 0; j < 16; j++) {
+                mul_t p[16];
+                for (int k = 0; k < 16; k++) p[k] = Qmul<mul_t>(a[i, k], b[k, j]);
+                c_t want = Qreduce<levels>(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8], p[9], p[10], p[11], p[12], p[13], p[14], p[15]);
+                if (want.data.data != c[i, j].data.data) bad++;
+            }
+        }
+        std::printf("batched Qgemul: %s\n", bad ? "MISMATCH" : "OK");
+
+        // ---- complex Qgemul (8x8 times 8x1) with TFComplexMul and with the default BasicComplexMul ----
+        using t = Qu<intBits<3>, fracBits<12>>;
+        using cx = Qcomplex<t, t>;
+        using P = Qu<intBits<6>, fracBits<12>>; using S = Qu<intBits<7>, fracBits<12>>;
+        using TF = TFComplexMul<abT<Qu<intBits<4>, fracBits<12>>>, cdT<Qu<intBits<4>, fracBits<11>>>, abcT<P>, cdbT<P>, badT<P>, ABT<S>, BCT<S>>;
+        using clv = TypeList<Qu<intBits<8>, fracBits<12>, QuMode<RND::CONV>>, Qu<intBits<9>, fracBits<11>, QuMode<RND::CONV>>, Qu<intBits<10>, fracBits<10>, QuMode<RND::CONV>>>;
+        using out_s = Qu<intBits<10>, fracBits<10>, QuMode<RND::CONV>>;
+        using H_t = Qu<dim<8, 8>, cx>; using x_t = Qu<dim<8>, cx>; using y_t = Qu<dim<8>, Qcomplex<out_s, out_s>>;
+        H_t H; x_t x; y_t y, yb;
+        for (std::size_t i = 0; i < 64; i++) { H[i].real.fill(); H[i].imag.fill(); }
+        for (std::size_t i = 0; i < 8; i++) { x[i].real.fill(); x[i].imag.fill(); }
+        Qgemul<QgemulAddArgs<clv>, QgemulMulArgs<TF>>(y, H, x);
+        Qgemul<QgemulAddArgs<clv>>(yb, H, x);                                   // no MulArgs: BasicComplexMul<>
+        int bad_tf = 0, bad_b = 0;
+        for (int i = 0; i < 8; i++) {
+            auto w = Qreduce<clv>(Qmul<TF>(H[i, 0], x[0]), Qmul<TF>(H[i, 1], x[1]), Qmul<TF>(H[i, 2], x[2]), Qmul<TF>(H[i, 3], x[3]),
+                                  Qmul<TF>(H[i, 4], x[4]), Qmul<TF>(H[i, 5], x[5]), Qmul<TF>(H[i, 6], x[6]), Qmul<TF>(H[i, 7], x[7]));
+            out_s wr = w.real, wi = w.imag;
+            if (wr.data.data != y[i].real.data.data || wi.data.data != y[i].imag.data.data) bad_tf++;
+            auto v = Qreduce<clv>(Qmul(H[i, 0], x[0]), Qmul(H[i, 1], x[1]), Qmul(H[i, 2], x[2]), Qmul(H[i, 3], x[3]),
+                                  Qmul(H[i, 4], x[4]), Qmul(H[i, 5], x[5]), Qmul(H[i, 6], x[6]), Qmul(H[i, 7], x[7]));
+            out_s vr = v.real, vi = v.imag;
+            if (vr.data.data != yb[i].real.data.data || vi.data.data != yb[i].imag.data.data) bad_b++;
+        }
+        std::printf("complex Qgemul TFComplexMul: %s\n", bad_tf ? "MISMATCH" : "OK");
+        std::printf("complex Qgemul BasicComplexMul: %s\n", bad_b ? "MISMATCH" : "OK");
+        bad += bad_tf + bad_b;
+
+        // ---- a vector-form Qreduce on a heap-backed (> 1000 elements) tensor: the reference cannot instantiate this ----
+        using big_t = Qu<dim<4096>, Qu<intBits<8>, fracBits<8>>>;
+        using rl = TypeList<Qu<intBits<9>, fracBits<8>>, Qu<intBits<10>, fracBits<7>, QuMode<RND::CONV>>, Qu<intBits<20>, fracBits<6>, QuMode<RND::INF>>>;
+        big_t big; big.fill();
+        auto r = Qreduce<rl>(big);
+        std::printf("Qreduce 4096: raw %lld\n", (long long)r.data.data);
+    } catch (const std::runtime_error &e) {
+        std::printf("runtime_error: %s\n", e.what());
+        return 3;
+    }
+    return bad ? 1 : 0;
+}

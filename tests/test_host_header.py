@@ -101,3 +101,27 @@ def test_readme_example_on_gpu(tmp_path):
     assert r["m3"] == [192, 448, 192, 448, 448, 448, 0, 0, 192, 0, 0, 0, 448, 0, 0, 0]      # SURVEY 3.5, TransposedA=true
     assert r["m4"] == [64, 64, 128, 448, 448, 320, 448, 0, 448, 0, 192, 256, 64, 192, 256, 384]
     assert r["cvec"] == [0, 0, 0, 0, 0, 0]
+
+
+def _build_cpp(tmp_path, name):
+    exe = str(tmp_path / name)
+    subprocess.check_call(["g++", "-std=c++23", "-O1", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-o", exe] + LINK)
+    return exe
+
+
+def test_batched_and_complex_example_compiles(tmp_path):
+    """Qbatch / QgemulBatched, complex Qgemul with TFComplexMul and with the default BasicComplexMul, a heap-backed
+    Qreduce: compiles as user code; on a box without GPU it stops at the first tensor call with std::runtime_error."""
+    exe = _build_cpp(tmp_path, "batched_example")
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode in (0, 3), p.stdout + p.stderr
+
+
+@pytest.mark.gpu
+def test_batched_and_complex_example_on_gpu(tmp_path):
+    exe = _build_cpp(tmp_path, "batched_example")
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "batched Qgemul: OK" in p.stdout and "complex Qgemul TFComplexMul: OK" in p.stdout
+    assert "complex Qgemul BasicComplexMul: OK" in p.stdout and "Qreduce 4096: raw" in p.stdout
