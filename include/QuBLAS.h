@@ -786,6 +786,38 @@ auto Qmul(const Qu_s<dim<D...>, EX> &x, const Qu_s<dim<D...>, EY> &y)
 }
 
 // ------------------------------------------------------------------------------------------------
+// element-wise Qmul / Qadd / Qsub of two real tensors: the reference returns lazy Mul/Add/SubExpression
+// objects evaluated per element (QuBLAS.h:3741-3811, 4080-4156); here the same per-element result is
+// computed eagerly on the GPU and returned as a tensor of the merger's result type.
+// ------------------------------------------------------------------------------------------------
+namespace detail {
+template <int OP, class... toArgs, std::size_t... D, class EA, class EB>
+auto tensor_ew(const Qu_s<dim<D...>, EA> &a, const Qu_s<dim<D...>, EB> &b)
+{
+    static constexpr Spec t = merge(EA::spec, EB::spec, parse<toArgs...>(), OP == QB_EW_MUL);
+    static constexpr qb_ew_plan plan = [] {
+        qb_ew_plan p{};
+        p.a = lower(EA::spec); p.b = lower(EB::spec); p.to = lower(t);
+        p.len = dim<D...>::elemSize; p.op = OP;
+        return p;
+    }();
+    Qu_s<dim<D...>, scalar_of<t>> out;
+    qb_exec ex{ QB_MEM_HOST, -1, nullptr, 0, 0 };
+    check(qb200_elementwise_batched(&plan, a.raw(), b.raw(), out.raw(), 1, &ex));
+    return out;
+}
+}  // namespace detail
+template <class... toArgs, std::size_t... D, class EA, class EB>
+    requires(detail::is_scalar<EA>::value && detail::is_scalar<EB>::value)
+auto Qmul(const Qu_s<dim<D...>, EA> &a, const Qu_s<dim<D...>, EB> &b) { return detail::tensor_ew<QB_EW_MUL, toArgs...>(a, b); }
+template <class... toArgs, std::size_t... D, class EA, class EB>
+    requires(detail::is_scalar<EA>::value && detail::is_scalar<EB>::value)
+auto Qadd(const Qu_s<dim<D...>, EA> &a, const Qu_s<dim<D...>, EB> &b) { return detail::tensor_ew<QB_EW_ADD, toArgs...>(a, b); }
+template <class... toArgs, std::size_t... D, class EA, class EB>
+    requires(detail::is_scalar<EA>::value && detail::is_scalar<EB>::value)
+auto Qsub(const Qu_s<dim<D...>, EA> &a, const Qu_s<dim<D...>, EB> &b) { return detail::tensor_ew<QB_EW_SUB, toArgs...>(a, b); }
+
+// ------------------------------------------------------------------------------------------------
 // Batched ("Monte-Carlo") containers: `count` tensors of one type in ONE contiguous raw buffer, so a
 // whole accuracy sweep is a single C-ABI call sharded by batch (tensors above 1000 elements are
 // std::vector-backed in the reference, QuBLAS.h:2694-2697, so an array of tensors is not contiguous).

@@ -143,6 +143,16 @@ typedef struct qb_tfcmul_plan {
     uint32_t     reserved;
 } qb_tfcmul_plan;
 
+/* Element-wise Qmul / Qadd / Qsub of two real tensors (the reference's lazy Mul/Add/SubExpression evaluated
+ * eagerly, include/QuBLAS.h:3741-3811, 4080-4156): out[i] = op<to>(a[i], b[i]); `to` = resolved merger type. */
+enum qb_ewop { QB_EW_MUL = 0, QB_EW_ADD = 1, QB_EW_SUB = 2 };
+typedef struct qb_ew_plan {
+    qb_qdesc a, b, to;
+    uint64_t len;
+    uint32_t op;          /* enum qb_ewop */
+    uint32_t reserved;
+} qb_ew_plan;
+
 /* Element-wise conversion from -> to (converting ctor, target's modes). */
 typedef struct qb_convert_plan {
     qb_qdesc from, to;
@@ -204,6 +214,9 @@ int qb200_tfcmul_batched(const qb_tfcmul_plan *plan, const void *x, const void *
 
 int qb200_convert_batched(const qb_convert_plan *plan, const void *in, void *out,
                           uint64_t batch, const qb_exec *exec);
+
+int qb200_elementwise_batched(const qb_ew_plan *plan, const void *a, const void *b, void *out,
+                              uint64_t batch, const qb_exec *exec);
 
 /* ---- the steps on either side of the path in an accuracy sweep ----
  * qb200_quantize_f64  <- Qu_s(double)  include/QuBLAS.h:2387-2393 (exact value, the type's QuMode, then its OfMode)

@@ -42,6 +42,7 @@ def load():
         L.qbo_cgemul_batched.argtypes = [C.POINTER(abi.qb_cgemul_plan), vp, vp, vp, u64]
         L.qbo_tfcmul_batched.argtypes = [C.POINTER(abi.qb_tfcmul_plan), vp, vp, vp, u64]
         L.qbo_convert_batched.argtypes = [C.POINTER(abi.qb_convert_plan), vp, vp, u64]
+        L.qbo_elementwise_batched.argtypes = [C.POINTER(abi.qb_ew_plan), vp, vp, vp, u64]
         L.qbo_synth_fill.argtypes = [vp, u64, u32, i64, i64, u64, u64, u64]
         dp = C.POINTER(C.c_double)
         L.qbo_from_double.restype = i64; L.qbo_from_double.argtypes = [C.c_double, qd]
@@ -177,3 +178,11 @@ def error_stats(t: QType, w, ref):
     a, b, c = C.c_double(), C.c_double(), C.c_double()
     assert load().qbo_error_stats(C.byref(abi.desc(t)), _ptr(w), _ptr(ref), w.size, C.byref(a), C.byref(b), C.byref(c)) == 0
     return a.value, b.value, c.value
+
+
+def elementwise(plan: abi.qb_ew_plan, a, b, batch=1):
+    to = abi.qtype_of(plan.to)
+    out = np.zeros(batch * plan.len, dtype=np_dtype(plan.to.word_bytes or to.word_bytes))
+    a = np.ascontiguousarray(a); b = np.ascontiguousarray(b)
+    assert load().qbo_elementwise_batched(C.byref(plan), _ptr(a), _ptr(b), _ptr(out), batch) == 0
+    return out

@@ -461,3 +461,16 @@ int qbo_error_stats(const qb_qdesc *t, const void *words, const double *ref, uin
     *sum_sq_err = se; *sum_sq_ref = sr; *max_abs_err = mx;
     return QB_OK;
 }
+
+/* element-wise Qmul / Qadd / Qsub of two tensors (the reference's lazy expressions, QuBLAS.h:3783-3811, evaluated per element) */
+int qbo_elementwise_batched(const qb_ew_plan *p, const void *a, const void *b, void *out, uint64_t batch)
+{
+    int wa = word_bytes_of(p->a), wb = word_bytes_of(p->b), wo = word_bytes_of(p->to);
+    size_t n = (size_t)(p->len * batch);
+    for (size_t i = 0; i < n; i++) {
+        qval x = { load_word(a, i, wa), p->a }, y = { load_word(b, i, wb), p->b };
+        qval r = p->op == QB_EW_MUL ? qbo_qmul(x, y, p->to) : (p->op == QB_EW_ADD ? qbo_qadd(x, y, p->to) : qbo_qsub(x, y, p->to));
+        store_word(out, i, wo, r.raw);
+    }
+    return QB_OK;
+}

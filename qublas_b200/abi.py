@@ -61,6 +61,13 @@ class qb_tfcmul_plan(C.Structure):
                 ("tf", qb_tfc_types), ("bcm", qb_bcm_types), ("len", C.c_uint64), ("product", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class qb_ew_plan(C.Structure):
+    _fields_ = [("a", qb_qdesc), ("b", qb_qdesc), ("to", qb_qdesc), ("len", C.c_uint64), ("op", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+QB_EW_MUL, QB_EW_ADD, QB_EW_SUB = 0, 1, 2
+
+
 class qb_convert_plan(C.Structure):
     _fields_ = [("from_", qb_qdesc), ("to", qb_qdesc), ("len", C.c_uint64)]
 
@@ -118,7 +125,7 @@ ABI_SYMBOLS = [
     "qb200_abi_version", "qb200_last_error", "qb200_device_count", "qb200_launch_count",
     "qb200_launch_count_reset", "qb200_reduce_plan_info", "qb200_gemul_plan_info", "qb200_cgemul_plan_info",
     "qb200_reduce_batched", "qb200_gemul_batched", "qb200_cgemul_batched", "qb200_tfcmul_batched",
-    "qb200_convert_batched", "qb200_synth_fill", "qb200_shard_range", "qb200_measure_int_peak", "qb200_jit_check_gemul", "qb200_quantize_f64", "qb200_dequantize_f64", "qb200_error_stats",
+    "qb200_convert_batched", "qb200_elementwise_batched", "qb200_synth_fill", "qb200_shard_range", "qb200_measure_int_peak", "qb200_jit_check_gemul", "qb200_quantize_f64", "qb200_dequantize_f64", "qb200_error_stats",
 ]
 
 _LIB = None
@@ -152,6 +159,7 @@ def load() -> C.CDLL:
     L.qb200_cgemul_batched.argtypes = [C.POINTER(qb_cgemul_plan), vp, vp, vp, u64, C.POINTER(qb_exec)]
     L.qb200_tfcmul_batched.argtypes = [C.POINTER(qb_tfcmul_plan), vp, vp, vp, u64, C.POINTER(qb_exec)]
     L.qb200_convert_batched.argtypes = [C.POINTER(qb_convert_plan), vp, vp, u64, C.POINTER(qb_exec)]
+    L.qb200_elementwise_batched.argtypes = [C.POINTER(qb_ew_plan), vp, vp, vp, u64, C.POINTER(qb_exec)]
     L.qb200_synth_fill.argtypes = [vp, u64, u32, i64, i64, u64, u64, u64, C.POINTER(qb_exec)]
     L.qb200_shard_range.argtypes = [u64, u32, u32, C.POINTER(u64), C.POINTER(u64)]
     L.qb200_quantize_f64.argtypes = [C.POINTER(qb_qdesc), vp, vp, u64, C.POINTER(qb_exec)]

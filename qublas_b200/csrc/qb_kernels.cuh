@@ -249,6 +249,18 @@ __global__ void k_convert(const void *__restrict__ in, void *__restrict__ out, u
         store_word<I>(out, e, out_wb, conv_apply<I, false>(load_word<I>(in, e, in_wb), q));
 }
 
+// element-wise Qmul / Qadd / Qsub (op 0 / 1 / 2)
+template <typename I>
+__global__ void k_elementwise(const void *__restrict__ a, const void *__restrict__ b, void *__restrict__ out, uint64_t n, int a_wb, int b_wb,
+                              int o_wb, int op, const __grid_constant__ AddStage st)
+{
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) {
+        const I x = load_word<I>(a, e, a_wb), y = load_word<I>(b, e, b_wb);
+        const I r = op == 0 ? mul_apply<I, false>(x, y, st.q) : add_apply<I, false>(x, y, st);
+        store_word<I>(out, e, o_wb, r);
+    }
+}
+
 __global__ void k_synth_fill(void *__restrict__ dst, uint64_t count, int wb, int64_t lo, uint64_t span, uint64_t key,
                              uint64_t first_index)
 {

@@ -865,3 +865,31 @@ extern "C" int qb200_error_stats(const qb_qdesc *type, const void *words, const 
     stats->sum_sq_err = h[0]; stats->sum_sq_ref = h[1]; stats->max_abs_err = h[2];
     return cx.finish();
 }
+
+// ---------------------------------------------------------------------------------------------
+// element-wise Qmul / Qadd / Qsub on tensors
+// ---------------------------------------------------------------------------------------------
+extern "C" int qb200_elementwise_batched(const qb_ew_plan *plan, const void *a, const void *b, void *out, uint64_t batch, const qb_exec *exec)
+{
+    if (!plan || !a || !b || !out) return fail(QB_EINVAL, "null argument");
+    if (plan->op > 2) return fail(QB_EINVAL, "bad element-wise op");
+    Analysis an;
+    if (!check_type(plan->a, an, "a type") || !check_type(plan->b, an, "b type") || !check_type(plan->to, an, "result type")) return fail(an.status, an.err);
+    TVal ta = { plan->a, type_range(plan->a) }, tb = { plan->b, type_range(plan->b) }, o;
+    AddStage st; memset(&st, 0, sizeof(st));
+    if (plan->op == QB_EW_MUL) st.q = make_mul(ta, tb, plan->to, &o, an);
+    else st = make_add(ta, tb, plan->to, plan->op == QB_EW_SUB, &o, an);
+    if (an.status) return fail(an.status, an.err);
+    if (an.ref_width > 64 || an.max_bits > 64) return fail(QB_EDOMAIN, "an intermediate would be wider than 64 bits");
+    const uint64_t n = plan->len * batch;
+    if (n == 0) return QB_OK;
+    Ctx cx; int rc = cx.init(exec); if (rc) return rc;
+    const int aw = word_bytes(plan->a), bw = word_bytes(plan->b), ow = word_bytes(plan->to);
+    const void *da, *db; void *dout;
+    if ((rc = cx.in(a, n * aw, &da)) || (rc = cx.in(b, n * bw, &db)) || (rc = cx.out(out, n * ow, &dout))) return rc;
+    if (arith_bits(an) == 32) { sanitize32_stage(st.q); k_elementwise<int32_t><<<grid_for(n, 256), 256, 0, cx.stream>>>(da, db, dout, n, aw, bw, ow, (int)plan->op, st); }
+    else k_elementwise<int64_t><<<grid_for(n, 256), 256, 0, cx.stream>>>(da, db, dout, n, aw, bw, ow, (int)plan->op, st);
+    if ((rc = post_launch("k_elementwise"))) return rc;
+    if ((rc = cx.out_done(out, n * ow, dout))) return rc;
+    return cx.finish();
+}

@@ -19,7 +19,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import abi
-from .qtypes import (QType, TREE_VARIADIC, TREE_VECTOR, mul_merge, resolve_bcm, resolve_tf, tree_out_type)
+from .qtypes import (QType, TREE_VARIADIC, TREE_VECTOR, add_merge, mul_merge, resolve_bcm, resolve_tf, tree_out_type)
 
 try:  # torch is plumbing (device memory, streams); host-only use works without it
     import torch
@@ -205,6 +205,26 @@ def tfcmul(x, y, x_re: QType, x_im: QType, y_re: QType, y_im: QType, tf_tags=Non
     ex = _exec_for(x, y)
     abi.check(abi.load().qb200_tfcmul_batched(C.byref(p), _ptr(x), _ptr(y), _ptr(out), batch, C.byref(ex)))
     return out, (o_re, o_im)
+
+
+def make_ew_plan(op: str, ta: QType, tb: QType, n: int, to=None) -> abi.qb_ew_plan:
+    """op in {"mul", "add", "sub"}; `to` = merger arguments (full QType, dict of partial tags, or None for the defaults)."""
+    p = abi.qb_ew_plan()
+    rt = to if isinstance(to, QType) else (mul_merge if op == "mul" else add_merge)(ta, tb, to)
+    p.a, p.b, p.to, p.len = abi.desc(ta), abi.desc(tb), abi.desc(rt), n
+    p.op = {"mul": abi.QB_EW_MUL, "add": abi.QB_EW_ADD, "sub": abi.QB_EW_SUB}[op]
+    return p
+
+
+def elementwise(op: str, a, b, ta: QType, tb: QType, to=None):
+    """Element-wise Qmul / Qadd / Qsub<to>(a, b) of two real tensors on the GPU; returns (out, result type)."""
+    n = a.numel() if _is_torch(a) else a.size
+    p = make_ew_plan(op, ta, tb, n, to)
+    rt = abi.qtype_of(p.to)
+    out = _new_like(a, n, rt.word_bytes)
+    ex = _exec_for(a, b)
+    abi.check(abi.load().qb200_elementwise_batched(C.byref(p), _ptr(a), _ptr(b), _ptr(out), 1, C.byref(ex)))
+    return out, rt
 
 
 def convert(x, src: QType, dst: QType):

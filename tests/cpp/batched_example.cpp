@@ -61,6 +61,21 @@ int main()
         std::printf("complex Qgemul BasicComplexMul: %s\n", bad_b ? "MISMATCH" : "OK");
         bad += bad_tf + bad_b;
 
+        // ---- element-wise tensor ops (the reference's lazy expressions, evaluated eagerly on the GPU) ----
+        {
+            using v_t = Qu<dim<100>, in_t>;
+            v_t u, w; u.fill(); w.fill();
+            auto s = Qadd<lv<0>>(u, w); auto d = Qsub<>(u, w); auto m = Qmul<mul_t>(u, w);
+            int bad_ew = 0;
+            for (std::size_t i = 0; i < 100; i++) {
+                if (s[i].data.data != Qadd<lv<0>>(u[i], w[i]).data.data) bad_ew++;
+                if (d[i].data.data != Qsub<>(u[i], w[i]).data.data) bad_ew++;
+                if (m[i].data.data != Qmul<mul_t>(u[i], w[i]).data.data) bad_ew++;
+            }
+            std::printf("element-wise Qadd/Qsub/Qmul: %s\n", bad_ew ? "MISMATCH" : "OK");
+            bad += bad_ew;
+        }
+
         // ---- a vector-form Qreduce on a heap-backed (> 1000 elements) tensor: the reference cannot instantiate this ----
         using big_t = Qu<dim<4096>, Qu<intBits<8>, fracBits<8>>>;
         using rl = TypeList<Qu<intBits<9>, fracBits<8>>, Qu<intBits<10>, fracBits<7>, QuMode<RND::CONV>>, Qu<intBits<20>, fracBits<6>, QuMode<RND::INF>>>;

@@ -434,6 +434,31 @@ def test_basic_complex_mul_gpu():
         assert np.array_equal(Cd.cpu().numpy(), want), (M, N, K, form)
 
 
+def test_elementwise_tensor_ops_vs_reference_goldens_and_oracle():
+    """Element-wise Qmul/Qadd/Qsub on tensors (next row 8(f).3): every scalar golden of the reference, run as
+    one-element-per-input tensors on the GPU, plus random large tensors against the oracle."""
+    n = 0
+    for c in load_cases("ref_scalar.json"):
+        if c["op"] == "conv":
+            continue
+        a, b = qt(c["a"]), qt(c["b"])
+        to = qt(c["to"]) if "to" in c else c.get("tags")
+        A = np_words([i[0] for i in c["inputs"]], a); B = np_words([i[1] for i in c["inputs"]], b)
+        out, rt = ops.elementwise(c["op"], dev(A), dev(B), a, b, to)
+        assert [int(v) for v in out.cpu().numpy()] == [o[0] for o in c["outputs"]], c
+        assert [rt.i, rt.f, int(rt.s), rt.q, rt.o] == c["outputs"][0][1:6]
+        n += len(A)
+    assert n > 8000
+    rng = np.random.default_rng(8)
+    for op in ("mul", "add", "sub"):
+        a = QType(9, 14, True, 3, 1); b = QType(12, 9, True, 2, 2)             # 64-bit register class for the product
+        to = QType(15, 10, True, 4, 0)
+        A = rand_words(rng, a, 100003); B = rand_words(rng, b, 100003)
+        out, _ = ops.elementwise(op, dev(A), dev(B), a, b, to)
+        want = oracle.elementwise(ops.make_ew_plan(op, a, b, 100003, to), A, B)
+        assert np.array_equal(out.cpu().numpy(), want), op
+
+
 def test_synth_fill_matches_oracle_all_word_sizes():
     for wb, lo, hi in [(1, -127, 127), (2, -(1 << 15), (1 << 15) - 1), (4, -65536, 65535), (8, -(1 << 40), (1 << 40))]:
         t = torch.empty(10007, dtype={1: torch.int8, 2: torch.int16, 4: torch.int32, 8: torch.int64}[wb], device="cuda")
