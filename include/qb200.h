@@ -186,7 +186,7 @@ typedef struct qb_exec {
 int         qb200_abi_version(void);
 const char *qb200_last_error(void);
 int         qb200_device_count(void);
-/* Number of kernels launched by this library on this thread since the last reset. */
+/* Number of kernels launched by this library (process-wide, all threads) since the last reset. */
 uint64_t    qb200_launch_count(void);
 void        qb200_launch_count_reset(void);
 
@@ -232,7 +232,8 @@ int qb200_dequantize_f64(const qb_qdesc *from, const void *in, double *out, uint
 int qb200_error_stats(const qb_qdesc *type, const void *words, const double *ref, uint64_t n, qb_err_stats *stats, const qb_exec *exec);
 
 /* Deterministic synthetic raw words, uniform over [lo, hi], counter-based:
- * word[i] = lo + mix64(seed, stream_id, first_index + i) mod (hi - lo + 1).
+ * word[i] = lo + floor(mix64(mix64(seed * C + stream_id) ^ (first_index + i)) * (hi - lo + 1) / 2^64)
+ * (splitmix64 finaliser, multiply-high range reduction; oracle/qb_oracle.c:qbo_synth_word is the twin).
  * Same function on host and device; buffers are device memory when
  * exec->mem_kind == QB_MEM_DEVICE. */
 int qb200_synth_fill(void *dst, uint64_t count, uint32_t word_bytes, int64_t lo, int64_t hi,

@@ -200,15 +200,36 @@ QB_DEV void gemul_tile_body(const int32_t *__restrict__ A, const int32_t *__rest
 #pragma unroll
             for (int part = 0; part < 2; ++part) {
                 int4 *w = (int4 *)(part ? Bs : As);
-                const int n4 = (part ? T::B_WORDS : T::A_WORDS) / 4;
-                for (int i = tid; i < n4; i += T::THREADS) {
-                    const int4 v = w[i];
-                    if constexpr (DYN) {
-                        lo[part] = imin<int>(imin<int>(imin<int>(lo[part], v.x), imin<int>(v.y, v.z)), v.w);
-                        hi[part] = imax<int>(imax<int>(imax<int>(hi[part], v.x), imax<int>(v.y, v.z)), v.w);
+                constexpr int N4A = T::A_WORDS / 4, N4B = T::B_WORDS / 4;
+                const int n4 = part ? N4B : N4A;
+                constexpr int PER = ((N4A > N4B ? N4A : N4B) + T::THREADS - 1) / T::THREADS;
+                if constexpr (PER <= 8) {
+                    // all loads of this part in flight first, then ranges / conversion / stores
+                    int4 v[PER];
+#pragma unroll
+                    for (int u = 0; u < PER; ++u) { const int i = tid + u * T::THREADS; if (i < n4) v[u] = w[i]; }
+#pragma unroll
+                    for (int u = 0; u < PER; ++u) {
+                        const int i = tid + u * T::THREADS;
+                        if (i < n4) {
+                            if constexpr (DYN) {
+                                lo[part] = imin<int>(imin<int>(imin<int>(lo[part], v[u].x), imin<int>(v[u].y, v[u].z)), v[u].w);
+                                hi[part] = imax<int>(imax<int>(imax<int>(hi[part], v[u].x), imax<int>(v[u].y, v[u].z)), v[u].w);
+                            }
+                            if constexpr (Cfg::FP_MUL)
+                                ((float4 *)w)[i] = make_float4(__int2float_rn(v[u].x), __int2float_rn(v[u].y), __int2float_rn(v[u].z), __int2float_rn(v[u].w));
+                        }
                     }
-                    if constexpr (Cfg::FP_MUL)
-                        ((float4 *)w)[i] = make_float4(__int2float_rn(v.x), __int2float_rn(v.y), __int2float_rn(v.z), __int2float_rn(v.w));
+                } else {
+                    for (int i = tid; i < n4; i += T::THREADS) {
+                        const int4 v = w[i];
+                        if constexpr (DYN) {
+                            lo[part] = imin<int>(imin<int>(imin<int>(lo[part], v.x), imin<int>(v.y, v.z)), v.w);
+                            hi[part] = imax<int>(imax<int>(imax<int>(hi[part], v.x), imax<int>(v.y, v.z)), v.w);
+                        }
+                        if constexpr (Cfg::FP_MUL)
+                            ((float4 *)w)[i] = make_float4(__int2float_rn(v.x), __int2float_rn(v.y), __int2float_rn(v.z), __int2float_rn(v.w));
+                    }
                 }
             }
             if constexpr (DYN) {
