@@ -344,11 +344,15 @@ def run_secondary(args):
     from qublas_b200 import abi, ops
     from qublas_b200.qtypes import QType, RND_CONV, RND_POS_INF, SAT_TCPL, TREE_VARIADIC, tree_out_type, resolve_tf
 
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
     lib = abi.load()
     if lib.qb200_device_count() < 1:
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
-    torch.cuda.set_device(0)
-    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -361,19 +365,28 @@ def run_secondary(args):
         for _ in range(args.warmup):
             fn()
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
         lib.qb200_launch_count_reset()
-        sampler = ClockSampler(0); sampler.start()
+        sampler = ClockSampler(local); sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         # a step of these kernels lasts ~1 ms: repeat the K-step block so that the clock sampler sees the load
         t_probe0 = time.perf_counter(); fn(); torch.cuda.synchronize(); probe = max(time.perf_counter() - t_probe0, 1e-5)
         reps = max(1, int(1.2 / (probe * args.steps)))
+        if world > 1:
+            rt = torch.tensor([reps], dtype=torch.int64, device=dev); dist.broadcast(rt, 0); reps = int(rt.item())
         lib.qb200_launch_count_reset()
         e0.record()
         for _ in range(args.steps * reps):
             fn()
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / (args.steps * reps), int(lib.qb200_launch_count()) // reps, sampler.stop()
+        ms_local = e0.elapsed_time(e1) / (args.steps * reps)
+        if world > 1:                                   # device time, max over ranks
+            tt = torch.tensor([ms_local], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms_local = float(tt.item())
+        return ms_local, int(lib.qb200_launch_count()) // reps, sampler.stop()
 
     def wall(fn, n=2):
         fn()
@@ -398,7 +411,7 @@ def run_secondary(args):
         rout = torch.empty(batch, dtype=torch.int32, device=dev)
         ms, launches, clocks = timed(lambda: ops.Qreduce(x, elem, lv, length=n, batch=batch, plan=rplan, out=rout))
         units = batch * n
-        value, unit, metric = units / (ms * 1e-3) / 1e9, "Gelem/s", "bit-exact Qreduce throughput, 2^24-element Qu<8,8> vectors, 24-level TypeList (RND::POS_INF)"
+        value, unit, metric = world * units / (ms * 1e-3) / 1e9, "Gelem/s", "bit-exact Qreduce throughput, 2^24-element Qu<8,8> vectors, 24-level TypeList (RND::POS_INF)"
         bytes_alg = units * 4 + batch * 4
         roof = {"bound": "hbm", "achieved": bytes_alg / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s"}
         hx = torch.empty(n, dtype=torch.int32).pin_memory(); hx.copy_(x[:n]); hxn = hx.numpy()
@@ -431,7 +444,7 @@ def run_secondary(args):
         assert np.array_equal(y[:Mm * 2].cpu().numpy(), want), "complex mat-vec differs from the oracle"
         ms, launches, clocks = timed(lambda: ops.Qcgemul(y, H, xv, plan, batch=batch))
         units = batch * Mm * Kk
-        value, unit, metric = units / (ms * 1e-3) / 1e9, "G complex-MAC/s", "bit-exact TFComplexMul (3-mult/5-add) complex mat-vec throughput, batched 256x256"
+        value, unit, metric = world * units / (ms * 1e-3) / 1e9, "G complex-MAC/s", "bit-exact TFComplexMul (3-mult/5-add) complex mat-vec throughput, batched 256x256"
         bytes_alg = batch * (Mm * Kk + Kk + Mm) * 8
         roof = {"bound": "hbm", "achieved": bytes_alg / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "note": "near the HBM / integer-ALU balance point (8 B and ~25 integer ops per complex MAC)"}
@@ -448,13 +461,14 @@ def run_secondary(args):
             t0 = time.perf_counter(); oracle.cgemul_batched(plan, H[:4 * Mm * Kk * 2].cpu().numpy(), xv[:4 * Kk * 2].cpu().numpy(), 4); dt = time.perf_counter() - t0
             return {"value": 4 * Mm * Kk / dt / 1e9, "unit": unit, "cores": 1, "kind": "port", "sample": "4 instances through the C oracle, 1 core"}
     else:  # c5
-        Mm = Nn = Kk = 8192
+        Mm = Kk = 8192
+        Nn = 8192 // world          # column panel of B and C per GPU (contiguous in column-major storage); A is replicated
         a = QType(7, 0); acc = QType(30, 0)
         plan = ops.make_gemul_plan(a, a, acc, Mm, Nn, Kk, mul=QType(15, 0), add=[acc])
         info = ops.plan_info_gemul(plan)
         assert info.tensor_core == 1
         A = torch.empty(Mm * Kk, dtype=torch.int32, device=dev); B = torch.empty(Kk * Nn, dtype=torch.int32, device=dev)
-        ops.synth_fill(A, -128, 127, 1, 0); ops.synth_fill(B, -128, 127, 1, 1)
+        ops.synth_fill(A, -128, 127, 1, 0); ops.synth_fill(B, -128, 127, 1, 1, rank * Kk * Nn)
         Cd = torch.empty(Mm * Nn, dtype=torch.int32, device=dev)
         ops.Qgemul(Cd, A, B, plan)
         rows = torch.arange(0, Mm, 127, device=dev)                                  # exact float64 cross-check on 65 sampled rows
@@ -462,7 +476,7 @@ def run_secondary(args):
         assert torch.equal(Cd.view(Nn, Mm).t()[rows].double(), ref), "tensor-core Qgemul differs from the exact float64 GEMM"
         ms, launches, clocks = timed(lambda: ops.Qgemul(Cd, A, B, plan))
         ops_total = 2.0 * Mm * Nn * Kk
-        value, unit, metric = ops_total / (ms * 1e-3) / 1e12, "TOP/s", "bit-exact Qgemul 8192^3, int8-range operands, lossless accumulators (tcgen05 kind::i8), incl. int32->int8 pack"
+        value, unit, metric = world * ops_total / (ms * 1e-3) / 1e12, "TOP/s", "bit-exact Qgemul 8192^3, int8-range operands, lossless accumulators (tcgen05 kind::i8), incl. int32->int8 pack"
         # library int8 GEMM on the same box = the measured tensor peak for this dtype
         A8 = torch.randint(-128, 128, (Mm, Kk), dtype=torch.int8, device=dev); B8 = torch.randint(-128, 128, (Kk, Nn), dtype=torch.int8, device=dev)
         best = 0.0
@@ -476,7 +490,7 @@ def run_secondary(args):
         except Exception:
             best = 0.0
         nominal = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
-        roof = {"bound": "tensor", "achieved": value, "peak": best if best > 0 else nominal, "unit": "TOP/s",
+        roof = {"bound": "tensor", "achieved": value / world, "peak": best if best > 0 else nominal, "unit": "TOP/s", "scope": "per GPU",
                 "peak_source": "torch._int_mm (cuBLASLt int8) 8192^3 on this box" if best > 0 else "2 x measured bf16 (nominal i8:bf16 ratio)",
                 "peak_2x_bf16": nominal}
         hA = torch.empty(Mm * Kk, dtype=torch.int32).pin_memory(); hA.copy_(A)
@@ -485,7 +499,7 @@ def run_secondary(args):
         e2e_s = wall(lambda: ops.Qgemul(hC.numpy(), hA.numpy(), hB.numpy(), plan))
         e2e = {"value": ops_total / e2e_s / 1e12, "unit": unit, "h2d_bytes_per_step": 2 * Mm * Kk * 4, "d2h_bytes_per_step": Mm * Nn * 4}
         cfg = {"workload": "BASELINE config 5: 8192^3 Qgemul, A,B Qu<7,0> raws in [-128,127], MulArgs Qu<15,0>, AddArgs Qu<30,0>, C Qu<30,0>",
-               "kernel": info.kernel.decode()}
+               "kernel": info.kernel.decode(), "sharding": "column panels of B and C (%d columns per GPU), A replicated, no collective" % Nn}
 
         def cpu():
             pl = ops.make_gemul_plan(a, a, acc, 16, 16, Kk, mul=QType(15, 0), add=[acc])
@@ -496,15 +510,21 @@ def run_secondary(args):
     roof["frac"] = roof["achieved"] / roof["peak"]
     roof["traffic"] = None
     roof.setdefault("peak_source", "MEASURED_PEAKS.json" if peaks else "fallback")
-    line = {"metric": metric, "value": value, "unit": unit, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32" if w != "c5" else "int8 x int8 -> int32",
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+    line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong" if w == "c5" else "weak", "vs_baseline": None,
+            "dtype": "int32" if w != "c5" else "int8 x int8 -> int32",
             "data": "synthetic", "config": cfg, "roofline": roof, "clocks": clocks, "e2e": e2e, "gpu_launches": launches}
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         try:
             line["cpu_baseline"] = cpu()
         except Exception as ex:      # e.g. oracle/_ref absent
             line["cpu_baseline"] = {"unavailable": str(ex)}
     print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
