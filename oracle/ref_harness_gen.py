@@ -147,6 +147,58 @@ def scalar_cases(rng):
     return cases
 
 
+def wide_cases(rng):
+    """Two-word slice: Qmul / Qadd whose exact intermediate is a 65..126-bit ArbiInt in the
+    reference.  `band` = the value compared by intConvert can reach [2^63, 2^64) (reference defect 4)."""
+    cases = []
+    for q in (0, 1, 2, 3, 5, 6):            # RND::CONV is defective on the wide path (defect 3)
+        for o in range(4):
+            for band in (False, True):
+                while True:
+                    wa, wb = rng.randint(33, 60), rng.randint(33, 60)
+                    if not 66 <= wa + wb <= 120:
+                        continue
+                    fa, fb = rng.randint(0, wa - 2), rng.randint(0, wb - 2)
+                    a = T(wa - 1 - fa, fa, True, rng.randrange(7), rng.randrange(4))
+                    b = T(wb - 1 - fb, fb, True, rng.randrange(7), rng.randrange(4))
+                    prod_bits = wa + wb
+                    s = prod_bits - (rng.randint(40, 61) if not band else rng.randint(64, 70))
+                    if s < 1 or s in BAD_SHIFTS or s > 62:
+                        continue
+                    to_f = fa + fb - s
+                    to_w = rng.randint(24, 60)
+                    to_i = to_w - 1 - to_f
+                    if to_i + to_f < 1:
+                        continue
+                    to = T(to_i, to_f, rng.random() < 0.8, q, o)
+                    if o == 3 and not to["s"] and (to_i + to_f) in (32, 64):
+                        continue
+                    break
+                cases.append({"kind": "scalar", "op": "mul", "a": a, "b": b, "to": to, "wide": True, "band": band})
+    # wide ADD: alignment shift pushes one operand beyond 64 bits
+    for q in (0, 1, 2, 3, 5, 6):
+        for o in range(4):
+            while True:
+                wa, wb = rng.randint(40, 60), rng.randint(20, 60)
+                fa = rng.randint(0, 8); fb = fa + rng.randint(10, 30)            # a is shifted left by fb - fa
+                if wa + (fb - fa) < 66 or wa + (fb - fa) > 120 or fb > wb - 2:
+                    continue
+                a = T(wa - 1 - fa, fa, True, rng.randrange(7), rng.randrange(4))
+                b = T(wb - 1 - fb, fb, True, rng.randrange(7), rng.randrange(4))
+                s = rng.randint(wa + fb - fa - 60, wa + fb - fa - 30)
+                if s < 1 or s in BAD_SHIFTS or s > 62:
+                    continue
+                to_f = fb - s
+                to_w = rng.randint(24, 60)
+                to_i = to_w - 1 - to_f
+                if to_i + to_f < 1:
+                    continue
+                to = T(to_i, to_f, True, q, o)
+                break
+            cases.append({"kind": "scalar", "op": "add", "a": a, "b": b, "to": to, "wide": True, "band": False})
+    return cases
+
+
 def level_list(rng, elem, nlev, uniform_mode=None):
     lv = []
     i, f = elem["i"], elem["f"]
@@ -502,7 +554,7 @@ def build_harness(cases, include_dir, out_dir, tag, n_tu=8, extra_flags=()):
 
 
 def all_cases(rng):
-    return scalar_cases(rng) + reduce_cases(rng) + tf_cases(rng) + gemul_cases(rng) + cgemul_cases(rng) + fromdouble_cases(rng) + bcm_cases(rng)
+    return scalar_cases(rng) + reduce_cases(rng) + tf_cases(rng) + gemul_cases(rng) + cgemul_cases(rng) + fromdouble_cases(rng) + bcm_cases(rng) + wide_cases(rng)
 
 
 def main():
@@ -520,7 +572,7 @@ def main():
         rec = dict(c)
         rec["inputs"] = ins
         rec["outputs"] = outs
-        fixtures.setdefault(c["kind"], []).append(rec)
+        fixtures.setdefault("wide" if c.get("wide") else c["kind"], []).append(rec)
     for kind, recs in fixtures.items():
         path = os.path.join(GOLD_DIR, "ref_%s.json" % kind)
         with open(path, "w") as f:

@@ -15,6 +15,9 @@ namespace qb {
 template <typename I> struct ITraits;
 template <> struct ITraits<int32_t> { typedef uint32_t U; static constexpr int BITS = 32; };
 template <> struct ITraits<int64_t> { typedef uint64_t U; static constexpr int BITS = 64; };
+#ifndef QB_JIT
+template <> struct ITraits<__int128> { typedef unsigned __int128 U; static constexpr int BITS = 128; };   // two-word intermediates
+#endif
 
 template <typename I> QB_DEV I imin(I a, I b) { return a < b ? a : b; }
 template <typename I> QB_DEV I imax(I a, I b) { return a > b ? a : b; }
@@ -81,6 +84,9 @@ template <typename I, bool CT> QB_DEV I q_apply(I v, const QStage &s)
 template <typename I, bool CT> QB_DEV I conv_apply(I v, const QStage &s)
 {
     if constexpr (sizeof(I) == 4) { if (s.wide) return (I)q_apply<int64_t, CT>((int64_t)v, s); }
+#ifndef QB_JIT
+    if constexpr (sizeof(I) == 8) { if (s.wide == 2) return (I)q_apply<__int128, CT>((__int128)v, s); }
+#endif
     return q_apply<I, CT>(v, s);
 }
 
@@ -88,6 +94,9 @@ template <typename I, bool CT> QB_DEV I conv_apply(I v, const QStage &s)
 template <typename I, bool CT> QB_DEV I mul_apply(I a, I b, const QStage &s)
 {
     if constexpr (sizeof(I) == 4) { if (s.wide) return (I)q_apply<int64_t, CT>((int64_t)a * (int64_t)b, s); }
+#ifndef QB_JIT
+    if constexpr (sizeof(I) == 8) { if (s.wide == 2) return (I)q_apply<__int128, CT>((__int128)a * (__int128)b, s); }   // 65..126-bit product
+#endif
     return q_apply<I, CT>(a * b, s);
 }
 
@@ -100,6 +109,14 @@ template <typename I, bool CT> QB_DEV I add_apply(I a, I b, const AddStage &s)
             return (I)q_apply<int64_t, CT>(s.sub ? x - y : x + y, s.q);
         }
     }
+#ifndef QB_JIT
+    if constexpr (sizeof(I) == 8) {
+        if (s.q.wide == 2) {
+            __int128 x = shl_exact<__int128>((__int128)a, s.shl_a), y = shl_exact<__int128>((__int128)b, s.shl_b);
+            return (I)q_apply<__int128, CT>(s.sub ? x - y : x + y, s.q);
+        }
+    }
+#endif
     I x = shl_exact<I>(a, s.shl_a), y = shl_exact<I>(b, s.shl_b);
     return q_apply<I, CT>(s.sub ? x - y : x + y, s.q);
 }
@@ -108,6 +125,9 @@ template <typename I, bool CT> QB_DEV I add_apply(I a, I b, const AddStage &s)
 template <typename I, bool CT> QB_DEV I merge_apply(I a, I b, const AddStage &s)
 {
     if constexpr (sizeof(I) == 4) { if (s.q.wide) return (I)q_apply<int64_t, CT>((int64_t)a + (int64_t)b, s.q); }
+#ifndef QB_JIT
+    if constexpr (sizeof(I) == 8) { if (s.q.wide == 2) return (I)q_apply<__int128, CT>((__int128)a + (__int128)b, s.q); }
+#endif
     return q_apply<I, CT>(a + b, s.q);
 }
 

@@ -635,7 +635,7 @@ extern "C" int qb200_convert_batched(const qb_convert_plan *plan, const void *in
     TVal o;
     QStage q = make_stage(plan->from.frac_bits, type_range(plan->from), width(plan->from), plan->to, &o, an);
     if (an.status) return fail(an.status, an.err);
-    if (an.max_bits > 64) return fail(QB_EDOMAIN, "conversion intermediate wider than 64 bits");
+    if (an.max_bits > 126) return fail(QB_EDOMAIN, "conversion intermediate too wide");
     an.max_reg_bits = std::max(an.max_reg_bits, width(plan->from));      // the input word itself lives in a register
     const uint64_t n = plan->len * batch;
     if (n == 0) return QB_OK;
@@ -880,7 +880,7 @@ extern "C" int qb200_elementwise_batched(const qb_ew_plan *plan, const void *a, 
     if (plan->op == QB_EW_MUL) st.q = make_mul(ta, tb, plan->to, &o, an);
     else st = make_add(ta, tb, plan->to, plan->op == QB_EW_SUB, &o, an);
     if (an.status) return fail(an.status, an.err);
-    if (an.ref_width > 64 || an.max_bits > 64) return fail(QB_EDOMAIN, "an intermediate would be wider than 64 bits");
+    if (an.ref_width > 128 || an.max_bits > 126) return fail(QB_EDOMAIN, "an intermediate would be wider than 128 bits");
     const uint64_t n = plan->len * batch;
     if (n == 0) return QB_OK;
     Ctx cx; int rc = cx.init(exec); if (rc) return rc;

@@ -83,12 +83,17 @@ QStage make_stage(int from_frac, Ival in, int in_width, qb_qdesc to, TVal *out, 
     an.max_bits = std::max(an.max_bits, bits_for(in));
     an.ref_width = std::max(an.ref_width, in_width);
     int stage_bits = bits_for(in);
+    // Two-word slice: the reference instantiates a 65..128-bit ArbiInt for this stage.  Its wide path equals the
+    // ideal model (tests/golden/ref_wide.json) except for RND::CONV (SURVEY 2.3 defect 3) and for values that reach
+    // +-[2^63, 2^64) at the overflow compare (defect 4); left shifts beyond 64 bits are untested and fenced too.
+    const bool ref_wide = in_width > 64;
     Ival r;
     if (s <= 0) {
         r = { shl(in.lo, -s), shl(in.hi, -s) };
         an.max_bits = std::max(an.max_bits, bits_for(r));
         stage_bits = std::max(stage_bits, bits_for(r));
         an.ref_width = std::max(an.ref_width, in_width - s);
+        if (in_width - s > 64) an.fail(QB_EDOMAIN, "a left shift would create an intermediate wider than 64 bits (outside the parity domain)");
     } else {
         bool rnd = to.qu_mode <= RND_CONV;
         // Reference defects: ArbiInt<32/64>::allOnes() sign-extends and
@@ -98,7 +103,11 @@ QStage make_stage(int from_frac, Ival in, int in_width, qb_qdesc to, TVal *out, 
         if (to.qu_mode == RND_CONV && (s == 31 || s == 63))
             an.fail(QB_EDOMAIN, "RND::CONV right shift of 31/63 bits hits a reference defect (outside the parity domain)");
         if (s >= 63) an.fail(QB_EDOMAIN, "right shift >= 63 not supported");
+        if (ref_wide && to.qu_mode == RND_CONV)
+            an.fail(QB_EDOMAIN, "RND::CONV on an intermediate wider than 64 bits hits a reference defect (outside the parity domain)");
         r = { round_exact(in.lo, s, to.qu_mode), round_exact(in.hi, s, to.qu_mode) };
+        if (ref_wide && bits_for(r) > 64)
+            an.fail(QB_EDOMAIN, "a >64-bit intermediate can reach +-[2^63, 2^64) at the overflow compare (reference defect, outside the parity domain)");
         i128 bias = rnd ? ((i128)1 << (s - 1)) : 0;                       // device computes (v + bias) >> s
         Ival biased = { in.lo, in.hi + bias };
         an.max_bits = std::max(an.max_bits, bits_for(biased));
@@ -147,7 +156,8 @@ QStage make_stage(int from_frac, Ival in, int in_width, qb_qdesc to, TVal *out, 
     if (st.need_lo || st.need_hi) an.lossless = false;
     an.max_bits = std::max(an.max_bits, bits_for(o));
     an.max_reg_bits = std::max(an.max_reg_bits, bits_for(o));
-    st.wide = stage_bits > 32 || s > 30 || s < -30;
+    st.wide = stage_bits > 64 ? 2 : ((stage_bits > 32 || s > 30 || s < -30) ? 1 : 0);   // 2: evaluate in __int128
+    if (st.wide == 2) an.max_reg_bits = std::max(an.max_reg_bits, 33);                   // the __int128 path lives in the 64-bit register class
     st.identity = (s <= 0 && !st.need_lo && !st.need_hi);
     if (out) { out->t = to; out->t.word_bytes = 0; out->r = o; }
     return st;
@@ -175,8 +185,9 @@ AddStage make_add(TVal a, TVal b, qb_qdesc to, bool sub, TVal *out, Analysis &an
     an.max_reg_bits = std::max(an.max_reg_bits, std::max(bits_for(a.r), bits_for(b.r)));
     Ival e = sub ? Ival{ x.lo - y.hi, x.hi - y.lo } : Ival{ x.lo + y.lo, x.hi + y.hi };
     int w = std::max(width(a.t) + sa, width(b.t) + sb) + 1;
+    if (sub && w > 64) an.fail(QB_EDOMAIN, "Qsub on an intermediate wider than 64 bits hits a reference defect (outside the parity domain)");
     s.q = make_stage(mf, e, w, to, out, an);
-    if (std::max(bits_for(x), bits_for(y)) > 32 || sa > 30 || sb > 30) s.q.wide = 1;
+    if (s.q.wide == 0 && (std::max(bits_for(x), bits_for(y)) > 32 || sa > 30 || sb > 30)) s.q.wide = 1;
     return s;
 }
 
@@ -331,10 +342,10 @@ BcmProg build_bcm(TVal a, TVal b, TVal c, TVal d, const qb_bcm_types &t, TVal *r
 static void finish(Analysis &an)
 {
     if (an.status) return;
-    if (an.ref_width > 64)
-        an.fail(QB_EDOMAIN, "an intermediate of the reference would be wider than 64 bits (two-word path not built yet)");
-    else if (an.max_bits > 64)
-        an.fail(QB_EDOMAIN, "an exact intermediate needs more than 64 bits");
+    if (an.ref_width > 128)
+        an.fail(QB_EDOMAIN, "an intermediate of the reference would be wider than 128 bits (outside the two-word slice)");
+    else if (an.max_bits > 126)
+        an.fail(QB_EDOMAIN, "an exact intermediate needs more than 126 bits");
 }
 
 int compile_reduce(const qb_reduce_plan &p, ReduceProg *out, Analysis &an)

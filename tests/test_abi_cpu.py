@@ -86,8 +86,15 @@ def test_parity_domain_fence_shifts(shift, mode, ok):
 def test_parity_domain_fence_width_and_wrap():
     lib = abi.load()
     info = abi.qb_plan_info()
-    # product of two 40-bit types is an 80-bit ArbiInt in the reference -> fenced
+    # two-word slice: the product of two 40-bit types is an 80-bit ArbiInt in the reference; after the shift by 20
+    # it fits 63 bits -> inside the parity domain (tests/golden/ref_wide.json), evaluated in __int128
     p = ops.make_gemul_plan(QType(19, 20), QType(19, 20), QType(20, 20), 2, 2, 2, mul=QType(20, 20))
+    assert lib.qb200_gemul_plan_info(C.byref(p), C.byref(info)) == 0 and info.arith_bits == 64 and info.max_inter_bits > 64
+    # ... but not when the value at the overflow compare can reach [2^63, 2^64) (reference defect 4)
+    p = ops.make_gemul_plan(QType(19, 20), QType(19, 20), QType(20, 36), 2, 2, 2, mul=QType(20, 36))
+    assert lib.qb200_gemul_plan_info(C.byref(p), C.byref(info)) == abi.QB_EDOMAIN
+    # ... nor with RND::CONV on the wide intermediate (defect 3), nor beyond 128 bits
+    p = ops.make_gemul_plan(QType(19, 20), QType(19, 20), QType(20, 20), 2, 2, 2, mul=QType(20, 20, True, RND_CONV, SAT_TCPL))
     assert lib.qb200_gemul_plan_info(C.byref(p), C.byref(info)) == abi.QB_EDOMAIN
     # unsigned WRP::TCPL with int+frac == 32 (reference mask is a no-op)
     r = ops.make_reduce_plan(QType(20, 14), [QType(20, 12, False, 5, WRP_TCPL)], 4)

@@ -459,6 +459,40 @@ def test_elementwise_tensor_ops_vs_reference_goldens_and_oracle():
         assert np.array_equal(out.cpu().numpy(), want), op
 
 
+def test_wide_two_word_slice_gpu():
+    """Intermediates of 65..126 bits (products of two > 32-bit operands, wide aligned sums) run in __int128 inside the
+    64-bit kernels: reference goldens through the element-wise entry point, the fenced cases are refused, and a
+    random Qgemul with 82-bit products against the oracle."""
+    n = refused = 0
+    for c in load_cases("ref_wide.json"):
+        a, b, to = qt(c["a"]), qt(c["b"]), qt(c["to"])
+        A = np_words([i[0] for i in c["inputs"]], a); B = np_words([i[1] for i in c["inputs"]], b)
+        try:
+            out, _ = ops.elementwise(c["op"], dev(A), dev(B), a, b, to)
+        except abi.QbError as e:
+            assert e.code == abi.QB_EDOMAIN and c["band"], (c["a"], c["b"], c["to"], str(e))
+            refused += 1
+            continue
+        # whatever the fence admits (incl. `band` candidates whose true range stays below 2^63) must equal the reference
+        assert [int(v) for v in out.cpu().numpy()] == [o[0] for o in c["outputs"]], (c["op"], c["a"], c["b"], c["to"])
+        n += len(A)
+    assert n >= 48 * 40 and refused >= 12
+    rng = np.random.default_rng(77)
+    a = QType(20, 20, True, 5, 0); b = QType(22, 18, True, 5, 0)
+    mul = QType(24, 20, True, 3, 0)                            # 83-bit product >> 18 with RND::INF
+    lv = [QType(25 + l, 20 - 2 * l, True, (l * 2) % 4, l % 3) for l in range(4)]
+    cc = QType(30, 10, True, 1, 2)
+    M, N, K, batch = 8, 6, 16, 3
+    plan = gemul_plan(a, b, mul, cc, lv, M, N, K)
+    info = ops.plan_info_gemul(plan)
+    assert info.arith_bits == 64 and info.max_inter_bits > 64
+    A = rand_words(rng, a, batch * M * K); B = rand_words(rng, b, batch * K * N)
+    want = oracle.gemul_batched(plan, A, B, batch)
+    Cd = torch.empty(batch * M * N, dtype=torch.int64, device="cuda")
+    ops.Qgemul(Cd, dev(A), dev(B), plan, batch=batch)
+    assert np.array_equal(Cd.cpu().numpy(), want)
+
+
 def test_synth_fill_matches_oracle_all_word_sizes():
     for wb, lo, hi in [(1, -127, 127), (2, -(1 << 15), (1 << 15) - 1), (4, -65536, 65535), (8, -(1 << 40), (1 << 40))]:
         t = torch.empty(10007, dtype={1: torch.int8, 2: torch.int16, 4: torch.int32, 8: torch.int64}[wb], device="cuda")
