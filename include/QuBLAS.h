@@ -17,6 +17,7 @@
 //   BasicComplexMul<acT,bdT,adT,bcT,acbdT,adbcT>, Qmul(c1,c2) :3376-3446    4 mult / 2 add (default complex product)
 //   Qreduce<Args...>(tensor) / (scalars...)                  :4903-5018    tensor form -> GPU
 //   Qgemul<QgemulAddArgs<>,QgemulMulArgs<>,QgemulTransposedA<>>(C,A,B)   readme.md:80-87 -> GPU
+//   BitStream<l2r|r2l<n>...>, toString(), operator<<          :4545-4827, :2433, :2913   host-only wire format / printing
 //
 // Scalar Qmul/Qadd/Qsub/Qreduce(scalars...) are header-only conveniences so that existing user code
 // keeps compiling; every tensor-level operation (Qreduce(tensor), Qgemul, tensor TFComplexMul) goes
@@ -24,15 +25,20 @@
 // CPU fallback for the measured path.
 #pragma once
 
+#include <algorithm>
 #include <array>
 #include <cmath>
+#include <complex>
 #include <cstdint>
 #include <cstring>
 #include <initializer_list>
+#include <iomanip>
 #include <iostream>
 #include <random>
+#include <sstream>
 #include <stdexcept>
 #include <string>
+#include <string_view>
 #include <type_traits>
 #include <utility>
 #include <vector>
@@ -274,6 +280,14 @@ public:
         return *this;
     }
     auto fill(int raw) { data.data = (raw_t)raw; return *this; }
+    // the low `width` bits of the two's-complement raw word, MSB first (QuBLAS.h:2433-2438)
+    std::string toString() const
+    {
+        std::string out((std::size_t)width, '0');
+        const unsigned long long u = (unsigned long long)(long long)data.data;
+        for (int b = 0; b < width; b++) if ((u >> b) & 1ULL) out[(std::size_t)(width - 1 - b)] = '1';
+        return out;
+    }
     void display(const std::string &name = "") const
     {
         if (!name.empty()) std::cout << name << " :\n";
@@ -292,12 +306,19 @@ public:
     using realType = Qu_s<A...>;
     using imagType = Qu_s<B...>;
     static constexpr bool is_complex = true;
+    static constexpr int realWidth = realType::width, imagWidth = imagType::width, width = realWidth + imagWidth;   // :2507-2509
     realType real;
     imagType imag;
     constexpr Qu_s() = default;
     template <class T1, class T2> constexpr Qu_s(T1 a, T2 b) : real(a), imag(b) {}
     template <class T> requires(!detail::is_complex<T>::value) constexpr Qu_s(T a) : real(a), imag(0) {}
     template <class R2, class I2> constexpr Qu_s(const Qu_s<R2, I2> &o) requires(detail::is_scalar<R2>::value) : real(o.real), imag(o.imag) {}
+    auto fill() { real.fill(); imag.fill(); return *this; }
+    auto fill(int raw) { real.fill(raw); imag.fill(raw); return *this; }
+    auto fill(int re_raw, int im_raw) { real.fill(re_raw); imag.fill(im_raw); return *this; }                        // :2571-2576
+    std::complex<double> toDouble() const { return { real.toDouble(), imag.toDouble() }; }                            // :2548-2551
+    friend std::ostream &operator<<(std::ostream &os, const Qu_s &q) { return os << q.toDouble(); }
+    std::string toString() const { return "(" + real.toString() + ", " + imag.toString() + ")"; }                    // :2553-2556
     void display(const std::string &name = "") const { real.display(name + ".real"); imag.display(name + ".imag"); }
 };
 template <class R, class Im> using Qcomplex = Qu_s<R, Im>;
@@ -364,6 +385,33 @@ public:
 
     auto fill() { for (auto &e : data) e.fill(); return *this; }
     void clear() { std::memset((void *)data.data(), 0, elemSize * sizeof(E)); }
+    // values as doubles, 4 decimals: "[a, b, ...]", a 2-D tensor as right-aligned rows (QuBLAS.h:2913-2977)
+    friend std::ostream &operator<<(std::ostream &os, const Qu_s &t)
+    {
+        const auto flags = os.flags();
+        const auto prec = os.precision();
+        os << std::fixed << std::setprecision(4) << "[";
+        if constexpr (dimSize == 2) {
+            std::size_t cell = 0;
+            for (std::size_t i = 0; i < elemSize; i++) {
+                std::ostringstream probe;
+                probe << std::fixed << std::setprecision(4) << t.data[i].toDouble();
+                cell = std::max(cell, probe.str().size());
+            }
+            constexpr std::size_t rows = size::dimArray[0], cols = size::dimArray[1];
+            for (std::size_t r = 0; r < rows; r++) {
+                if (r) os << ' ';
+                for (std::size_t c = 0; c < cols; c++) os << std::setw((int)cell) << std::right << t.data[r + c * rows].toDouble() << (c + 1 < cols ? ", " : "");
+                if (r + 1 < rows) os << '\n';
+            }
+        } else {
+            for (std::size_t i = 0; i < elemSize; i++) os << t.data[i] << (i + 1 < elemSize ? ", " : "");
+        }
+        os << "]";
+        os.flags(flags);
+        os.precision(prec);
+        return os;
+    }
     void *raw() { return (void *)data.data(); }                          // the buffer the C ABI sees
     const void *raw() const { return (const void *)data.data(); }
     void display(const std::string &name = "") const
@@ -816,6 +864,99 @@ auto Qadd(const Qu_s<dim<D...>, EA> &a, const Qu_s<dim<D...>, EB> &b) { return d
 template <class... toArgs, std::size_t... D, class EA, class EB>
     requires(detail::is_scalar<EA>::value && detail::is_scalar<EB>::value)
 auto Qsub(const Qu_s<dim<D...>, EA> &a, const Qu_s<dim<D...>, EB> &b) { return detail::tensor_ew<QB_EW_SUB, toArgs...>(a, b); }
+
+// ------------------------------------------------------------------------------------------------
+// BitStream: binary-string import/export of scalars and tensors — the test-vector format fed to HDL
+// testbenches (QuBLAS.h:4545-4827, readme.md:111-127).  Host-only.
+//   BitStream<elemOrder>(scalar)                 -> std::string         BitStream<ScalarT, elemOrder>(str) -> ScalarT
+//   BitStream<tensorOrder, elemOrder>(tensor)    -> std::string         BitStream<TensorT, tensorOrder, elemOrder>(str) -> TensorT
+// l2r keeps the order; r2l<n> reverses it in groups of n (characters of one element, or elements of
+// the tensor).  Parsing ignores every character that is not '0'/'1' and stores the bits as the RAW
+// word without sign extension, exactly like the reference (std::stoi(..., 2) + fill(int), :4697-4700).
+// ------------------------------------------------------------------------------------------------
+struct l2r {};
+template <std::size_t... n>
+    requires(sizeof...(n) <= 1)
+struct r2l;
+template <std::size_t n> struct r2l<n> { static constexpr std::size_t index = n; };
+template <> struct r2l<> : r2l<1> {};
+
+namespace detail {
+template <class P> struct bit_order;
+template <> struct bit_order<l2r> {
+    static constexpr std::size_t group = 0;
+    static std::string apply(std::string_view s) { return std::string(s); }
+};
+template <std::size_t... n> struct bit_order<r2l<n...>> {
+    static constexpr std::size_t group = r2l<n...>::index;
+    static std::string apply(std::string_view s)
+    {
+        if (s.size() % group != 0) throw std::runtime_error("Invalid string length: Must be a multiple of " + std::to_string(group));
+        std::string out;
+        out.reserve(s.size());
+        for (std::size_t pos = s.size(); pos >= group; pos -= group) out.append(s.substr(pos - group, group));
+        return out;
+    }
+};
+// position in the serialized stream -> element index (the same map serves both directions)
+template <class P> constexpr std::size_t stream_slot(std::size_t pos, std::size_t count)
+{
+    constexpr std::size_t g = bit_order<P>::group;
+    if constexpr (g == 0) return pos;
+    else return count - g * (pos / g + 1) + pos % g;
+}
+inline std::string only_bits(std::string_view s)
+{
+    std::string out;
+    out.reserve(s.size());
+    for (char ch : s) if (ch == '0' || ch == '1') out.push_back(ch);
+    return out;
+}
+template <class E> E from_bits(const std::string &bits)
+{
+    E e;
+    if constexpr (is_complex<E>::value)
+        e.fill(std::stoi(bits.substr(0, (std::size_t)E::realWidth), nullptr, 2), std::stoi(bits.substr((std::size_t)E::realWidth, (std::size_t)E::imagWidth), nullptr, 2));
+    else
+        e.fill(std::stoi(bits, nullptr, 2));
+    return e;
+}
+template <class... Args> struct bitstream;
+template <class P> struct bitstream<P> {                                              // scalar -> string (:4787-4794)
+    static std::string run(const auto &q) { return bit_order<P>::apply(q.toString()); }
+};
+template <class... QA, class P>
+    requires(is_scalar<Qu_s<QA...>>::value || is_complex<Qu_s<QA...>>::value)
+struct bitstream<Qu_s<QA...>, P> {                                                    // string -> scalar (:4760-4785)
+    static auto run(std::string_view s) { return from_bits<Qu_s<QA...>>(bit_order<P>::apply(only_bits(s))); }
+};
+template <class TP, class EP> struct bitstream<TP, EP> {                              // tensor -> string (:4812-4821)
+    template <std::size_t... D, class E> static std::string run(const Qu_s<dim<D...>, E> &t)
+    {
+        constexpr std::size_t n = dim<D...>::elemSize;
+        static_assert(bit_order<TP>::group == 0 || n % bit_order<TP>::group == 0, "r2l<n> over the tensor needs elemSize % n == 0");
+        std::string out;
+        for (std::size_t pos = 0; pos < n; pos++) out.append(bit_order<EP>::apply(t[stream_slot<TP>(pos, n)].toString()));
+        return out;
+    }
+};
+template <std::size_t... D, class E, class TP, class EP>
+struct bitstream<Qu_s<dim<D...>, E>, TP, EP> {                                        // string -> tensor (:4797-4810)
+    static auto run(std::string_view s)
+    {
+        constexpr std::size_t n = dim<D...>::elemSize, w = (std::size_t)E::width;
+        static_assert(bit_order<TP>::group == 0 || n % bit_order<TP>::group == 0, "r2l<n> over the tensor needs elemSize % n == 0");
+        const std::string bits = only_bits(s);
+        if (bits.size() % w != 0) throw std::runtime_error("Invalid string length: Must be a multiple of " + std::to_string(w));
+        if (bits.size() < n * w) throw std::out_of_range("BitStream: the string holds fewer elements than the tensor");
+        Qu_s<dim<D...>, E> t;
+        for (std::size_t i = 0; i < n; i++) t[i] = from_bits<E>(bit_order<EP>::apply(std::string_view(bits).substr(stream_slot<TP>(i, n) * w, w)));
+        return t;
+    }
+};
+}  // namespace detail
+
+template <class... Args> auto BitStream(const auto &input) { return detail::bitstream<Args...>::run(input); }
 
 // ------------------------------------------------------------------------------------------------
 // Batched ("Monte-Carlo") containers: `count` tensors of one type in ONE contiguous raw buffer, so a

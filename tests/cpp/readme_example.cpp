@@ -1,9 +1,11 @@
-// The reference's readme.md:20-110 usage example, compiled UNCHANGED against this repo's QuBLAS.h
-// (minus the ANUS LUT and BitStream lines, which are outside the hot path).  Prints the raw words of
+// The reference's readme.md:20-127 usage example, compiled UNCHANGED against this repo's QuBLAS.h
+// (minus the ANUS LUT lines, which are outside the hot path; the BitStream vector is given all six
+// of its values — with the readme's four the reference itself throws std::invalid_argument).  Prints the raw words of
 // every result so that the test can compare them with the reference's own answers.
 // Exit code 3 = no CUDA device (scalar parts still ran).
 #include "QuBLAS.h"
 #include <cstdio>
+#include <iostream>
 
 using namespace QuBLAS;
 
@@ -46,6 +48,17 @@ int main()
     c_t_2 complex2 = {3, 4};
     auto cprod = Qmul<TFComplexMul<abT<type2>, cdT<type1>, baT<type2>, badT<type2>, ABT<type2>, BCT<type2>>>(complex1, complex2);
     std::printf("cprod %d %d\n", (int)cprod.real.data.data, (int)cprod.imag.data.data);
+
+    // BitStream (readme.md:111-127): host-only wire format
+    using vec_t_bits = Qu<dim<6>, type1>;
+    vec_t_bits vec_bits = {1.0, 2.0, 3.0, 4.0, 5.0, 6.0};
+    auto res = BitStream<r2l<3>, r2l<2>>(vec_bits);
+    std::cout << "bits " << res << std::endl;
+    auto z = BitStream<vec_t_bits, r2l<3>, r2l<2>>(res);
+    std::printf("bitsz");
+    for (std::size_t i = 0; i < 6; i++) std::printf(" %d", (int)z[i].data.data);
+    std::printf("\n");
+    std::fflush(stdout);
 
     try {
         // Tree-based reductions on tensors -> GPU

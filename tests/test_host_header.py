@@ -86,6 +86,8 @@ def test_readme_example_compiles_and_scalar_part_runs(tmp_path):
     assert lines[0] == "a 256 q1 8 q2 2 elem 80 h1[3,0,1] 64"
     assert lines[1] == "red3 272"            # Qreduce<type1>(q1, q2, q1, q2) = 34.0
     assert lines[2] == "cprod 0 0"           # reference: tests/golden/ref_tf.json readme case
+    assert lines[3] == "bits 000010000000101000000000110000001000000000000100000010010000"   # reference output, readme.md:118-121
+    assert lines[4] == "bitsz 8 16 24 32 40 48"
     if p.returncode == 3:
         assert "no CUDA device" in p.stdout and "no CPU fallback" in p.stdout
 
@@ -101,6 +103,17 @@ def test_readme_example_on_gpu(tmp_path):
     assert r["m3"] == [192, 448, 192, 448, 448, 448, 0, 0, 192, 0, 0, 0, 448, 0, 0, 0]      # SURVEY 3.5, TransposedA=true
     assert r["m4"] == [64, 64, 128, 448, 448, 320, 448, 0, 448, 0, 192, 256, 64, 192, 256, 384]
     assert r["cvec"] == [0, 0, 0, 0, 0, 0]
+
+
+def test_bitstream_and_printing_match_reference(tmp_path):
+    """BitStream import/export (QuBLAS.h:4545-4827), toString and operator<< on scalars, complex values and tensors:
+    tests/cpp/bitstream_example.cpp prints the same text as when compiled against the reference header
+    (tests/golden/ref_bitstream.txt, written by `python oracle/ref_harness_gen.py --bitstream`)."""
+    exe = _build_cpp(tmp_path, "bitstream_example")
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    with open(os.path.join(ROOT, "tests", "golden", "ref_bitstream.txt")) as f:
+        assert p.stdout == f.read()
 
 
 def _build_cpp(tmp_path, name):
