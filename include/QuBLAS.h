@@ -18,6 +18,7 @@
 //   Qreduce<Args...>(tensor) / (scalars...)                  :4903-5018    tensor form -> GPU
 //   Qgemul<QgemulAddArgs<>,QgemulMulArgs<>,QgemulTransposedA<>>(C,A,B)   readme.md:80-87 -> GPU
 //   BitStream<l2r|r2l<n>...>, toString(), operator<<          :4545-4827, :2433, :2913   host-only wire format / printing
+//   ANUS::Qpoly / Segment / Qapprox / Qapprox_s               :4829-4897    host-only, scalar
 //
 // Scalar Qmul/Qadd/Qsub/Qreduce(scalars...) are header-only conveniences so that existing user code
 // keeps compiling; every tensor-level operation (Qreduce(tensor), Qgemul, tensor TFComplexMul) goes
@@ -864,6 +865,36 @@ auto Qadd(const Qu_s<dim<D...>, EA> &a, const Qu_s<dim<D...>, EB> &b) { return d
 template <class... toArgs, std::size_t... D, class EA, class EB>
     requires(detail::is_scalar<EA>::value && detail::is_scalar<EB>::value)
 auto Qsub(const Qu_s<dim<D...>, EA> &a, const Qu_s<dim<D...>, EB> &b) { return detail::tensor_ew<QB_EW_SUB, toArgs...>(a, b); }
+
+// ------------------------------------------------------------------------------------------------
+// ANUS: polynomial / piecewise-polynomial non-linearities on scalars (QuBLAS.h:4829-4897), host-only.
+// Qpoly<a0, a1, ...>(x) evaluates a0 + x*(a1 + x*(...)) by Horner's rule; the product and the sum
+// of each step are quantized to the type of that step's own coefficient (decltype(a0)).
+// Qapprox<Segment<breakpoint, coeffs...>, ...>(x) picks the first segment whose breakpoint exceeds
+// x.toDouble() (the last one otherwise) and converts the value back to x's type.
+// ------------------------------------------------------------------------------------------------
+namespace ANUS {
+template <auto a0> constexpr auto Qpoly(auto) { return a0; }
+template <auto a0, auto a1, auto... more> constexpr auto Qpoly(auto x)
+{
+    return Qadd<decltype(a0)>(a0, Qmul<decltype(a0)>(x, Qpoly<a1, more...>(x)));
+}
+template <double BreakPoint, auto... coeffs> struct Segment {
+    static constexpr double breakpoint = BreakPoint;
+    static constexpr auto func(auto x) { return Qpoly<coeffs...>(x); }
+};
+template <class First, class... Rest> constexpr auto Qapprox(auto x)
+{
+    if constexpr (sizeof...(Rest) == 0) return decltype(x){ First::func(x) };
+    else {
+        if (x.toDouble() < First::breakpoint) return decltype(x){ First::func(x) };
+        return Qapprox<Rest...>(x);
+    }
+}
+template <class... Segments> struct Qapprox_s {
+    static constexpr auto execute(auto x) { return Qapprox<Segments...>(x); }
+};
+}  // namespace ANUS
 
 // ------------------------------------------------------------------------------------------------
 // BitStream: binary-string import/export of scalars and tensors — the test-vector format fed to HDL

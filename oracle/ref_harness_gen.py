@@ -557,22 +557,26 @@ def all_cases(rng):
     return scalar_cases(rng) + reduce_cases(rng) + tf_cases(rng) + gemul_cases(rng) + cgemul_cases(rng) + fromdouble_cases(rng) + bcm_cases(rng) + wide_cases(rng)
 
 
-def bitstream_golden():
-    """tests/cpp/bitstream_example.cpp compiled against the REFERENCE header; its stdout is the fixture."""
-    src = os.path.join(os.path.dirname(GOLD_DIR), "cpp", "bitstream_example.cpp")
+TEXT_GOLDENS = {"bitstream_example": "ref_bitstream.txt", "anus_example": "ref_anus.txt"}
+
+
+def text_goldens():
+    """tests/cpp/<name>.cpp compiled against the REFERENCE header; its stdout is the fixture."""
     os.makedirs(OUT_DIR, exist_ok=True)
-    exe = os.path.join(OUT_DIR, "bitstream_ref")
-    subprocess.check_call(["g++", "-std=c++23", "-O0", "-w", "-I" + REF_INC, src, "-o", exe])
-    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
-    path = os.path.join(GOLD_DIR, "ref_bitstream.txt")
-    with open(path, "w") as f:
-        f.write(out)
-    print("wrote", path, len(out.splitlines()), "lines")
+    for name, gold in TEXT_GOLDENS.items():
+        src = os.path.join(os.path.dirname(GOLD_DIR), "cpp", name + ".cpp")
+        exe = os.path.join(OUT_DIR, name + "_ref")
+        subprocess.check_call(["g++", "-std=c++23", "-O0", "-w", "-I" + REF_INC, src, "-o", exe])
+        out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+        path = os.path.join(GOLD_DIR, gold)
+        with open(path, "w") as f:
+            f.write(out)
+        print("wrote", path, len(out.splitlines()), "lines")
 
 
 def main():
-    if "--bitstream" in sys.argv[1:]:
-        return bitstream_golden()
+    if "--text" in sys.argv[1:]:
+        return text_goldens()
     rng = random.Random(20261018)
     cases = all_cases(rng)
     os.makedirs(GOLD_DIR, exist_ok=True)

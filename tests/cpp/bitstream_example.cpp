@@ -1,6 +1,6 @@
 // BitStream wire format (the reference's RTL test-vector I/O, include/QuBLAS.h:4545-4827; main.cpp:6-43;
 // readme.md:111-127).  The same source is compiled against the reference header (golden output,
-// tests/golden/ref_bitstream.txt, written by oracle/ref_harness_gen.py --bitstream) and against this
+// tests/golden/ref_bitstream.txt, written by oracle/ref_harness_gen.py --text) and against this
 // repo's header; the outputs must be identical.
 #include "QuBLAS.h"
 #include <iostream>

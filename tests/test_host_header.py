@@ -108,11 +108,21 @@ def test_readme_example_on_gpu(tmp_path):
 def test_bitstream_and_printing_match_reference(tmp_path):
     """BitStream import/export (QuBLAS.h:4545-4827), toString and operator<< on scalars, complex values and tensors:
     tests/cpp/bitstream_example.cpp prints the same text as when compiled against the reference header
-    (tests/golden/ref_bitstream.txt, written by `python oracle/ref_harness_gen.py --bitstream`)."""
+    (tests/golden/ref_bitstream.txt, written by `python oracle/ref_harness_gen.py --text`)."""
     exe = _build_cpp(tmp_path, "bitstream_example")
     p = subprocess.run([exe], capture_output=True, text=True)
     assert p.returncode == 0, p.stdout + p.stderr
     with open(os.path.join(ROOT, "tests", "golden", "ref_bitstream.txt")) as f:
+        assert p.stdout == f.read()
+
+
+def test_anus_poly_and_approx_match_reference(tmp_path):
+    """ANUS::Qpoly / Qapprox / Qapprox_s (QuBLAS.h:4829-4897) over a sweep of 222 inputs: same raw words and same
+    deduced result types as the reference header (tests/golden/ref_anus.txt)."""
+    exe = _build_cpp(tmp_path, "anus_example")
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    with open(os.path.join(ROOT, "tests", "golden", "ref_anus.txt")) as f:
         assert p.stdout == f.read()
 
 
