@@ -160,6 +160,22 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm)}
 
 
+# algorithmic bytes of the launch that each committed `ncu --set full` capture profiled (tools/prof.py)
+NCU_CAPTURE_ALG_BYTES = {"c3": 32768 * 3 * 4096 * 4, "c2": 16 * (1 << 24) * 4 + 16 * 4, "c4": 4096 * (256 * 256 + 256 + 256) * 8,
+                         "c5": 2 * 8192 * 8192 + 8192 * 8192 * 4}
+
+
+def ncu_traffic(tag, alg_bytes_per_launch):
+    """DRAM bytes per launch of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum of the committed
+    `ncu --set full` capture (profiles/r1_<tag>_ncu_summary.json), scaled from the capture's launch size to this
+    run's by the ratio of algorithmic bytes (the kernels stream every byte once, so traffic is linear in the batch)."""
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_%s_ncu_summary.json" % tag)))[0]
+        return float(prof["traffic_bytes"]) * alg_bytes_per_launch / NCU_CAPTURE_ALG_BYTES[tag]
+    except Exception:
+        return None
+
+
 def roofline_alu(lib, gmacs, device):
     """The headline kernel is bound by instruction issue on the INT32/FP32 pipes, not by HBM: compare its
     achieved thread-instruction rate (instructions per MAC from the committed ncu capture,
@@ -309,7 +325,9 @@ def run_ours(args):
                        "l2": "inputs (%.1f GB per GPU) are far larger than the 126 MB L2; no flush needed" % (2 * Bn * WORDS * 4 / 1e9),
                        "e2e_host_ring": "%d pinned slots x %d instances, reused cyclically; %d instances per e2e step" % (slots, chunk, e2e_instances)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                         "traffic": ncu_traffic("c3", bytes_per_launch), "algorithmic_bytes": bytes_per_launch,
+                         "traffic_source": "profiles/r1_c3_ncu_summary.json (32768-instance launch), scaled to this launch",
+                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                          "note": "this kernel is bound by the INT32 issue rate, not HBM: see roofline_alu"},
             "roofline_alu": roofline_alu(lib, value / world, local),
             "clocks": clocks,
@@ -508,7 +526,8 @@ def run_secondary(args):
             return {"value": 2.0 * 16 * 16 * Kk / dt / 1e12, "unit": unit, "cores": 1, "kind": "port", "sample": "a 16x16x8192 corner through the C oracle, 1 core"}
 
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof["traffic"] = None
+    roof["traffic"] = ncu_traffic(args.workload, bytes_alg) if args.workload in ("c2", "c4") else (ncu_traffic("c5", NCU_CAPTURE_ALG_BYTES["c5"]) if world == 1 else None)
+    roof["traffic_source"] = "profiles/r1_%s_ncu_summary.json, scaled to this launch by algorithmic bytes" % args.workload
     roof.setdefault("peak_source", "MEASURED_PEAKS.json" if peaks else "fallback")
     if rank != 0:
         dist.destroy_process_group()
