@@ -472,6 +472,10 @@ struct find_tag<Tag, Tag<In...>, Rest...> { static constexpr bool found = true; 
 template <template <class...> class Tag, class First, class... Rest>
 struct find_tag<Tag, First, Rest...> : find_tag<Tag, Rest...> {};
 
+template <std::size_t N, class... Ts> struct type_at_c;
+template <std::size_t N, class H, class... T> struct type_at_c<N, H, T...> : type_at_c<N - 1, T...> {};
+template <class H, class... T> struct type_at_c<0, H, T...> { using type = H; };
+
 template <template <class...> class Tag, class... Pack> constexpr Partial tf_partial()
 {
     using F = find_tag<Tag, Pack...>;
@@ -569,14 +573,98 @@ constexpr auto Qmul(const X x, const Y y)
     auto im = Qadd<detail::scalar_of<t.adbc>>(ad, bc);
     return Qcomplex<decltype(re), decltype(im)>(re, im);
 }
-// component-wise complex add with one level type for both parts (QuBLAS.h:3549-3563)
+// realT<...> / imagT<...>: per-component target of a complex-valued result (QuBLAS.h:3537-3547).
+// Without them the whole pack serves both components; two bare scalar types are positional
+// (first = real part, second = imaginary part, :3567-3569).
+template <class... Args> struct realT {};
+template <class... Args> struct imagT {};
+namespace detail {
+template <bool Imag, class... Pack> constexpr Partial ri_partial()
+{
+    if constexpr (Imag ? find_tag<imagT, Pack...>::found : find_tag<realT, Pack...>::found) {
+        if constexpr (Imag) return parse<typename find_tag<imagT, Pack...>::list>();
+        else return parse<typename find_tag<realT, Pack...>::list>();
+    } else if constexpr (sizeof...(Pack) == 2 && (is_scalar<Pack>::value && ...)) {
+        return parse<typename type_at_c<Imag ? 1 : 0, Pack...>::type>();
+    } else return parse<Pack...>();
+}
+template <bool Imag, class L> struct ri_partial_l;
+template <bool Imag, class... Pack> struct ri_partial_l<Imag, TypeList<Pack...>> { static constexpr Partial value = ri_partial<Imag, Pack...>(); };
+}  // namespace detail
+
+// component-wise complex add / subtract (QuBLAS.h:3549-3590)
 template <class... toArgs, class X, class Y>
     requires(detail::is_complex<X>::value && detail::is_complex<Y>::value)
 constexpr auto Qadd(const X x, const Y y)
 {
-    auto re = Qadd<toArgs...>(x.real, y.real);
-    auto im = Qadd<toArgs...>(x.imag, y.imag);
+    constexpr detail::Spec rt = detail::merge(X::realType::spec, Y::realType::spec, detail::ri_partial<false, toArgs...>(), false);
+    constexpr detail::Spec it = detail::merge(X::imagType::spec, Y::imagType::spec, detail::ri_partial<true, toArgs...>(), false);
+    auto re = Qadd<detail::scalar_of<rt>>(x.real, y.real);
+    auto im = Qadd<detail::scalar_of<it>>(x.imag, y.imag);
     return Qcomplex<decltype(re), decltype(im)>(re, im);
+}
+template <class... toArgs, class X, class Y>
+    requires(detail::is_complex<X>::value && detail::is_complex<Y>::value)
+constexpr auto Qsub(const X x, const Y y)
+{
+    constexpr detail::Spec rt = detail::merge(X::realType::spec, Y::realType::spec, detail::ri_partial<false, toArgs...>(), false);
+    constexpr detail::Spec it = detail::merge(X::imagType::spec, Y::imagType::spec, detail::ri_partial<true, toArgs...>(), false);
+    auto re = Qsub<detail::scalar_of<rt>>(x.real, y.real);
+    auto im = Qsub<detail::scalar_of<it>>(x.imag, y.imag);
+    return Qcomplex<decltype(re), decltype(im)>(re, im);
+}
+
+// real (x) complex: the real operand scales both components (QuBLAS.h:3600-3637)
+template <class... toArgs, class X, class Y>
+    requires(detail::is_scalar<X>::value && detail::is_complex<Y>::value)
+constexpr auto Qmul(const X x, const Y y)
+{
+    constexpr detail::Spec rt = detail::merge(X::spec, Y::realType::spec, detail::ri_partial<false, toArgs...>(), true);
+    constexpr detail::Spec it = detail::merge(X::spec, Y::imagType::spec, detail::ri_partial<true, toArgs...>(), true);
+    auto re = Qmul<detail::scalar_of<rt>>(x, y.real);
+    auto im = Qmul<detail::scalar_of<it>>(x, y.imag);
+    return Qcomplex<decltype(re), decltype(im)>(re, im);
+}
+template <class... toArgs, class X, class Y>
+    requires(detail::is_complex<X>::value && detail::is_scalar<Y>::value)
+constexpr auto Qmul(const X x, const Y y)
+{
+    constexpr detail::Spec rt = detail::merge(X::realType::spec, Y::spec, detail::ri_partial<false, toArgs...>(), true);
+    constexpr detail::Spec it = detail::merge(X::imagType::spec, Y::spec, detail::ri_partial<true, toArgs...>(), true);
+    auto re = Qmul<detail::scalar_of<rt>>(x.real, y);
+    auto im = Qmul<detail::scalar_of<it>>(x.imag, y);
+    return Qcomplex<decltype(re), decltype(im)>(re, im);
+}
+// real (+/-) complex: only the real parts meet; the imaginary part passes through unchanged, except
+// for real - complex, where it is Qsub<toArgs...>(0 of the real operand's type, imag) (QuBLAS.h:3646-3696)
+template <class... toArgs, class X, class Y>
+    requires(detail::is_scalar<X>::value && detail::is_complex<Y>::value)
+constexpr auto Qadd(const X x, const Y y)
+{
+    auto re = Qadd<toArgs...>(x, y.real);
+    return Qcomplex<decltype(re), typename Y::imagType>(re, y.imag);
+}
+template <class... toArgs, class X, class Y>
+    requires(detail::is_complex<X>::value && detail::is_scalar<Y>::value)
+constexpr auto Qadd(const X x, const Y y)
+{
+    auto re = Qadd<toArgs...>(x.real, y);
+    return Qcomplex<decltype(re), typename X::imagType>(re, x.imag);
+}
+template <class... toArgs, class X, class Y>
+    requires(detail::is_scalar<X>::value && detail::is_complex<Y>::value)
+constexpr auto Qsub(const X x, const Y y)
+{
+    auto re = Qsub<toArgs...>(x, y.real);
+    auto im = Qsub<toArgs...>(X(), y.imag);
+    return Qcomplex<decltype(re), decltype(im)>(re, im);
+}
+template <class... toArgs, class X, class Y>
+    requires(detail::is_complex<X>::value && detail::is_scalar<Y>::value)
+constexpr auto Qsub(const X x, const Y y)
+{
+    auto re = Qsub<toArgs...>(x.real, y);
+    return Qcomplex<decltype(re), typename X::imagType>(re, x.imag);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -744,8 +832,39 @@ void Qgemul(CT &C, const AT &A, const BT &B)
     static_assert(DC::rows == M && DC::cols == N, "Qgemul: output shape does not match");
     using EA = typename DA::elem; using EB = typename DB::elem; using EC = typename DC::elem;
     qb_exec ex{ QB_MEM_HOST, -1, nullptr, 0, 0 };
-    if constexpr (detail::is_scalar<EA>::value) {
-        static_assert(detail::is_scalar<EB>::value && detail::is_scalar<EC>::value, "Qgemul: mixed real/complex operands are not supported");
+    if constexpr (detail::is_scalar<EA>::value != detail::is_scalar<EB>::value) {
+        // one real and one complex operand: real (x) complex products (QuBLAS.h:3600-3637), QgemulMulArgs<realT<..>, imagT<..>>
+        // (or one type for both components), accumulated by the component-wise complex tree
+        static_assert(detail::is_complex<EC>::value, "Qgemul: a real-by-complex product needs a complex output tensor");
+        static constexpr bool real_a = detail::is_scalar<EA>::value;
+        using ER = std::conditional_t<real_a, EA, EB>;                        // the real operand's element
+        using EZ = std::conditional_t<real_a, EB, EA>;                        // the complex operand's element
+        static constexpr detail::Spec leaf_re = detail::merge(real_a ? ER::spec : EZ::realType::spec, real_a ? EZ::realType::spec : ER::spec,
+                                                              detail::ri_partial_l<false, typename G::mul>::value, true);
+        static constexpr detail::Spec leaf_im = detail::merge(real_a ? ER::spec : EZ::imagType::spec, real_a ? EZ::imagType::spec : ER::spec,
+                                                              detail::ri_partial_l<true, typename G::mul>::value, true);
+        using Low = detail::reduce_lowering<typename G::add, K>;
+        static constexpr qb_cgemul_plan plan = [] {
+            qb_cgemul_plan p{};
+            if constexpr (real_a) {
+                p.a_re = p.a_im = detail::lower(ER::spec);
+                p.b_re = detail::lower(EZ::realType::spec); p.b_im = detail::lower(EZ::imagType::spec);
+                p.product = QB_CPROD_REAL_A; p.bcm.ac = detail::lower(leaf_re); p.bcm.ad = detail::lower(leaf_im);
+            } else {
+                p.a_re = detail::lower(EZ::realType::spec); p.a_im = detail::lower(EZ::imagType::spec);
+                p.b_re = p.b_im = detail::lower(ER::spec);
+                p.product = QB_CPROD_REAL_B; p.bcm.ac = detail::lower(leaf_re); p.bcm.bc = detail::lower(leaf_im);
+            }
+            p.add_re = Low::levels(leaf_re); p.add_im = Low::levels(leaf_im);
+            p.c_re = detail::lower(EC::realType::spec); p.c_im = detail::lower(EC::imagType::spec);
+            p.M = (uint32_t)M; p.N = (uint32_t)N; p.K = (uint32_t)K;
+            p.trans_a = G::ta; p.trans_b = G::tb; p.tree_form = QB_TREE_VARIADIC;
+            p.stride_a = (int64_t)(M * K); p.stride_b = (int64_t)(K * N); p.stride_c = (int64_t)(M * N);
+            return p;
+        }();
+        detail::check(qb200_cgemul_batched(&plan, A.raw(), B.raw(), C.raw(), 1, &ex));
+    } else if constexpr (detail::is_scalar<EA>::value) {
+        static_assert(detail::is_scalar<EC>::value, "Qgemul: real operands need a real output tensor");
         static constexpr detail::Spec mul = detail::merge(EA::spec, EB::spec, detail::parse<typename G::mul>(), true);
         using Low = detail::reduce_lowering<typename G::add, K>;
         static constexpr qb_gemul_plan plan = [] {
@@ -833,6 +952,42 @@ auto Qmul(const Qu_s<dim<D...>, EX> &x, const Qu_s<dim<D...>, EY> &y)
     detail::check(qb200_tfcmul_batched(&plan, x.raw(), y.raw(), out.raw(), 1, &ex));
     return out;
 }
+
+// tensor Qmul<realT<..>, imagT<..>>(real tensor, complex tensor) and the mirrored order: element-wise
+// real (x) complex products (QuBLAS.h:3600-3637) on the GPU
+namespace detail {
+template <bool RealFirst, class... toArgs, std::size_t... D, class ER, class EZ>
+auto tensor_rc(const void *x, const void *y, const Qu_s<dim<D...>, ER> *, const Qu_s<dim<D...>, EZ> *)
+{
+    static constexpr Spec tre = merge(RealFirst ? ER::spec : EZ::realType::spec, RealFirst ? EZ::realType::spec : ER::spec, ri_partial<false, toArgs...>(), true);
+    static constexpr Spec tim = merge(RealFirst ? ER::spec : EZ::imagType::spec, RealFirst ? EZ::imagType::spec : ER::spec, ri_partial<true, toArgs...>(), true);
+    using R = Qcomplex<scalar_of<tre>, scalar_of<tim>>;
+    static_assert(sizeof(typename EZ::realType) == sizeof(typename EZ::imagType) && sizeof(scalar_of<tre>) == sizeof(scalar_of<tim>),
+                  "complex parts with different storage words are not supported on the GPU path");
+    static constexpr qb_tfcmul_plan plan = [] {
+        qb_tfcmul_plan p{};
+        if constexpr (RealFirst) {
+            p.x_re = p.x_im = lower(ER::spec); p.y_re = lower(EZ::realType::spec); p.y_im = lower(EZ::imagType::spec);
+            p.product = QB_CPROD_REAL_A; p.bcm.ac = lower(tre); p.bcm.ad = lower(tim);
+        } else {
+            p.x_re = lower(EZ::realType::spec); p.x_im = lower(EZ::imagType::spec); p.y_re = p.y_im = lower(ER::spec);
+            p.product = QB_CPROD_REAL_B; p.bcm.ac = lower(tre); p.bcm.bc = lower(tim);
+        }
+        p.len = dim<D...>::elemSize;
+        return p;
+    }();
+    Qu_s<dim<D...>, R> out;
+    qb_exec ex{ QB_MEM_HOST, -1, nullptr, 0, 0 };
+    check(qb200_tfcmul_batched(&plan, x, y, out.raw(), 1, &ex));
+    return out;
+}
+}  // namespace detail
+template <class... toArgs, std::size_t... D, class EX, class EY>
+    requires(detail::is_scalar<EX>::value && detail::is_complex<EY>::value)
+auto Qmul(const Qu_s<dim<D...>, EX> &x, const Qu_s<dim<D...>, EY> &y) { return detail::tensor_rc<true, toArgs...>(x.raw(), y.raw(), &x, &y); }
+template <class... toArgs, std::size_t... D, class EX, class EY>
+    requires(detail::is_complex<EX>::value && detail::is_scalar<EY>::value)
+auto Qmul(const Qu_s<dim<D...>, EX> &x, const Qu_s<dim<D...>, EY> &y) { return detail::tensor_rc<false, toArgs...>(x.raw(), y.raw(), &y, &x); }
 
 // ------------------------------------------------------------------------------------------------
 // element-wise Qmul / Qadd / Qsub of two real tensors: the reference returns lazy Mul/Add/SubExpression

@@ -117,7 +117,12 @@ typedef struct qb_bcm_types {
     qb_qdesc ac, bd, ad, bc, acbd, adbc;
 } qb_bcm_types;
 
-enum qb_cproduct { QB_CPROD_TF = 0, QB_CPROD_BASIC = 1 };
+/* QB_CPROD_REAL_A / QB_CPROD_REAL_B: one operand is a REAL tensor (one word per element, typed by
+ * a_re resp. b_re; the matching *_im descriptor is ignored) and scales both components of the
+ * complex one (real (x) complex Qmul, QuBLAS.h:3600-3637).  Product types live in .bcm:
+ *   REAL_A  x = a,      y = c + di :  re = Qmul<bcm.ac>(a, c), im = Qmul<bcm.ad>(a, d)
+ *   REAL_B  x = a + bi, y = c      :  re = Qmul<bcm.ac>(a, c), im = Qmul<bcm.bc>(b, c)      */
+enum qb_cproduct { QB_CPROD_TF = 0, QB_CPROD_BASIC = 1, QB_CPROD_REAL_A = 2, QB_CPROD_REAL_B = 3 };
 
 /* Complex Qgemul with TFComplexMul (product == QB_CPROD_TF, uses .tf) or BasicComplexMul
  * (product == QB_CPROD_BASIC, uses .bcm) products and component-wise tree accumulation. */

@@ -131,7 +131,9 @@ def cgemul_batched(plan: abi.qb_cgemul_plan, A, B, batch):
 
 
 def tfcmul_batched(plan: abi.qb_tfcmul_plan, x, y, batch):
-    wb = cword_bytes(plan.bcm.acbd, plan.bcm.adbc) if plan.product == abi.QB_CPROD_BASIC else cword_bytes(plan.tf.AB, plan.tf.BC)
+    re_t, im_t = {abi.QB_CPROD_TF: (plan.tf.AB, plan.tf.BC), abi.QB_CPROD_BASIC: (plan.bcm.acbd, plan.bcm.adbc),
+                  abi.QB_CPROD_REAL_A: (plan.bcm.ac, plan.bcm.ad), abi.QB_CPROD_REAL_B: (plan.bcm.ac, plan.bcm.bc)}[plan.product]
+    wb = cword_bytes(re_t, im_t)
     out = np.zeros(2 * batch * plan.len, dtype=np_dtype(wb))
     x = np.ascontiguousarray(x); y = np.ascontiguousarray(y)
     rc = load().qbo_tfcmul_batched(C.byref(plan), _ptr(x), _ptr(y), _ptr(out), batch)

@@ -331,15 +331,53 @@ static cval bcmul(cval x, cval y, const qb_bcm_types *t)
     return r;
 }
 
+/* real (x) complex Qmul, QuBLAS.h:3600-3637: the real operand multiplies each component, each product with
+ * its own target type.  real_first: x.re is the real operand (x.im unused); otherwise y.re is (y.im unused). */
+static cval rcmul(cval x, cval y, const qb_bcm_types *t, int real_first)
+{
+    cval r;
+    r.re = qbo_qmul(x.re, y.re, t->ac);                                                   /* :3612 / :3633 */
+    r.im = real_first ? qbo_qmul(x.re, y.im, t->ad) : qbo_qmul(x.im, y.re, t->bc);        /* :3613 / :3634 */
+    return r;
+}
+
+static cval cproduct(int kind, cval X, cval Y, const qb_tfc_types *tf, const qb_bcm_types *bcm)
+{
+    if (kind == QB_CPROD_BASIC) return bcmul(X, Y, bcm);
+    if (kind == QB_CPROD_REAL_A) return rcmul(X, Y, bcm, 1);
+    if (kind == QB_CPROD_REAL_B) return rcmul(X, Y, bcm, 0);
+    return tfcmul(X, Y, tf);
+}
+
+/* operand loads: a real operand stores one word per element */
+static cval load_cval(const void *buf, size_t e, int wb, int is_real, qb_qdesc re_t, qb_qdesc im_t)
+{
+    cval v;
+    if (is_real) { v.re.raw = load_word(buf, e, wb); v.re.t = re_t; v.im.raw = 0; v.im.t = re_t; }
+    else { v.re.raw = load_word(buf, 2 * e, wb); v.re.t = re_t; v.im.raw = load_word(buf, 2 * e + 1, wb); v.im.t = im_t; }
+    return v;
+}
+
+static void cproduct_types(int kind, const qb_tfc_types *tf, const qb_bcm_types *bcm, qb_qdesc *re, qb_qdesc *im)
+{
+    if (kind == QB_CPROD_BASIC) { *re = bcm->acbd; *im = bcm->adbc; }
+    else if (kind == QB_CPROD_REAL_A) { *re = bcm->ac; *im = bcm->ad; }
+    else if (kind == QB_CPROD_REAL_B) { *re = bcm->ac; *im = bcm->bc; }
+    else { *re = tf->AB; *im = tf->BC; }
+}
+
 int qbo_tfcmul_batched(const qb_tfcmul_plan *p, const void *x, const void *y, void *out, uint64_t batch)
 {
-    int wx = cword_bytes(p->x_re, p->x_im), wy = cword_bytes(p->y_re, p->y_im);
-    int wo = p->product == QB_CPROD_BASIC ? cword_bytes(p->bcm.acbd, p->bcm.adbc) : cword_bytes(p->tf.AB, p->tf.BC);
+    int rx = p->product == QB_CPROD_REAL_A, ry = p->product == QB_CPROD_REAL_B;
+    int wx = rx ? word_bytes_of(p->x_re) : cword_bytes(p->x_re, p->x_im), wy = ry ? word_bytes_of(p->y_re) : cword_bytes(p->y_re, p->y_im);
+    qb_qdesc tre, tim;
+    cproduct_types((int)p->product, &p->tf, &p->bcm, &tre, &tim);
+    int wo = cword_bytes(tre, tim);
     size_t n = (size_t)(p->len * batch);
     for (size_t i = 0; i < n; i++) {
-        cval X = { { load_word(x, 2 * i, wx), p->x_re }, { load_word(x, 2 * i + 1, wx), p->x_im } };
-        cval Y = { { load_word(y, 2 * i, wy), p->y_re }, { load_word(y, 2 * i + 1, wy), p->y_im } };
-        cval r = p->product == QB_CPROD_BASIC ? bcmul(X, Y, &p->bcm) : tfcmul(X, Y, &p->tf);
+        cval X = load_cval(x, i, wx, rx, p->x_re, p->x_im);
+        cval Y = load_cval(y, i, wy, ry, p->y_re, p->y_im);
+        cval r = cproduct((int)p->product, X, Y, &p->tf, &p->bcm);
         store_word(out, 2 * i, wo, r.re.raw);
         store_word(out, 2 * i + 1, wo, r.im.raw);
     }
@@ -352,7 +390,11 @@ int qbo_cgemul_batched(const qb_cgemul_plan *p, const void *A, const void *B, vo
 {
     size_t M = p->M, N = p->N, K = p->K;
     if (!M || !N || !K) return QB_EINVAL;
-    int wa = cword_bytes(p->a_re, p->a_im), wbb = cword_bytes(p->b_re, p->b_im), wc = cword_bytes(p->c_re, p->c_im);
+    int ra = p->product == QB_CPROD_REAL_A, rb = p->product == QB_CPROD_REAL_B;
+    int wa = ra ? word_bytes_of(p->a_re) : cword_bytes(p->a_re, p->a_im), wbb = rb ? word_bytes_of(p->b_re) : cword_bytes(p->b_re, p->b_im);
+    int wc = cword_bytes(p->c_re, p->c_im);
+    qb_qdesc tre, tim;
+    cproduct_types((int)p->product, &p->tf, &p->bcm, &tre, &tim);
     int64_t *xr = (int64_t *)malloc(K * sizeof(int64_t)), *xi = (int64_t *)malloc(K * sizeof(int64_t));
     if (!xr || !xi) { free(xr); free(xi); return QB_ENOMEM; }
     for (uint64_t b = 0; b < batch; b++) {
@@ -363,13 +405,13 @@ int qbo_cgemul_batched(const qb_cgemul_plan *p, const void *A, const void *B, vo
                 for (size_t k = 0; k < K; k++) {
                     size_t ia = oa + (p->trans_a ? (k + i * K) : (i + k * M));
                     size_t ib = ob + (p->trans_b ? (j + k * N) : (k + j * K));
-                    cval X = { { load_word(A, 2 * ia, wa), p->a_re }, { load_word(A, 2 * ia + 1, wa), p->a_im } };
-                    cval Y = { { load_word(B, 2 * ib, wbb), p->b_re }, { load_word(B, 2 * ib + 1, wbb), p->b_im } };
-                    cval r = p->product == QB_CPROD_BASIC ? bcmul(X, Y, &p->bcm) : tfcmul(X, Y, &p->tf);
+                    cval X = load_cval(A, ia, wa, ra, p->a_re, p->a_im);
+                    cval Y = load_cval(B, ib, wbb, rb, p->b_re, p->b_im);
+                    cval r = cproduct((int)p->product, X, Y, &p->tf, &p->bcm);
                     xr[k] = (int64_t)r.re.raw; xi[k] = (int64_t)r.im.raw;
                 }
-                qval rr = tree(xr, K, p->product == QB_CPROD_BASIC ? p->bcm.acbd : p->tf.AB, &p->add_re, p->tree_form);
-                qval ri = tree(xi, K, p->product == QB_CPROD_BASIC ? p->bcm.adbc : p->tf.BC, &p->add_im, p->tree_form);
+                qval rr = tree(xr, K, tre, &p->add_re, p->tree_form);
+                qval ri = tree(xi, K, tim, &p->add_im, p->tree_form);
                 size_t ic = oc + i + j * M;
                 store_word(C, 2 * ic, wc, qbo_conv(rr.raw, rr.t.frac_bits, p->c_re));
                 store_word(C, 2 * ic + 1, wc, qbo_conv(ri.raw, ri.t.frac_bits, p->c_im));

@@ -286,6 +286,38 @@ def bcm_cases(rng):
     return cases
 
 
+def _rc_targs(rng, rt, allow_split):
+    mode = rng.choice(["none", "one", "pair", "tags"] if allow_split else ["none", "one"])
+    if mode == "none":
+        return {"mode": "none"}
+    if mode == "one":
+        return {"mode": "one", "t": rt(4, 14)}
+    return {"mode": mode, "re": rt(4, 14), "im": rt(4, 14)}
+
+
+def rc_cases(rng):
+    """real (x) complex scalar Qmul / Qadd / Qsub in both operand orders (QuBLAS.h:3600-3696), complex +/- complex with
+    realT / imagT / positional targets (:3549-3590), and dot products of real-by-complex Qmul accumulated by the
+    variadic complex Qreduce — the composition a mixed real/complex Qgemul performs."""
+    def rt(lo=2, hi=8):
+        return T(rng.randint(lo, hi), rng.randint(0, 8), rng.random() < 0.85, rng.randrange(7), rng.randrange(4))
+    cases = []
+    for op in ("mul", "add", "sub"):
+        for real_first in (True, False):
+            for rep in range(5):
+                cases.append({"kind": "rc", "op": op, "real_first": real_first, "r": rt(), "c_re": rt(), "c_im": rt(),
+                              "targs": _rc_targs(rng, rt, op == "mul")})
+    for op in ("cadd", "csub"):
+        for rep in range(6):
+            cases.append({"kind": "rc", "op": op, "x_re": rt(), "x_im": rt(), "y_re": rt(), "y_im": rt(), "targs": _rc_targs(rng, rt, True)})
+    for (K, real_first) in [(4, True), (8, False), (5, True), (7, False), (16, True), (3, False)]:
+        r, cre, cim = T(rng.randint(3, 6), rng.randint(4, 8)), T(rng.randint(3, 6), rng.randint(4, 8)), T(rng.randint(3, 6), rng.randint(4, 8))
+        targs = _rc_targs(rng, lambda lo, hi: T(rng.randint(7, 10), rng.randint(5, 9), True, rng.randrange(7), rng.randrange(4)), True)
+        lv = [T(9 + l, 7 - l, True, rng.randrange(7), rng.randrange(3)) for l in range(rng.randint(1, 4))]
+        cases.append({"kind": "rcgemul", "K": K, "real_first": real_first, "r": r, "c_re": cre, "c_im": cim, "targs": targs, "levels": lv})
+    return cases
+
+
 def gemul_cases(rng):
     cases = []
     type1 = T(6, 3, True, 5, 1)     # readme.md:31  Qu<isSigned<true>,intBits<6>,fracBits<3>,OfMode<SAT::ZERO>>
@@ -437,12 +469,56 @@ def emit_cgemul(c, idx):
     return "\n".join(lines)
 
 
+def emit_targs(t):
+    if t["mode"] == "none": return ""
+    if t["mode"] == "one": return cxx_type(t["t"])
+    if t["mode"] == "pair": return "%s, %s" % (cxx_type(t["re"]), cxx_type(t["im"]))
+    return "realT<%s>, imagT<%s>" % (cxx_type(t["re"]), cxx_type(t["im"]))
+
+
+_PUT_C = ("out[0] = (int64_t)r.real.data.data; out[1] = (int64_t)r.imag.data.data; put_type(out + 2, r.real); put_type(out + 7, r.imag);")
+
+
+def emit_rc(c, idx):
+    ta = emit_targs(c["targs"])
+    if c["op"] in ("cadd", "csub"):
+        X = "Qcomplex<%s, %s>" % (cxx_type(c["x_re"]), cxx_type(c["x_im"]))
+        Y = "Qcomplex<%s, %s>" % (cxx_type(c["y_re"]), cxx_type(c["y_im"]))
+        body = ("%s x; x.real = mk<%s>(in[0]); x.imag = mk<%s>(in[1]); %s y; y.real = mk<%s>(in[2]); y.imag = mk<%s>(in[3]); auto r = %s<%s>(x, y); %s"
+                % (X, cxx_type(c["x_re"]), cxx_type(c["x_im"]), Y, cxx_type(c["y_re"]), cxx_type(c["y_im"]),
+                   "Qadd" if c["op"] == "cadd" else "Qsub", ta, _PUT_C))
+    else:
+        Cx = "Qcomplex<%s, %s>" % (cxx_type(c["c_re"]), cxx_type(c["c_im"]))
+        fn = {"mul": "Qmul", "add": "Qadd", "sub": "Qsub"}[c["op"]]
+        args = "s, z" if c["real_first"] else "z, s"
+        body = ("auto s = mk<%s>(in[0]); %s z; z.real = mk<%s>(in[1]); z.imag = mk<%s>(in[2]); auto r = %s<%s>(%s); %s"
+                % (cxx_type(c["r"]), Cx, cxx_type(c["c_re"]), cxx_type(c["c_im"]), fn, ta, args, _PUT_C))
+    return "static void case_%d(const int64_t *in, int64_t *out) { %s }\n" % (idx, body)
+
+
+def emit_rcgemul(c, idx):
+    """One output of a mixed real/complex dot product: variadic complex Qreduce over real-by-complex Qmul."""
+    K = c["K"]
+    Cx = "Qcomplex<%s, %s>" % (cxx_type(c["c_re"]), cxx_type(c["c_im"]))
+    ta = emit_targs(c["targs"])
+    lines = ["static void case_%d(const int64_t *in, int64_t *out) {" % idx,
+             "  %s s[%d]; %s z[%d];" % (cxx_type(c["r"]), K, Cx, K),
+             "  for (int k = 0; k < %d; k++) { s[k] = mk<%s>(in[3*k]); z[k].real = mk<%s>(in[3*k+1]); z[k].imag = mk<%s>(in[3*k+2]); }"
+             % (K, cxx_type(c["r"]), cxx_type(c["c_re"]), cxx_type(c["c_im"]))]
+    args = ", ".join(("Qmul<%s>(s[%d], z[%d])" if c["real_first"] else "Qmul<%s>(z[%d], s[%d])") % (ta, k, k) for k in range(K))
+    lines.append("  auto r = Qreduce<%s>(%s);" % (emit_levels(c["levels"]), args))
+    lines.append("  " + _PUT_C)
+    lines.append("}\n")
+    return "\n".join(lines)
+
+
 def emit_fromdouble(c, idx):
     body = ("double d; __builtin_memcpy(&d, &in[0], 8); %s r = d;" % cxx_type(c["to"]))
     return "static void case_%d(const int64_t *in, int64_t *out) { %s out[0] = (int64_t)r.data.data; put_type(out + 1, r); }\n" % (idx, body)
 
 
-EMIT = {"bcm": emit_bcm, "fromdouble": emit_fromdouble, "scalar": emit_scalar, "reduce": emit_reduce, "tf": emit_tf, "gemul": emit_gemul, "cgemul": emit_cgemul}
+EMIT = {"bcm": emit_bcm, "fromdouble": emit_fromdouble, "scalar": emit_scalar, "reduce": emit_reduce, "tf": emit_tf, "gemul": emit_gemul, "cgemul": emit_cgemul,
+        "rc": emit_rc, "rcgemul": emit_rcgemul}
 
 
 def n_inputs(c):
@@ -453,12 +529,14 @@ def n_inputs(c):
     if k == "tf" or k == "bcm": return 4
     if k == "gemul": return c["M"] * c["K"] + c["K"] * c["N"]
     if k == "cgemul": return 4 * c["K"]
+    if k == "rc": return 4 if c["op"] in ("cadd", "csub") else 3
+    if k == "rcgemul": return 3 * c["K"]
 
 
 def n_outputs(c):
     k = c["kind"]
     if k == "scalar" or k == "reduce" or k == "fromdouble": return 6
-    if k == "tf" or k == "cgemul" or k == "bcm": return 12
+    if k in ("tf", "cgemul", "bcm", "rc", "rcgemul"): return 12
     if k == "gemul": return c["M"] * c["N"]
 
 
@@ -500,6 +578,11 @@ def gen_inputs(rng, c):
             return [m1 + m1]
         return [[rand_raw(rng, c["a"]) for _ in range(c["M"] * c["K"])] + [rand_raw(rng, c["b"]) for _ in range(c["K"] * c["N"])]
                 for _ in range(4)]
+    if k == "rc":
+        ts = [c[n] for n in (("x_re", "x_im", "y_re", "y_im") if c["op"] in ("cadd", "csub") else ("r", "c_re", "c_im"))]
+        return [[rand_raw(rng, t) for t in ts] for _ in range(48)]
+    if k == "rcgemul":
+        return [[rand_raw(rng, c[n]) for _ in range(c["K"]) for n in ("r", "c_re", "c_im")] for _ in range(8)]
     if k == "cgemul":
         out = []
         for _ in range(8):
@@ -577,8 +660,12 @@ def text_goldens():
 def main():
     if "--text" in sys.argv[1:]:
         return text_goldens()
-    rng = random.Random(20261018)
-    cases = all_cases(rng)
+    if "--rc" in sys.argv[1:]:              # added later: own seed, own fixture, the earlier fixtures stay byte-identical
+        rng = random.Random(20261019)
+        cases = rc_cases(rng)
+    else:
+        rng = random.Random(20261018)
+        cases = all_cases(rng)
     os.makedirs(GOLD_DIR, exist_ok=True)
     run = build_harness(cases, REF_INC, OUT_DIR, "ref")
     fixtures = {}
@@ -591,7 +678,7 @@ def main():
         rec = dict(c)
         rec["inputs"] = ins
         rec["outputs"] = outs
-        fixtures.setdefault("wide" if c.get("wide") else c["kind"], []).append(rec)
+        fixtures.setdefault("wide" if c.get("wide") else ("rc" if c["kind"] == "rcgemul" else c["kind"]), []).append(rec)
     for kind, recs in fixtures.items():
         path = os.path.join(GOLD_DIR, "ref_%s.json" % kind)
         with open(path, "w") as f:

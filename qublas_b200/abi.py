@@ -44,7 +44,7 @@ class qb_bcm_types(C.Structure):
     _fields_ = [(k, qb_qdesc) for k in ("ac", "bd", "ad", "bc", "acbd", "adbc")]
 
 
-QB_CPROD_TF, QB_CPROD_BASIC = 0, 1
+QB_CPROD_TF, QB_CPROD_BASIC, QB_CPROD_REAL_A, QB_CPROD_REAL_B = 0, 1, 2, 3
 
 
 class qb_cgemul_plan(C.Structure):
@@ -109,7 +109,8 @@ def levels(ts: Optional[Sequence[QType]]) -> qb_levels:
 def bcm_types(r) -> qb_bcm_types:
     t = qb_bcm_types()
     for k in ("ac", "bd", "ad", "bc", "acbd", "adbc"):
-        setattr(t, k, desc(r[k]))
+        if k in r:                      # the real (x) complex kinds fill only the products they use
+            setattr(t, k, desc(r[k]))
     return t
 
 

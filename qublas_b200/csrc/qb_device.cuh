@@ -155,6 +155,19 @@ QB_DEV void bcm_apply(I a, I b, I c, I d, const BcmProg &t, I &re, I &im)
     im = add_apply<I, CT>(ad, bc, t.im);
 }
 
+// One complex-valued product of the kind the plan names (enum qb_cproduct); for the real (x) complex
+// kinds (QuBLAS.h:3600-3637) the absent imaginary operand is never read.
+template <typename I, bool CT>
+QB_DEV void cprod_apply(int kind, I a, I b, I c, I d, const TfProg &tf, const BcmProg &bcm, I &re, I &im)
+{
+    if (kind == 0) tf_apply<I, CT>(a, b, c, d, tf, re, im);
+    else if (kind == 1) bcm_apply<I, CT>(a, b, c, d, bcm, re, im);
+    else {
+        re = mul_apply<I, CT>(a, c, bcm.ac);
+        im = kind == 2 ? mul_apply<I, CT>(a, d, bcm.ad) : mul_apply<I, CT>(b, c, bcm.bc);
+    }
+}
+
 // Qmul through the FP32 FMA pipe (see qb_codegen.cpp:fp_mul_ok): fma(a, b, 1.5 * 2^(23+S)) is the exact product
 // plus ONE IEEE rounding at ulp 2^S, i.e. the rounded right shift by S (round-to-nearest-even == RND::CONV,
 // round toward -inf == TRN::TCPL).  Returns the quantized product BIASED by the constant's bit pattern

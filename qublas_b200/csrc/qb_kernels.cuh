@@ -204,11 +204,13 @@ k_cgemul_thread(const void *__restrict__ A, const void *__restrict__ B, void *__
     for (uint64_t k = 0; k < S.K; ++k) {
         const uint64_t ia = oa + (S.trans_a ? (k + (uint64_t)i * S.K) : (i + k * S.M));
         const uint64_t ib = ob + (S.trans_b ? (j + k * S.N) : (k + (uint64_t)j * S.K));
-        I a = load_word<I>(A, 2 * ia, S.a_wb), b = load_word<I>(A, 2 * ia + 1, S.a_wb);
-        I c = load_word<I>(B, 2 * ib, S.b_wb), d = load_word<I>(B, 2 * ib + 1, S.b_wb);
+        I a, b = 0, c, d = 0;
+        if (kind == 2) a = load_word<I>(A, ia, S.a_wb);                        // real A: one word per element
+        else { a = load_word<I>(A, 2 * ia, S.a_wb); b = load_word<I>(A, 2 * ia + 1, S.a_wb); }
+        if (kind == 3) c = load_word<I>(B, ib, S.b_wb);                        // real B
+        else { c = load_word<I>(B, 2 * ib, S.b_wb); d = load_word<I>(B, 2 * ib + 1, S.b_wb); }
         I vr, vi;
-        if (kind == 1) bcm_apply<I, false>(a, b, c, d, bcm, vr, vi);
-        else tf_apply<I, false>(a, b, c, d, tf, vr, vi);
+        cprod_apply<I, false>(kind, a, b, c, d, tf, bcm, vr, vi);
         unsigned l = 0; uint64_t m = k;
         while (m & 1) {
             vr = merge_apply<I, false>(sr[l], vr, Pre.lvl[l]);
@@ -231,11 +233,13 @@ __global__ void k_tfcmul(const void *__restrict__ x, const void *__restrict__ y,
                          int x_wb, int y_wb, int o_wb, const int kind, const __grid_constant__ TfProg tf, const __grid_constant__ BcmProg bcm)
 {
     for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) {
-        I a = load_word<I>(x, 2 * e, x_wb), b = load_word<I>(x, 2 * e + 1, x_wb);
-        I c = load_word<I>(y, 2 * e, y_wb), d = load_word<I>(y, 2 * e + 1, y_wb);
+        I a, b = 0, c, d = 0;
+        if (kind == 2) a = load_word<I>(x, e, x_wb);
+        else { a = load_word<I>(x, 2 * e, x_wb); b = load_word<I>(x, 2 * e + 1, x_wb); }
+        if (kind == 3) c = load_word<I>(y, e, y_wb);
+        else { c = load_word<I>(y, 2 * e, y_wb); d = load_word<I>(y, 2 * e + 1, y_wb); }
         I re, im;
-        if (kind == 1) bcm_apply<I, false>(a, b, c, d, bcm, re, im);
-        else tf_apply<I, false>(a, b, c, d, tf, re, im);
+        cprod_apply<I, false>(kind, a, b, c, d, tf, bcm, re, im);
         store_word<I>(out, 2 * e, o_wb, re);
         store_word<I>(out, 2 * e + 1, o_wb, im);
     }

@@ -571,7 +571,8 @@ extern "C" int qb200_cgemul_batched(const qb_cgemul_plan *plan, const void *A, c
     if (batch == 0) return QB_OK;
     Ctx cx; int rc = cx.init(exec); if (rc) return rc;
     const uint64_t ea = (uint64_t)plan->M * plan->K, eb = (uint64_t)plan->K * plan->N, ec = (uint64_t)plan->M * plan->N;
-    const size_t bytes_a = 2 * span_elems(batch, plan->stride_a, ea) * gp.a_wb, bytes_b = 2 * span_elems(batch, plan->stride_b, eb) * gp.b_wb,
+    const size_t wa = plan->product == QB_CPROD_REAL_A ? 1 : 2, wbn = plan->product == QB_CPROD_REAL_B ? 1 : 2;   // words per element
+    const size_t bytes_a = wa * span_elems(batch, plan->stride_a, ea) * gp.a_wb, bytes_b = wbn * span_elems(batch, plan->stride_b, eb) * gp.b_wb,
                  bytes_c = 2 * span_elems(batch, plan->stride_c, ec) * gp.c_wb;
     const void *dA, *dB; void *dC;
     if ((rc = cx.in(A, bytes_a, &dA)) || (rc = cx.in(B, bytes_b, &dB)) || (rc = cx.out(C, bytes_c, &dC))) return rc;
@@ -614,11 +615,12 @@ extern "C" int qb200_tfcmul_batched(const qb_tfcmul_plan *plan, const void *x, c
     const uint64_t n = plan->len * batch;
     if (n == 0) return QB_OK;
     Ctx cx; int rc = cx.init(exec); if (rc) return rc;
-    const int xw = std::max(word_bytes(plan->x_re), word_bytes(plan->x_im)), yw = std::max(word_bytes(plan->y_re), word_bytes(plan->y_im));
-    const int ow = plan->product == QB_CPROD_BASIC ? std::max(natural_word(plan->bcm.acbd), natural_word(plan->bcm.adbc))
-                                                   : std::max(natural_word(plan->tf.AB), natural_word(plan->tf.BC));
+    const bool real_x = plan->product == QB_CPROD_REAL_A, real_y = plan->product == QB_CPROD_REAL_B;
+    const int xw = real_x ? word_bytes(plan->x_re) : std::max(word_bytes(plan->x_re), word_bytes(plan->x_im));
+    const int yw = real_y ? word_bytes(plan->y_re) : std::max(word_bytes(plan->y_re), word_bytes(plan->y_im));
+    const int ow = std::max(natural_word(re.t), natural_word(im.t));
     const void *dx, *dy; void *dout;
-    if ((rc = cx.in(x, 2 * n * xw, &dx)) || (rc = cx.in(y, 2 * n * yw, &dy)) || (rc = cx.out(out, 2 * n * ow, &dout))) return rc;
+    if ((rc = cx.in(x, (real_x ? 1 : 2) * n * xw, &dx)) || (rc = cx.in(y, (real_y ? 1 : 2) * n * yw, &dy)) || (rc = cx.out(out, 2 * n * ow, &dout))) return rc;
     if (arith_bits(an) == 32) { sanitize32(tf); sanitize32(bcm); }
     if (arith_bits(an) == 32) k_tfcmul<int32_t><<<grid_for(n, 256), 256, 0, cx.stream>>>(dx, dy, dout, n, xw, yw, ow, (int)plan->product, tf, bcm);
     else                      k_tfcmul<int64_t><<<grid_for(n, 256), 256, 0, cx.stream>>>(dx, dy, dout, n, xw, yw, ow, (int)plan->product, tf, bcm);

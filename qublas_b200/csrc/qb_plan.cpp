@@ -339,6 +339,20 @@ BcmProg build_bcm(TVal a, TVal b, TVal c, TVal d, const qb_bcm_types &t, TVal *r
     return p;
 }
 
+// real (x) complex (QuBLAS.h:3600-3637): two independent products.  kind = QB_CPROD_REAL_A (x = a real,
+// y = c + di) or QB_CPROD_REAL_B (x = a + bi, y = c real); unused stages stay zero.
+BcmProg build_rc(int kind, TVal a, TVal b, TVal c, TVal d, const qb_bcm_types &t, TVal *re, TVal *im, Analysis &an)
+{
+    BcmProg p;
+    memset(&p, 0, sizeof(p));
+    const qb_qdesc &imt = kind == QB_CPROD_REAL_A ? t.ad : t.bc;
+    if (!check_type(t.ac, an, "real-complex product type (real part)") || !check_type(imt, an, "real-complex product type (imaginary part)")) return p;
+    p.ac = make_mul(a, c, t.ac, re, an);
+    if (kind == QB_CPROD_REAL_A) p.ad = make_mul(a, d, t.ad, im, an);
+    else p.bc = make_mul(b, c, t.bc, im, an);
+    return p;
+}
+
 static void finish(Analysis &an)
 {
     if (an.status) return;
@@ -382,17 +396,20 @@ static int cword(qb_qdesc re, qb_qdesc im) { return std::max(word_bytes(re), wor
 
 int compile_cgemul(const qb_cgemul_plan &p, CGemulProg *out, Analysis &an)
 {
-    const qb_qdesc *ts[6] = { &p.a_re, &p.a_im, &p.b_re, &p.b_im, &p.c_re, &p.c_im };
+    if (p.product > QB_CPROD_REAL_B) { an.fail(QB_EINVAL, "bad complex product kind"); return an.status; }
+    const bool real_a = p.product == QB_CPROD_REAL_A, real_b = p.product == QB_CPROD_REAL_B;
+    const qb_qdesc &a_im = real_a ? p.a_re : p.a_im, &b_im = real_b ? p.b_re : p.b_im;       // the ignored descriptor is not validated
+    const qb_qdesc *ts[6] = { &p.a_re, &a_im, &p.b_re, &b_im, &p.c_re, &p.c_im };
     for (auto t : ts) if (!check_type(*t, an, "complex element type")) return an.status;
     if (!p.M || !p.N || !p.K) { an.fail(QB_EINVAL, "M, N, K must be >= 1"); return an.status; }
     if (p.tree_form > 1) { an.fail(QB_EINVAL, "bad tree_form"); return an.status; }
-    TVal a = { p.a_re, type_range(p.a_re) }, b = { p.a_im, type_range(p.a_im) };
-    TVal c = { p.b_re, type_range(p.b_re) }, d = { p.b_im, type_range(p.b_im) };
+    TVal a = { p.a_re, type_range(p.a_re) }, b = { a_im, type_range(a_im) };
+    TVal c = { p.b_re, type_range(p.b_re) }, d = { b_im, type_range(b_im) };
     TVal re, im;
-    if (p.product > 1) { an.fail(QB_EINVAL, "bad complex product kind"); return an.status; }
     out->kind = p.product;
     memset(&out->tf, 0, sizeof(out->tf)); memset(&out->bcm, 0, sizeof(out->bcm));
-    if (p.product == QB_CPROD_BASIC) out->bcm = build_bcm(a, b, c, d, p.bcm, &re, &im, an);
+    if (real_a || real_b) out->bcm = build_rc(p.product, a, b, c, d, p.bcm, &re, &im, an);
+    else if (p.product == QB_CPROD_BASIC) out->bcm = build_bcm(a, b, c, d, p.bcm, &re, &im, an);
     else out->tf = build_tf(a, b, c, d, p.tf, &re, &im, an);
     if (an.status) return an.status;
     TVal ar = build_tree(p.K, re, p.add_re, p.tree_form, &out->tree_re, an);
@@ -400,7 +417,7 @@ int compile_cgemul(const qb_cgemul_plan &p, CGemulProg *out, Analysis &an)
     TVal o;
     out->out_re = make_stage(ar.frac(), ar.r, width(ar.t), p.c_re, &o, an);
     out->out_im = make_stage(ai.frac(), ai.r, width(ai.t), p.c_im, &o, an);
-    out->a_wb = cword(p.a_re, p.a_im); out->b_wb = cword(p.b_re, p.b_im); out->c_wb = cword(p.c_re, p.c_im);
+    out->a_wb = cword(p.a_re, a_im); out->b_wb = cword(p.b_re, b_im); out->c_wb = cword(p.c_re, p.c_im);
     finish(an);
     return an.status;
 }
@@ -408,12 +425,15 @@ int compile_cgemul(const qb_cgemul_plan &p, CGemulProg *out, Analysis &an)
 int compile_tfcmul(const qb_tfcmul_plan &p, TfProg *out, BcmProg *bout, TVal *re, TVal *im, Analysis &an)
 {
     memset(out, 0, sizeof(*out)); memset(bout, 0, sizeof(*bout));
-    if (p.product > 1) { an.fail(QB_EINVAL, "bad complex product kind"); return an.status; }
-    const qb_qdesc *ts[4] = { &p.x_re, &p.x_im, &p.y_re, &p.y_im };
+    if (p.product > QB_CPROD_REAL_B) { an.fail(QB_EINVAL, "bad complex product kind"); return an.status; }
+    const bool real_x = p.product == QB_CPROD_REAL_A, real_y = p.product == QB_CPROD_REAL_B;
+    const qb_qdesc &x_im = real_x ? p.x_re : p.x_im, &y_im = real_y ? p.y_re : p.y_im;
+    const qb_qdesc *ts[4] = { &p.x_re, &x_im, &p.y_re, &y_im };
     for (auto t : ts) if (!check_type(*t, an, "complex element type")) return an.status;
-    TVal a = { p.x_re, type_range(p.x_re) }, b = { p.x_im, type_range(p.x_im) };
-    TVal c = { p.y_re, type_range(p.y_re) }, d = { p.y_im, type_range(p.y_im) };
-    if (p.product == QB_CPROD_BASIC) *bout = build_bcm(a, b, c, d, p.bcm, re, im, an);
+    TVal a = { p.x_re, type_range(p.x_re) }, b = { x_im, type_range(x_im) };
+    TVal c = { p.y_re, type_range(p.y_re) }, d = { y_im, type_range(y_im) };
+    if (real_x || real_y) *bout = build_rc((int)p.product, a, b, c, d, p.bcm, re, im, an);
+    else if (p.product == QB_CPROD_BASIC) *bout = build_bcm(a, b, c, d, p.bcm, re, im, an);
     else *out = build_tf(a, b, c, d, p.tf, re, im, an);
     finish(an);
     return an.status;

@@ -56,9 +56,10 @@ struct GemulProg {
     TVal     prod, acc;
 };
 BcmProg build_bcm(TVal a, TVal b, TVal c, TVal d, const qb_bcm_types &t, TVal *re, TVal *im, Analysis &an);
+BcmProg build_rc(int kind, TVal a, TVal b, TVal c, TVal d, const qb_bcm_types &t, TVal *re, TVal *im, Analysis &an);
 
 struct CGemulProg {
-    int      kind;         // QB_CPROD_TF / QB_CPROD_BASIC
+    int      kind;         // enum qb_cproduct
     TfProg   tf;
     BcmProg  bcm;
     TreeProg tree_re, tree_im;

@@ -19,7 +19,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import abi
-from .qtypes import (QType, TREE_VARIADIC, TREE_VECTOR, add_merge, mul_merge, resolve_bcm, resolve_tf, tree_out_type)
+from .qtypes import (QType, TREE_VARIADIC, TREE_VECTOR, add_merge, mul_merge, resolve_bcm, resolve_rc, resolve_tf, tree_out_type)
 
 try:  # torch is plumbing (device memory, streams); host-only use works without it
     import torch
@@ -164,10 +164,18 @@ def Qgemul(Cbuf, A, B, plan: abi.qb_gemul_plan, batch: int = 1, flags: int = 0):
 def make_cgemul_plan(a_re: QType, a_im: QType, b_re: QType, b_im: QType, c_re: QType, c_im: QType, M: int, N: int, K: int, *,
                      tf_tags=None, add_re: Optional[Sequence[QType]] = None, add_im: Optional[Sequence[QType]] = None,
                      trans_a=False, trans_b=False, form: int = TREE_VARIADIC, product: str = "tf") -> abi.qb_cgemul_plan:
-    """product: "tf" = TFComplexMul<tf_tags> (3 mult / 5 add), "basic" = BasicComplexMul<tf_tags> (4 mult / 2 add)."""
+    """product: "tf" = TFComplexMul<tf_tags> (3 mult / 5 add), "basic" = BasicComplexMul<tf_tags> (4 mult / 2 add),
+    "real_a" / "real_b" = real (x) complex Qmul<tf_tags> with A resp. B a REAL tensor (its *_im type is ignored;
+    tf_tags as in qtypes.resolve_rc)."""
     p = abi.qb_cgemul_plan()
-    p.a_re, p.a_im, p.b_re, p.b_im = (abi.desc(t) for t in (a_re, a_im, b_re, b_im))
-    if product == "basic":
+    p.a_re, p.a_im, p.b_re, p.b_im = (abi.desc(t) for t in (a_re, a_im if a_im is not None else a_re, b_re, b_im if b_im is not None else b_re))
+    if product == "real_a":
+        p.product = abi.QB_CPROD_REAL_A
+        p.bcm = abi.bcm_types(resolve_rc(True, a_re, b_re, b_im, tf_tags))
+    elif product == "real_b":
+        p.product = abi.QB_CPROD_REAL_B
+        p.bcm = abi.bcm_types(resolve_rc(False, b_re, a_re, a_im, tf_tags))
+    elif product == "basic":
         p.product = abi.QB_CPROD_BASIC
         p.bcm = abi.bcm_types(resolve_bcm(a_re, a_im, b_re, b_im, tf_tags))
     else:
@@ -188,11 +196,21 @@ def Qcgemul(Cbuf, A, B, plan: abi.qb_cgemul_plan, batch: int = 1, flags: int = 0
 
 
 def tfcmul(x, y, x_re: QType, x_im: QType, y_re: QType, y_im: QType, tf_tags=None, batch: int = 1, product: str = "tf"):
-    """Element-wise Qmul<TFComplexMul<tags...>>(x, y) (or BasicComplexMul with product="basic") on complex vectors (AoS pairs)."""
-    n = (x.numel() if _is_torch(x) else x.size) // 2
+    """Element-wise Qmul<TFComplexMul<tags...>>(x, y) (or BasicComplexMul with product="basic") on complex vectors (AoS pairs);
+    product="real_a" / "real_b": x resp. y is a REAL vector (one word per element) scaling the complex one."""
+    n = (y if product == "real_a" else x)
+    n = (n.numel() if _is_torch(n) else n.size) // 2
     p = abi.qb_tfcmul_plan()
-    p.x_re, p.x_im, p.y_re, p.y_im = (abi.desc(t) for t in (x_re, x_im, y_re, y_im))
-    if product == "basic":
+    p.x_re, p.x_im, p.y_re, p.y_im = (abi.desc(t) for t in (x_re, x_im if x_im is not None else x_re, y_re, y_im if y_im is not None else y_re))
+    if product == "real_a":
+        r = resolve_rc(True, x_re, y_re, y_im, tf_tags)
+        p.bcm = abi.bcm_types(r); p.product = abi.QB_CPROD_REAL_A
+        o_re, o_im = r["ac"], r["ad"]
+    elif product == "real_b":
+        r = resolve_rc(False, y_re, x_re, x_im, tf_tags)
+        p.bcm = abi.bcm_types(r); p.product = abi.QB_CPROD_REAL_B
+        o_re, o_im = r["ac"], r["bc"]
+    elif product == "basic":
         r = resolve_bcm(x_re, x_im, y_re, y_im, tf_tags)
         p.bcm = abi.bcm_types(r); p.product = abi.QB_CPROD_BASIC
         o_re, o_im = r["acbd"], r["adbc"]

@@ -140,6 +140,23 @@ def resolve_bcm(x_re: QType, x_im: QType, y_re: QType, y_im: QType, tags: Option
     return r
 
 
+def resolve_rc(real_first: bool, r: QType, c_re: QType, c_im: QType, tags=None) -> Dict[str, QType]:
+    """Product types of real (x) complex Qmul (QuBLAS.h:3600-3637).  `tags` is the merger argument pack:
+    {"realT": t, "imagT": t} per component, a (t_real, t_imag) pair (two positional types, :3618-3619), or one
+    QType / partial-tag dict / None that serves both components.  Keys follow qb_bcm_types: real operand first
+    (x = a, y = c+di): ac, ad; complex operand first (x = a+bi, y = c): ac, bc."""
+    if isinstance(tags, dict) and ("realT" in tags or "imagT" in tags):
+        rest = {k: v for k, v in tags.items() if k not in ("realT", "imagT")} or None
+        t_re, t_im = tags.get("realT", rest), tags.get("imagT", rest)
+    elif isinstance(tags, (tuple, list)):
+        t_re, t_im = tags
+    else:
+        t_re = t_im = tags
+    if real_first:
+        return {"ac": mul_merge(r, c_re, t_re), "ad": mul_merge(r, c_im, t_im)}
+    return {"ac": mul_merge(c_re, r, t_re), "bc": mul_merge(c_im, r, t_im)}
+
+
 def level_type(levels: Sequence[QType], layer: int, a: QType, b: QType) -> QType:
     """TypeAt<min(layer, n-1)> (QuBLAS.h:4913); no levels -> default AddMerger (:4917-4921)."""
     if not levels:

@@ -61,6 +61,38 @@ int main()
         std::printf("complex Qgemul BasicComplexMul: %s\n", bad_b ? "MISMATCH" : "OK");
         bad += bad_tf + bad_b;
 
+        // ---- mixed real / complex Qgemul: real 8x8 matrix times complex vector, and complex matrix times real vector ----
+        {
+            using R_t = Qu<dim<8, 8>, t>; using rv_t = Qu<dim<8>, t>;
+            using pr = Qu<intBits<6>, fracBits<12>, QuMode<RND::CONV>>; using pi = Qu<intBits<6>, fracBits<11>, QuMode<RND::ZERO>, OfMode<SAT::ZERO>>;
+            R_t Rm; rv_t rv; y_t ya, yb2;
+            for (std::size_t i = 0; i < 64; i++) Rm[i].fill();
+            for (std::size_t i = 0; i < 8; i++) rv[i].fill();
+            Qgemul<QgemulAddArgs<clv>, QgemulMulArgs<realT<pr>, imagT<pi>>>(ya, Rm, x);       // real A, complex B
+            Qgemul<QgemulMulArgs<pr>, QgemulAddArgs<clv>>(yb2, H, rv);                        // complex A, real B, one type for both parts
+            int bad_rc = 0;
+            for (int i = 0; i < 8; i++) {
+                auto w = Qreduce<clv>(Qmul<realT<pr>, imagT<pi>>(Rm[i, 0], x[0]), Qmul<realT<pr>, imagT<pi>>(Rm[i, 1], x[1]), Qmul<realT<pr>, imagT<pi>>(Rm[i, 2], x[2]),
+                                      Qmul<realT<pr>, imagT<pi>>(Rm[i, 3], x[3]), Qmul<realT<pr>, imagT<pi>>(Rm[i, 4], x[4]), Qmul<realT<pr>, imagT<pi>>(Rm[i, 5], x[5]),
+                                      Qmul<realT<pr>, imagT<pi>>(Rm[i, 6], x[6]), Qmul<realT<pr>, imagT<pi>>(Rm[i, 7], x[7]));
+                out_s wr = w.real, wi = w.imag;
+                if (wr.data.data != ya[i].real.data.data || wi.data.data != ya[i].imag.data.data) bad_rc++;
+                auto v = Qreduce<clv>(Qmul<pr>(H[i, 0], rv[0]), Qmul<pr>(H[i, 1], rv[1]), Qmul<pr>(H[i, 2], rv[2]), Qmul<pr>(H[i, 3], rv[3]),
+                                      Qmul<pr>(H[i, 4], rv[4]), Qmul<pr>(H[i, 5], rv[5]), Qmul<pr>(H[i, 6], rv[6]), Qmul<pr>(H[i, 7], rv[7]));
+                out_s vr = v.real, vi = v.imag;
+                if (vr.data.data != yb2[i].real.data.data || vi.data.data != yb2[i].imag.data.data) bad_rc++;
+            }
+            auto ez = Qmul<realT<pr>, imagT<pi>>(rv, x);                                      // element-wise real (x) complex tensors
+            auto ez2 = Qmul<pi, pr>(x, rv);
+            for (std::size_t i = 0; i < 8; i++) {
+                auto e1 = Qmul<realT<pr>, imagT<pi>>(rv[i], x[i]); auto e2 = Qmul<pi, pr>(x[i], rv[i]);
+                if (e1.real.data.data != ez[i].real.data.data || e1.imag.data.data != ez[i].imag.data.data) bad_rc++;
+                if (e2.real.data.data != ez2[i].real.data.data || e2.imag.data.data != ez2[i].imag.data.data) bad_rc++;
+            }
+            std::printf("real-by-complex Qgemul / Qmul: %s\n", bad_rc ? "MISMATCH" : "OK");
+            bad += bad_rc;
+        }
+
         // ---- element-wise tensor ops (the reference's lazy expressions, evaluated eagerly on the GPU) ----
         {
             using v_t = Qu<dim<100>, in_t>;

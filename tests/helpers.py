@@ -69,3 +69,14 @@ def tfcmul_plan(x_re, x_im, y_re, y_im, tags, n):
 
 def tf_tags(d):
     return {k: qt(v) for k, v in d.items()}
+
+
+def rc_targs(t):
+    """Merger arguments of a ref_rc.json case in the form qtypes.resolve_rc takes."""
+    if t["mode"] == "none":
+        return None
+    if t["mode"] == "one":
+        return qt(t["t"])
+    if t["mode"] == "pair":
+        return (qt(t["re"]), qt(t["im"]))
+    return {"realT": qt(t["re"]), "imagT": qt(t["im"])}

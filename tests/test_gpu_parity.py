@@ -434,6 +434,67 @@ def test_basic_complex_mul_gpu():
         assert np.array_equal(Cd.cpu().numpy(), want), (M, N, K, form)
 
 
+def test_real_complex_products_gpu():
+    """real (x) complex Qmul and mixed real/complex Qgemul (next row 8(f).2): the reference's own answers
+    (tests/golden/ref_rc.json) element-wise and as 1xK dot products, then random shapes against the oracle."""
+    from qublas_b200.qtypes import resolve_rc
+    from tests.helpers import rc_targs
+    n = 0
+    for c in load_cases("ref_rc.json"):
+        if c["kind"] == "rc" and c["op"] == "mul":
+            r, cre, cim = qt(c["r"]), qt(c["c_re"]), qt(c["c_im"])
+            real = np.array([i[0] for i in c["inputs"]], dtype=np.int32)
+            cplx = np.array([i[1:3] for i in c["inputs"]], dtype=np.int32).reshape(-1)
+            if c["real_first"]:
+                out, _ = ops.tfcmul(dev(real), dev(cplx), r, None, cre, cim, rc_targs(c["targs"]), product="real_a")
+            else:
+                out, _ = ops.tfcmul(dev(cplx), dev(real), cre, cim, r, None, rc_targs(c["targs"]), product="real_b")
+            got = out.cpu().numpy().reshape(-1, 2)
+            assert [[int(a), int(b)] for a, b in got] == [o[0:2] for o in c["outputs"]], c["targs"]
+            n += len(c["inputs"])
+        elif c["kind"] == "rcgemul":
+            K = c["K"]; rf = c["real_first"]
+            r, cre, cim = qt(c["r"]), qt(c["c_re"]), qt(c["c_im"])
+            rr = resolve_rc(rf, r, cre, cim, rc_targs(c["targs"]))
+            lv = [qt(t) for t in c["levels"]]
+            o_re = tree_out_type(K, rr["ac"], lv, TREE_VARIADIC); o_im = tree_out_type(K, rr["ad" if rf else "bc"], lv, TREE_VARIADIC)
+            args = (r, None, cre, cim) if rf else (cre, cim, r, None)
+            plan = ops.make_cgemul_plan(*args, o_re, o_im, 1, 1, K, tf_tags=rc_targs(c["targs"]), add_re=lv, form=TREE_VARIADIC,
+                                        product="real_a" if rf else "real_b")
+            batch = len(c["inputs"])
+            v = np.array(c["inputs"], dtype=np.int32).reshape(batch, K, 3)
+            real = np.ascontiguousarray(v[:, :, 0]).reshape(-1); cplx = np.ascontiguousarray(v[:, :, 1:3]).reshape(-1)
+            Cd = torch.empty(batch * 2, dtype=torch.int32, device="cuda"); assert max(o_re.word_bytes, o_im.word_bytes) == 4
+            ops.Qcgemul(Cd, dev(real if rf else cplx), dev(cplx if rf else real), plan, batch=batch)
+            got = Cd.cpu().numpy().reshape(batch, 2)
+            assert [[int(a), int(b)] for a, b in got] == [o[0:2] for o in c["outputs"]], (K, rf)
+            n += batch
+    assert n >= 448
+    rng = np.random.default_rng(33)
+    for (M, N, K, form, rf, ta, tb, wide) in [(4, 3, 16, TREE_VARIADIC, True, False, False, False), (8, 2, 7, TREE_VECTOR, False, True, False, False),
+                                              (3, 5, 9, TREE_VECTOR, True, False, True, False), (6, 4, 33, TREE_VARIADIC, False, False, False, True)]:
+        r, cre, cim = QType(5, 7), QType(4, 8, True, 2, 1), QType(3, 9)
+        tags = {"realT": QType(22 if wide else 9, 14 if wide else 8, True, 4, 0), "imagT": QType(8, 9, True, 3, 2)}
+        rr = resolve_rc(rf, r, cre, cim, tags)
+        lre = _rand_levels(rng, rr["ac"], 4); lim = _rand_levels(rng, rr["ad" if rf else "bc"], 4)
+        args = (r, None, cre, cim) if rf else (cre, cim, r, None)
+        plan = ops.make_cgemul_plan(*args, QType(12, 4, True, 4, 0), QType(12, 3), M, N, K, tf_tags=tags, add_re=lre, add_im=lim,
+                                    form=form, product="real_a" if rf else "real_b", trans_a=ta, trans_b=tb)
+        batch = 3
+        ea, eb = batch * M * K, batch * K * N
+        def cplx_words(n):
+            return np.stack([rand_words(rng, cre, n), rand_words(rng, cim, n)], axis=1).astype(np.int32).reshape(-1)
+        A = rand_words(rng, r, ea).astype(np.int32) if rf else cplx_words(ea)
+        B = cplx_words(eb) if rf else rand_words(rng, r, eb).astype(np.int32)
+        want = oracle.cgemul_batched(plan, A, B, batch)
+        Cd = torch.empty(batch * M * N * 2, dtype=torch.int32, device="cuda")
+        ops.Qcgemul(Cd, dev(A), dev(B), plan, batch=batch)
+        assert np.array_equal(Cd.cpu().numpy(), want), (M, N, K, form, rf)
+        Ch = np.zeros(batch * M * N * 2, dtype=np.int32)                 # host buffers through the staging pipeline
+        ops.Qcgemul(Ch, A, B, plan, batch=batch)
+        assert np.array_equal(Ch, want)
+
+
 def test_elementwise_tensor_ops_vs_reference_goldens_and_oracle():
     """Element-wise Qmul/Qadd/Qsub on tensors (next row 8(f).3): every scalar golden of the reference, run as
     one-element-per-input tensors on the GPU, plus random large tensors against the oracle."""

@@ -22,7 +22,7 @@ LINK = ["-L" + os.path.join(ROOT, "qublas_b200"), "-lqb200", "-Wl,-rpath," + os.
 
 def _load():
     cases = []
-    for kind in ("scalar", "reduce", "tf", "gemul", "cgemul", "fromdouble", "bcm"):
+    for kind in ("scalar", "reduce", "tf", "gemul", "cgemul", "fromdouble", "bcm", "rc"):
         with open(os.path.join(GOLD, "ref_%s.json" % kind)) as f:
             cases += json.load(f)["cases"]
     return cases
@@ -37,7 +37,7 @@ def harness(tmp_path_factory):
 
 
 def _host_only(c):
-    return c["kind"] in ("scalar", "tf", "cgemul", "fromdouble", "bcm") or (c["kind"] == "reduce" and c["form"] == "variadic")
+    return c["kind"] in ("scalar", "tf", "cgemul", "fromdouble", "bcm", "rc", "rcgemul") or (c["kind"] == "reduce" and c["form"] == "variadic")
 
 
 def test_header_scalar_paths_match_reference(harness):

@@ -145,6 +145,49 @@ def test_basic_complex_mul_matches_reference():
     assert [int(got[0]), int(got[1])] == [-91, 113]
 
 
+def _rc_plan_args(c):
+    """(x_re, x_im, y_re, y_im, product, key of the imaginary product type) of a real-by-complex case."""
+    r, cre, cim = qt(c["r"]), qt(c["c_re"]), qt(c["c_im"])
+    return (r, None, cre, cim, "real_a", "ad") if c["real_first"] else (cre, cim, r, None, "real_b", "bc")
+
+
+def test_real_complex_products_match_reference():
+    """real (x) complex Qmul in both operand orders, every form of its target arguments (QuBLAS.h:3600-3637), and the
+    mixed dot product = variadic complex Qreduce over such products: oracle == reference header."""
+    from qublas_b200 import ops
+    from qublas_b200.qtypes import resolve_rc
+    from tests.helpers import rc_targs
+    n_mul = n_dot = 0
+    for c in load_cases("ref_rc.json"):
+        if c["kind"] == "rc" and c["op"] == "mul":
+            xr, xi, yr, yi, product, imk = _rc_plan_args(c)
+            r = resolve_rc(c["real_first"], qt(c["r"]), qt(c["c_re"]), qt(c["c_im"]), rc_targs(c["targs"]))
+            p = abi.qb_tfcmul_plan()
+            p.x_re, p.x_im, p.y_re, p.y_im = (abi.desc(t) for t in (xr, xi or xr, yr, yi or yr))
+            p.bcm = abi.bcm_types(r); p.product = abi.QB_CPROD_REAL_A if c["real_first"] else abi.QB_CPROD_REAL_B; p.len = 1
+            for inp, out in zip(c["inputs"], c["outputs"]):
+                assert out[2:7] == type_tuple(r["ac"]) and out[7:12] == type_tuple(r[imk]), c["targs"]
+                real, cplx = np.array(inp[:1], dtype=np.int32), np.array(inp[1:], dtype=np.int32)
+                got = oracle.tfcmul_batched(p, real if c["real_first"] else cplx, cplx if c["real_first"] else real, 1)
+                assert [int(got[0]), int(got[1])] == out[:2], (c["targs"], inp)
+                n_mul += 1
+        elif c["kind"] == "rcgemul":
+            K = c["K"]
+            xr, xi, yr, yi, product, imk = _rc_plan_args(c)
+            r = resolve_rc(c["real_first"], qt(c["r"]), qt(c["c_re"]), qt(c["c_im"]), rc_targs(c["targs"]))
+            lv = [qt(t) for t in c["levels"]]
+            o_re = tree_out_type(K, r["ac"], lv, TREE_VARIADIC); o_im = tree_out_type(K, r[imk], lv, TREE_VARIADIC)
+            plan = ops.make_cgemul_plan(xr, xi, yr, yi, o_re, o_im, 1, 1, K, tf_tags=rc_targs(c["targs"]), add_re=lv, form=TREE_VARIADIC, product=product)
+            for inp, out in zip(c["inputs"], c["outputs"]):
+                v = np.array(inp, dtype=np.int32).reshape(K, 3)
+                real, cplx = np.ascontiguousarray(v[:, 0]), np.ascontiguousarray(v[:, 1:3]).reshape(-1)
+                assert out[2:7] == type_tuple(o_re) and out[7:12] == type_tuple(o_im)
+                got = oracle.cgemul_batched(plan, real if c["real_first"] else cplx, cplx if c["real_first"] else real, 1)
+                assert [int(got[0]), int(got[1])] == out[0:2], (K, c["real_first"], out, got)
+                n_dot += 1
+    assert n_mul >= 400 and n_dot >= 48
+
+
 def test_gemul_matches_reference_composition():
     cases = load_cases("ref_gemul.json")
     for c in cases:
