@@ -298,6 +298,51 @@ __global__ void k_pack_i8_transpose(const W *__restrict__ src, int8_t *__restric
         dst[(uint64_t)(r0 + i) * Cn + c0 + threadIdx.x] = tile[threadIdx.x][i];
 }
 
+// int32 words (the reference's storage for W <= 32), streamed at HBM rate: 16-byte loads, 128-byte row stores.
+__device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d)
+{
+    return (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) | ((uint32_t)d << 24);
+}
+// straight: 4 independent 16-byte loads per thread, one 16-byte store; n % 16 == 0
+__global__ void __launch_bounds__(256)
+k_pack_i8_straight_w4(const int4 *__restrict__ src, uint4 *__restrict__ dst, uint64_t n16)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) {
+        const int4 a = __ldcs(src + 4 * i), b = __ldcs(src + 4 * i + 1), c = __ldcs(src + 4 * i + 2), d = __ldcs(src + 4 * i + 3);
+        dst[i] = make_uint4(pack4(a.x, a.y, a.z, a.w), pack4(b.x, b.y, b.z, b.w), pack4(c.x, c.y, c.z, c.w), pack4(d.x, d.y, d.z, d.w));
+    }
+}
+// transpose: one CTA moves a 128 (r) x 128 (c) tile.  A lane is (lr, lc): 8 lanes along r read one full 128-byte line
+// of a column as int4, 4 lane groups take 4 neighbouring column quads; each thread so holds a 4x4 block, packs the four
+// columns of each of its rows into one word and parks it in shared memory (row stride 33 words: conflict-free both
+// ways); rows then leave as 128 contiguous bytes.  R % 128 == 0, Cn % 128 == 0.
+__global__ void __launch_bounds__(256)
+k_pack_i8_transpose_w4(const int *__restrict__ src, uint32_t *__restrict__ dst, uint32_t R, uint32_t Cn)
+{
+    __shared__ uint32_t tile[128 * 33];
+    const uint32_t r0 = blockIdx.x * 128, c0 = blockIdx.y * 128;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, lr = lane & 7, lc = lane >> 3;
+#pragma unroll
+    for (uint32_t it = 0; it < 4; ++it) {
+        const uint32_t blk = warp * 4 + it;                    // 32 warp-iterations: 4 r-blocks of 32 x 8 c-blocks of 16
+        const uint32_t rb = (blk & 3) * 32 + lr * 4, cb = (blk >> 2) * 16 + lc * 4;
+        int4 v[4];
+#pragma unroll
+        for (uint32_t i = 0; i < 4; ++i) v[i] = __ldcs((const int4 *)(src + (uint64_t)(c0 + cb + i) * R + r0 + rb));
+        uint32_t *t = tile + rb * 33 + (cb >> 2);
+        t[0] = pack4(v[0].x, v[1].x, v[2].x, v[3].x);
+        t[33] = pack4(v[0].y, v[1].y, v[2].y, v[3].y);
+        t[66] = pack4(v[0].z, v[1].z, v[2].z, v[3].z);
+        t[99] = pack4(v[0].w, v[1].w, v[2].w, v[3].w);
+    }
+    __syncthreads();
+#pragma unroll
+    for (uint32_t it = 0; it < 16; ++it) {
+        const uint32_t r = warp * 16 + it;
+        dst[((uint64_t)(r0 + r) * Cn + c0) / 4 + lane] = tile[r * 33 + lane];
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -334,6 +379,19 @@ template <typename W>
 static void pack_operand(const void *src, int8_t *dst, uint32_t rows_contig, uint32_t cols, bool transpose, cudaStream_t s)
 {
     // src is column-major rows_contig x cols
+    if constexpr (sizeof(W) == 4) {
+        const uint64_t n = (uint64_t)rows_contig * cols;
+        if (!transpose && n % 16 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0) {
+            k_pack_i8_straight_w4<<<(unsigned)std::min<uint64_t>((n / 16 + 255) / 256, 148 * 16), 256, 0, s>>>((const int4 *)src, (uint4 *)dst, n / 16);
+            count_launch(1);
+            return;
+        }
+        if (transpose && rows_contig % 128 == 0 && cols % 128 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 3) == 0) {
+            k_pack_i8_transpose_w4<<<dim3(rows_contig / 128, cols / 128), 256, 0, s>>>((const int *)src, (uint32_t *)dst, rows_contig, cols);
+            count_launch(1);
+            return;
+        }
+    }
     if (!transpose) {
         const uint64_t n = (uint64_t)rows_contig * cols;
         k_pack_i8_straight<W><<<(unsigned)std::min<uint64_t>((n / 4 + 255) / 256, 148 * 32), 256, 0, s>>>((const W *)src, dst, n);
