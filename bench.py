@@ -269,7 +269,7 @@ def run_ours(args):
 
     # ---- end to end through the public API with pinned HOST buffers ----
     chunk = min(args.e2e_chunk, Bn)
-    slots = 4
+    slots = 2
     hA = [torch.empty(chunk * WORDS, dtype=torch.int32).pin_memory() for _ in range(slots)]
     hB = [torch.empty(chunk * WORDS, dtype=torch.int32).pin_memory() for _ in range(slots)]
     hC = [torch.empty(chunk * WORDS, dtype=torch.int32).pin_memory() for _ in range(slots)]
@@ -553,7 +553,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=1000000, help="instances per GPU (BASELINE config 3: 1e6)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--e2e-chunk", type=int, default=8192, help="instances per host-buffer API call")
+    ap.add_argument("--e2e-chunk", type=int, default=32768, help="instances per host-buffer API call")
     ap.add_argument("--e2e-instances", type=int, default=1000000, help="instances per end-to-end step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5"],

@@ -170,7 +170,17 @@ static int host_pipeline(int nin, const PipeIn *ins, char *out, size_t out_unit_
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     size_t unit_total = out_unit_bytes, shared_total = 0;
     for (int i = 0; i < nin; i++) { if (ins[i].shared) shared_total += al(ins[i].shared_bytes); else unit_total += ins[i].unit_bytes; }
-    uint64_t cu = (48u << 20) / (unit_total ? unit_total : 1);
+    // Chunk = bytes in + out per pipeline step.  Measured on B200 / PCIe gen5 (tools/e2e_sweep.py): the link saturates with
+    // 48..96 MiB chunks as long as a call is cut into >= 8 of them; smaller chunks pay per-copy latency, fewer chunks
+    // leave the ends of the pipeline exposed.  QB200_PIPE_MB overrides.
+    static long forced_mb = -1;
+    if (forced_mb < 0) { const char *e = getenv("QB200_PIPE_MB"); long v = e ? atol(e) : 0; forced_mb = (v > 0 && v <= 1024) ? v : 0; }
+    size_t chunk_bytes = (size_t)forced_mb << 20;
+    if (!chunk_bytes) {
+        const size_t total = (size_t)units * unit_total;
+        chunk_bytes = std::min<size_t>((size_t)96 << 20, std::max<size_t>((size_t)12 << 20, total / 8));
+    }
+    uint64_t cu = chunk_bytes / (unit_total ? unit_total : 1);
     if (cu < 1) cu = 1;
     if (cu > units) cu = units;
     size_t slot_bytes = al(cu * out_unit_bytes);
