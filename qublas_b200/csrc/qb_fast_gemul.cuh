@@ -79,6 +79,22 @@ QB_DEV void stack_push(I (&st)[NTOP > 0 ? NTOP : 1], uint32_t c, I v, I &result)
     }
 }
 
+// Occupancy target: 512 resident threads per SM at the 128-register cap, bounded by shared memory.  Measured on B200
+// (config 3, via QB200_JIT_DEFINES=-DQB_MIN_BLOCKS=n): 2 CTAs of 256 threads (16 warps, 52 words spilled) and 1 CTA with
+// 202 registers and no spills run within noise of each other, 3 CTAs (85 registers) are 6 % slower, and prefetching the
+// operands one half-chunk ahead (235 registers) changes nothing -- the loop is bound by pipe issue, not by latency.
+constexpr int gemul_min_blocks(int threads, unsigned smem_bytes)
+{
+#ifdef QB_MIN_BLOCKS
+    (void)threads; (void)smem_bytes;
+    return QB_MIN_BLOCKS;
+#else
+    int n = 512 / threads, by_smem = (int)((227u * 1024u) / (smem_bytes + 1024u));
+    if (n > by_smem) n = by_smem;
+    return n < 1 ? 1 : (n > 8 ? 8 : n);
+#endif
+}
+
 constexpr QStage stage_without_clamps(QStage q) { q.need_lo = 0; q.need_hi = 0; return q; }
 
 // One instance's 4x4 register tile.  CLAMP = false is the same arithmetic with Qmul's saturation removed;
@@ -278,7 +294,7 @@ QB_DEV void gemul_tile_body(const int32_t *__restrict__ A, const int32_t *__rest
 }
 
 template <class Cfg>
-__global__ void __launch_bounds__(GemulTile<Cfg, 4, 4>::THREADS, (GemulTile<Cfg, 4, 4>::THREADS <= 256 ? 2 : 1))
+__global__ void __launch_bounds__(GemulTile<Cfg, 4, 4>::THREADS, gemul_min_blocks(GemulTile<Cfg, 4, 4>::THREADS, GemulTile<Cfg, 4, 4>::SMEM_BYTES))
 k_gemul_tile(const int32_t *__restrict__ A, const int32_t *__restrict__ B, int32_t *__restrict__ C, uint64_t batch)
 {
     gemul_tile_body<Cfg>(A, B, C, batch);

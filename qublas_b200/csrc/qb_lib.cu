@@ -276,7 +276,7 @@ static std::shared_ptr<GemulC> get_gemul(const qb_gemul_plan &p)
         e.bits = arith_bits(e.an); e.fast = nullptr; e.tc = false;
         if (!e.an.status) {
             if (e.bits == 32) { sanitize32_stage(e.prog.mul); sanitize32(e.prog.tree); sanitize32_stage(e.prog.out); }
-            e.fast = find_fast_gemul(p, e.prog, e.bits);
+            e.fast = getenv("QB200_NO_AOT") ? nullptr : find_fast_gemul(p, e.prog, e.bits);   // experiments: force the JIT build of the same source
             e.tc = gemul_tensor_core_ok(p, e.prog, e.an) && i8gemm_shape_ok(p.M, p.N, p.K);
         }
     });
