@@ -331,8 +331,8 @@ def run_ours(args):
                          "note": "this kernel is bound by the INT32 issue rate, not HBM: see roofline_alu"},
             "roofline_alu": roofline_alu(lib, value / world, local),
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "GMAC/s", "h2d_bytes_per_step": e2e_instances * 2 * WORDS * 4,
-                    "d2h_bytes_per_step": e2e_instances * WORDS * 4},
+            "e2e": {"value": e2e_value, "unit": "GMAC/s", "h2d_bytes_per_step": world * e2e_instances * 2 * WORDS * 4,
+                    "d2h_bytes_per_step": world * e2e_instances * WORDS * 4, "scope": "whole job (all ranks)"},
             "gpu_launches": launches,
             "bit_exact_checked": "first and last instance of every rank vs oracle",
         }
