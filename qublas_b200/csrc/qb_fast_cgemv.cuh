@@ -107,7 +107,10 @@ k_cgemv_rows(const int2 *__restrict__ H, const int2 *__restrict__ X, int2 *__res
 template <class Cfg>
 static int launch_cgemv_rows(const void *A, const void *B, void *C, uint64_t batch, cudaStream_t s)
 {
-    static int grid_cap = 0;
+    static int grid_caps[64] = { 0 };                 // per device: function attributes and occupancy belong to a context
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    int &grid_cap = grid_caps[cur_dev & 63];
     if (!grid_cap) {
         int dev = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);

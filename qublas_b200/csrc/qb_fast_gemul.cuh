@@ -305,7 +305,10 @@ template <class Cfg>
 static int launch_gemul_tile(const void *A, const void *B, void *C, uint64_t batch, cudaStream_t s)
 {
     typedef GemulTile<Cfg, 4, 4> T;
-    static int grid_cap = 0;
+    static int grid_caps[64] = { 0 };                 // per device: function attributes and occupancy belong to a context
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    int &grid_cap = grid_caps[cur_dev & 63];
     if (!grid_cap) {
         cudaError_t e = cudaFuncSetAttribute(k_gemul_tile<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM_BYTES);
         if (e != cudaSuccess) return (int)e;

@@ -429,14 +429,14 @@ int i8gemm_run(const void *A, const void *B, void *C, uint32_t M, uint32_t N, ui
     const bool mc = variant == 1 && (M / BM) % 2 == 0;
     CUtensorMap mapA, mapB;
     if (make_map(&mapA, Ap, M, K, BM) || make_map(&mapB, Bp, N, K, mc ? BN / 2 : BN)) { *err = "cuTensorMapEncodeTiled failed"; return -1; }
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(k_i8gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(k_i8gemm_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) { *err = "cannot raise dynamic smem"; return -1; }
-        attr_set = true;
-    }
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
+    static bool attr_set[64] = { false };          // function attributes are per device
+    if (!attr_set[dev & 63]) {
+        if (cudaFuncSetAttribute(k_i8gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(k_i8gemm_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) { *err = "cannot raise dynamic smem"; return -1; }
+        attr_set[dev & 63] = true;
+    }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     I8Params P;
     P.M = M; P.N = N; P.K = K; P.tiles_m = M / BM; P.tiles_n = N / BN; P.c_wb = c_wb; P.group_m = 16;

@@ -238,9 +238,23 @@ static void fill_info(qb_plan_info *info, const Analysis &an, qb_qdesc out_t, in
 // compiled-plan cache: a plan is compiled (types resolved, intervals analysed, kernel selected) once
 // per process; later calls with the same plan bytes cost one hash lookup.
 // ---------------------------------------------------------------------------------------------
-struct ReduceC { ReduceProg prog; Analysis an; int bits; const FastReduce *fast; std::once_flag jit_once; std::shared_ptr<JitKernel> jit; };
-struct GemulC  { GemulProg prog; Analysis an; int bits; const FastGemul *fast; bool tc; std::once_flag jit_once; std::shared_ptr<JitKernel> jit; };
-struct CGemulC { CGemulProg prog; Analysis an; int bits; const FastCGemul *fast; std::once_flag jit_once; std::shared_ptr<JitKernel> jit; };
+// A JIT-built kernel is a CUmodule in ONE device's primary context, so every cached plan keeps one slot per device.
+static constexpr int QB_MAX_DEV = 64;
+struct JitSlots {
+    std::once_flag once[QB_MAX_DEV];
+    std::shared_ptr<JitKernel> k[QB_MAX_DEV];
+    static int here() { int d = 0; if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); d = 0; } return d & (QB_MAX_DEV - 1); }
+    template <class Build> JitKernel *get(Build build)
+    {
+        const int d = here();
+        std::call_once(once[d], [&] { k[d] = build(); });
+        return (k[d] && k[d]->ok) ? k[d].get() : nullptr;
+    }
+    bool built_here() const { const int d = here(); return k[d] && k[d]->ok; }
+};
+struct ReduceC { ReduceProg prog; Analysis an; int bits; const FastReduce *fast; JitSlots jit; };
+struct GemulC  { GemulProg prog; Analysis an; int bits; const FastGemul *fast; bool tc; JitSlots jit; };
+struct CGemulC { CGemulProg prog; Analysis an; int bits; const FastCGemul *fast; JitSlots jit; };
 
 template <class Plan, class Entry, class Build>
 static std::shared_ptr<Entry> cached(const Plan &p, Build build)
@@ -428,8 +442,7 @@ extern "C" int qb200_reduce_batched(const qb_reduce_plan *plan, const void *x, v
     const FastReduce *fr = (partials || (cx.flags & QB_F_NO_SPECIALIZE) || ((uintptr_t)dx & 15)) ? nullptr : ce->fast;
     JitKernel *jk = nullptr;
     if (!fr && !partials && !(cx.flags & QB_F_NO_SPECIALIZE) && !((uintptr_t)dx & 15)) {
-        std::call_once(ce->jit_once, [&] { ce->jit = jit_reduce(*plan, rp, arith_bits(an)); });
-        if (ce->jit && ce->jit->ok) jk = ce->jit.get();
+        jk = ce->jit.get([&] { return jit_reduce(*plan, rp, arith_bits(an)); });
     }
     if (fr) {
         void *scratch;
@@ -476,7 +489,7 @@ extern "C" int qb200_gemul_plan_info(const qb_gemul_plan *plan, qb_plan_info *in
     const GemulProg &gp = ce->prog; const Analysis &an = ce->an; const FastGemul *f = ce->fast;
     qb_qdesc ct = plan->c; ct.word_bytes = 0;
     const bool tc = ce->tc;
-    const bool jit_built = ce->jit && ce->jit->ok;
+    const bool jit_built = ce->jit.built_here();
     fill_info(info, an, ct, gp.c_wb, tc ? "k_i8gemm (tcgen05 kind::i8)" : (f ? f->name : (jit_built ? "k_gemul_tile<jit>" : "k_gemul_thread")), tc,
               f != nullptr || jit_built);
     return QB_OK;
@@ -498,8 +511,7 @@ extern "C" int qb200_gemul_batched(const qb_gemul_plan *plan, const void *A, con
     const FastGemul *f = (cx.flags & QB_F_NO_SPECIALIZE) ? nullptr : ce->fast;
     JitKernel *jk = nullptr;
     if (!f && !ce->tc && !(cx.flags & QB_F_NO_SPECIALIZE) && plan->stride_a == (int64_t)ea && plan->stride_b == (int64_t)eb && plan->stride_c == (int64_t)ec) {
-        std::call_once(ce->jit_once, [&] { ce->jit = jit_gemul(*plan, gp, bits); });
-        if (ce->jit && ce->jit->ok) jk = ce->jit.get();
+        jk = ce->jit.get([&] { return jit_gemul(*plan, gp, bits); });
     }
     // one launch over n instances laid out with the given strides
     auto launch = [&](const void *dA, const void *dB, void *dC, uint64_t n, int64_t sa, int64_t sb, int64_t sc, cudaStream_t st) -> int {
@@ -590,8 +602,7 @@ extern "C" int qb200_cgemul_batched(const qb_cgemul_plan *plan, const void *A, c
     const FastCGemul *f = (cx.flags & QB_F_NO_SPECIALIZE) ? nullptr : ce->fast;
     JitKernel *jk = nullptr;
     if (!f && !(cx.flags & QB_F_NO_SPECIALIZE) && plan->stride_a == (int64_t)ea && plan->stride_b == (int64_t)eb && plan->stride_c == (int64_t)ec) {
-        std::call_once(ce->jit_once, [&] { ce->jit = jit_cgemul(*plan, gp, bits); });
-        if (ce->jit && ce->jit->ok) jk = ce->jit.get();
+        jk = ce->jit.get([&] { return jit_cgemul(*plan, gp, bits); });
     }
     if (f) {
         rc = f->launch(dA, dB, dC, batch, cx.stream);

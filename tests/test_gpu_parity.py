@@ -568,3 +568,27 @@ def test_launch_counter_counts_kernels():
     x = torch.zeros(1 << 16, dtype=torch.int32, device="cuda")
     ops.Qreduce(x, QType(8, 8), [QType(9, 8)])
     assert lib.qb200_launch_count() == 2          # 2^16 -> 16 partials -> root
+
+
+def test_two_devices_in_one_process():
+    """The C ABI takes a device ordinal per call: function attributes, occupancy figures and JIT-built modules are kept
+    per device, so one process can drive several GPUs (needs >= 2 visible GPUs; `gpurun --gpus 2`)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rng = np.random.default_rng(77)
+    a = QType(7, 8); mul = QType(14, 8, True, RND_CONV, SAT_TCPL)
+    lv = [QType(15 + l, 8 - l, True, RND_POS_INF, SAT_TCPL) for l in range(6)]; c = QType(17, 4, True, RND_POS_INF, SAT_TCPL)
+    aot = ops.make_gemul_plan(a, a, c, 64, 64, 64, mul=mul, add=lv)                        # ahead-of-time kernel (dynamic smem attribute)
+    ja = QType(5, 6); jmul = QType(9, 6, True, 4, 0); jlv = [QType(10 + l, 6 - l, True, 2, 0) for l in range(4)]
+    jit = gemul_plan(ja, ja, jmul, QType(13, 2, True, 0, 0), jlv, 32, 32, 16)              # NVRTC-built kernel (module per context)
+    i8 = QType(7, 0); acc = QType(30, 0)
+    tc = ops.make_gemul_plan(i8, i8, acc, 128, 256, 128, mul=QType(15, 0), add=[acc])      # tcgen05 path
+    for plan, t, batch in ((aot, a, 6), (jit, ja, 5), (tc, i8, 1)):
+        M, N, K = plan.M, plan.N, plan.K
+        A = rand_words(rng, t, batch * M * K).astype(np.int32); B = rand_words(rng, t, batch * K * N).astype(np.int32)
+        want = oracle.gemul_batched(plan, A, B, batch)
+        for d in (0, 1, 0):
+            dv = torch.device("cuda", d)
+            Cd = torch.empty(batch * M * N, dtype=torch.int32, device=dv)
+            ops.Qgemul(Cd, torch.from_numpy(A).to(dv), torch.from_numpy(B).to(dv), plan, batch=batch)
+            assert np.array_equal(Cd.cpu().numpy(), want), (d, M, N, K)
