@@ -76,6 +76,31 @@ std::string emit_gemul_cfg(const std::string &name, const qb_gemul_plan &p, cons
     return o.str();
 }
 
+// Tag struct for the thread-per-output template (qb_fast_gemul_thread.cuh): any shape, both forms, transposes.
+std::string emit_gemul_thread_cfg(const std::string &name, const qb_gemul_plan &p, const GemulProg &g, int bits)
+{
+    std::ostringstream o;
+    unsigned nlev = 0;
+    while (((uint64_t)1 << nlev) < p.K) nlev++;                       // ceil(log2 K): levels 0 .. nlev-1 exist
+    o << "struct " << name << " {\n";
+    o << "  typedef " << (bits == 32 ? "int32_t" : "int64_t") << " I;\n";
+    o << "  typedef " << word_t(g.a_wb) << " WA; typedef " << word_t(g.b_wb) << " WB; typedef " << word_t(g.c_wb) << " WC;\n";
+    o << "  static constexpr unsigned M = " << p.M << ", N = " << p.N << ", K = " << p.K << ";\n";
+    o << "  static constexpr int NLEV = " << nlev << ", NFLUSH = " << g.tree.nflush << ", TOP_SLOT = " << g.tree.top_slot << ";\n";
+    o << "  static constexpr bool TRANS_A = " << (p.trans_a ? "true" : "false") << ", TRANS_B = " << (p.trans_b ? "true" : "false") << ";\n";
+    o << "  static constexpr __host__ __device__ qb::QStage mul() { return " << emit_qstage(g.mul) << "; }\n";
+    o << "  static constexpr __host__ __device__ qb::QStage out() { return " << emit_qstage(g.out) << "; }\n";
+    o << emit_levels("lvl", g.tree, nlev);
+    o << "  static constexpr __host__ __device__ qb::FlushStep flush(int i) {\n    constexpr qb::FlushStep t[" << (g.tree.nflush ? g.tree.nflush : 1) << "] = {\n";
+    for (unsigned i = 0; i < (g.tree.nflush ? g.tree.nflush : 1); i++) {
+        const FlushStep &f = g.tree.flush[i];
+        o << "      qb::FlushStep{" << (unsigned)f.kind << "," << (unsigned)f.slot << ",{0,0,0,0,0,0}," << emit_addstage(f.a) << "},\n";
+    }
+    o << "    };\n    return t[i];\n  }\n";
+    o << "};\n";
+    return o.str();
+}
+
 // Is fma(x, y, 1.5 * 2^(23+s)) an exact implementation of stage q on operands with these ranges?
 static bool fp_mul_ok(const QStage &q, const TVal &x, const TVal &y)
 {

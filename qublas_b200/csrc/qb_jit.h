@@ -20,6 +20,7 @@ struct JitKernel {
     void *func[2] = { nullptr, nullptr };   // CUfunction(s)
     unsigned threads = 0, smem = 0;
     int blocks_per_sm = 1, sms = 0;
+    unsigned outputs_per_unit = 0;          // > 0: thread-per-output kernel, grid = ceil(batch * outputs_per_unit / threads)
     std::string name, log;
     bool ok = false;
 };

@@ -489,9 +489,9 @@ extern "C" int qb200_gemul_plan_info(const qb_gemul_plan *plan, qb_plan_info *in
     const GemulProg &gp = ce->prog; const Analysis &an = ce->an; const FastGemul *f = ce->fast;
     qb_qdesc ct = plan->c; ct.word_bytes = 0;
     const bool tc = ce->tc;
-    const bool jit_built = ce->jit.built_here();
-    fill_info(info, an, ct, gp.c_wb, tc ? "k_i8gemm (tcgen05 kind::i8)" : (f ? f->name : (jit_built ? "k_gemul_tile<jit>" : "k_gemul_thread")), tc,
-              f != nullptr || jit_built);
+    const JitKernel *jk = ce->jit.built_here() ? ce->jit.k[JitSlots::here()].get() : nullptr;
+    fill_info(info, an, ct, gp.c_wb, tc ? "k_i8gemm (tcgen05 kind::i8)" : (f ? f->name : (jk ? jk->name.c_str() : "k_gemul_thread")), tc,
+              f != nullptr || jk != nullptr);
     return QB_OK;
 }
 
@@ -522,7 +522,7 @@ extern "C" int qb200_gemul_batched(const qb_gemul_plan *plan, const void *A, con
         }
         if (jk && sa == (int64_t)ea && sb == (int64_t)eb && sc == (int64_t)ec && !((uintptr_t)dA & 15) && !((uintptr_t)dB & 15) && !((uintptr_t)dC & 15)) {
             int e = jit_launch_gemul(*jk, dA, dB, dC, n, st);
-            if (e) return fail(QB_ECUDA, "k_gemul_tile<jit> launch failed (CUresult " + std::to_string(e) + ")");
+            if (e) return fail(QB_ECUDA, jk->name + " launch failed (CUresult " + std::to_string(e) + ")");
             return QB_OK;
         }
         GemulShape S = shape_of(plan->M, plan->N, plan->K, plan->trans_a, plan->trans_b, gp.a_wb, gp.b_wb, gp.c_wb, sa, sb, sc);

@@ -592,3 +592,40 @@ def test_two_devices_in_one_process():
             Cd = torch.empty(batch * M * N, dtype=torch.int32, device=dv)
             ops.Qgemul(Cd, torch.from_numpy(A).to(dv), torch.from_numpy(B).to(dv), plan, batch=batch)
             assert np.array_equal(Cd.cpu().numpy(), want), (d, M, N, K)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_jit_thread_kernel_odd_shapes_vs_oracle(seed):
+    """Shapes the register-tile template does not take (K not a power of two, M/N not multiples of 4, tiny instances,
+    mat-vec, transposed operands, the 64-bit register class, both tree forms) get the NVRTC-specialised
+    thread-per-output kernel: bit-exact against the oracle and against the runtime-descriptor kernel."""
+    rng = np.random.default_rng(9100 + seed)
+    shapes = [(48, 48, 48), (20, 12, 100), (16, 16, 16), (64, 1, 64), (3, 5, 7), (2, 2, 1), (33, 7, 65), (8, 8, 200)]
+    n_jit = 0
+    for (M, N, K) in shapes:
+        form = TREE_VECTOR if rng.random() < 0.5 else TREE_VARIADIC
+        ta, tb = bool(rng.random() < 0.3), bool(rng.random() < 0.3)
+        wide = rng.random() < 0.25
+        a = QType(int(rng.integers(3, 8)) + (14 if wide else 0), int(rng.integers(3, 9)), True, 5, 0)
+        b = QType(int(rng.integers(3, 8)) + (14 if wide else 0), int(rng.integers(3, 9)), True, 5, 0)
+        mul = QType(a.i + b.i - 1, max(a.f, b.f), True, int(rng.integers(0, 7)), int(rng.integers(0, 4)))
+        lv = _rand_levels(rng, mul, int(rng.choice([1, 3, 7])))
+        cc = QType(lv[-1].i, max(lv[-1].f - 1, 1 - lv[-1].i), True, int(rng.integers(0, 7)), int(rng.integers(0, 4)))
+        plan = gemul_plan(a, b, mul, cc, lv, M, N, K, trans_a=ta, trans_b=tb, form=form)
+        batch = 7
+        A = rand_words(rng, a, batch * M * K); B = rand_words(rng, b, batch * K * N)
+        tdt = torch.int32 if cc.word_bytes == 4 else torch.int64
+        Cd = torch.empty(batch * M * N, dtype=tdt, device="cuda")
+        try:
+            ops.Qgemul(Cd, dev(A), dev(B), plan, batch=batch)
+        except abi.QbError as e:
+            assert e.code == abi.QB_EDOMAIN
+            continue
+        want = oracle.gemul_batched(plan, A, B, batch)
+        assert np.array_equal(Cd.cpu().numpy(), want), (M, N, K, form, ta, tb, a, b, mul, lv, cc)
+        gen = torch.empty_like(Cd)
+        ops.Qgemul(gen, dev(A), dev(B), plan, batch=batch, flags=abi.QB_F_NO_SPECIALIZE)
+        assert torch.equal(Cd, gen)
+        if ops.plan_info_gemul(plan).kernel == b"k_gemul_thread<jit>":
+            n_jit += 1
+    assert n_jit >= 5
