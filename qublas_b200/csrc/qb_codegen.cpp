@@ -101,6 +101,53 @@ std::string emit_gemul_thread_cfg(const std::string &name, const qb_gemul_plan &
     return o.str();
 }
 
+static std::string emit_flush(const char *fn, const TreeProg &t)
+{
+    std::ostringstream o;
+    o << "  static constexpr __host__ __device__ qb::FlushStep " << fn << "(int i) {\n    constexpr qb::FlushStep t[" << (t.nflush ? t.nflush : 1) << "] = {\n";
+    for (unsigned i = 0; i < (t.nflush ? t.nflush : 1); i++) {
+        const FlushStep &f = t.flush[i];
+        o << "      qb::FlushStep{" << (unsigned)f.kind << "," << (unsigned)f.slot << ",{0,0,0,0,0,0}," << emit_addstage(f.a) << "},\n";
+    }
+    o << "    };\n    return t[i];\n  }\n";
+    return o.str();
+}
+
+static std::string emit_tfprog(const TfProg &t)
+{
+    return "qb::TfProg{" + emit_addstage(t.ab) + ",\n      " + emit_addstage(t.cd) + ",\n      " + emit_addstage(t.ba) + ",\n      " + emit_qstage(t.A) + ",\n      " +
+           emit_qstage(t.B) + ",\n      " + emit_qstage(t.C) + ",\n      " + emit_addstage(t.re) + ",\n      " + emit_addstage(t.im) + "}";
+}
+
+static std::string emit_bcmprog(const BcmProg &t)
+{
+    return "qb::BcmProg{" + emit_qstage(t.ac) + ",\n      " + emit_qstage(t.bd) + ",\n      " + emit_qstage(t.ad) + ",\n      " + emit_qstage(t.bc) + ",\n      " +
+           emit_addstage(t.re) + ",\n      " + emit_addstage(t.im) + "}";
+}
+
+// Tag struct for the complex thread-per-output template (qb_fast_gemul_thread.cuh): any product kind, shape, form.
+std::string emit_cgemul_thread_cfg(const std::string &name, const qb_cgemul_plan &p, const CGemulProg &g, int bits)
+{
+    std::ostringstream o;
+    unsigned nlev = 0;
+    while (((uint64_t)1 << nlev) < p.K) nlev++;
+    o << "struct " << name << " {\n";
+    o << "  typedef " << (bits == 32 ? "int32_t" : "int64_t") << " I;\n";
+    o << "  typedef " << word_t(g.a_wb) << " WA; typedef " << word_t(g.b_wb) << " WB; typedef " << word_t(g.c_wb) << " WC;\n";
+    o << "  static constexpr unsigned M = " << p.M << ", N = " << p.N << ", K = " << p.K << ";\n";
+    o << "  static constexpr int KIND = " << g.kind << ", NLEV = " << nlev << ", NFLUSH_RE = " << g.tree_re.nflush << ", NFLUSH_IM = " << g.tree_im.nflush
+      << ", TOP_RE = " << g.tree_re.top_slot << ", TOP_IM = " << g.tree_im.top_slot << ";\n";
+    o << "  static constexpr bool TRANS_A = " << (p.trans_a ? "true" : "false") << ", TRANS_B = " << (p.trans_b ? "true" : "false") << ";\n";
+    o << "  static constexpr __host__ __device__ qb::TfProg tf() { return " << emit_tfprog(g.tf) << "; }\n";
+    o << "  static constexpr __host__ __device__ qb::BcmProg bcm() { return " << emit_bcmprog(g.bcm) << "; }\n";
+    o << "  static constexpr __host__ __device__ qb::QStage out_re() { return " << emit_qstage(g.out_re) << "; }\n";
+    o << "  static constexpr __host__ __device__ qb::QStage out_im() { return " << emit_qstage(g.out_im) << "; }\n";
+    o << emit_levels("lvl_re", g.tree_re, nlev) << emit_levels("lvl_im", g.tree_im, nlev);
+    o << emit_flush("flush_re", g.tree_re) << emit_flush("flush_im", g.tree_im);
+    o << "};\n";
+    return o.str();
+}
+
 // Is fma(x, y, 1.5 * 2^(23+s)) an exact implementation of stage q on operands with these ranges?
 static bool fp_mul_ok(const QStage &q, const TVal &x, const TVal &y)
 {

@@ -577,7 +577,8 @@ extern "C" int qb200_cgemul_plan_info(const qb_cgemul_plan *plan, qb_plan_info *
     if (ce->an.status) return fail(ce->an.status, ce->an.err);
     const CGemulProg &gp = ce->prog; const Analysis &an = ce->an; const FastCGemul *f = ce->fast;
     qb_qdesc ct = plan->c_re; ct.word_bytes = 0;
-    fill_info(info, an, ct, gp.c_wb, f ? f->name : "k_cgemul_thread", 0, f != nullptr);
+    const JitKernel *jk = ce->jit.built_here() ? ce->jit.k[JitSlots::here()].get() : nullptr;
+    fill_info(info, an, ct, gp.c_wb, f ? f->name : (jk ? jk->name.c_str() : "k_cgemul_thread"), 0, f != nullptr || jk != nullptr);
     return QB_OK;
 }
 
@@ -607,9 +608,9 @@ extern "C" int qb200_cgemul_batched(const qb_cgemul_plan *plan, const void *A, c
     if (f) {
         rc = f->launch(dA, dB, dC, batch, cx.stream);
         if (rc) return fail(QB_ECUDA, std::string(f->name) + " launch failed: " + cudaGetErrorString((cudaError_t)rc));
-    } else if (jk) {
+    } else if (jk && !((uintptr_t)dA & 15) && !((uintptr_t)dB & 15) && !((uintptr_t)dC & 15)) {      // vector loads of {re, im} pairs
         int e = jit_launch_gemul(*jk, dA, dB, dC, batch, cx.stream);
-        if (e) return fail(QB_ECUDA, "k_cgemv_rows<jit> launch failed (CUresult " + std::to_string(e) + ")");
+        if (e) return fail(QB_ECUDA, jk->name + " launch failed (CUresult " + std::to_string(e) + ")");
     } else {
         GemulShape S = shape_of(plan->M, plan->N, plan->K, plan->trans_a, plan->trans_b, gp.a_wb, gp.b_wb, gp.c_wb,
                                 plan->stride_a, plan->stride_b, plan->stride_c);

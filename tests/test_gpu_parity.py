@@ -629,3 +629,52 @@ def test_jit_thread_kernel_odd_shapes_vs_oracle(seed):
         if ops.plan_info_gemul(plan).kernel == b"k_gemul_thread<jit>":
             n_jit += 1
     assert n_jit >= 5
+
+
+@pytest.mark.parametrize("kind", ["tf", "basic", "real_a", "real_b"])
+def test_jit_complex_thread_kernel_all_product_kinds(kind):
+    """Complex Qgemul outside the mat-vec template (all four product kinds, ragged shapes, both forms, transposes)
+    runs the NVRTC-specialised thread-per-output kernel: bit-exact against the oracle and the runtime-descriptor kernel."""
+    from qublas_b200.qtypes import resolve_bcm, resolve_rc
+    rng = np.random.default_rng({"tf": 1, "basic": 2, "real_a": 3, "real_b": 4}[kind] + 500)
+    n_jit = 0
+    for (M, N, K) in [(5, 3, 12), (8, 8, 40), (16, 2, 7), (4, 4, 64), (33, 1, 100), (2, 2, 1)]:
+        form = TREE_VECTOR if rng.random() < 0.5 else TREE_VARIADIC
+        ta, tb = bool(rng.random() < 0.3), bool(rng.random() < 0.3)
+        def rt(lo=2, hi=7):
+            return QType(int(rng.integers(lo, hi)), int(rng.integers(1, 8)), True, int(rng.integers(0, 7)), int(rng.integers(0, 4)))
+        ar, ai, br, bi = rt(), rt(), rt(), rt()
+        if kind == "tf":
+            tags = {k: rt(5, 12) for k in ("abT", "cdT", "abcT", "cdbT", "badT", "ABT", "BCT") if rng.random() < 0.8}
+            r = resolve_tf(ar, ai, br, bi, tags); leaf = (r["AB"], r["BC"]); args = (ar, ai, br, bi)
+        elif kind == "basic":
+            tags = {k: rt(5, 12) for k in ("acT", "bdT", "adT", "bcT", "acbdT", "adbcT") if rng.random() < 0.8}
+            r = resolve_bcm(ar, ai, br, bi, tags); leaf = (r["acbd"], r["adbc"]); args = (ar, ai, br, bi)
+        elif kind == "real_a":
+            tags = {"realT": rt(6, 12), "imagT": rt(6, 12)}
+            r = resolve_rc(True, ar, br, bi, tags); leaf = (r["ac"], r["ad"]); args = (ar, None, br, bi)
+        else:
+            tags = {"realT": rt(6, 12), "imagT": rt(6, 12)}
+            r = resolve_rc(False, br, ar, ai, tags); leaf = (r["ac"], r["bc"]); args = (ar, ai, br, None)
+        lre = _rand_levels(rng, leaf[0], 3); lim = _rand_levels(rng, leaf[1], 2)
+        plan = ops.make_cgemul_plan(*args, QType(10, 4, True, 4, 0), QType(9, 3, True, 2, 2), M, N, K, tf_tags=tags, add_re=lre, add_im=lim,
+                                    form=form, product=kind, trans_a=ta, trans_b=tb)
+        batch = 5
+        def words(re_t, im_t, n):
+            if im_t is None:
+                return rand_words(rng, re_t, n).astype(np.int32)
+            return np.stack([rand_words(rng, re_t, n), rand_words(rng, im_t, n)], axis=1).astype(np.int32).reshape(-1)
+        A = words(args[0], args[1], batch * M * K); B = words(args[2], args[3], batch * K * N)
+        try:
+            Cd = torch.empty(batch * M * N * 2, dtype=torch.int32, device="cuda")
+            ops.Qcgemul(Cd, dev(A), dev(B), plan, batch=batch)
+        except abi.QbError as e:
+            assert e.code == abi.QB_EDOMAIN
+            continue
+        want = oracle.cgemul_batched(plan, A, B, batch)
+        assert np.array_equal(Cd.cpu().numpy(), want), (kind, M, N, K, form, ta, tb)
+        gen = torch.empty_like(Cd)
+        ops.Qcgemul(gen, dev(A), dev(B), plan, batch=batch, flags=abi.QB_F_NO_SPECIALIZE)
+        assert torch.equal(Cd, gen)
+        n_jit += ops.plan_info_cgemul(plan).kernel == b"k_cgemul_thread<jit>"
+    assert n_jit >= 4
