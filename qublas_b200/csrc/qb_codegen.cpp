@@ -202,6 +202,22 @@ std::string emit_reduce_cfg(const std::string &name, const qb_reduce_plan &p, co
     return o.str();
 }
 
+// Tag struct for the any-length vector-form reduction (qb_fast_reduce.cuh, reduce_any_body): level and carry tables
+// over all ceil(log2 len) levels.
+std::string emit_reduce_any_cfg(const std::string &name, const qb_reduce_plan &p, const ReduceProg &r)
+{
+    std::ostringstream o;
+    unsigned nlev = 0;
+    while (((uint64_t)1 << nlev) < p.len) nlev++;
+    o << "struct " << name << " {\n  typedef int32_t I;\n  static constexpr int NLEVELS = " << nlev << ";\n";
+    o << emit_levels("lvl", r.tree, nlev);
+    o << "  static constexpr __host__ __device__ qb::QStage carry(int l) {\n    constexpr qb::QStage t[" << (nlev ? nlev : 1) << "] = {\n";
+    for (unsigned l = 0; l < (nlev ? nlev : 1); l++) o << "      " << emit_qstage(r.tree.carry[l]) << ",\n";
+    o << "    };\n    return t[l];\n  }\n";
+    o << "};\n";
+    return o.str();
+}
+
 std::string emit_plan_bytes(const void *plan, size_t n)
 {
     std::ostringstream o;

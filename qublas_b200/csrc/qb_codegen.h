@@ -15,6 +15,7 @@ std::string emit_addstage(const AddStage &a);
 std::string emit_gemul_cfg(const std::string &name, const qb_gemul_plan &p, const GemulProg &g);
 std::string emit_gemul_thread_cfg(const std::string &name, const qb_gemul_plan &p, const GemulProg &g, int arith_bits);
 std::string emit_reduce_cfg(const std::string &name, const qb_reduce_plan &p, const ReduceProg &r);
+std::string emit_reduce_any_cfg(const std::string &name, const qb_reduce_plan &p, const ReduceProg &r);
 std::string emit_cgemul_cfg(const std::string &name, const qb_cgemul_plan &p, const CGemulProg &g);
 std::string emit_cgemul_thread_cfg(const std::string &name, const qb_cgemul_plan &p, const CGemulProg &g, int arith_bits);
 std::string emit_plan_bytes(const void *plan, size_t n);

@@ -83,6 +83,124 @@ k_reduce_ct(const int32_t *__restrict__ x, int32_t *__restrict__ out, uint64_t t
     reduce_ct_body<Cfg, LEV0, PW>(x, out, total_chunks);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Any length (vector form): the same lane / warp / chunk decomposition, one warp per chunk of 2^PW leaves.  Chunks
+// that are complete take the path above; the last chunk of a vector whose length is not a multiple of 2^PW tracks
+// which nodes exist and, where a right-hand partner is missing, converts the leftover into the level's type exactly
+// as the reference carries it upward (QuBLAS.h:4977-4980).  RMAX = number of levels this pass may apply (PW, or
+// fewer in the final pass, where the tree ends at ceil(log2 n)).
+// ---------------------------------------------------------------------------------------------------------------
+template <class Cfg, int LEV0, int RMAX, int R, typename I>
+QB_DEV void comb_ct(I &lv, bool &lp, I rv, bool rp)
+{
+    if constexpr (R < RMAX) {
+        if (!lp) return;
+        if (rp) { constexpr AddStage s = Cfg::lvl(LEV0 + R); lv = merge_apply<I, true>(lv, rv, s); }
+        else    { constexpr QStage c = Cfg::carry(LEV0 + R); lv = conv_apply<I, true>(lv, c); }
+    }
+}
+
+template <class Cfg, int LEV0, int RMAX, int S, typename I>
+QB_DEV void comb_shfl_ct(I &cur, bool &cp, int lane)
+{
+    const I ov = shfl_xor_ct<I>(cur, 1 << S);
+    const bool op = __shfl_xor_sync(0xffffffffu, (int)cp, 1 << S) != 0;
+    const bool upper = (lane >> S) & 1;
+    I lv = upper ? ov : cur, rv = upper ? cur : ov;
+    bool lp = upper ? op : cp, rp = upper ? cp : op;
+    comb_ct<Cfg, LEV0, RMAX, 3 + S, I>(lv, lp, rv, rp);
+    cur = lv; cp = lp;
+}
+
+template <class Cfg, int LEV0, int RMAX, int L, int NTOP, typename I>
+QB_DEV void pstack_push(I (&st)[NTOP + 1], bool (&sp)[NTOP + 1], uint32_t j, I cur, bool cp)
+{
+    if constexpr (L >= NTOP) {
+        st[L] = cur; sp[L] = cp;
+    } else {
+        if ((j >> L) & 1) {
+            I lv = st[L]; bool lp = sp[L];
+            comb_ct<Cfg, LEV0, RMAX, 8 + L, I>(lv, lp, cur, cp);
+            pstack_push<Cfg, LEV0, RMAX, L + 1, NTOP, I>(st, sp, j, lv, lp);
+        } else {
+            st[L] = cur; sp[L] = cp;
+        }
+    }
+}
+
+// x: batch vectors of n_in words; out: ceil(n_in / 2^PW) nodes per vector.
+template <class Cfg, int LEV0, int PW, int RMAX>
+QB_DEV void reduce_any_body(const int32_t *__restrict__ x, int32_t *__restrict__ out, uint64_t n_in, uint64_t batch, int vec_ok)
+{
+    typedef typename Cfg::I I;
+    constexpr int NSUB = 1 << (PW - 8), NTOP = PW - 8, U = NSUB < 4 ? NSUB : 4;
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t per_vec = (n_in + ((uint64_t)1 << PW) - 1) >> PW;
+    if (warp >= batch * per_vec) return;
+    const uint64_t b = warp / per_vec, c = warp - b * per_vec;
+    const int32_t *xv = x + b * n_in;
+    const uint64_t e_begin = c << PW;
+    const uint64_t e_end = (e_begin + ((uint64_t)1 << PW)) < n_in ? e_begin + ((uint64_t)1 << PW) : n_in;
+    I result = 0;
+    if (RMAX >= PW && e_end - e_begin == ((uint64_t)1 << PW)) {
+        if constexpr (RMAX >= PW) {
+            constexpr AddStage l0 = Cfg::lvl(LEV0), l1 = Cfg::lvl(LEV0 + 1), l2 = Cfg::lvl(LEV0 + 2);
+            I st[NTOP > 0 ? NTOP : 1];
+#pragma unroll 1
+            for (int j0 = 0; j0 < NSUB; j0 += U) {
+                I v[U][8];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int32_t *p = xv + e_begin + (uint64_t)(j0 + u) * 256 + lane * 8;
+                    if (vec_ok) {
+                        const int4 q0 = __ldcs((const int4 *)p), q1 = __ldcs((const int4 *)p + 1);
+                        v[u][0] = q0.x; v[u][1] = q0.y; v[u][2] = q0.z; v[u][3] = q0.w; v[u][4] = q1.x; v[u][5] = q1.y; v[u][6] = q1.z; v[u][7] = q1.w;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) v[u][i] = __ldcs(p + i);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    I a0 = merge_apply<I, true>(v[u][0], v[u][1], l0), a1 = merge_apply<I, true>(v[u][2], v[u][3], l0);
+                    I a2 = merge_apply<I, true>(v[u][4], v[u][5], l0), a3 = merge_apply<I, true>(v[u][6], v[u][7], l0);
+                    I cur = merge_apply<I, true>(merge_apply<I, true>(a0, a1, l1), merge_apply<I, true>(a2, a3, l1), l2);
+                    { constexpr AddStage s = Cfg::lvl(LEV0 + 3); cur = merge_apply<I, true>(cur, shfl_xor_ct<I>(cur, 1), s); }
+                    { constexpr AddStage s = Cfg::lvl(LEV0 + 4); cur = merge_apply<I, true>(cur, shfl_xor_ct<I>(cur, 2), s); }
+                    { constexpr AddStage s = Cfg::lvl(LEV0 + 5); cur = merge_apply<I, true>(cur, shfl_xor_ct<I>(cur, 4), s); }
+                    { constexpr AddStage s = Cfg::lvl(LEV0 + 6); cur = merge_apply<I, true>(cur, shfl_xor_ct<I>(cur, 8), s); }
+                    { constexpr AddStage s = Cfg::lvl(LEV0 + 7); cur = merge_apply<I, true>(cur, shfl_xor_ct<I>(cur, 16), s); }
+                    rstack_push<Cfg, LEV0 + 8, 0, NTOP, I>(st, (uint32_t)(j0 + u), cur, result);
+                }
+            }
+        }
+    } else {
+        I st[NTOP + 1]; bool sp[NTOP + 1];
+#pragma unroll 1
+        for (uint32_t j = 0; j < (uint32_t)NSUB; j++) {
+            const uint64_t e0 = e_begin + (uint64_t)j * 256 + lane * 8;
+            I v[8]; bool p[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) { p[i] = e0 + i < e_end; v[i] = p[i] ? (I)__ldcs(xv + e0 + i) : (I)0; }
+#pragma unroll
+            for (int i = 0; i < 4; i++) comb_ct<Cfg, LEV0, RMAX, 0, I>(v[2 * i], p[2 * i], v[2 * i + 1], p[2 * i + 1]);
+            comb_ct<Cfg, LEV0, RMAX, 1, I>(v[0], p[0], v[2], p[2]);
+            comb_ct<Cfg, LEV0, RMAX, 1, I>(v[4], p[4], v[6], p[6]);
+            comb_ct<Cfg, LEV0, RMAX, 2, I>(v[0], p[0], v[4], p[4]);
+            I cur = v[0]; bool cp = p[0];
+            comb_shfl_ct<Cfg, LEV0, RMAX, 0, I>(cur, cp, lane);
+            comb_shfl_ct<Cfg, LEV0, RMAX, 1, I>(cur, cp, lane);
+            comb_shfl_ct<Cfg, LEV0, RMAX, 2, I>(cur, cp, lane);
+            comb_shfl_ct<Cfg, LEV0, RMAX, 3, I>(cur, cp, lane);
+            comb_shfl_ct<Cfg, LEV0, RMAX, 4, I>(cur, cp, lane);
+            pstack_push<Cfg, LEV0, RMAX, 0, NTOP, I>(st, sp, j, cur, cp);
+        }
+        result = st[NTOP];
+    }
+    if (lane == 0) out[warp] = (int32_t)result;
+}
+
 #ifndef QB_JIT
 // Two chained passes for len = 2^LOGN (LOGN in [16, 24]): pass 1 PW1 = 12, pass 2 covers the rest.
 template <class Cfg>

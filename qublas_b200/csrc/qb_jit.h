@@ -17,7 +17,9 @@ namespace qb {
 
 struct JitKernel {
     void *module = nullptr;        // CUmodule
-    void *func[2] = { nullptr, nullptr };   // CUfunction(s)
+    void *func[4] = { nullptr, nullptr, nullptr, nullptr };   // CUfunction(s)
+    int npass = 0;                                             // > 0: any-length reduction, one entry point per pass
+    struct { uint64_t n_in, n_out; } pass[4] = {};
     unsigned threads = 0, smem = 0;
     int blocks_per_sm = 1, sms = 0;
     unsigned outputs_per_unit = 0;          // > 0: thread-per-output kernel, grid = ceil(batch * outputs_per_unit / threads)
@@ -36,5 +38,7 @@ int jit_check_gemul(const qb_gemul_plan &p, const GemulProg &g, int arith_bits, 
 // launches; return 0 or a CUresult / cudaError code
 int jit_launch_gemul(const JitKernel &k, const void *A, const void *B, void *C, uint64_t batch, cudaStream_t s);
 int jit_launch_reduce(const JitKernel &k, unsigned logn, const void *x, void *out, void *scratch, uint64_t batch, cudaStream_t s);
+// any-length variant: scratch must hold 2 * batch * pass[0].n_out words (two ping-pong halves)
+int jit_launch_reduce_any(const JitKernel &k, const void *x, void *out, void *scratch, uint64_t batch, cudaStream_t s);
 
 }  // namespace qb

@@ -342,13 +342,24 @@ static const char *reduce_kernel_name(const qb_reduce_plan *p)
     return "k_reduce_thread";
 }
 
-extern "C" int qb200_reduce_plan_info(const qb_reduce_plan *plan, qb_plan_info *info)
+// With a power-of-two length no level ever has an odd leftover, so the variadic form (QuBLAS.h:4936-4949) and the vector
+// form (:4966-4980) are the same computation: run it on the vector-form kernels.
+static qb_reduce_plan canonical_reduce(const qb_reduce_plan &p)
 {
-    if (!plan || !info) return fail(QB_EINVAL, "null argument");
+    qb_reduce_plan q = p;
+    if (q.tree_form == QB_TREE_VARIADIC && q.len && !(q.len & (q.len - 1))) q.tree_form = QB_TREE_VECTOR;
+    return q;
+}
+
+extern "C" int qb200_reduce_plan_info(const qb_reduce_plan *plan_in, qb_plan_info *info)
+{
+    if (!plan_in || !info) return fail(QB_EINVAL, "null argument");
+    const qb_reduce_plan canon = canonical_reduce(*plan_in), *plan = &canon;
     auto ce = get_reduce(*plan);
     if (ce->an.status) return fail(ce->an.status, ce->an.err);
     const ReduceProg &rp = ce->prog; const Analysis &an = ce->an; const FastReduce *fr = ce->fast;
-    fill_info(info, an, rp.out.t, rp.out_wb, fr ? fr->name : reduce_kernel_name(plan), 0, fr != nullptr);
+    const JitKernel *jk = ce->jit.built_here() ? ce->jit.k[JitSlots::here()].get() : nullptr;
+    fill_info(info, an, rp.out.t, rp.out_wb, fr ? fr->name : (jk ? jk->name.c_str() : reduce_kernel_name(plan)), 0, fr != nullptr || jk != nullptr);
     return QB_OK;
 }
 
@@ -420,15 +431,17 @@ static int run_reduce(const qb_reduce_plan *plan, const ReduceProg &rp, const vo
     }
 }
 
-extern "C" int qb200_reduce_batched(const qb_reduce_plan *plan, const void *x, void *out, void *partials,
+extern "C" int qb200_reduce_batched(const qb_reduce_plan *plan_in, const void *x, void *out, void *partials,
                                     uint32_t partial_level, uint64_t batch, const qb_exec *exec)
 {
-    if (!plan || !x || !out) return fail(QB_EINVAL, "null argument");
+    if (!plan_in || !x || !out) return fail(QB_EINVAL, "null argument");
+    if (plan_in->tree_form > 1) return fail(QB_EINVAL, "bad tree_form");
+    const qb_reduce_plan canon = canonical_reduce(*plan_in), *plan = &canon;
     auto ce = get_reduce(*plan);
     if (ce->an.status) return fail(ce->an.status, ce->an.err);
     const ReduceProg &rp = ce->prog; const Analysis &an = ce->an;
     if (partials) {
-        if (plan->tree_form != QB_TREE_VECTOR) return fail(QB_EINVAL, "partials are defined for the vector form only");
+        if (plan_in->tree_form != QB_TREE_VECTOR) return fail(QB_EINVAL, "partials are defined for the vector form only");
         if (partial_level != 0 && partial_level < 8) return fail(QB_EINVAL, "partial_level must be 0 or >= 8");
         if (partial_level > ceil_log2(plan->len)) return fail(QB_EINVAL, "partial_level above the root");
     }
@@ -449,6 +462,11 @@ extern "C" int qb200_reduce_batched(const qb_reduce_plan *plan, const void *x, v
         if ((rc = cx.alloc(&scratch, batch * 4096 * sizeof(int32_t)))) return rc;
         int e = fr->launch(dx, dout, scratch, batch, cx.stream);
         rc = e ? fail(QB_ECUDA, std::string(fr->name) + " launch failed: " + cudaGetErrorString((cudaError_t)e)) : QB_OK;
+    } else if (jk && jk->npass > 0) {
+        void *scratch = nullptr;
+        if (jk->npass > 1 && (rc = cx.alloc(&scratch, 2 * batch * jk->pass[0].n_out * sizeof(int32_t)))) return rc;
+        int e = jit_launch_reduce_any(*jk, dx, dout, scratch, batch, cx.stream);
+        rc = e ? fail(QB_ECUDA, "k_reduce_any<jit> launch failed (CUresult " + std::to_string(e) + ")") : QB_OK;
     } else if (jk) {
         void *scratch;
         if ((rc = cx.alloc(&scratch, batch * 4096 * sizeof(int32_t)))) return rc;

@@ -678,3 +678,38 @@ def test_jit_complex_thread_kernel_all_product_kinds(kind):
         assert torch.equal(Cd, gen)
         n_jit += ops.plan_info_cgemul(plan).kernel == b"k_cgemul_thread<jit>"
     assert n_jit >= 4
+
+
+@pytest.mark.parametrize("seed", range(2))
+def test_jit_any_length_reduce_vs_oracle(seed):
+    """Vector-form Qreduce at lengths that are not 2^16..2^24 powers of two: the NVRTC-specialised any-length kernel
+    (complete chunks on the fast path, the ragged last chunk with presence tracking and carry conversions) against the
+    oracle and the runtime-descriptor kernels; power-of-two variadic plans are routed to the same kernels."""
+    rng = np.random.default_rng(700 + seed)
+    n_jit = 0
+    for n in (64, 65, 100, 255, 256, 257, 1000, 4095, 4096, 4097, 65535, 100000, (1 << 20) + 1, 3 << 18):
+        elem = QType(int(rng.integers(4, 9)), int(rng.integers(3, 9)), True, int(rng.integers(0, 7)), int(rng.integers(0, 4)))
+        lv = _rand_levels(rng, elem, int(rng.choice([2, 6, 20])))
+        batch = 3 if n < 200000 else 2
+        x = rand_words(rng, elem, batch * n).astype(np.int32)
+        plan = reduce_plan(elem, lv, n)
+        try:
+            out, _ = ops.Qreduce(dev(x), elem, lv, length=n, batch=batch)
+        except abi.QbError as e:
+            assert e.code == abi.QB_EDOMAIN
+            continue
+        want, _ = oracle.reduce_batched(plan, x, batch)
+        assert np.array_equal(out.cpu().numpy(), want), (n, elem, lv)
+        gen, _ = ops.Qreduce(dev(x), elem, lv, length=n, batch=batch, flags=abi.QB_F_NO_SPECIALIZE)
+        assert torch.equal(out, gen)
+        if out.dtype == torch.int32 and ops.plan_info_reduce(plan).arith_bits == 32:
+            assert ops.plan_info_reduce(plan).kernel == b"k_reduce_any<jit>", n
+            n_jit += 1
+    assert n_jit >= 8
+    # power of two, variadic form == vector form
+    elem = QType(8, 8); lv = [QType(9 + l, 8 - l, True, 0, 0) for l in range(8)]
+    n = 1 << 12
+    x = rand_words(rng, elem, 2 * n).astype(np.int32)
+    out, _ = ops.Qreduce(dev(x), elem, lv, length=n, batch=2, form=TREE_VARIADIC)
+    want, _ = oracle.reduce_batched(reduce_plan(elem, lv, n, form=TREE_VARIADIC), x, 2)
+    assert np.array_equal(out.cpu().numpy(), want)
