@@ -1,5 +1,6 @@
 #include "qb_codegen.h"
 #include <cstdio>
+#include <cstring>
 #include <sstream>
 
 namespace qb {
@@ -214,6 +215,24 @@ std::string emit_reduce_any_cfg(const std::string &name, const qb_reduce_plan &p
     o << "  static constexpr __host__ __device__ qb::QStage carry(int l) {\n    constexpr qb::QStage t[" << (nlev ? nlev : 1) << "] = {\n";
     for (unsigned l = 0; l < (nlev ? nlev : 1); l++) o << "      " << emit_qstage(r.tree.carry[l]) << ",\n";
     o << "    };\n    return t[l];\n  }\n";
+    o << "};\n";
+    return o.str();
+}
+
+// Tag struct for the element-wise templates (qb_fast_ew.cuh).  kind >= 0: complex product of that kind (uses tf / bcm);
+// kind < 0: real element-wise op `op` (0 mul, 1 add, 2 sub, 3 convert) with `stage`.
+std::string emit_ew_cfg(const std::string &name, int kind, const TfProg *tf, const BcmProg *bcm, int op, const AddStage *stage, int xw, int yw, int ow, int bits)
+{
+    std::ostringstream o;
+    TfProg ztf; BcmProg zb; AddStage zs;
+    memset(&ztf, 0, sizeof(ztf)); memset(&zb, 0, sizeof(zb)); memset(&zs, 0, sizeof(zs));
+    o << "struct " << name << " {\n";
+    o << "  typedef " << (bits == 32 ? "int32_t" : "int64_t") << " I;\n";
+    o << "  typedef " << word_t(xw) << " WX; typedef " << word_t(yw) << " WY; typedef " << word_t(ow) << " WO;\n";
+    o << "  static constexpr int KIND = " << kind << ", OP = " << op << ";\n";
+    o << "  static constexpr __host__ __device__ qb::TfProg tf() { return " << emit_tfprog(tf ? *tf : ztf) << "; }\n";
+    o << "  static constexpr __host__ __device__ qb::BcmProg bcm() { return " << emit_bcmprog(bcm ? *bcm : zb) << "; }\n";
+    o << "  static constexpr __host__ __device__ qb::AddStage stage() { return " << emit_addstage(stage ? *stage : zs) << "; }\n";
     o << "};\n";
     return o.str();
 }

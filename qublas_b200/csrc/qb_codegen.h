@@ -18,6 +18,8 @@ std::string emit_reduce_cfg(const std::string &name, const qb_reduce_plan &p, co
 std::string emit_reduce_any_cfg(const std::string &name, const qb_reduce_plan &p, const ReduceProg &r);
 std::string emit_cgemul_cfg(const std::string &name, const qb_cgemul_plan &p, const CGemulProg &g);
 std::string emit_cgemul_thread_cfg(const std::string &name, const qb_cgemul_plan &p, const CGemulProg &g, int arith_bits);
+std::string emit_ew_cfg(const std::string &name, int kind, const TfProg *tf, const BcmProg *bcm, int op, const AddStage *stage, int xw, int yw, int ow,
+                        int arith_bits);
 std::string emit_plan_bytes(const void *plan, size_t n);
 
 }  // namespace qb

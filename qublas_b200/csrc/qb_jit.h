@@ -33,6 +33,10 @@ std::shared_ptr<JitKernel> jit_gemul(const qb_gemul_plan &p, const GemulProg &g,
 std::shared_ptr<JitKernel> jit_cgemul(const qb_cgemul_plan &p, const CGemulProg &g, int arith_bits);
 std::shared_ptr<JitKernel> jit_reduce(const qb_reduce_plan &p, const ReduceProg &r, int arith_bits);
 
+// element-wise templates (qb_fast_ew.cuh): kind >= 0 complex product (tf / bcm), kind < 0 real op (0 mul, 1 add, 2 sub, 3 convert)
+std::shared_ptr<JitKernel> jit_ew(int kind, const TfProg *tf, const BcmProg *bcm, int op, const AddStage *stage, int xw, int yw, int ow, int arith_bits);
+int jit_launch_ew(const JitKernel &k, const void *x, const void *y, void *out, uint64_t n, cudaStream_t s);
+
 int jit_check_gemul(const qb_gemul_plan &p, const GemulProg &g, int arith_bits, std::string &log);
 
 // launches; return 0 or a CUresult / cudaError code

@@ -646,6 +646,20 @@ extern "C" int qb200_cgemul_batched(const qb_cgemul_plan *plan, const void *A, c
 // ---------------------------------------------------------------------------------------------
 // element-wise TFComplexMul, conversion, synthetic fill
 // ---------------------------------------------------------------------------------------------
+// The element-wise kernels do not depend on the length, so their specialised builds are cached on the plan with len = 0.
+struct EwC { JitSlots jit; };
+template <class Plan> static std::shared_ptr<EwC> ew_cache(Plan key)
+{
+    key.len = 0;
+    return cached<Plan, EwC>(key, [](EwC &) {});
+}
+static bool ew_jit_usable(const Ctx &cx, std::initializer_list<const void *> ptrs)
+{
+    if (cx.flags & QB_F_NO_SPECIALIZE) return false;
+    for (const void *p : ptrs) if ((uintptr_t)p & 15) return false;       // vector accesses of {re, im} pairs
+    return true;
+}
+
 extern "C" int qb200_tfcmul_batched(const qb_tfcmul_plan *plan, const void *x, const void *y, void *out, uint64_t batch,
                                     const qb_exec *exec)
 {
@@ -661,10 +675,19 @@ extern "C" int qb200_tfcmul_batched(const qb_tfcmul_plan *plan, const void *x, c
     const int ow = std::max(natural_word(re.t), natural_word(im.t));
     const void *dx, *dy; void *dout;
     if ((rc = cx.in(x, (real_x ? 1 : 2) * n * xw, &dx)) || (rc = cx.in(y, (real_y ? 1 : 2) * n * yw, &dy)) || (rc = cx.out(out, 2 * n * ow, &dout))) return rc;
-    if (arith_bits(an) == 32) { sanitize32(tf); sanitize32(bcm); }
-    if (arith_bits(an) == 32) k_tfcmul<int32_t><<<grid_for(n, 256), 256, 0, cx.stream>>>(dx, dy, dout, n, xw, yw, ow, (int)plan->product, tf, bcm);
-    else                      k_tfcmul<int64_t><<<grid_for(n, 256), 256, 0, cx.stream>>>(dx, dy, dout, n, xw, yw, ow, (int)plan->product, tf, bcm);
-    if ((rc = post_launch("k_tfcmul"))) return rc;
+    const int bits = arith_bits(an);
+    if (bits == 32) { sanitize32(tf); sanitize32(bcm); }
+    JitKernel *jk = nullptr;
+    if (ew_jit_usable(cx, { dx, dy, dout }))
+        jk = ew_cache(*plan)->jit.get([&] { return jit_ew((int)plan->product, &tf, &bcm, 0, nullptr, xw, yw, ow, bits); });
+    if (jk) {
+        int e = jit_launch_ew(*jk, dx, dy, dout, n, cx.stream);
+        if (e) return fail(QB_ECUDA, jk->name + " launch failed (CUresult " + std::to_string(e) + ")");
+    } else {
+        if (bits == 32) k_tfcmul<int32_t><<<grid_for(n, 256), 256, 0, cx.stream>>>(dx, dy, dout, n, xw, yw, ow, (int)plan->product, tf, bcm);
+        else            k_tfcmul<int64_t><<<grid_for(n, 256), 256, 0, cx.stream>>>(dx, dy, dout, n, xw, yw, ow, (int)plan->product, tf, bcm);
+        if ((rc = post_launch("k_tfcmul"))) return rc;
+    }
     if ((rc = cx.out_done(out, 2 * n * ow, dout))) return rc;
     return cx.finish();
 }
@@ -685,10 +708,21 @@ extern "C" int qb200_convert_batched(const qb_convert_plan *plan, const void *in
     const int iw = word_bytes(plan->from), ow = word_bytes(plan->to);
     const void *din; void *dout;
     if ((rc = cx.in(in, n * iw, &din)) || (rc = cx.out(out, n * ow, &dout))) return rc;
-    if (arith_bits(an) == 32) sanitize32_stage(q);
-    if (arith_bits(an) == 32) k_convert<int32_t><<<grid_for(n, 256), 256, 0, cx.stream>>>(din, dout, n, iw, ow, q);
-    else                      k_convert<int64_t><<<grid_for(n, 256), 256, 0, cx.stream>>>(din, dout, n, iw, ow, q);
-    if ((rc = post_launch("k_convert"))) return rc;
+    const int bits = arith_bits(an);
+    if (bits == 32) sanitize32_stage(q);
+    JitKernel *jk = nullptr;
+    if (ew_jit_usable(cx, { din, dout })) {
+        AddStage st; memset(&st, 0, sizeof(st)); st.q = q;
+        jk = ew_cache(*plan)->jit.get([&] { return jit_ew(-1, nullptr, nullptr, 3, &st, iw, iw, ow, bits); });
+    }
+    if (jk) {
+        int e = jit_launch_ew(*jk, din, din, dout, n, cx.stream);
+        if (e) return fail(QB_ECUDA, jk->name + " launch failed (CUresult " + std::to_string(e) + ")");
+    } else {
+        if (bits == 32) k_convert<int32_t><<<grid_for(n, 256), 256, 0, cx.stream>>>(din, dout, n, iw, ow, q);
+        else            k_convert<int64_t><<<grid_for(n, 256), 256, 0, cx.stream>>>(din, dout, n, iw, ow, q);
+        if ((rc = post_launch("k_convert"))) return rc;
+    }
     if ((rc = cx.out_done(out, n * ow, dout))) return rc;
     return cx.finish();
 }
@@ -929,9 +963,19 @@ extern "C" int qb200_elementwise_batched(const qb_ew_plan *plan, const void *a, 
     const int aw = word_bytes(plan->a), bw = word_bytes(plan->b), ow = word_bytes(plan->to);
     const void *da, *db; void *dout;
     if ((rc = cx.in(a, n * aw, &da)) || (rc = cx.in(b, n * bw, &db)) || (rc = cx.out(out, n * ow, &dout))) return rc;
-    if (arith_bits(an) == 32) { sanitize32_stage(st.q); k_elementwise<int32_t><<<grid_for(n, 256), 256, 0, cx.stream>>>(da, db, dout, n, aw, bw, ow, (int)plan->op, st); }
-    else k_elementwise<int64_t><<<grid_for(n, 256), 256, 0, cx.stream>>>(da, db, dout, n, aw, bw, ow, (int)plan->op, st);
-    if ((rc = post_launch("k_elementwise"))) return rc;
+    const int bits = arith_bits(an);
+    if (bits == 32) sanitize32_stage(st.q);
+    JitKernel *jk = nullptr;
+    if (ew_jit_usable(cx, { da, db, dout }))
+        jk = ew_cache(*plan)->jit.get([&] { return jit_ew(-1, nullptr, nullptr, (int)plan->op, &st, aw, bw, ow, bits); });
+    if (jk) {
+        int e = jit_launch_ew(*jk, da, db, dout, n, cx.stream);
+        if (e) return fail(QB_ECUDA, jk->name + " launch failed (CUresult " + std::to_string(e) + ")");
+    } else {
+        if (bits == 32) k_elementwise<int32_t><<<grid_for(n, 256), 256, 0, cx.stream>>>(da, db, dout, n, aw, bw, ow, (int)plan->op, st);
+        else            k_elementwise<int64_t><<<grid_for(n, 256), 256, 0, cx.stream>>>(da, db, dout, n, aw, bw, ow, (int)plan->op, st);
+        if ((rc = post_launch("k_elementwise"))) return rc;
+    }
     if ((rc = cx.out_done(out, n * ow, dout))) return rc;
     return cx.finish();
 }

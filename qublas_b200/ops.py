@@ -195,7 +195,7 @@ def Qcgemul(Cbuf, A, B, plan: abi.qb_cgemul_plan, batch: int = 1, flags: int = 0
     return Cbuf
 
 
-def tfcmul(x, y, x_re: QType, x_im: QType, y_re: QType, y_im: QType, tf_tags=None, batch: int = 1, product: str = "tf"):
+def tfcmul(x, y, x_re: QType, x_im: QType, y_re: QType, y_im: QType, tf_tags=None, batch: int = 1, product: str = "tf", flags: int = 0):
     """Element-wise Qmul<TFComplexMul<tags...>>(x, y) (or BasicComplexMul with product="basic") on complex vectors (AoS pairs);
     product="real_a" / "real_b": x resp. y is a REAL vector (one word per element) scaling the complex one."""
     n = (y if product == "real_a" else x)
@@ -220,7 +220,7 @@ def tfcmul(x, y, x_re: QType, x_im: QType, y_re: QType, y_im: QType, tf_tags=Non
         o_re, o_im = r["AB"], r["BC"]
     p.len = n // batch
     out = _new_like(x, 2 * n, max(o_re.word_bytes, o_im.word_bytes))
-    ex = _exec_for(x, y)
+    ex = _exec_for(x, y, flags=flags)
     abi.check(abi.load().qb200_tfcmul_batched(C.byref(p), _ptr(x), _ptr(y), _ptr(out), batch, C.byref(ex)))
     return out, (o_re, o_im)
 
@@ -234,23 +234,23 @@ def make_ew_plan(op: str, ta: QType, tb: QType, n: int, to=None) -> abi.qb_ew_pl
     return p
 
 
-def elementwise(op: str, a, b, ta: QType, tb: QType, to=None):
+def elementwise(op: str, a, b, ta: QType, tb: QType, to=None, flags: int = 0):
     """Element-wise Qmul / Qadd / Qsub<to>(a, b) of two real tensors on the GPU; returns (out, result type)."""
     n = a.numel() if _is_torch(a) else a.size
     p = make_ew_plan(op, ta, tb, n, to)
     rt = abi.qtype_of(p.to)
     out = _new_like(a, n, rt.word_bytes)
-    ex = _exec_for(a, b)
+    ex = _exec_for(a, b, flags=flags)
     abi.check(abi.load().qb200_elementwise_batched(C.byref(p), _ptr(a), _ptr(b), _ptr(out), 1, C.byref(ex)))
     return out, rt
 
 
-def convert(x, src: QType, dst: QType):
+def convert(x, src: QType, dst: QType, flags: int = 0):
     n = x.numel() if _is_torch(x) else x.size
     p = abi.qb_convert_plan()
     p.from_, p.to, p.len = abi.desc(src), abi.desc(dst), n
     out = _new_like(x, n, dst.word_bytes)
-    ex = _exec_for(x)
+    ex = _exec_for(x, flags=flags)
     abi.check(abi.load().qb200_convert_batched(C.byref(p), _ptr(x), _ptr(out), 1, C.byref(ex)))
     return out
 

@@ -713,3 +713,34 @@ def test_jit_any_length_reduce_vs_oracle(seed):
     out, _ = ops.Qreduce(dev(x), elem, lv, length=n, batch=2, form=TREE_VARIADIC)
     want, _ = oracle.reduce_batched(reduce_plan(elem, lv, n, form=TREE_VARIADIC), x, 2)
     assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_jit_elementwise_kernels_vs_runtime_descriptor_and_oracle():
+    """The NVRTC-specialised element-wise kernels (complex products of all four kinds, real Qmul/Qadd/Qsub, converting
+    assignment) on odd lengths (ragged tail of the 4-way unrolled loop), 32- and 64-bit register classes: identical to the
+    runtime-descriptor kernels, and to the oracle on a prefix."""
+    from qublas_b200.qtypes import resolve_bcm, resolve_rc
+    rng = np.random.default_rng(4242)
+    n = 100003
+    for wide in (False, True):
+        t = QType(7, 8) if not wide else QType(20, 10)
+        to = QType(10, 6, True, 4, 0) if not wide else QType(36, 9, True, 3, 2)
+        a = rand_words(rng, t, n).astype(np.int32); b = rand_words(rng, t, n).astype(np.int32)
+        for op in ("mul", "add", "sub"):
+            out, rt = ops.elementwise(op, dev(a), dev(b), t, t, to=to)
+            gen, _ = ops.elementwise(op, dev(a), dev(b), t, t, to=to, flags=abi.QB_F_NO_SPECIALIZE)
+            assert torch.equal(out, gen), (op, wide)
+            want = oracle.elementwise(ops.make_ew_plan(op, t, t, 257, to), a[:257], b[:257])
+            assert np.array_equal(out[:257].cpu().numpy(), want), (op, wide)
+        cv = ops.convert(dev(a), t, to)
+        assert torch.equal(cv, ops.convert(dev(a), t, to, flags=abi.QB_F_NO_SPECIALIZE))
+    c = QType(3, 12); P = QType(6, 12); S = QType(7, 12)
+    x = rand_words(rng, c, 2 * n).astype(np.int32); y = rand_words(rng, c, 2 * n).astype(np.int32); r1 = rand_words(rng, c, n).astype(np.int32)
+    tf = {"abT": QType(4, 12), "cdT": QType(4, 11), "abcT": P, "cdbT": P, "badT": P, "ABT": S, "BCT": S}
+    bc = {"acT": P, "bdT": QType(6, 11, True, 4, 1), "adT": P, "bcT": P, "acbdT": S, "adbcT": QType(7, 10, True, 0, 2)}
+    rc = {"realT": P, "imagT": QType(6, 10, True, 2, 0)}
+    for product, tags, xx, yy, ty in (("tf", tf, x, y, (c, c, c, c)), ("basic", bc, x, y, (c, c, c, c)), ("real_a", rc, r1, y, (c, None, c, c)),
+                                      ("real_b", rc, x, r1, (c, c, c, None))):
+        out, _ = ops.tfcmul(dev(xx), dev(yy), *ty, tags, product=product)
+        gen, _ = ops.tfcmul(dev(xx), dev(yy), *ty, tags, product=product, flags=abi.QB_F_NO_SPECIALIZE)
+        assert torch.equal(out, gen), product
