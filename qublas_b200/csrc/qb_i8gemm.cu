@@ -272,6 +272,178 @@ k_i8gemm_mc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
 }
 
 // ---------------------------------------------------------------------------------------------
+// Pair variant: the two CTAs of a cluster (one TPC) execute ONE tcgen05.mma.cta_group::2 of M = 256, N = 256.  Each CTA
+// stages only its own 128 rows of A and its own half of B (128 of the 256 columns), 32 KB per stage instead of 48, so six
+// stages fit and every operand byte is read from shared memory once per pair instead of once per CTA.  Rank 0 issues the
+// MMAs; both producers' TMA loads report to rank 0's `full` barrier (cta_group::2 form, peer bit cleared), the MMA
+// commits are multicast to both CTAs (slot release and accumulator-ready), and both epilogues hand the accumulator back
+// by arriving on rank 0's `tempty` barrier.  D rows 0..127 live in rank 0's TMEM, 128..255 in rank 1's.
+// ---------------------------------------------------------------------------------------------
+#ifndef QB_P2_STAGES
+#define QB_P2_STAGES 6
+#endif
+static constexpr int P2_STAGES = QB_P2_STAGES;
+static constexpr int P2_A_STAGE = BM * BK, P2_B_STAGE = (BN / 2) * BK;
+static constexpr int P2_STAGE_BYTES = P2_A_STAGE + P2_B_STAGE;
+static constexpr int P2_SMEM_BYTES = P2_STAGES * P2_STAGE_BYTES + 1024 + 256;
+
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, uint64_t *leader_bar, int c0, int c1)
+{
+    const uint32_t bar = s32(leader_bar) & 0xFEFFFFFFu;              // clear the peer bit: the bytes are counted on rank 0's barrier
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(s32(dst)), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(s32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void bar_arrive_rank0(uint64_t *b)
+{
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, 0;\n"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+        "}\n" ::"r"(s32(b)) : "memory");
+}
+__device__ __forceinline__ void bar_wait_cluster(uint64_t *b, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAITC:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONEC;\n"
+        "bra LAB_WAITC;\n"
+        "DONEC:\n"
+        "}\n" ::"r"(s32(b)), "r"(parity) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1)
+k_i8gemm_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, void *__restrict__ C,
+              const __grid_constant__ I8Params P, const __grid_constant__ QStage outq)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char *sA = smem, *sB = smem + P2_STAGES * P2_A_STAGE;
+    uint64_t *bars = (uint64_t *)(smem + P2_STAGES * P2_STAGE_BYTES);
+    uint64_t *full = bars, *empty = bars + P2_STAGES, *tfull = bars + 2 * P2_STAGES, *tempty = bars + 2 * P2_STAGES + 2;
+    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * P2_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t nkb = P.K / BK;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t worker = cluster_id_x(), n_workers = n_clusters_x();
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < P2_STAGES; s++) { bar_init(&full[s], 1); bar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; a++) { bar_init(&tfull[a], 1); bar_init(&tempty[a], 8); }       // 4 epilogue warps in each CTA
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const uint32_t rows = P.tiles_m / 2;                       // work item = a 256 x 256 tile pair
+    const uint32_t nwork = rows * P.tiles_n;
+    auto pair_coords = [&](uint32_t t, uint32_t &row, uint32_t &tn) {
+        const uint32_t per_group = P.group_m * P.tiles_n;
+        const uint32_t g = t / per_group, r = t - g * per_group;
+        const uint32_t gm = (rows - g * P.group_m) < P.group_m ? (rows - g * P.group_m) : P.group_m;
+        row = g * P.group_m + r % gm;
+        tn = r / gm;
+    };
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): my 128 rows of A, my 128 columns of B =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = worker; t < nwork; t += n_workers) {
+                uint32_t row, tn; pair_coords(t, row, tn);
+                for (uint32_t kb = 0; kb < nkb; kb++) {
+                    bar_wait(&empty[stage], phase ^ 1);                                   // released by the pair MMA's multicast commit
+                    if (rank == 0) bar_expect_tx(&full[stage], 2 * P2_STAGE_BYTES);       // both CTAs' bytes land on rank 0's barrier
+                    tma_load_2d_pair(sA + stage * P2_A_STAGE, &mapA, &full[stage], (int)(kb * BK), (int)((2 * row + rank) * BM));
+                    tma_load_2d_pair(sB + stage * P2_B_STAGE, &mapB, &full[stage], (int)(kb * BK), (int)(tn * BN + rank * (BN / 2)));
+                    if (++stage == P2_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread of rank 0 drives both tensor cores =====
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_i8(2 * BM, BN);
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (uint32_t t = worker; t < nwork; t += n_workers) {
+                bar_wait_cluster(&tempty[acc], acc_phase ^ 1);         // both epilogues have drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (uint32_t kb = 0; kb < nkb; kb++) {
+                    bar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_k_sw128(s32(sA + stage * P2_A_STAGE));
+                    const uint64_t db = umma_desc_k_sw128(s32(sB + stage * P2_B_STAGE));
+#pragma unroll
+                    for (uint32_t k = 0; k < BK / 32; k++)
+                        tc_mma_i8_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    tc_commit_pair(&empty[stage]);                     // slot free in both CTAs when these MMAs retire
+                    if (++stage == P2_STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit_pair(&tfull[acc]);                           // accumulator complete in both CTAs
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue warps 2..5 of both CTAs: my 128 rows of the pair =====
+        const uint32_t quad = warp & 3;
+        uint32_t acc = 0, acc_phase = 0;
+        const bool plain = outq.identity && outq.shift == 0;
+        for (uint32_t t = worker; t < nwork; t += n_workers) {
+            uint32_t prow, tn; pair_coords(t, prow, tn);
+            bar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint64_t row = (uint64_t)(2 * prow + rank) * BM + quad * 32 + lane;
+#pragma unroll 1
+            for (uint32_t c0 = 0; c0 < (uint32_t)BN; c0 += 32) {
+                uint32_t v[32];
+                tc_ld32(tmem_base + ((quad * 32) << 16) + acc * BN + c0, v);
+#pragma unroll
+                for (int c = 0; c < 32; c++) {
+                    const uint64_t col = (uint64_t)tn * BN + c0 + c;
+                    const int32_t q = plain ? (int32_t)v[c] : conv_apply<int32_t, false>((int32_t)v[c], outq);
+                    if (P.c_wb == 4) ((int32_t *)C)[col * P.M + row] = q;
+                    else             ((int64_t *)C)[col * P.M + row] = (int64_t)q;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) bar_arrive_rank0(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+}
+
+// ---------------------------------------------------------------------------------------------
 // pack: raw ABI words -> int8, K-major.  src is column-major R x Cn (R contiguous).
 //   straight : dst[c][r] = src[r + c*R]     (K is already the contiguous index)
 //   transpose: dst[r][c] = src[r + c*R]     (the contiguous index must become the row)
@@ -424,9 +596,10 @@ int i8gemm_run(const void *A, const void *B, void *C, uint32_t M, uint32_t N, ui
     case 4: pack_operand<int32_t>(B, Bp, b_r, b_c, b_tr, s); break;
     default: pack_operand<int64_t>(B, Bp, b_r, b_c, b_tr, s); break;
     }
-    static int variant = -1;                       // QB200_I8_VARIANT=0 forces the single-CTA kernel
-    if (variant < 0) { const char *e = getenv("QB200_I8_VARIANT"); variant = (e && e[0] == '0') ? 0 : 1; }
-    const bool mc = variant == 1 && (M / BM) % 2 == 0;
+    static int variant = -1;                       // QB200_I8_VARIANT: 0 single-CTA kernel, 1 multicast clusters, 2 pair MMA (cta_group::2)
+    if (variant < 0) { const char *e = getenv("QB200_I8_VARIANT"); variant = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2; }
+    const bool pair = variant == 2 && (M / BM) % 2 == 0;
+    const bool mc = (variant == 1 || pair) && (M / BM) % 2 == 0;
     CUtensorMap mapA, mapB;
     if (make_map(&mapA, Ap, M, K, BM) || make_map(&mapB, Bp, N, K, mc ? BN / 2 : BN)) { *err = "cuTensorMapEncodeTiled failed"; return -1; }
     int dev = 0, sms = 0;
@@ -434,7 +607,8 @@ int i8gemm_run(const void *A, const void *B, void *C, uint32_t M, uint32_t N, ui
     static bool attr_set[64] = { false };          // function attributes are per device
     if (!attr_set[dev & 63]) {
         if (cudaFuncSetAttribute(k_i8gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(k_i8gemm_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) { *err = "cannot raise dynamic smem"; return -1; }
+            cudaFuncSetAttribute(k_i8gemm_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(k_i8gemm_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES) != cudaSuccess) { *err = "cannot raise dynamic smem"; return -1; }
         attr_set[dev & 63] = true;
     }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -444,7 +618,8 @@ int i8gemm_run(const void *A, const void *B, void *C, uint32_t M, uint32_t N, ui
     if (mc) {
         P.group_m = 8;                                                     // 8 tile pairs = 16 m-tiles per group
         const uint32_t npairs = ntiles / 2, clusters = npairs < (uint32_t)(sms / 2) ? npairs : (uint32_t)(sms / 2);
-        k_i8gemm_mc<<<clusters * 2, I8_THREADS, SMEM_BYTES, s>>>(mapA, mapB, C, P, outq);
+        if (pair) k_i8gemm_pair<<<clusters * 2, I8_THREADS, P2_SMEM_BYTES, s>>>(mapA, mapB, C, P, outq);
+        else      k_i8gemm_mc<<<clusters * 2, I8_THREADS, SMEM_BYTES, s>>>(mapA, mapB, C, P, outq);
     } else {
         const unsigned grid = ntiles < (uint32_t)sms ? ntiles : (unsigned)sms;
         k_i8gemm<<<grid, I8_THREADS, SMEM_BYTES, s>>>(mapA, mapB, C, P, outq);
