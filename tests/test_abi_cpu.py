@@ -136,6 +136,15 @@ def test_jit_specialisation_compiles_without_a_device():
         plan = ops.make_gemul_plan(a, a, lv[-1], M, N, K, mul=mul, add=lv)
         rc = lib.qb200_jit_check_gemul(ctypes.byref(plan), log, 8192)
         assert rc == 0, log.value.decode()
-    # shapes the tile template cannot take are reported as "not applicable", not as errors
-    plan = ops.make_gemul_plan(QType(7, 8), QType(7, 8), QType(17, 4), 5, 7, 12, mul=QType(14, 8))
-    assert lib.qb200_jit_check_gemul(ctypes.byref(plan), log, 8192) == 1
+    # shapes the register-tile template cannot take (ragged M/N, K not a power of two, transposes, both tree forms, the
+    # 64-bit register class) compile through the thread-per-output template
+    from qublas_b200.qtypes import TREE_VARIADIC, TREE_VECTOR
+    for (M, N, K, form, ta, tb, wide) in [(5, 7, 12, TREE_VECTOR, False, False, False), (48, 48, 48, TREE_VARIADIC, True, False, False),
+                                          (64, 1, 100, TREE_VECTOR, False, True, False), (2, 2, 1, TREE_VECTOR, False, False, False),
+                                          (8, 8, 12, TREE_VARIADIC, False, False, True)]:
+        a = QType(20, 10) if wide else QType(7, 8)
+        mul = QType(40, 12, True, 4, 0) if wide else QType(14, 8, True, 4, 0)
+        lv = [QType(mul.i + 1 + l, max(mul.f - l, 2), True, int(rng.integers(0, 7)), int(rng.integers(0, 4))) for l in range(3)]
+        plan = ops.make_gemul_plan(a, a, lv[-1], M, N, K, mul=mul, add=lv, form=form, trans_a=ta, trans_b=tb)
+        rc = lib.qb200_jit_check_gemul(ctypes.byref(plan), log, 8192)
+        assert rc == 0, (M, N, K, log.value.decode())
