@@ -254,6 +254,10 @@ int qb200_measure_int_peak(double fma_share, double *tera_ops_per_s, const qb_ex
  * Returns 0 if a cubin was produced, 1 if the plan does not fit the specialised kernel template,
  * -1 if NVRTC is unavailable or compilation failed (message in `log`). */
 int qb200_jit_check_gemul(const qb_gemul_plan *plan, char *log, uint64_t log_cap);
+/* The same check for the other run-time specialised kernel templates (no device needed).
+ * what: 1 = qb_cgemul_plan, 2 = qb_reduce_plan, 3 = qb_tfcmul_plan, 4 = qb_ew_plan, 5 = qb_convert_plan.
+ * Returns 0 = cubin produced, 1 = no template applies to this plan, -1 = NVRTC failed (log filled), < -1 = plan error. */
+int qb200_jit_check(int what, const void *plan, char *log, uint64_t log_cap);
 
 /* Contiguous shard [first, first+count) of `total` units for `rank` of `world` (batch or M-panel). */
 int qb200_shard_range(uint64_t total, uint32_t world, uint32_t rank, uint64_t *first, uint64_t *count);

@@ -126,7 +126,7 @@ ABI_SYMBOLS = [
     "qb200_abi_version", "qb200_last_error", "qb200_device_count", "qb200_launch_count",
     "qb200_launch_count_reset", "qb200_reduce_plan_info", "qb200_gemul_plan_info", "qb200_cgemul_plan_info",
     "qb200_reduce_batched", "qb200_gemul_batched", "qb200_cgemul_batched", "qb200_tfcmul_batched",
-    "qb200_convert_batched", "qb200_elementwise_batched", "qb200_synth_fill", "qb200_shard_range", "qb200_measure_int_peak", "qb200_jit_check_gemul", "qb200_quantize_f64", "qb200_dequantize_f64", "qb200_error_stats",
+    "qb200_convert_batched", "qb200_elementwise_batched", "qb200_synth_fill", "qb200_shard_range", "qb200_measure_int_peak", "qb200_jit_check_gemul", "qb200_jit_check", "qb200_quantize_f64", "qb200_dequantize_f64", "qb200_error_stats",
 ]
 
 _LIB = None
@@ -167,6 +167,7 @@ def load() -> C.CDLL:
     L.qb200_dequantize_f64.argtypes = [C.POINTER(qb_qdesc), vp, vp, u64, C.POINTER(qb_exec)]
     L.qb200_error_stats.argtypes = [C.POINTER(qb_qdesc), vp, vp, u64, C.POINTER(qb_err_stats), C.POINTER(qb_exec)]
     L.qb200_jit_check_gemul.argtypes = [C.POINTER(qb_gemul_plan), C.c_char_p, u64]
+    L.qb200_jit_check.argtypes = [C.c_int, C.c_void_p, C.c_char_p, u64]
     L.qb200_measure_int_peak.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(qb_exec)]
     for name in ABI_SYMBOLS:
         getattr(L, name)

@@ -37,6 +37,10 @@ std::shared_ptr<JitKernel> jit_reduce(const qb_reduce_plan &p, const ReduceProg 
 std::shared_ptr<JitKernel> jit_ew(int kind, const TfProg *tf, const BcmProg *bcm, int op, const AddStage *stage, int xw, int yw, int ow, int arith_bits);
 int jit_launch_ew(const JitKernel &k, const void *x, const void *y, void *out, uint64_t n, cudaStream_t s);
 
+// compile-only mode for the calling thread: jit_* build the source and run NVRTC, nothing is loaded (no GPU needed)
+void jit_set_compile_only(bool on);
+int jit_compile_only_result(std::string &log);   // 1 = no template applied, 0 = cubin produced, -1 = NVRTC failed
+
 int jit_check_gemul(const qb_gemul_plan &p, const GemulProg &g, int arith_bits, std::string &log);
 
 // launches; return 0 or a CUresult / cudaError code

@@ -819,6 +819,63 @@ extern "C" int qb200_jit_check_gemul(const qb_gemul_plan *plan, char *log, uint6
     return rc;
 }
 
+// Same for the other run-time specialised templates.  what: 1 = qb_cgemul_plan, 2 = qb_reduce_plan, 3 = qb_tfcmul_plan,
+// 4 = qb_ew_plan, 5 = qb_convert_plan.  Returns 0 = cubin produced, 1 = no template applies, -1 = NVRTC failed, < -1 = plan error.
+extern "C" int qb200_jit_check(int what, const void *plan, char *log, uint64_t log_cap)
+{
+    if (!plan) return fail(QB_EINVAL, "null argument");
+    int rc = 1; std::string l;
+    auto run = [&](auto build) { jit_set_compile_only(true); build(); rc = jit_compile_only_result(l); jit_set_compile_only(false); };
+    if (what == 1) {
+        auto ce = get_cgemul(*(const qb_cgemul_plan *)plan);
+        if (ce->an.status) return fail(ce->an.status, ce->an.err);
+        run([&] { jit_cgemul(*(const qb_cgemul_plan *)plan, ce->prog, ce->bits); });
+    } else if (what == 2) {
+        const qb_reduce_plan canon = canonical_reduce(*(const qb_reduce_plan *)plan);
+        auto ce = get_reduce(canon);
+        if (ce->an.status) return fail(ce->an.status, ce->an.err);
+        run([&] { jit_reduce(canon, ce->prog, arith_bits(ce->an)); });
+    } else if (what == 3) {
+        const qb_tfcmul_plan &p = *(const qb_tfcmul_plan *)plan;
+        TfProg tf; BcmProg bcm; TVal re, im; Analysis an;
+        if (compile_tfcmul(p, &tf, &bcm, &re, &im, an)) return fail(an.status, an.err);
+        const bool real_x = p.product == QB_CPROD_REAL_A, real_y = p.product == QB_CPROD_REAL_B;
+        const int xw = real_x ? word_bytes(p.x_re) : std::max(word_bytes(p.x_re), word_bytes(p.x_im));
+        const int yw = real_y ? word_bytes(p.y_re) : std::max(word_bytes(p.y_re), word_bytes(p.y_im));
+        const int ow = std::max(natural_word(re.t), natural_word(im.t)), bits = arith_bits(an);
+        if (bits == 32) { sanitize32(tf); sanitize32(bcm); }
+        run([&] { jit_ew((int)p.product, &tf, &bcm, 0, nullptr, xw, yw, ow, bits); });
+    } else if (what == 4) {
+        const qb_ew_plan &p = *(const qb_ew_plan *)plan;
+        if (p.op > 2) return fail(QB_EINVAL, "bad element-wise op");
+        Analysis an;
+        if (!check_type(p.a, an, "a type") || !check_type(p.b, an, "b type") || !check_type(p.to, an, "result type")) return fail(an.status, an.err);
+        TVal ta = { p.a, type_range(p.a) }, tb = { p.b, type_range(p.b) }, o;
+        AddStage st; memset(&st, 0, sizeof(st));
+        if (p.op == QB_EW_MUL) st.q = make_mul(ta, tb, p.to, &o, an); else st = make_add(ta, tb, p.to, p.op == QB_EW_SUB, &o, an);
+        if (an.status) return fail(an.status, an.err);
+        const int bits = arith_bits(an);
+        if (bits == 32) sanitize32_stage(st.q);
+        run([&] { jit_ew(-1, nullptr, nullptr, (int)p.op, &st, word_bytes(p.a), word_bytes(p.b), word_bytes(p.to), bits); });
+    } else if (what == 5) {
+        const qb_convert_plan &p = *(const qb_convert_plan *)plan;
+        Analysis an;
+        if (!check_type(p.from, an, "from type") || !check_type(p.to, an, "to type")) return fail(an.status, an.err);
+        TVal o;
+        AddStage st; memset(&st, 0, sizeof(st));
+        st.q = make_stage(p.from.frac_bits, type_range(p.from), width(p.from), p.to, &o, an);
+        if (an.status) return fail(an.status, an.err);
+        an.max_reg_bits = std::max(an.max_reg_bits, width(p.from));
+        const int bits = arith_bits(an);
+        if (bits == 32) sanitize32_stage(st.q);
+        run([&] { jit_ew(-1, nullptr, nullptr, 3, &st, word_bytes(p.from), word_bytes(p.from), word_bytes(p.to), bits); });
+    } else {
+        return fail(QB_EINVAL, "unknown plan kind");
+    }
+    if (log && log_cap) snprintf(log, (size_t)log_cap, "%s", l.c_str());
+    return rc;
+}
+
 // ---------------------------------------------------------------------------------------------
 // double -> Qu, Qu -> double, on-device error statistics
 // ---------------------------------------------------------------------------------------------

@@ -148,3 +148,51 @@ def test_jit_specialisation_compiles_without_a_device():
         plan = ops.make_gemul_plan(a, a, lv[-1], M, N, K, mul=mul, add=lv, form=form, trans_a=ta, trans_b=tb)
         rc = lib.qb200_jit_check_gemul(ctypes.byref(plan), log, 8192)
         assert rc == 0, (M, N, K, log.value.decode())
+
+
+def test_every_jit_template_compiles_without_a_device():
+    """qb200_jit_check: the complex thread-per-output template (all four product kinds), the mat-vec rows template, both
+    Qreduce templates, and the element-wise templates (complex products, real ops, convert) go through codegen + NVRTC
+    on a machine without a GPU."""
+    import ctypes
+    from qublas_b200.qtypes import TREE_VARIADIC, TREE_VECTOR
+    lib = abi.load()
+    log = ctypes.create_string_buffer(16384)
+
+    def check(what, plan):
+        rc = lib.qb200_jit_check(what, ctypes.cast(ctypes.byref(plan), ctypes.c_void_p), log, 16384)
+        assert rc == 0, (what, rc, log.value.decode()[:2000])
+
+    t = QType(3, 12); P = QType(6, 12); S = QType(7, 12)
+    tf = {"abT": QType(4, 12), "cdT": QType(4, 11), "abcT": P, "cdbT": P, "badT": P, "ABT": S, "BCT": S}
+    bc = {"acT": P, "bdT": QType(6, 11, True, 4, 1), "adT": P, "bcT": P, "acbdT": S, "adbcT": QType(7, 10, True, 0, 2)}
+    rc_tags = {"realT": P, "imagT": QType(6, 10, True, 2, 0)}
+    lv = [QType(8 + l, 12 - l, True, 4, 0) for l in range(4)]
+    out = QType(12, 8)
+    # complex Qgemul: mat-vec rows template, then the thread template for every product kind
+    check(1, ops.make_cgemul_plan(t, t, t, t, out, out, 64, 1, 64, tf_tags=tf, add_re=lv))
+    for kind, tags, args in (("tf", tf, (t, t, t, t)), ("basic", bc, (t, t, t, t)), ("real_a", rc_tags, (t, None, t, t)), ("real_b", rc_tags, (t, t, t, None))):
+        check(1, ops.make_cgemul_plan(*args, out, out, 5, 3, 12, tf_tags=tags, add_re=lv, form=TREE_VECTOR, product=kind, trans_a=True))
+    # Qreduce: power-of-two two-pass template, any-length template, variadic power of two routed to the vector kernels
+    elem = QType(8, 8); rl = [QType(9 + l, 8 - l, True, 0, 0) for l in range(8)]
+    for n, form in ((1 << 16, TREE_VECTOR), (100000, TREE_VECTOR), (64, TREE_VECTOR), (4097, TREE_VECTOR), (1 << 12, TREE_VARIADIC)):
+        check(2, ops.make_reduce_plan(elem, rl, n, form=form))
+    # element-wise: complex products, real ops, converting assignment
+    for kind, tags, args in (("tf", tf, (t, t, t, t)), ("basic", bc, (t, t, t, t)), ("real_a", rc_tags, (t, None, t, t))):
+        p = abi.qb_tfcmul_plan()
+        p.x_re, p.x_im, p.y_re, p.y_im = (abi.desc(q if q is not None else t) for q in args)
+        if kind == "tf":
+            from qublas_b200.qtypes import resolve_tf
+            p.tf = abi.tfc_types(resolve_tf(t, t, t, t, tags))
+        elif kind == "basic":
+            from qublas_b200.qtypes import resolve_bcm
+            p.bcm = abi.bcm_types(resolve_bcm(t, t, t, t, tags)); p.product = abi.QB_CPROD_BASIC
+        else:
+            from qublas_b200.qtypes import resolve_rc
+            p.bcm = abi.bcm_types(resolve_rc(True, t, t, t, tags)); p.product = abi.QB_CPROD_REAL_A
+        p.len = 100
+        check(3, p)
+    for op in ("mul", "add", "sub"):
+        check(4, ops.make_ew_plan(op, QType(7, 8), QType(5, 6), 100, QType(10, 6, True, 4, 0)))
+    cp = abi.qb_convert_plan(); cp.from_, cp.to, cp.len = abi.desc(QType(20, 10)), abi.desc(QType(36, 9, True, 3, 2)), 10
+    check(5, cp)
