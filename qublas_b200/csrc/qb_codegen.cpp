@@ -188,6 +188,17 @@ std::string emit_cgemul_cfg(const std::string &name, const qb_cgemul_plan &p, co
         const bool fa = fp_mul_ok(g.tf.A, mid[0], c), fb = fp_mul_ok(g.tf.B, mid[1], b), fc = fp_mul_ok(g.tf.C, mid[2], d);
         o << "  static constexpr bool FP_A = " << (fa ? "true" : "false") << ", FP_B = " << (fb ? "true" : "false") << ", FP_C = " << (fc ? "true" : "false") << ";\n";
         o << "  static constexpr int SH_A = " << (fa ? (int)g.tf.A.shift : 1) << ", SH_B = " << (fb ? (int)g.tf.B.shift : 1) << ", SH_C = " << (fc ? (int)g.tf.C.shift : 1) << ";\n";
+        // The pre-adds a + b and b - a feed those products as floats.  When the stage is an exact add (no alignment,
+        // no rounding shift) whose only other effect is a SAT::TCPL clamp, and both operands are exact floats below 2^23,
+        // the add itself runs on the FP pipe (FADD is exact below 2^24, the clamp is min/max on floats) and one
+        // int->float conversion per product disappears.
+        auto fadd_ok = [](const AddStage &s, const TVal &x, const TVal &y) {
+            auto small = [](const Ival &r) { return r.lo >= -((i128)1 << 23) && r.hi <= ((i128)1 << 23); };
+            return !s.shl_a && !s.shl_b && s.q.shift == 0 && !s.q.wrap_bits && !s.q.wide && (s.q.of == SAT_TCPL || (!s.q.need_lo && !s.q.need_hi)) &&
+                   small(x.r) && small(y.r) && s.q.lo >= -(1LL << 24) && s.q.hi <= (1LL << 24);
+        };
+        o << "  static constexpr bool FADD_AB = " << (fa && fadd_ok(g.tf.ab, a, b) ? "true" : "false")
+          << ", FADD_BA = " << (fc && fadd_ok(g.tf.ba, b, a) ? "true" : "false") << ";\n";
     }
     o << "};\n";
     return o.str();

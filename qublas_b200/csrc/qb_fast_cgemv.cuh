@@ -16,6 +16,18 @@
 
 namespace qb {
 
+#ifndef QB_FADD
+#define QB_FADD 1
+#endif
+// x + y (or x - y) of two exact floats below 2^23 with the stage's SAT::TCPL clamp: exact, on the FP pipe
+QB_DEV float fadd_stage(float x, float y, const QStage &q, bool sub)
+{
+    float r = sub ? x - y : x + y;
+    if (q.need_hi) r = fminf(r, (float)q.hi);
+    if (q.need_lo) r = fmaxf(r, (float)q.lo);
+    return r;
+}
+
 template <class Cfg, int L, int NTOP, typename I>
 QB_DEV void cstack_push(I (&sr)[NTOP > 0 ? NTOP : 1], I (&si)[NTOP > 0 ? NTOP : 1], uint32_t c, I vr, I vi, I &rr, I &ri)
 {
@@ -69,15 +81,19 @@ QB_DEV void cgemv_rows_body(const int2 *__restrict__ H, const int2 *__restrict__
             for (int u = 0; u < 8; ++u) {
                 const int k = c * 8 + u;
                 const I a = h[u].x, b = h[u].y, cc = xc[k], d = xd[k], cd = xcd[k];
-                const I ab = add_apply<I, true>(a, b, tf.ab);            // :3524
-                const I ba = add_apply<I, true>(b, a, tf.ba);            // :3526 (default merger: baT is ignored upstream)
+                const float af = __int2float_rn((int)a), bf = __int2float_rn((int)b);     // exact; dead code unless an FP path uses them
+                float abf, baf;
+                if constexpr (Cfg::FADD_AB && QB_FADD) abf = fadd_stage(af, bf, tf.ab.q, false);          // :3524 on the FP pipe
+                else abf = __int2float_rn((int)add_apply<I, true>(a, b, tf.ab));
+                if constexpr (Cfg::FADD_BA && QB_FADD) baf = fadd_stage(bf, af, tf.ba.q, true);           // :3526 (default merger: baT is ignored upstream)
+                else baf = __int2float_rn((int)add_apply<I, true>(b, a, tf.ba));
                 I A, Bv, Cv;
-                if constexpr (Cfg::FP_A) A = (I)(fp_mul_apply<Cfg::SH_A, true>(__int2float_rn((int)ab), __int_as_float((int)cc), tf.A) - fp_kbits<Cfg::SH_A>());
-                else A = mul_apply<I, true>(ab, cc, tf.A);
-                if constexpr (Cfg::FP_B) Bv = (I)(fp_mul_apply<Cfg::SH_B, true>(__int_as_float((int)cd), __int2float_rn((int)b), tf.B) - fp_kbits<Cfg::SH_B>());
+                if constexpr (Cfg::FP_A) A = (I)(fp_mul_apply<Cfg::SH_A, true>(abf, __int_as_float((int)cc), tf.A) - fp_kbits<Cfg::SH_A>());
+                else A = mul_apply<I, true>(add_apply<I, true>(a, b, tf.ab), cc, tf.A);
+                if constexpr (Cfg::FP_B) Bv = (I)(fp_mul_apply<Cfg::SH_B, true>(__int_as_float((int)cd), bf, tf.B) - fp_kbits<Cfg::SH_B>());
                 else Bv = mul_apply<I, true>(cd, b, tf.B);
-                if constexpr (Cfg::FP_C) Cv = (I)(fp_mul_apply<Cfg::SH_C, true>(__int2float_rn((int)ba), __int_as_float((int)d), tf.C) - fp_kbits<Cfg::SH_C>());
-                else Cv = mul_apply<I, true>(ba, d, tf.C);
+                if constexpr (Cfg::FP_C) Cv = (I)(fp_mul_apply<Cfg::SH_C, true>(baf, __int_as_float((int)d), tf.C) - fp_kbits<Cfg::SH_C>());
+                else Cv = mul_apply<I, true>(add_apply<I, true>(b, a, tf.ba), d, tf.C);
                 pr[u] = add_apply<I, true>(A, Bv, tf.re);                // :3528
                 pi[u] = add_apply<I, true>(Bv, Cv, tf.im);               // :3529
             }
@@ -96,8 +112,20 @@ QB_DEV void cgemv_rows_body(const int2 *__restrict__ H, const int2 *__restrict__
     }
 }
 
+// Occupancy target: 1280 resident threads per SM (5 CTAs of 256 rows), i.e. at most 48 registers per thread.  The
+// kernel sits at the HBM / ALU balance point and the extra CTA of loads in flight is worth 7 % (config 4: 716 -> 773
+// G complex MAC/s, 0.88 -> 0.95 of the measured HBM bandwidth); found because NVRTC happened to allocate 47 registers
+// where nvcc took 52.
+#ifndef QB_CGEMV_THREADS_PER_SM
+#define QB_CGEMV_THREADS_PER_SM 1280
+#endif
+constexpr int cgemv_min_blocks(int rows)
+{
+    return QB_CGEMV_THREADS_PER_SM / rows < 1 ? 1 : (QB_CGEMV_THREADS_PER_SM / rows > 16 ? 16 : QB_CGEMV_THREADS_PER_SM / rows);
+}
+
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::M)
+__global__ void __launch_bounds__(Cfg::M, cgemv_min_blocks(Cfg::M))
 k_cgemv_rows(const int2 *__restrict__ H, const int2 *__restrict__ X, int2 *__restrict__ Y, uint64_t batch)
 {
     cgemv_rows_body<Cfg>(H, X, Y, batch);

@@ -302,7 +302,7 @@ static std::shared_ptr<CGemulC> get_cgemul(const qb_cgemul_plan &p)
         e.bits = arith_bits(e.an); e.fast = nullptr;
         if (!e.an.status) {
             if (e.bits == 32) { sanitize32(e.prog.tf); sanitize32(e.prog.bcm); sanitize32(e.prog.tree_re); sanitize32(e.prog.tree_im); sanitize32_stage(e.prog.out_re); sanitize32_stage(e.prog.out_im); }
-            e.fast = find_fast_cgemul(p, e.prog, e.bits);
+            e.fast = getenv("QB200_NO_AOT") ? nullptr : find_fast_cgemul(p, e.prog, e.bits);
         }
     });
 }
