@@ -124,7 +124,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_i8(int m, int n)
 }
 
 struct I8Params {
-    uint32_t M, N, K;             // multiples of BM, BN, BK
+    uint32_t M, N, K;             // M, N: real extents of C (leading dimension M, stores are guarded); K: padded to a multiple of BK
     uint32_t tiles_m, tiles_n;
     int32_t  c_wb;
     uint32_t group_m;             // rasterisation: group_m m-tiles share each B panel while it is hot in L2
@@ -241,8 +241,10 @@ __device__ __forceinline__ void i8gemm_body(const CUtensorMap &mapA, const CUten
                 for (int c = 0; c < 32; c++) {
                     const uint64_t col = (uint64_t)tn * BN + c0 + c;
                     const int32_t q = plain ? (int32_t)v[c] : conv_apply<int32_t, false>((int32_t)v[c], outq);   // converting assignment into C's type
-                    if (P.c_wb == 4) ((int32_t *)C)[col * P.M + row] = q;                // column-major: 32 lanes = 128 contiguous bytes
-                    else             ((int64_t *)C)[col * P.M + row] = (int64_t)q;
+                    if (row < P.M && col < P.N) {                                        // ragged shapes run on zero-padded operands
+                        if (P.c_wb == 4) ((int32_t *)C)[col * P.M + row] = q;            // column-major: 32 lanes = 128 contiguous bytes
+                        else             ((int64_t *)C)[col * P.M + row] = (int64_t)q;
+                    }
                 }
             }
             tc_fence_before();
@@ -427,8 +429,10 @@ k_i8gemm_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 for (int c = 0; c < 32; c++) {
                     const uint64_t col = (uint64_t)tn * BN + c0 + c;
                     const int32_t q = plain ? (int32_t)v[c] : conv_apply<int32_t, false>((int32_t)v[c], outq);
-                    if (P.c_wb == 4) ((int32_t *)C)[col * P.M + row] = q;
-                    else             ((int64_t *)C)[col * P.M + row] = (int64_t)q;
+                    if (row < P.M && col < P.N) {
+                        if (P.c_wb == 4) ((int32_t *)C)[col * P.M + row] = q;
+                        else             ((int64_t *)C)[col * P.M + row] = (int64_t)q;
+                    }
                 }
             }
             tc_fence_before();
@@ -515,6 +519,25 @@ k_pack_i8_transpose_w4(const int *__restrict__ src, uint32_t *__restrict__ dst, 
     }
 }
 
+// Ragged shapes: dst is the zero-padded rows_p x k_p int8 operand (k contiguous); src holds rows x k words, either with
+// k contiguous (transpose == 0: src[r * k + kk]) or with rows contiguous (transpose == 1: src[r + kk * rows]).
+template <typename W>
+__global__ void k_pack_i8_padded(const W *__restrict__ src, int8_t *__restrict__ dst, uint32_t rows, uint32_t k, uint32_t rows_p, uint32_t k_p, int transpose)
+{
+    __shared__ int8_t tile[32][33];
+    const uint32_t r0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+    if (!transpose) {
+        const uint32_t r = r0 + threadIdx.y, kk = k0 + threadIdx.x;
+        if (r < rows_p && kk < k_p) dst[(uint64_t)r * k_p + kk] = (r < rows && kk < k) ? (int8_t)src[(uint64_t)r * k + kk] : (int8_t)0;
+    } else {
+        const uint32_t rs = r0 + threadIdx.x, ks = k0 + threadIdx.y;                 // read with rows contiguous
+        tile[threadIdx.y][threadIdx.x] = (rs < rows && ks < k) ? (int8_t)src[(uint64_t)ks * rows + rs] : (int8_t)0;
+        __syncthreads();
+        const uint32_t r = r0 + threadIdx.y, kk = k0 + threadIdx.x;                  // write with k contiguous
+        if (r < rows_p && kk < k_p) dst[(uint64_t)r * k_p + kk] = tile[threadIdx.x][threadIdx.y];
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -545,7 +568,21 @@ static int make_map(CUtensorMap *m, const int8_t *base, uint64_t rows, uint64_t 
     return r == CUDA_SUCCESS ? 0 : -2;
 }
 
-bool i8gemm_shape_ok(uint32_t M, uint32_t N, uint32_t K) { return M % BM == 0 && N % BN == 0 && K % BK == 0 && M && N && K; }
+static uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
+void i8gemm_padded_dims(uint32_t M, uint32_t N, uint32_t K, uint32_t *Mp, uint32_t *Np, uint32_t *Kp)
+{
+    *Mp = round_up(M, BM); *Np = round_up(N, BN); *Kp = round_up(K, BK);
+}
+// Tile multiples always qualify; ragged shapes run on zero-padded operands when the problem is large enough to be worth
+// the tensor cores (>= 2^24 MACs) and the padding at most doubles the work.
+bool i8gemm_shape_ok(uint32_t M, uint32_t N, uint32_t K)
+{
+    if (!M || !N || !K || M > (1u << 20) || N > (1u << 20) || K > (1u << 20)) return false;
+    if (M % BM == 0 && N % BN == 0 && K % BK == 0) return true;
+    uint32_t Mp, Np, Kp; i8gemm_padded_dims(M, N, K, &Mp, &Np, &Kp);
+    const double real = (double)M * N * K, padded = (double)Mp * Np * Kp;
+    return real >= (double)(1u << 24) && padded <= 2.0 * real;
+}
 
 template <typename W>
 static void pack_operand(const void *src, int8_t *dst, uint32_t rows_contig, uint32_t cols, bool transpose, cudaStream_t s)
@@ -574,34 +611,60 @@ static void pack_operand(const void *src, int8_t *dst, uint32_t rows_contig, uin
     count_launch(1);
 }
 
+template <typename W>
+static void pack_padded(const void *src, int8_t *dst, uint32_t rows, uint32_t k, uint32_t rows_p, uint32_t k_p, bool transpose, cudaStream_t s)
+{
+    k_pack_i8_padded<W><<<dim3(k_p / 32, rows_p / 32), dim3(32, 32), 0, s>>>((const W *)src, dst, rows, k, rows_p, k_p, transpose ? 1 : 0);
+    count_launch(1);
+}
+
 // One instance.  A, B: device pointers to raw ABI words (a_wb / b_wb bytes each), column-major as in the plan.
+// Ap / Bp: int8 staging of Mp x Kp and Np x Kp bytes (i8gemm_padded_dims).
 int i8gemm_run(const void *A, const void *B, void *C, uint32_t M, uint32_t N, uint32_t K, bool trans_a, bool trans_b, int a_wb,
                int b_wb, int c_wb, const QStage &outq, int8_t *Ap, int8_t *Bp, cudaStream_t s, const char **err)
 {
+    uint32_t Mp, Np, Kp;
+    i8gemm_padded_dims(M, N, K, &Mp, &Np, &Kp);
+    const bool ragged = Mp != M || Np != N || Kp != K;
     // A operand must become M rows x K (K contiguous).  Stored M x K column-major (M contiguous) unless trans_a (K x M, K contiguous).
     const bool a_tr = !trans_a;
     // B operand must become N rows x K.  Stored K x N column-major (K contiguous) unless trans_b (N x K, N contiguous).
     const bool b_tr = trans_b;
-    const uint32_t a_r = trans_a ? K : M, a_c = trans_a ? M : K;
-    const uint32_t b_r = trans_b ? N : K, b_c = trans_b ? K : N;
-    switch (a_wb) {
-    case 1: pack_operand<int8_t>(A, Ap, a_r, a_c, a_tr, s); break;
-    case 2: pack_operand<int16_t>(A, Ap, a_r, a_c, a_tr, s); break;
-    case 4: pack_operand<int32_t>(A, Ap, a_r, a_c, a_tr, s); break;
-    default: pack_operand<int64_t>(A, Ap, a_r, a_c, a_tr, s); break;
-    }
-    switch (b_wb) {
-    case 1: pack_operand<int8_t>(B, Bp, b_r, b_c, b_tr, s); break;
-    case 2: pack_operand<int16_t>(B, Bp, b_r, b_c, b_tr, s); break;
-    case 4: pack_operand<int32_t>(B, Bp, b_r, b_c, b_tr, s); break;
-    default: pack_operand<int64_t>(B, Bp, b_r, b_c, b_tr, s); break;
+    if (ragged) {
+        switch (a_wb) {
+        case 1: pack_padded<int8_t>(A, Ap, M, K, Mp, Kp, a_tr, s); break;
+        case 2: pack_padded<int16_t>(A, Ap, M, K, Mp, Kp, a_tr, s); break;
+        case 4: pack_padded<int32_t>(A, Ap, M, K, Mp, Kp, a_tr, s); break;
+        default: pack_padded<int64_t>(A, Ap, M, K, Mp, Kp, a_tr, s); break;
+        }
+        switch (b_wb) {
+        case 1: pack_padded<int8_t>(B, Bp, N, K, Np, Kp, b_tr, s); break;
+        case 2: pack_padded<int16_t>(B, Bp, N, K, Np, Kp, b_tr, s); break;
+        case 4: pack_padded<int32_t>(B, Bp, N, K, Np, Kp, b_tr, s); break;
+        default: pack_padded<int64_t>(B, Bp, N, K, Np, Kp, b_tr, s); break;
+        }
+    } else {
+        const uint32_t a_r = trans_a ? K : M, a_c = trans_a ? M : K;
+        const uint32_t b_r = trans_b ? N : K, b_c = trans_b ? K : N;
+        switch (a_wb) {
+        case 1: pack_operand<int8_t>(A, Ap, a_r, a_c, a_tr, s); break;
+        case 2: pack_operand<int16_t>(A, Ap, a_r, a_c, a_tr, s); break;
+        case 4: pack_operand<int32_t>(A, Ap, a_r, a_c, a_tr, s); break;
+        default: pack_operand<int64_t>(A, Ap, a_r, a_c, a_tr, s); break;
+        }
+        switch (b_wb) {
+        case 1: pack_operand<int8_t>(B, Bp, b_r, b_c, b_tr, s); break;
+        case 2: pack_operand<int16_t>(B, Bp, b_r, b_c, b_tr, s); break;
+        case 4: pack_operand<int32_t>(B, Bp, b_r, b_c, b_tr, s); break;
+        default: pack_operand<int64_t>(B, Bp, b_r, b_c, b_tr, s); break;
+        }
     }
     static int variant = -1;                       // QB200_I8_VARIANT: 0 single-CTA kernel, 1 multicast clusters, 2 pair MMA (cta_group::2)
     if (variant < 0) { const char *e = getenv("QB200_I8_VARIANT"); variant = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2; }
-    const bool pair = variant == 2 && (M / BM) % 2 == 0;
-    const bool mc = (variant == 1 || pair) && (M / BM) % 2 == 0;
+    const bool pair = variant == 2 && (Mp / BM) % 2 == 0;
+    const bool mc = (variant == 1 || pair) && (Mp / BM) % 2 == 0;
     CUtensorMap mapA, mapB;
-    if (make_map(&mapA, Ap, M, K, BM) || make_map(&mapB, Bp, N, K, mc ? BN / 2 : BN)) { *err = "cuTensorMapEncodeTiled failed"; return -1; }
+    if (make_map(&mapA, Ap, Mp, Kp, BM) || make_map(&mapB, Bp, Np, Kp, mc ? BN / 2 : BN)) { *err = "cuTensorMapEncodeTiled failed"; return -1; }
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     static bool attr_set[64] = { false };          // function attributes are per device
@@ -613,7 +676,7 @@ int i8gemm_run(const void *A, const void *B, void *C, uint32_t M, uint32_t N, ui
     }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     I8Params P;
-    P.M = M; P.N = N; P.K = K; P.tiles_m = M / BM; P.tiles_n = N / BN; P.c_wb = c_wb; P.group_m = 16;
+    P.M = M; P.N = N; P.K = Kp; P.tiles_m = Mp / BM; P.tiles_n = Np / BN; P.c_wb = c_wb; P.group_m = 16;
     const uint32_t ntiles = P.tiles_m * P.tiles_n;
     if (mc) {
         P.group_m = 8;                                                     // 8 tile pairs = 16 m-tiles per group

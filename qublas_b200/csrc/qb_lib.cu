@@ -557,7 +557,9 @@ extern "C" int qb200_gemul_batched(const qb_gemul_plan *plan, const void *A, con
                      bytes_c = span_elems(batch, plan->stride_c, ec) * gp.c_wb;
         const void *dA, *dB; void *dC; void *Ap, *Bp;
         if ((rc = cx.in(A, bytes_a, &dA)) || (rc = cx.in(B, bytes_b, &dB)) || (rc = cx.out(C, bytes_c, &dC))) return rc;
-        if ((rc = cx.alloc(&Ap, ea)) || (rc = cx.alloc(&Bp, eb))) return rc;
+        uint32_t Mp, Np, Kp;
+        i8gemm_padded_dims(plan->M, plan->N, plan->K, &Mp, &Np, &Kp);
+        if ((rc = cx.alloc(&Ap, (size_t)Mp * Kp)) || (rc = cx.alloc(&Bp, (size_t)Np * Kp))) return rc;
         for (uint64_t i = 0; i < batch; i++) {
             const char *err = "";
             if (i8gemm_run((const char *)dA + i * plan->stride_a * gp.a_wb, (const char *)dB + i * plan->stride_b * gp.b_wb,

@@ -79,3 +79,25 @@ def test_i8_large_vs_exact_float64_gemm():
     Am = A.view(K, M).t().double(); Bm = B.view(N, K).t().double()         # column-major views
     ref = (Am @ Bm).t().contiguous().view(-1)                               # back to column-major
     assert torch.equal(Cd.double(), ref)
+
+
+@pytest.mark.parametrize("M,N,K,ta,tb", [(300, 500, 200, False, False), (380, 500, 333, True, False), (600, 500, 250, False, True), (250, 700, 380, True, True)])
+def test_i8_tensor_core_ragged_shapes_run_on_zero_padded_operands(M, N, K, ta, tb):
+    """Shapes that are not tile multiples: the operands are packed into zero-padded int8 staging buffers (zeros add
+    nothing to an exact dot product) and the epilogue stores only the real M x N block."""
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    a, plan = c5_plan(M, N, K, trans_a=ta, trans_b=tb)
+    info = ops.plan_info_gemul(plan)
+    assert info.tensor_core == 1 and b"tcgen05" in info.kernel
+    A = rng.integers(-128, 128, size=M * K).astype(np.int32)
+    B = rng.integers(-128, 128, size=K * N).astype(np.int32)
+    want = oracle.gemul_batched(plan, A, B, 1)
+    guard = 64
+    Cd = torch.full((M * N + guard,), 123456789, dtype=torch.int32, device="cuda")        # canary behind the result
+    ops.Qgemul(Cd[:M * N], torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda(), plan)
+    assert np.array_equal(Cd[:M * N].cpu().numpy(), want)
+    assert bool((Cd[M * N:] == 123456789).all())
+    # small or badly padded ragged shapes stay on the ALU kernels
+    assert ops.plan_info_gemul(c5_plan(40, 50, 60)[1]).tensor_core == 0
+    assert ops.plan_info_gemul(c5_plan(129, 4096, 4096)[1]).tensor_core == 1           # 256/129 < 2
+    assert ops.plan_info_gemul(c5_plan(5, 4096, 4096)[1]).tensor_core == 0
