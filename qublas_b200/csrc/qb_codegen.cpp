@@ -33,6 +33,7 @@ static std::string emit_levels(const char *fn, const TreeProg &t, unsigned n)
     return o.str();
 }
 
+static std::string emit_flush(const char *fn, const TreeProg &t);
 static unsigned ilog2(uint64_t n) { unsigned l = 0; while (((uint64_t)1 << (l + 1)) <= n) l++; return l; }
 
 static const char *word_t(int wb) { return wb == 1 ? "int8_t" : wb == 2 ? "int16_t" : wb == 4 ? "int32_t" : "int64_t"; }
@@ -43,10 +44,13 @@ std::string emit_gemul_cfg(const std::string &name, const qb_gemul_plan &p, cons
     o << "struct " << name << " {\n";
     o << "  typedef int32_t I;\n";
     o << "  typedef " << word_t(g.a_wb) << " WA; typedef " << word_t(g.b_wb) << " WB; typedef " << word_t(g.c_wb) << " WC;\n";
-    o << "  static constexpr int M = " << p.M << ", N = " << p.N << ", K = " << p.K << ", NLEV = " << ilog2(p.K) << ";\n";
+    unsigned nlev_c = 0;
+    while (((uint64_t)1 << nlev_c) < p.K) nlev_c++;                  // ceil(log2 K); == log2 K for the power-of-two case
+    o << "  static constexpr int M = " << p.M << ", N = " << p.N << ", K = " << p.K << ", NLEV = " << nlev_c << ", NFLUSH = " << g.tree.nflush << ";\n";
     o << "  static constexpr __host__ __device__ qb::QStage mul() { return " << emit_qstage(g.mul) << "; }\n";
     o << "  static constexpr __host__ __device__ qb::QStage out() { return " << emit_qstage(g.out) << "; }\n";
-    o << emit_levels("lvl", g.tree, ilog2(p.K));
+    o << emit_levels("lvl", g.tree, nlev_c);
+    o << emit_flush("flush", g.tree);
     // FP32-FMA product quantizer: fma(a, b, 1.5 * 2^(23+s)) is exact-product-plus-one-IEEE-rounding at a
     // granularity of 2^s, i.e. Qmul's rounded right shift by s in ONE instruction on the FMA pipe
     // (round-to-nearest-even == RND::CONV, round toward -inf == TRN::TCPL; the half-up / half-down modes

@@ -58,7 +58,8 @@ struct GemulTile {
     static constexpr uint32_t STAGE_BYTES = (A_WORDS + B_WORDS) * 4;
     static constexpr uint32_t SMEM_BYTES = 2 * STAGE_BYTES + 64;
     static_assert(M % TM == 0 && N % TN == 0 && TM == 4 && TN == 4, "tile shape");
-    static_assert(K % KC == 0 && (K & (K - 1)) == 0 && K >= KC, "K must be a power of two >= 8");
+    static constexpr bool K_POW2 = (K & (K - 1)) == 0;         // otherwise the pending nodes go through the flush program
+    static_assert(K % KC == 0 && K >= KC, "K must be a multiple of 8");
     static_assert(sizeof(typename Cfg::WA) == 4 && sizeof(typename Cfg::WB) == 4 && sizeof(typename Cfg::WC) == 4, "int32 words");
 };
 
@@ -93,6 +94,34 @@ constexpr int gemul_min_blocks(int threads, unsigned smem_bytes)
     if (n > by_smem) n = by_smem;
     return n < 1 ? 1 : (n > 8 ? 8 : n);
 #endif
+}
+
+// K = 8 * (not a power of two): the same stack, but nodes stay pending at the end and are combined by the host-built
+// flush program (vector form QuBLAS.h:4977-4980, variadic form :4942-4949), unrolled at compile time.  Slot = level - 3.
+template <class Cfg, int L, int NTOP, typename I>
+QB_DEV void stack_push_pending(I (&st)[NTOP > 0 ? NTOP : 1], uint32_t c, I v)
+{
+    if constexpr (L < NTOP) {
+        if ((c >> L) & 1) {
+            constexpr AddStage lv = Cfg::lvl(3 + L);
+            stack_push_pending<Cfg, L + 1, NTOP, I>(st, c, merge_apply<I, true>(st[L], v, lv));
+        } else {
+            st[L] = v;
+        }
+    }
+}
+template <class Cfg, int IDX, int NTOP, typename I>
+QB_DEV I stack_flush(const I (&st)[NTOP > 0 ? NTOP : 1], I cur)
+{
+    if constexpr (IDX >= Cfg::NFLUSH) {
+        return cur;
+    } else {
+        constexpr FlushStep f = Cfg::flush(IDX);
+        if constexpr (f.kind == FL_LOAD) cur = st[f.slot - 3];
+        else if constexpr (f.kind == FL_CONV) cur = conv_apply<I, true>(cur, f.a.q);
+        else cur = add_apply<I, true>(st[f.slot - 3], cur, f.a);
+        return stack_flush<Cfg, IDX + 1, NTOP, I>(st, cur);
+    }
 }
 
 constexpr QStage stage_without_clamps(QStage q) { q.need_lo = 0; q.need_hi = 0; return q; }
@@ -150,11 +179,18 @@ QB_DEV void tile_compute(const int32_t *As, const int32_t *Bs, int i0, int j0, t
                         half0[ii][jj] = hv;
                     } else {
                         const I v = merge_apply<I, true>(half0[ii][jj], hv, l2);
-                        stack_push<Cfg, 0, NTOP, I>(st[ii][jj], c, v, res[ii][jj]);
+                        if constexpr (T::K_POW2) stack_push<Cfg, 0, NTOP, I>(st[ii][jj], c, v, res[ii][jj]);
+                        else stack_push_pending<Cfg, 0, NTOP, I>(st[ii][jj], c, v);
                     }
                 }
             }
         }
+    }
+    if constexpr (!T::K_POW2) {
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) res[ii][jj] = stack_flush<Cfg, 0, NTOP, I>(st[ii][jj], (I)0);
     }
 }
 

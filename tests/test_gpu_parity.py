@@ -744,3 +744,29 @@ def test_jit_elementwise_kernels_vs_runtime_descriptor_and_oracle():
         out, _ = ops.tfcmul(dev(xx), dev(yy), *ty, tags, product=product)
         gen, _ = ops.tfcmul(dev(xx), dev(yy), *ty, tags, product=product, flags=abi.QB_F_NO_SPECIALIZE)
         assert torch.equal(out, gen), product
+
+
+@pytest.mark.parametrize("form", [TREE_VECTOR, TREE_VARIADIC])
+def test_jit_tile_kernel_k_multiple_of_8_vs_oracle(form):
+    """The register-tile template with K = 8 x (not a power of two): pending nodes are combined by the compile-time
+    flush program of the requested tree form."""
+    rng = np.random.default_rng(31 + form)
+    for (M, N, K) in [(64, 64, 48), (32, 32, 24), (64, 32, 40), (64, 64, 56), (32, 64, 104)]:
+        a = QType(int(rng.integers(3, 8)), int(rng.integers(3, 9)), True, 5, 0)
+        b = QType(int(rng.integers(3, 8)), int(rng.integers(3, 9)), True, 5, 0)
+        mul = QType(a.i + b.i - 1, max(a.f, b.f), True, int(rng.integers(0, 7)), int(rng.integers(0, 4)))
+        lv = _rand_levels(rng, mul, int(rng.choice([1, 3, 7])))
+        cc = QType(lv[-1].i, max(lv[-1].f - 1, 1 - lv[-1].i), True, int(rng.integers(0, 7)), int(rng.integers(0, 4)))
+        plan = gemul_plan(a, b, mul, cc, lv, M, N, K, form=form)
+        batch = 5
+        A = rand_words(rng, a, batch * M * K); B = rand_words(rng, b, batch * K * N)
+        Cd = torch.empty(batch * M * N, dtype=torch.int32 if cc.word_bytes == 4 else torch.int64, device="cuda")
+        try:
+            ops.Qgemul(Cd, dev(A), dev(B), plan, batch=batch)
+        except abi.QbError as e:
+            assert e.code == abi.QB_EDOMAIN
+            continue
+        want = oracle.gemul_batched(plan, A, B, batch)
+        assert np.array_equal(Cd.cpu().numpy(), want), (M, N, K, form, a, b, mul, lv, cc)
+        if cc.word_bytes == 4 and ops.plan_info_gemul(plan).arith_bits == 32:
+            assert ops.plan_info_gemul(plan).kernel == b"k_gemul_tile<jit>", (M, N, K)
