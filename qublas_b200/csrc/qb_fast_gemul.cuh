@@ -53,7 +53,8 @@ struct GemulTile {
     static constexpr int KC = 8;                               // products reduced in registers per chunk
     static constexpr int NCH = K / KC;
     static constexpr int NTOP = Cfg::NLEV - 3;                 // stack levels above a chunk
-    static constexpr int THREADS = (M / TM) * (N / TN);
+    static constexpr int THREADS = (M / TM) * (N / TN);          // threads that own a 4x4 tile
+    static constexpr int BLOCK = (THREADS + 31) / 32 * 32;       // launched threads: the rest only helps with staging, conversion and barriers
     static constexpr int A_WORDS = M * K, B_WORDS = K * N;
     static constexpr uint32_t STAGE_BYTES = (A_WORDS + B_WORDS) * 4;
     static constexpr uint32_t SMEM_BYTES = 2 * STAGE_BYTES + 64;
@@ -254,15 +255,15 @@ QB_DEV void gemul_tile_body(const int32_t *__restrict__ A, const int32_t *__rest
                 int4 *w = (int4 *)(part ? Bs : As);
                 constexpr int N4A = T::A_WORDS / 4, N4B = T::B_WORDS / 4;
                 const int n4 = part ? N4B : N4A;
-                constexpr int PER = ((N4A > N4B ? N4A : N4B) + T::THREADS - 1) / T::THREADS;
+                constexpr int PER = ((N4A > N4B ? N4A : N4B) + T::BLOCK - 1) / T::BLOCK;
                 if constexpr (PER <= 8) {
                     // all loads of this part in flight first, then ranges / conversion / stores
                     int4 v[PER];
 #pragma unroll
-                    for (int u = 0; u < PER; ++u) { const int i = tid + u * T::THREADS; if (i < n4) v[u] = w[i]; }
+                    for (int u = 0; u < PER; ++u) { const int i = tid + u * T::BLOCK; if (i < n4) v[u] = w[i]; }
 #pragma unroll
                     for (int u = 0; u < PER; ++u) {
-                        const int i = tid + u * T::THREADS;
+                        const int i = tid + u * T::BLOCK;
                         if (i < n4) {
                             if constexpr (DYN) {
                                 lo[part] = imin<int>(imin<int>(imin<int>(lo[part], v[u].x), imin<int>(v[u].y, v[u].z)), v[u].w);
@@ -273,7 +274,7 @@ QB_DEV void gemul_tile_body(const int32_t *__restrict__ A, const int32_t *__rest
                         }
                     }
                 } else {
-                    for (int i = tid; i < n4; i += T::THREADS) {
+                    for (int i = tid; i < n4; i += T::BLOCK) {
                         const int4 v = w[i];
                         if constexpr (DYN) {
                             lo[part] = imin<int>(imin<int>(imin<int>(lo[part], v.x), imin<int>(v.y, v.z)), v.w);
@@ -296,7 +297,7 @@ QB_DEV void gemul_tile_body(const int32_t *__restrict__ A, const int32_t *__rest
             if constexpr (DYN) {
                 int alo = 0x7fffffff, ahi = (int)0x80000000, blo = 0x7fffffff, bhi = (int)0x80000000;
 #pragma unroll
-                for (int wv = 0; wv < T::THREADS / 32; ++wv) {
+                for (int wv = 0; wv < T::BLOCK / 32; ++wv) {
                     alo = imin<int>(alo, range_smem[wv][0]); ahi = imax<int>(ahi, range_smem[wv][1]);
                     blo = imin<int>(blo, range_smem[wv][2]); bhi = imax<int>(bhi, range_smem[wv][3]);
                 }
@@ -307,30 +308,32 @@ QB_DEV void gemul_tile_body(const int32_t *__restrict__ A, const int32_t *__rest
             }
         }
 
-        I res[4][4];
-        if constexpr (DYN) {
-            if (clamp) tile_compute<Cfg, true>(As, Bs, i0, j0, res);
-            else       tile_compute<Cfg, false>(As, Bs, i0, j0, res);
-        } else {
-            tile_compute<Cfg, true>(As, Bs, i0, j0, res);
-        }
-        // converting assignment into C's element type, column-major 128-bit stores
-        int32_t *Ci = C + inst * (uint64_t)(M * N);
+        if (T::BLOCK == T::THREADS || tid < T::THREADS) {           // padding threads of the last warp own no tile
+            I res[4][4];
+            if constexpr (DYN) {
+                if (clamp) tile_compute<Cfg, true>(As, Bs, i0, j0, res);
+                else       tile_compute<Cfg, false>(As, Bs, i0, j0, res);
+            } else {
+                tile_compute<Cfg, true>(As, Bs, i0, j0, res);
+            }
+            // converting assignment into C's element type, column-major 128-bit stores
+            int32_t *Ci = C + inst * (uint64_t)(M * N);
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-            int4 o;
-            o.x = (int32_t)conv_apply<I, true>(res[0][jj], outq);
-            o.y = (int32_t)conv_apply<I, true>(res[1][jj], outq);
-            o.z = (int32_t)conv_apply<I, true>(res[2][jj], outq);
-            o.w = (int32_t)conv_apply<I, true>(res[3][jj], outq);
-            *(int4 *)(Ci + (j0 + jj) * M + i0) = o;
+            for (int jj = 0; jj < 4; ++jj) {
+                int4 o;
+                o.x = (int32_t)conv_apply<I, true>(res[0][jj], outq);
+                o.y = (int32_t)conv_apply<I, true>(res[1][jj], outq);
+                o.z = (int32_t)conv_apply<I, true>(res[2][jj], outq);
+                o.w = (int32_t)conv_apply<I, true>(res[3][jj], outq);
+                *(int4 *)(Ci + (j0 + jj) * M + i0) = o;
+            }
         }
         __syncthreads();      // everyone is done reading stage s (and range_smem) before it is refilled
     }
 }
 
 template <class Cfg>
-__global__ void __launch_bounds__(GemulTile<Cfg, 4, 4>::THREADS, gemul_min_blocks(GemulTile<Cfg, 4, 4>::THREADS, GemulTile<Cfg, 4, 4>::SMEM_BYTES))
+__global__ void __launch_bounds__(GemulTile<Cfg, 4, 4>::BLOCK, gemul_min_blocks(GemulTile<Cfg, 4, 4>::BLOCK, GemulTile<Cfg, 4, 4>::SMEM_BYTES))
 k_gemul_tile(const int32_t *__restrict__ A, const int32_t *__restrict__ B, int32_t *__restrict__ C, uint64_t batch)
 {
     gemul_tile_body<Cfg>(A, B, C, batch);
@@ -351,12 +354,12 @@ static int launch_gemul_tile(const void *A, const void *B, void *C, uint64_t bat
         int dev = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gemul_tile<Cfg>, T::THREADS, T::SMEM_BYTES);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gemul_tile<Cfg>, T::BLOCK, T::SMEM_BYTES);
         if (e != cudaSuccess) return (int)e;
         grid_cap = sms * (per_sm > 0 ? per_sm : 1);
     }
     const unsigned grid = (unsigned)(batch < (uint64_t)grid_cap ? batch : (uint64_t)grid_cap);
-    k_gemul_tile<Cfg><<<grid, T::THREADS, T::SMEM_BYTES, s>>>((const int32_t *)A, (const int32_t *)B, (int32_t *)C, batch);
+    k_gemul_tile<Cfg><<<grid, T::BLOCK, T::SMEM_BYTES, s>>>((const int32_t *)A, (const int32_t *)B, (int32_t *)C, batch);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) count_launch(1);
     return (int)e;

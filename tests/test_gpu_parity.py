@@ -751,7 +751,7 @@ def test_jit_tile_kernel_k_multiple_of_8_vs_oracle(form):
     """The register-tile template with K = 8 x (not a power of two): pending nodes are combined by the compile-time
     flush program of the requested tree form."""
     rng = np.random.default_rng(31 + form)
-    for (M, N, K) in [(64, 64, 48), (32, 32, 24), (64, 32, 40), (64, 64, 56), (32, 64, 104)]:
+    for (M, N, K) in [(64, 64, 48), (32, 32, 24), (64, 32, 40), (64, 64, 56), (32, 64, 104), (48, 48, 48), (40, 40, 16), (36, 60, 24), (28, 28, 8)]:
         a = QType(int(rng.integers(3, 8)), int(rng.integers(3, 9)), True, 5, 0)
         b = QType(int(rng.integers(3, 8)), int(rng.integers(3, 9)), True, 5, 0)
         mul = QType(a.i + b.i - 1, max(a.f, b.f), True, int(rng.integers(0, 7)), int(rng.integers(0, 4)))
