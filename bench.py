@@ -200,6 +200,19 @@ def roofline_alu(lib, gmacs, device):
 
 
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local):
+    """Multi-GPU end-to-end runs move ~75 GB/s per GPU through host memory: keep each rank's threads (and so the
+    first-touch placement of its pinned buffers) on the CPUs next to its GPU.  Best effort; returns what was done."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return "cpus %d" % len(os.sched_getaffinity(0))
+    except Exception as e:            # no NVML, a single NUMA node, a restricted container: nothing to do
+        return "unchanged (%s)" % type(e).__name__
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -214,6 +227,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = bind_to_gpu_numa_node(local) if world > 1 else "unchanged (single GPU)"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -323,7 +337,8 @@ def run_ours(args):
                                    "MulArgs Qu<14,8,RND::CONV,SAT::TCPL>, 6-level TypeList tree RND::POS_INF, C Qu<17,4>",
                        "batch_per_gpu": Bn, "sharding": "batch, no data-path collective", "kernel": info.kernel.decode(),
                        "l2": "inputs (%.1f GB per GPU) are far larger than the 126 MB L2; no flush needed" % (2 * Bn * WORDS * 4 / 1e9),
-                       "e2e_host_ring": "%d pinned slots x %d instances, reused cyclically; %d instances per e2e step" % (slots, chunk, e2e_instances)},
+                       "e2e_host_ring": "%d pinned slots x %d instances, reused cyclically; %d instances per e2e step" % (slots, chunk, e2e_instances),
+                       "cpu_affinity": affinity},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": ncu_traffic("c3", bytes_per_launch), "algorithmic_bytes": bytes_per_launch,
                          "traffic_source": "profiles/r1_c3_ncu_summary.json (32768-instance launch), scaled to this launch",

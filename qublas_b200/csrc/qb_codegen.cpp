@@ -38,7 +38,7 @@ static unsigned ilog2(uint64_t n) { unsigned l = 0; while (((uint64_t)1 << (l + 
 
 static const char *word_t(int wb) { return wb == 1 ? "int8_t" : wb == 2 ? "int16_t" : wb == 4 ? "int32_t" : "int64_t"; }
 
-std::string emit_gemul_cfg(const std::string &name, const qb_gemul_plan &p, const GemulProg &g)
+std::string emit_gemul_cfg(const std::string &name, const qb_gemul_plan &p, const GemulProg &g, int group)
 {
     std::ostringstream o;
     o << "struct " << name << " {\n";
@@ -46,7 +46,7 @@ std::string emit_gemul_cfg(const std::string &name, const qb_gemul_plan &p, cons
     o << "  typedef " << word_t(g.a_wb) << " WA; typedef " << word_t(g.b_wb) << " WB; typedef " << word_t(g.c_wb) << " WC;\n";
     unsigned nlev_c = 0;
     while (((uint64_t)1 << nlev_c) < p.K) nlev_c++;                  // ceil(log2 K); == log2 K for the power-of-two case
-    o << "  static constexpr int M = " << p.M << ", N = " << p.N << ", K = " << p.K << ", NLEV = " << nlev_c << ", NFLUSH = " << g.tree.nflush << ";\n";
+    o << "  static constexpr int M = " << p.M << ", N = " << p.N << ", K = " << p.K << ", NLEV = " << nlev_c << ", NFLUSH = " << g.tree.nflush << ", G = " << (group > 0 ? group : 1) << ";\n";
     o << "  static constexpr __host__ __device__ qb::QStage mul() { return " << emit_qstage(g.mul) << "; }\n";
     o << "  static constexpr __host__ __device__ qb::QStage out() { return " << emit_qstage(g.out) << "; }\n";
     o << emit_levels("lvl", g.tree, nlev_c);

@@ -12,7 +12,8 @@ namespace qb {
 
 std::string emit_qstage(const QStage &q);
 std::string emit_addstage(const AddStage &a);
-std::string emit_gemul_cfg(const std::string &name, const qb_gemul_plan &p, const GemulProg &g);
+// group = instances a CTA of the register-tile template works on at a time (1 unless the instance is small)
+std::string emit_gemul_cfg(const std::string &name, const qb_gemul_plan &p, const GemulProg &g, int group = 1);
 std::string emit_gemul_thread_cfg(const std::string &name, const qb_gemul_plan &p, const GemulProg &g, int arith_bits);
 std::string emit_reduce_cfg(const std::string &name, const qb_reduce_plan &p, const ReduceProg &r);
 std::string emit_reduce_any_cfg(const std::string &name, const qb_reduce_plan &p, const ReduceProg &r);

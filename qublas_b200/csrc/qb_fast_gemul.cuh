@@ -53,10 +53,12 @@ struct GemulTile {
     static constexpr int KC = 8;                               // products reduced in registers per chunk
     static constexpr int NCH = K / KC;
     static constexpr int NTOP = Cfg::NLEV - 3;                 // stack levels above a chunk
-    static constexpr int THREADS = (M / TM) * (N / TN);          // threads that own a 4x4 tile
+    static constexpr int G = Cfg::G;                             // instances a CTA works on at a time (small shapes: fill the block)
+    static constexpr int TPI = (M / TM) * (N / TN);              // threads per instance, each owns a 4x4 tile
+    static constexpr int THREADS = G * TPI;                      // threads that own a tile
     static constexpr int BLOCK = (THREADS + 31) / 32 * 32;       // launched threads: the rest only helps with staging, conversion and barriers
-    static constexpr int A_WORDS = M * K, B_WORDS = K * N;
-    static constexpr uint32_t STAGE_BYTES = (A_WORDS + B_WORDS) * 4;
+    static constexpr int A_WORDS = M * K, B_WORDS = K * N;       // per instance
+    static constexpr uint32_t STAGE_BYTES = G * (A_WORDS + B_WORDS) * 4;
     static constexpr uint32_t SMEM_BYTES = 2 * STAGE_BYTES + 64;
     static_assert(M % TM == 0 && N % TN == 0 && TM == 4 && TN == 4, "tile shape");
     static constexpr bool K_POW2 = (K & (K - 1)) == 0;         // otherwise the pending nodes go through the flush program
@@ -207,7 +209,8 @@ QB_DEV void gemul_tile_body(const int32_t *__restrict__ A, const int32_t *__rest
     __shared__ int range_smem[32][4];
 
     const int tid = threadIdx.x;
-    const int tx = tid % (M / 4), ty = tid / (M / 4);
+    const int g = T::G == 1 ? 0 : tid / T::TPI, tl = T::G == 1 ? tid : tid - g * T::TPI;       // instance within the group, thread within the instance
+    const int tx = tl % (M / 4), ty = tl / (M / 4);
     const int i0 = tx * 4, j0 = ty * 4;
 
     if (tid == 0) {
@@ -217,15 +220,23 @@ QB_DEV void gemul_tile_body(const int32_t *__restrict__ A, const int32_t *__rest
     }
     __syncthreads();
 
-    auto issue = [&](uint64_t inst, int s) {
+    // a work item is a group of G consecutive instances (the last group of the batch may be shorter); their A arrays are
+    // contiguous in memory, and so are their B arrays: two bulk copies per group
+    const uint64_t ngroups = (batch + T::G - 1) / T::G;
+    auto group_count = [&](uint64_t grp) -> uint32_t {
+        const uint64_t left = batch - grp * T::G;
+        return (uint32_t)(left < (uint64_t)T::G ? left : (uint64_t)T::G);
+    };
+    auto issue = [&](uint64_t grp, int s) {
         int32_t *dst = stage0 + (size_t)s * (T::STAGE_BYTES / 4);
-        mbar_expect_tx(&bars[s], T::STAGE_BYTES);
-        tma_load_1d(dst, A + inst * T::A_WORDS, T::A_WORDS * 4, &bars[s]);
-        tma_load_1d(dst + T::A_WORDS, B + inst * T::B_WORDS, T::B_WORDS * 4, &bars[s]);
+        const uint32_t cnt = group_count(grp);
+        mbar_expect_tx(&bars[s], cnt * (uint32_t)(T::A_WORDS + T::B_WORDS) * 4u);
+        tma_load_1d(dst, A + grp * T::G * T::A_WORDS, cnt * (uint32_t)T::A_WORDS * 4u, &bars[s]);
+        tma_load_1d(dst + T::G * T::A_WORDS, B + grp * T::G * T::B_WORDS, cnt * (uint32_t)T::B_WORDS * 4u, &bars[s]);
     };
 
-    uint64_t inst = blockIdx.x;
-    if (inst < batch && tid == 0) issue(inst, 0);
+    uint64_t inst = blockIdx.x;                                   // group index
+    if (inst < ngroups && tid == 0) issue(inst, 0);
 
     constexpr QStage mulq = Cfg::mul();
     constexpr QStage outq = Cfg::out();
@@ -236,16 +247,16 @@ QB_DEV void gemul_tile_body(const int32_t *__restrict__ A, const int32_t *__rest
     constexpr bool DYN = (mulq.need_lo || mulq.need_hi) && (mulq.of == SAT_TCPL || mulq.of == SAT_SMGN);
     constexpr bool PASS = DYN || Cfg::FP_MUL;
 
-    for (uint32_t it = 0; inst < batch; inst += gridDim.x, ++it) {
+    for (uint32_t it = 0; inst < ngroups; inst += gridDim.x, ++it) {
         const int s = it & 1;
         const uint64_t next = inst + gridDim.x;
-        if (tid == 0 && next < batch) {
+        if (tid == 0 && next < ngroups) {
             if constexpr (Cfg::FP_MUL) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes (int->float) before TMA refill
             issue(next, s ^ 1);                                   // stage s^1 was released by the barrier below
         }
         mbar_wait(&bars[s], (it >> 1) & 1);
         int32_t *As = stage0 + (size_t)s * (T::STAGE_BYTES / 4);
-        int32_t *Bs = As + T::A_WORDS;
+        int32_t *Bs = As + T::G * T::A_WORDS;
         bool clamp = true;
         if constexpr (PASS) {
             // one pass over the staged operands: exact int->float conversion (FP_MUL) and per-instance ranges (DYN)
@@ -253,7 +264,7 @@ QB_DEV void gemul_tile_body(const int32_t *__restrict__ A, const int32_t *__rest
 #pragma unroll
             for (int part = 0; part < 2; ++part) {
                 int4 *w = (int4 *)(part ? Bs : As);
-                constexpr int N4A = T::A_WORDS / 4, N4B = T::B_WORDS / 4;
+                constexpr int N4A = T::G * T::A_WORDS / 4, N4B = T::G * T::B_WORDS / 4;      // the whole group (a short last group leaves stale words: harmless, conservative for the ranges)
                 const int n4 = part ? N4B : N4A;
                 constexpr int PER = ((N4A > N4B ? N4A : N4B) + T::BLOCK - 1) / T::BLOCK;
                 if constexpr (PER <= 8) {
@@ -308,16 +319,17 @@ QB_DEV void gemul_tile_body(const int32_t *__restrict__ A, const int32_t *__rest
             }
         }
 
-        if (T::BLOCK == T::THREADS || tid < T::THREADS) {           // padding threads of the last warp own no tile
+        if ((T::BLOCK == T::THREADS || tid < T::THREADS) && (T::G == 1 || (uint32_t)g < group_count(inst))) {   // padding threads / a short last group own no tile
+            const int32_t *Ag = As + g * T::A_WORDS, *Bg = Bs + g * T::B_WORDS;
             I res[4][4];
             if constexpr (DYN) {
-                if (clamp) tile_compute<Cfg, true>(As, Bs, i0, j0, res);
-                else       tile_compute<Cfg, false>(As, Bs, i0, j0, res);
+                if (clamp) tile_compute<Cfg, true>(Ag, Bg, i0, j0, res);
+                else       tile_compute<Cfg, false>(Ag, Bg, i0, j0, res);
             } else {
-                tile_compute<Cfg, true>(As, Bs, i0, j0, res);
+                tile_compute<Cfg, true>(Ag, Bg, i0, j0, res);
             }
             // converting assignment into C's element type, column-major 128-bit stores
-            int32_t *Ci = C + inst * (uint64_t)(M * N);
+            int32_t *Ci = C + (inst * T::G + g) * (uint64_t)(M * N);
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
                 int4 o;
@@ -358,7 +370,8 @@ static int launch_gemul_tile(const void *A, const void *B, void *C, uint64_t bat
         if (e != cudaSuccess) return (int)e;
         grid_cap = sms * (per_sm > 0 ? per_sm : 1);
     }
-    const unsigned grid = (unsigned)(batch < (uint64_t)grid_cap ? batch : (uint64_t)grid_cap);
+    const uint64_t ngroups = (batch + T::G - 1) / T::G;
+    const unsigned grid = (unsigned)(ngroups < (uint64_t)grid_cap ? ngroups : (uint64_t)grid_cap);
     k_gemul_tile<Cfg><<<grid, T::BLOCK, T::SMEM_BYTES, s>>>((const int32_t *)A, (const int32_t *)B, (int32_t *)C, batch);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) count_launch(1);

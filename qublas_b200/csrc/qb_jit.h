@@ -22,6 +22,7 @@ struct JitKernel {
     struct { uint64_t n_in, n_out; } pass[4] = {};
     unsigned threads = 0, smem = 0;
     int blocks_per_sm = 1, sms = 0;
+    unsigned group = 1;                     // tile template: instances one CTA works on at a time
     unsigned outputs_per_unit = 0;          // > 0: thread-per-output kernel, grid = ceil(batch * outputs_per_unit / threads)
     std::string name, log;
     bool ok = false;

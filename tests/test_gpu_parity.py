@@ -770,3 +770,29 @@ def test_jit_tile_kernel_k_multiple_of_8_vs_oracle(form):
         assert np.array_equal(Cd.cpu().numpy(), want), (M, N, K, form, a, b, mul, lv, cc)
         if cc.word_bytes == 4 and ops.plan_info_gemul(plan).arith_bits == 32:
             assert ops.plan_info_gemul(plan).kernel == b"k_gemul_tile<jit>", (M, N, K)
+
+
+@pytest.mark.parametrize("form", [TREE_VECTOR, TREE_VARIADIC])
+def test_jit_tile_kernel_small_instances_in_groups(form):
+    """Instances with fewer than 48 tile threads: one CTA of the register-tile template works on a group of consecutive
+    instances at a time (two bulk copies per group); batches that are not a multiple of the group exercise the short
+    last group."""
+    rng = np.random.default_rng(77 + form)
+    for (M, N, K, batch) in [(16, 16, 16, 37), (8, 8, 64, 100), (20, 12, 64, 35), (4, 4, 8, 513), (12, 8, 24, 64), (16, 16, 16, 3)]:
+        a = QType(int(rng.integers(3, 8)), int(rng.integers(3, 9)), True, 5, 0)
+        b = QType(int(rng.integers(3, 8)), int(rng.integers(3, 9)), True, 5, 0)
+        mul = QType(a.i + b.i - 1, max(a.f, b.f), True, int(rng.integers(0, 7)), int(rng.integers(0, 4)))
+        lv = _rand_levels(rng, mul, int(rng.choice([1, 3, 7])))
+        cc = QType(lv[-1].i, max(lv[-1].f - 1, 1 - lv[-1].i), True, int(rng.integers(0, 7)), int(rng.integers(0, 4)))
+        plan = gemul_plan(a, b, mul, cc, lv, M, N, K, form=form)
+        A = rand_words(rng, a, batch * M * K); B = rand_words(rng, b, batch * K * N)
+        Cd = torch.empty(batch * M * N, dtype=torch.int32 if cc.word_bytes == 4 else torch.int64, device="cuda")
+        try:
+            ops.Qgemul(Cd, dev(A), dev(B), plan, batch=batch)
+        except abi.QbError as e:
+            assert e.code == abi.QB_EDOMAIN
+            continue
+        want = oracle.gemul_batched(plan, A, B, batch)
+        assert np.array_equal(Cd.cpu().numpy(), want), (M, N, K, batch, form, a, b, mul, lv, cc)
+        if cc.word_bytes == 4 and ops.plan_info_gemul(plan).arith_bits == 32:
+            assert ops.plan_info_gemul(plan).kernel == b"k_gemul_tile<jit>", (M, N, K)
