@@ -142,7 +142,16 @@ QB_DEV void tile_compute(const int32_t *As, const int32_t *Bs, int i0, int j0, t
     const int4 *As4 = (const int4 *)As;
     const int4 *Bs4 = (const int4 *)Bs;
     I st[4][4][NTOP > 0 ? NTOP : 1];
-#pragma unroll 1
+    // The chunk loop is unrolled (up to 8 chunks = the whole K = 64 of config 3): the branches of the level-indexed stack
+    // on the chunk counter then fold at compile time, the stack slots get exact live ranges instead of being loop-carried,
+    // and the scheduler can overlap the tail of one chunk with the loads of the next.  Measured on config 3 (NVRTC build):
+    // unroll 1 / 2 / 4 / 8 = 8 398 / 8 978 / 8 929 / 10 244 GMAC/s.  QB_CHUNK_UNROLL overrides (kernel experiments).
+#ifndef QB_CHUNK_UNROLL
+#define QB_CHUNK_UNROLL 0
+#endif
+    // (not for blocks above 512 threads: their register cap is 64 and the unrolled body spills: 128x128x64 drops from 8.3 to 6.7 TMAC/s)
+    constexpr int CHUNK_UNROLL = QB_CHUNK_UNROLL > 0 ? QB_CHUNK_UNROLL : (T::BLOCK > 512 ? 1 : (T::NCH <= 8 ? T::NCH : 8));
+#pragma unroll CHUNK_UNROLL
     for (uint32_t c = 0; c < (uint32_t)T::NCH; ++c) {
         I half0[4][4];
 #pragma unroll
