@@ -66,6 +66,10 @@ struct GemulTile {
     static_assert(sizeof(typename Cfg::WA) == 4 && sizeof(typename Cfg::WB) == 4 && sizeof(typename Cfg::WC) == 4, "int32 words");
 };
 
+// three-input min / max (one VIMNMX3 each on sm_90+)
+QB_DEV int min3i(int a, int b, int c) { return __vimin3_s32(a, b, c); }
+QB_DEV int max3i(int a, int b, int c) { return __vimax3_s32(a, b, c); }
+
 // level-indexed register stack above the 8-product chunks; c = chunk counter (uniform)
 template <class Cfg, int L, int NTOP, typename I>
 QB_DEV void stack_push(I (&st)[NTOP > 0 ? NTOP : 1], uint32_t c, I v, I &result)
@@ -286,8 +290,8 @@ QB_DEV void gemul_tile_body(const int32_t *__restrict__ A, const int32_t *__rest
                         const int i = tid + u * T::BLOCK;
                         if (i < n4) {
                             if constexpr (DYN) {
-                                lo[part] = imin<int>(imin<int>(imin<int>(lo[part], v[u].x), imin<int>(v[u].y, v[u].z)), v[u].w);
-                                hi[part] = imax<int>(imax<int>(imax<int>(hi[part], v[u].x), imax<int>(v[u].y, v[u].z)), v[u].w);
+                                lo[part] = min3i(min3i(lo[part], v[u].x, v[u].y), v[u].z, v[u].w);      // two VIMNMX3 per four words
+                                hi[part] = max3i(max3i(hi[part], v[u].x, v[u].y), v[u].z, v[u].w);
                             }
                             if constexpr (Cfg::FP_MUL)
                                 ((float4 *)w)[i] = make_float4(__int2float_rn(v[u].x), __int2float_rn(v[u].y), __int2float_rn(v[u].z), __int2float_rn(v[u].w));
@@ -297,8 +301,8 @@ QB_DEV void gemul_tile_body(const int32_t *__restrict__ A, const int32_t *__rest
                     for (int i = tid; i < n4; i += T::BLOCK) {
                         const int4 v = w[i];
                         if constexpr (DYN) {
-                            lo[part] = imin<int>(imin<int>(imin<int>(lo[part], v.x), imin<int>(v.y, v.z)), v.w);
-                            hi[part] = imax<int>(imax<int>(imax<int>(hi[part], v.x), imax<int>(v.y, v.z)), v.w);
+                            lo[part] = min3i(min3i(lo[part], v.x, v.y), v.z, v.w);
+                            hi[part] = max3i(max3i(hi[part], v.x, v.y), v.z, v.w);
                         }
                         if constexpr (Cfg::FP_MUL)
                             ((float4 *)w)[i] = make_float4(__int2float_rn(v.x), __int2float_rn(v.y), __int2float_rn(v.z), __int2float_rn(v.w));
