@@ -541,6 +541,8 @@ def run_secondary(args):
             return {"value": 2.0 * 16 * 16 * Kk / dt / 1e12, "unit": unit, "cores": 1, "kind": "port", "sample": "a 16x16x8192 corner through the C oracle, 1 core"}
 
     roof["frac"] = roof["achieved"] / roof["peak"]
+    if roof["bound"] == "hbm" and roof["frac"] > 1.0:
+        roof["note"] = "the measured peak in MEASURED_PEAKS.json is a copy (read + write) bandwidth; this kernel only reads"
     roof["traffic"] = ncu_traffic(args.workload, bytes_alg) if args.workload in ("c2", "c4") else (ncu_traffic("c5", NCU_CAPTURE_ALG_BYTES["c5"]) if world == 1 else None)
     roof["traffic_source"] = "profiles/r1_%s_ncu_summary.json, scaled to this launch by algorithmic bytes" % args.workload
     roof.setdefault("peak_source", "MEASURED_PEAKS.json" if peaks else "fallback")

@@ -71,7 +71,13 @@ QB_DEV void cgemv_rows_body(const int2 *__restrict__ H, const int2 *__restrict__
         const int2 *Hi = H + inst * (uint64_t)M * K + i;
         I sr[NTOP > 0 ? NTOP : 1], si[NTOP > 0 ? NTOP : 1];
         I rr = 0, ri = 0;
-#pragma unroll 1
+        // chunk loop unrolled by 4: the two lowest stack levels fold at compile time and 32 loads are in flight per thread
+        // (config 4, NVRTC build: unroll 1 / 2 / 4 = 770 / 780 / 796 G complex MAC/s)
+#ifndef QB_CGEMV_UNROLL
+#define QB_CGEMV_UNROLL 4
+#endif
+        constexpr int CHUNK_UNROLL = QB_CGEMV_UNROLL;
+#pragma unroll CHUNK_UNROLL
         for (uint32_t c = 0; c < (uint32_t)(K / 8); ++c) {
             int2 h[8];
 #pragma unroll

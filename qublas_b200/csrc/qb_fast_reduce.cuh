@@ -47,7 +47,13 @@ QB_DEV void reduce_ct_body(const int32_t *__restrict__ x, int32_t *__restrict__ 
         const int4 *src = (const int4 *)(x + (chunk << PW)) + lane * 2;
         I st[NTOP > 0 ? NTOP : 1];
         I result = 0;
-#pragma unroll 1
+        // fully unrolled (<= 4 passes): the stack branches on the group counter fold and all loads of a chunk can be in
+        // flight at once; measured on config 2 (NVRTC build): unroll 1 / 2 / 4 = 1 499 / 1 539 / 1 663 Gelem/s
+#ifndef QB_REDUCE_UNROLL
+#define QB_REDUCE_UNROLL 0
+#endif
+        constexpr int GROUP_UNROLL = QB_REDUCE_UNROLL > 0 ? QB_REDUCE_UNROLL : (NSUB / U > 0 ? NSUB / U : 1);
+#pragma unroll GROUP_UNROLL
         for (int j0 = 0; j0 < NSUB; j0 += U) {
             int4 q[U][2];
 #pragma unroll
@@ -147,7 +153,8 @@ QB_DEV void reduce_any_body(const int32_t *__restrict__ x, int32_t *__restrict__
         if constexpr (RMAX >= PW) {
             constexpr AddStage l0 = Cfg::lvl(LEV0), l1 = Cfg::lvl(LEV0 + 1), l2 = Cfg::lvl(LEV0 + 2);
             I st[NTOP > 0 ? NTOP : 1];
-#pragma unroll 1
+            constexpr int GROUP_UNROLL = NSUB / U > 0 ? NSUB / U : 1;          // as in reduce_ct_body
+#pragma unroll GROUP_UNROLL
             for (int j0 = 0; j0 < NSUB; j0 += U) {
                 I v[U][8];
 #pragma unroll

@@ -280,7 +280,7 @@ static std::shared_ptr<ReduceC> get_reduce(const qb_reduce_plan &p)
     return cached<qb_reduce_plan, ReduceC>(p, [&](ReduceC &e) {
         compile_reduce(p, &e.prog, e.an);
         e.bits = arith_bits(e.an); e.fast = nullptr;
-        if (!e.an.status) { if (e.bits == 32) sanitize32(e.prog.tree); e.fast = find_fast_reduce(p, e.prog, e.bits); }
+        if (!e.an.status) { if (e.bits == 32) sanitize32(e.prog.tree); e.fast = getenv("QB200_NO_AOT") ? nullptr : find_fast_reduce(p, e.prog, e.bits); }
     });
 }
 static std::shared_ptr<GemulC> get_gemul(const qb_gemul_plan &p)
