@@ -47,6 +47,7 @@ std::string emit_gemul_cfg(const std::string &name, const qb_gemul_plan &p, cons
     unsigned nlev_c = 0;
     while (((uint64_t)1 << nlev_c) < p.K) nlev_c++;                  // ceil(log2 K); == log2 K for the power-of-two case
     o << "  static constexpr int M = " << p.M << ", N = " << p.N << ", K = " << p.K << ", NLEV = " << nlev_c << ", NFLUSH = " << g.tree.nflush << ", G = " << (group > 0 ? group : 1) << ";\n";
+    o << "  static constexpr bool TRANS_A = " << (p.trans_a ? "true" : "false") << ", TRANS_B = " << (p.trans_b ? "true" : "false") << ";\n";
     o << "  static constexpr __host__ __device__ qb::QStage mul() { return " << emit_qstage(g.mul) << "; }\n";
     o << "  static constexpr __host__ __device__ qb::QStage out() { return " << emit_qstage(g.out) << "; }\n";
     o << emit_levels("lvl", g.tree, nlev_c);

@@ -161,17 +161,22 @@ QB_DEV void tile_compute(const int32_t *As, const int32_t *Bs, int i0, int j0, t
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int k0 = c * 8 + h * 4;
+            // a 4 (i) x 4 (k) block of op(A) and a 4 (k) x 4 (j) block of op(B) as four 16-byte loads each; which index runs
+            // inside a load depends on the storage: A is M x K column-major (i contiguous), transposed K x M (k contiguous);
+            // B is K x N column-major (k contiguous), transposed N x K (j contiguous)
             int4 bq[4], aq[4];
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) bq[jj] = Bs4[((j0 + jj) * K + k0) >> 2];      // B[k0..k0+3, j]
+            for (int u = 0; u < 4; ++u) bq[u] = Cfg::TRANS_B ? Bs4[((k0 + u) * T::N + j0) >> 2] : Bs4[((j0 + u) * K + k0) >> 2];
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) aq[kk] = As4[((k0 + kk) * M + i0) >> 2];      // A[i0..i0+3, k]
+            for (int u = 0; u < 4; ++u) aq[u] = Cfg::TRANS_A ? As4[((i0 + u) * K + k0) >> 2] : As4[((k0 + u) * M + i0) >> 2];
+            auto a_at = [&](int ii, int kk) -> I { return Cfg::TRANS_A ? (&aq[ii].x)[kk] : (&aq[kk].x)[ii]; };
+            auto b_at = [&](int kk, int jj) -> I { return Cfg::TRANS_B ? (&bq[kk].x)[jj] : (&bq[jj].x)[kk]; };
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
-                const I b0 = bq[jj].x, b1 = bq[jj].y, b2 = bq[jj].z, b3 = bq[jj].w;
+                const I b0 = b_at(0, jj), b1 = b_at(1, jj), b2 = b_at(2, jj), b3 = b_at(3, jj);
 #pragma unroll
                 for (int ii = 0; ii < 4; ++ii) {
-                    const I a0 = (&aq[0].x)[ii], a1 = (&aq[1].x)[ii], a2 = (&aq[2].x)[ii], a3 = (&aq[3].x)[ii];
+                    const I a0 = a_at(ii, 0), a1 = a_at(ii, 1), a2 = a_at(ii, 2), a3 = a_at(ii, 3);
                     I s01, s23;
                     if constexpr (Cfg::FP_MUL) {
                         constexpr int S = Cfg::FP_SHIFT;

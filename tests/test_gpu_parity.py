@@ -757,7 +757,8 @@ def test_jit_tile_kernel_k_multiple_of_8_vs_oracle(form):
         mul = QType(a.i + b.i - 1, max(a.f, b.f), True, int(rng.integers(0, 7)), int(rng.integers(0, 4)))
         lv = _rand_levels(rng, mul, int(rng.choice([1, 3, 7])))
         cc = QType(lv[-1].i, max(lv[-1].f - 1, 1 - lv[-1].i), True, int(rng.integers(0, 7)), int(rng.integers(0, 4)))
-        plan = gemul_plan(a, b, mul, cc, lv, M, N, K, form=form)
+        ta, tb = bool(rng.random() < 0.4), bool(rng.random() < 0.4)              # transposed operands use the same template
+        plan = gemul_plan(a, b, mul, cc, lv, M, N, K, form=form, trans_a=ta, trans_b=tb)
         batch = 5
         A = rand_words(rng, a, batch * M * K); B = rand_words(rng, b, batch * K * N)
         Cd = torch.empty(batch * M * N, dtype=torch.int32 if cc.word_bytes == 4 else torch.int64, device="cuda")
@@ -767,7 +768,7 @@ def test_jit_tile_kernel_k_multiple_of_8_vs_oracle(form):
             assert e.code == abi.QB_EDOMAIN
             continue
         want = oracle.gemul_batched(plan, A, B, batch)
-        assert np.array_equal(Cd.cpu().numpy(), want), (M, N, K, form, a, b, mul, lv, cc)
+        assert np.array_equal(Cd.cpu().numpy(), want), (M, N, K, form, ta, tb, a, b, mul, lv, cc)
         if cc.word_bytes == 4 and ops.plan_info_gemul(plan).arith_bits == 32:
             assert ops.plan_info_gemul(plan).kernel == b"k_gemul_tile<jit>", (M, N, K)
 
@@ -784,7 +785,8 @@ def test_jit_tile_kernel_small_instances_in_groups(form):
         mul = QType(a.i + b.i - 1, max(a.f, b.f), True, int(rng.integers(0, 7)), int(rng.integers(0, 4)))
         lv = _rand_levels(rng, mul, int(rng.choice([1, 3, 7])))
         cc = QType(lv[-1].i, max(lv[-1].f - 1, 1 - lv[-1].i), True, int(rng.integers(0, 7)), int(rng.integers(0, 4)))
-        plan = gemul_plan(a, b, mul, cc, lv, M, N, K, form=form)
+        ta, tb = bool(rng.random() < 0.4), bool(rng.random() < 0.4)
+        plan = gemul_plan(a, b, mul, cc, lv, M, N, K, form=form, trans_a=ta, trans_b=tb)
         A = rand_words(rng, a, batch * M * K); B = rand_words(rng, b, batch * K * N)
         Cd = torch.empty(batch * M * N, dtype=torch.int32 if cc.word_bytes == 4 else torch.int64, device="cuda")
         try:
