@@ -9,6 +9,10 @@
 
 namespace qb {
 
+#ifndef QB_EW_U
+#define QB_EW_U 4
+#endif
+
 template <typename W> QB_DEV void ew_load_pair(const W *p, uint64_t e, W &re, W &im) { re = __ldcs(p + 2 * e); im = __ldcs(p + 2 * e + 1); }
 template <> QB_DEV void ew_load_pair<int32_t>(const int32_t *p, uint64_t e, int32_t &re, int32_t &im)
 {
@@ -24,7 +28,7 @@ QB_DEV void cew_body(const typename Cfg::WX *__restrict__ x, const typename Cfg:
 {
     typedef typename Cfg::I I;
     typedef typename Cfg::WX WX; typedef typename Cfg::WY WY; typedef typename Cfg::WO WO;
-    constexpr int KIND = Cfg::KIND, U = 4;
+    constexpr int KIND = Cfg::KIND, U = QB_EW_U;
     constexpr TfProg tf = Cfg::tf();
     constexpr BcmProg bcm = Cfg::bcm();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -56,7 +60,7 @@ template <class Cfg>
 QB_DEV void ew_body(const typename Cfg::WX *__restrict__ x, const typename Cfg::WY *__restrict__ y, typename Cfg::WO *__restrict__ out, uint64_t n)
 {
     typedef typename Cfg::I I;
-    constexpr int U = 4;
+    constexpr int U = QB_EW_U;
     constexpr AddStage st = Cfg::stage();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t e0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e0 < n; e0 += U * stride) {
@@ -83,7 +87,7 @@ template <class Cfg>
 QB_DEV void conv_body(const typename Cfg::WX *__restrict__ x, const typename Cfg::WY *__restrict__, typename Cfg::WO *__restrict__ out, uint64_t n)
 {
     typedef typename Cfg::I I;
-    constexpr int U = 4;
+    constexpr int U = QB_EW_U;
     constexpr QStage q = Cfg::stage().q;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t e0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e0 < n; e0 += U * stride) {
