@@ -68,7 +68,7 @@ QB_DEV void gemul_thread_body(const typename Cfg::WA *__restrict__ A, const type
         for (uint32_t k = 0; k < K; ++k) tstack_push<Cfg, 0>(st, k, leaf(k));
     } else {
         constexpr uint32_t KC = K / 8;
-#pragma unroll 1
+#pragma unroll 4                                   // four chunks: the two lowest stack levels above the chunk fold as well
         for (uint32_t c = 0; c < KC; ++c) {
 #pragma unroll
             for (uint32_t u = 0; u < 8; ++u) tstack_push<Cfg, 0>(st, c * 8 + u, leaf(c * 8 + u));
@@ -155,7 +155,7 @@ QB_DEV void cgemul_thread_body(const typename Cfg::WA *__restrict__ A, const typ
         for (uint32_t k = 0; k < K; ++k) { I vr, vi; leaf(k, vr, vi); ctstack_push<Cfg, 0>(sr, si, k, vr, vi); }
     } else {
         constexpr uint32_t KC = K / 8;
-#pragma unroll 1
+#pragma unroll 4                                   // four chunks: the two lowest stack levels above the chunk fold as well
         for (uint32_t c = 0; c < KC; ++c) {
 #pragma unroll
             for (uint32_t u = 0; u < 8; ++u) { I vr, vi; leaf(c * 8 + u, vr, vi); ctstack_push<Cfg, 0>(sr, si, c * 8 + u, vr, vi); }
