@@ -34,6 +34,13 @@ static std::string emit_levels(const char *fn, const TreeProg &t, unsigned n)
 }
 
 static std::string emit_flush(const char *fn, const TreeProg &t);
+// batch strides of the plan (in elements), baked into the tag: a kernel is specialised per plan anyway
+static std::string emit_strides(int64_t sa, int64_t sb, int64_t sc)
+{
+    std::ostringstream o;
+    o << "  static constexpr unsigned long long SA = " << (unsigned long long)sa << "ULL, SB = " << (unsigned long long)sb << "ULL, SC = " << (unsigned long long)sc << "ULL;\n";
+    return o.str();
+}
 static unsigned ilog2(uint64_t n) { unsigned l = 0; while (((uint64_t)1 << (l + 1)) <= n) l++; return l; }
 
 static const char *word_t(int wb) { return wb == 1 ? "int8_t" : wb == 2 ? "int16_t" : wb == 4 ? "int32_t" : "int64_t"; }
@@ -48,6 +55,7 @@ std::string emit_gemul_cfg(const std::string &name, const qb_gemul_plan &p, cons
     while (((uint64_t)1 << nlev_c) < p.K) nlev_c++;                  // ceil(log2 K); == log2 K for the power-of-two case
     o << "  static constexpr int M = " << p.M << ", N = " << p.N << ", K = " << p.K << ", NLEV = " << nlev_c << ", NFLUSH = " << g.tree.nflush << ", G = " << (group > 0 ? group : 1) << ";\n";
     o << "  static constexpr bool TRANS_A = " << (p.trans_a ? "true" : "false") << ", TRANS_B = " << (p.trans_b ? "true" : "false") << ";\n";
+    o << emit_strides(p.stride_a, p.stride_b, p.stride_c);
     o << "  static constexpr __host__ __device__ qb::QStage mul() { return " << emit_qstage(g.mul) << "; }\n";
     o << "  static constexpr __host__ __device__ qb::QStage out() { return " << emit_qstage(g.out) << "; }\n";
     o << emit_levels("lvl", g.tree, nlev_c);
@@ -94,6 +102,7 @@ std::string emit_gemul_thread_cfg(const std::string &name, const qb_gemul_plan &
     o << "  static constexpr unsigned M = " << p.M << ", N = " << p.N << ", K = " << p.K << ";\n";
     o << "  static constexpr int NLEV = " << nlev << ", NFLUSH = " << g.tree.nflush << ", TOP_SLOT = " << g.tree.top_slot << ";\n";
     o << "  static constexpr bool TRANS_A = " << (p.trans_a ? "true" : "false") << ", TRANS_B = " << (p.trans_b ? "true" : "false") << ";\n";
+    o << emit_strides(p.stride_a, p.stride_b, p.stride_c);
     o << "  static constexpr __host__ __device__ qb::QStage mul() { return " << emit_qstage(g.mul) << "; }\n";
     o << "  static constexpr __host__ __device__ qb::QStage out() { return " << emit_qstage(g.out) << "; }\n";
     o << emit_levels("lvl", g.tree, nlev);
@@ -144,6 +153,7 @@ std::string emit_cgemul_thread_cfg(const std::string &name, const qb_cgemul_plan
     o << "  static constexpr int KIND = " << g.kind << ", NLEV = " << nlev << ", NFLUSH_RE = " << g.tree_re.nflush << ", NFLUSH_IM = " << g.tree_im.nflush
       << ", TOP_RE = " << g.tree_re.top_slot << ", TOP_IM = " << g.tree_im.top_slot << ";\n";
     o << "  static constexpr bool TRANS_A = " << (p.trans_a ? "true" : "false") << ", TRANS_B = " << (p.trans_b ? "true" : "false") << ";\n";
+    o << emit_strides(p.stride_a, p.stride_b, p.stride_c);
     o << "  static constexpr __host__ __device__ qb::TfProg tf() { return " << emit_tfprog(g.tf) << "; }\n";
     o << "  static constexpr __host__ __device__ qb::BcmProg bcm() { return " << emit_bcmprog(g.bcm) << "; }\n";
     o << "  static constexpr __host__ __device__ qb::QStage out_re() { return " << emit_qstage(g.out_re) << "; }\n";
@@ -177,6 +187,7 @@ std::string emit_cgemul_cfg(const std::string &name, const qb_cgemul_plan &p, co
     o << "  typedef int32_t I;\n";
     o << "  typedef " << word_t(g.a_wb) << " WA; typedef " << word_t(g.b_wb) << " WB; typedef " << word_t(g.c_wb) << " WC;\n";
     o << "  static constexpr int M = " << p.M << ", N = " << p.N << ", K = " << p.K << ", NLEV = " << ilog2(p.K) << ";\n";
+    o << emit_strides(p.stride_a, p.stride_b, p.stride_c);
     o << "  static constexpr __host__ __device__ qb::TfProg tf() { return qb::TfProg{" << emit_addstage(g.tf.ab) << ",\n      "
       << emit_addstage(g.tf.cd) << ",\n      " << emit_addstage(g.tf.ba) << ",\n      " << emit_qstage(g.tf.A) << ",\n      "
       << emit_qstage(g.tf.B) << ",\n      " << emit_qstage(g.tf.C) << ",\n      " << emit_addstage(g.tf.re) << ",\n      "

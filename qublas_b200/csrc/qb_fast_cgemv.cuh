@@ -61,14 +61,14 @@ QB_DEV void cgemv_rows_body(const int2 *__restrict__ H, const int2 *__restrict__
     for (uint64_t inst = blockIdx.x; inst < batch; inst += gridDim.x) {
         __syncthreads();                                   // previous instance finished with xc/xd/xcd
         for (int k = i; k < K; k += M) {
-            const int2 x = __ldg(X + inst * K + k);
+            const int2 x = __ldg(X + inst * (uint64_t)Cfg::SB + k);          // batch strides in complex elements; 0 = shared operand
             const int cdv = (int)add_apply<I, true>((I)x.x, (I)x.y, tf.cd);       // Qadd<cdT>(c, d), QuBLAS.h:3525
             xc[k] = Cfg::FP_A ? __float_as_int(__int2float_rn(x.x)) : x.x;
             xd[k] = Cfg::FP_C ? __float_as_int(__int2float_rn(x.y)) : x.y;
             xcd[k] = Cfg::FP_B ? __float_as_int(__int2float_rn(cdv)) : cdv;
         }
         __syncthreads();
-        const int2 *Hi = H + inst * (uint64_t)M * K + i;
+        const int2 *Hi = H + inst * (uint64_t)Cfg::SA + i;
         I sr[NTOP > 0 ? NTOP : 1], si[NTOP > 0 ? NTOP : 1];
         I rr = 0, ri = 0;
         // chunk loop unrolled by 4: the two lowest stack levels fold at compile time and 32 loads are in flight per thread
@@ -114,7 +114,7 @@ QB_DEV void cgemv_rows_body(const int2 *__restrict__ H, const int2 *__restrict__
         int2 o;
         o.x = (int)conv_apply<I, true>(rr, ore);
         o.y = (int)conv_apply<I, true>(ri, oim);
-        Y[inst * M + i] = o;
+        Y[inst * (uint64_t)Cfg::SC + i] = o;
     }
 }
 

@@ -64,6 +64,10 @@ struct GemulTile {
     static constexpr bool K_POW2 = (K & (K - 1)) == 0;         // otherwise the pending nodes go through the flush program
     static_assert(K % KC == 0 && K >= KC, "K must be a multiple of 8");
     static_assert(sizeof(typename Cfg::WA) == 4 && sizeof(typename Cfg::WB) == 4 && sizeof(typename Cfg::WC) == 4, "int32 words");
+    // batch strides in words (plan.stride_*): dense by default, 0 = the operand is shared by all instances, larger = padded
+    static constexpr unsigned long long SA = Cfg::SA, SB = Cfg::SB, SC = Cfg::SC;
+    static_assert(G == 1 || (SA == (unsigned long long)A_WORDS && SB == (unsigned long long)B_WORDS), "groups of instances need dense operands");
+    static_assert(SA % 4 == 0 && SB % 4 == 0 && SC % 4 == 0, "16-byte aligned instances");
 };
 
 // three-input min / max (one VIMNMX3 each on sm_90+)
@@ -220,7 +224,7 @@ QB_DEV void gemul_tile_body(const int32_t *__restrict__ A, const int32_t *__rest
 {
     typedef GemulTile<Cfg, 4, 4> T;
     typedef typename T::I I;
-    constexpr int M = T::M, N = T::N;
+    constexpr int M = T::M;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     int32_t *stage0 = (int32_t *)smem_raw;
     uint64_t *bars = (uint64_t *)(smem_raw + 2 * T::STAGE_BYTES);
@@ -249,8 +253,8 @@ QB_DEV void gemul_tile_body(const int32_t *__restrict__ A, const int32_t *__rest
         int32_t *dst = stage0 + (size_t)s * (T::STAGE_BYTES / 4);
         const uint32_t cnt = group_count(grp);
         mbar_expect_tx(&bars[s], cnt * (uint32_t)(T::A_WORDS + T::B_WORDS) * 4u);
-        tma_load_1d(dst, A + grp * T::G * T::A_WORDS, cnt * (uint32_t)T::A_WORDS * 4u, &bars[s]);
-        tma_load_1d(dst + T::G * T::A_WORDS, B + grp * T::G * T::B_WORDS, cnt * (uint32_t)T::B_WORDS * 4u, &bars[s]);
+        tma_load_1d(dst, A + grp * T::G * T::SA, cnt * (uint32_t)T::A_WORDS * 4u, &bars[s]);
+        tma_load_1d(dst + T::G * T::A_WORDS, B + grp * T::G * T::SB, cnt * (uint32_t)T::B_WORDS * 4u, &bars[s]);
     };
 
     uint64_t inst = blockIdx.x;                                   // group index
@@ -347,7 +351,7 @@ QB_DEV void gemul_tile_body(const int32_t *__restrict__ A, const int32_t *__rest
                 tile_compute<Cfg, true>(Ag, Bg, i0, j0, res);
             }
             // converting assignment into C's element type, column-major 128-bit stores
-            int32_t *Ci = C + (inst * T::G + g) * (uint64_t)(M * N);
+            int32_t *Ci = C + (inst * T::G + g) * T::SC;
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
                 int4 o;

@@ -55,8 +55,8 @@ QB_DEV void gemul_thread_body(const typename Cfg::WA *__restrict__ A, const type
     if (t >= batch * PER) return;
     const uint64_t inst = t / PER;
     const uint32_t ij = (uint32_t)(t - inst * PER), j = ij / M, i = ij - j * M;
-    const typename Cfg::WA *a = A + inst * (uint64_t)(M * K);
-    const typename Cfg::WB *b = B + inst * (uint64_t)(K * N);
+    const typename Cfg::WA *a = A + inst * (uint64_t)Cfg::SA;          // batch strides in words; 0 = shared operand
+    const typename Cfg::WB *b = B + inst * (uint64_t)Cfg::SB;
     auto leaf = [&](uint32_t k) -> I {
         const uint32_t ia = Cfg::TRANS_A ? (k + i * K) : (i + k * M);                 // column-major, QuBLAS.h:2680-2692
         const uint32_t ib = Cfg::TRANS_B ? (j + k * N) : (k + j * K);
@@ -79,7 +79,7 @@ QB_DEV void gemul_thread_body(const typename Cfg::WA *__restrict__ A, const type
     I r;
     if constexpr (Cfg::NFLUSH == 0) r = st[Cfg::TOP_SLOT];
     else r = tstack_flush<Cfg, 0>(st, (I)0);
-    C[inst * (uint64_t)PER + ij] = (typename Cfg::WC)conv_apply<I, true>(r, outq);
+    C[inst * (uint64_t)Cfg::SC + ij] = (typename Cfg::WC)conv_apply<I, true>(r, outq);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -139,7 +139,7 @@ QB_DEV void cgemul_thread_body(const typename Cfg::WA *__restrict__ A, const typ
     if (t >= batch * PER) return;
     const uint64_t inst = t / PER;
     const uint32_t ij = (uint32_t)(t - inst * PER), j = ij / M, i = ij - j * M;
-    const uint64_t oa = inst * (uint64_t)(M * K), ob = inst * (uint64_t)(K * N);
+    const uint64_t oa = inst * (uint64_t)Cfg::SA, ob = inst * (uint64_t)Cfg::SB;      // batch strides in elements; 0 = shared operand
     auto leaf = [&](uint32_t k, I &vr, I &vi) {
         const uint32_t ia = Cfg::TRANS_A ? (k + i * K) : (i + k * M);
         const uint32_t ib = Cfg::TRANS_B ? (j + k * N) : (k + j * K);
@@ -166,7 +166,7 @@ QB_DEV void cgemul_thread_body(const typename Cfg::WA *__restrict__ A, const typ
     I rr, ri;
     if constexpr (Cfg::NFLUSH_RE == 0) rr = sr[Cfg::TOP_RE]; else rr = ctstack_flush<Cfg, false, 0>(sr, (I)0);
     if constexpr (Cfg::NFLUSH_IM == 0) ri = si[Cfg::TOP_IM]; else ri = ctstack_flush<Cfg, true, 0>(si, (I)0);
-    const uint64_t ic = inst * (uint64_t)PER + ij;
+    const uint64_t ic = inst * (uint64_t)Cfg::SC + ij;
     C[2 * ic] = (typename Cfg::WC)conv_apply<I, true>(rr, ore);
     C[2 * ic + 1] = (typename Cfg::WC)conv_apply<I, true>(ri, oim);
 }

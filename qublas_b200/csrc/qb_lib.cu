@@ -528,7 +528,8 @@ extern "C" int qb200_gemul_batched(const qb_gemul_plan *plan, const void *A, con
     const int bits = ce->bits;
     const FastGemul *f = (cx.flags & QB_F_NO_SPECIALIZE) ? nullptr : ce->fast;
     JitKernel *jk = nullptr;
-    if (!f && !ce->tc && !(cx.flags & QB_F_NO_SPECIALIZE) && plan->stride_a == (int64_t)ea && plan->stride_b == (int64_t)eb && plan->stride_c == (int64_t)ec) {
+    const bool dense_plan = plan->stride_a == (int64_t)ea && plan->stride_b == (int64_t)eb && plan->stride_c == (int64_t)ec;
+    if ((!f || !dense_plan) && !ce->tc && !(cx.flags & QB_F_NO_SPECIALIZE)) {      // run-time specialised kernels carry the plan's strides
         jk = ce->jit.get([&] { return jit_gemul(*plan, gp, bits); });
     }
     // one launch over n instances laid out with the given strides
@@ -538,7 +539,7 @@ extern "C" int qb200_gemul_batched(const qb_gemul_plan *plan, const void *A, con
             if (e) return fail(QB_ECUDA, std::string(f->name) + " launch failed: " + cudaGetErrorString((cudaError_t)e));
             return QB_OK;
         }
-        if (jk && sa == (int64_t)ea && sb == (int64_t)eb && sc == (int64_t)ec && !((uintptr_t)dA & 15) && !((uintptr_t)dB & 15) && !((uintptr_t)dC & 15)) {
+        if (jk && sa == plan->stride_a && sb == plan->stride_b && sc == plan->stride_c && !((uintptr_t)dA & 15) && !((uintptr_t)dB & 15) && !((uintptr_t)dC & 15)) {
             int e = jit_launch_gemul(*jk, dA, dB, dC, n, st);
             if (e) return fail(QB_ECUDA, jk->name + " launch failed (CUresult " + std::to_string(e) + ")");
             return QB_OK;
@@ -622,10 +623,11 @@ extern "C" int qb200_cgemul_batched(const qb_cgemul_plan *plan, const void *A, c
     const int bits = ce->bits;
     const FastCGemul *f = (cx.flags & QB_F_NO_SPECIALIZE) ? nullptr : ce->fast;
     JitKernel *jk = nullptr;
-    if (!f && !(cx.flags & QB_F_NO_SPECIALIZE) && plan->stride_a == (int64_t)ea && plan->stride_b == (int64_t)eb && plan->stride_c == (int64_t)ec) {
+    const bool dense_plan = plan->stride_a == (int64_t)ea && plan->stride_b == (int64_t)eb && plan->stride_c == (int64_t)ec;
+    if ((!f || !dense_plan) && !(cx.flags & QB_F_NO_SPECIALIZE)) {                  // run-time specialised kernels carry the plan's strides
         jk = ce->jit.get([&] { return jit_cgemul(*plan, gp, bits); });
     }
-    if (f) {
+    if (f && dense_plan) {
         rc = f->launch(dA, dB, dC, batch, cx.stream);
         if (rc) return fail(QB_ECUDA, std::string(f->name) + " launch failed: " + cudaGetErrorString((cudaError_t)rc));
     } else if (jk && !((uintptr_t)dA & 15) && !((uintptr_t)dB & 15) && !((uintptr_t)dC & 15)) {      // vector loads of {re, im} pairs

@@ -798,3 +798,39 @@ def test_jit_tile_kernel_small_instances_in_groups(form):
         assert np.array_equal(Cd.cpu().numpy(), want), (M, N, K, batch, form, a, b, mul, lv, cc)
         if cc.word_bytes == 4 and ops.plan_info_gemul(plan).arith_bits == 32:
             assert ops.plan_info_gemul(plan).kernel == b"k_gemul_tile<jit>", (M, N, K)
+
+
+def test_batch_strides_on_the_specialised_kernels():
+    """Batch strides (0 = an operand shared by every instance, larger than dense = padded layouts) are part of the plan and
+    are baked into the run-time specialised kernels: real tile and thread templates, complex rows and thread templates."""
+    rng = np.random.default_rng(515)
+    a = QType(7, 8); mul = QType(14, 8, True, RND_CONV, SAT_TCPL)
+    lv = [QType(15 + l, 8 - l, True, RND_POS_INF, SAT_TCPL) for l in range(6)]; c = QType(17, 4, True, RND_POS_INF, SAT_TCPL)
+    for (M, N, K, sa, sb, sc, kernel) in [(64, 64, 64, 0, 4096, 4096, b"k_gemul_tile<jit>"), (64, 64, 64, 4096, 0, 4100, b"k_gemul_tile<jit>"),
+                                          (32, 32, 16, 512 + 8, 512 + 4, 1024 + 12, b"k_gemul_tile<jit>"), (5, 7, 12, 0, 84 + 3, 35 + 1, b"k_gemul_thread<jit>")]:
+        plan = ops.make_gemul_plan(a, a, c, M, N, K, mul=mul, add=lv)
+        plan.stride_a, plan.stride_b, plan.stride_c = sa, sb, sc
+        batch = 6
+        A = rand_words(rng, a, (batch - 1) * sa + M * K).astype(np.int32); B = rand_words(rng, a, (batch - 1) * sb + K * N).astype(np.int32)
+        want = oracle.gemul_batched(plan, A, B, batch)
+        Cd = torch.zeros((batch - 1) * sc + M * N, dtype=torch.int32, device="cuda")
+        ops.Qgemul(Cd, dev(A), dev(B), plan, batch=batch)
+        got = Cd.cpu().numpy()
+        for i in range(batch):
+            assert np.array_equal(got[i * sc:i * sc + M * N], want[i * sc:i * sc + M * N]), (M, N, K, sa, sb, sc, i)
+        assert ops.plan_info_gemul(plan).kernel == kernel
+    # complex: a channel matrix shared by all instances (stride 0), mat-vec rows template and thread template
+    t = QType(3, 12); P = QType(6, 12); S = QType(7, 12)
+    tags = {"abT": QType(4, 12), "cdT": QType(4, 11), "abcT": P, "cdbT": P, "badT": P, "ABT": S, "BCT": S}
+    clv = [QType(8 + l, 12 - l, True, RND_CONV, SAT_TCPL) for l in range(6)]
+    for (M, N, K, kernel) in [(64, 1, 64, b"k_cgemv_rows<jit>"), (6, 2, 10, b"k_cgemul_thread<jit>")]:
+        plan = ops.make_cgemul_plan(t, t, t, t, clv[-1], clv[-1], M, N, K, tf_tags=tags, add_re=clv)
+        plan.stride_a = 0
+        batch = 9
+        H = np.stack([rand_words(rng, t, M * K), rand_words(rng, t, M * K)], axis=1).astype(np.int32).reshape(-1)
+        X = np.stack([rand_words(rng, t, batch * K * N), rand_words(rng, t, batch * K * N)], axis=1).astype(np.int32).reshape(-1)
+        want = oracle.cgemul_batched(plan, H, X, batch)
+        Y = torch.empty(batch * M * N * 2, dtype=torch.int32, device="cuda")
+        ops.Qcgemul(Y, dev(H), dev(X), plan, batch=batch)
+        assert np.array_equal(Y.cpu().numpy(), want), (M, N, K)
+        assert ops.plan_info_cgemul(plan).kernel == kernel
