@@ -196,3 +196,19 @@ def test_every_jit_template_compiles_without_a_device():
         check(4, ops.make_ew_plan(op, QType(7, 8), QType(5, 6), 100, QType(10, 6, True, 4, 0)))
     cp = abi.qb_convert_plan(); cp.from_, cp.to, cp.len = abi.desc(QType(20, 10)), abi.desc(QType(36, 9, True, 3, 2)), 10
     check(5, cp)
+
+
+def test_jit_disk_cache(tmp_path, monkeypatch):
+    """QB200_JIT_CACHE=<dir>: compiled kernels are stored under a hash of their generated source and reused."""
+    import ctypes
+    import time
+    monkeypatch.setenv("QB200_JIT_CACHE", str(tmp_path))
+    lib = abi.load()
+    log = ctypes.create_string_buffer(8192)
+    plan = ops.make_gemul_plan(QType(6, 7), QType(6, 7), QType(15, 5), 32, 32, 16, mul=QType(12, 7, True, 4, 0),
+                               add=[QType(13 + l, 7 - l, True, 0, 0) for l in range(4)])
+    t0 = time.time(); assert lib.qb200_jit_check_gemul(ctypes.byref(plan), log, 8192) == 0; cold = time.time() - t0
+    files = [f for f in os.listdir(tmp_path) if f.endswith(".cubin")]
+    assert len(files) == 1 and os.path.getsize(os.path.join(tmp_path, files[0])) > 1000
+    t0 = time.time(); assert lib.qb200_jit_check_gemul(ctypes.byref(plan), log, 8192) == 0; warm = time.time() - t0
+    assert warm < cold and [f for f in os.listdir(tmp_path) if f.endswith(".cubin")] == files
