@@ -319,6 +319,32 @@ def run_ours(args):
     if not np.array_equal(nC[0][:WORDS], Cd[:WORDS].cpu().numpy()):
         raise SystemExit("bench.py: host-path result differs from device-path result")
 
+    # supplementary: the same call with the operands handed over as packed int16 words (qb_qdesc.word_bytes = 2; the
+    # 16-bit operand type fits).  Not the reference's layout (int32 words), so it is not the e2e figure -- it shows what
+    # the PCIe-bound path does when the caller can supply half the bytes.
+    e2e16 = None
+    if world == 1 and not args.no_packed16:
+        plan16 = ops.make_gemul_plan(a, a, c, M, N, K, mul=mul, add=lv, word_bytes=(2, 2, 0))
+        hA16 = [x.to(torch.int16).pin_memory() for x in hA]; hB16 = [x.to(torch.int16).pin_memory() for x in hB]
+        nA16 = [x.numpy() for x in hA16]; nB16 = [x.numpy() for x in hB16]
+        n16 = min(e2e_instances, 8 * chunk)
+
+        def e2e16_step():
+            done = 0
+            for i in range((n16 + chunk - 1) // chunk):
+                n = min(chunk, n16 - done)
+                ops.Qgemul(nC[i % slots], nA16[i % slots], nB16[i % slots], plan16, batch=n)
+                done += n
+
+        e2e16_step()
+        t0 = time.perf_counter()
+        e2e16_step()
+        dt = time.perf_counter() - t0
+        if not np.array_equal(nC[0][:WORDS], Cd[:WORDS].cpu().numpy()):
+            raise SystemExit("bench.py: packed-word host path differs from the device-path result")
+        e2e16 = {"value": n16 * MACS_PER_INSTANCE / dt / 1e9, "unit": "GMAC/s", "h2d_bytes_per_step": n16 * 2 * WORDS * 2, "d2h_bytes_per_step": n16 * WORDS * 4,
+                 "note": "operands as packed int16 words (qb_qdesc.word_bytes = 2), not the reference's int32 layout"}
+
     if rank == 0:
         peaks = {}
         try:
@@ -349,6 +375,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "GMAC/s", "h2d_bytes_per_step": world * e2e_instances * 2 * WORDS * 4,
                     "d2h_bytes_per_step": world * e2e_instances * WORDS * 4, "scope": "whole job (all ranks)"},
             "gpu_launches": launches,
+            "e2e_packed16": e2e16,
             "bit_exact_checked": "first and last instance of every rank vs oracle",
         }
         if world == 1 and not args.no_cpu:
@@ -571,6 +598,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1000000, help="instances per GPU (BASELINE config 3: 1e6)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-chunk", type=int, default=32768, help="instances per host-buffer API call")
+    ap.add_argument("--no-packed16", action="store_true", help="skip the supplementary packed-int16 end-to-end measurement")
     ap.add_argument("--e2e-instances", type=int, default=1000000, help="instances per end-to-end step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5"],

@@ -58,16 +58,22 @@ struct GemulTile {
     static constexpr int THREADS = G * TPI;                      // threads that own a tile
     static constexpr int BLOCK = (THREADS + 31) / 32 * 32;       // launched threads: the rest only helps with staging, conversion and barriers
     static constexpr int A_WORDS = M * K, B_WORDS = K * N;       // per instance
-    static constexpr uint32_t STAGE_BYTES = G * (A_WORDS + B_WORDS) * 4;
-    static constexpr uint32_t SMEM_BYTES = 2 * STAGE_BYTES + 64;
+    // operand words: int32 (the reference's storage) or packed int16 (qb_qdesc.word_bytes = 2: half the HBM / PCIe bytes).
+    // Packed words are staged as they are and widened by the conversion pass into a separate single-buffered region.
+    static constexpr int WORD = (int)sizeof(typename Cfg::WA);
+    static constexpr bool NARROW = WORD == 2;
+    static constexpr uint32_t STAGE_BYTES = G * (A_WORDS + B_WORDS) * WORD;
+    static constexpr uint32_t WIDE_BYTES = NARROW ? G * (A_WORDS + B_WORDS) * 4 : 0;
+    static constexpr uint32_t SMEM_BYTES = 2 * STAGE_BYTES + WIDE_BYTES + 64;
     static_assert(M % TM == 0 && N % TN == 0 && TM == 4 && TN == 4, "tile shape");
     static constexpr bool K_POW2 = (K & (K - 1)) == 0;         // otherwise the pending nodes go through the flush program
     static_assert(K % KC == 0 && K >= KC, "K must be a multiple of 8");
-    static_assert(sizeof(typename Cfg::WA) == 4 && sizeof(typename Cfg::WB) == 4 && sizeof(typename Cfg::WC) == 4, "int32 words");
+    static_assert(sizeof(typename Cfg::WA) == sizeof(typename Cfg::WB) && (WORD == 4 || WORD == 2) && sizeof(typename Cfg::WC) == 4, "int32 or int16 operand words, int32 results");
+    static_assert(!NARROW || (A_WORDS % 8 == 0 && B_WORDS % 8 == 0), "16-byte aligned int16 instances");
     // batch strides in words (plan.stride_*): dense by default, 0 = the operand is shared by all instances, larger = padded
     static constexpr unsigned long long SA = Cfg::SA, SB = Cfg::SB, SC = Cfg::SC;
     static_assert(G == 1 || (SA == (unsigned long long)A_WORDS && SB == (unsigned long long)B_WORDS), "groups of instances need dense operands");
-    static_assert(SA % 4 == 0 && SB % 4 == 0 && SC % 4 == 0, "16-byte aligned instances");
+    static_assert(SA % (16 / WORD) == 0 && SB % (16 / WORD) == 0 && SC % 4 == 0, "16-byte aligned instances");
 };
 
 // three-input min / max (one VIMNMX3 each on sm_90+)
@@ -220,14 +226,13 @@ QB_DEV void tile_compute(const int32_t *As, const int32_t *Bs, int i0, int j0, t
 }
 
 template <class Cfg>
-QB_DEV void gemul_tile_body(const int32_t *__restrict__ A, const int32_t *__restrict__ B, int32_t *__restrict__ C, uint64_t batch)
+QB_DEV void gemul_tile_body(const typename Cfg::WA *__restrict__ A, const typename Cfg::WB *__restrict__ B, int32_t *__restrict__ C, uint64_t batch)
 {
     typedef GemulTile<Cfg, 4, 4> T;
     typedef typename T::I I;
     constexpr int M = T::M;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    int32_t *stage0 = (int32_t *)smem_raw;
-    uint64_t *bars = (uint64_t *)(smem_raw + 2 * T::STAGE_BYTES);
+    uint64_t *bars = (uint64_t *)(smem_raw + 2 * T::STAGE_BYTES + T::WIDE_BYTES);
     __shared__ int range_smem[32][4];
 
     const int tid = threadIdx.x;
@@ -250,11 +255,11 @@ QB_DEV void gemul_tile_body(const int32_t *__restrict__ A, const int32_t *__rest
         return (uint32_t)(left < (uint64_t)T::G ? left : (uint64_t)T::G);
     };
     auto issue = [&](uint64_t grp, int s) {
-        int32_t *dst = stage0 + (size_t)s * (T::STAGE_BYTES / 4);
+        unsigned char *dst = smem_raw + (size_t)s * T::STAGE_BYTES;
         const uint32_t cnt = group_count(grp);
-        mbar_expect_tx(&bars[s], cnt * (uint32_t)(T::A_WORDS + T::B_WORDS) * 4u);
-        tma_load_1d(dst, A + grp * T::G * T::SA, cnt * (uint32_t)T::A_WORDS * 4u, &bars[s]);
-        tma_load_1d(dst + T::G * T::A_WORDS, B + grp * T::G * T::SB, cnt * (uint32_t)T::B_WORDS * 4u, &bars[s]);
+        mbar_expect_tx(&bars[s], cnt * (uint32_t)(T::A_WORDS + T::B_WORDS) * (uint32_t)T::WORD);
+        tma_load_1d(dst, A + grp * T::G * T::SA, cnt * (uint32_t)T::A_WORDS * (uint32_t)T::WORD, &bars[s]);
+        tma_load_1d(dst + T::G * T::A_WORDS * T::WORD, B + grp * T::G * T::SB, cnt * (uint32_t)T::B_WORDS * (uint32_t)T::WORD, &bars[s]);
     };
 
     uint64_t inst = blockIdx.x;                                   // group index
@@ -267,7 +272,7 @@ QB_DEV void gemul_tile_body(const int32_t *__restrict__ A, const int32_t *__rest
     // ranges; if even the extreme corner products stay inside [P_LO, P_HI] (host-computed, conservative),
     // the clamp-free instantiation runs.  Same bits either way.
     constexpr bool DYN = (mulq.need_lo || mulq.need_hi) && (mulq.of == SAT_TCPL || mulq.of == SAT_SMGN);
-    constexpr bool PASS = DYN || Cfg::FP_MUL;
+    constexpr bool PASS = DYN || Cfg::FP_MUL || T::NARROW;
 
     for (uint32_t it = 0; inst < ngroups; inst += gridDim.x, ++it) {
         const int s = it & 1;
@@ -277,7 +282,8 @@ QB_DEV void gemul_tile_body(const int32_t *__restrict__ A, const int32_t *__rest
             issue(next, s ^ 1);                                   // stage s^1 was released by the barrier below
         }
         mbar_wait(&bars[s], (it >> 1) & 1);
-        int32_t *As = stage0 + (size_t)s * (T::STAGE_BYTES / 4);
+        unsigned char *stage = smem_raw + (size_t)s * T::STAGE_BYTES;
+        int32_t *As = T::NARROW ? (int32_t *)(smem_raw + 2 * T::STAGE_BYTES) : (int32_t *)stage;      // 32-bit operands the tiles read
         int32_t *Bs = As + T::G * T::A_WORDS;
         bool clamp = true;
         if constexpr (PASS) {
@@ -286,6 +292,28 @@ QB_DEV void gemul_tile_body(const int32_t *__restrict__ A, const int32_t *__rest
 #pragma unroll
             for (int part = 0; part < 2; ++part) {
                 int4 *w = (int4 *)(part ? Bs : As);
+                if constexpr (T::NARROW) {
+                    // packed int16 words: widen (sign-extend) into the 32-bit region, converting / scanning on the way
+                    const int4 *raw = (const int4 *)(stage + (part ? T::G * T::A_WORDS * 2 : 0));
+                    const int n8 = (part ? T::G * T::B_WORDS : T::G * T::A_WORDS) / 8;
+                    for (int i = tid; i < n8; i += T::BLOCK) {
+                        const int4 v = raw[i];
+                        const int e[8] = { (int)(short)(v.x & 0xffff), v.x >> 16, (int)(short)(v.y & 0xffff), v.y >> 16,
+                                           (int)(short)(v.z & 0xffff), v.z >> 16, (int)(short)(v.w & 0xffff), v.w >> 16 };
+                        if constexpr (DYN) {
+                            lo[part] = min3i(min3i(min3i(min3i(lo[part], e[0], e[1]), e[2], e[3]), e[4], e[5]), e[6], e[7]);
+                            hi[part] = max3i(max3i(max3i(max3i(hi[part], e[0], e[1]), e[2], e[3]), e[4], e[5]), e[6], e[7]);
+                        }
+                        if constexpr (Cfg::FP_MUL) {
+                            ((float4 *)w)[2 * i] = make_float4(__int2float_rn(e[0]), __int2float_rn(e[1]), __int2float_rn(e[2]), __int2float_rn(e[3]));
+                            ((float4 *)w)[2 * i + 1] = make_float4(__int2float_rn(e[4]), __int2float_rn(e[5]), __int2float_rn(e[6]), __int2float_rn(e[7]));
+                        } else {
+                            w[2 * i] = make_int4(e[0], e[1], e[2], e[3]);
+                            w[2 * i + 1] = make_int4(e[4], e[5], e[6], e[7]);
+                        }
+                    }
+                    continue;
+                }
                 constexpr int N4A = T::G * T::A_WORDS / 4, N4B = T::G * T::B_WORDS / 4;      // the whole group (a short last group leaves stale words: harmless, conservative for the ranges)
                 const int n4 = part ? N4B : N4A;
                 constexpr int PER = ((N4A > N4B ? N4A : N4B) + T::BLOCK - 1) / T::BLOCK;
@@ -368,7 +396,7 @@ QB_DEV void gemul_tile_body(const int32_t *__restrict__ A, const int32_t *__rest
 
 template <class Cfg>
 __global__ void __launch_bounds__(GemulTile<Cfg, 4, 4>::BLOCK, gemul_min_blocks(GemulTile<Cfg, 4, 4>::BLOCK, GemulTile<Cfg, 4, 4>::SMEM_BYTES))
-k_gemul_tile(const int32_t *__restrict__ A, const int32_t *__restrict__ B, int32_t *__restrict__ C, uint64_t batch)
+k_gemul_tile(const typename Cfg::WA *__restrict__ A, const typename Cfg::WB *__restrict__ B, int32_t *__restrict__ C, uint64_t batch)
 {
     gemul_tile_body<Cfg>(A, B, C, batch);
 }
@@ -394,7 +422,7 @@ static int launch_gemul_tile(const void *A, const void *B, void *C, uint64_t bat
     }
     const uint64_t ngroups = (batch + T::G - 1) / T::G;
     const unsigned grid = (unsigned)(ngroups < (uint64_t)grid_cap ? ngroups : (uint64_t)grid_cap);
-    k_gemul_tile<Cfg><<<grid, T::BLOCK, T::SMEM_BYTES, s>>>((const int32_t *)A, (const int32_t *)B, (int32_t *)C, batch);
+    k_gemul_tile<Cfg><<<grid, T::BLOCK, T::SMEM_BYTES, s>>>((const typename Cfg::WA *)A, (const typename Cfg::WB *)B, (int32_t *)C, batch);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) count_launch(1);
     return (int)e;

@@ -834,3 +834,25 @@ def test_batch_strides_on_the_specialised_kernels():
         ops.Qcgemul(Y, dev(H), dev(X), plan, batch=batch)
         assert np.array_equal(Y.cpu().numpy(), want), (M, N, K)
         assert ops.plan_info_cgemul(plan).kernel == kernel
+
+
+def test_packed_int16_operand_words_on_the_tile_template():
+    """qb_qdesc.word_bytes = 2: operands arrive as packed int16 words (half the HBM / PCIe bytes), are staged as they are
+    and widened by the conversion pass.  Same results as the oracle on the same packed buffers, and as the int32 call."""
+    rng = np.random.default_rng(1616)
+    a = QType(7, 8); mul = QType(14, 8, True, RND_CONV, SAT_TCPL)
+    lv = [QType(15 + l, 8 - l, True, RND_POS_INF, SAT_TCPL) for l in range(6)]; c = QType(17, 4, True, RND_POS_INF, SAT_TCPL)
+    for (M, N, K, batch, ta) in [(64, 64, 64, 9, False), (32, 32, 24, 7, True), (16, 16, 16, 37, False), (64, 32, 40, 5, False)]:
+        p16 = ops.make_gemul_plan(a, a, c, M, N, K, mul=mul, add=lv, word_bytes=(2, 2, 0), trans_a=ta)
+        p32 = ops.make_gemul_plan(a, a, c, M, N, K, mul=mul, add=lv, trans_a=ta)
+        A = rng.integers(a.raw_min, a.raw_max + 1, size=batch * M * K).astype(np.int16)
+        B = rng.integers(a.raw_min, a.raw_max + 1, size=batch * K * N).astype(np.int16)
+        A[:5] = a.raw_min; B[:5] = a.raw_min
+        want = oracle.gemul_batched(p16, A, B, batch)
+        C16 = torch.empty(batch * M * N, dtype=torch.int32, device="cuda")
+        ops.Qgemul(C16, dev(A), dev(B), p16, batch=batch)
+        assert np.array_equal(C16.cpu().numpy(), want), (M, N, K)
+        C32 = torch.empty_like(C16)
+        ops.Qgemul(C32, dev(A.astype(np.int32)), dev(B.astype(np.int32)), p32, batch=batch)
+        assert torch.equal(C16, C32)
+        assert ops.plan_info_gemul(p16).kernel == b"k_gemul_tile<jit>", (M, N, K)
