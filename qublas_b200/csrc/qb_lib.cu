@@ -909,23 +909,51 @@ __device__ __forceinline__ int64_t from_double_dev(double v, int frac, const QSt
 
 __global__ void k_quantize_f64(const double *__restrict__ in, void *__restrict__ out, uint64_t n, int wb, int frac, const __grid_constant__ QStage q)
 {
-    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x)
-        store_word<int64_t>(out, e, wb, from_double_dev(in[e], frac, q));
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e0 < n; e0 += 4 * stride) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const uint64_t e = e0 + u * stride; v[u] = e < n ? in[e] : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const uint64_t e = e0 + u * stride; if (e < n) store_word<int64_t>(out, e, wb, from_double_dev(v[u], frac, q)); }
+    }
 }
+// 2^-frac as a double (exact for |frac| <= 1022): multiplying by it is the exact scaling of toDouble (QuBLAS.h:2413-2416)
+__device__ __forceinline__ double pow2_neg(int frac) { return __longlong_as_double((long long)(1023 - frac) << 52); }
+
 __global__ void k_dequantize_f64(const void *__restrict__ in, double *__restrict__ out, uint64_t n, int wb, int frac)
 {
-    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x)
-        out[e] = scalbn((double)load_word<int64_t>(in, e, wb), -frac);
+    const double sc = pow2_neg(frac);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e0 < n; e0 += 4 * stride) {
+        int64_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const uint64_t e = e0 + u * stride; v[u] = e < n ? load_word<int64_t>(in, e, wb) : 0; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const uint64_t e = e0 + u * stride; if (e < n) out[e] = (wb <= 4 ? (double)(int)v[u] : (double)v[u]) * sc; }   // int32 -> double is one instruction
+    }
 }
 // fixed grid, fixed per-thread order, fixed tree: the sums are reproducible run to run
 __global__ void __launch_bounds__(256) k_err_stats(const void *__restrict__ w, const double *__restrict__ ref, uint64_t n, int wb, int frac, double *__restrict__ part)
 {
     __shared__ double s0[256], s1[256], s2[256];
-    double se = 0, sr = 0, mx = 0;
-    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) {
-        const double v = scalbn((double)load_word<int64_t>(w, e, wb), -frac), r = ref[e], d = v - r;
-        se += d * d; sr += r * r; mx = fmax(mx, fabs(d));
+    // four independent accumulation chains per thread (loads of four strided elements in flight), combined in a fixed order
+    double se4[4] = { 0, 0, 0, 0 }, sr4[4] = { 0, 0, 0, 0 }, mx = 0;
+    const double sc = pow2_neg(frac);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e0 < n; e0 += 4 * stride) {
+        int64_t wv[4]; double rv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const uint64_t e = e0 + u * stride; const bool ok = e < n; wv[u] = ok ? load_word<int64_t>(w, e, wb) : 0; rv[u] = ok ? ref[e] : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (e0 + u * stride < n) {
+                const double d = (wb <= 4 ? (double)(int)wv[u] : (double)wv[u]) * sc - rv[u];
+                se4[u] += d * d; sr4[u] += rv[u] * rv[u]; mx = fmax(mx, fabs(d));
+            }
+        }
     }
+    const double se = (se4[0] + se4[1]) + (se4[2] + se4[3]), sr = (sr4[0] + sr4[1]) + (sr4[2] + sr4[3]);
     s0[threadIdx.x] = se; s1[threadIdx.x] = sr; s2[threadIdx.x] = mx;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
@@ -989,7 +1017,7 @@ extern "C" int qb200_error_stats(const qb_qdesc *type, const void *words, const 
     stats->n = n;
     if (n == 0) return QB_OK;
     Ctx cx; int rc = cx.init(exec); if (rc) return rc;
-    const int wb = word_bytes(*type), nblocks = 592;
+    const int wb = word_bytes(*type), nblocks = 1184;
     const void *dw, *dr; void *part, *res;
     if ((rc = cx.in(words, n * wb, &dw)) || (rc = cx.in(ref, n * 8, &dr)) || (rc = cx.alloc(&part, 3 * nblocks * 8)) || (rc = cx.alloc(&res, 3 * 8))) return rc;
     k_err_stats<<<nblocks, 256, 0, cx.stream>>>(dw, (const double *)dr, n, wb, type->frac_bits, (double *)part);
