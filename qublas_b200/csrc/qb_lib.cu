@@ -962,11 +962,19 @@ __global__ void __launch_bounds__(256) k_err_stats(const void *__restrict__ w, c
     }
     if (threadIdx.x == 0) { part[3 * blockIdx.x] = s0[0]; part[3 * blockIdx.x + 1] = s1[0]; part[3 * blockIdx.x + 2] = s2[0]; }
 }
-__global__ void k_err_final(const double *__restrict__ part, int nblocks, double *__restrict__ out)
+// one block: thread t adds the partials t, t + 256, ... in order, then the same fixed tree as above
+__global__ void __launch_bounds__(256) k_err_final(const double *__restrict__ part, int nblocks, double *__restrict__ out)
 {
+    __shared__ double s0[256], s1[256], s2[256];
     double se = 0, sr = 0, mx = 0;
-    for (int i = 0; i < nblocks; i++) { se += part[3 * i]; sr += part[3 * i + 1]; mx = fmax(mx, part[3 * i + 2]); }
-    out[0] = se; out[1] = sr; out[2] = mx;
+    for (int i = threadIdx.x; i < nblocks; i += 256) { se += part[3 * i]; sr += part[3 * i + 1]; mx = fmax(mx, part[3 * i + 2]); }
+    s0[threadIdx.x] = se; s1[threadIdx.x] = sr; s2[threadIdx.x] = mx;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { s0[threadIdx.x] += s0[threadIdx.x + o]; s1[threadIdx.x] += s1[threadIdx.x + o]; s2[threadIdx.x] = fmax(s2[threadIdx.x], s2[threadIdx.x + o]); }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[0] = s0[0]; out[1] = s1[0]; out[2] = s2[0]; }
 }
 
 static int stage_for_type(const qb_qdesc &t, QStage *q, const char *what)
@@ -1022,7 +1030,7 @@ extern "C" int qb200_error_stats(const qb_qdesc *type, const void *words, const 
     if ((rc = cx.in(words, n * wb, &dw)) || (rc = cx.in(ref, n * 8, &dr)) || (rc = cx.alloc(&part, 3 * nblocks * 8)) || (rc = cx.alloc(&res, 3 * 8))) return rc;
     k_err_stats<<<nblocks, 256, 0, cx.stream>>>(dw, (const double *)dr, n, wb, type->frac_bits, (double *)part);
     if ((rc = post_launch("k_err_stats"))) return rc;
-    k_err_final<<<1, 1, 0, cx.stream>>>((const double *)part, nblocks, (double *)res);
+    k_err_final<<<1, 256, 0, cx.stream>>>((const double *)part, nblocks, (double *)res);
     if ((rc = post_launch("k_err_final"))) return rc;
     double h[3];
     CUDA_TRY(cudaMemcpyAsync(h, res, sizeof(h), cudaMemcpyDeviceToHost, cx.stream));
