@@ -260,7 +260,7 @@ public:
         int sh = 53 - e - F;                                // raw = mi * 2^(-sh)
         detail::i128 r;
         if (sh >= 0) r = detail::round_shift(mi, sh, QuM);
-        else if (-sh > 60) r = mi > 0 ? ((detail::i128)1 << 120) : -((detail::i128)1 << 120);
+        else if (-sh > 70) r = mi > 0 ? ((detail::i128)1 << 124) : -((detail::i128)1 << 124);   // beyond every 64-bit type, low 64 bits zero
         else r = detail::shl(mi, -sh);
         data.data = (raw_t)detail::overflow(r, spec);
     }

@@ -6,16 +6,31 @@ legs.  The product package (qublas_b200/) never imports this module.
 import ctypes as C
 import os
 import subprocess
-import sys
 
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.dirname(HERE))
-from qublas_b200 import abi  # noqa: E402  (POD struct definitions only)
-from qublas_b200.qtypes import QType, tree_out_type  # noqa: E402
 
 _LIB = None
+
+
+# The checker does not import the product: plans arrive as ctypes structures laid out like include/qb200.h (whoever built
+# them) and are passed by address; the few PODs the oracle has to build itself are mirrored here.
+class qb_qdesc(C.Structure):
+    _fields_ = [("int_bits", C.c_int16), ("frac_bits", C.c_int16), ("is_signed", C.c_uint8),
+                ("qu_mode", C.c_uint8), ("of_mode", C.c_uint8), ("word_bytes", C.c_uint8)]
+
+
+def _desc(t, word_bytes=0):
+    """qb_qdesc of a type given as an object with .i .f .s .q .o (e.g. qtypes.QType) or as a qb_qdesc-like structure."""
+    if hasattr(t, "int_bits"):
+        return qb_qdesc(t.int_bits, t.frac_bits, t.is_signed, t.qu_mode, t.of_mode, t.word_bytes)
+    return qb_qdesc(t.i, t.f, 1 if t.s else 0, t.q, t.o, word_bytes)
+
+
+def _word_bytes(d):
+    """storage word of a qb_qdesc: the explicit one, else the reference's natural word (QuBLAS.h:353)."""
+    return d.word_bytes or (4 if 1 + d.int_bits + d.frac_bits <= 32 else 8)
 
 
 def build():
@@ -31,18 +46,18 @@ def load():
     global _LIB
     if _LIB is None:
         L = C.CDLL(build())
-        i64, u64, u32, vp, qd = C.c_int64, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(abi.qb_qdesc)
+        i64, u64, u32, vp, qd = C.c_int64, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(qb_qdesc)
         L.qbo_conv_i64.restype = i64; L.qbo_conv_i64.argtypes = [i64, C.c_int, qd]
         L.qbo_conv_i128.restype = i64; L.qbo_conv_i128.argtypes = [i64, u64, C.c_int, qd]
         for f in (L.qbo_qmul_i64, L.qbo_qadd_i64, L.qbo_qsub_i64):
             f.restype = i64; f.argtypes = [i64, qd, i64, qd, qd]
-        L.qbo_reduce_out_type.argtypes = [C.POINTER(abi.qb_reduce_plan), qd]
-        L.qbo_reduce_batched.argtypes = [C.POINTER(abi.qb_reduce_plan), vp, vp, vp, u32, u64]
-        L.qbo_gemul_batched.argtypes = [C.POINTER(abi.qb_gemul_plan), vp, vp, vp, u64]
-        L.qbo_cgemul_batched.argtypes = [C.POINTER(abi.qb_cgemul_plan), vp, vp, vp, u64]
-        L.qbo_tfcmul_batched.argtypes = [C.POINTER(abi.qb_tfcmul_plan), vp, vp, vp, u64]
-        L.qbo_convert_batched.argtypes = [C.POINTER(abi.qb_convert_plan), vp, vp, u64]
-        L.qbo_elementwise_batched.argtypes = [C.POINTER(abi.qb_ew_plan), vp, vp, vp, u64]
+        L.qbo_reduce_out_type.argtypes = [vp, qd]
+        L.qbo_reduce_batched.argtypes = [vp, vp, vp, vp, u32, u64]
+        L.qbo_gemul_batched.argtypes = [vp, vp, vp, vp, u64]
+        L.qbo_cgemul_batched.argtypes = [vp, vp, vp, vp, u64]
+        L.qbo_tfcmul_batched.argtypes = [vp, vp, vp, vp, u64]
+        L.qbo_convert_batched.argtypes = [vp, vp, vp, u64]
+        L.qbo_elementwise_batched.argtypes = [vp, vp, vp, vp, u64]
         L.qbo_synth_fill.argtypes = [vp, u64, u32, i64, i64, u64, u64, u64]
         dp = C.POINTER(C.c_double)
         L.qbo_from_double.restype = i64; L.qbo_from_double.argtypes = [C.c_double, qd]
@@ -62,35 +77,34 @@ def np_dtype(word_bytes):
     return {1: np.int8, 2: np.int16, 4: np.int32, 8: np.int64}[word_bytes]
 
 
-def conv(raw, from_frac, to: QType):
-    return load().qbo_conv_i64(int(raw), int(from_frac), C.byref(abi.desc(to)))
+def conv(raw, from_frac, to):
+    return load().qbo_conv_i64(int(raw), int(from_frac), C.byref(_desc(to)))
 
 
-def conv128(raw, from_frac, to: QType):
+def conv128(raw, from_frac, to):
     raw = int(raw)
     lo = raw & ((1 << 64) - 1)
     hi = raw >> 64
-    return load().qbo_conv_i128(hi, lo, int(from_frac), C.byref(abi.desc(to)))
+    return load().qbo_conv_i128(hi, lo, int(from_frac), C.byref(_desc(to)))
 
 
 def qmul(a, ta, b, tb, to):
-    return load().qbo_qmul_i64(int(a), C.byref(abi.desc(ta)), int(b), C.byref(abi.desc(tb)), C.byref(abi.desc(to)))
+    return load().qbo_qmul_i64(int(a), C.byref(_desc(ta)), int(b), C.byref(_desc(tb)), C.byref(_desc(to)))
 
 
 def qadd(a, ta, b, tb, to):
-    return load().qbo_qadd_i64(int(a), C.byref(abi.desc(ta)), int(b), C.byref(abi.desc(tb)), C.byref(abi.desc(to)))
+    return load().qbo_qadd_i64(int(a), C.byref(_desc(ta)), int(b), C.byref(_desc(tb)), C.byref(_desc(to)))
 
 
 def qsub(a, ta, b, tb, to):
-    return load().qbo_qsub_i64(int(a), C.byref(abi.desc(ta)), int(b), C.byref(abi.desc(tb)), C.byref(abi.desc(to)))
+    return load().qbo_qsub_i64(int(a), C.byref(_desc(ta)), int(b), C.byref(_desc(tb)), C.byref(_desc(to)))
 
 
-def reduce_batched(plan: abi.qb_reduce_plan, x: np.ndarray, batch: int, partial_level=None):
+def reduce_batched(plan, x: np.ndarray, batch: int, partial_level=None):
     """Returns (out, partials|None); out dtype = natural word of the result type."""
-    elem = abi.qtype_of(plan.elem)
-    lv = [abi.qtype_of(plan.levels.lv[i]) for i in range(plan.levels.n)]
-    ot = tree_out_type(int(plan.len), elem, lv, int(plan.tree_form))
-    out = np.zeros(batch, dtype=np_dtype(ot.word_bytes))
+    ot = qb_qdesc()
+    assert load().qbo_reduce_out_type(C.byref(plan), C.byref(ot)) == 0
+    out = np.zeros(batch, dtype=np_dtype(_word_bytes(ot)))
     partials = None
     pl = 0
     if partial_level is not None:
@@ -105,9 +119,8 @@ def reduce_batched(plan: abi.qb_reduce_plan, x: np.ndarray, batch: int, partial_
     return out, partials
 
 
-def gemul_batched(plan: abi.qb_gemul_plan, A, B, batch):
-    c = abi.qtype_of(plan.c)
-    wb = plan.c.word_bytes or c.word_bytes
+def gemul_batched(plan, A, B, batch):
+    wb = _word_bytes(plan.c)
     Cc = np.zeros(batch * plan.M * plan.N if plan.stride_c == plan.M * plan.N else (batch - 1) * plan.stride_c + plan.M * plan.N,
                   dtype=np_dtype(wb))
     A = np.ascontiguousarray(A); B = np.ascontiguousarray(B)
@@ -116,12 +129,11 @@ def gemul_batched(plan: abi.qb_gemul_plan, A, B, batch):
     return Cc
 
 
-def cword_bytes(re: abi.qb_qdesc, im: abi.qb_qdesc):
-    f = lambda d: d.word_bytes or abi.qtype_of(d).word_bytes
-    return max(f(re), f(im))
+def cword_bytes(re, im):
+    return max(_word_bytes(re), _word_bytes(im))
 
 
-def cgemul_batched(plan: abi.qb_cgemul_plan, A, B, batch):
+def cgemul_batched(plan, A, B, batch):
     wb = cword_bytes(plan.c_re, plan.c_im)
     Cc = np.zeros(2 * batch * plan.M * plan.N, dtype=np_dtype(wb))
     A = np.ascontiguousarray(A); B = np.ascontiguousarray(B)
@@ -130,9 +142,10 @@ def cgemul_batched(plan: abi.qb_cgemul_plan, A, B, batch):
     return Cc
 
 
-def tfcmul_batched(plan: abi.qb_tfcmul_plan, x, y, batch):
-    re_t, im_t = {abi.QB_CPROD_TF: (plan.tf.AB, plan.tf.BC), abi.QB_CPROD_BASIC: (plan.bcm.acbd, plan.bcm.adbc),
-                  abi.QB_CPROD_REAL_A: (plan.bcm.ac, plan.bcm.ad), abi.QB_CPROD_REAL_B: (plan.bcm.ac, plan.bcm.bc)}[plan.product]
+def tfcmul_batched(plan, x, y, batch):
+    # enum qb_cproduct (include/qb200.h): 0 = TF, 1 = BASIC, 2 = REAL_A, 3 = REAL_B
+    re_t, im_t = {0: (plan.tf.AB, plan.tf.BC), 1: (plan.bcm.acbd, plan.bcm.adbc),
+                  2: (plan.bcm.ac, plan.bcm.ad), 3: (plan.bcm.ac, plan.bcm.bc)}[plan.product]
     wb = cword_bytes(re_t, im_t)
     out = np.zeros(2 * batch * plan.len, dtype=np_dtype(wb))
     x = np.ascontiguousarray(x); y = np.ascontiguousarray(y)
@@ -141,9 +154,8 @@ def tfcmul_batched(plan: abi.qb_tfcmul_plan, x, y, batch):
     return out
 
 
-def convert_batched(plan: abi.qb_convert_plan, x, batch):
-    to = abi.qtype_of(plan.to)
-    out = np.zeros(batch * plan.len, dtype=np_dtype(plan.to.word_bytes or to.word_bytes))
+def convert_batched(plan, x, batch):
+    out = np.zeros(batch * plan.len, dtype=np_dtype(_word_bytes(plan.to)))
     x = np.ascontiguousarray(x)
     rc = load().qbo_convert_batched(C.byref(plan), _ptr(x), _ptr(out), batch)
     assert rc == 0, rc
@@ -157,34 +169,33 @@ def synth_fill(count, word_bytes, lo, hi, seed, stream_id, first_index=0):
     return out
 
 
-def from_double(v, t: QType):
-    return load().qbo_from_double(float(v), C.byref(abi.desc(t)))
+def from_double(v, t):
+    return load().qbo_from_double(float(v), C.byref(_desc(t)))
 
 
-def quantize_f64(t: QType, x):
+def quantize_f64(t, x):
     x = np.ascontiguousarray(x, dtype=np.float64)
-    out = np.zeros(x.size, dtype=np_dtype(t.word_bytes))
-    assert load().qbo_quantize_f64(C.byref(abi.desc(t)), _ptr(x), _ptr(out), x.size) == 0
+    out = np.zeros(x.size, dtype=np_dtype(_word_bytes(_desc(t))))
+    assert load().qbo_quantize_f64(C.byref(_desc(t)), _ptr(x), _ptr(out), x.size) == 0
     return out
 
 
-def dequantize_f64(t: QType, w):
+def dequantize_f64(t, w):
     w = np.ascontiguousarray(w)
     out = np.zeros(w.size, dtype=np.float64)
-    assert load().qbo_dequantize_f64(C.byref(abi.desc(t)), _ptr(w), _ptr(out), w.size) == 0
+    assert load().qbo_dequantize_f64(C.byref(_desc(t)), _ptr(w), _ptr(out), w.size) == 0
     return out
 
 
-def error_stats(t: QType, w, ref):
+def error_stats(t, w, ref):
     w = np.ascontiguousarray(w); ref = np.ascontiguousarray(ref, dtype=np.float64)
     a, b, c = C.c_double(), C.c_double(), C.c_double()
-    assert load().qbo_error_stats(C.byref(abi.desc(t)), _ptr(w), _ptr(ref), w.size, C.byref(a), C.byref(b), C.byref(c)) == 0
+    assert load().qbo_error_stats(C.byref(_desc(t)), _ptr(w), _ptr(ref), w.size, C.byref(a), C.byref(b), C.byref(c)) == 0
     return a.value, b.value, c.value
 
 
-def elementwise(plan: abi.qb_ew_plan, a, b, batch=1):
-    to = abi.qtype_of(plan.to)
-    out = np.zeros(batch * plan.len, dtype=np_dtype(plan.to.word_bytes or to.word_bytes))
+def elementwise(plan, a, b, batch=1):
+    out = np.zeros(batch * plan.len, dtype=np_dtype(_word_bytes(plan.to)))
     a = np.ascontiguousarray(a); b = np.ascontiguousarray(b)
     assert load().qbo_elementwise_batched(C.byref(plan), _ptr(a), _ptr(b), _ptr(out), batch) == 0
     return out

@@ -471,8 +471,8 @@ int64_t qbo_from_double(double v, const qb_qdesc *t)
     int sh = 53 - e - t->frac_bits;                                           /* raw = mi * 2^-sh */
     i128 r;
     if (sh >= 0) r = sh > 120 ? ((t->qu_mode == QB_TRN_TCPL && mi < 0) ? -1 : 0) : qbo_round(mi, sh, t->qu_mode);
-    else if (-sh > 60) r = mi > 0 ? ((i128)1 << 120) : -((i128)1 << 120);
-    else r = shl128(mi, -sh);
+    else if (-sh > 70) r = mi > 0 ? ((i128)1 << 124) : -((i128)1 << 124);   /* beyond every <= 64-bit type; low 64 bits are zero */
+    else r = shl128(mi, -sh);                                                 /* |mi| < 2^53: exact below 2^123 */
     return (int64_t)qbo_ovf(r, *t);
 }
 int qbo_quantize_f64(const qb_qdesc *t, const double *in, void *out, uint64_t n)

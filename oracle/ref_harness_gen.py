@@ -349,6 +349,17 @@ def fromdouble_cases(rng):
     return cases
 
 
+def fromdouble64_cases(rng):
+    """Round 2: Qu_s(double) into 64-bit-wide targets (intBits + fracBits = 63) and neighbours, with |v| around 2^62..2^64
+    in units of the target's lsb -- the band where a 64-bit implementation must decide the overflow on the exact value."""
+    cases = []
+    for (i, f) in ((63, 0), (40, 23), (62, 0), (50, 13)):
+        for q in (0, 1, 2, 3, 5, 6):
+            for o in range(4):
+                cases.append({"kind": "fromdouble", "to": T(i, f, True, q, o), "big": True})
+    return cases
+
+
 def cgemul_cases(rng):
     cases = []
     for (K, half) in [(4, False), (8, True), (16, False), (5, False)]:
@@ -547,6 +558,17 @@ def _dbits(x):
 
 def gen_inputs(rng, c):
     k = c["kind"]
+    if k == "fromdouble" and c.get("big"):
+        t = c["to"]
+        ulp = 2.0 ** (-t["f"])
+        W = t["i"] + t["f"]                       # value bits; max raw = 2^W - 1
+        mags = [2.0 ** (W - 1), 2.0 ** (W - 1) + 2.0 ** (W - 40), 2.0 ** W - 2.0 ** (W - 52), 2.0 ** W, 2.0 ** W + 2.0 ** (W - 50),
+                1.5 * 2.0 ** W, 2.0 ** (W + 1) - 2.0 ** (W - 51), 2.0 ** (W + 1), 3.0 * 2.0 ** (W + 1), 2.0 ** (W + 7), 2.0 ** (W + 30), 1e30, 1e300]
+        mags += [rng.uniform(2.0 ** (W - 2), 2.0 ** (W + 2)) for _ in range(10)]
+        vals = []
+        for m in mags:
+            vals += [m * ulp, -m * ulp]
+        return [[_dbits(v)] for v in vals]
     if k == "fromdouble":
         t = c["to"]
         ulp = 2.0 ** (-t["f"])
@@ -660,7 +682,10 @@ def text_goldens():
 def main():
     if "--text" in sys.argv[1:]:
         return text_goldens()
-    if "--rc" in sys.argv[1:]:              # added later: own seed, own fixture, the earlier fixtures stay byte-identical
+    if "--fd64" in sys.argv[1:]:            # round 2: 64-bit-wide Qu_s(double) targets; own seed, own fixture
+        rng = random.Random(20261020)
+        cases = fromdouble64_cases(rng)
+    elif "--rc" in sys.argv[1:]:            # added later: own seed, own fixture, the earlier fixtures stay byte-identical
         rng = random.Random(20261019)
         cases = rc_cases(rng)
     else:
@@ -678,7 +703,7 @@ def main():
         rec = dict(c)
         rec["inputs"] = ins
         rec["outputs"] = outs
-        fixtures.setdefault("wide" if c.get("wide") else ("rc" if c["kind"] == "rcgemul" else c["kind"]), []).append(rec)
+        fixtures.setdefault("wide" if c.get("wide") else ("fromdouble64" if c.get("big") else ("rc" if c["kind"] == "rcgemul" else c["kind"])), []).append(rec)
     for kind, recs in fixtures.items():
         path = os.path.join(GOLD_DIR, "ref_%s.json" % kind)
         with open(path, "w") as f:

@@ -534,12 +534,14 @@ extern "C" int qb200_gemul_batched(const qb_gemul_plan *plan, const void *A, con
     }
     // one launch over n instances laid out with the given strides
     auto launch = [&](const void *dA, const void *dB, void *dC, uint64_t n, int64_t sa, int64_t sb, int64_t sc, cudaStream_t st) -> int {
-        if (f && sa == (int64_t)ea && sb == (int64_t)eb && sc == (int64_t)ec) {
+        // the specialised kernels stage operands with cp.async.bulk and store C as int4: 16-byte aligned buffers only
+        const bool aligned16 = !(((uintptr_t)dA | (uintptr_t)dB | (uintptr_t)dC) & 15);
+        if (f && aligned16 && sa == (int64_t)ea && sb == (int64_t)eb && sc == (int64_t)ec) {
             int e = f->launch(dA, dB, dC, n, st);
             if (e) return fail(QB_ECUDA, std::string(f->name) + " launch failed: " + cudaGetErrorString((cudaError_t)e));
             return QB_OK;
         }
-        if (jk && sa == plan->stride_a && sb == plan->stride_b && sc == plan->stride_c && !((uintptr_t)dA & 15) && !((uintptr_t)dB & 15) && !((uintptr_t)dC & 15)) {
+        if (jk && aligned16 && sa == plan->stride_a && sb == plan->stride_b && sc == plan->stride_c) {
             int e = jit_launch_gemul(*jk, dA, dB, dC, n, st);
             if (e) return fail(QB_ECUDA, jk->name + " launch failed (CUresult " + std::to_string(e) + ")");
             return QB_OK;
@@ -627,10 +629,11 @@ extern "C" int qb200_cgemul_batched(const qb_cgemul_plan *plan, const void *A, c
     if ((!f || !dense_plan) && !(cx.flags & QB_F_NO_SPECIALIZE)) {                  // run-time specialised kernels carry the plan's strides
         jk = ce->jit.get([&] { return jit_cgemul(*plan, gp, bits); });
     }
-    if (f && dense_plan) {
+    const bool aligned16 = !(((uintptr_t)dA | (uintptr_t)dB | (uintptr_t)dC) & 15);      // vector loads / stores of {re, im} pairs
+    if (f && dense_plan && aligned16) {
         rc = f->launch(dA, dB, dC, batch, cx.stream);
         if (rc) return fail(QB_ECUDA, std::string(f->name) + " launch failed: " + cudaGetErrorString((cudaError_t)rc));
-    } else if (jk && !((uintptr_t)dA & 15) && !((uintptr_t)dB & 15) && !((uintptr_t)dC & 15)) {      // vector loads of {re, im} pairs
+    } else if (jk && aligned16) {
         int e = jit_launch_gemul(*jk, dA, dB, dC, batch, cx.stream);
         if (e) return fail(QB_ECUDA, jk->name + " launch failed (CUresult " + std::to_string(e) + ")");
     } else {
@@ -899,10 +902,27 @@ __device__ __forceinline__ int64_t from_double_dev(double v, int frac, const QSt
         if (sh >= 62) {                                                  // |mi| < 2^53 << 2^(sh-1): everything but floor of a negative gives 0
             r = (q.qu == TRN_TCPL && mi < 0) ? -1 : 0;
         } else r = q_round<int64_t>(mi, sh, q.qu);
-    } else if (-sh > 9) {                                                // far outside any <= 64-bit type: saturate before the shift can overflow
-        r = mi > 0 ? INT64_MAX : INT64_MIN;
-        if (q.of == WRP_TCPL) r = (-sh >= 64) ? 0 : (int64_t)((uint64_t)mi << (-sh));   // wrap keeps the low bits
-    } else r = (int64_t)((uint64_t)mi << (-sh));
+    } else if (-sh <= 10) {                                              // |mi| < 2^53: the shifted value still fits 64 bits
+        r = (int64_t)((uint64_t)mi << (-sh));
+    } else {
+        // beyond 64 bits: decide the overflow on the exact value (a 64-bit-wide target holds e.g. -2^63 exactly, and
+        // SAT::ZERO must see "out of range", not a pre-clamped bound)
+        bool over = true;
+        int64_t low = 0;                                                 // low 64 bits of the exact value (what WRP::TCPL keeps)
+        if (-sh < 64) {
+            const __int128 w = (__int128)mi << (-sh);
+            low = (int64_t)(uint64_t)w;
+            over = w > (__int128)q.hi || w < (__int128)q.lo;
+        }
+        if (over) {
+            switch (q.of) {
+            case SAT_TCPL: case SAT_SMGN: return mi > 0 ? q.hi : q.lo;
+            case SAT_ZERO: return 0;
+            default: { QStage o = q; o.need_lo = 1; o.need_hi = 1; return q_ovf<int64_t, false>(low, o); }
+            }
+        }
+        r = low;
+    }
     QStage o = q; o.need_lo = 1; o.need_hi = 1;
     return q_ovf<int64_t, false>(r, o);
 }

@@ -153,9 +153,25 @@ def make_gemul_plan(a: QType, b: QType, c: QType, M: int, N: int, K: int, *, mul
     return p
 
 
+def _numel(x):
+    return x.numel() if _is_torch(x) else x.size
+
+
+def _check_operand(x, desc, words_per_elem, batch, stride, per_instance, what):
+    """Raw-word buffer of a batched operand: word size of the plan's type, long enough for (batch-1)*stride + one instance."""
+    wb = desc.word_bytes or abi.qtype_of(desc).word_bytes
+    _check_words(x, wb, what)
+    need = words_per_elem * ((batch - 1) * stride + per_instance) if batch > 0 else 0
+    if _numel(x) < need:
+        raise ValueError("%s: buffer holds %d words, the plan needs %d" % (what, _numel(x), need))
+
+
 def Qgemul(Cbuf, A, B, plan: abi.qb_gemul_plan, batch: int = 1, flags: int = 0):
     """Qgemul<AddArgs, MulArgs, TransposedA>(C, A, B): out-parameter first, like the reference."""
     lib = abi.load()
+    _check_operand(A, plan.a, 1, batch, plan.stride_a, plan.M * plan.K, "A")
+    _check_operand(B, plan.b, 1, batch, plan.stride_b, plan.K * plan.N, "B")
+    _check_operand(Cbuf, plan.c, 1, batch, plan.stride_c, plan.M * plan.N, "C")
     ex = _exec_for(Cbuf, A, B, flags=flags)
     abi.check(lib.qb200_gemul_batched(C.byref(plan), _ptr(A), _ptr(B), _ptr(Cbuf), batch, C.byref(ex)))
     return Cbuf
@@ -188,8 +204,20 @@ def make_cgemul_plan(a_re: QType, a_im: QType, b_re: QType, b_im: QType, c_re: Q
     return p
 
 
+def _cdesc(re, im):
+    """Complex buffers are AoS pairs; both parts use the wider of the two natural words (qb200.h)."""
+    wb = max(re.word_bytes or abi.qtype_of(re).word_bytes, im.word_bytes or abi.qtype_of(im).word_bytes)
+    d = abi.qb_qdesc()
+    d.int_bits, d.frac_bits, d.is_signed, d.qu_mode, d.of_mode, d.word_bytes = re.int_bits, re.frac_bits, re.is_signed, re.qu_mode, re.of_mode, wb
+    return d
+
+
 def Qcgemul(Cbuf, A, B, plan: abi.qb_cgemul_plan, batch: int = 1, flags: int = 0):
     lib = abi.load()
+    real_a, real_b = plan.product == abi.QB_CPROD_REAL_A, plan.product == abi.QB_CPROD_REAL_B
+    _check_operand(A, plan.a_re if real_a else _cdesc(plan.a_re, plan.a_im), 1 if real_a else 2, batch, plan.stride_a, plan.M * plan.K, "A")
+    _check_operand(B, plan.b_re if real_b else _cdesc(plan.b_re, plan.b_im), 1 if real_b else 2, batch, plan.stride_b, plan.K * plan.N, "B")
+    _check_operand(Cbuf, _cdesc(plan.c_re, plan.c_im), 2, batch, plan.stride_c, plan.M * plan.N, "C")
     ex = _exec_for(Cbuf, A, B, flags=flags)
     abi.check(lib.qb200_cgemul_batched(C.byref(plan), _ptr(A), _ptr(B), _ptr(Cbuf), batch, C.byref(ex)))
     return Cbuf

@@ -80,3 +80,14 @@ def rc_targs(t):
     if t["mode"] == "pair":
         return (qt(t["re"]), qt(t["im"]))
     return {"realT": qt(t["re"]), "imagT": qt(t["im"])}
+
+
+def fd64_defect_band(v, t: QType):
+    """True when a double -> Qu conversion falls into the reference's defect band: with a SAT OfMode, a rounded raw value
+    of magnitude in [2^63, 2^64) is compared against the bounds through the low 64-bit word only (SURVEY.md 2.3 item 4,
+    QuBLAS.h:1792) and comes back as its truncated two's-complement word instead of the saturated bound.  The library and
+    the oracle implement the documented behaviour (saturate); the band is excluded from the parity domain."""
+    if t.o == 3:                                  # WRP::TCPL keeps the low bits either way: reference == ideal model
+        return False
+    raw = abs(v) * 2.0 ** t.f
+    return 2.0 ** 63 * (1 - 2.0 ** -40) <= raw <= 2.0 ** 64 * (1 + 2.0 ** -40)

@@ -212,3 +212,33 @@ def test_jit_disk_cache(tmp_path, monkeypatch):
     assert len(files) == 1 and os.path.getsize(os.path.join(tmp_path, files[0])) > 1000
     t0 = time.time(); assert lib.qb200_jit_check_gemul(ctypes.byref(plan), log, 8192) == 0; warm = time.time() - t0
     assert warm < cold and [f for f in os.listdir(tmp_path) if f.endswith(".cubin")] == files
+    # the file carries a verified header (NVRTC version, source length, second hash, cubin length): a stale, foreign or
+    # truncated file under the same name is recompiled and replaced instead of being loaded
+    path = os.path.join(tmp_path, files[0])
+    good = open(path, "rb").read()
+    assert good[:8] == b"QB200JC2"
+    for bad in (good[:len(good) // 2], good[:24] + bytes([good[24] ^ 1]) + good[25:], b"\x7fELF" + good[4:], good + b"x"):
+        open(path, "wb").write(bad)
+        assert lib.qb200_jit_check_gemul(ctypes.byref(plan), log, 8192) == 0
+        assert open(path, "rb").read() == good
+
+
+def test_python_wrappers_validate_buffers():
+    """a wrong dtype or a short buffer is a ValueError, not an out-of-bounds device access."""
+    a = QType(7, 8)
+    plan = ops.make_gemul_plan(a, a, QType(17, 4), 8, 8, 8, mul=QType(14, 8), add=[QType(20, 8)])
+    ok = np.zeros(2 * 64, dtype=np.int32)
+    with pytest.raises(ValueError):
+        ops.Qgemul(ok.copy(), ok.astype(np.int16), ok, plan, batch=2)            # int16 words under a natural (4-byte) plan
+    with pytest.raises(ValueError):
+        ops.Qgemul(ok.copy(), ok[:100], ok, plan, batch=2)                         # A too short for two instances
+    with pytest.raises(ValueError):
+        ops.Qgemul(ok[:64].copy(), ok, ok, plan, batch=2)                          # C too short
+    with pytest.raises(ValueError):
+        ops.Qgemul(ok.astype(np.float32), ok, ok, plan, batch=2)
+    t = QType(3, 12)
+    cplan = ops.make_cgemul_plan(t, t, t, t, t, t, 4, 1, 4, product="basic")
+    with pytest.raises(ValueError):
+        ops.Qcgemul(np.zeros(8, dtype=np.int32), np.zeros(16, dtype=np.int32), np.zeros(8, dtype=np.int32), cplan)   # A needs 32 words
+    with pytest.raises(ValueError):
+        ops.Qcgemul(np.zeros(8, dtype=np.int64), np.zeros(32, dtype=np.int32), np.zeros(8, dtype=np.int32), cplan)

@@ -856,3 +856,36 @@ def test_packed_int16_operand_words_on_the_tile_template():
         ops.Qgemul(C32, dev(A.astype(np.int32)), dev(B.astype(np.int32)), p32, batch=batch)
         assert torch.equal(C16, C32)
         assert ops.plan_info_gemul(p16).kernel == b"k_gemul_tile<jit>", (M, N, K)
+
+
+def test_unaligned_buffers_fall_back_to_word_access_kernels():
+    """the specialised kernels stage operands with bulk copies and store 16-byte vectors; a buffer that is only
+    word-aligned (a slice offset by one word) must take the word-access kernels and give the same bits."""
+    a = QType(7, 8)
+    mul = QType(14, 8, True, RND_CONV, SAT_TCPL)
+    lv = [QType(15 + l, 8 - l, True, RND_POS_INF, SAT_TCPL) for l in range(6)]
+    c = QType(17, 4, True, RND_POS_INF, SAT_TCPL)
+    plan = ops.make_gemul_plan(a, a, c, 64, 64, 64, mul=mul, add=lv)
+    batch = 5
+    n = batch * 4096
+    for offs in ((1, 0, 0), (0, 2, 0), (0, 0, 3), (1, 1, 1)):
+        bufs = [torch.zeros(n + 4, dtype=torch.int32, device="cuda") for _ in range(3)]
+        A, B, Cd = (b[o:o + n] for b, o in zip(bufs, offs))
+        ops.synth_fill(A, a.raw_min, a.raw_max, 7, 0); ops.synth_fill(B, a.raw_min, a.raw_max, 7, 1)
+        ops.Qgemul(Cd, A, B, plan, batch=batch)
+        want = oracle.gemul_batched(plan, A.cpu().numpy(), B.cpu().numpy(), batch)
+        assert np.array_equal(Cd.cpu().numpy(), want), offs
+    # complex mat-vec (config-4 types): {re, im} pairs, buffers offset by one complex element (8 bytes)
+    t = QType(3, 12); P = QType(6, 12); S = QType(7, 12)
+    tags = {"abT": QType(4, 12), "cdT": QType(4, 11), "abcT": P, "cdbT": P, "badT": P, "ABT": S, "BCT": S}
+    lvc = [QType(8 + l, 12 - l, True, RND_CONV, SAT_TCPL) for l in range(8)]
+    cplan = ops.make_cgemul_plan(t, t, t, t, lvc[-1], lvc[-1], 256, 1, 256, tf_tags=tags, add_re=lvc, form=TREE_VARIADIC)
+    nb = 3
+    Hb = torch.zeros(nb * 256 * 256 * 2 + 8, dtype=torch.int32, device="cuda"); xb = torch.zeros(nb * 512 + 8, dtype=torch.int32, device="cuda")
+    yb = torch.zeros(nb * 512 + 8, dtype=torch.int32, device="cuda")
+    for o in (2, 1):                                  # 8-byte aligned only, then 4-byte aligned only
+        H, xv, y = Hb[o:o + nb * 256 * 256 * 2], xb[o:o + nb * 512], yb[o:o + nb * 512]
+        ops.synth_fill(H, -(1 << 14), (1 << 14) - 1, 3, 0); ops.synth_fill(xv, -(1 << 14), (1 << 14) - 1, 3, 1)
+        ops.Qcgemul(y, H, xv, cplan, batch=nb)
+        want = oracle.cgemul_batched(cplan, H.cpu().numpy(), xv.cpu().numpy(), nb)
+        assert np.array_equal(y.cpu().numpy(), want), o

@@ -28,6 +28,26 @@ def test_quantize_matches_reference_goldens():
     assert n >= 1200
 
 
+def test_quantize_64bit_wide_targets_match_reference_goldens():
+    """Qu_s(double) into 64-bit-wide targets, |raw| around 2^62..2^64 and far beyond (the overflow decision must
+    be made on the exact value): reference goldens outside the reference's own defect band, the oracle everywhere."""
+    from tests.helpers import fd64_defect_band
+    n = 0
+    for c in load_cases("ref_fromdouble64.json"):
+        t = qt(c["to"])
+        x = np.array([struct.unpack("<d", struct.pack("<q", i[0]))[0] for i in c["inputs"]], dtype=np.float64)
+        got = [int(v) for v in ops.quantize(torch.from_numpy(x).cuda(), t).cpu().numpy()]
+        assert got == [int(v) for v in oracle.quantize_f64(t, x)], c["to"]
+        for v, g, o in zip(x, got, c["outputs"]):
+            if not fd64_defect_band(float(v), t):
+                assert g == o[0], (c["to"], v)
+                n += 1
+    assert n >= 3300
+    t = QType(63, 0)                                   # the ADVICE example: 2^62 is representable, not saturated
+    assert int(ops.quantize(torch.tensor([2.0 ** 62, -2.0 ** 63], dtype=torch.float64).cuda(), t).cpu()[0]) == 2 ** 62
+    assert int(ops.quantize(torch.tensor([-2.0 ** 63], dtype=torch.float64).cuda(), t).cpu()[0]) == -2 ** 63
+
+
 @pytest.mark.parametrize("mem", ["device", "host"])
 def test_quantize_dequantize_vs_oracle_all_modes(mem):
     rng = np.random.default_rng(12)

@@ -238,3 +238,22 @@ def test_readme_reductions():
     a = oracle.qadd(8, type1, 2, type2, type1)
     r3 = oracle.qadd(a, type1, a, type1, type1)
     assert r3 / 8 == 34
+
+
+def test_from_double_matches_reference():
+    """Qu_s(double) (QuBLAS.h:2387-2393): the round-1 goldens, and the round-2 goldens for 64-bit-wide targets with
+    |raw| around 2^62..2^64 (outside the reference's defect band, see helpers.fd64_defect_band)."""
+    import struct
+    from tests.helpers import fd64_defect_band
+    n = skipped = 0
+    for name in ("ref_fromdouble.json", "ref_fromdouble64.json"):
+        for c in load_cases(name):
+            t = qt(c["to"])
+            for i, o in zip(c["inputs"], c["outputs"]):
+                v = struct.unpack("<d", struct.pack("<q", i[0]))[0]
+                if c.get("big") and fd64_defect_band(v, t):
+                    skipped += 1
+                    continue
+                assert oracle.from_double(v, t) == o[0], (c["to"], v)
+                n += 1
+    assert n >= 4500 and skipped < 1300
