@@ -32,6 +32,10 @@ M = N = K = 64
 MACS_PER_INSTANCE = M * N * K
 WORDS = M * K                      # words per matrix (all three are 64x64)
 METRIC = "bit-exact quantized GMAC/s, batched Qgemul (64x64x64, 16-bit operands, per-product + per-level quantization)"
+METRICS = {"c3": METRIC,
+           "c2": "bit-exact Qreduce throughput, 2^24-element Qu<8,8> vectors, 24-level TypeList (RND::POS_INF)",
+           "c4": "bit-exact TFComplexMul (3-mult/5-add) complex mat-vec throughput, batched 256x256",
+           "c5": "bit-exact Qgemul 8192^3, int8-range operands, lossless accumulators (tcgen05 kind::i8), incl. int32->int8 pack"}
 
 
 def c3_types():
@@ -46,50 +50,190 @@ def c3_types():
 # ------------------------------------------------------------------------------------------------
 # CPU baseline: the reference's own implementation (oracle/_ref) or, if absent, the oracle port
 # ------------------------------------------------------------------------------------------------
+WORKLOADS = {
+    "c3": "BASELINE config 3: batched 64x64x64 Qgemul, 16-bit signed operands Qu<7,8>, MulArgs Qu<14,8,RND::CONV,SAT::TCPL>, "
+          "6-level TypeList tree RND::POS_INF, C Qu<17,4>",
+    "c2": "BASELINE config 2 (C2b): Qreduce of 2^24 x Qu<8,8>, 24-level TypeList (RND::POS_INF), batch of 16 vectors (1 GiB, > L2)",
+    "c4": "BASELINE config 4: batched 256x256 complex mat-vec, TFComplexMul with mixed abT/cdT types, 8-level RND::CONV tree",
+    "c5": "BASELINE config 5: 8192^3 Qgemul, A,B Qu<7,0> raws in [-128,127], MulArgs Qu<15,0>, AddArgs Qu<30,0>, C Qu<30,0>",
+}
+
+
+_REF_PICK = None
+
+
+def ref_lib_path():
+    """oracle/_ref = the unmodified reference header compiled in the container that has it (oracle/Makefile).  Two builds
+    travel: x86-64-v4 (AVX-512; what -march=native gives on the Xeon hosts) and x86-64-v3.  Both are timed once on a few
+    config-3 instances and the faster one that this CPU can run is used (the reference arm gets its best build)."""
+    global _REF_PICK
+    if _REF_PICK is not None:
+        return _REF_PICK
+    if os.environ.get("QB_REF_SO"):
+        _REF_PICK = (os.environ["QB_REF_SO"], os.environ.get("QB_REF_BUILD", "?"))
+        return _REF_PICK
+    d = os.path.join(ROOT, "oracle", "_ref")
+    try:
+        flags = set(open("/proc/cpuinfo").read().split("flags")[1].split("\n")[0].split())
+    except Exception:
+        flags = set()
+    cands = []
+    v4 = os.path.join(d, "libqref_bench_v4.so")
+    if {"avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"} <= flags and os.path.exists(v4):
+        cands.append((v4, "-O3 -march=x86-64-v4"))
+    v3 = os.path.join(d, "libqref_bench.so")
+    if os.path.exists(v3):
+        cands.append((v3, "-O3 -march=x86-64-v3"))
+    if not cands:
+        _REF_PICK = (None, None)
+        return _REF_PICK
+    if len(cands) > 1:
+        import numpy as np
+        from oracle import oracle
+        a = c3_types()[0]
+        A = oracle.synth_fill(4 * WORDS, 4, a.raw_min, a.raw_max, 1, 0); B = oracle.synth_fill(4 * WORDS, 4, a.raw_min, a.raw_max, 1, 1)
+        Cc = np.zeros(4 * WORDS, dtype=np.int32)
+        vp = ctypes.c_void_p
+        best = None
+        for so, build in cands:
+            lib = ctypes.CDLL(so)
+            lib.qref_c3_gemul.argtypes = [vp, vp, vp, ctypes.c_int]
+            dt = 1e9
+            for _ in range(3):
+                t0 = time.perf_counter(); lib.qref_c3_gemul(A.ctypes.data_as(vp), B.ctypes.data_as(vp), Cc.ctypes.data_as(vp), 4)
+                dt = min(dt, time.perf_counter() - t0)
+            if best is None or dt < best[0]:
+                best = (dt, so, build)
+        _REF_PICK = (best[1], best[2])
+    else:
+        _REF_PICK = cands[0]
+    os.environ["QB_REF_SO"], os.environ["QB_REF_BUILD"] = _REF_PICK
+    return _REF_PICK
+
+
+def c4_types():
+    from qublas_b200.qtypes import QType, RND_CONV, SAT_TCPL
+    t = QType(3, 12); P = QType(6, 12); S = QType(7, 12)
+    tags = {"abT": QType(4, 12), "cdT": QType(4, 11), "abcT": P, "cdbT": P, "badT": P, "ABT": S, "BCT": S}
+    lv = [QType(8 + l, 12 - l, True, RND_CONV, SAT_TCPL) for l in range(8)]
+    return t, tags, lv
+
+
+def c2_types():
+    from qublas_b200.qtypes import QType, RND_POS_INF, SAT_TCPL
+    elem = QType(8, 8)
+    lv = [QType(9 + l, 8 - l, True, RND_POS_INF, SAT_TCPL) for l in range(8)]
+    lv += [QType(17 + (l - 6) // 2, 0, True, RND_POS_INF, SAT_TCPL) for l in range(8, 24)]      # C2b: 24-entry list
+    return elem, lv
+
+
 def _cpu_worker(args):
-    kind, first, count, reps = args
+    """One host core: `count` units of workload `w` starting at unit `first` of the synthetic stream, `reps` times.
+    Returns (seconds, checksum).  kind "reference" = oracle/_ref (the reference's own code), "port" = the C oracle."""
+    w, kind, first, count, reps = args
     import numpy as np
     from oracle import oracle
-    a, mul, lv, c = c3_types()
-    A = oracle.synth_fill(count * WORDS, 4, a.raw_min, a.raw_max, 1, 0, first * WORDS)
-    B = oracle.synth_fill(count * WORDS, 4, a.raw_min, a.raw_max, 1, 1, first * WORDS)
-    Cc = np.zeros(count * WORDS, dtype=np.int32)
+    vp = ctypes.c_void_p
+    lib = None
     if kind == "reference":
-        lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libqref_bench.so"))
-        vp = ctypes.c_void_p
-        lib.qref_c3_gemul.argtypes = [vp, vp, vp, ctypes.c_int]
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            lib.qref_c3_gemul(A.ctypes.data_as(vp), B.ctypes.data_as(vp), Cc.ctypes.data_as(vp), count)
-        dt = time.perf_counter() - t0
-    else:
+        lib = ctypes.CDLL(ref_lib_path()[0])
+    if w == "c3":
+        a, mul, lv, c = c3_types()
+        A = oracle.synth_fill(count * WORDS, 4, a.raw_min, a.raw_max, 1, 0, first * WORDS)
+        B = oracle.synth_fill(count * WORDS, 4, a.raw_min, a.raw_max, 1, 1, first * WORDS)
+        Cc = np.zeros(count * WORDS, dtype=np.int32)
+        if lib is not None:
+            lib.qref_c3_gemul.argtypes = [vp, vp, vp, ctypes.c_int]
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                lib.qref_c3_gemul(A.ctypes.data_as(vp), B.ctypes.data_as(vp), Cc.ctypes.data_as(vp), count)
+            dt = time.perf_counter() - t0
+        else:
+            from qublas_b200 import ops
+            plan = ops.make_gemul_plan(a, a, c, M, N, K, mul=mul, add=lv)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                Cc = oracle.gemul_batched(plan, A, B, count)
+            dt = time.perf_counter() - t0
+        return dt, int(Cc[:64].astype(np.int64).sum())
+    if w == "c4":
         from qublas_b200 import ops
-        plan = ops.make_gemul_plan(a, a, c, M, N, K, mul=mul, add=lv)
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            Cc = oracle.gemul_batched(plan, A, B, count)
-        dt = time.perf_counter() - t0
-    return dt, int(Cc[:64].astype(np.int64).sum())
+        from qublas_b200.qtypes import TREE_VARIADIC
+        t, tags, lv = c4_types()
+        H = oracle.synth_fill(count * 256 * 256 * 2, 4, -(1 << 14), (1 << 14) - 1, 1, 0, first * 256 * 256 * 2)
+        x = oracle.synth_fill(count * 512, 4, -(1 << 14), (1 << 14) - 1, 1, 1, first * 512)
+        y = np.zeros(count * 512, dtype=np.int32)
+        if lib is not None:
+            lib.qref_c4_matvec.argtypes = [vp, vp, vp, ctypes.c_int]
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                lib.qref_c4_matvec(H.ctypes.data_as(vp), x.ctypes.data_as(vp), y.ctypes.data_as(vp), count)
+            dt = time.perf_counter() - t0
+        else:
+            plan = ops.make_cgemul_plan(t, t, t, t, lv[-1], lv[-1], 256, 1, 256, tf_tags=tags, add_re=lv, form=TREE_VARIADIC)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                y = oracle.cgemul_batched(plan, H, x, count)
+            dt = time.perf_counter() - t0
+        return dt, int(y[:64].astype(np.int64).sum())
+    if w == "c2":                      # a unit = one 2^24-element vector
+        from qublas_b200 import ops
+        elem, lv = c2_types()
+        n = 1 << 24
+        out = np.zeros(1, dtype=np.int32)
+        dt = 0.0
+        for v in range(count):
+            xv = oracle.synth_fill(n, 4, elem.raw_min, elem.raw_max, 1, 0, (first + v) * n)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                if lib is not None:
+                    lib.qref_c2_chain.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp]
+                    assert lib.qref_c2_chain(xv.ctypes.data_as(vp), 1, 0, out.ctypes.data_as(vp), None) == 0
+                else:
+                    out, _ = oracle.reduce_batched(ops.make_reduce_plan(elem, lv, n), xv, 1)
+            dt += time.perf_counter() - t0
+        return dt, int(out[0])
+    raise ValueError(w)
+
+
+# units and work per unit of each workload (metric numerator)
+UNIT_WORK = {"c3": MACS_PER_INSTANCE, "c4": 256 * 256, "c2": 1 << 24}
+UNIT_NAME = {"c3": "instances", "c4": "instances", "c2": "vectors"}
+UNIT_OUT = {"c3": "GMAC/s", "c4": "G complex-MAC/s", "c2": "Gelem/s"}
 
 
 def cpu_kind():
-    return "reference" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libqref_bench.so")) else "port"
+    return "reference" if ref_lib_path()[0] else "port"
 
 
-def cpu_rate(per_core_instances, cores, kind):
-    """All-core throughput (GMAC/s) on a bounded sample: every core runs `per_core_instances`
-    distinct instances of the workload (fork, one process per core — the reference is not
-    thread-safe)."""
+def cpu_rate(w, per_core_units, cores, kind):
+    """All-core throughput (G work-items/s) on a bounded sample: every core runs `per_core_units` distinct units of the
+    workload (fork, one process per core -- the reference is not thread-safe)."""
     import multiprocessing as mp
     ctx = mp.get_context("fork")
-    jobs = [(kind, r * per_core_instances, per_core_instances, 1) for r in range(cores)]
+    jobs = [(w, kind, r * per_core_units, per_core_units, 1) for r in range(cores)]
     t0 = time.perf_counter()
     with ctx.Pool(cores) as pool:
         res = pool.map(_cpu_worker, jobs)
     wall = time.perf_counter() - t0
     busy = max(r[0] for r in res)
-    total = per_core_instances * cores * MACS_PER_INSTANCE
+    total = per_core_units * cores * UNIT_WORK[w]
     return total / busy / 1e9, wall
+
+
+def cpu_baseline(w, seconds):
+    """cpu_baseline object: the reference's own CPU path on all host cores, ~`seconds` of work per core."""
+    from oracle import oracle
+    oracle.build()
+    kind = cpu_kind()
+    cores = os.cpu_count() or 1
+    probe = {"c3": 4 if kind == "reference" else 1, "c4": 1, "c2": 1}[w]
+    t1, _ = _cpu_worker((w, kind, 0, probe, 1))
+    per_core = max(1, int(seconds / (t1 / probe)))
+    g, wall = cpu_rate(w, per_core, cores, kind)
+    return {"value": g, "unit": UNIT_OUT[w], "cores": cores, "kind": kind,
+            "build": ref_lib_path()[1] if kind == "reference" else "gcc -O2 (C oracle)",
+            "sample": "%d %s/core x %d cores (%.1f s wall) of the same synthetic stream" % (per_core, UNIT_NAME[w], cores, wall)}
 
 
 def run_reference(args):
@@ -98,29 +242,41 @@ def run_reference(args):
         return
     from oracle import oracle
     oracle.build()
+    w = args.workload
+    if w not in UNIT_WORK:
+        print(json.dumps({"impl": "reference", "unavailable": "no CPU reference arm for workload %s (the header cannot instantiate it)" % w}), flush=True)
+        return
     kind = cpu_kind()
     cores = os.cpu_count() or 1
     # calibrate on one core, then size a step for ~2.5 s of all-core work
-    t, _ = _cpu_worker((kind, 0, 4 if kind == "reference" else 1, 1))
-    per_inst = t / (4 if kind == "reference" else 1)
-    per_core = max(1, int(2.5 / per_inst))
+    probe = {"c3": 4 if kind == "reference" else 1, "c4": 1, "c2": 1}[w]
+    t, _ = _cpu_worker((w, kind, 0, probe, 1))
+    per_core = max(1, int(2.5 / (t / probe)))
     vals = []
     for step in range(args.warmup + args.steps):
-        g, _ = cpu_rate(per_core, cores, kind)
+        g, _ = cpu_rate(w, per_core, cores, kind)
         if step >= args.warmup:
             vals.append(g)
     value = statistics.mean(vals)
-    sample = "%d instances/core x %d cores per step (bounded sample of the %d-instance batch)" % (per_core, cores, args.batch)
+    sample = "%d %s/core x %d cores per step (bounded sample of the workload)" % (per_core, UNIT_NAME[w], cores)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "GMAC/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * per_core * cores * MACS_PER_INSTANCE / (value * 1e9),
+        "impl": "reference", "metric": METRICS[w], "value": value, "unit": UNIT_OUT[w], "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * per_core * cores * UNIT_WORK[w] / (value * 1e9),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": "BASELINE config 3: batched 64x64x64 Qgemul, 16-bit signed operands, CPU reference path",
-                   "batch_per_gpu": args.batch},
-        "cpu_baseline": {"value": value, "unit": "GMAC/s", "cores": cores, "kind": kind, "sample": sample},
-        "e2e": {"value": value, "unit": "GMAC/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": workload_config(w, args),
+        "cpu_baseline": {"value": value, "unit": UNIT_OUT[w], "cores": cores, "kind": kind,
+                         "build": ref_lib_path()[1] if kind == "reference" else "gcc -O2 (C oracle)", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT_OUT[w], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def workload_config(w, args):
+    """The part of `config` that both arms print identically (the driver compares it)."""
+    cfg = {"workload": WORKLOADS[w]}
+    if w == "c3":
+        cfg["batch_per_gpu"] = args.batch
+    return cfg
 
 
 # ------------------------------------------------------------------------------------------------
@@ -277,15 +433,30 @@ def run_ours(args):
     ops.synth_fill(A, a.raw_min, a.raw_max, 1, 0, first * WORDS)
     ops.synth_fill(B, a.raw_min, a.raw_max, 1, 1, first * WORDS)
 
-    # ---- parity spot check on this rank's first and last instances (not timed) ----
+    # ---- parity check (not timed): >= 512 full instances of this rank -- the first, the last, and evenly strided ones in
+    # between -- bit for bit against the oracle ----
     from oracle import oracle
     ops.Qgemul(Cd, A, B, plan, batch=Bn)
     torch.cuda.synchronize()
-    for inst in (0, Bn - 1):
-        sl = slice(inst * WORDS, (inst + 1) * WORDS)
-        want = oracle.gemul_batched(plan, A[sl].cpu().numpy(), B[sl].cpu().numpy(), 1)
-        if not np.array_equal(Cd[sl].cpu().numpy(), want):
-            raise SystemExit("bench.py: GPU result differs from the oracle on instance %d of rank %d" % (inst, rank))
+    n_chk = min(Bn, args.check_instances)
+    picks = sorted({0, Bn - 1} | {int(i * (Bn - 1) / max(n_chk - 1, 1)) for i in range(n_chk)})
+    idx = torch.tensor(picks, dtype=torch.int64, device=dev)
+    gA = A.view(Bn, WORDS).index_select(0, idx).cpu().numpy(); gB = B.view(Bn, WORDS).index_select(0, idx).cpu().numpy()
+    gC = Cd.view(Bn, WORDS).index_select(0, idx).cpu().numpy()
+
+    def _check(lo_hi):
+        lo, hi = lo_hi
+        want = oracle.gemul_batched(plan, gA[lo:hi].reshape(-1), gB[lo:hi].reshape(-1), hi - lo)      # ctypes releases the GIL
+        return np.array_equal(gC[lo:hi].reshape(-1), want)
+
+    from concurrent.futures import ThreadPoolExecutor
+    nthr = max(1, min(16, (os.cpu_count() or 1) // world))
+    cuts = [(i * len(picks) // nthr, (i + 1) * len(picks) // nthr) for i in range(nthr)]
+    with ThreadPoolExecutor(nthr) as pool:
+        oks = list(pool.map(_check, [c for c in cuts if c[1] > c[0]]))
+    if not all(oks):
+        raise SystemExit("bench.py: GPU result differs from the oracle on rank %d" % rank)
+    checked = "%d full instances per rank (first, last, evenly strided) vs the oracle, all ranks" % len(picks)
 
     # ---- device-resident timing: K steps, one C-ABI call per step ----
     for _ in range(args.warmup):
@@ -389,9 +560,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "GMAC/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
-            "config": {"workload": "BASELINE config 3: batched 64x64x64 Qgemul, 16-bit signed operands Qu<7,8>, "
-                                   "MulArgs Qu<14,8,RND::CONV,SAT::TCPL>, 6-level TypeList tree RND::POS_INF, C Qu<17,4>",
-                       "batch_per_gpu": Bn, "sharding": "batch, no data-path collective", "kernel": info.kernel.decode(),
+            "config": {**workload_config("c3", args), "sharding": "batch, no data-path collective", "kernel": info.kernel.decode(),
                        "l2": "inputs (%.1f GB per GPU) are far larger than the 126 MB L2; no flush needed" % (2 * Bn * WORDS * 4 / 1e9),
                        "e2e_host_ring": "%d pinned slots x %d instances, reused cyclically; %d instances per e2e step" % (slots, chunk, e2e_instances),
                        "cpu_affinity": affinity},
@@ -406,18 +575,10 @@ def run_ours(args):
                     "d2h_bytes_per_step": world * e2e_instances * WORDS * 4, "scope": "whole job (all ranks)"},
             "gpu_launches": launches,
             "e2e_packed16": e2e16,
-            "bit_exact_checked": "first and last instance of every rank vs oracle",
+            "bit_exact_checked": checked,
         }
         if world == 1 and not args.no_cpu:
-            oracle.build()
-            kind = cpu_kind()
-            cores = os.cpu_count() or 1
-            t1, _ = _cpu_worker((kind, 0, 4 if kind == "reference" else 1, 1))
-            per_inst = t1 / (4 if kind == "reference" else 1)
-            per_core = max(1, int(12.0 / per_inst))
-            g, wall = cpu_rate(per_core, cores, kind)
-            line["cpu_baseline"] = {"value": g, "unit": "GMAC/s", "cores": cores, "kind": kind,
-                                    "sample": "%d instances/core x %d cores (%.1f s wall) of the same synthetic batch" % (per_core, cores, wall)}
+            line["cpu_baseline"] = cpu_baseline("c3", 12.0)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -489,9 +650,7 @@ def run_secondary(args):
 
     if w == "c2":
         n, batch = 1 << 24, 16
-        elem = QType(8, 8)
-        lv = [QType(9 + l, 8 - l, True, RND_POS_INF, SAT_TCPL) for l in range(8)]
-        lv += [QType(17 + (l - 7 + 1) // 2, 0, True, RND_POS_INF, SAT_TCPL) for l in range(8, 24)]      # C2b: 24-entry list
+        elem, lv = c2_types()
         x = torch.empty(batch * n, dtype=torch.int32, device=dev)
         ops.synth_fill(x, elem.raw_min, elem.raw_max, 1, 0)
         out, _ = ops.Qreduce(x, elem, lv, length=n, batch=batch)
@@ -507,23 +666,15 @@ def run_secondary(args):
         hx = torch.empty(n, dtype=torch.int32).pin_memory(); hx.copy_(x[:n]); hxn = hx.numpy()
         e2e_s = wall(lambda: ops.Qreduce(hxn, elem, lv))
         e2e = {"value": n / e2e_s / 1e9, "unit": unit, "h2d_bytes_per_step": n * 4, "d2h_bytes_per_step": 4}
-        cfg = {"workload": "BASELINE config 2 (C2b): Qreduce of 2^24 x Qu<8,8>, per-level TypeList, batch of 16 vectors (1 GiB, > L2)",
+        cfg = {"workload": WORKLOADS["c2"],
                "kernel": ops.plan_info_reduce(ops.make_reduce_plan(elem, lv, n)).kernel.decode() + " (2 chained passes)"}
 
         def cpu():
-            libr = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libqref_bench.so"))
-            nb = 1 << 15
-            xs = x[:nb * 512].cpu().numpy(); o = np.zeros(nb, dtype=np.int32)
-            vp = ctypes.c_void_p
-            t0 = time.perf_counter(); libr.qref_c2_reduce512(xs.ctypes.data_as(vp), o.ctypes.data_as(vp), nb); dt = time.perf_counter() - t0
-            return {"value": nb * 512 / dt / 1e9, "unit": unit, "cores": 1, "kind": "reference",
-                    "sample": "2^15 blocks of 512 elements through the header's vector-form Qreduce (levels 0-8 = 99.8% of the adds), 1 core"}
+            return cpu_baseline("c2", 4.0)
     elif w == "c4":
         Mm = Kk = 256
         batch = args.batch if args.batch != 1000000 else 8192
-        t = QType(3, 12); P = QType(6, 12); S = QType(7, 12)
-        tags = {"abT": QType(4, 12), "cdT": QType(4, 11), "abcT": P, "cdbT": P, "badT": P, "ABT": S, "BCT": S}
-        lv = [QType(8 + l, 12 - l, True, RND_CONV, SAT_TCPL) for l in range(8)]
+        t, tags, lv = c4_types()
         plan = ops.make_cgemul_plan(t, t, t, t, lv[-1], lv[-1], Mm, 1, Kk, tf_tags=tags, add_re=lv, form=TREE_VARIADIC)
         info = ops.plan_info_cgemul(plan)
         H = torch.empty(batch * Mm * Kk * 2, dtype=torch.int32, device=dev); xv = torch.empty(batch * Kk * 2, dtype=torch.int32, device=dev)
@@ -544,12 +695,11 @@ def run_secondary(args):
         hy = torch.empty(nb * Mm * 2, dtype=torch.int32).pin_memory()
         e2e_s = wall(lambda: ops.Qcgemul(hy.numpy(), hH.numpy(), hx.numpy(), plan, batch=nb))
         e2e = {"value": nb * Mm * Kk / e2e_s / 1e9, "unit": unit, "h2d_bytes_per_step": nb * (Mm * Kk + Kk) * 8, "d2h_bytes_per_step": nb * Mm * 8}
-        cfg = {"workload": "BASELINE config 4: batched 256x256 complex mat-vec, TFComplexMul with mixed abT/cdT types, 8-level RND::CONV tree",
+        cfg = {"workload": WORKLOADS["c4"],
                "batch": batch, "kernel": info.kernel.decode()}
 
         def cpu():
-            t0 = time.perf_counter(); oracle.cgemul_batched(plan, H[:4 * Mm * Kk * 2].cpu().numpy(), xv[:4 * Kk * 2].cpu().numpy(), 4); dt = time.perf_counter() - t0
-            return {"value": 4 * Mm * Kk / dt / 1e9, "unit": unit, "cores": 1, "kind": "port", "sample": "4 instances through the C oracle, 1 core"}
+            return cpu_baseline("c4", 8.0)
     else:  # c5
         Mm = Kk = 8192
         Nn = 8192 // world          # column panel of B and C per GPU (contiguous in column-major storage); A is replicated
@@ -588,7 +738,7 @@ def run_secondary(args):
         hC = torch.empty(Mm * Nn, dtype=torch.int32).pin_memory()
         e2e_s = wall(lambda: ops.Qgemul(hC.numpy(), hA.numpy(), hB.numpy(), plan))
         e2e = {"value": ops_total / e2e_s / 1e12, "unit": unit, "h2d_bytes_per_step": 2 * Mm * Kk * 4, "d2h_bytes_per_step": Mm * Nn * 4}
-        cfg = {"workload": "BASELINE config 5: 8192^3 Qgemul, A,B Qu<7,0> raws in [-128,127], MulArgs Qu<15,0>, AddArgs Qu<30,0>, C Qu<30,0>",
+        cfg = {"workload": WORKLOADS["c5"],
                "kernel": info.kernel.decode(), "sharding": "column panels of B and C (%d columns per GPU), A replicated, no collective" % Nn}
 
         def cpu():
@@ -631,6 +781,7 @@ def main():
     ap.add_argument("--no-packed16", action="store_true", help="skip the supplementary packed-int16 end-to-end measurement")
     ap.add_argument("--e2e-instances", type=int, default=1000000, help="instances per end-to-end step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--check-instances", type=int, default=512, help="instances per rank compared with the oracle before timing")
     ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5"],
                     help="c3 = headline (batched 64^3 Qgemul); c2 = Qreduce 2^24; c4 = TFComplexMul 256x256 mat-vec; c5 = 8192^3 tcgen05 i8")
     args = ap.parse_args()

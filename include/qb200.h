@@ -259,6 +259,13 @@ int qb200_jit_check_gemul(const qb_gemul_plan *plan, char *log, uint64_t log_cap
  * Returns 0 = cubin produced, 1 = no template applies to this plan, -1 = NVRTC failed (log filled), < -1 = plan error. */
 int qb200_jit_check(int what, const void *plan, char *log, uint64_t log_cap);
 
+/* Diagnostic / parity evidence: exhaustive sweep of the quantizers that the specialised kernels of a plan run on the FP32
+ * pipe (Qmul as one FFMA with a magic constant, exact FADD pre-adds) against the integer form (Qmul_s::mul / Qadd_s::add,
+ * include/QuBLAS.h:3146-3235), over EVERY pair of operand raw values the plan's types admit (config 3: all 2^32 pairs,
+ * with and without the per-instance clamp elision; config 4: a+b, b-a and the three TFComplexMul products).
+ * what: 0 = qb_gemul_plan, 1 = qb_cgemul_plan.  checked = pairs compared (0: the plan uses no FP-pipe quantizer). */
+int qb200_selftest_fp(int what, const void *plan, uint64_t *checked, uint64_t *mismatches, const qb_exec *exec);
+
 /* Contiguous shard [first, first+count) of `total` units for `rank` of `world` (batch or M-panel). */
 int qb200_shard_range(uint64_t total, uint32_t world, uint32_t rank, uint64_t *first, uint64_t *count);
 

@@ -1,4 +1,4 @@
-// ref_bench.cpp — the reference's OWN CPU implementation of the benchmark configs.
+// ref_bench.cpp — the reference's OWN CPU implementation of BASELINE config 3 (ref_bench_c2.cpp / ref_bench_c4.cpp: configs 2, 4).
 // TEST / BASELINE INFRASTRUCTURE.  Compiled (oracle/Makefile, target `ref`) against the unmodified
 // header where it lies (/root/reference/include/QuBLAS.h); the output oracle/_ref/libqref_bench.so
 // is git-ignored and travels to the GPU box.  Nothing from the reference is copied into this repo.
@@ -41,18 +41,3 @@ extern "C" void qref_c3_gemul(const int32_t *A, const int32_t *B, int32_t *C, in
     }
 }
 
-namespace c2 {   // BASELINE config 2 building block: vector-form Qreduce over 512 elements (header limit is 1000)
-using e_t = Qu<intBits<8>, fracBits<8>>;
-template <int l> using lv = Qu<intBits<9 + l>, fracBits<8 - l>, QuMode<RND::POS_INF>, OfMode<SAT::TCPL>>;
-using list = TypeList<lv<0>, lv<1>, lv<2>, lv<3>, lv<4>, lv<5>, lv<6>, lv<7>>;
-}
-extern "C" void qref_c2_reduce512(const int32_t *x, int32_t *out, int n_blocks)
-{
-    using namespace c2;
-    static Qu<dim<512>, e_t> v;
-    for (int b = 0; b < n_blocks; b++) {
-        for (int i = 0; i < 512; i++) v[i].data.data = x[(size_t)b * 512 + i];
-        auto r = Qreduce<list>(v);
-        out[b] = r.data.data;
-    }
-}

@@ -45,6 +45,33 @@ static unsigned ilog2(uint64_t n) { unsigned l = 0; while (((uint64_t)1 << (l + 
 
 static const char *word_t(int wb) { return wb == 1 ? "int8_t" : wb == 2 ? "int16_t" : wb == 4 ? "int32_t" : "int64_t"; }
 
+static bool fp_mul_ok(const QStage &q, const TVal &x, const TVal &y);
+
+// Does the register-tile template run Qmul<MulArgs> of this plan as one FFMA (qb_device.cuh:fp_mul_apply)?
+bool gemul_fp_mul(const qb_gemul_plan &p, const GemulProg &g)
+{
+    const int s = g.mul.shift;
+    const Ival ra = type_range(p.a), rb = type_range(p.b);
+    const i128 c4[4] = { ra.lo * rb.lo, ra.lo * rb.hi, ra.hi * rb.lo, ra.hi * rb.hi };
+    i128 lo = c4[0], hi = c4[0];
+    for (int i = 1; i < 4; i++) { if (c4[i] < lo) lo = c4[i]; if (c4[i] > hi) hi = c4[i]; }
+    const bool mode_ok = g.mul.qu == RND_CONV || g.mul.qu == TRN_TCPL;
+    const i128 mag = (hi > -lo ? hi : -lo);
+    const bool ops_ok = width(p.a) <= 24 && width(p.b) <= 24;
+    const bool of_ok = g.mul.of == SAT_TCPL || g.mul.of == SAT_SMGN;
+    return s >= 1 && s <= 30 && mode_ok && ops_ok && of_ok && !g.mul.wide && mag <= ((i128)1 << (22 + s));
+}
+
+// Conservative product thresholds for the per-instance clamp elision (qb_fast_gemul.cuh): an instance whose extreme
+// corner products stay inside [p_lo, p_hi] cannot reach Qmul's saturation bounds, because
+// round(p) <= floor(p / 2^s) + 1 and round(p) >= floor(p / 2^s).
+void gemul_clamp_thresholds(const GemulProg &g, long long *p_hi, long long *p_lo)
+{
+    const int s = g.mul.shift;
+    if (s > 0) { *p_hi = (long long)(((i128)g.mul.hi << s) - 1); *p_lo = (long long)((i128)g.mul.lo << s); }
+    else       { *p_hi = g.mul.hi >> (-s); *p_lo = -((-(g.mul.lo)) >> (-s)); }
+}
+
 std::string emit_gemul_cfg(const std::string &name, const qb_gemul_plan &p, const GemulProg &g, int group)
 {
     std::ostringstream o;
@@ -68,20 +95,9 @@ std::string emit_gemul_cfg(const std::string &name, const qb_gemul_plan &p, cons
     // [2^(23+s), 2^(24+s)] around the magic constant.
     {
         const int s = g.mul.shift;
-        const Ival ra = type_range(p.a), rb = type_range(p.b);
-        const i128 c4[4] = { ra.lo * rb.lo, ra.lo * rb.hi, ra.hi * rb.lo, ra.hi * rb.hi };
-        i128 lo = c4[0], hi = c4[0];
-        for (int i = 1; i < 4; i++) { if (c4[i] < lo) lo = c4[i]; if (c4[i] > hi) hi = c4[i]; }
-        const bool mode_ok = g.mul.qu == RND_CONV || g.mul.qu == TRN_TCPL;
-        const i128 mag = (hi > -lo ? hi : -lo);
-        const bool ops_ok = width(p.a) <= 24 && width(p.b) <= 24;
-        const bool of_ok = g.mul.of == SAT_TCPL || g.mul.of == SAT_SMGN;
-        const bool fp = s >= 1 && s <= 30 && mode_ok && ops_ok && of_ok && !g.mul.wide && mag <= ((i128)1 << (22 + s));
-        // conservative product thresholds for the per-instance clamp elision (qb_fast_gemul.cuh):
-        // round(p) <= floor(p / 2^s) + 1 and round(p) >= floor(p / 2^s)
+        const bool fp = gemul_fp_mul(p, g);
         long long p_hi, p_lo;
-        if (s > 0) { p_hi = (long long)(((i128)g.mul.hi << s) - 1); p_lo = (long long)((i128)g.mul.lo << s); }
-        else       { p_hi = g.mul.hi >> (-s); p_lo = -((-(g.mul.lo)) >> (-s)); }
+        gemul_clamp_thresholds(g, &p_hi, &p_lo);
         o << "  static constexpr long long P_HI = " << p_hi << "LL, P_LO = " << p_lo << "LL;\n";
         o << "  static constexpr bool FP_MUL = " << (fp ? "true" : "false") << ";\n";
         o << "  static constexpr int FP_SHIFT = " << (s > 0 ? s : 1) << ";\n";
@@ -180,6 +196,30 @@ static bool fp_mul_ok(const QStage &q, const TVal &x, const TVal &y)
     return lo >= -((i128)1 << 30) && hi <= ((i128)1 << 30);
 }
 
+// Which nodes of the TFComplexMul dataflow the mat-vec rows template runs on the FP32 pipe (qb_fast_cgemv.cuh).
+CgemulFp cgemul_fp(const qb_cgemul_plan &p, const CGemulProg &g)
+{
+    CgemulFp f;
+    // FP32-FMA quantizer for the three TF products where it is exact
+    Analysis an; TVal re, im, mid[3];
+    TVal a = { p.a_re, type_range(p.a_re) }, b = { p.a_im, type_range(p.a_im) }, c = { p.b_re, type_range(p.b_re) }, d = { p.b_im, type_range(p.b_im) };
+    build_tf(a, b, c, d, p.tf, &re, &im, an, mid);
+    f.fa = fp_mul_ok(g.tf.A, mid[0], c); f.fb = fp_mul_ok(g.tf.B, mid[1], b); f.fc = fp_mul_ok(g.tf.C, mid[2], d);
+    // The pre-adds a + b and b - a feed those products as floats.  When the stage is an exact add (no alignment,
+    // no rounding shift) whose only other effect is a SAT::TCPL clamp, and both operands are exact floats below 2^23,
+    // the add itself runs on the FP pipe (FADD is exact below 2^24, the clamp is min/max on floats) and one
+    // int->float conversion per product disappears.
+    auto fadd_ok = [](const AddStage &s, const TVal &x, const TVal &y) {
+        auto small = [](const Ival &r) { return r.lo >= -((i128)1 << 23) && r.hi <= ((i128)1 << 23); };
+        return !s.shl_a && !s.shl_b && s.q.shift == 0 && !s.q.wrap_bits && !s.q.wide && (s.q.of == SAT_TCPL || (!s.q.need_lo && !s.q.need_hi)) &&
+               small(x.r) && small(y.r) && s.q.lo >= -(1LL << 24) && s.q.hi <= (1LL << 24);
+    };
+    f.fadd_ab = f.fa && fadd_ok(g.tf.ab, a, b);
+    f.fadd_ba = f.fc && fadd_ok(g.tf.ba, b, a);
+    f.ab = mid[0].r; f.cd = mid[1].r; f.ba = mid[2].r;
+    return f;
+}
+
 std::string emit_cgemul_cfg(const std::string &name, const qb_cgemul_plan &p, const CGemulProg &g)
 {
     std::ostringstream o;
@@ -197,24 +237,10 @@ std::string emit_cgemul_cfg(const std::string &name, const qb_cgemul_plan &p, co
     o << emit_levels("lvl_re", g.tree_re, ilog2(p.K));
     o << emit_levels("lvl_im", g.tree_im, ilog2(p.K));
     {
-        // FP32-FMA quantizer for the three TF products where it is exact
-        Analysis an; TVal re, im, mid[3];
-        TVal a = { p.a_re, type_range(p.a_re) }, b = { p.a_im, type_range(p.a_im) }, c = { p.b_re, type_range(p.b_re) }, d = { p.b_im, type_range(p.b_im) };
-        build_tf(a, b, c, d, p.tf, &re, &im, an, mid);
-        const bool fa = fp_mul_ok(g.tf.A, mid[0], c), fb = fp_mul_ok(g.tf.B, mid[1], b), fc = fp_mul_ok(g.tf.C, mid[2], d);
-        o << "  static constexpr bool FP_A = " << (fa ? "true" : "false") << ", FP_B = " << (fb ? "true" : "false") << ", FP_C = " << (fc ? "true" : "false") << ";\n";
-        o << "  static constexpr int SH_A = " << (fa ? (int)g.tf.A.shift : 1) << ", SH_B = " << (fb ? (int)g.tf.B.shift : 1) << ", SH_C = " << (fc ? (int)g.tf.C.shift : 1) << ";\n";
-        // The pre-adds a + b and b - a feed those products as floats.  When the stage is an exact add (no alignment,
-        // no rounding shift) whose only other effect is a SAT::TCPL clamp, and both operands are exact floats below 2^23,
-        // the add itself runs on the FP pipe (FADD is exact below 2^24, the clamp is min/max on floats) and one
-        // int->float conversion per product disappears.
-        auto fadd_ok = [](const AddStage &s, const TVal &x, const TVal &y) {
-            auto small = [](const Ival &r) { return r.lo >= -((i128)1 << 23) && r.hi <= ((i128)1 << 23); };
-            return !s.shl_a && !s.shl_b && s.q.shift == 0 && !s.q.wrap_bits && !s.q.wide && (s.q.of == SAT_TCPL || (!s.q.need_lo && !s.q.need_hi)) &&
-                   small(x.r) && small(y.r) && s.q.lo >= -(1LL << 24) && s.q.hi <= (1LL << 24);
-        };
-        o << "  static constexpr bool FADD_AB = " << (fa && fadd_ok(g.tf.ab, a, b) ? "true" : "false")
-          << ", FADD_BA = " << (fc && fadd_ok(g.tf.ba, b, a) ? "true" : "false") << ";\n";
+        const CgemulFp f = cgemul_fp(p, g);
+        o << "  static constexpr bool FP_A = " << (f.fa ? "true" : "false") << ", FP_B = " << (f.fb ? "true" : "false") << ", FP_C = " << (f.fc ? "true" : "false") << ";\n";
+        o << "  static constexpr int SH_A = " << (f.fa ? (int)g.tf.A.shift : 1) << ", SH_B = " << (f.fb ? (int)g.tf.B.shift : 1) << ", SH_C = " << (f.fc ? (int)g.tf.C.shift : 1) << ";\n";
+        o << "  static constexpr bool FADD_AB = " << (f.fadd_ab ? "true" : "false") << ", FADD_BA = " << (f.fadd_ba ? "true" : "false") << ";\n";
     }
     o << "};\n";
     return o.str();

@@ -17,6 +17,8 @@
 #include "qb_fast.h"
 #include "qb_i8gemm.h"
 #include "qb_jit.h"
+#include "qb_codegen.h"
+#include "qb_fast_cgemv.cuh"
 
 using namespace qb;
 
@@ -1094,5 +1096,129 @@ extern "C" int qb200_elementwise_batched(const qb_ew_plan *plan, const void *a, 
         if ((rc = post_launch("k_elementwise"))) return rc;
     }
     if ((rc = cx.out_done(out, n * ow, dout))) return rc;
+    return cx.finish();
+}
+
+// ---------------------------------------------------------------------------------------------
+// diagnostic / parity evidence: exhaustive sweep of the quantizers that run on the FP32 pipe
+// ---------------------------------------------------------------------------------------------
+// The specialised kernels replace some integer quantizers by floating-point instructions (qb_device.cuh:fp_mul_apply,
+// qb_fast_cgemv.cuh:fadd_stage).  These kernels run the SAME device functions over every operand pair the plan's types
+// admit and compare with the integer form (mul_apply / add_apply, the restatement of QuBLAS.h:3146-3235).
+// mode 0: clamps as the plan has them; mode 1: clamp-free variant, counted only where the product lies inside [p_lo, p_hi]
+// (the per-instance clamp elision of qb_fast_gemul.cuh).
+template <int S>
+__global__ void __launch_bounds__(256) k_selftest_fpmul(long long xlo, unsigned long long nx, long long ylo, unsigned long long ny,
+                                                        const __grid_constant__ QStage q, int mode, long long p_lo, long long p_hi,
+                                                        unsigned long long *counts)
+{
+    unsigned long long bad = 0, seen = 0;
+    QStage qq = q;
+    if (mode == 1) { qq.need_lo = 0; qq.need_hi = 0; }
+    for (unsigned long long iy = blockIdx.x; iy < ny; iy += gridDim.x) {
+        const int y = (int)(ylo + (long long)iy);
+        const float yf = __int2float_rn(y);
+        for (unsigned long long ix = threadIdx.x; ix < nx; ix += blockDim.x) {
+            const int x = (int)(xlo + (long long)ix);
+            if (mode == 1) { const long long p = (long long)x * y; if (p < p_lo || p > p_hi) continue; }
+            const int got = fp_mul_apply<S, true>(__int2float_rn(x), yf, qq) - fp_kbits<S>();
+            const int want = mul_apply<int32_t, false>(x, y, q);
+            bad += got != want; ++seen;
+        }
+    }
+    __shared__ unsigned long long sb[256], ss[256];
+    sb[threadIdx.x] = bad; ss[threadIdx.x] = seen;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) { sb[threadIdx.x] += sb[threadIdx.x + o]; ss[threadIdx.x] += ss[threadIdx.x + o]; } __syncthreads(); }
+    if (threadIdx.x == 0) { atomicAdd(&counts[0], ss[0]); atomicAdd(&counts[1], sb[0]); }
+}
+
+__global__ void __launch_bounds__(256) k_selftest_fadd(long long xlo, unsigned long long nx, long long ylo, unsigned long long ny,
+                                                       const __grid_constant__ AddStage st, unsigned long long *counts)
+{
+    unsigned long long bad = 0, seen = 0;
+    for (unsigned long long iy = blockIdx.x; iy < ny; iy += gridDim.x) {
+        const int y = (int)(ylo + (long long)iy);
+        const float yf = __int2float_rn(y);
+        for (unsigned long long ix = threadIdx.x; ix < nx; ix += blockDim.x) {
+            const int x = (int)(xlo + (long long)ix);
+            const float r = fadd_stage(__int2float_rn(x), yf, st.q, st.sub != 0);
+            const int want = add_apply<int32_t, false>(x, y, st);
+            bad += (r != (float)want) || (__float2int_rn(r) != want); ++seen;
+        }
+    }
+    __shared__ unsigned long long sb[256], ss[256];
+    sb[threadIdx.x] = bad; ss[threadIdx.x] = seen;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) { sb[threadIdx.x] += sb[threadIdx.x + o]; ss[threadIdx.x] += ss[threadIdx.x + o]; } __syncthreads(); }
+    if (threadIdx.x == 0) { atomicAdd(&counts[0], ss[0]); atomicAdd(&counts[1], sb[0]); }
+}
+
+static int launch_selftest_fpmul(int S, const Ival &x, const Ival &y, const QStage &q, int mode, long long p_lo, long long p_hi,
+                                 unsigned long long *counts, cudaStream_t st)
+{
+    const unsigned long long nx = (unsigned long long)(x.hi - x.lo + 1), ny = (unsigned long long)(y.hi - y.lo + 1);
+    const unsigned grid = (unsigned)std::min<unsigned long long>(ny, 148ull * 32);
+#define QB_ST(SV) case SV: k_selftest_fpmul<SV><<<grid, 256, 0, st>>>((long long)x.lo, nx, (long long)y.lo, ny, q, mode, p_lo, p_hi, counts); break;
+    switch (S) {
+        QB_ST(1) QB_ST(2) QB_ST(3) QB_ST(4) QB_ST(5) QB_ST(6) QB_ST(7) QB_ST(8) QB_ST(9) QB_ST(10) QB_ST(11) QB_ST(12) QB_ST(13) QB_ST(14) QB_ST(15)
+        QB_ST(16) QB_ST(17) QB_ST(18) QB_ST(19) QB_ST(20) QB_ST(21) QB_ST(22) QB_ST(23) QB_ST(24) QB_ST(25) QB_ST(26) QB_ST(27) QB_ST(28) QB_ST(29) QB_ST(30)
+    default: return fail(QB_EINVAL, "FP product shift out of range");
+    }
+#undef QB_ST
+    return post_launch("k_selftest_fpmul");
+}
+
+extern "C" int qb200_selftest_fp(int what, const void *plan, uint64_t *checked, uint64_t *mismatches, const qb_exec *exec)
+{
+    if (!plan || !checked || !mismatches) return fail(QB_EINVAL, "null argument");
+    *checked = 0; *mismatches = 0;
+    Ctx cx; int rc = cx.init(exec); if (rc) return rc;
+    if (cx.host) { /* buffers are internal: the memory kind of the caller does not matter */ }
+    unsigned long long *counts;
+    if ((rc = cx.alloc((void **)&counts, 16))) return rc;
+    CUDA_TRY(cudaMemsetAsync(counts, 0, 16, cx.stream));
+    auto sweepable = [](const Ival &r) { return r.hi - r.lo < ((i128)1 << 24) && r.lo >= -((i128)1 << 24) && r.hi <= ((i128)1 << 24); };
+    if (what == 0) {
+        const qb_gemul_plan &p = *(const qb_gemul_plan *)plan;
+        auto ce = get_gemul(p);
+        if (ce->an.status) return fail(ce->an.status, ce->an.err);
+        if (ce->bits == 32 && gemul_fp_mul(p, ce->prog)) {
+            const Ival ra = type_range(p.a), rb = type_range(p.b);
+            if (!sweepable(ra) || !sweepable(rb)) return fail(QB_EINVAL, "operand range too large to sweep");
+            long long p_hi, p_lo;
+            gemul_clamp_thresholds(ce->prog, &p_hi, &p_lo);
+            if ((rc = launch_selftest_fpmul(ce->prog.mul.shift, ra, rb, ce->prog.mul, 0, 0, 0, counts, cx.stream))) return rc;
+            const QStage &m = ce->prog.mul;
+            if ((m.need_lo || m.need_hi) && (m.of == SAT_TCPL || m.of == SAT_SMGN))
+                if ((rc = launch_selftest_fpmul(m.shift, ra, rb, m, 1, p_lo, p_hi, counts, cx.stream))) return rc;
+        }
+    } else if (what == 1) {
+        const qb_cgemul_plan &p = *(const qb_cgemul_plan *)plan;
+        auto ce = get_cgemul(p);
+        if (ce->an.status) return fail(ce->an.status, ce->an.err);
+        if (ce->bits == 32 && p.product == QB_CPROD_TF) {
+            const CgemulFp f = cgemul_fp(p, ce->prog);
+            const Ival a = type_range(p.a_re), b = type_range(p.a_im), c = type_range(p.b_re), d = type_range(p.b_im);
+            const TfProg &tf = ce->prog.tf;
+            for (const Ival *r : { &a, &b, &c, &d, &f.ab, &f.cd, &f.ba }) if (!sweepable(*r)) return fail(QB_EINVAL, "operand range too large to sweep");
+            auto fadd = [&](const Ival &x, const Ival &y, const AddStage &st) -> int {
+                const unsigned long long nx = (unsigned long long)(x.hi - x.lo + 1), ny = (unsigned long long)(y.hi - y.lo + 1);
+                k_selftest_fadd<<<(unsigned)std::min<unsigned long long>(ny, 148ull * 32), 256, 0, cx.stream>>>((long long)x.lo, nx, (long long)y.lo, ny, st, counts);
+                return post_launch("k_selftest_fadd");
+            };
+            if (f.fadd_ab && (rc = fadd(a, b, tf.ab))) return rc;                    // a + b  (QuBLAS.h:3524)
+            if (f.fadd_ba && (rc = fadd(b, a, tf.ba))) return rc;                    // b - a  (QuBLAS.h:3526)
+            if (f.fa && (rc = launch_selftest_fpmul(tf.A.shift, f.ab, c, tf.A, 0, 0, 0, counts, cx.stream))) return rc;   // (a+b) * c
+            if (f.fb && (rc = launch_selftest_fpmul(tf.B.shift, f.cd, b, tf.B, 0, 0, 0, counts, cx.stream))) return rc;   // (c+d) * b
+            if (f.fc && (rc = launch_selftest_fpmul(tf.C.shift, f.ba, d, tf.C, 0, 0, 0, counts, cx.stream))) return rc;   // (b-a) * d
+        }
+    } else {
+        return fail(QB_EINVAL, "unknown plan kind");
+    }
+    unsigned long long h[2];
+    CUDA_TRY(cudaMemcpyAsync(h, counts, 16, cudaMemcpyDeviceToHost, cx.stream));
+    CUDA_TRY(cudaStreamSynchronize(cx.stream));
+    *checked = h[0]; *mismatches = h[1];
     return cx.finish();
 }

@@ -889,3 +889,32 @@ def test_unaligned_buffers_fall_back_to_word_access_kernels():
         ops.Qcgemul(y, H, xv, cplan, batch=nb)
         want = oracle.cgemul_batched(cplan, H.cpu().numpy(), xv.cpu().numpy(), nb)
         assert np.array_equal(y.cpu().numpy(), want), o
+
+
+def test_fp_pipe_quantizers_exhaustive_sweep():
+    """VERDICT r1: the FP32-FMA product quantizer and the FADD pre-adds are a departure from "integer shift/mask/clamp";
+    pin them exhaustively.  Config 3: all 2^32 operand pairs through fp_mul_apply (with Qmul's clamp, and clamp-free inside
+    the per-instance elision thresholds) against the integer mul_apply.  Config 4: a+b, b-a (2^32 pairs each) and the three
+    TFComplexMul products (2^33 + 2^32 + 2^32 pairs) against the integer forms."""
+    import ctypes
+    lib = abi.load()
+    ex = abi.qb_exec(abi.QB_MEM_DEVICE, 0, None, 0, 0)
+    a = QType(7, 8)
+    mul = QType(14, 8, True, RND_CONV, SAT_TCPL)
+    lv = [QType(15 + l, 8 - l, True, RND_POS_INF, SAT_TCPL) for l in range(6)]
+    c = QType(17, 4, True, RND_POS_INF, SAT_TCPL)
+    plan = ops.make_gemul_plan(a, a, c, 64, 64, 64, mul=mul, add=lv)
+    checked, bad = ctypes.c_uint64(), ctypes.c_uint64()
+    abi.check(lib.qb200_selftest_fp(0, ctypes.cast(ctypes.byref(plan), ctypes.c_void_p), ctypes.byref(checked), ctypes.byref(bad), ctypes.byref(ex)))
+    assert checked.value > (1 << 32) + (1 << 31) and bad.value == 0, (checked.value, bad.value)      # 2^32 clamped + nearly 2^32 clamp-free
+    # a TRN::TCPL product (round toward -inf: fma.rm) with another shift
+    plan2 = ops.make_gemul_plan(QType(5, 6), QType(7, 4), c, 64, 64, 64, mul=QType(10, 5, True, 5, 0), add=[QType(20, 5)])
+    abi.check(lib.qb200_selftest_fp(0, ctypes.cast(ctypes.byref(plan2), ctypes.c_void_p), ctypes.byref(checked), ctypes.byref(bad), ctypes.byref(ex)))
+    assert checked.value >= 1 << 24 and bad.value == 0, (checked.value, bad.value)
+    # config 4
+    t = QType(3, 12); P = QType(6, 12); S = QType(7, 12)
+    tags = {"abT": QType(4, 12), "cdT": QType(4, 11), "abcT": P, "cdbT": P, "badT": P, "ABT": S, "BCT": S}
+    lvc = [QType(8 + l, 12 - l, True, RND_CONV, SAT_TCPL) for l in range(8)]
+    cplan = ops.make_cgemul_plan(t, t, t, t, lvc[-1], lvc[-1], 256, 1, 256, tf_tags=tags, add_re=lvc, form=TREE_VARIADIC)
+    abi.check(lib.qb200_selftest_fp(1, ctypes.cast(ctypes.byref(cplan), ctypes.c_void_p), ctypes.byref(checked), ctypes.byref(bad), ctypes.byref(ex)))
+    assert checked.value >= 2 * (1 << 32) + (1 << 33) + 2 * (1 << 32) - (1 << 20) and bad.value == 0, (checked.value, bad.value)
