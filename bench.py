@@ -482,69 +482,66 @@ def run_ours(args):
     ms_per_step = ms / args.steps
     value = world * Bn * MACS_PER_INSTANCE / (ms_per_step * 1e-3) / 1e9
 
-    # ---- end to end through the public API with pinned HOST buffers ----
+    # ---- end to end through the C++ drop-in API (include/QuBLAS.h): qublas_b200/libqb200_e2e.so is user code written
+    # against the header -- Qbatch containers in pinned host memory, QgemulBatched<QgemulAddArgs<..>, QgemulMulArgs<..>>(C, A, B)
+    # per chunk; the H2D copy of every chunk's operands and the D2H copy of its results happen inside the call ----
+    e2e_lib = ctypes.CDLL(os.path.join(ROOT, "qublas_b200", "libqb200_e2e.so"))
+    e2e_lib.qbx_last_error.restype = ctypes.c_char_p
+    u64 = ctypes.c_uint64
+    e2e_lib.qbx_c3_init.argtypes = [ctypes.c_int, u64, ctypes.c_int, u64]
+    e2e_lib.qbx_c3_step.argtypes = [ctypes.c_int, u64, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64), ctypes.POINTER(u64)]
+    e2e_lib.qbx_c3_result.argtypes = [ctypes.c_int, ctypes.c_void_p, u64]
+    e2e_lib.qbx_c3_sweep.argtypes = [u64, u64, ctypes.c_int, u64] + [ctypes.POINTER(ctypes.c_double)] * 3
     chunk = min(args.e2e_chunk, Bn)
-    slots = 2
-    hA = [torch.empty(chunk * WORDS, dtype=torch.int32).pin_memory() for _ in range(slots)]
-    hB = [torch.empty(chunk * WORDS, dtype=torch.int32).pin_memory() for _ in range(slots)]
-    hC = [torch.empty(chunk * WORDS, dtype=torch.int32).pin_memory() for _ in range(slots)]
-    for s in range(slots):
-        hA[s].copy_(A[s * chunk * WORDS:(s + 1) * chunk * WORDS] if (s + 1) * chunk <= Bn else A[:chunk * WORDS])
-        hB[s].copy_(B[s * chunk * WORDS:(s + 1) * chunk * WORDS] if (s + 1) * chunk <= Bn else B[:chunk * WORDS])
-    nA = [x.numpy() for x in hA]; nB = [x.numpy() for x in hB]; nC = [x.numpy() for x in hC]
-    e2e_instances = min(Bn, args.e2e_instances)
-    calls = (e2e_instances + chunk - 1) // chunk
-
-    def e2e_step():
-        done = 0
-        for i in range(calls):
-            n = min(chunk, e2e_instances - done)
-            s = i % slots
-            ops.Qgemul(nC[s], nA[s], nB[s], plan, batch=n)     # host buffers: H2D + kernel + D2H inside the call
-            done += n
-
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
+    e2e_instances = max(chunk, min(Bn, args.e2e_instances) // chunk * chunk)        # whole chunks
     e2e_steps = max(1, min(args.steps, 3))
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    e2e_value = world * e2e_instances * MACS_PER_INSTANCE / e2e_s / 1e9
-    # host results must equal the device-resident ones
-    if not np.array_equal(nC[0][:WORDS], Cd[:WORDS].cpu().numpy()):
-        raise SystemExit("bench.py: host-path result differs from device-path result")
+    want0 = Cd[:WORDS].cpu().numpy()
 
-    # supplementary: the same call with the operands handed over as packed int16 words (qb_qdesc.word_bytes = 2; the
-    # 16-bit operand type fits).  Not the reference's layout (int32 words), so it is not the e2e figure -- it shows what
-    # the PCIe-bound path does when the caller can supply half the bytes.
-    e2e16 = None
-    if world == 1 and not args.no_packed16:
-        plan16 = ops.make_gemul_plan(a, a, c, M, N, K, mul=mul, add=lv, word_bytes=(2, 2, 0))
-        hA16 = [x.to(torch.int16).pin_memory() for x in hA]; hB16 = [x.to(torch.int16).pin_memory() for x in hB]
-        nA16 = [x.numpy() for x in hA16]; nB16 = [x.numpy() for x in hB16]
-        n16 = min(e2e_instances, 8 * chunk)
+    def e2e_run(words):
+        """words 0: the header's native narrow words (int16 operands, int32 results); 1: the reference's int32 words."""
+        if e2e_lib.qbx_c3_init(words, chunk, local, first) != 0:
+            raise SystemExit("bench.py: " + e2e_lib.qbx_last_error().decode())
+        sec, h2d, d2h = ctypes.c_double(), u64(), u64()
 
-        def e2e16_step():
-            done = 0
-            for i in range((n16 + chunk - 1) // chunk):
-                n = min(chunk, n16 - done)
-                ops.Qgemul(nC[i % slots], nA16[i % slots], nB16[i % slots], plan16, batch=n)
-                done += n
-
-        e2e16_step()
+        def step():
+            if e2e_lib.qbx_c3_step(words, e2e_instances, ctypes.byref(sec), ctypes.byref(h2d), ctypes.byref(d2h)) != 0:
+                raise SystemExit("bench.py: " + e2e_lib.qbx_last_error().decode())
+        step()                                                   # warm-up (staging buffers, pipeline streams)
+        got = np.zeros(WORDS, dtype=np.int32)
+        e2e_lib.qbx_c3_result(words, got.ctypes.data_as(ctypes.c_void_p), WORDS)
+        if not np.array_equal(got, want0):
+            raise SystemExit("bench.py: C++ host-path result differs from the device-path result")
+        barrier()
         t0 = time.perf_counter()
-        e2e16_step()
-        dt = time.perf_counter() - t0
-        if not np.array_equal(nC[0][:WORDS], Cd[:WORDS].cpu().numpy()):
-            raise SystemExit("bench.py: packed-word host path differs from the device-path result")
-        e2e16 = {"value": n16 * MACS_PER_INSTANCE / dt / 1e9, "unit": "GMAC/s", "h2d_bytes_per_step": n16 * 2 * WORDS * 2, "d2h_bytes_per_step": n16 * WORDS * 4,
-                 "note": "operands as packed int16 words (qb_qdesc.word_bytes = 2), not the reference's int32 layout"}
+        for _ in range(e2e_steps):
+            step()
+        barrier()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_lib.qbx_c3_free()
+        return float(tt.item()), int(h2d.value), int(d2h.value)
+
+    e2e_s, h2d_b, d2h_b = e2e_run(0)
+    e2e_value = world * e2e_instances * MACS_PER_INSTANCE / e2e_s / 1e9
+    e2e_ref_words = None
+    if not args.no_ref_words:
+        s32, h32, d32 = e2e_run(1)
+        e2e_ref_words = {"value": world * e2e_instances * MACS_PER_INSTANCE / s32 / 1e9, "unit": "GMAC/s", "h2d_bytes_per_step": world * h32,
+                         "d2h_bytes_per_step": world * d32, "note": "the same C++ call with Qwords::reference containers (the reference's int32 words): 48 KiB instead of 32 KiB per instance over PCIe"}
+
+    # supplementary: the Monte-Carlo sweep north_star names, device-resident through the same C++ API: inputs generated in
+    # HBM, Qgemul, float64 yardstick GEMM and SQNR / max-error statistics on the GPU; 32 bytes per chunk cross PCIe
+    sweep = None
+    if not args.no_sweep:
+        sec, sq, mx = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        n_sw = min(Bn, 4 * chunk)
+        for _ in range(2):
+            if e2e_lib.qbx_c3_sweep(n_sw, chunk, local, first, ctypes.byref(sec), ctypes.byref(sq), ctypes.byref(mx)) != 0:
+                raise SystemExit("bench.py: " + e2e_lib.qbx_last_error().decode())
+        sweep = {"value": n_sw * MACS_PER_INSTANCE / sec.value / 1e9, "unit": "GMAC/s", "scope": "rank 0's GPU", "instances": n_sw, "sqnr_db": sq.value, "max_abs_err": mx.value,
+                 "note": "synth + Qgemul + float64 reference GEMM + error statistics, all on the device (Qbatch(Qmem::device), QgemulError)"}
 
     if rank == 0:
         peaks = {}
@@ -562,7 +559,7 @@ def run_ours(args):
             "dtype": "int32", "data": "synthetic",
             "config": {**workload_config("c3", args), "sharding": "batch, no data-path collective", "kernel": info.kernel.decode(),
                        "l2": "inputs (%.1f GB per GPU) are far larger than the 126 MB L2; no flush needed" % (2 * Bn * WORDS * 4 / 1e9),
-                       "e2e_host_ring": "%d pinned slots x %d instances, reused cyclically; %d instances per e2e step" % (slots, chunk, e2e_instances),
+                       "e2e_host_ring": "2 pinned slots x %d instances, reused cyclically; %d instances per e2e step" % (chunk, e2e_instances),
                        "cpu_affinity": affinity},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": ncu_traffic("c3", bytes_per_launch), "algorithmic_bytes": bytes_per_launch,
@@ -571,10 +568,12 @@ def run_ours(args):
                          "note": "this kernel is bound by the INT32 issue rate, not HBM: see roofline_alu"},
             "roofline_alu": roofline_alu(lib, value / world, local),
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "GMAC/s", "h2d_bytes_per_step": world * e2e_instances * 2 * WORDS * 4,
-                    "d2h_bytes_per_step": world * e2e_instances * WORDS * 4, "scope": "whole job (all ranks)"},
+            "e2e": {"value": e2e_value, "unit": "GMAC/s", "h2d_bytes_per_step": world * h2d_b, "d2h_bytes_per_step": world * d2h_b,
+                    "scope": "whole job (all ranks)",
+                    "api": "C++ drop-in header: Qbatch (pinned, native narrow words: int16 operands / int32 results) + QgemulBatched, qublas_b200/cxx/e2e_c3.cpp"},
             "gpu_launches": launches,
-            "e2e_packed16": e2e16,
+            "e2e_reference_words": e2e_ref_words,
+            "device_resident_sweep": sweep,
             "bit_exact_checked": checked,
         }
         if world == 1 and not args.no_cpu:
@@ -777,8 +776,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=1000000, help="instances per GPU (BASELINE config 3: 1e6)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--e2e-chunk", type=int, default=32768, help="instances per host-buffer API call")
-    ap.add_argument("--no-packed16", action="store_true", help="skip the supplementary packed-int16 end-to-end measurement")
+    ap.add_argument("--e2e-chunk", type=int, default=65536, help="instances per host-buffer API call")
+    ap.add_argument("--no-ref-words", action="store_true", help="skip the supplementary end-to-end measurement with the reference's int32 words")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the supplementary device-resident Monte-Carlo sweep")
     ap.add_argument("--e2e-instances", type=int, default=1000000, help="instances per end-to-end step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--check-instances", type=int, default=512, help="instances per rank compared with the oracle before timing")

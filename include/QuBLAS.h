@@ -35,6 +35,7 @@
 #include <initializer_list>
 #include <iomanip>
 #include <iostream>
+#include <new>
 #include <random>
 #include <sstream>
 #include <stdexcept>
@@ -1148,63 +1149,183 @@ template <class... Args> auto BitStream(const auto &input) { return detail::bits
 // Batched ("Monte-Carlo") containers: `count` tensors of one type in ONE contiguous raw buffer, so a
 // whole accuracy sweep is a single C-ABI call sharded by batch (tensors above 1000 elements are
 // std::vector-backed in the reference, QuBLAS.h:2694-2697, so an array of tensors is not contiguous).
+//
+//  * Storage word: the NARROWEST two's-complement word that holds the element (int8 for stored width <= 8, int16 for
+//    <= 16, int32, int64) -- the layout of this container is ours, and the host link is what bounds a batched call from
+//    host memory: 16-bit operands cross PCIe as 2 bytes, not as the reference's 4.  Qwords::reference selects the
+//    reference's ArbiInt word (int32 / int64) for zero-copy exchange with buffers in the reference's layout.
+//  * Memory: Qmem::pinned (default; page-locked host memory from qb200_host_alloc, so the library's H2D / kernel / D2H
+//    pipeline really overlaps), Qmem::pageable, or Qmem::device (the batch lives in HBM: synth(), QgemulBatched() and
+//    QgemulError() then never cross PCIe -- a Monte-Carlo sweep returns 32 bytes of statistics).
 // ------------------------------------------------------------------------------------------------
-template <class TensorT> class Qbatch {
+enum class Qmem { pinned, pageable, device };
+enum class Qwords { narrow, reference };
+
+namespace detail {
+template <int W, Qwords P> struct batch_word {
+    using type = std::conditional_t<P == Qwords::reference, std::conditional_t<(W <= 32), std::int32_t, std::int64_t>,
+                 std::conditional_t<(W <= 8), std::int8_t, std::conditional_t<(W <= 16), std::int16_t,
+                 std::conditional_t<(W <= 32), std::int32_t, std::int64_t>>>>;
+};
+}  // namespace detail
+
+template <class TensorT, Qwords Words = Qwords::narrow> class Qbatch {
 public:
     using tensor_t = TensorT;
     using elem_t = typename TensorT::elem_t;
     static_assert(detail::is_scalar<elem_t>::value, "Qbatch holds real tensors");
-    using raw_t = typename elem_t::raw_t;
-    explicit Qbatch(std::size_t count) : count_(count), words_(count * TensorT::elemSize) {}
+    static constexpr int W = 1 + elem_t::intB + elem_t::fracB;
+    using raw_t = typename detail::batch_word<W, Words>::type;
+    static constexpr std::size_t per = TensorT::elemSize;
+
+    explicit Qbatch(std::size_t count, Qmem mem = Qmem::pinned, int device = -1) : count_(count), mem_(mem), device_(device)
+    {
+        const std::size_t bytes = count * per * sizeof(raw_t);
+        if (mem == Qmem::device) {
+            detail::check(qb200_device_alloc(&p_, bytes, device));
+        } else {
+            if (mem == Qmem::pinned && qb200_host_alloc(&p_, bytes, QB_ALLOC_DEFAULT) != 0) { p_ = nullptr; mem_ = Qmem::pageable; }   // no GPU / no lockable memory
+            if (mem_ == Qmem::pageable) { p_ = ::operator new(bytes ? bytes : 16, std::align_val_t(64)); }
+        }
+    }
+    ~Qbatch()
+    {
+        if (!p_) return;
+        if (mem_ == Qmem::device) qb200_device_free(p_, device_);
+        else if (mem_ == Qmem::pinned) qb200_host_free(p_);
+        else ::operator delete(p_, std::align_val_t(64));
+    }
+    Qbatch(const Qbatch &) = delete;
+    Qbatch &operator=(const Qbatch &) = delete;
+    Qbatch(Qbatch &&o) noexcept : count_(o.count_), mem_(o.mem_), device_(o.device_), p_(o.p_) { o.p_ = nullptr; }
+
     std::size_t count() const { return count_; }
-    raw_t *raw() { return words_.data(); }
-    const raw_t *raw() const { return words_.data(); }
-    raw_t &at(std::size_t inst, std::size_t linear) { return words_[inst * TensorT::elemSize + linear]; }
+    std::size_t words() const { return count_ * per; }
+    std::size_t bytes() const { return count_ * per * sizeof(raw_t); }
+    Qmem memory() const { return mem_; }
+    int device() const { return device_; }
+    bool on_device() const { return mem_ == Qmem::device; }
+    raw_t *raw() { return (raw_t *)p_; }
+    const raw_t *raw() const { return (const raw_t *)p_; }
+    static constexpr qb_qdesc desc() { qb_qdesc d = detail::lower(elem_t::spec); d.word_bytes = (uint8_t)sizeof(raw_t); return d; }
+
+    // host access (host-resident batches only)
+    raw_t &at(std::size_t inst, std::size_t linear) { host_only(); return raw()[inst * per + linear]; }
     TensorT get(std::size_t inst) const
     {
+        host_only();
         TensorT t;
-        for (std::size_t i = 0; i < TensorT::elemSize; i++) t[i].data.data = words_[inst * TensorT::elemSize + i];
+        for (std::size_t i = 0; i < per; i++) t[i].data.data = (typename elem_t::raw_t)raw()[inst * per + i];
         return t;
     }
     void set(std::size_t inst, const TensorT &t)
     {
-        for (std::size_t i = 0; i < TensorT::elemSize; i++) words_[inst * TensorT::elemSize + i] = t[i].data.data;
+        host_only();
+        for (std::size_t i = 0; i < per; i++) raw()[inst * per + i] = (raw_t)t[i].data.data;
     }
-    // counter-based synthetic inputs, identical to the device generator
-    void synth(std::uint64_t seed, std::uint64_t stream_id)
+    // counter-based synthetic inputs over the element type's full raw range, identical on host and device
+    // (mirrors fill(), QuBLAS.h:526-536): word index = first_instance * elemSize + linear index
+    void synth(std::uint64_t seed, std::uint64_t stream_id, std::uint64_t first_instance = 0)
     {
-        qb_exec ex{ QB_MEM_HOST, -1, nullptr, 0, 0 };
-        constexpr int W = 1 + elem_t::intB + elem_t::fracB;
-        detail::check(qb200_synth_fill(words_.data(), words_.size(), sizeof(raw_t), -(1LL << (W - 1)), (1LL << (W - 1)) - 1, seed, stream_id, 0, &ex));
+        qb_exec ex{ on_device() ? QB_MEM_DEVICE : QB_MEM_HOST, device_, nullptr, 0, 0 };
+        detail::check(qb200_synth_fill(p_, words(), sizeof(raw_t), -(1LL << (W - 1)), (1LL << (W - 1)) - 1, seed, stream_id, first_instance * per, &ex));
+    }
+    // copies between batches of the same tensor type and word policy, in any direction (host <-> device)
+    void copy_from(const Qbatch &src)
+    {
+        if (src.count_ != count_) throw std::invalid_argument("Qbatch::copy_from: batch sizes differ");
+        detail::check(qb200_memcpy(p_, src.p_, bytes(), on_device() ? device_ : src.device_));
     }
 private:
+    void host_only() const { if (mem_ == Qmem::device) throw std::runtime_error("Qbatch: element access on a device-resident batch (copy it to a host batch first)"); }
     std::size_t count_;
-    std::vector<raw_t> words_;
+    Qmem mem_;
+    int device_;
+    void *p_ = nullptr;
 };
 
-template <class... Tags, class CT, class AT, class BT>
-void QgemulBatched(Qbatch<CT> &C, const Qbatch<AT> &A, const Qbatch<BT> &B, int device = -1)
+namespace detail {
+template <class G, class AT, class BT, class CT, Qwords WA, Qwords WB, Qwords WC>
+const qb_gemul_plan &batched_plan()
 {
-    if (C.count() != A.count() || C.count() != B.count()) throw std::invalid_argument("QgemulBatched: batch sizes differ");
-    using G = detail::gemul_tags<Tags...>;
-    using DA = detail::dims_of<AT>; using DB = detail::dims_of<BT>; using DC = detail::dims_of<CT>;
+    using DA = dims_of<AT>; using DB = dims_of<BT>; using DC = dims_of<CT>;
     constexpr std::size_t M = G::ta ? DA::cols : DA::rows, K = G::ta ? DA::rows : DA::cols;
     constexpr std::size_t Kb = G::tb ? DB::cols : DB::rows, N = G::tb ? DB::rows : DB::cols;
     static_assert(K == Kb && DC::rows == M && DC::cols == N, "QgemulBatched: shapes do not match");
-    using EA = typename DA::elem; using EB = typename DB::elem; using EC = typename DC::elem;
-    static constexpr detail::Spec mul = detail::merge(EA::spec, EB::spec, detail::parse<typename G::mul>(), true);
-    using Low = detail::reduce_lowering<typename G::add, K>;
+    using EA = typename DA::elem; using EB = typename DB::elem;
+    static constexpr Spec mul = merge(EA::spec, EB::spec, parse<typename G::mul>(), true);
+    using Low = reduce_lowering<typename G::add, K>;
     static constexpr qb_gemul_plan plan = [] {
         qb_gemul_plan p{};
-        p.a = detail::lower(EA::spec); p.b = detail::lower(EB::spec); p.mul = detail::lower(mul); p.c = detail::lower(EC::spec);
+        p.a = Qbatch<AT, WA>::desc(); p.b = Qbatch<BT, WB>::desc(); p.mul = lower(mul); p.c = Qbatch<CT, WC>::desc();
         p.add = Low::levels(mul);
         p.M = (uint32_t)M; p.N = (uint32_t)N; p.K = (uint32_t)K;
         p.trans_a = G::ta; p.trans_b = G::tb; p.tree_form = QB_TREE_VARIADIC;
         p.stride_a = (int64_t)(M * K); p.stride_b = (int64_t)(K * N); p.stride_c = (int64_t)(M * N);
         return p;
     }();
-    qb_exec ex{ QB_MEM_HOST, device, nullptr, 0, 0 };
+    return plan;
+}
+template <class A, class B, class C> qb_exec batched_exec(const A &a, const B &b, const C &c, int device)
+{
+    if (c.count() != a.count() || c.count() != b.count()) throw std::invalid_argument("QgemulBatched: batch sizes differ");
+    if (a.on_device() != c.on_device() || b.on_device() != c.on_device()) throw std::invalid_argument("QgemulBatched: host and device batches cannot be mixed");
+    if (c.on_device()) {
+        if (a.device() != c.device() || b.device() != c.device()) throw std::invalid_argument("QgemulBatched: batches live on different devices");
+        if (device != -1 && device != c.device()) throw std::invalid_argument("QgemulBatched: the batches live on another device");
+        return qb_exec{ QB_MEM_DEVICE, c.device(), nullptr, 0, 0 };
+    }
+    return qb_exec{ QB_MEM_HOST, device, nullptr, 0, 0 };
+}
+}  // namespace detail
+
+// device: CUDA ordinal, -1 = the current device, QB_DEVICE_ALL = shard the batch over every visible GPU (host batches)
+template <class... Tags, class CT, class AT, class BT, Qwords WC, Qwords WA, Qwords WB>
+void QgemulBatched(Qbatch<CT, WC> &C, const Qbatch<AT, WA> &A, const Qbatch<BT, WB> &B, int device = -1)
+{
+    const qb_gemul_plan &plan = detail::batched_plan<detail::gemul_tags<Tags...>, AT, BT, CT, WA, WB, WC>();
+    qb_exec ex = detail::batched_exec(A, B, C, device);
     detail::check(qb200_gemul_batched(&plan, A.raw(), B.raw(), C.raw(), C.count(), &ex));
+}
+
+// Accuracy of a batched Qgemul result against the float64 GEMM of the same (dequantized) operands: SQNR sums and the
+// maximum absolute error, reduced on the GPU in a fixed order.  With device-resident batches nothing but the 32-byte
+// result crosses PCIe (Qu -> double, QuBLAS.h:2413-2416, on either side of the path).
+struct Qerror {
+    double sum_sq_err = 0, sum_sq_ref = 0, max_abs_err = 0;
+    std::uint64_t n = 0;
+    double sqnr_db() const { return 10.0 * std::log10(sum_sq_ref / sum_sq_err); }
+};
+template <class... Tags, class CT, class AT, class BT, Qwords WC, Qwords WA, Qwords WB>
+Qerror QgemulError(const Qbatch<CT, WC> &C, const Qbatch<AT, WA> &A, const Qbatch<BT, WB> &B, int device = -1)
+{
+    const qb_gemul_plan &plan = detail::batched_plan<detail::gemul_tags<Tags...>, AT, BT, CT, WA, WB, WC>();
+    qb_exec ex = detail::batched_exec(A, B, C, device);
+    const int dev = C.on_device() ? C.device() : device;
+    void *ref = nullptr;
+    detail::check(qb200_device_alloc(&ref, C.words() * sizeof(double), dev));
+    qb_err_stats st{};
+    qb_exec dex{ QB_MEM_DEVICE, dev, nullptr, 0, 0 };
+    int rc = 0;
+    if (C.on_device()) {
+        rc = qb200_gemul_f64_batched(&plan, A.raw(), B.raw(), (double *)ref, C.count(), &ex);
+        if (!rc) { const qb_qdesc ct = Qbatch<CT, WC>::desc(); rc = qb200_error_stats(&ct, C.raw(), (const double *)ref, C.words(), &st, &dex); }
+    } else {
+        // host batches: stage the operands once, keep the float64 reference on the device
+        void *dA = nullptr, *dB = nullptr, *dC = nullptr;
+        rc = qb200_device_alloc(&dA, A.bytes(), dev);
+        if (!rc) rc = qb200_device_alloc(&dB, B.bytes(), dev);
+        if (!rc) rc = qb200_device_alloc(&dC, C.bytes(), dev);
+        if (!rc) rc = qb200_memcpy(dA, A.raw(), A.bytes(), dev);
+        if (!rc) rc = qb200_memcpy(dB, B.raw(), B.bytes(), dev);
+        if (!rc) rc = qb200_memcpy(dC, C.raw(), C.bytes(), dev);
+        if (!rc) rc = qb200_gemul_f64_batched(&plan, dA, dB, (double *)ref, C.count(), &dex);
+        if (!rc) { const qb_qdesc ct = Qbatch<CT, WC>::desc(); rc = qb200_error_stats(&ct, dC, (const double *)ref, C.words(), &st, &dex); }
+        qb200_device_free(dA, dev); qb200_device_free(dB, dev); qb200_device_free(dC, dev);
+    }
+    qb200_device_free(ref, dev);
+    detail::check(rc);
+    return Qerror{ st.sum_sq_err, st.sum_sq_ref, st.max_abs_err, st.n };
 }
 
 }  // namespace QuBLAS

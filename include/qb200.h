@@ -236,6 +236,20 @@ int qb200_quantize_f64(const qb_qdesc *to, const double *in, void *out, uint64_t
 int qb200_dequantize_f64(const qb_qdesc *from, const void *in, double *out, uint64_t n, const qb_exec *exec);
 int qb200_error_stats(const qb_qdesc *type, const void *words, const double *ref, uint64_t n, qb_err_stats *stats, const qb_exec *exec);
 
+/* float64 GEMM of the dequantized operands of a real Qgemul plan (same shapes, transposes and batch strides; C64 is
+ * batch x M x N doubles, column-major): the yardstick qb200_error_stats compares a quantized result with. */
+int qb200_gemul_f64_batched(const qb_gemul_plan *plan, const void *A, const void *B, double *C64, uint64_t batch, const qb_exec *exec);
+
+/* Memory helpers for the host bindings.  Pinned (page-locked) host buffers make the copies of QB_MEM_HOST calls truly
+ * asynchronous, so that the library's internal H2D / kernel / D2H pipeline overlaps; device buffers keep a whole
+ * Monte-Carlo sweep (synth -> Qgemul -> error statistics) on the GPU.  qb200_memcpy is a synchronous copy in any direction. */
+enum qb_allocflags { QB_ALLOC_DEFAULT = 0, QB_ALLOC_WRITE_COMBINED = 1 /* host: fast for the GPU to read, slow for the CPU to read */ };
+int qb200_host_alloc(void **ptr, size_t bytes, uint32_t flags);
+int qb200_host_free(void *ptr);
+int qb200_device_alloc(void **ptr, size_t bytes, int device);
+int qb200_device_free(void *ptr, int device);
+int qb200_memcpy(void *dst, const void *src, size_t bytes, int device);
+
 /* Deterministic synthetic raw words, uniform over [lo, hi], counter-based:
  * word[i] = lo + floor(mix64(mix64(seed * C + stream_id) ^ (first_index + i)) * (hi - lo + 1) / 2^64)
  * (splitmix64 finaliser, multiply-high range reduction; oracle/qb_oracle.c:qbo_synth_word is the twin).

@@ -1222,3 +1222,97 @@ extern "C" int qb200_selftest_fp(int what, const void *plan, uint64_t *checked, 
     *checked = h[0]; *mismatches = h[1];
     return cx.finish();
 }
+
+// ---------------------------------------------------------------------------------------------
+// memory helpers for the host bindings (pinned host buffers, device-resident batches)
+// ---------------------------------------------------------------------------------------------
+extern "C" int qb200_host_alloc(void **ptr, size_t bytes, uint32_t flags)
+{
+    if (!ptr) return fail(QB_EINVAL, "null argument");
+    *ptr = nullptr;
+    if (flags & ~(uint32_t)QB_ALLOC_WRITE_COMBINED) return fail(QB_EINVAL, "unknown allocation flags");
+    Ctx cx; int rc = cx.init(nullptr); if (rc) return rc;
+    unsigned f = cudaHostAllocPortable | ((flags & QB_ALLOC_WRITE_COMBINED) ? cudaHostAllocWriteCombined : 0);
+    cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 16, f);
+    if (e != cudaSuccess) { cudaGetLastError(); *ptr = nullptr; return fail(e == cudaErrorMemoryAllocation ? QB_ENOMEM : QB_ECUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e)); }
+    return QB_OK;
+}
+extern "C" int qb200_host_free(void *ptr)
+{
+    if (!ptr) return QB_OK;
+    CUDA_TRY(cudaFreeHost(ptr));
+    return QB_OK;
+}
+extern "C" int qb200_device_alloc(void **ptr, size_t bytes, int device)
+{
+    if (!ptr) return fail(QB_EINVAL, "null argument");
+    *ptr = nullptr;
+    qb_exec ex = { QB_MEM_DEVICE, device, nullptr, 0, 0 };
+    Ctx cx; int rc = cx.init(&ex); if (rc) return rc;
+    cudaError_t e = cudaMalloc(ptr, bytes ? bytes : 16);
+    if (e != cudaSuccess) { cudaGetLastError(); *ptr = nullptr; return fail(e == cudaErrorMemoryAllocation ? QB_ENOMEM : QB_ECUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+    return QB_OK;
+}
+extern "C" int qb200_device_free(void *ptr, int device)
+{
+    if (!ptr) return QB_OK;
+    if (device >= 0) CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaFree(ptr));
+    return QB_OK;
+}
+// dst / src may be host or device memory (unified addressing decides); synchronous on return
+extern "C" int qb200_memcpy(void *dst, const void *src, size_t bytes, int device)
+{
+    if (!dst || !src) return fail(QB_EINVAL, "null argument");
+    if (!bytes) return QB_OK;
+    qb_exec ex = { QB_MEM_DEVICE, device, nullptr, 0, 0 };
+    Ctx cx; int rc = cx.init(&ex); if (rc) return rc;
+    CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
+    return QB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// float64 reference GEMM of the DEQUANTIZED operands (the yardstick of an accuracy sweep):
+// C64[i,j] = sum_k toDouble(opA(i,k)) * toDouble(opB(k,j)), k ascending, one FMA per term (deterministic).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_gemul_f64(const void *__restrict__ A, const void *__restrict__ B, double *__restrict__ C, uint64_t batch,
+                                                   const __grid_constant__ GemulShape S, int frac_a, int frac_b)
+{
+    const uint64_t per = (uint64_t)S.M * S.N;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= batch * per) return;
+    const uint64_t inst = t / per, ij = t - inst * per;
+    const uint32_t j = (uint32_t)(ij / S.M), i = (uint32_t)(ij - (uint64_t)j * S.M);
+    const uint64_t oa = inst * (uint64_t)S.stride_a, ob = inst * (uint64_t)S.stride_b;
+    double acc = 0.0;
+    for (uint64_t k = 0; k < S.K; ++k) {
+        const uint64_t ia = S.trans_a ? (k + (uint64_t)i * S.K) : (i + k * S.M);
+        const uint64_t ib = S.trans_b ? (j + k * S.N) : (k + (uint64_t)j * S.K);
+        acc = fma((double)load_word<int64_t>(A, oa + ia, S.a_wb), (double)load_word<int64_t>(B, ob + ib, S.b_wb), acc);
+    }
+    C[inst * (uint64_t)S.stride_c + ij] = acc * pow2_neg(frac_a + frac_b);         // raw products are exact integers below 2^53 per term
+}
+
+extern "C" int qb200_gemul_f64_batched(const qb_gemul_plan *plan, const void *A, const void *B, double *C, uint64_t batch, const qb_exec *exec)
+{
+    if (!plan || !A || !B || !C) return fail(QB_EINVAL, "null argument");
+    auto ce = get_gemul(*plan);
+    if (ce->an.status) return fail(ce->an.status, ce->an.err);
+    const GemulProg &gp = ce->prog;
+    if (width(plan->a) + width(plan->b) > 53) return fail(QB_EDOMAIN, "operand products do not fit a float64 mantissa");
+    if (plan->stride_a < 0 || plan->stride_b < 0 || plan->stride_c < (int64_t)((uint64_t)plan->M * plan->N)) return fail(QB_EINVAL, "bad batch strides");
+    if (batch == 0) return QB_OK;
+    Ctx cx; int rc = cx.init(exec); if (rc) return rc;
+    const uint64_t ea = (uint64_t)plan->M * plan->K, eb = (uint64_t)plan->K * plan->N, ec = (uint64_t)plan->M * plan->N;
+    const size_t bytes_a = span_elems(batch, plan->stride_a, ea) * gp.a_wb, bytes_b = span_elems(batch, plan->stride_b, eb) * gp.b_wb,
+                 bytes_c = span_elems(batch, plan->stride_c, ec) * sizeof(double);
+    const void *dA, *dB; void *dC;
+    if ((rc = cx.in(A, bytes_a, &dA)) || (rc = cx.in(B, bytes_b, &dB)) || (rc = cx.out(C, bytes_c, &dC))) return rc;
+    GemulShape S = shape_of(plan->M, plan->N, plan->K, plan->trans_a, plan->trans_b, gp.a_wb, gp.b_wb, 8, plan->stride_a, plan->stride_b, plan->stride_c);
+    const uint64_t blocks = (batch * ec + 127) / 128;
+    if (blocks > 0x7fffffffull) return fail(QB_EINVAL, "too many outputs for one launch");
+    k_gemul_f64<<<(unsigned)blocks, 128, 0, cx.stream>>>(dA, dB, (double *)dC, batch, S, plan->a.frac_bits, plan->b.frac_bits);
+    if ((rc = post_launch("k_gemul_f64"))) return rc;
+    if ((rc = cx.out_done(C, bytes_c, dC))) return rc;
+    return cx.finish();
+}

@@ -32,6 +32,32 @@ int main()
             }
         }
         std::printf("batched Qgemul: %s\n", bad ? "MISMATCH" : "OK");
+        static_assert(sizeof(Qbatch<A_t>::raw_t) == 2 && sizeof(Qbatch<C_t>::raw_t) == 4, "narrowest storage word: 16-bit operands, 22-bit results");
+
+        // ---- the same sweep device-resident (inputs generated in HBM, only statistics come back), and in the reference's words ----
+        {
+            Qbatch<A_t> dA(n, Qmem::device), dB(n, Qmem::device); Qbatch<C_t> dC(n, Qmem::device), hC(n);
+            dA.synth(1, 0); dB.synth(1, 1);
+            QgemulBatched<QgemulAddArgs<levels>, QgemulMulArgs<mul_t>>(dC, dA, dB);
+            hC.copy_from(dC);
+            int bad_dev = 0;
+            for (std::size_t w = 0; w < hC.words(); w++) if (hC.raw()[w] != C.raw()[w]) bad_dev++;
+            Qbatch<A_t, Qwords::reference> rA(n, Qmem::pageable), rB(n, Qmem::pageable); Qbatch<C_t, Qwords::reference> rC(n, Qmem::pageable);
+            static_assert(sizeof(decltype(rA)::raw_t) == 4, "reference words: int32 for widths up to 32");
+            rA.synth(1, 0); rB.synth(1, 1);
+            QgemulBatched<QgemulAddArgs<levels>, QgemulMulArgs<mul_t>>(rC, rA, rB);
+            for (std::size_t w = 0; w < rC.words(); w++) if (rC.raw()[w] != C.raw()[w]) bad_dev++;
+            Qerror e_dev = QgemulError<QgemulAddArgs<levels>, QgemulMulArgs<mul_t>>(dC, dA, dB);
+            Qerror e_host = QgemulError<QgemulAddArgs<levels>, QgemulMulArgs<mul_t>>(C, A, B);
+            if (e_dev.n != n * 256 || e_dev.sum_sq_err != e_host.sum_sq_err || e_dev.max_abs_err != e_host.max_abs_err) bad_dev++;
+            // the result type has 4 fraction bits, the tree drops bits at every level: the error is a few lsbs of C
+            if (!(e_dev.max_abs_err > 0 && e_dev.max_abs_err < 64.0 / 16 && e_dev.sqnr_db() > 20)) bad_dev++;
+            bool threw = false;
+            try { (void)dC.get(0); } catch (const std::runtime_error &) { threw = true; }
+            if (!threw) bad_dev++;
+            std::printf("device-resident sweep: %s (SQNR %.1f dB, max |err| %.4f)\n", bad_dev ? "MISMATCH" : "OK", e_dev.sqnr_db(), e_dev.max_abs_err);
+            bad += bad_dev;
+        }
 
         // ---- complex Qgemul (8x8 times 8x1) with TFComplexMul and with the default BasicComplexMul ----
         using t = Qu<intBits<3>, fracBits<12>>;

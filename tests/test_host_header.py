@@ -148,4 +148,4 @@ def test_batched_and_complex_example_on_gpu(tmp_path):
     assert p.returncode == 0, p.stdout + p.stderr
     assert "batched Qgemul: OK" in p.stdout and "complex Qgemul TFComplexMul: OK" in p.stdout
     assert "complex Qgemul BasicComplexMul: OK" in p.stdout and "Qreduce 4096: raw" in p.stdout
-    assert "element-wise Qadd/Qsub/Qmul: OK" in p.stdout
+    assert "element-wise Qadd/Qsub/Qmul: OK" in p.stdout and "device-resident sweep: OK" in p.stdout
