@@ -1158,7 +1158,7 @@ template <class... Args> auto BitStream(const auto &input) { return detail::bits
 //    pipeline really overlaps), Qmem::pageable, or Qmem::device (the batch lives in HBM: synth(), QgemulBatched() and
 //    QgemulError() then never cross PCIe -- a Monte-Carlo sweep returns 32 bytes of statistics).
 // ------------------------------------------------------------------------------------------------
-enum class Qmem { pinned, pageable, device };
+enum class Qmem { pinned, pageable, device, write_combined /* pinned, uncached on the CPU side: for input batches that the CPU only writes */ };
 enum class Qwords { narrow, reference };
 
 namespace detail {
@@ -1184,7 +1184,9 @@ public:
         if (mem == Qmem::device) {
             detail::check(qb200_device_alloc(&p_, bytes, device));
         } else {
-            if (mem == Qmem::pinned && qb200_host_alloc(&p_, bytes, QB_ALLOC_DEFAULT) != 0) { p_ = nullptr; mem_ = Qmem::pageable; }   // no GPU / no lockable memory
+            if (mem != Qmem::pageable && qb200_host_alloc(&p_, bytes, mem == Qmem::write_combined ? QB_ALLOC_WRITE_COMBINED : QB_ALLOC_DEFAULT) != 0) {
+                p_ = nullptr; mem_ = Qmem::pageable;                            // no GPU / no lockable memory
+            }
             if (mem_ == Qmem::pageable) { p_ = ::operator new(bytes ? bytes : 16, std::align_val_t(64)); }
         }
     }
@@ -1192,7 +1194,7 @@ public:
     {
         if (!p_) return;
         if (mem_ == Qmem::device) qb200_device_free(p_, device_);
-        else if (mem_ == Qmem::pinned) qb200_host_free(p_);
+        else if (mem_ != Qmem::pageable) qb200_host_free(p_);
         else ::operator delete(p_, std::align_val_t(64));
     }
     Qbatch(const Qbatch &) = delete;

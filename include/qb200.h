@@ -176,10 +176,14 @@ typedef struct qb_plan_info {
     char    kernel[96];        /* kernel variant name                                           */
 } qb_plan_info;
 
+/* exec.device = QB_DEVICE_ALL (batched calls on HOST buffers): the batch is cut into contiguous shards, one per visible
+ * GPU, which run concurrently (one host thread, stream set and staging pipeline per device); no inter-GPU traffic. */
+#define QB_DEVICE_ALL (-2)
+
 /* Execution context: where buffers live, which device, which stream (cudaStream_t or NULL). */
 typedef struct qb_exec {
     int32_t  mem_kind;   /* enum qb_memkind */
-    int32_t  device;     /* CUDA device ordinal; -1 = current device                           */
+    int32_t  device;     /* CUDA device ordinal; -1 = current device; QB_DEVICE_ALL = every visible device */
     void    *stream;     /* cudaStream_t; NULL = default stream. Host-memory calls synchronise. */
     uint32_t flags;      /* QB_F_*                                                             */
     uint32_t reserved;
@@ -279,6 +283,26 @@ int qb200_jit_check(int what, const void *plan, char *log, uint64_t log_cap);
  * with and without the per-instance clamp elision; config 4: a+b, b-a and the three TFComplexMul products).
  * what: 0 = qb_gemul_plan, 1 = qb_cgemul_plan.  checked = pairs compared (0: the plan uses no FP-pipe quantizer). */
 int qb200_selftest_fp(int what, const void *plan, uint64_t *checked, uint64_t *mismatches, const qb_exec *exec);
+
+/* One call, several GPUs, device-resident shards: shard i = `batch` instances whose buffers live on `device` (or in host
+ * memory when exec->mem_kind == QB_MEM_HOST).  The shards run concurrently (one host thread each) and are complete on
+ * return.  exec->device is ignored; exec->stream must be NULL. */
+typedef struct qb_shard {
+    int32_t     device;
+    int32_t     reserved;
+    const void *A, *B;
+    void       *C;
+    uint64_t    batch;
+} qb_shard;
+int qb200_gemul_sharded(const qb_gemul_plan *plan, const qb_shard *shards, uint32_t n_shards, const qb_exec *exec);
+
+/* Optional output all-gather over NVLink / NVSwitch (direct peer copies; not on the compute path):
+ * shard i = `rows` rows of width[i] bytes (pitch src_pitch[i]) at src[i] on devices[i]; afterwards it sits at byte offset
+ * dst_off[i] of every row of dst[j] (pitch dst_pitch) on EVERY device j.  rows == 1: contiguous shards (batches; src_pitch
+ * may be NULL).  rows = N: M-row panels of a column-major M x N matrix (width = panel rows * word, dst_pitch = M * word).
+ * seconds (optional): device-timed duration, max over the source devices. */
+int qb200_allgather(void *const *dst, const void *const *src, const int32_t *devices, uint32_t n, uint64_t rows, uint64_t dst_pitch,
+                    const uint64_t *dst_off, const uint64_t *src_pitch, const uint64_t *width, double *seconds);
 
 /* Contiguous shard [first, first+count) of `total` units for `rank` of `world` (batch or M-panel). */
 int qb200_shard_range(uint64_t total, uint32_t world, uint32_t rank, uint64_t *first, uint64_t *count);

@@ -10,6 +10,7 @@ from typing import Optional, Sequence
 from .qtypes import QType
 
 QB_MAX_LEVELS = 64
+QB_DEVICE_ALL = -2
 QB_MEM_HOST, QB_MEM_DEVICE = 0, 1
 QB_F_NO_TENSOR_CORE, QB_F_NO_SPECIALIZE = 1, 2
 QB_OK, QB_EINVAL, QB_EDOMAIN, QB_ENODEVICE, QB_ECUDA, QB_ENOMEM = 0, -1, -2, -3, -4, -5
@@ -72,6 +73,10 @@ class qb_convert_plan(C.Structure):
     _fields_ = [("from_", qb_qdesc), ("to", qb_qdesc), ("len", C.c_uint64)]
 
 
+class qb_shard(C.Structure):
+    _fields_ = [("device", C.c_int32), ("reserved", C.c_int32), ("A", C.c_void_p), ("B", C.c_void_p), ("C", C.c_void_p), ("batch", C.c_uint64)]
+
+
 class qb_plan_info(C.Structure):
     _fields_ = [("arith_bits", C.c_int32), ("max_inter_bits", C.c_int32), ("lossless", C.c_int32),
                 ("tensor_core", C.c_int32), ("specialized", C.c_int32), ("out_word_bytes", C.c_int32),
@@ -127,7 +132,7 @@ ABI_SYMBOLS = [
     "qb200_launch_count_reset", "qb200_reduce_plan_info", "qb200_gemul_plan_info", "qb200_cgemul_plan_info",
     "qb200_reduce_batched", "qb200_gemul_batched", "qb200_cgemul_batched", "qb200_tfcmul_batched",
     "qb200_convert_batched", "qb200_elementwise_batched", "qb200_synth_fill", "qb200_shard_range", "qb200_measure_int_peak", "qb200_jit_check_gemul", "qb200_jit_check", "qb200_quantize_f64", "qb200_dequantize_f64", "qb200_error_stats",
-    "qb200_selftest_fp", "qb200_gemul_f64_batched", "qb200_host_alloc", "qb200_host_free", "qb200_device_alloc", "qb200_device_free", "qb200_memcpy",
+    "qb200_selftest_fp", "qb200_gemul_f64_batched", "qb200_host_alloc", "qb200_host_free", "qb200_device_alloc", "qb200_device_free", "qb200_memcpy", "qb200_gemul_sharded", "qb200_allgather",
 ]
 
 _LIB = None
@@ -176,6 +181,8 @@ def load() -> C.CDLL:
     L.qb200_device_alloc.argtypes = [C.POINTER(vp), C.c_size_t, C.c_int]
     L.qb200_device_free.argtypes = [vp, C.c_int]
     L.qb200_memcpy.argtypes = [vp, vp, C.c_size_t, C.c_int]
+    L.qb200_gemul_sharded.argtypes = [C.POINTER(qb_gemul_plan), C.POINTER(qb_shard), u32, C.POINTER(qb_exec)]
+    L.qb200_allgather.argtypes = [C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int32), u32, u64, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_double)]
     L.qb200_selftest_fp.argtypes = [C.c_int, C.c_void_p, C.POINTER(u64), C.POINTER(u64), C.POINTER(qb_exec)]
     for name in ABI_SYMBOLS:
         getattr(L, name)

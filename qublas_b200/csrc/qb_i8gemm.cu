@@ -618,26 +618,39 @@ static void pack_padded(const void *src, int8_t *dst, uint32_t rows, uint32_t k,
     count_launch(1);
 }
 
+// An operand that already is what the tensor maps want -- int8 words, K contiguous (A stored K x M, i.e. trans_a; B stored
+// K x N, i.e. !trans_b), 16-byte aligned base and row stride -- is read in place: the tensor map is built on the caller's
+// buffer and no pack kernel runs.  Ragged extents need no padding either: TMA fills out-of-bounds box elements with zeros,
+// and zeros add nothing to an exact dot product.
+bool i8gemm_zero_copy(const void *ptr, int wb, bool k_major, uint32_t K)
+{
+    static int off = -1;                           // QB200_I8_NO_ZERO_COPY=1: always pack (experiments)
+    if (off < 0) { const char *e = getenv("QB200_I8_NO_ZERO_COPY"); off = (e && e[0] == '1') ? 1 : 0; }
+    return !off && wb == 1 && k_major && (((uintptr_t)ptr) & 15) == 0 && K % 16 == 0;
+}
+
 // One instance.  A, B: device pointers to raw ABI words (a_wb / b_wb bytes each), column-major as in the plan.
-// Ap / Bp: int8 staging of Mp x Kp and Np x Kp bytes (i8gemm_padded_dims).
+// Ap / Bp: int8 staging of Mp x Kp and Np x Kp bytes (i8gemm_padded_dims); may be NULL for an operand that is read in place.
 int i8gemm_run(const void *A, const void *B, void *C, uint32_t M, uint32_t N, uint32_t K, bool trans_a, bool trans_b, int a_wb,
                int b_wb, int c_wb, const QStage &outq, int8_t *Ap, int8_t *Bp, cudaStream_t s, const char **err)
 {
     uint32_t Mp, Np, Kp;
     i8gemm_padded_dims(M, N, K, &Mp, &Np, &Kp);
     const bool ragged = Mp != M || Np != N || Kp != K;
+    const bool zc_a = i8gemm_zero_copy(A, a_wb, trans_a, K), zc_b = i8gemm_zero_copy(B, b_wb, !trans_b, K);
+    if ((!zc_a && !Ap) || (!zc_b && !Bp)) { *err = "missing int8 staging buffer"; return -1; }
     // A operand must become M rows x K (K contiguous).  Stored M x K column-major (M contiguous) unless trans_a (K x M, K contiguous).
     const bool a_tr = !trans_a;
     // B operand must become N rows x K.  Stored K x N column-major (K contiguous) unless trans_b (N x K, N contiguous).
     const bool b_tr = trans_b;
     if (ragged) {
-        switch (a_wb) {
+        if (!zc_a) switch (a_wb) {
         case 1: pack_padded<int8_t>(A, Ap, M, K, Mp, Kp, a_tr, s); break;
         case 2: pack_padded<int16_t>(A, Ap, M, K, Mp, Kp, a_tr, s); break;
         case 4: pack_padded<int32_t>(A, Ap, M, K, Mp, Kp, a_tr, s); break;
         default: pack_padded<int64_t>(A, Ap, M, K, Mp, Kp, a_tr, s); break;
         }
-        switch (b_wb) {
+        if (!zc_b) switch (b_wb) {
         case 1: pack_padded<int8_t>(B, Bp, N, K, Np, Kp, b_tr, s); break;
         case 2: pack_padded<int16_t>(B, Bp, N, K, Np, Kp, b_tr, s); break;
         case 4: pack_padded<int32_t>(B, Bp, N, K, Np, Kp, b_tr, s); break;
@@ -646,13 +659,13 @@ int i8gemm_run(const void *A, const void *B, void *C, uint32_t M, uint32_t N, ui
     } else {
         const uint32_t a_r = trans_a ? K : M, a_c = trans_a ? M : K;
         const uint32_t b_r = trans_b ? N : K, b_c = trans_b ? K : N;
-        switch (a_wb) {
+        if (!zc_a) switch (a_wb) {
         case 1: pack_operand<int8_t>(A, Ap, a_r, a_c, a_tr, s); break;
         case 2: pack_operand<int16_t>(A, Ap, a_r, a_c, a_tr, s); break;
         case 4: pack_operand<int32_t>(A, Ap, a_r, a_c, a_tr, s); break;
         default: pack_operand<int64_t>(A, Ap, a_r, a_c, a_tr, s); break;
         }
-        switch (b_wb) {
+        if (!zc_b) switch (b_wb) {
         case 1: pack_operand<int8_t>(B, Bp, b_r, b_c, b_tr, s); break;
         case 2: pack_operand<int16_t>(B, Bp, b_r, b_c, b_tr, s); break;
         case 4: pack_operand<int32_t>(B, Bp, b_r, b_c, b_tr, s); break;
@@ -664,7 +677,9 @@ int i8gemm_run(const void *A, const void *B, void *C, uint32_t M, uint32_t N, ui
     const bool pair = variant == 2 && (Mp / BM) % 2 == 0;
     const bool mc = (variant == 1 || pair) && (Mp / BM) % 2 == 0;
     CUtensorMap mapA, mapB;
-    if (make_map(&mapA, Ap, Mp, Kp, BM) || make_map(&mapB, Bp, Np, Kp, mc ? BN / 2 : BN)) { *err = "cuTensorMapEncodeTiled failed"; return -1; }
+    // in place: the real extents (out-of-bounds box elements read as zero); staged: the zero-padded copy
+    if ((zc_a ? make_map(&mapA, (const int8_t *)A, M, K, BM) : make_map(&mapA, Ap, Mp, Kp, BM)) ||
+        (zc_b ? make_map(&mapB, (const int8_t *)B, N, K, mc ? BN / 2 : BN) : make_map(&mapB, Bp, Np, Kp, mc ? BN / 2 : BN))) { *err = "cuTensorMapEncodeTiled failed"; return -1; }
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     static bool attr_set[64] = { false };          // function attributes are per device

@@ -8,6 +8,7 @@
 #include <mutex>
 #include <memory>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -333,6 +334,44 @@ extern "C" int qb200_shard_range(uint64_t total, uint32_t world, uint32_t rank, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// exec.device == QB_DEVICE_ALL: one call drives every visible GPU.  The units of a batched call (instances, vectors) are
+// independent, so the batch is cut into contiguous shards (qb200_shard_range), one host thread per device runs the
+// ordinary single-device path on its shard (own streams, own staging pipeline), and the call returns when all are done.
+// There is no inter-GPU traffic on this path.
+// ---------------------------------------------------------------------------------------------
+template <class Fn>   // fn(int device, uint64_t first, uint64_t count) -> int
+static int on_all_devices(uint64_t units, Fn fn)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return fail(QB_ENODEVICE, "no CUDA device available (there is no CPU fallback)"); }
+    const uint32_t world = (uint32_t)std::min<uint64_t>((uint64_t)ndev, units ? units : 1);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    std::vector<int> rcs(world, QB_OK);
+    std::vector<std::string> errs(world);
+    std::vector<std::thread> th;
+    for (uint32_t r = 0; r < world; r++) {
+        th.emplace_back([&, r] {
+            uint64_t first = 0, count = 0;
+            qb200_shard_range(units, world, r, &first, &count);
+            rcs[r] = count ? fn((int)r, first, count) : QB_OK;
+            if (rcs[r]) errs[r] = g_err;                                   // the error text is thread-local
+        });
+    }
+    for (auto &t : th) t.join();
+    cudaSetDevice(prev);
+    for (uint32_t r = 0; r < world; r++) if (rcs[r]) return fail(rcs[r], "device " + std::to_string(r) + ": " + errs[r]);
+    return QB_OK;
+}
+static bool wants_all_devices(const qb_exec *ex) { return ex && ex->device == QB_DEVICE_ALL; }
+static int check_all_devices(const qb_exec *ex)
+{
+    if (ex->mem_kind != QB_MEM_HOST) return fail(QB_EINVAL, "QB_DEVICE_ALL shards HOST buffers; device-resident shards go through qb200_gemul_sharded");
+    if (ex->stream) return fail(QB_EINVAL, "QB_DEVICE_ALL runs on the library's own streams (exec.stream must be NULL)");
+    return QB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Qreduce
 // ---------------------------------------------------------------------------------------------
 static unsigned ceil_log2(uint64_t n) { unsigned l = 0; while (((uint64_t)1 << l) < n) l++; return l; }
@@ -448,6 +487,15 @@ extern "C" int qb200_reduce_batched(const qb_reduce_plan *plan_in, const void *x
         if (partial_level > ceil_log2(plan->len)) return fail(QB_EINVAL, "partial_level above the root");
     }
     if (batch == 0) return QB_OK;
+    if (wants_all_devices(exec)) {
+        int rc = check_all_devices(exec); if (rc) return rc;
+        uint64_t per = plan->len; for (uint32_t l = 0; l < partial_level; l++) per = (per + 1) / 2;
+        return on_all_devices(batch, [&](int dev, uint64_t first, uint64_t count) {
+            qb_exec ex = *exec; ex.device = dev;
+            return qb200_reduce_batched(plan_in, (const char *)x + first * plan->len * rp.elem_wb, (char *)out + first * rp.out_wb,
+                                        partials ? (char *)partials + first * per * 8 : nullptr, partial_level, count, &ex);
+        });
+    }
     Ctx cx; int rc = cx.init(exec); if (rc) return rc;
     uint64_t per = plan->len; for (uint32_t l = 0; l < partial_level; l++) per = (per + 1) / 2;
     const void *dx; void *dout, *dpart = nullptr;
@@ -525,6 +573,14 @@ extern "C" int qb200_gemul_batched(const qb_gemul_plan *plan, const void *A, con
     if (plan->stride_a < 0 || plan->stride_b < 0 || plan->stride_c < (int64_t)((uint64_t)plan->M * plan->N))
         return fail(QB_EINVAL, "bad batch strides");
     if (batch == 0) return QB_OK;
+    if (wants_all_devices(exec)) {
+        int rc = check_all_devices(exec); if (rc) return rc;
+        return on_all_devices(batch, [&](int dev, uint64_t first, uint64_t count) {
+            qb_exec ex = *exec; ex.device = dev;
+            return qb200_gemul_batched(plan, (const char *)A + first * plan->stride_a * gp.a_wb, (const char *)B + first * plan->stride_b * gp.b_wb,
+                                       (char *)C + first * plan->stride_c * gp.c_wb, count, &ex);
+        });
+    }
     Ctx cx; int rc = cx.init(exec); if (rc) return rc;
     const uint64_t ea = (uint64_t)plan->M * plan->K, eb = (uint64_t)plan->K * plan->N, ec = (uint64_t)plan->M * plan->N;
     const int bits = ce->bits;
@@ -564,7 +620,14 @@ extern "C" int qb200_gemul_batched(const qb_gemul_plan *plan, const void *A, con
         if ((rc = cx.in(A, bytes_a, &dA)) || (rc = cx.in(B, bytes_b, &dB)) || (rc = cx.out(C, bytes_c, &dC))) return rc;
         uint32_t Mp, Np, Kp;
         i8gemm_padded_dims(plan->M, plan->N, plan->K, &Mp, &Np, &Kp);
-        if ((rc = cx.alloc(&Ap, (size_t)Mp * Kp)) || (rc = cx.alloc(&Bp, (size_t)Np * Kp))) return rc;
+        // staging only for operands that have to be packed (int8 K-major operands are read in place)
+        bool need_a = false, need_b = false;
+        for (uint64_t i = 0; i < batch; i++) {
+            need_a |= !i8gemm_zero_copy((const char *)dA + i * plan->stride_a * gp.a_wb, gp.a_wb, plan->trans_a != 0, plan->K);
+            need_b |= !i8gemm_zero_copy((const char *)dB + i * plan->stride_b * gp.b_wb, gp.b_wb, plan->trans_b == 0, plan->K);
+        }
+        Ap = Bp = nullptr;
+        if ((need_a && (rc = cx.alloc(&Ap, (size_t)Mp * Kp))) || (need_b && (rc = cx.alloc(&Bp, (size_t)Np * Kp)))) return rc;
         for (uint64_t i = 0; i < batch; i++) {
             const char *err = "";
             if (i8gemm_run((const char *)dA + i * plan->stride_a * gp.a_wb, (const char *)dB + i * plan->stride_b * gp.b_wb,
@@ -617,6 +680,15 @@ extern "C" int qb200_cgemul_batched(const qb_cgemul_plan *plan, const void *A, c
     if (plan->stride_a < 0 || plan->stride_b < 0 || plan->stride_c < (int64_t)((uint64_t)plan->M * plan->N))
         return fail(QB_EINVAL, "bad batch strides");
     if (batch == 0) return QB_OK;
+    if (wants_all_devices(exec)) {
+        int rc = check_all_devices(exec); if (rc) return rc;
+        const size_t wpa = plan->product == QB_CPROD_REAL_A ? 1 : 2, wpb = plan->product == QB_CPROD_REAL_B ? 1 : 2;
+        return on_all_devices(batch, [&](int dev, uint64_t first, uint64_t count) {
+            qb_exec ex = *exec; ex.device = dev;
+            return qb200_cgemul_batched(plan, (const char *)A + first * plan->stride_a * wpa * gp.a_wb, (const char *)B + first * plan->stride_b * wpb * gp.b_wb,
+                                        (char *)C + first * plan->stride_c * 2 * gp.c_wb, count, &ex);
+        });
+    }
     Ctx cx; int rc = cx.init(exec); if (rc) return rc;
     const uint64_t ea = (uint64_t)plan->M * plan->K, eb = (uint64_t)plan->K * plan->N, ec = (uint64_t)plan->M * plan->N;
     const size_t wa = plan->product == QB_CPROD_REAL_A ? 1 : 2, wbn = plan->product == QB_CPROD_REAL_B ? 1 : 2;   // words per element
@@ -1315,4 +1387,101 @@ extern "C" int qb200_gemul_f64_batched(const qb_gemul_plan *plan, const void *A,
     if ((rc = post_launch("k_gemul_f64"))) return rc;
     if ((rc = cx.out_done(C, bytes_c, dC))) return rc;
     return cx.finish();
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-resident shards on several GPUs in one call, and the optional output all-gather over NVLink
+// ---------------------------------------------------------------------------------------------
+extern "C" int qb200_gemul_sharded(const qb_gemul_plan *plan, const qb_shard *shards, uint32_t n_shards, const qb_exec *exec)
+{
+    if (!plan || (!shards && n_shards)) return fail(QB_EINVAL, "null argument");
+    if (exec && exec->stream) return fail(QB_EINVAL, "sharded calls run on the library's own streams (exec.stream must be NULL)");
+    if (n_shards == 0) return QB_OK;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    std::vector<int> rcs(n_shards, QB_OK);
+    std::vector<std::string> errs(n_shards);
+    std::vector<std::thread> th;
+    for (uint32_t r = 0; r < n_shards; r++) {
+        th.emplace_back([&, r] {
+            const qb_shard &sh = shards[r];
+            qb_exec ex = { exec ? exec->mem_kind : (int32_t)QB_MEM_DEVICE, sh.device, nullptr, exec ? exec->flags : 0u, 0 };
+            int rc = sh.batch ? qb200_gemul_batched(plan, sh.A, sh.B, sh.C, sh.batch, &ex) : QB_OK;
+            if (!rc && ex.mem_kind == QB_MEM_DEVICE) {                       // device-memory calls are asynchronous: complete the shard before returning
+                cudaError_t e = cudaStreamSynchronize(nullptr);
+                if (e != cudaSuccess) rc = fail(QB_ECUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
+            }
+            rcs[r] = rc;
+            if (rc) errs[r] = g_err;
+        });
+    }
+    for (auto &t : th) t.join();
+    cudaSetDevice(prev);
+    for (uint32_t r = 0; r < n_shards; r++) if (rcs[r]) return fail(rcs[r], "shard " + std::to_string(r) + " (device " + std::to_string(shards[r].device) + "): " + errs[r]);
+    return QB_OK;
+}
+
+// Every device ends up with every shard: direct peer copies over NVLink / NVSwitch (no host staging, no compute-path
+// dependency: it is optional and separate from the kernels).  Shard i is `rows` rows of width[i] bytes with pitch
+// src_pitch[i] on devices[i]; it lands at byte offset dst_off[i] of every row of dst[j] (pitch dst_pitch) on every device j.
+// rows == 1 is the contiguous case (batch shards); rows = N with column-major M x N matrices gathers M-row panels.
+extern "C" int qb200_allgather(void *const *dst, const void *const *src, const int32_t *devices, uint32_t n, uint64_t rows, uint64_t dst_pitch,
+                               const uint64_t *dst_off, const uint64_t *src_pitch, const uint64_t *width, double *seconds)
+{
+    if (!dst || !src || !devices || !dst_off || !width || (rows > 1 && !src_pitch)) return fail(QB_EINVAL, "null argument");
+    if (n == 0 || rows == 0) return QB_OK;
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    for (uint32_t i = 0; i < n; i++) if (devices[i] < 0 || devices[i] >= ndev) return fail(QB_EINVAL, "bad device ordinal");
+    int prev = 0;
+    cudaGetDevice(&prev);
+    // peer access in both directions between every pair (a copy without it would be staged through the host)
+    for (uint32_t i = 0; i < n; i++) {
+        CUDA_TRY(cudaSetDevice(devices[i]));
+        for (uint32_t j = 0; j < n; j++) {
+            if (devices[j] == devices[i]) continue;
+            int can = 0;
+            CUDA_TRY(cudaDeviceCanAccessPeer(&can, devices[i], devices[j]));
+            if (!can) { cudaSetDevice(prev); return fail(QB_ECUDA, "no peer access between devices " + std::to_string(devices[i]) + " and " + std::to_string(devices[j])); }
+            cudaError_t e = cudaDeviceEnablePeerAccess(devices[j], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaSetDevice(prev); return fail(QB_ECUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)); }
+            cudaGetLastError();
+        }
+    }
+    std::vector<cudaStream_t> st(n);
+    std::vector<cudaEvent_t> e0(n), e1(n);
+    for (uint32_t i = 0; i < n; i++) {
+        CUDA_TRY(cudaSetDevice(devices[i]));
+        CUDA_TRY(cudaDeviceSynchronize());                                  // the shards are complete before anybody reads them
+        CUDA_TRY(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreate(&e0[i])); CUDA_TRY(cudaEventCreate(&e1[i]));
+    }
+    int rc = QB_OK;
+    for (uint32_t i = 0; i < n && !rc; i++) {                               // source device i pushes its shard: step s goes to (i + s) mod n
+        cudaSetDevice(devices[i]);
+        cudaEventRecord(e0[i], st[i]);
+        for (uint32_t s = 0; s < n && !rc; s++) {
+            const uint32_t j = (i + s) % n;
+            char *d = (char *)dst[j] + dst_off[i];
+            const uint64_t sp = rows > 1 ? src_pitch[i] : width[i];
+            if ((const void *)d == src[i] && (rows == 1 || sp == dst_pitch)) continue;        // already in place on its own device
+            cudaError_t e;
+            if (rows == 1) e = cudaMemcpyPeerAsync(d, devices[j], src[i], devices[i], width[i], st[i]);
+            else e = cudaMemcpy2DAsync(d, dst_pitch, src[i], sp, width[i], rows, cudaMemcpyDefault, st[i]);
+            if (e != cudaSuccess) rc = fail(QB_ECUDA, std::string("peer copy: ") + cudaGetErrorString(e));
+        }
+        cudaEventRecord(e1[i], st[i]);
+    }
+    double worst = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        cudaSetDevice(devices[i]);
+        cudaError_t e = cudaStreamSynchronize(st[i]);
+        if (e != cudaSuccess && !rc) rc = fail(QB_ECUDA, std::string("all-gather: ") + cudaGetErrorString(e));
+        float ms = 0;
+        if (!rc && cudaEventElapsedTime(&ms, e0[i], e1[i]) == cudaSuccess && ms * 1e-3 > worst) worst = ms * 1e-3;
+        cudaStreamDestroy(st[i]); cudaEventDestroy(e0[i]); cudaEventDestroy(e1[i]);
+    }
+    cudaSetDevice(prev);
+    if (seconds) *seconds = worst;
+    return rc;
 }

@@ -6,6 +6,7 @@
 #include "QuBLAS.h"
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <memory>
 
 using namespace QuBLAS;
@@ -29,8 +30,10 @@ template <Qwords W> struct Ring {
     {
         chunk = n; device = dev;
         for (int s = 0; s < SLOTS; s++) {
-            A[s] = std::make_unique<Qbatch<A_t, W>>(n); B[s] = std::make_unique<Qbatch<A_t, W>>(n); C[s] = std::make_unique<Qbatch<C_t, W>>(n);
-            if (A[s]->memory() != Qmem::pinned) throw std::runtime_error("pinned host memory unavailable");
+            const char *wc = std::getenv("QB200_E2E_WC");                        // experiment: write-combined input batches
+            const Qmem in_mem = (wc && wc[0] == '1') ? Qmem::write_combined : Qmem::pinned;
+            A[s] = std::make_unique<Qbatch<A_t, W>>(n, in_mem); B[s] = std::make_unique<Qbatch<A_t, W>>(n, in_mem); C[s] = std::make_unique<Qbatch<C_t, W>>(n);
+            if (A[s]->memory() == Qmem::pageable || C[s]->memory() == Qmem::pageable) throw std::runtime_error("pinned host memory unavailable");
             A[s]->synth(1, 0, first_instance + s * n); B[s]->synth(1, 1, first_instance + s * n);     // the bench's synthetic stream
         }
     }

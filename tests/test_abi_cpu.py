@@ -27,7 +27,7 @@ def test_struct_layout_matches_header(tmp_path):
     """ctypes mirrors == the C compiler's view of include/qb200.h."""
     import subprocess
     names = ["qb_qdesc", "qb_levels", "qb_reduce_plan", "qb_gemul_plan", "qb_tfc_types", "qb_bcm_types", "qb_cgemul_plan", "qb_err_stats",
-             "qb_tfcmul_plan", "qb_ew_plan", "qb_convert_plan", "qb_plan_info", "qb_exec"]
+             "qb_tfcmul_plan", "qb_ew_plan", "qb_convert_plan", "qb_plan_info", "qb_exec", "qb_shard"]
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include "qb200.h"\nint main(void){' +
                    "".join('printf("%%zu\\n", sizeof(%s));' % n for n in names) + "return 0;}\n")

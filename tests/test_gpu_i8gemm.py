@@ -101,3 +101,41 @@ def test_i8_tensor_core_ragged_shapes_run_on_zero_padded_operands(M, N, K, ta, t
     assert ops.plan_info_gemul(c5_plan(40, 50, 60)[1]).tensor_core == 0
     assert ops.plan_info_gemul(c5_plan(129, 4096, 4096)[1]).tensor_core == 1           # 256/129 < 2
     assert ops.plan_info_gemul(c5_plan(5, 4096, 4096)[1]).tensor_core == 0
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 256), (384, 512, 128), (200, 300, 208), (8192, 512, 1024)])
+def test_i8_operands_handed_over_k_major_are_read_in_place(M, N, K):
+    """int8 words, K contiguous (A stored K x M = trans_a, B stored K x N) -> the tensor maps sit on the caller's
+    buffers, no pack kernel runs (ONE launch per call); ragged extents rely on TMA's zero fill.  Same bits as the oracle and
+    as the int32-word call; a buffer that is not 16-byte aligned takes the pack path and still gives the same bits."""
+    rng = np.random.default_rng(M * 3 + N + K)
+    a = QType(7, 0); acc = QType(30, 0)
+    plan8 = ops.make_gemul_plan(a, a, acc, M, N, K, mul=QType(15, 0), add=[acc], trans_a=True, word_bytes=(1, 1, 0))
+    plan32 = ops.make_gemul_plan(a, a, acc, M, N, K, mul=QType(15, 0), add=[acc], trans_a=True)
+    assert ops.plan_info_gemul(plan8).tensor_core == 1
+    A = rng.integers(-128, 128, size=M * K).astype(np.int8); B = rng.integers(-128, 128, size=K * N).astype(np.int8)
+    A[:5] = -128; B[:5] = -128
+    dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    Cd = torch.empty(M * N, dtype=torch.int32, device="cuda")
+    lib = abi.load()
+    ops.Qgemul(Cd, dA, dB, plan8)                                # first call: function attributes etc.
+    torch.cuda.synchronize(); lib.qb200_launch_count_reset()
+    ops.Qgemul(Cd, dA, dB, plan8)
+    torch.cuda.synchronize()
+    assert lib.qb200_launch_count() == 1                         # the GEMM alone: no pack kernels
+    C32 = torch.empty_like(Cd)
+    lib.qb200_launch_count_reset()
+    ops.Qgemul(C32, dA.to(torch.int32), dB.to(torch.int32), plan32)
+    torch.cuda.synchronize()
+    assert lib.qb200_launch_count() == 3 and torch.equal(Cd, C32)
+    if M * N * K <= 1 << 26:
+        assert np.array_equal(Cd.cpu().numpy(), oracle.gemul_batched(plan8, A, B, 1))
+    else:
+        rows = torch.arange(0, M, 61, device="cuda")
+        ref = dA.view(M, K)[rows].double() @ dB.view(N, K).t().double()
+        assert torch.equal(Cd.view(N, M).t()[rows].double(), ref)
+    # word-aligned only: staged through the pack kernels
+    bufA = torch.zeros(M * K + 16, dtype=torch.int8, device="cuda"); bufA[1:1 + M * K] = dA
+    C3 = torch.empty_like(Cd)
+    ops.Qgemul(C3, bufA[1:1 + M * K], dB, plan8)
+    assert torch.equal(C3, Cd)

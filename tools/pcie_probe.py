@@ -1,7 +1,7 @@
 """Host<->device link ceiling of this box with N GPUs copying AT THE SAME TIME (python tools/pcie_probe.py --gpus N):
 per direction alone, both directions at once, with the chunk sizes and 2:1 / 1:1 byte ratios of the library's host
 pipeline.  One process per GPU (like bench.py under torchrun), pinned buffers, a barrier before every timed phase; the
-result is what bounds the `e2e` figure of bench.py and its 1 -> 8 GPU curve.  --wc also tries write-combined buffers."""
+result is what bounds the `e2e` figure of bench.py and its 1 -> 8 GPU curve."""
 import argparse
 import json
 import multiprocessing as mp
