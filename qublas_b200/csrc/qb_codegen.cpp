@@ -72,6 +72,24 @@ void gemul_clamp_thresholds(const GemulProg &g, long long *p_hi, long long *p_lo
     else       { *p_hi = g.mul.hi >> (-s); *p_lo = -((-(g.mul.lo)) >> (-s)); }
 }
 
+// Shared memory of the register-tile template (qb_fast_gemul.cuh:GemulTile) for `group` instances per CTA: a two-stage
+// ring of staged instances, plus -- when the kernel makes a pass over every staged instance (FP32 conversion, operand
+// ranges for the clamp elision, packed words) and the budget allows -- a separate 32-bit copy the tiles read (*sep).
+// Packed int16 words cannot do without the copy: 0 is returned when it does not fit.
+uint64_t gemul_tile_smem(const qb_gemul_plan &p, const GemulProg &g, int group, bool *sep)
+{
+    const uint64_t words = (uint64_t)(group > 0 ? group : 1) * ((uint64_t)p.M * p.K + (uint64_t)p.K * p.N);
+    const bool narrow = g.a_wb == 2;
+    const bool dyn = (g.mul.need_lo || g.mul.need_hi) && (g.mul.of == SAT_TCPL || g.mul.of == SAT_SMGN);
+    const bool pass = narrow || dyn || gemul_fp_mul(p, g);
+    const uint64_t stage = words * (uint64_t)g.a_wb, limit = 220 * 1024;
+    const bool s = pass && stage + words * 4 + 64 <= limit;           // one staging buffer + the copy
+    if (narrow && !s) return 0;
+    if (sep) *sep = s;
+    const uint64_t total = s ? stage + words * 4 + 64 : 2 * stage + 64;   // ... or the two-stage ring, converted in place
+    return total <= limit ? total : 0;
+}
+
 std::string emit_gemul_cfg(const std::string &name, const qb_gemul_plan &p, const GemulProg &g, int group)
 {
     std::ostringstream o;
@@ -101,6 +119,11 @@ std::string emit_gemul_cfg(const std::string &name, const qb_gemul_plan &p, cons
         o << "  static constexpr long long P_HI = " << p_hi << "LL, P_LO = " << p_lo << "LL;\n";
         o << "  static constexpr bool FP_MUL = " << (fp ? "true" : "false") << ";\n";
         o << "  static constexpr int FP_SHIFT = " << (s > 0 ? s : 1) << ";\n";
+        bool sep = false;
+        gemul_tile_smem(p, g, group, &sep);
+        o << "  static constexpr bool SEP = " << (sep ? "true" : "false") << ";\n";
+        const Ival ra = type_range(p.a), rb = type_range(p.b);           // operand types' own bounds (32-bit register class: they fit)
+        o << "  static constexpr long long A_LO = " << (long long)ra.lo << "LL, A_HI = " << (long long)ra.hi << "LL, B_LO = " << (long long)rb.lo << "LL, B_HI = " << (long long)rb.hi << "LL;\n";
     }
     o << "};\n";
     return o.str();

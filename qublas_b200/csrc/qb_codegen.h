@@ -26,6 +26,8 @@ std::string emit_plan_bytes(const void *plan, size_t n);
 // The decisions to run a quantizer on the FP32 pipe (shared by the code generator and by qb200_selftest_fp, which sweeps
 // every operand pair of exactly those nodes against the integer form).
 bool gemul_fp_mul(const qb_gemul_plan &p, const GemulProg &g);
+// dynamic shared memory of the register-tile template for `group` instances per CTA (0: does not fit); *sep: separate 32-bit copy
+uint64_t gemul_tile_smem(const qb_gemul_plan &p, const GemulProg &g, int group, bool *sep);
 void gemul_clamp_thresholds(const GemulProg &g, long long *p_hi, long long *p_lo);
 struct CgemulFp { bool fa = false, fb = false, fc = false, fadd_ab = false, fadd_ba = false; Ival ab, cd, ba; };
 CgemulFp cgemul_fp(const qb_cgemul_plan &p, const CGemulProg &g);

@@ -62,9 +62,31 @@ struct GemulTile {
     // Packed words are staged as they are and widened by the conversion pass into a separate single-buffered region.
     static constexpr int WORD = (int)sizeof(typename Cfg::WA);
     static constexpr bool NARROW = WORD == 2;
+    // One pass over each staged instance (gemul_tile_body): exact int->float conversion for the FP32-FMA product quantizer,
+    // the per-instance operand ranges of the dynamic clamp elision, widening of packed words.
+    static constexpr bool DYN = (Cfg::mul().need_lo || Cfg::mul().need_hi) && (Cfg::mul().of == SAT_TCPL || Cfg::mul().of == SAT_SMGN);
+    static constexpr bool PASS = DYN || Cfg::FP_MUL || NARROW;
+    // SEP: the pass writes a separate single-buffered 32-bit copy (the host grants it when shared memory allows) instead of
+    // converting in place; only then can the copy be laid out differently from the staged instance (swizzles below).
+    static constexpr bool SEP = PASS && Cfg::SEP;
     static constexpr uint32_t STAGE_BYTES = G * (A_WORDS + B_WORDS) * WORD;
-    static constexpr uint32_t WIDE_BYTES = NARROW ? G * (A_WORDS + B_WORDS) * 4 : 0;
-    static constexpr uint32_t SMEM_BYTES = 2 * STAGE_BYTES + WIDE_BYTES + 64;
+    static constexpr uint32_t WIDE_BYTES = SEP ? G * (A_WORDS + B_WORDS) * 4 : 0;
+    // With the separate copy one staging buffer is enough: it is free again as soon as the pass is over, and the next
+    // instance streams into it while the tiles work on the copy.  Converting in place needs the two-stage ring.
+    static constexpr int NSTAGE = SEP ? 1 : 2;
+    static constexpr uint32_t SMEM_BYTES = NSTAGE * STAGE_BYTES + WIDE_BYTES + 64;
+    // Lane -> tile mapping.  The cost of a 16-byte shared-memory load depends on how the lanes share addresses
+    // (tools/lds_probe.cu, profiles/r2_lds_probe.jsonl; ncu counts the same two classes as 4 and 2 wavefronts): it is at
+    // the fast rate when every aligned group of four lanes reads at most two distinct 16-byte chunks, and takes 1.6x as long
+    // otherwise -- no matter how few chunks the warp reads in total.  With tiles numbered row by row, four consecutive lanes
+    // read four different A chunks.  PATCH: a warp owns 8 x 4 tiles with the lane bits interleaved (tx0, ty0, tx1, ty1, tx2),
+    // so a group of four lanes spans 2 x 2 tiles: two A chunks and two B chunks; the warp reads 128 contiguous bytes of A.
+    static constexpr bool PATCH = G == 1 && (M / TM) % 8 == 0 && (N / TN) % 4 == 0;
+    // A K-contiguous operand (A stored transposed, B stored plain) puts the row blocks of a warp 4*K words apart, i.e. in the
+    // same banks; the separate copy XORs the 16-byte chunk index with (row / 4) % 4, which spreads them over four bank groups.
+    static constexpr bool SWZ_A = SEP && PATCH && Cfg::TRANS_A && K % 16 == 0;
+    static constexpr bool SWZ_B = SEP && PATCH && !Cfg::TRANS_B && K % 16 == 0;
+    static_assert(!NARROW || SEP, "packed words are widened into the separate copy");
     static_assert(M % TM == 0 && N % TN == 0 && TM == 4 && TN == 4, "tile shape");
     static constexpr bool K_POW2 = (K & (K - 1)) == 0;         // otherwise the pending nodes go through the flush program
     static_assert(K % KC == 0 && K >= KC, "K must be a multiple of 8");
@@ -143,6 +165,71 @@ QB_DEV I stack_flush(const I (&st)[NTOP > 0 ? NTOP : 1], I cur)
 
 constexpr QStage stage_without_clamps(QStage q) { q.need_lo = 0; q.need_hi = 0; return q; }
 
+// ---- deferred-shift tree ("S form") -------------------------------------------------------------------------------
+// When level 0 is an exact add and every level above it is a clamp-free halving with a data-independent bias --
+// v = (x + y + b) >> 1 with b = 1 (RND::POS_INF) or b = 0 (RND::NEG_INF, TRN::TCPL at a 1-bit shift) -- a node is carried
+// as its PRE-SHIFT sum S (value = S >> 1), and a merge is S' = (Sa >> 1) + (Sb >> 1) + b: one SHF and one LEA.HI.  The
+// bias needs no instruction at all: ((S + 2e) >> 1) == (S >> 1) + e exactly, so the +b of a level-l node is pushed down
+// its chain of left children and lands, as b * 2^(l-1), in the additive constant of the leftmost 4-product group below
+// it -- a constant the level-0/1 IADD3 carries anyway (it also removes the FFMA magic-constant bias).  Same bits as the
+// per-level quantizers (QuBLAS.h:3185-3194 applied per tree level, :4936-4941); tests compare with the oracle and with
+// the runtime-descriptor kernels.
+template <class Cfg> __host__ __device__ constexpr bool s_form_ok()
+{
+    typedef GemulTile<Cfg, 4, 4> T;
+    if (!T::K_POW2 || Cfg::NLEV < 3 || T::NCH > 8 || T::BLOCK > 512) return false;       // needs the fully unrolled chunk loop
+    constexpr AddStage l0 = Cfg::lvl(0);
+    if (l0.q.shift != 0 || l0.q.need_lo || l0.q.need_hi || l0.q.wide || l0.shl_a || l0.shl_b || l0.sub) return false;
+    if (l0.q.of == WRP_TCPL && (l0.q.need_lo || l0.q.need_hi)) return false;
+    for (int l = 1; l < Cfg::NLEV; ++l) {
+        const AddStage s = Cfg::lvl(l);
+        if (s.q.shift != 1 || s.q.need_lo || s.q.need_hi || s.q.wide || s.shl_a || s.shl_b || s.sub) return false;
+        if (!(s.q.qu == RND_POS_INF || s.q.qu == RND_NEG_INF || s.q.qu == TRN_TCPL)) return false;
+    }
+    return true;
+}
+// additive constant of 4-product group g (0 .. K/4-1): the level-1 bias plus every bias pushed down from the levels above
+template <class Cfg> __host__ __device__ constexpr int s_form_const(int g)
+{
+    int c = Cfg::lvl(1).q.qu == RND_POS_INF ? 1 : 0;
+    for (int l = 2; l < Cfg::NLEV; ++l)
+        if (g % (1 << (l - 1)) == 0 && Cfg::lvl(l).q.qu == RND_POS_INF) c += 1 << (l - 1);
+    return c;
+}
+// level-indexed stack of pre-shift sums; slot L holds a pending node of level 2 + L
+template <class Cfg, int L, int NTOP, typename I>
+QB_DEV void s_push(I (&st)[NTOP > 0 ? NTOP : 1], uint32_t c, I S, I &result)
+{
+    if constexpr (L >= NTOP) {
+        result = S;
+    } else {
+        if ((c >> L) & 1) s_push<Cfg, L + 1, NTOP, I>(st, c, (I)((st[L] >> 1) + (S >> 1)), result);
+        else st[L] = S;
+    }
+}
+
+// Fragment addressing shared by both tile loops: 16-byte chunk pointers into the 32-bit operands the tiles read.  kc = k0 / 4
+// is a compile-time constant once the chunk loop is unrolled, so with a swizzled operand the address is one of four
+// per-thread base registers (kc % 4 XOR the thread's row-block index) plus an immediate.
+template <class Cfg>
+struct TileFrag {
+    typedef GemulTile<Cfg, 4, 4> T;
+    const int4 *a[4], *b[4];
+    QB_DEV TileFrag(const int32_t *As, const int32_t *Bs, int i0, int j0)
+    {
+        const int swa = T::SWZ_A ? (i0 >> 2) & 3 : 0, swb = T::SWZ_B ? (j0 >> 2) & 3 : 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            a[q] = (const int4 *)As + (Cfg::TRANS_A ? i0 * (T::K / 4) + (q ^ swa) : (i0 >> 2));
+            b[q] = (const int4 *)Bs + (Cfg::TRANS_B ? (j0 >> 2) : j0 * (T::K / 4) + (q ^ swb));
+        }
+    }
+    // A: row i0 + u at k-chunk kc (stored transposed: k contiguous) or rows i0 .. i0+3 at k = 4 kc + u (plain: i contiguous)
+    QB_DEV int4 lda(int u, int kc) const { return Cfg::TRANS_A ? a[kc & 3][u * (T::K / 4) + (kc & ~3)] : a[0][((4 * kc + u) * T::M) >> 2]; }
+    // B: column j0 + u at k-chunk kc (plain: k contiguous) or columns j0 .. j0+3 at k = 4 kc + u (stored transposed)
+    QB_DEV int4 ldb(int u, int kc) const { return Cfg::TRANS_B ? b[0][((4 * kc + u) * T::N) >> 2] : b[kc & 3][u * (T::K / 4) + (kc & ~3)]; }
+};
+
 // One instance's 4x4 register tile.  CLAMP = false is the same arithmetic with Qmul's saturation removed;
 // it is selected per instance when the instance's own operand ranges prove that no product can saturate.
 template <class Cfg, bool CLAMP>
@@ -150,11 +237,10 @@ QB_DEV void tile_compute(const int32_t *As, const int32_t *Bs, int i0, int j0, t
 {
     typedef GemulTile<Cfg, 4, 4> T;
     typedef typename T::I I;
-    constexpr int M = T::M, K = T::K, NTOP = T::NTOP;
+    constexpr int NTOP = T::NTOP;
     constexpr QStage mulq = CLAMP ? Cfg::mul() : stage_without_clamps(Cfg::mul());
     constexpr AddStage l0 = Cfg::lvl(0), l1 = Cfg::lvl(1), l2 = Cfg::lvl(2);
-    const int4 *As4 = (const int4 *)As;
-    const int4 *Bs4 = (const int4 *)Bs;
+    const TileFrag<Cfg> fr(As, Bs, i0, j0);
     I st[4][4][NTOP > 0 ? NTOP : 1];
     // The chunk loop is unrolled (up to 8 chunks = the whole K = 64 of config 3): the branches of the level-indexed stack
     // on the chunk counter then fold at compile time, the stack slots get exact live ranges instead of being loop-carried,
@@ -170,15 +256,23 @@ QB_DEV void tile_compute(const int32_t *As, const int32_t *Bs, int i0, int j0, t
         I half0[4][4];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int k0 = c * 8 + h * 4;
             // a 4 (i) x 4 (k) block of op(A) and a 4 (k) x 4 (j) block of op(B) as four 16-byte loads each; which index runs
             // inside a load depends on the storage: A is M x K column-major (i contiguous), transposed K x M (k contiguous);
             // B is K x N column-major (k contiguous), transposed N x K (j contiguous)
             int4 bq[4], aq[4];
+            if constexpr (CHUNK_UNROLL >= T::NCH) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) bq[u] = Cfg::TRANS_B ? Bs4[((k0 + u) * T::N + j0) >> 2] : Bs4[((j0 + u) * K + k0) >> 2];
+                for (int u = 0; u < 4; ++u) { bq[u] = fr.ldb(u, 2 * (int)c + h); aq[u] = fr.lda(u, 2 * (int)c + h); }
+            } else {
+                // rolled chunk loop: the chunk index is a run-time value, the XOR of a swizzled operand is computed per load
+                const int k0 = c * 8 + h * 4;
+                const int swa = T::SWZ_A ? (i0 >> 2) & 3 : 0, swb = T::SWZ_B ? (j0 >> 2) & 3 : 0;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) aq[u] = Cfg::TRANS_A ? As4[((i0 + u) * K + k0) >> 2] : As4[((k0 + u) * M + i0) >> 2];
+                for (int u = 0; u < 4; ++u) {
+                    bq[u] = Cfg::TRANS_B ? ((const int4 *)Bs)[((k0 + u) * T::N + j0) >> 2] : ((const int4 *)Bs)[(j0 + u) * (T::K / 4) + ((k0 >> 2) ^ swb)];
+                    aq[u] = Cfg::TRANS_A ? ((const int4 *)As)[(i0 + u) * (T::K / 4) + ((k0 >> 2) ^ swa)] : ((const int4 *)As)[((k0 + u) * T::M + i0) >> 2];
+                }
+            }
             auto a_at = [&](int ii, int kk) -> I { return Cfg::TRANS_A ? (&aq[ii].x)[kk] : (&aq[kk].x)[ii]; };
             auto b_at = [&](int kk, int jj) -> I { return Cfg::TRANS_B ? (&bq[kk].x)[jj] : (&bq[jj].x)[kk]; };
 #pragma unroll
@@ -225,6 +319,88 @@ QB_DEV void tile_compute(const int32_t *As, const int32_t *Bs, int i0, int j0, t
     }
 }
 
+// The same tile in S form (s_form_ok): JW of its four columns per pass over K (JW = 4: one pass; JW = 2: two passes, the
+// A fragments are read twice from shared memory but only 8 accumulator chains are live).  out(jj, v0..v3) receives the four
+// finished rows of column j0 + jj.
+#ifndef QB_SFORM_JW
+#define QB_SFORM_JW 2
+#endif
+template <class Cfg, bool CLAMP, int JW, class Out>
+QB_DEV void tile_compute_s(const int32_t *As, const int32_t *Bs, int i0, int j0, Out out)
+{
+    typedef GemulTile<Cfg, 4, 4> T;
+    typedef typename T::I I;
+    constexpr int NTOP = T::NTOP;
+    constexpr QStage mulq = CLAMP ? Cfg::mul() : stage_without_clamps(Cfg::mul());
+    static_assert(JW == 4 || JW == 2, "columns per pass");
+    // the passes must stay sequential (unrolled, the scheduler interleaves them and every chain is live again)
+#pragma unroll 1
+    for (int jp = 0; jp < 4; jp += JW) {
+        asm volatile("" ::: "memory");                        // keep the (pass-invariant) A fragment loads inside their pass
+        const TileFrag<Cfg> fr(As, Bs + (Cfg::TRANS_B ? 0 : jp * T::K), i0, j0);      // plain B: the pass starts at column j0 + jp (same row block: same swizzle)
+        I st[4][JW][NTOP > 0 ? NTOP : 1], res[4][JW];
+#pragma unroll
+        for (uint32_t c = 0; c < (uint32_t)T::NCH; ++c) {
+            I half0[4][JW];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int kc = 2 * (int)c + h;
+                int4 bq[4], aq[4];
+#pragma unroll
+                for (int u = 0; u < (Cfg::TRANS_B ? 4 : JW); ++u) bq[u] = fr.ldb(u, kc);            // stored transposed: j contiguous, all four columns come along
+#pragma unroll
+                for (int u = 0; u < 4; ++u) aq[u] = fr.lda(u, kc);
+                auto a_at = [&](int ii, int kk) -> I { return Cfg::TRANS_A ? (&aq[ii].x)[kk] : (&aq[kk].x)[ii]; };
+                auto b_at = [&](int kk, int jj) -> I {
+                    if constexpr (!Cfg::TRANS_B) return (&bq[jj].x)[kk];
+                    else if constexpr (JW == 4) return (&bq[kk].x)[jj];
+                    else return jp ? (&bq[kk].z)[jj] : (&bq[kk].x)[jj];            // second pass: columns 2, 3
+                };
+#pragma unroll
+                for (int jj = 0; jj < JW; ++jj) {
+                    const I b0 = b_at(0, jj), b1 = b_at(1, jj), b2 = b_at(2, jj), b3 = b_at(3, jj);
+#pragma unroll
+                    for (int ii = 0; ii < 4; ++ii) {
+                        const I a0 = a_at(ii, 0), a1 = a_at(ii, 1), a2 = a_at(ii, 2), a3 = a_at(ii, 3);
+                        // four products -> the pre-shift level-1 sum (two IADD3): level 0 is exact, the constant removes the
+                        // FFMA bias and carries every rounding bias that belongs to this group
+                        uint32_t sum;
+                        if constexpr (Cfg::FP_MUL) {
+                            constexpr int S = Cfg::FP_SHIFT;
+                            sum = (uint32_t)fp_mul_apply<S, true>(__int_as_float(a0), __int_as_float(b0), mulq) + (uint32_t)fp_mul_apply<S, true>(__int_as_float(a1), __int_as_float(b1), mulq) +
+                                  (uint32_t)fp_mul_apply<S, true>(__int_as_float(a2), __int_as_float(b2), mulq) + (uint32_t)fp_mul_apply<S, true>(__int_as_float(a3), __int_as_float(b3), mulq) -
+                                  4u * (uint32_t)fp_kbits<S>();
+                        } else {
+                            sum = (uint32_t)mul_apply<I, true>(a0, b0, mulq) + (uint32_t)mul_apply<I, true>(a1, b1, mulq) + (uint32_t)mul_apply<I, true>(a2, b2, mulq) + (uint32_t)mul_apply<I, true>(a3, b3, mulq);
+                        }
+                        const I S1 = (I)(sum + (uint32_t)s_form_const<Cfg>(2 * (int)c + h));
+                        if (h == 0) half0[ii][jj] = S1;
+                        else s_push<Cfg, 0, NTOP, I>(st[ii][jj], c, (I)((half0[ii][jj] >> 1) + (S1 >> 1)), res[ii][jj]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int jj = 0; jj < JW; ++jj) out(jp + jj, (I)(res[0][jj] >> 1), (I)(res[1][jj] >> 1), (I)(res[2][jj] >> 1), (I)(res[3][jj] >> 1));   // root: pre-shift sum -> value
+    }
+}
+
+// Which operand extremes the dynamic clamp elision has to find per instance.  A corner product of the operand TYPES' own
+// bounds that already satisfies the thresholds can never be the reason for a clamp, so the pass only tracks the side
+// (minima, maxima) that takes part in a corner that can; the other side enters the check with the type's static bound.
+template <class Cfg> __host__ __device__ constexpr bool dyn_violates(long long p)
+{
+    return (Cfg::mul().need_hi && p > Cfg::P_HI) || (Cfg::mul().need_lo && p < Cfg::P_LO);
+}
+template <class Cfg> __host__ __device__ constexpr bool dyn_track_hi()
+{
+    return dyn_violates<Cfg>(Cfg::A_LO * Cfg::B_HI) || dyn_violates<Cfg>(Cfg::A_HI * Cfg::B_LO) || dyn_violates<Cfg>(Cfg::A_HI * Cfg::B_HI);
+}
+template <class Cfg> __host__ __device__ constexpr bool dyn_track_lo()
+{
+    return dyn_violates<Cfg>(Cfg::A_LO * Cfg::B_HI) || dyn_violates<Cfg>(Cfg::A_HI * Cfg::B_LO) || dyn_violates<Cfg>(Cfg::A_LO * Cfg::B_LO);
+}
+
 template <class Cfg>
 QB_DEV void gemul_tile_body(const typename Cfg::WA *__restrict__ A, const typename Cfg::WB *__restrict__ B, int32_t *__restrict__ C, uint64_t batch)
 {
@@ -232,12 +408,20 @@ QB_DEV void gemul_tile_body(const typename Cfg::WA *__restrict__ A, const typena
     typedef typename T::I I;
     constexpr int M = T::M;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t *bars = (uint64_t *)(smem_raw + 2 * T::STAGE_BYTES + T::WIDE_BYTES);
-    __shared__ int range_smem[32][4];
+    uint64_t *bars = (uint64_t *)(smem_raw + T::NSTAGE * T::STAGE_BYTES + T::WIDE_BYTES);
+    __shared__ int4 range_smem[32];                                // per warp: { min A, max A, min B, max B }
 
     const int tid = threadIdx.x;
     const int g = T::G == 1 ? 0 : tid / T::TPI, tl = T::G == 1 ? tid : tid - g * T::TPI;       // instance within the group, thread within the instance
-    const int tx = tl % (M / 4), ty = tl / (M / 4);
+    int tx, ty;
+    if constexpr (T::PATCH) {                                      // a warp owns 8 x 4 tiles, lane bits interleaved (GemulTile::PATCH)
+        constexpr int WX = (M / 4) / 8;
+        const int wp = tl >> 5;
+        tx = (wp % WX) * 8 + ((tl & 1) | ((tl >> 1) & 2) | ((tl >> 2) & 4));
+        ty = (wp / WX) * 4 + (((tl >> 1) & 1) | ((tl >> 2) & 2));
+    } else {
+        tx = tl % (M / 4); ty = tl / (M / 4);
+    }
     const int i0 = tx * 4, j0 = ty * 4;
 
     if (tid == 0) {
@@ -271,97 +455,97 @@ QB_DEV void gemul_tile_body(const typename Cfg::WA *__restrict__ A, const typena
     // operand values (config 3: min x min).  One pass over the staged instance finds its actual operand
     // ranges; if even the extreme corner products stay inside [P_LO, P_HI] (host-computed, conservative),
     // the clamp-free instantiation runs.  Same bits either way.
-    constexpr bool DYN = (mulq.need_lo || mulq.need_hi) && (mulq.of == SAT_TCPL || mulq.of == SAT_SMGN);
-    constexpr bool PASS = DYN || Cfg::FP_MUL || T::NARROW;
+    constexpr bool DYN = T::DYN, PASS = T::PASS;
+    constexpr bool TRACK_LO = DYN && dyn_track_lo<Cfg>(), TRACK_HI = DYN && dyn_track_hi<Cfg>();
 
     for (uint32_t it = 0; inst < ngroups; inst += gridDim.x, ++it) {
-        const int s = it & 1;
+        const int s = T::NSTAGE == 2 ? it & 1 : 0;
         const uint64_t next = inst + gridDim.x;
-        if (tid == 0 && next < ngroups) {
-            if constexpr (Cfg::FP_MUL) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes (int->float) before TMA refill
-            issue(next, s ^ 1);                                   // stage s^1 was released by the barrier below
+        if constexpr (T::NSTAGE == 2) {
+            if (tid == 0 && next < ngroups) {
+                if constexpr (PASS && Cfg::FP_MUL) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // in-place int->float writes (generic proxy) before the TMA refill
+                issue(next, s ^ 1);                               // stage s^1 was released by the barrier that ended the previous iteration
+            }
         }
-        mbar_wait(&bars[s], (it >> 1) & 1);
+        mbar_wait(&bars[s], T::NSTAGE == 2 ? (it >> 1) & 1 : it & 1);
         unsigned char *stage = smem_raw + (size_t)s * T::STAGE_BYTES;
-        int32_t *As = T::NARROW ? (int32_t *)(smem_raw + 2 * T::STAGE_BYTES) : (int32_t *)stage;      // 32-bit operands the tiles read
+        int32_t *As = T::SEP ? (int32_t *)(smem_raw + T::NSTAGE * T::STAGE_BYTES) : (int32_t *)stage;      // 32-bit operands the tiles read
         int32_t *Bs = As + T::G * T::A_WORDS;
         bool clamp = true;
         if constexpr (PASS) {
-            // one pass over the staged operands: exact int->float conversion (FP_MUL) and per-instance ranges (DYN)
+            // one pass over the staged operands: exact int->float conversion (FP_MUL), per-instance ranges (DYN), widening of
+            // packed words, and the swizzle of K-contiguous operands (SEP: into the separate copy)
             int lo[2] = { 0x7fffffff, 0x7fffffff }, hi[2] = { (int)0x80000000, (int)0x80000000 };
+            auto scan4 = [&](int part, const int4 &v) {
+                if constexpr (TRACK_LO) lo[part] = min3i(min3i(lo[part], v.x, v.y), v.z, v.w);      // two VIMNMX3 per four words
+                if constexpr (TRACK_HI) hi[part] = max3i(max3i(hi[part], v.x, v.y), v.z, v.w);
+            };
+            auto put4 = [&](int part, int4 *w, int i, const int4 &v) {          // i = 16-byte chunk index within the part
+                const bool swz = part ? T::SWZ_B : T::SWZ_A;
+                const int o = swz ? i ^ ((i / T::K) & 3) : i;                    // chunk ^ (row / 4) % 4, row = i / (K / 4)
+                if constexpr (Cfg::FP_MUL) ((float4 *)w)[o] = make_float4(__int2float_rn(v.x), __int2float_rn(v.y), __int2float_rn(v.z), __int2float_rn(v.w));
+                else w[o] = v;
+            };
 #pragma unroll
             for (int part = 0; part < 2; ++part) {
                 int4 *w = (int4 *)(part ? Bs : As);
                 if constexpr (T::NARROW) {
-                    // packed int16 words: widen (sign-extend) into the 32-bit region, converting / scanning on the way
+                    // packed int16 words: widen (sign-extend) into the 32-bit copy, converting / scanning on the way
                     const int4 *raw = (const int4 *)(stage + (part ? T::G * T::A_WORDS * 2 : 0));
                     const int n8 = (part ? T::G * T::B_WORDS : T::G * T::A_WORDS) / 8;
                     for (int i = tid; i < n8; i += T::BLOCK) {
                         const int4 v = raw[i];
-                        const int e[8] = { (int)(short)(v.x & 0xffff), v.x >> 16, (int)(short)(v.y & 0xffff), v.y >> 16,
-                                           (int)(short)(v.z & 0xffff), v.z >> 16, (int)(short)(v.w & 0xffff), v.w >> 16 };
-                        if constexpr (DYN) {
-                            lo[part] = min3i(min3i(min3i(min3i(lo[part], e[0], e[1]), e[2], e[3]), e[4], e[5]), e[6], e[7]);
-                            hi[part] = max3i(max3i(max3i(max3i(hi[part], e[0], e[1]), e[2], e[3]), e[4], e[5]), e[6], e[7]);
-                        }
-                        if constexpr (Cfg::FP_MUL) {
-                            ((float4 *)w)[2 * i] = make_float4(__int2float_rn(e[0]), __int2float_rn(e[1]), __int2float_rn(e[2]), __int2float_rn(e[3]));
-                            ((float4 *)w)[2 * i + 1] = make_float4(__int2float_rn(e[4]), __int2float_rn(e[5]), __int2float_rn(e[6]), __int2float_rn(e[7]));
-                        } else {
-                            w[2 * i] = make_int4(e[0], e[1], e[2], e[3]);
-                            w[2 * i + 1] = make_int4(e[4], e[5], e[6], e[7]);
-                        }
-                    }
-                    continue;
-                }
-                constexpr int N4A = T::G * T::A_WORDS / 4, N4B = T::G * T::B_WORDS / 4;      // the whole group (a short last group leaves stale words: harmless, conservative for the ranges)
-                const int n4 = part ? N4B : N4A;
-                constexpr int PER = ((N4A > N4B ? N4A : N4B) + T::BLOCK - 1) / T::BLOCK;
-                if constexpr (PER <= 8) {
-                    // all loads of this part in flight first, then ranges / conversion / stores
-                    int4 v[PER];
-#pragma unroll
-                    for (int u = 0; u < PER; ++u) { const int i = tid + u * T::BLOCK; if (i < n4) v[u] = w[i]; }
-#pragma unroll
-                    for (int u = 0; u < PER; ++u) {
-                        const int i = tid + u * T::BLOCK;
-                        if (i < n4) {
-                            if constexpr (DYN) {
-                                lo[part] = min3i(min3i(lo[part], v[u].x, v[u].y), v[u].z, v[u].w);      // two VIMNMX3 per four words
-                                hi[part] = max3i(max3i(hi[part], v[u].x, v[u].y), v[u].z, v[u].w);
-                            }
-                            if constexpr (Cfg::FP_MUL)
-                                ((float4 *)w)[i] = make_float4(__int2float_rn(v[u].x), __int2float_rn(v[u].y), __int2float_rn(v[u].z), __int2float_rn(v[u].w));
-                        }
+                        const int4 e0 = make_int4((int)(short)(v.x & 0xffff), v.x >> 16, (int)(short)(v.y & 0xffff), v.y >> 16);
+                        const int4 e1 = make_int4((int)(short)(v.z & 0xffff), v.z >> 16, (int)(short)(v.w & 0xffff), v.w >> 16);
+                        scan4(part, e0); scan4(part, e1);
+                        put4(part, w, 2 * i, e0); put4(part, w, 2 * i + 1, e1);
                     }
                 } else {
-                    for (int i = tid; i < n4; i += T::BLOCK) {
-                        const int4 v = w[i];
-                        if constexpr (DYN) {
-                            lo[part] = min3i(min3i(lo[part], v.x, v.y), v.z, v.w);
-                            hi[part] = max3i(max3i(hi[part], v.x, v.y), v.z, v.w);
+                    const int4 *raw = (const int4 *)(stage + (part ? T::G * T::A_WORDS * 4 : 0));
+                    constexpr int N4A = T::G * T::A_WORDS / 4, N4B = T::G * T::B_WORDS / 4;      // the whole group (a short last group leaves stale words: harmless, conservative for the ranges)
+                    const int n4 = part ? N4B : N4A;
+                    constexpr int PER = ((N4A > N4B ? N4A : N4B) + T::BLOCK - 1) / T::BLOCK;
+                    if constexpr (PER <= 8) {
+                        // all loads of this part in flight first, then ranges / conversion / stores
+                        int4 v[PER];
+#pragma unroll
+                        for (int u = 0; u < PER; ++u) { const int i = tid + u * T::BLOCK; if (i < n4) v[u] = raw[i]; }
+#pragma unroll
+                        for (int u = 0; u < PER; ++u) {
+                            const int i = tid + u * T::BLOCK;
+                            if (i < n4) { scan4(part, v[u]); if constexpr (T::SEP || Cfg::FP_MUL) put4(part, w, i, v[u]); }
                         }
-                        if constexpr (Cfg::FP_MUL)
-                            ((float4 *)w)[i] = make_float4(__int2float_rn(v.x), __int2float_rn(v.y), __int2float_rn(v.z), __int2float_rn(v.w));
+                    } else {
+                        for (int i = tid; i < n4; i += T::BLOCK) {
+                            const int4 v = raw[i];
+                            scan4(part, v);
+                            if constexpr (T::SEP || Cfg::FP_MUL) put4(part, w, i, v);
+                        }
                     }
                 }
             }
             if constexpr (DYN) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
-                    lo[0] = imin<int>(lo[0], __shfl_xor_sync(0xffffffffu, lo[0], o)); hi[0] = imax<int>(hi[0], __shfl_xor_sync(0xffffffffu, hi[0], o));
-                    lo[1] = imin<int>(lo[1], __shfl_xor_sync(0xffffffffu, lo[1], o)); hi[1] = imax<int>(hi[1], __shfl_xor_sync(0xffffffffu, hi[1], o));
+                    if constexpr (TRACK_LO) { lo[0] = imin<int>(lo[0], __shfl_xor_sync(0xffffffffu, lo[0], o)); lo[1] = imin<int>(lo[1], __shfl_xor_sync(0xffffffffu, lo[1], o)); }
+                    if constexpr (TRACK_HI) { hi[0] = imax<int>(hi[0], __shfl_xor_sync(0xffffffffu, hi[0], o)); hi[1] = imax<int>(hi[1], __shfl_xor_sync(0xffffffffu, hi[1], o)); }
                 }
-                if ((tid & 31) == 0) { range_smem[tid >> 5][0] = lo[0]; range_smem[tid >> 5][1] = hi[0]; range_smem[tid >> 5][2] = lo[1]; range_smem[tid >> 5][3] = hi[1]; }
+                if ((tid & 31) == 0) range_smem[tid >> 5] = make_int4(lo[0], hi[0], lo[1], hi[1]);
             }
             __syncthreads();
+            if constexpr (T::NSTAGE == 1) {
+                if (tid == 0 && next < ngroups) issue(next, 0);    // the pass has consumed the staged instance: stream the next one in behind the tiles
+            }
             if constexpr (DYN) {
                 int alo = 0x7fffffff, ahi = (int)0x80000000, blo = 0x7fffffff, bhi = (int)0x80000000;
 #pragma unroll
-                for (int wv = 0; wv < T::BLOCK / 32; ++wv) {
-                    alo = imin<int>(alo, range_smem[wv][0]); ahi = imax<int>(ahi, range_smem[wv][1]);
-                    blo = imin<int>(blo, range_smem[wv][2]); bhi = imax<int>(bhi, range_smem[wv][3]);
+                for (int wv = 0; wv < T::BLOCK / 32; wv += 2) {
+                    const int4 r0 = range_smem[wv], r1 = wv + 1 < T::BLOCK / 32 ? range_smem[wv + 1] : r0;
+                    if constexpr (TRACK_LO) { alo = min3i(alo, r0.x, r1.x); blo = min3i(blo, r0.z, r1.z); }
+                    if constexpr (TRACK_HI) { ahi = max3i(ahi, r0.y, r1.y); bhi = max3i(bhi, r0.w, r1.w); }
                 }
+                if constexpr (!TRACK_LO) { alo = (int)Cfg::A_LO; blo = (int)Cfg::B_LO; }          // statically harmless side: the type's own bound
+                if constexpr (!TRACK_HI) { ahi = (int)Cfg::A_HI; bhi = (int)Cfg::B_HI; }
                 const long long c0 = (long long)alo * blo, c1 = (long long)alo * bhi, c2 = (long long)ahi * blo, c3 = (long long)ahi * bhi;
                 const long long pmax = imax<long long>(imax<long long>(c0, c1), imax<long long>(c2, c3));
                 const long long pmin = imin<long long>(imin<long long>(c0, c1), imin<long long>(c2, c3));
@@ -371,26 +555,36 @@ QB_DEV void gemul_tile_body(const typename Cfg::WA *__restrict__ A, const typena
 
         if ((T::BLOCK == T::THREADS || tid < T::THREADS) && (T::G == 1 || (uint32_t)g < group_count(inst))) {   // padding threads / a short last group own no tile
             const int32_t *Ag = As + g * T::A_WORDS, *Bg = Bs + g * T::B_WORDS;
-            I res[4][4];
-            if constexpr (DYN) {
-                if (clamp) tile_compute<Cfg, true>(Ag, Bg, i0, j0, res);
-                else       tile_compute<Cfg, false>(Ag, Bg, i0, j0, res);
-            } else {
-                tile_compute<Cfg, true>(Ag, Bg, i0, j0, res);
-            }
             // converting assignment into C's element type, column-major 128-bit stores
             int32_t *Ci = C + (inst * T::G + g) * T::SC;
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
+            auto store_col = [&](int jj, I r0, I r1, I r2, I r3) {
                 int4 o;
-                o.x = (int32_t)conv_apply<I, true>(res[0][jj], outq);
-                o.y = (int32_t)conv_apply<I, true>(res[1][jj], outq);
-                o.z = (int32_t)conv_apply<I, true>(res[2][jj], outq);
-                o.w = (int32_t)conv_apply<I, true>(res[3][jj], outq);
+                o.x = (int32_t)conv_apply<I, true>(r0, outq);
+                o.y = (int32_t)conv_apply<I, true>(r1, outq);
+                o.z = (int32_t)conv_apply<I, true>(r2, outq);
+                o.w = (int32_t)conv_apply<I, true>(r3, outq);
                 *(int4 *)(Ci + (j0 + jj) * M + i0) = o;
+            };
+            if constexpr (s_form_ok<Cfg>()) {
+                if constexpr (DYN) {
+                    if (clamp) tile_compute_s<Cfg, true, QB_SFORM_JW>(Ag, Bg, i0, j0, store_col);
+                    else       tile_compute_s<Cfg, false, QB_SFORM_JW>(Ag, Bg, i0, j0, store_col);
+                } else {
+                    tile_compute_s<Cfg, true, QB_SFORM_JW>(Ag, Bg, i0, j0, store_col);
+                }
+            } else {
+                I res[4][4];
+                if constexpr (DYN) {
+                    if (clamp) tile_compute<Cfg, true>(Ag, Bg, i0, j0, res);
+                    else       tile_compute<Cfg, false>(Ag, Bg, i0, j0, res);
+                } else {
+                    tile_compute<Cfg, true>(Ag, Bg, i0, j0, res);
+                }
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) store_col(jj, res[0][jj], res[1][jj], res[2][jj], res[3][jj]);
             }
         }
-        __syncthreads();      // everyone is done reading stage s (and range_smem) before it is refilled
+        __syncthreads();      // everyone is done reading the operands (and range_smem) before they are overwritten
     }
 }
 

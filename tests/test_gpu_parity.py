@@ -918,3 +918,32 @@ def test_fp_pipe_quantizers_exhaustive_sweep():
     cplan = ops.make_cgemul_plan(t, t, t, t, lvc[-1], lvc[-1], 256, 1, 256, tf_tags=tags, add_re=lvc, form=TREE_VARIADIC)
     abi.check(lib.qb200_selftest_fp(1, ctypes.cast(ctypes.byref(cplan), ctypes.c_void_p), ctypes.byref(checked), ctypes.byref(bad), ctypes.byref(ex)))
     assert checked.value >= 2 * (1 << 32) + (1 << 33) + 2 * (1 << 32) - (1 << 20) and bad.value == 0, (checked.value, bad.value)
+
+
+@pytest.mark.parametrize("K,modes,fp", [(64, "PPPPP", True), (64, "PNTPN", True), (32, "TTTT", False), (16, "NPP", True), (8, "PP", False), (64, "PPPPP", False)])
+def test_tile_kernel_deferred_shift_tree_vs_oracle(K, modes, fp):
+    """The S form of the register-tile kernel (qb_fast_gemul.cuh: exact level 0, clamp-free halving levels with a
+    data-independent bias -- RND::POS_INF, RND::NEG_INF, TRN::TCPL at a 1-bit shift -- carried as pre-shift sums with the
+    biases folded into compile-time constants) against the oracle and the runtime-descriptor kernel, full-range operands,
+    instances with and without the saturating min x min product."""
+    from qublas_b200.qtypes import RND_NEG_INF, TRN_TCPL
+    m = {"P": RND_POS_INF, "N": RND_NEG_INF, "T": TRN_TCPL}
+    a = QType(7, 8)
+    mul = QType(14, 8, True, RND_CONV if fp else RND_POS_INF, SAT_TCPL)          # CONV: FP32-FMA product; POS_INF: integer product
+    lv = [QType(15, 8, True, RND_POS_INF, SAT_TCPL)] + [QType(15 + l, 8 - l, True, m[modes[l - 1]], SAT_TCPL) for l in range(1, len(modes) + 1)]
+    assert len(lv) == K.bit_length() - 1
+    c = QType(17, 4, True, RND_POS_INF, SAT_TCPL)
+    plan = ops.make_gemul_plan(a, a, c, 64, 32, K, mul=mul, add=lv)
+    batch = 11
+    A = torch.empty(batch * 64 * K, dtype=torch.int32, device="cuda"); B = torch.empty(batch * K * 32, dtype=torch.int32, device="cuda")
+    ops.synth_fill(A, a.raw_min, a.raw_max, 21, 0); ops.synth_fill(B, a.raw_min, a.raw_max, 21, 1)
+    A[:64 * K] = a.raw_min; B[:K * 32] = a.raw_min                                # instance 0: every product saturates
+    A[3 * 64 * K + 5] = a.raw_min; B[3 * K * 32 + 7] = a.raw_min                  # instance 3: the clamped variant on random data
+    Cd = torch.empty(batch * 64 * 32, dtype=torch.int32, device="cuda")
+    ops.Qgemul(Cd, A, B, plan, batch=batch)
+    assert b"tile" in ops.plan_info_gemul(plan).kernel
+    want = oracle.gemul_batched(plan, A.cpu().numpy(), B.cpu().numpy(), batch)
+    assert np.array_equal(Cd.cpu().numpy(), want)
+    C2 = torch.empty_like(Cd)
+    ops.Qgemul(C2, A, B, plan, batch=batch, flags=abi.QB_F_NO_SPECIALIZE)
+    assert torch.equal(Cd, C2)
