@@ -17,7 +17,7 @@ def main():
             continue
         if fn is None or pat not in fn:
             continue
-        m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", l)
+        m = re.match(r"\s+/\*[0-9a-f]{4,5}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", l)
         if m:
             c[m.group(1)] += 1
     print(sum(c.values()), "instructions")
