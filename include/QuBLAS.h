@@ -1023,23 +1023,54 @@ template <class... toArgs, std::size_t... D, class EA, class EB>
 auto Qsub(const Qu_s<dim<D...>, EA> &a, const Qu_s<dim<D...>, EB> &b) { return detail::tensor_ew<QB_EW_SUB, toArgs...>(a, b); }
 
 // ------------------------------------------------------------------------------------------------
-// ANUS: polynomial / piecewise-polynomial non-linearities on scalars (QuBLAS.h:4829-4897), host-only.
+// ANUS: polynomial / piecewise-polynomial non-linearities (QuBLAS.h:4829-4897) and lookup tables (readme.md:66-78).
 // Qpoly<a0, a1, ...>(x) evaluates a0 + x*(a1 + x*(...)) by Horner's rule; the product and the sum
 // of each step are quantized to the type of that step's own coefficient (decltype(a0)).
 // Qapprox<Segment<breakpoint, coeffs...>, ...>(x) picks the first segment whose breakpoint exceeds
 // x.toDouble() (the last one otherwise) and converts the value back to x's type.
+// On a scalar both run on the host, as in the reference.  On a TENSOR (no upstream counterpart: the reference's take one
+// scalar) every element is evaluated on the GPU through qb200_poly_batched -- same quantizers, same bits as the scalar form.
+// Qtable<func>(x) = decltype(x){ func(x.toDouble()) }; the reference documents it in its readme only, the three
+// predefined tables are rsqrtFunc, reciprocalFunc and sqrtFunc; a tensor is looked up on the GPU (qb200_table_batched).
 // ------------------------------------------------------------------------------------------------
 namespace ANUS {
-template <auto a0> constexpr auto Qpoly(auto) { return a0; }
-template <auto a0, auto a1, auto... more> constexpr auto Qpoly(auto x)
+namespace detail {
+template <auto... coeffs> constexpr qb_poly_segment lower_segment(double breakpoint)
+{
+    qb_poly_segment s{};
+    s.breakpoint = breakpoint;
+    s.ncoef = sizeof...(coeffs);
+    std::size_t i = 0;
+    ((s.coef[i].type = ::QuBLAS::detail::lower(std::remove_cvref_t<decltype(coeffs)>::spec), s.coef[i].raw = (int64_t)coeffs.data.data, ++i), ...);
+    return s;
+}
+}  // namespace detail
+template <auto a0> constexpr auto Qpoly(::QuBLAS::isScalar auto) { return a0; }
+template <auto a0, auto a1, auto... more> constexpr auto Qpoly(::QuBLAS::isScalar auto x)
 {
     return Qadd<decltype(a0)>(a0, Qmul<decltype(a0)>(x, Qpoly<a1, more...>(x)));
+}
+template <auto a0, auto... more, std::size_t... D, class E>
+    requires(::QuBLAS::detail::is_scalar<E>::value && sizeof...(more) < QB_POLY_MAX_COEF)
+auto Qpoly(const Qu_s<dim<D...>, E> &x)
+{
+    static constexpr qb_poly_plan plan = [] {
+        qb_poly_plan p{};
+        p.x = ::QuBLAS::detail::lower(E::spec); p.nseg = 1; p.approx = 0; p.len = dim<D...>::elemSize;
+        p.seg[0] = detail::lower_segment<a0, more...>(0.0);
+        return p;
+    }();
+    Qu_s<dim<D...>, std::remove_cvref_t<decltype(a0)>> out;
+    qb_exec ex{ QB_MEM_HOST, -1, nullptr, 0, 0 };
+    ::QuBLAS::detail::check(qb200_poly_batched(&plan, x.raw(), out.raw(), 1, &ex));
+    return out;
 }
 template <double BreakPoint, auto... coeffs> struct Segment {
     static constexpr double breakpoint = BreakPoint;
     static constexpr auto func(auto x) { return Qpoly<coeffs...>(x); }
+    static constexpr qb_poly_segment lowered() { return detail::lower_segment<coeffs...>(BreakPoint); }
 };
-template <class First, class... Rest> constexpr auto Qapprox(auto x)
+template <class First, class... Rest> constexpr auto Qapprox(::QuBLAS::isScalar auto x)
 {
     if constexpr (sizeof...(Rest) == 0) return decltype(x){ First::func(x) };
     else {
@@ -1047,9 +1078,50 @@ template <class First, class... Rest> constexpr auto Qapprox(auto x)
         return Qapprox<Rest...>(x);
     }
 }
+template <class... Segments, std::size_t... D, class E>
+    requires(::QuBLAS::detail::is_scalar<E>::value && sizeof...(Segments) >= 1 && sizeof...(Segments) <= QB_POLY_MAX_SEG)
+auto Qapprox(const Qu_s<dim<D...>, E> &x)
+{
+    static constexpr qb_poly_plan plan = [] {
+        qb_poly_plan p{};
+        p.x = ::QuBLAS::detail::lower(E::spec); p.nseg = sizeof...(Segments); p.approx = 1; p.len = dim<D...>::elemSize;
+        std::size_t i = 0;
+        ((p.seg[i++] = Segments::lowered()), ...);
+        return p;
+    }();
+    Qu_s<dim<D...>, E> out;
+    qb_exec ex{ QB_MEM_HOST, -1, nullptr, 0, 0 };
+    ::QuBLAS::detail::check(qb200_poly_batched(&plan, x.raw(), out.raw(), 1, &ex));
+    return out;
+}
 template <class... Segments> struct Qapprox_s {
-    static constexpr auto execute(auto x) { return Qapprox<Segments...>(x); }
+    static constexpr auto execute(const auto &x) { return Qapprox<Segments...>(x); }
 };
+
+inline constexpr auto rsqrtFunc = [](double v) { return 1.0 / std::sqrt(v); };
+inline constexpr auto reciprocalFunc = [](double v) { return 1.0 / v; };
+inline constexpr auto sqrtFunc = [](double v) { return std::sqrt(v); };
+namespace detail {
+template <auto func> double table_value(double v) { const double r = func(v); return std::isfinite(r) ? r : 0.0; }    // poles and domain errors read as 0
+}
+template <auto func> auto Qtable(::QuBLAS::isScalar auto x) { return decltype(x){ detail::table_value<func>(x.toDouble()) }; }
+template <auto func, std::size_t... D, class E>
+    requires(::QuBLAS::detail::is_scalar<E>::value && E::intB + E::fracB + 1 <= 20)
+auto Qtable(const Qu_s<dim<D...>, E> &x)
+{
+    // one entry per raw value of E, built once per (func, E) with the scalar form
+    static const std::vector<typename E::raw_t> table = [] {
+        constexpr long long lo = -(1ll << (E::intB + E::fracB)), n = 1ll << (E::intB + E::fracB + 1);
+        std::vector<typename E::raw_t> t((std::size_t)n);
+        for (long long r = 0; r < n; r++) { E e; e.data.data = (typename E::raw_t)(lo + r); t[(std::size_t)r] = Qtable<func>(e).data.data; }
+        return t;
+    }();
+    static constexpr qb_qdesc d = ::QuBLAS::detail::lower(E::spec);
+    Qu_s<dim<D...>, E> out;
+    qb_exec ex{ QB_MEM_HOST, -1, nullptr, 0, 0 };
+    ::QuBLAS::detail::check(qb200_table_batched(&d, &d, table.data(), x.raw(), out.raw(), dim<D...>::elemSize, &ex));
+    return out;
+}
 }  // namespace ANUS
 
 // ------------------------------------------------------------------------------------------------

@@ -20,6 +20,7 @@
  *   qb200_tfcmul_batched   <- tensor Qmul<TFComplexMul<...>>(x, y) / Qmul<BasicComplexMul<...>>(x, y)
  *                             include/QuBLAS.h:3783-3811, 4080-4085, 3426-3446
  *   qb200_convert_batched  <- element-wise converting assignment      include/QuBLAS.h:2398-2411, 2759-2830
+ *   qb200_poly_batched     <- ANUS::Qpoly / Qapprox over a tensor         include/QuBLAS.h:4829-4897
  *
  * All functions return 0 on success and a negative QB_E* code on failure; the message is
  * available from qb200_last_error() (thread-local).  Nothing throws.  There is no CPU
@@ -164,6 +165,28 @@ typedef struct qb_convert_plan {
     uint64_t len;
 } qb_convert_plan;
 
+/* ANUS::Qpoly / Segment / Qapprox on tensors (include/QuBLAS.h:4829-4897; the reference evaluates one scalar per call).
+ * A segment is Qpoly<a0, a1, ...>(x) = a0 + x*(a1 + x*(...)) by Horner's rule: at step i the product Qmul<Ai>(x, inner)
+ * and the sum Qadd<Ai>(ai, product) are quantized to Ai = the type of coefficient ai (QuBLAS.h:4846-4853).
+ *   approx == 0: nseg must be 1; out[e] = Qpoly(x[e]), result type = coef[0].type (a single coefficient is returned as is).
+ *   approx == 1: Qapprox<Segment<bp0, ...>, ...>: the first segment whose breakpoint exceeds x.toDouble(), the last one
+ *                otherwise; the value is converted back into x's own type (QuBLAS.h:4866-4888).  breakpoint of the last
+ *                segment is unused.  x wider than 53 bits is refused (toDouble would round). */
+#define QB_POLY_MAX_COEF 8
+#define QB_POLY_MAX_SEG  8
+typedef struct qb_poly_coef { qb_qdesc type; int64_t raw; } qb_poly_coef;
+typedef struct qb_poly_segment {
+    double       breakpoint;
+    uint32_t     ncoef, reserved;
+    qb_poly_coef coef[QB_POLY_MAX_COEF];
+} qb_poly_segment;
+typedef struct qb_poly_plan {
+    qb_qdesc        x;
+    uint32_t        nseg, approx;
+    qb_poly_segment seg[QB_POLY_MAX_SEG];
+    uint64_t        len;
+} qb_poly_plan;
+
 /* What the library decided for a plan (for tests, benchmarks and DESIGN.md tables). */
 typedef struct qb_plan_info {
     int32_t arith_bits;        /* 32 or 64: register arithmetic class of the kernel            */
@@ -226,6 +249,21 @@ int qb200_convert_batched(const qb_convert_plan *plan, const void *in, void *out
 
 int qb200_elementwise_batched(const qb_ew_plan *plan, const void *a, const void *b, void *out,
                               uint64_t batch, const qb_exec *exec);
+
+/* ---- non-linearities around the GEMM ----
+ * qb200_poly_batched       <- ANUS::Qpoly<a0, ...>(x) / ANUS::Qapprox<Segment<...>...>(x), element by element over a tensor
+ * qb200_gemul_poly_batched <- the same applied to every element of a Qgemul result before it is stored (fused epilogue):
+ *                             gemul->c is the type Qgemul converts into and must equal poly->x; C holds words of the
+ *                             polynomial's result type.  poly->len is ignored.
+ * qb200_table_batched      <- ANUS::Qtable<func>(x) of readme.md:66-78 (absent from the header): a lookup table indexed by
+ *                             x's raw value; table[r - raw_min(x)] is the raw result word (out type) for raw input r, built by
+ *                             the host binding as out_type(func(x.toDouble())).  x wider than 20 bits is refused. */
+int qb200_poly_plan_info(const qb_poly_plan *plan, qb_plan_info *info);
+int qb200_poly_batched(const qb_poly_plan *plan, const void *x, void *out, uint64_t batch, const qb_exec *exec);
+int qb200_gemul_poly_batched(const qb_gemul_plan *gemul, const qb_poly_plan *poly, const void *A, const void *B, void *C,
+                             uint64_t batch, const qb_exec *exec);
+int qb200_table_batched(const qb_qdesc *x, const qb_qdesc *out_type, const void *table, const void *in, void *out, uint64_t n,
+                        const qb_exec *exec);
 
 /* ---- the steps on either side of the path in an accuracy sweep ----
  * qb200_quantize_f64  <- Qu_s(double)  include/QuBLAS.h:2387-2393 (exact value, the type's QuMode, then its OfMode)

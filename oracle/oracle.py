@@ -58,6 +58,7 @@ def load():
         L.qbo_tfcmul_batched.argtypes = [vp, vp, vp, vp, u64]
         L.qbo_convert_batched.argtypes = [vp, vp, vp, u64]
         L.qbo_elementwise_batched.argtypes = [vp, vp, vp, vp, u64]
+        L.qbo_poly_batched.argtypes = [vp, vp, vp, u64]
         L.qbo_synth_fill.argtypes = [vp, u64, u32, i64, i64, u64, u64, u64]
         dp = C.POINTER(C.c_double)
         L.qbo_from_double.restype = i64; L.qbo_from_double.argtypes = [C.c_double, qd]
@@ -198,4 +199,13 @@ def elementwise(plan, a, b, batch=1):
     out = np.zeros(batch * plan.len, dtype=np_dtype(_word_bytes(plan.to)))
     a = np.ascontiguousarray(a); b = np.ascontiguousarray(b)
     assert load().qbo_elementwise_batched(C.byref(plan), _ptr(a), _ptr(b), _ptr(out), batch) == 0
+    return out
+
+
+def poly_batched(plan, x, batch=1):
+    """ANUS::Qpoly / Qapprox over a tensor; plan = a qb_poly_plan-shaped ctypes structure (include/qb200.h)."""
+    ot = plan.x if plan.approx else plan.seg[0].coef[0].type
+    out = np.zeros(batch * plan.len, dtype=np_dtype(_word_bytes(ot)))
+    x = np.ascontiguousarray(x)
+    assert load().qbo_poly_batched(C.byref(plan), _ptr(x), _ptr(out), batch) == 0
     return out

@@ -516,3 +516,37 @@ int qbo_elementwise_batched(const qb_ew_plan *p, const void *a, const void *b, v
     }
     return QB_OK;
 }
+
+/* ANUS::Qpoly (QuBLAS.h:4836-4853): Qpoly<a0>(x) = a0; Qpoly<a0, a1, ...>(x) = Qadd<A0>(a0, Qmul<A0>(x, Qpoly<a1, ...>(x))),
+ * A0 = decltype(a0).  Evaluated innermost first. */
+static qval poly_eval(const qb_poly_segment *s, qval x)
+{
+    qval acc = { s->coef[s->ncoef - 1].raw, s->coef[s->ncoef - 1].type };
+    for (int i = (int)s->ncoef - 2; i >= 0; i--) {
+        qval a = { s->coef[i].raw, s->coef[i].type };
+        acc = qbo_qadd(a, qbo_qmul(x, acc, a.t), a.t);
+    }
+    return acc;
+}
+
+/* ANUS::Qapprox (QuBLAS.h:4866-4888): the first Segment with x.toDouble() < breakpoint, the last one otherwise; the value is
+ * converted into decltype(x).  approx == 0: plain Qpoly of segment 0. */
+int qbo_poly_batched(const qb_poly_plan *p, const void *x, void *out, uint64_t batch)
+{
+    if (p->nseg < 1 || p->nseg > QB_POLY_MAX_SEG || (!p->approx && p->nseg != 1)) return QB_EINVAL;
+    qb_qdesc ot = p->approx ? p->x : p->seg[0].coef[0].type;
+    int wx = word_bytes_of(p->x), wo = word_bytes_of(ot);
+    size_t n = (size_t)(p->len * batch);
+    for (size_t i = 0; i < n; i++) {
+        qval xv = { load_word(x, i, wx), p->x };
+        uint32_t s = 0;
+        if (p->approx) {
+            double xd = ldexp((double)(int64_t)xv.raw, -p->x.frac_bits);                 /* toDouble, :2413-2416 */
+            while (s + 1 < p->nseg && !(xd < p->seg[s].breakpoint)) s++;
+        }
+        qval r = poly_eval(&p->seg[s], xv);
+        if (p->approx) r.raw = qbo_conv(r.raw, r.t.frac_bits, p->x);                     /* decltype(x){ ... }, converting ctor :2398-2411 */
+        store_word(out, i, wo, r.raw);
+    }
+    return QB_OK;
+}

@@ -73,6 +73,21 @@ class qb_convert_plan(C.Structure):
     _fields_ = [("from_", qb_qdesc), ("to", qb_qdesc), ("len", C.c_uint64)]
 
 
+QB_POLY_MAX_COEF, QB_POLY_MAX_SEG = 8, 8
+
+
+class qb_poly_coef(C.Structure):
+    _fields_ = [("type", qb_qdesc), ("raw", C.c_int64)]
+
+
+class qb_poly_segment(C.Structure):
+    _fields_ = [("breakpoint", C.c_double), ("ncoef", C.c_uint32), ("reserved", C.c_uint32), ("coef", qb_poly_coef * QB_POLY_MAX_COEF)]
+
+
+class qb_poly_plan(C.Structure):
+    _fields_ = [("x", qb_qdesc), ("nseg", C.c_uint32), ("approx", C.c_uint32), ("seg", qb_poly_segment * QB_POLY_MAX_SEG), ("len", C.c_uint64)]
+
+
 class qb_shard(C.Structure):
     _fields_ = [("device", C.c_int32), ("reserved", C.c_int32), ("A", C.c_void_p), ("B", C.c_void_p), ("C", C.c_void_p), ("batch", C.c_uint64)]
 
@@ -133,6 +148,7 @@ ABI_SYMBOLS = [
     "qb200_reduce_batched", "qb200_gemul_batched", "qb200_cgemul_batched", "qb200_tfcmul_batched",
     "qb200_convert_batched", "qb200_elementwise_batched", "qb200_synth_fill", "qb200_shard_range", "qb200_measure_int_peak", "qb200_jit_check_gemul", "qb200_jit_check", "qb200_quantize_f64", "qb200_dequantize_f64", "qb200_error_stats",
     "qb200_selftest_fp", "qb200_gemul_f64_batched", "qb200_host_alloc", "qb200_host_free", "qb200_device_alloc", "qb200_device_free", "qb200_memcpy", "qb200_gemul_sharded", "qb200_allgather",
+    "qb200_poly_plan_info", "qb200_poly_batched", "qb200_gemul_poly_batched", "qb200_table_batched",
 ]
 
 _LIB = None
@@ -183,6 +199,10 @@ def load() -> C.CDLL:
     L.qb200_memcpy.argtypes = [vp, vp, C.c_size_t, C.c_int]
     L.qb200_gemul_sharded.argtypes = [C.POINTER(qb_gemul_plan), C.POINTER(qb_shard), u32, C.POINTER(qb_exec)]
     L.qb200_allgather.argtypes = [C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int32), u32, u64, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_double)]
+    L.qb200_poly_plan_info.argtypes = [C.POINTER(qb_poly_plan), C.POINTER(qb_plan_info)]
+    L.qb200_poly_batched.argtypes = [C.POINTER(qb_poly_plan), vp, vp, u64, C.POINTER(qb_exec)]
+    L.qb200_gemul_poly_batched.argtypes = [C.POINTER(qb_gemul_plan), C.POINTER(qb_poly_plan), vp, vp, vp, u64, C.POINTER(qb_exec)]
+    L.qb200_table_batched.argtypes = [C.POINTER(qb_qdesc), C.POINTER(qb_qdesc), vp, vp, vp, u64, C.POINTER(qb_exec)]
     L.qb200_selftest_fp.argtypes = [C.c_int, C.c_void_p, C.POINTER(u64), C.POINTER(u64), C.POINTER(qb_exec)]
     for name in ABI_SYMBOLS:
         getattr(L, name)

@@ -168,6 +168,23 @@ QB_DEV void cprod_apply(int kind, I a, I b, I c, I d, const TfProg &tf, const Bc
     }
 }
 
+// ANUS::Qpoly / Qapprox on one element (QuBLAS.h:4846-4853, :4866-4888): segment selection on the raw value, Horner chain
+// with both quantizers of every step, optional conversion back into x's type.
+template <typename I, bool CT>
+QB_DEV I poly_apply(const PolyProg &P, I x)
+{
+    uint32_t s = 0;
+    while (s + 1 < P.nseg && !((int64_t)x < P.seg[s].below)) ++s;          // first segment whose breakpoint exceeds x, else the last
+    const PolySeg &S = P.seg[s];
+    I acc = (I)S.top;
+    for (int i = (int)S.ncoef - 2; i >= 0; --i) {
+        const I m = mul_apply<I, CT>(x, acc, S.step[i].mul);
+        acc = add_apply<I, CT>((I)S.step[i].a, m, S.step[i].add);
+    }
+    if (P.approx) acc = conv_apply<I, CT>(acc, S.back);
+    return acc;
+}
+
 // Qmul through the FP32 FMA pipe (see qb_codegen.cpp:fp_mul_ok): fma(a, b, 1.5 * 2^(23+S)) is the exact product
 // plus ONE IEEE rounding at ulp 2^S, i.e. the rounded right shift by S (round-to-nearest-even == RND::CONV,
 // round toward -inf == TRN::TCPL).  Returns the quantized product BIASED by the constant's bit pattern

@@ -265,6 +265,25 @@ __global__ void k_elementwise(const void *__restrict__ a, const void *__restrict
     }
 }
 
+// ANUS::Qpoly / Qapprox over a tensor; in place is fine (one element per thread and step)
+template <typename I>
+__global__ void __launch_bounds__(256) k_poly(const void *__restrict__ x, void *__restrict__ out, uint64_t n, int x_wb, int o_wb, const __grid_constant__ PolyProg P)
+{
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x)
+        store_word<I>(out, e, o_wb, poly_apply<I, false>(P, load_word<I>(x, e, x_wb)));
+}
+
+// ANUS::Qtable: out[e] = table[raw(x[e]) - raw_min]
+__global__ void __launch_bounds__(256) k_table(const void *__restrict__ x, void *__restrict__ out, const void *__restrict__ table, uint64_t n, int x_wb, int o_wb,
+                                               int64_t raw_min, uint64_t entries)
+{
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t idx = (uint64_t)(load_word<int64_t>(x, e, x_wb) - raw_min);
+        if (idx >= entries) idx = entries - 1;                 // words outside the type's range cannot occur in a well-formed buffer
+        store_word<int64_t>(out, e, o_wb, load_word<int64_t>(table, idx, o_wb));
+    }
+}
+
 __global__ void k_synth_fill(void *__restrict__ dst, uint64_t count, int wb, int64_t lo, uint64_t span, uint64_t key,
                              uint64_t first_index)
 {

@@ -1172,6 +1172,117 @@ extern "C" int qb200_elementwise_batched(const qb_ew_plan *plan, const void *a, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// ANUS::Qpoly / Qapprox over tensors, as an epilogue of Qgemul, and Qtable lookups
+// ---------------------------------------------------------------------------------------------
+static int poly_setup(const qb_poly_plan *plan, PolyProg *prog, qb_qdesc *out_t, Analysis &an)
+{
+    if (compile_poly(*plan, prog, out_t, an)) return fail(an.status, an.err);
+    return QB_OK;
+}
+
+extern "C" int qb200_poly_plan_info(const qb_poly_plan *plan, qb_plan_info *info)
+{
+    if (!plan || !info) return fail(QB_EINVAL, "null argument");
+    PolyProg prog; qb_qdesc ot; Analysis an;
+    int rc = poly_setup(plan, &prog, &ot, an); if (rc) return rc;
+    const int ow = word_bytes(ot);
+    ot.word_bytes = 0;
+    fill_info(info, an, ot, ow, "k_poly", 0, 0);
+    return QB_OK;
+}
+
+static int launch_poly(const PolyProg &prog_in, int bits, const void *dx, void *dout, uint64_t n, int xw, int ow, cudaStream_t st)
+{
+    if (n == 0) return QB_OK;
+    if (bits == 32) {
+        PolyProg prog = prog_in;
+        sanitize32(prog);
+        k_poly<int32_t><<<grid_for(n, 256), 256, 0, st>>>(dx, dout, n, xw, ow, prog);
+    } else {
+        k_poly<int64_t><<<grid_for(n, 256), 256, 0, st>>>(dx, dout, n, xw, ow, prog_in);
+    }
+    return post_launch("k_poly");
+}
+
+extern "C" int qb200_poly_batched(const qb_poly_plan *plan, const void *x, void *out, uint64_t batch, const qb_exec *exec)
+{
+    if (!plan || !x || !out) return fail(QB_EINVAL, "null argument");
+    PolyProg prog; qb_qdesc ot; Analysis an;
+    int rc = poly_setup(plan, &prog, &ot, an); if (rc) return rc;
+    const uint64_t n = plan->len * batch;
+    if (n == 0) return QB_OK;
+    Ctx cx; if ((rc = cx.init(exec))) return rc;
+    const int xw = word_bytes(plan->x), ow = word_bytes(ot);
+    const void *dx; void *dout;
+    if ((rc = cx.in(x, n * xw, &dx)) || (rc = cx.out(out, n * ow, &dout))) return rc;
+    if ((rc = launch_poly(prog, arith_bits(an), dx, dout, n, xw, ow, cx.stream))) return rc;
+    if ((rc = cx.out_done(out, n * ow, dout))) return rc;
+    return cx.finish();
+}
+
+// Qgemul followed by the polynomial on every output element, before the result leaves the GPU: the GEMM writes words of
+// poly->x (= gemul->c) into C's buffer and k_poly rewrites them in place as words of the polynomial's result type.
+extern "C" int qb200_gemul_poly_batched(const qb_gemul_plan *gemul, const qb_poly_plan *poly, const void *A, const void *B, void *C, uint64_t batch,
+                                        const qb_exec *exec)
+{
+    if (!gemul || !poly || !A || !B || !C) return fail(QB_EINVAL, "null argument");
+    if (memcmp(&gemul->c, &poly->x, sizeof(qb_qdesc)) != 0) return fail(QB_EINVAL, "the polynomial's x type must be the type Qgemul converts into (gemul->c)");
+    if (exec && exec->device == QB_DEVICE_ALL) return fail(QB_EINVAL, "QB_DEVICE_ALL is not supported by the fused call: shard the batch and pass one device per call");
+    PolyProg prog; qb_qdesc ot; Analysis an;
+    int rc = poly_setup(poly, &prog, &ot, an); if (rc) return rc;
+    const int xw = word_bytes(poly->x), ow = word_bytes(ot);
+    if (xw != ow) return fail(QB_EINVAL, "the polynomial's result words must be as wide as Qgemul's result words (in-place epilogue)");
+    if (gemul->stride_c < (int64_t)((uint64_t)gemul->M * gemul->N)) return fail(QB_EINVAL, "bad batch strides");
+    if (batch == 0) return QB_OK;
+    Ctx cx; if ((rc = cx.init(exec))) return rc;
+    const uint64_t ec = (uint64_t)gemul->M * gemul->N;
+    const size_t bytes_c = span_elems(batch, gemul->stride_c, ec) * xw;
+    void *dC;
+    if ((rc = cx.out(C, bytes_c, &dC))) return rc;
+    if (cx.host) {
+        // operands from host memory: the GEMM call stages them itself and leaves its result in the device buffer
+        const uint64_t ea = (uint64_t)gemul->M * gemul->K, eb = (uint64_t)gemul->K * gemul->N;
+        const int aw = word_bytes(gemul->a), bw = word_bytes(gemul->b);
+        const void *dA, *dB;
+        if ((rc = cx.in(A, span_elems(batch, gemul->stride_a, ea) * aw, &dA)) || (rc = cx.in(B, span_elems(batch, gemul->stride_b, eb) * bw, &dB))) return rc;
+        A = dA; B = dB;
+    }
+    int dev = 0; cudaGetDevice(&dev);
+    qb_exec ex = { QB_MEM_DEVICE, dev, (void *)cx.stream, cx.flags, 0 };
+    if ((rc = qb200_gemul_batched(gemul, A, B, dC, batch, &ex))) return rc;
+    // strided C: the words between instances are not results; run instance by instance only if there is padding
+    if (gemul->stride_c == (int64_t)ec) {
+        if ((rc = launch_poly(prog, arith_bits(an), dC, dC, batch * ec, xw, ow, cx.stream))) return rc;
+    } else {
+        for (uint64_t i = 0; i < batch; i++) {
+            char *ci = (char *)dC + i * (uint64_t)gemul->stride_c * xw;
+            if ((rc = launch_poly(prog, arith_bits(an), ci, ci, ec, xw, ow, cx.stream))) return rc;
+        }
+    }
+    if ((rc = cx.out_done(C, bytes_c, dC))) return rc;
+    return cx.finish();
+}
+
+extern "C" int qb200_table_batched(const qb_qdesc *x, const qb_qdesc *out_type, const void *table, const void *in, void *out, uint64_t n, const qb_exec *exec)
+{
+    if (!x || !out_type || !table || !in || !out) return fail(QB_EINVAL, "null argument");
+    Analysis an;
+    if (!check_type(*x, an, "x type") || !check_type(*out_type, an, "result type")) return fail(an.status, an.err);
+    if (width(*x) > 20) return fail(QB_EDOMAIN, "lookup tables are limited to inputs of at most 20 bits");
+    if (n == 0) return QB_OK;
+    const Ival r = type_range(*x);
+    const uint64_t entries = (uint64_t)(r.hi - r.lo + 1);
+    Ctx cx; int rc = cx.init(exec); if (rc) return rc;
+    const int xw = word_bytes(*x), ow = word_bytes(*out_type);
+    const void *din, *dtab; void *dout;
+    if ((rc = cx.in(in, n * xw, &din)) || (rc = cx.in(table, entries * ow, &dtab)) || (rc = cx.out(out, n * ow, &dout))) return rc;
+    k_table<<<grid_for(n, 256), 256, 0, cx.stream>>>(din, dout, dtab, n, xw, ow, (int64_t)r.lo, entries);
+    if ((rc = post_launch("k_table"))) return rc;
+    if ((rc = cx.out_done(out, n * ow, dout))) return rc;
+    return cx.finish();
+}
+
+// ---------------------------------------------------------------------------------------------
 // diagnostic / parity evidence: exhaustive sweep of the quantizers that run on the FP32 pipe
 // ---------------------------------------------------------------------------------------------
 // The specialised kernels replace some integer quantizers by floating-point instructions (qb_device.cuh:fp_mul_apply,

@@ -1,5 +1,6 @@
 // qb_plan.cpp — host plan compiler (no CUDA in this file).  See qb_plan.h.
 #include "qb_plan.h"
+#include <cmath>
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -442,6 +443,63 @@ int compile_tfcmul(const qb_tfcmul_plan &p, TfProg *out, BcmProg *bout, TVal *re
 // Lossless predicate for the tcgen05 kind::i8 path: operand raws fit int8,
 // every quantizer between the exact products and the tree result is an identity with shift 0,
 // so the tree result IS the exact integer dot product (order-independent) and fits int32.
+// ANUS::Qpoly<a0, a1, ...>(x) = Qadd<A0>(a0, Qmul<A0>(x, Qpoly<a1, ...>(x))) (QuBLAS.h:4846-4853), innermost first;
+// Qapprox picks the first Segment whose breakpoint exceeds x.toDouble() and converts the value into x's type (:4866-4888).
+int compile_poly(const qb_poly_plan &p, PolyProg *out, qb_qdesc *out_type, Analysis &an)
+{
+    memset(out, 0, sizeof(*out));
+    if (!check_type(p.x, an, "x type")) return an.status;
+    if (p.nseg < 1 || p.nseg > QB_POLY_MAX_SEG) { an.fail(QB_EINVAL, "1 .. 8 segments"); return an.status; }
+    if (!p.approx && p.nseg != 1) { an.fail(QB_EINVAL, "Qpoly takes one segment; several segments need approx = 1 (Qapprox)"); return an.status; }
+    if (p.approx && width(p.x) > 53) { an.fail(QB_EDOMAIN, "Qapprox compares x.toDouble(): x wider than 53 bits would round"); return an.status; }
+    out->nseg = p.nseg; out->approx = p.approx ? 1 : 0;
+    const TVal x = { p.x, type_range(p.x) };
+    an.max_reg_bits = std::max(an.max_reg_bits, width(p.x));
+    for (uint32_t s = 0; s < p.nseg; s++) {
+        const qb_poly_segment &sg = p.seg[s];
+        PolySeg &ps = out->seg[s];
+        if (sg.ncoef < 1 || sg.ncoef > QB_POLY_MAX_COEF) { an.fail(QB_EINVAL, "1 .. 8 coefficients per segment"); return an.status; }
+        ps.ncoef = sg.ncoef;
+        // x.toDouble() < breakpoint  <=>  raw < ceil(breakpoint * 2^fracBits)   (toDouble is exact up to 53 bits)
+        if (s + 1 < p.nseg) {
+            const long double t = ceill(ldexpl((long double)sg.breakpoint, p.x.frac_bits));
+            ps.below = sg.breakpoint != sg.breakpoint ? INT64_MIN : t >= 9.2e18L ? INT64_MAX : t <= -9.2e18L ? INT64_MIN : (int64_t)t;
+        } else {
+            ps.below = INT64_MAX;
+        }
+        for (uint32_t i = 0; i < sg.ncoef; i++) {
+            if (!check_type(sg.coef[i].type, an, "coefficient type")) return an.status;
+            const Ival r = type_range(sg.coef[i].type);
+            if ((i128)sg.coef[i].raw < r.lo || (i128)sg.coef[i].raw > r.hi) { an.fail(QB_EINVAL, "coefficient raw value outside its type"); return an.status; }
+        }
+        const qb_poly_coef &top = sg.coef[sg.ncoef - 1];
+        TVal acc = { top.type, { (i128)top.raw, (i128)top.raw } };
+        acc.t.word_bytes = 0;
+        ps.top = top.raw;
+        an.max_reg_bits = std::max(an.max_reg_bits, bits_for(acc.r));
+        for (int i = (int)sg.ncoef - 2; i >= 0; i--) {
+            const qb_poly_coef &c = sg.coef[i];
+            TVal prod, ai = { c.type, { (i128)c.raw, (i128)c.raw } };
+            ai.t.word_bytes = 0;
+            ps.step[i].mul = make_mul(x, acc, c.type, &prod, an);
+            ps.step[i].add = make_add(ai, prod, c.type, false, &acc, an);
+            ps.step[i].a = c.raw;
+        }
+        if (p.approx) {
+            TVal o;
+            ps.back = make_stage(acc.frac(), acc.r, width(acc.t), p.x, &o, an);       // decltype(x){ ... }: converting ctor :2398-2411
+        }
+        if (an.status) return an.status;
+    }
+    if (out_type) { *out_type = p.approx ? p.x : p.seg[0].coef[0].type; out_type->word_bytes = p.approx ? p.x.word_bytes : p.seg[0].coef[0].type.word_bytes; }
+    finish(an);
+    return an.status;
+}
+void sanitize32(PolyProg &t)
+{
+    for (auto &sg : t.seg) { for (auto &st : sg.step) { sanitize32(st.mul); sanitize32(st.add.q); } sanitize32(sg.back); }
+}
+
 bool gemul_tensor_core_ok(const qb_gemul_plan &p, const GemulProg &g, const Analysis &an)
 {
     if (an.status) return false;

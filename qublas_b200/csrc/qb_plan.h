@@ -71,6 +71,9 @@ int compile_reduce(const qb_reduce_plan &p, ReduceProg *out, Analysis &an);
 int compile_gemul(const qb_gemul_plan &p, GemulProg *out, Analysis &an);
 int compile_cgemul(const qb_cgemul_plan &p, CGemulProg *out, Analysis &an);
 int compile_tfcmul(const qb_tfcmul_plan &p, TfProg *out, BcmProg *bout, TVal *re, TVal *im, Analysis &an);
+// ANUS::Qpoly / Qapprox over a tensor (QuBLAS.h:4829-4897); *out_type = type of the result
+int compile_poly(const qb_poly_plan &p, PolyProg *out, qb_qdesc *out_type, Analysis &an);
+void sanitize32(PolyProg &t);
 
 // Register class of a compiled plan: 32 iff every leaf and every stage output fits int32; else 64.
 // Stages whose exact input is wider than 32 bits (e.g. a 17x16-bit product) are marked `wide` and

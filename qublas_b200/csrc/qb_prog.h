@@ -75,4 +75,25 @@ struct BcmProg {
     AddStage re, im;
 };
 
+// ANUS::Qpoly / Qapprox (QuBLAS.h:4829-4897): per segment a Horner chain acc = add(a_i, mul(x, acc)), i = n-2 .. 0,
+// starting from acc = a_(n-1); Qapprox converts the value back into x's type.
+#define QBP_POLY_MAX_COEF 8
+#define QBP_POLY_MAX_SEG  8
+struct PolyStep {
+    QStage   mul;        // Qmul<A_i>(x, acc)
+    AddStage add;        // Qadd<A_i>(a_i, product)
+    int64_t  a;          // raw a_i
+};
+struct PolySeg {
+    int64_t  below;      // the segment applies when raw(x) < below  (= ceil(breakpoint * 2^fracBits(x)))
+    uint32_t ncoef, pad;
+    int64_t  top;        // raw a_(n-1)
+    PolyStep step[QBP_POLY_MAX_COEF - 1];
+    QStage   back;       // Qapprox: converting ctor into x's type
+};
+struct PolyProg {
+    uint32_t nseg, approx;
+    PolySeg  seg[QBP_POLY_MAX_SEG];
+};
+
 }  // namespace qb

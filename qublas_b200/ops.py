@@ -283,6 +283,68 @@ def convert(x, src: QType, dst: QType, flags: int = 0):
     return out
 
 
+def make_poly_plan(x_t: QType, segments, n: int = 0, approx: Optional[bool] = None) -> abi.qb_poly_plan:
+    """ANUS::Qpoly / Qapprox (reference QuBLAS.h:4829-4897).  segments = [(breakpoint, [(QType, raw), ...]), ...] with the
+    coefficients in the reference's order a0, a1, ...; one segment with approx=False is Qpoly<a0, a1, ...>(x)."""
+    p = abi.qb_poly_plan()
+    p.x, p.len, p.nseg = abi.desc(x_t), n, len(segments)
+    p.approx = int(len(segments) > 1 if approx is None else approx)
+    if not 1 <= len(segments) <= abi.QB_POLY_MAX_SEG:
+        raise ValueError("1 .. %d segments" % abi.QB_POLY_MAX_SEG)
+    for k, (bp, coefs) in enumerate(segments):
+        if not 1 <= len(coefs) <= abi.QB_POLY_MAX_COEF:
+            raise ValueError("1 .. %d coefficients per segment" % abi.QB_POLY_MAX_COEF)
+        p.seg[k].breakpoint, p.seg[k].ncoef = float(bp), len(coefs)
+        for i, (t, raw) in enumerate(coefs):
+            p.seg[k].coef[i].type, p.seg[k].coef[i].raw = abi.desc(t), int(raw)
+    return p
+
+
+def plan_info_poly(plan):
+    info = abi.qb_plan_info()
+    abi.check(abi.load().qb200_poly_plan_info(C.byref(plan), C.byref(info)))
+    return info
+
+
+def Qpoly(x, x_t: QType, segments, approx: Optional[bool] = None):
+    """Polynomial / piecewise polynomial of every element of x on the GPU; returns (out, result type)."""
+    n = x.numel() if _is_torch(x) else x.size
+    p = make_poly_plan(x_t, segments, n, approx)
+    rt = abi.qtype_of(plan_info_poly(p).out_type)
+    _check_words(x, x_t.word_bytes, "x")
+    out = _new_like(x, n, rt.word_bytes)
+    ex = _exec_for(x)
+    abi.check(abi.load().qb200_poly_batched(C.byref(p), _ptr(x), _ptr(out), 1, C.byref(ex)))
+    return out, rt
+
+
+def Qgemul_poly(Cbuf, A, B, plan: abi.qb_gemul_plan, poly: abi.qb_poly_plan, batch: int = 1, flags: int = 0):
+    """Qgemul with the polynomial applied to every result element before it is stored (plan.c must be poly.x)."""
+    ex = _exec_for(A, B, Cbuf, flags=flags)
+    abi.check(abi.load().qb200_gemul_poly_batched(C.byref(plan), C.byref(poly), _ptr(A), _ptr(B), _ptr(Cbuf), batch, C.byref(ex)))
+    return Cbuf
+
+
+def Qtable(x, x_t: QType, out_t: QType, func):
+    """ANUS::Qtable<func>(x) (reference readme.md:66-78; not in the header): out = out_t(func(x.toDouble())), through a
+    table over every raw value of x_t built here with the library's own double -> Qu quantizer."""
+    lo, hi = x_t.raw_min, x_t.raw_max
+    raws = np.arange(lo, hi + 1, dtype=np.float64)
+    with np.errstate(all="ignore"):
+        vals = np.asarray(func(raws * 2.0 ** (-x_t.f)), dtype=np.float64)
+    vals = np.where(np.isfinite(vals), vals, 0.0)
+    if _is_torch(x):
+        table = quantize(torch.from_numpy(vals).to(x.device), out_t)
+    else:
+        table = quantize(vals, out_t)
+    n = x.numel() if _is_torch(x) else x.size
+    out = _new_like(x, n, out_t.word_bytes)
+    dx, do = abi.desc(x_t), abi.desc(out_t)
+    ex = _exec_for(x)
+    abi.check(abi.load().qb200_table_batched(C.byref(dx), C.byref(do), _ptr(table), _ptr(x), _ptr(out), n, C.byref(ex)))
+    return out
+
+
 def quantize(x, t: QType):
     """double -> Qu<t> raw words on the GPU: exact value, t's QuMode, t's OfMode (Qu_s(double), QuBLAS.h:2387-2393)."""
     n = x.numel() if _is_torch(x) else x.size

@@ -91,3 +91,31 @@ def fd64_defect_band(v, t: QType):
         return False
     raw = abs(v) * 2.0 ** t.f
     return 2.0 ** 63 * (1 - 2.0 ** -40) <= raw <= 2.0 ** 64 * (1 + 2.0 ** -40)
+
+
+def anus_golden():
+    """tests/golden/ref_anus.txt = stdout of tests/cpp/anus_example.cpp compiled against the REFERENCE header: per x raw value
+    the raws of six ANUS::Qpoly / Qapprox expressions.  Returns (x type, {name: segments}, x raws, {name: expected raws})."""
+    from oracle import oracle
+    from qublas_b200.qtypes import RND_POS_INF, SAT_ZERO, TRN_SMGN
+    x_t = QType(4, 8)
+    c_t = QType(3, 6, True, RND_POS_INF)
+    w_t = QType(2, 10, True, TRN_SMGN, SAT_ZERO)
+    a = [(c_t, oracle.from_double(v, c_t)) for v in (0.5, -1.25, 0.375, 2.0)]
+    b = [(w_t, oracle.from_double(v, w_t)) for v in (-0.3333, 0.75, -0.0625)]
+    exprs = {
+        "p1": [(0.0, [a[0]])],
+        "p2": [(0.0, [a[0], a[1]])],
+        "p3": [(0.0, [a[0], a[1], a[2]])],
+        "p4": [(0.0, [b[0], b[1], b[2], a[3]])],
+        "q": [(-2.0, [a[0], a[1]]), (0.5, [b[0], b[1], b[2]]), (3.0, [a[3], a[2]])],
+        "r": [(1.0, [b[1]]), (100.0, [a[1], b[2]])],
+    }
+    xs, want = [], {k: [] for k in exprs}
+    with open(os.path.join(GOLD, "ref_anus.txt")) as f:
+        for line in f:
+            t = line.split()
+            xs.append(int(t[0]))
+            for k, v in zip(("p1", "p2", "p3", "p4", "q", "r"), t[1:]):
+                want[k].append(int(v.split(":")[0]))
+    return x_t, exprs, np.array(xs, dtype=np.int32), {k: np.array(v, dtype=np.int64) for k, v in want.items()}

@@ -242,3 +242,18 @@ def test_python_wrappers_validate_buffers():
         ops.Qcgemul(np.zeros(8, dtype=np.int32), np.zeros(16, dtype=np.int32), np.zeros(8, dtype=np.int32), cplan)   # A needs 32 words
     with pytest.raises(ValueError):
         ops.Qcgemul(np.zeros(8, dtype=np.int64), np.zeros(32, dtype=np.int32), np.zeros(8, dtype=np.int32), cplan)
+
+
+def test_poly_plans_are_validated_without_a_gpu():
+    """ANUS plans: type rules and the parity fence are host code (no device needed)."""
+    from qublas_b200 import ops
+    from qublas_b200.qtypes import QType
+    x = QType(4, 8); k = QType(3, 6)
+    info = ops.plan_info_poly(ops.make_poly_plan(x, [(0.0, [(k, 5), (k, -7)])], 16))
+    assert abi.qtype_of(info.out_type) == k and info.arith_bits == 32
+    info = ops.plan_info_poly(ops.make_poly_plan(x, [(0.0, [(k, 5)]), (1.0, [(k, 1), (k, 2)])], 16))
+    assert abi.qtype_of(info.out_type) == x                                          # Qapprox converts back into x's type
+    with pytest.raises(abi.QbError):
+        ops.plan_info_poly(ops.make_poly_plan(x, [(0.0, [(k, 5)]), (1.0, [(k, 1)])], 16, approx=False))     # Qpoly takes one segment
+    with pytest.raises(abi.QbError):
+        ops.plan_info_poly(ops.make_poly_plan(x, [(0.0, [(k, 1 << 20)])], 16))        # coefficient outside its type

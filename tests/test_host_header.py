@@ -149,3 +149,19 @@ def test_batched_and_complex_example_on_gpu(tmp_path):
     assert "batched Qgemul: OK" in p.stdout and "complex Qgemul TFComplexMul: OK" in p.stdout
     assert "complex Qgemul BasicComplexMul: OK" in p.stdout and "Qreduce 4096: raw" in p.stdout
     assert "element-wise Qadd/Qsub/Qmul: OK" in p.stdout and "device-resident sweep: OK" in p.stdout
+
+
+def test_anus_tensor_example_compiles(tmp_path):
+    """ANUS::Qpoly / Qapprox / Qtable on tensors compile as user code; without a GPU the first tensor call throws."""
+    exe = _build_cpp(tmp_path, "anus_tensor_example")
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode in (0, 3), p.stdout + p.stderr
+
+
+@pytest.mark.gpu
+def test_anus_tensor_example_on_gpu(tmp_path):
+    """The tensor forms (GPU) give the same raw words as the scalar forms, which ref_anus.txt pins to the reference."""
+    exe = _build_cpp(tmp_path, "anus_tensor_example")
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "tensor ANUS: OK" in p.stdout and "rsqrt(4.0) raw 128 sqrt(4.0) raw 512" in p.stdout

@@ -257,3 +257,15 @@ def test_from_double_matches_reference():
                 assert oracle.from_double(v, t) == o[0], (c["to"], v)
                 n += 1
     assert n >= 4500 and skipped < 1300
+
+
+def test_anus_poly_and_approx_match_reference():
+    """ANUS::Qpoly / Qapprox (reference QuBLAS.h:4829-4897): the oracle's restatement against the reference's own outputs
+    (tests/golden/ref_anus.txt, generated by oracle/ref_harness_gen.py --text from the unmodified header)."""
+    from qublas_b200 import ops
+    from tests.helpers import anus_golden
+    x_t, exprs, xs, want = anus_golden()
+    for name, segs in exprs.items():
+        plan = ops.make_poly_plan(x_t, segs, len(xs), approx=name in ("q", "r"))
+        got = oracle.poly_batched(plan, xs)
+        assert np.array_equal(got.astype(np.int64), want[name]), name
