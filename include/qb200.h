@@ -311,7 +311,8 @@ int qb200_measure_int_peak(double fma_share, double *tera_ops_per_s, const qb_ex
  * -1 if NVRTC is unavailable or compilation failed (message in `log`). */
 int qb200_jit_check_gemul(const qb_gemul_plan *plan, char *log, uint64_t log_cap);
 /* The same check for the other run-time specialised kernel templates (no device needed).
- * what: 1 = qb_cgemul_plan, 2 = qb_reduce_plan, 3 = qb_tfcmul_plan, 4 = qb_ew_plan, 5 = qb_convert_plan.
+ * what: 1 = qb_cgemul_plan, 2 = qb_reduce_plan, 3 = qb_tfcmul_plan, 4 = qb_ew_plan, 5 = qb_convert_plan, 6 = qb_poly_plan,
+ * 7 = struct { qb_gemul_plan; qb_poly_plan; } (Qgemul with the polynomial fused into its store).
  * Returns 0 = cubin produced, 1 = no template applies to this plan, -1 = NVRTC failed (log filled), < -1 = plan error. */
 int qb200_jit_check(int what, const void *plan, char *log, uint64_t log_cap);
 

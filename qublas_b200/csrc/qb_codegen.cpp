@@ -34,6 +34,32 @@ static std::string emit_levels(const char *fn, const TreeProg &t, unsigned n)
 }
 
 static std::string emit_flush(const char *fn, const TreeProg &t);
+
+// ANUS polynomial program as a constexpr initialiser; only the segments and steps in use are spelled out (the rest is
+// value-initialised), so the text stays short
+std::string emit_polyprog(const PolyProg &P)
+{
+    std::ostringstream o;
+    o << "qb::PolyProg{" << P.nseg << "u," << P.approx << "u,{\n";
+    for (uint32_t s = 0; s < P.nseg; s++) {
+        const PolySeg &g = P.seg[s];
+        auto lit = [](int64_t v) { return v == INT64_MIN ? std::string("(-9223372036854775807LL-1)") : std::to_string((long long)v) + "LL"; };
+        o << "      qb::PolySeg{" << lit(g.below) << "," << g.ncoef << "u,0u," << lit(g.top) << ",{";
+        for (uint32_t i = 0; i + 1 < g.ncoef; i++)
+            o << "\n        qb::PolyStep{" << emit_qstage(g.step[i].mul) << "," << emit_addstage(g.step[i].add) << "," << lit(g.step[i].a) << "},";
+        o << "}," << emit_qstage(g.back) << "},\n";
+    }
+    o << "    }}";
+    return o.str();
+}
+static std::string emit_epilogue(const PolyProg *epi)
+{
+    PolyProg z; memset(&z, 0, sizeof(z));
+    std::ostringstream o;
+    o << "  static constexpr bool EPI = " << (epi ? "true" : "false") << ";\n";
+    o << "  static constexpr __host__ __device__ qb::PolyProg poly() { return " << emit_polyprog(epi ? *epi : z) << "; }\n";
+    return o.str();
+}
 // batch strides of the plan (in elements), baked into the tag: a kernel is specialised per plan anyway
 static std::string emit_strides(int64_t sa, int64_t sb, int64_t sc)
 {
@@ -90,7 +116,7 @@ uint64_t gemul_tile_smem(const qb_gemul_plan &p, const GemulProg &g, int group, 
     return total <= limit ? total : 0;
 }
 
-std::string emit_gemul_cfg(const std::string &name, const qb_gemul_plan &p, const GemulProg &g, int group)
+std::string emit_gemul_cfg(const std::string &name, const qb_gemul_plan &p, const GemulProg &g, int group, const PolyProg *epi)
 {
     std::ostringstream o;
     o << "struct " << name << " {\n";
@@ -125,12 +151,13 @@ std::string emit_gemul_cfg(const std::string &name, const qb_gemul_plan &p, cons
         const Ival ra = type_range(p.a), rb = type_range(p.b);           // operand types' own bounds (32-bit register class: they fit)
         o << "  static constexpr long long A_LO = " << (long long)ra.lo << "LL, A_HI = " << (long long)ra.hi << "LL, B_LO = " << (long long)rb.lo << "LL, B_HI = " << (long long)rb.hi << "LL;\n";
     }
+    o << emit_epilogue(epi);
     o << "};\n";
     return o.str();
 }
 
 // Tag struct for the thread-per-output template (qb_fast_gemul_thread.cuh): any shape, both forms, transposes.
-std::string emit_gemul_thread_cfg(const std::string &name, const qb_gemul_plan &p, const GemulProg &g, int bits)
+std::string emit_gemul_thread_cfg(const std::string &name, const qb_gemul_plan &p, const GemulProg &g, int bits, const PolyProg *epi)
 {
     std::ostringstream o;
     unsigned nlev = 0;
@@ -151,6 +178,7 @@ std::string emit_gemul_thread_cfg(const std::string &name, const qb_gemul_plan &
         o << "      qb::FlushStep{" << (unsigned)f.kind << "," << (unsigned)f.slot << ",{0,0,0,0,0,0}," << emit_addstage(f.a) << "},\n";
     }
     o << "    };\n    return t[i];\n  }\n";
+    o << emit_epilogue(epi);
     o << "};\n";
     return o.str();
 }
@@ -309,6 +337,18 @@ std::string emit_ew_cfg(const std::string &name, int kind, const TfProg *tf, con
     o << "  static constexpr __host__ __device__ qb::TfProg tf() { return " << emit_tfprog(tf ? *tf : ztf) << "; }\n";
     o << "  static constexpr __host__ __device__ qb::BcmProg bcm() { return " << emit_bcmprog(bcm ? *bcm : zb) << "; }\n";
     o << "  static constexpr __host__ __device__ qb::AddStage stage() { return " << emit_addstage(stage ? *stage : zs) << "; }\n";
+    o << "};\n";
+    return o.str();
+}
+
+// Tag struct of the specialised ANUS kernel (qb_fast_ew.cuh:poly_body)
+std::string emit_poly_cfg(const std::string &name, const PolyProg &prog, int xw, int ow, int bits)
+{
+    std::ostringstream o;
+    o << "struct " << name << " {\n";
+    o << "  typedef " << (bits == 32 ? "int32_t" : "int64_t") << " I;\n";
+    o << "  typedef " << word_t(xw) << " WX; typedef " << word_t(xw) << " WY; typedef " << word_t(ow) << " WO;\n";
+    o << emit_epilogue(&prog);
     o << "};\n";
     return o.str();
 }

@@ -185,6 +185,28 @@ QB_DEV I poly_apply(const PolyProg &P, I x)
     return acc;
 }
 
+// The same with the program as a compile-time constant (Cfg::poly()): segments are tested one after the other, every
+// Horner step is unrolled, all quantizers are immediates.
+template <class Cfg, typename I, int S>
+QB_DEV I poly_seg_ct(I x)
+{
+    constexpr PolySeg sg = Cfg::poly().seg[S];
+    I acc = (I)sg.top;
+#pragma unroll
+    for (int i = (int)sg.ncoef - 2; i >= 0; --i) {
+        const I m = mul_apply<I, true>(x, acc, sg.step[i].mul);
+        acc = add_apply<I, true>((I)sg.step[i].a, m, sg.step[i].add);
+    }
+    if constexpr (Cfg::poly().approx != 0) acc = conv_apply<I, true>(acc, sg.back);
+    return acc;
+}
+template <class Cfg, typename I, int S = 0>
+QB_DEV I poly_ct(I x)
+{
+    if constexpr (S + 1 >= (int)Cfg::poly().nseg) return poly_seg_ct<Cfg, I, S>(x);
+    else return (int64_t)x < Cfg::poly().seg[S].below ? poly_seg_ct<Cfg, I, S>(x) : poly_ct<Cfg, I, S + 1>(x);
+}
+
 // Qmul through the FP32 FMA pipe (see qb_codegen.cpp:fp_mul_ok): fma(a, b, 1.5 * 2^(23+S)) is the exact product
 // plus ONE IEEE rounding at ulp 2^S, i.e. the rounded right shift by S (round-to-nearest-even == RND::CONV,
 // round toward -inf == TRN::TCPL).  Returns the quantized product BIASED by the constant's bit pattern

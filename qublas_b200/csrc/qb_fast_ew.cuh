@@ -102,4 +102,23 @@ QB_DEV void conv_body(const typename Cfg::WX *__restrict__ x, const typename Cfg
     }
 }
 
+// out[i] = ANUS::Qpoly / Qapprox (in[i]) (QuBLAS.h:4829-4897); `y` is unused
+template <class Cfg>
+QB_DEV void poly_body(const typename Cfg::WX *__restrict__ x, const typename Cfg::WY *__restrict__, typename Cfg::WO *__restrict__ out, uint64_t n)
+{
+    typedef typename Cfg::I I;
+    constexpr int U = QB_EW_U;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e0 < n; e0 += U * stride) {
+        typename Cfg::WX a[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) { const uint64_t e = e0 + u * stride; a[u] = e < n ? __ldcs(x + e) : (typename Cfg::WX)0; }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint64_t e = e0 + u * stride;
+            if (e < n) __stcs(out + e, (typename Cfg::WO)poly_ct<Cfg, I>((I)a[u]));
+        }
+    }
+}
+
 }  // namespace qb

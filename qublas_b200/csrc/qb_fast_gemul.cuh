@@ -563,6 +563,10 @@ QB_DEV void gemul_tile_body(const typename Cfg::WA *__restrict__ A, const typena
                 o.y = (int32_t)conv_apply<I, true>(r1, outq);
                 o.z = (int32_t)conv_apply<I, true>(r2, outq);
                 o.w = (int32_t)conv_apply<I, true>(r3, outq);
+                if constexpr (Cfg::EPI) {                         // fused ANUS epilogue (qb200_gemul_poly_batched)
+                    o.x = (int32_t)poly_ct<Cfg, I>((I)o.x); o.y = (int32_t)poly_ct<Cfg, I>((I)o.y);
+                    o.z = (int32_t)poly_ct<Cfg, I>((I)o.z); o.w = (int32_t)poly_ct<Cfg, I>((I)o.w);
+                }
                 *(int4 *)(Ci + (j0 + jj) * M + i0) = o;
             };
             if constexpr (s_form_ok<Cfg>()) {

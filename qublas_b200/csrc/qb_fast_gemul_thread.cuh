@@ -79,7 +79,9 @@ QB_DEV void gemul_thread_body(const typename Cfg::WA *__restrict__ A, const type
     I r;
     if constexpr (Cfg::NFLUSH == 0) r = st[Cfg::TOP_SLOT];
     else r = tstack_flush<Cfg, 0>(st, (I)0);
-    C[inst * (uint64_t)Cfg::SC + ij] = (typename Cfg::WC)conv_apply<I, true>(r, outq);
+    I cv = conv_apply<I, true>(r, outq);
+    if constexpr (Cfg::EPI) cv = poly_ct<Cfg, I>(cv);          // fused ANUS epilogue (qb200_gemul_poly_batched)
+    C[inst * (uint64_t)Cfg::SC + ij] = (typename Cfg::WC)cv;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

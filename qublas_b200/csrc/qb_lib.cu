@@ -950,6 +950,26 @@ extern "C" int qb200_jit_check(int what, const void *plan, char *log, uint64_t l
         const int bits = arith_bits(an);
         if (bits == 32) sanitize32_stage(st.q);
         run([&] { jit_ew(-1, nullptr, nullptr, 3, &st, word_bytes(p.from), word_bytes(p.from), word_bytes(p.to), bits); });
+    } else if (what == 6) {
+        const qb_poly_plan &p = *(const qb_poly_plan *)plan;
+        PolyProg prog; qb_qdesc ot; Analysis an;
+        if (compile_poly(p, &prog, &ot, an)) return fail(an.status, an.err);
+        const int bits = arith_bits(an);
+        if (bits == 32) sanitize32(prog);
+        run([&] { jit_poly(prog, word_bytes(p.x), word_bytes(ot), bits); });
+    } else if (what == 7) {
+        // Qgemul with a fused polynomial epilogue: plan = { qb_gemul_plan, qb_poly_plan } back to back
+        struct Pair { qb_gemul_plan g; qb_poly_plan p; };
+        const Pair &pr = *(const Pair *)plan;
+        PolyProg prog; qb_qdesc ot; Analysis an;
+        if (compile_poly(pr.p, &prog, &ot, an)) return fail(an.status, an.err);
+        auto ce = get_gemul(pr.g);
+        if (ce->an.status) return fail(ce->an.status, ce->an.err);
+        if (arith_bits(an) > ce->bits) { rc = 1; }
+        else {
+            if (ce->bits == 32) sanitize32(prog);
+            run([&] { jit_gemul(pr.g, ce->prog, ce->bits, &prog); });
+        }
     } else {
         return fail(QB_EINVAL, "unknown plan kind");
     }
@@ -1204,6 +1224,23 @@ static int launch_poly(const PolyProg &prog_in, int bits, const void *dx, void *
     return post_launch("k_poly");
 }
 
+// specialised kernel (NVRTC, cached per plan and device) when the buffers allow vector accesses, else the runtime-descriptor one
+static int run_poly(const qb_poly_plan &plan, const PolyProg &prog, int bits, const Ctx &cx, const void *dx, void *dout, uint64_t n, int xw, int ow)
+{
+    JitKernel *jk = nullptr;
+    if (ew_jit_usable(cx, { dx, dout })) {
+        PolyProg p32 = prog;
+        if (bits == 32) sanitize32(p32);
+        jk = ew_cache(plan)->jit.get([&] { return jit_poly(p32, xw, ow, bits); });
+    }
+    if (jk) {
+        int e = jit_launch_ew(*jk, dx, dx, dout, n, cx.stream);
+        if (e) return fail(QB_ECUDA, jk->name + " launch failed (CUresult " + std::to_string(e) + ")");
+        return QB_OK;
+    }
+    return launch_poly(prog, bits, dx, dout, n, xw, ow, cx.stream);
+}
+
 extern "C" int qb200_poly_batched(const qb_poly_plan *plan, const void *x, void *out, uint64_t batch, const qb_exec *exec)
 {
     if (!plan || !x || !out) return fail(QB_EINVAL, "null argument");
@@ -1215,7 +1252,7 @@ extern "C" int qb200_poly_batched(const qb_poly_plan *plan, const void *x, void 
     const int xw = word_bytes(plan->x), ow = word_bytes(ot);
     const void *dx; void *dout;
     if ((rc = cx.in(x, n * xw, &dx)) || (rc = cx.out(out, n * ow, &dout))) return rc;
-    if ((rc = launch_poly(prog, arith_bits(an), dx, dout, n, xw, ow, cx.stream))) return rc;
+    if ((rc = run_poly(*plan, prog, arith_bits(an), cx, dx, dout, n, xw, ow))) return rc;
     if ((rc = cx.out_done(out, n * ow, dout))) return rc;
     return cx.finish();
 }
@@ -1246,6 +1283,28 @@ extern "C" int qb200_gemul_poly_batched(const qb_gemul_plan *gemul, const qb_pol
         const void *dA, *dB;
         if ((rc = cx.in(A, span_elems(batch, gemul->stride_a, ea) * aw, &dA)) || (rc = cx.in(B, span_elems(batch, gemul->stride_b, eb) * bw, &dB))) return rc;
         A = dA; B = dB;
+    }
+    // Fused: the run-time specialised Qgemul kernels apply the polynomial in registers, right after the converting assignment
+    // (qb_fast_gemul.cuh / qb_fast_gemul_thread.cuh: Cfg::EPI).  Needs a plan without the tensor-core path, the polynomial in
+    // the kernel's register class and 16-byte aligned buffers; everything else runs the two kernels back to back.
+    {
+        auto ce = get_gemul(*gemul);
+        if (ce->an.status) return fail(ce->an.status, ce->an.err);
+        const bool tc = !(cx.flags & QB_F_NO_TENSOR_CORE) && ce->tc;
+        const bool aligned16 = !(((uintptr_t)A | (uintptr_t)B | (uintptr_t)dC) & 15);
+        if (!tc && !(cx.flags & QB_F_NO_SPECIALIZE) && aligned16 && arith_bits(an) <= ce->bits) {
+            struct Key { qb_gemul_plan g; qb_poly_plan p; } key;
+            memset(&key, 0, sizeof(key)); key.g = *gemul; key.p = *poly; key.p.len = 0;
+            PolyProg pe = prog;
+            if (ce->bits == 32) sanitize32(pe);
+            JitKernel *jk = cached<Key, EwC>(key, [](EwC &) {})->jit.get([&] { return jit_gemul(*gemul, ce->prog, ce->bits, &pe); });
+            if (jk) {
+                int e = jit_launch_gemul(*jk, A, B, dC, batch, cx.stream);
+                if (e) return fail(QB_ECUDA, jk->name + " launch failed (CUresult " + std::to_string(e) + ")");
+                if ((rc = cx.out_done(C, bytes_c, dC))) return rc;
+                return cx.finish();
+            }
+        }
     }
     int dev = 0; cudaGetDevice(&dev);
     qb_exec ex = { QB_MEM_DEVICE, dev, (void *)cx.stream, cx.flags, 0 };

@@ -257,3 +257,28 @@ def test_poly_plans_are_validated_without_a_gpu():
         ops.plan_info_poly(ops.make_poly_plan(x, [(0.0, [(k, 5)]), (1.0, [(k, 1)])], 16, approx=False))     # Qpoly takes one segment
     with pytest.raises(abi.QbError):
         ops.plan_info_poly(ops.make_poly_plan(x, [(0.0, [(k, 1 << 20)])], 16))        # coefficient outside its type
+
+
+def test_poly_kernels_specialise_with_nvrtc_without_a_gpu():
+    """The specialised ANUS kernel and the Qgemul kernels with the polynomial fused into their store (register-tile and
+    thread-per-output templates) compile for sm_100a (NVRTC needs no device)."""
+    import ctypes
+    from qublas_b200.qtypes import RND_CONV, RND_POS_INF, SAT_TCPL
+    lib = abi.load()
+    log = ctypes.create_string_buffer(16384)
+    c = QType(17, 4, True, RND_POS_INF, SAT_TCPL)
+    k_t = QType(1, 14, True, RND_POS_INF, SAT_TCPL)
+    segs = [(-100.0, [(k_t, 0)]), (0.0, [(k_t, 0), (k_t, 1 << 11)]), (1e9, [(k_t, 0), (k_t, 1 << 14), (k_t, -3)])]
+    poly = ops.make_poly_plan(c, segs, 64, True)
+    rc = lib.qb200_jit_check(6, ctypes.cast(ctypes.byref(poly), ctypes.c_void_p), log, 16384)
+    assert rc == 0, log.value.decode()
+    a = QType(7, 8); mul = QType(14, 8, True, RND_CONV, SAT_TCPL)
+
+    class Pair(ctypes.Structure):
+        _fields_ = [("g", abi.qb_gemul_plan), ("p", abi.qb_poly_plan)]
+    for M, N, K in ((64, 64, 64), (10, 6, 12)):
+        nlev = max(1, (K - 1).bit_length())
+        lv = [QType(15 + l, 8 - min(l, 8), True, RND_POS_INF, SAT_TCPL) for l in range(nlev)]
+        pair = Pair(ops.make_gemul_plan(a, a, c, M, N, K, mul=mul, add=lv), poly)
+        rc = lib.qb200_jit_check(7, ctypes.cast(ctypes.byref(pair), ctypes.c_void_p), log, 16384)
+        assert rc == 0, log.value.decode()

@@ -57,8 +57,14 @@ def test_random_polynomials_vs_oracle(seed):
         assert e.code == abi.QB_EDOMAIN                      # outside the parity domain: refused, not computed
         return
     want = oracle.poly_batched(plan, xs)
-    got, _ = ops.Qpoly(torch.from_numpy(xs).cuda(), x_t, segs, approx)
+    xd = torch.from_numpy(xs).cuda()
+    got, rt = ops.Qpoly(xd, x_t, segs, approx)                                       # specialised kernel (NVRTC)
     assert np.array_equal(got.cpu().numpy(), want), (seed, info.arith_bits)
+    out2 = torch.empty_like(got)                                                      # runtime-descriptor kernel
+    ex = abi.qb_exec(abi.QB_MEM_DEVICE, -1, None, abi.QB_F_NO_SPECIALIZE, 0)
+    import ctypes as C
+    abi.check(abi.load().qb200_poly_batched(C.byref(plan), xd.data_ptr(), out2.data_ptr(), 1, C.byref(ex)))
+    assert torch.equal(got, out2)
 
 
 def test_gemul_with_polynomial_epilogue_vs_oracle():
@@ -84,6 +90,27 @@ def test_gemul_with_polynomial_epilogue_vs_oracle():
         Ch = np.empty(batch * M * N, dtype=np.int32)
         ops.Qgemul_poly(Ch, A.cpu().numpy(), B.cpu().numpy(), plan, poly, batch=batch)
         assert np.array_equal(Ch, want)
+        C2 = torch.empty_like(Cd)                                                     # the unfused pair of runtime-descriptor kernels
+        ops.Qgemul_poly(C2, A, B, plan, poly, batch=batch, flags=abi.QB_F_NO_SPECIALIZE)
+        assert torch.equal(Cd, C2)
+
+
+def test_fused_epilogue_is_one_launch():
+    """The polynomial rides in the store of the specialised Qgemul kernel: one launch per call, not two."""
+    a = QType(7, 8); mul = QType(14, 8, True, RND_CONV, SAT_TCPL)
+    c = QType(17, 4, True, RND_POS_INF, SAT_TCPL)
+    k_t = QType(1, 14, True, RND_POS_INF, SAT_TCPL)
+    lv = [QType(15 + l, 8 - l, True, RND_POS_INF, SAT_TCPL) for l in range(6)]
+    plan = ops.make_gemul_plan(a, a, c, 64, 64, 64, mul=mul, add=lv)
+    poly = ops.make_poly_plan(c, [(0.0, [(k_t, 0), (k_t, 1 << 11)]), (1e9, [(k_t, 0), (k_t, 1 << 14)])], 0, True)
+    batch = 64
+    A = torch.empty(batch * 4096, dtype=torch.int32, device="cuda"); B = torch.empty_like(A); Cd = torch.empty_like(A)
+    ops.synth_fill(A, a.raw_min, a.raw_max, 9, 0); ops.synth_fill(B, a.raw_min, a.raw_max, 9, 1)
+    ops.Qgemul_poly(Cd, A, B, plan, poly, batch=batch)                                # builds the kernel
+    lib = abi.load()
+    lib.qb200_launch_count_reset()
+    ops.Qgemul_poly(Cd, A, B, plan, poly, batch=batch)
+    assert lib.qb200_launch_count() == 1
 
 
 def test_table_lookup_matches_quantized_function():
