@@ -272,10 +272,11 @@ def run_reference(args):
 
 
 def workload_config(w, args):
-    """The part of `config` that both arms print identically (the driver compares it)."""
+    """`config`: printed identically by both arms (the driver compares it); what is specific to one arm goes to `details`."""
     cfg = {"workload": WORKLOADS[w]}
     if w == "c3":
         cfg["batch_per_gpu"] = args.batch
+        cfg["l2"] = "no flush needed: the inputs of a step (%.1f GB per GPU) are far larger than the 126 MB L2" % (2 * args.batch * WORDS * 4 / 1e9)
     return cfg
 
 
@@ -356,32 +357,59 @@ def ncu_traffic(tag, alg_bytes_per_launch):
     `ncu --set full` capture (profiles/r1_<tag>_ncu_summary.json), scaled from the capture's launch size to this
     run's by the ratio of algorithmic bytes (the kernels stream every byte once, so traffic is linear in the batch)."""
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_%s_ncu_summary.json" % tag)))[0]
+        path = os.path.join(ROOT, "profiles", "r2_%s_ncu_summary.json" % tag)
+        if not os.path.exists(path):
+            path = os.path.join(ROOT, "profiles", "r1_%s_ncu_summary.json" % tag)
+        prof = json.load(open(path))[0]
         return float(prof["traffic_bytes"]) * alg_bytes_per_launch / NCU_CAPTURE_ALG_BYTES[tag]
     except Exception:
         return None
 
 
-def roofline_alu(lib, gmacs, device):
-    """The headline kernel is bound by instruction issue on the INT32/FP32 pipes, not by HBM: compare its
-    achieved thread-instruction rate (instructions per MAC from the committed ncu capture,
-    profiles/r1_c3_ncu_summary.json) with the issue peak measured live by qb200_measure_int_peak."""
+def roofline_alu(lib, gmacs, device, sm_mhz=None):
+    """The headline kernel is bound by instruction issue on the INT32/FP32 pipes, not by HBM.  Three yardsticks:
+      frac      achieved thread-instruction rate (instructions per MAC of the committed ncu capture of THIS round's kernel)
+                over the issue peak measured live by qb200_measure_int_peak (IMAD + IADD3/LOP3 mix on all SMs);
+      frac_hw   the same over the hardware's issue rate, SMs x 4 schedulers x 32 lanes x the SM clock sampled in this run;
+      frac_mix  GMAC/s over the rate the SAME instruction mix reaches from registers alone (no shared memory, no barriers:
+                tools/mix_probe.cu, profiles/r2_mix_probe.jsonl) -- the ceiling of this formulation of the arithmetic."""
     from qublas_b200 import abi
     out = {"bound": "issue (INT32 ALU + FP32 FMA pipes)", "unit": "T thread-instr/s", "scope": "per GPU"}
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_c3_ncu_summary.json")))[0]
+        name = "r2_c3_ncu_summary.json" if os.path.exists(os.path.join(ROOT, "profiles", "r2_c3_ncu_summary.json")) else "r1_c3_ncu_summary.json"
+        prof = json.load(open(os.path.join(ROOT, "profiles", name)))[0]
         ipm = float(prof["thread_instructions_per_unit"])
         out.update({"instr_per_mac": ipm, "ncu_pipe_alu_pct": prof.get("pipe_alu_pct"), "ncu_pipe_fma_pct": prof.get("pipe_fma_pct"),
-                    "ncu_issue_active_pct": prof.get("issue_active_pct"), "source": "profiles/r1_c3_ncu_summary.json"})
+                    "ncu_issue_active_pct": prof.get("issue_active_pct"), "source": "profiles/" + name})
     except Exception:
         return out
+    out["achieved"] = gmacs * 1e9 * ipm / 1e12
     t = ctypes.c_double()
     ex = abi.qb_exec(abi.QB_MEM_DEVICE, device, None, 0, 0)
     if lib.qb200_measure_int_peak(0.25, ctypes.byref(t), ctypes.byref(ex)) == 0 and t.value > 0:
-        out["achieved"] = gmacs * 1e9 * ipm / 1e12
         out["peak"] = t.value
         out["frac"] = out["achieved"] / out["peak"]
         out["peak_source"] = "qb200_measure_int_peak (IMAD + IADD3/LOP3 mix, all SMs), this run"
+    try:
+        import torch
+        sms = torch.cuda.get_device_properties(device).multi_processor_count
+        if sm_mhz:
+            out["peak_hw"] = sms * 4 * 32 * sm_mhz * 1e6 / 1e12
+            out["frac_hw"] = out["achieved"] / out["peak_hw"]
+            out["peak_hw_source"] = "%d SMs x 4 schedulers x 32 lanes x %.0f MHz (median SM clock of the timed region)" % (sms, sm_mhz)
+    except Exception:
+        pass
+    try:
+        best = 0.0
+        for ln in open(os.path.join(ROOT, "profiles", "r2_mix_probe.jsonl")):
+            if ln.startswith("{") and "tmacs_equiv" in ln:
+                best = max(best, float(json.loads(ln)["tmacs_equiv"]))
+        if best > 0:
+            out["mix_ceiling_gmacs"] = best * 1e3
+            out["frac_mix"] = gmacs / (best * 1e3)
+            out["mix_source"] = "profiles/r2_mix_probe.jsonl (tools/mix_probe.cu: the kernel's FFMA/IADD3/SHF/LEA mix from registers only, best variant)"
+    except Exception:
+        pass
     return out
 
 
@@ -557,16 +585,16 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "GMAC/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
-            "config": {**workload_config("c3", args), "sharding": "batch, no data-path collective", "kernel": info.kernel.decode(),
-                       "l2": "inputs (%.1f GB per GPU) are far larger than the 126 MB L2; no flush needed" % (2 * Bn * WORDS * 4 / 1e9),
-                       "e2e_host_ring": "2 pinned slots x %d instances, reused cyclically; %d instances per e2e step" % (chunk, e2e_instances),
-                       "cpu_affinity": affinity},
+            "config": workload_config("c3", args),
+            "details": {"sharding": "batch, no data-path collective", "kernel": info.kernel.decode(),
+                        "e2e_host_ring": "2 pinned slots x %d instances, reused cyclically; %d instances per e2e step" % (chunk, e2e_instances),
+                        "cpu_affinity": affinity},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": ncu_traffic("c3", bytes_per_launch), "algorithmic_bytes": bytes_per_launch,
-                         "traffic_source": "profiles/r1_c3_ncu_summary.json (32768-instance launch), scaled to this launch",
+                         "traffic_source": "profiles/%s_c3_ncu_summary.json (32768-instance launch), scaled to this launch" % ("r2" if os.path.exists(os.path.join(ROOT, "profiles", "r2_c3_ncu_summary.json")) else "r1"),
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                          "note": "this kernel is bound by the INT32 issue rate, not HBM: see roofline_alu"},
-            "roofline_alu": roofline_alu(lib, value / world, local),
+            "roofline_alu": roofline_alu(lib, value / world, local, clocks.get("sm_mhz") if isinstance(clocks, dict) else None),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "GMAC/s", "h2d_bytes_per_step": world * h2d_b, "d2h_bytes_per_step": world * d2h_b,
                     "scope": "whole job (all ranks)",
@@ -578,6 +606,22 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline("c3", 12.0)
+        if world == 1 and not args.no_secondary:
+            # the other BASELINE configurations, measured in the same run with the same timing discipline (a few seconds each;
+            # `python bench.py --workload c2|c4|c5` prints their full lines, with their own CPU baselines)
+            del A, B, Cd
+            torch.cuda.empty_cache()
+            sec = {}
+            for w in ("c2", "c4", "c5"):
+                try:
+                    sub = argparse.Namespace(**{**vars(args), "workload": w, "no_cpu": True})
+                    r = run_secondary(sub, embed=True)
+                    sec[w] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "roofline", "clocks", "e2e", "gpu_launches") if k in r}
+                    sec[w]["kernel"] = r["config"].get("kernel")
+                except Exception as ex:          # a secondary leg must never cost the headline line
+                    sec[w] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+                torch.cuda.empty_cache()
+            line["secondary"] = sec
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -587,7 +631,8 @@ def run_ours(args):
 # ------------------------------------------------------------------------------------------------
 # secondary workloads (BASELINE configs 2, 4, 5): same timing discipline, one JSON line each
 # ------------------------------------------------------------------------------------------------
-def run_secondary(args):
+def run_secondary(args, embed=False):
+    """One JSON line for BASELINE config 2, 4 or 5; embed=True (single GPU): return the line instead of printing it."""
     import numpy as np
     import torch
     from oracle import oracle
@@ -601,7 +646,7 @@ def run_secondary(args):
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 and not embed:
         dist.init_process_group("nccl", device_id=dev)
     peaks = {}
     try:
@@ -700,18 +745,19 @@ def run_secondary(args):
         def cpu():
             return cpu_baseline("c4", 8.0)
     else:  # c5
-        Mm = Kk = 8192
-        Nn = 8192 // world          # column panel of B and C per GPU (contiguous in column-major storage); A is replicated
+        Nn = Kk = 8192
+        Mm = 8192 // world          # M-row panel of A and C per GPU; B is replicated.  A is handed over K-major (QgemulTransposedA:
+                                    # stored K x M), so a row panel of op(A) is one contiguous block of the caller's matrix
         a = QType(7, 0); acc = QType(30, 0)
-        plan = ops.make_gemul_plan(a, a, acc, Mm, Nn, Kk, mul=QType(15, 0), add=[acc])
+        plan = ops.make_gemul_plan(a, a, acc, Mm, Nn, Kk, mul=QType(15, 0), add=[acc], trans_a=True)
         info = ops.plan_info_gemul(plan)
         assert info.tensor_core == 1
         A = torch.empty(Mm * Kk, dtype=torch.int32, device=dev); B = torch.empty(Kk * Nn, dtype=torch.int32, device=dev)
-        ops.synth_fill(A, -128, 127, 1, 0); ops.synth_fill(B, -128, 127, 1, 1, rank * Kk * Nn)
+        ops.synth_fill(A, -128, 127, 1, 0, rank * Mm * Kk); ops.synth_fill(B, -128, 127, 1, 1)
         Cd = torch.empty(Mm * Nn, dtype=torch.int32, device=dev)
         ops.Qgemul(Cd, A, B, plan)
-        rows = torch.arange(0, Mm, 127, device=dev)                                  # exact float64 cross-check on 65 sampled rows
-        ref = (A.view(Kk, Mm).t()[rows].double() @ B.view(Nn, Kk).t().double())
+        rows = torch.arange(0, Mm, 127, device=dev)                                  # exact float64 cross-check on sampled rows
+        ref = (A.view(Mm, Kk)[rows].double() @ B.view(Nn, Kk).t().double())
         assert torch.equal(Cd.view(Nn, Mm).t()[rows].double(), ref), "tensor-core Qgemul differs from the exact float64 GEMM"
         ms, launches, clocks = timed(lambda: ops.Qgemul(Cd, A, B, plan))
         ops_total = 2.0 * Mm * Nn * Kk
@@ -738,11 +784,11 @@ def run_secondary(args):
         e2e_s = wall(lambda: ops.Qgemul(hC.numpy(), hA.numpy(), hB.numpy(), plan))
         e2e = {"value": ops_total / e2e_s / 1e12, "unit": unit, "h2d_bytes_per_step": 2 * Mm * Kk * 4, "d2h_bytes_per_step": Mm * Nn * 4}
         cfg = {"workload": WORKLOADS["c5"],
-               "kernel": info.kernel.decode(), "sharding": "column panels of B and C (%d columns per GPU), A replicated, no collective" % Nn}
+               "kernel": info.kernel.decode(), "sharding": "M-row panels of A and C (%d rows per GPU, A stored K-major), B replicated, no collective" % Mm}
 
         def cpu():
             pl = ops.make_gemul_plan(a, a, acc, 16, 16, Kk, mul=QType(15, 0), add=[acc])
-            Ah = np.ascontiguousarray(A.view(Kk, Mm)[:, :16].cpu().numpy()).reshape(-1); Bh = B[:16 * Kk].cpu().numpy()
+            Ah = np.ascontiguousarray(A.view(Mm, Kk)[:16].t().cpu().numpy()).reshape(-1); Bh = B[:16 * Kk].cpu().numpy()
             t0 = time.perf_counter(); oracle.gemul_batched(pl, Ah, Bh, 1); dt = time.perf_counter() - t0
             return {"value": 2.0 * 16 * 16 * Kk / dt / 1e12, "unit": unit, "cores": 1, "kind": "port", "sample": "a 16x16x8192 corner through the C oracle, 1 core"}
 
@@ -755,6 +801,8 @@ def run_secondary(args):
     if rank != 0:
         dist.destroy_process_group()
         return
+    if w in ("c2", "c4", "c5") and os.path.exists(os.path.join(ROOT, "profiles", "r2_%s_ncu_summary.json" % w)):
+        roof["traffic_source"] = roof["traffic_source"].replace("r1_", "r2_")
     line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong" if w == "c5" else "weak", "vs_baseline": None,
             "dtype": "int32" if w != "c5" else "int8 x int8 -> int32",
@@ -764,6 +812,8 @@ def run_secondary(args):
             line["cpu_baseline"] = cpu()
         except Exception as ex:      # e.g. oracle/_ref absent
             line["cpu_baseline"] = {"unavailable": str(ex)}
+    if embed:
+        return line
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -781,6 +831,7 @@ def main():
     ap.add_argument("--no-sweep", action="store_true", help="skip the supplementary device-resident Monte-Carlo sweep")
     ap.add_argument("--e2e-instances", type=int, default=1000000, help="instances per end-to-end step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the BASELINE config 2 / 4 / 5 legs appended to the default single-GPU line")
     ap.add_argument("--check-instances", type=int, default=512, help="instances per rank compared with the oracle before timing")
     ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5"],
                     help="c3 = headline (batched 64^3 Qgemul); c2 = Qreduce 2^24; c4 = TFComplexMul 256x256 mat-vec; c5 = 8192^3 tcgen05 i8")
