@@ -947,3 +947,32 @@ def test_tile_kernel_deferred_shift_tree_vs_oracle(K, modes, fp):
     C2 = torch.empty_like(Cd)
     ops.Qgemul(C2, A, B, plan, batch=batch, flags=abi.QB_F_NO_SPECIALIZE)
     assert torch.equal(Cd, C2)
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 64, 64), (128, 64, 32), (64, 32, 128), (32, 64, 16)])
+@pytest.mark.parametrize("product", ["tf", "basic"])
+def test_complex_gemul_register_tile_kernel_vs_oracle(M, N, K, product):
+    """Batched complex Qgemul with N > 1 on the register-tile kernel (qb_fast_cgemul_tile.cuh): TFComplexMul and
+    BasicComplexMul products with distinct node types, full-range operands, a shared B operand; same bits as the oracle and as
+    the runtime-descriptor kernel."""
+    t = QType(3, 12); P = QType(6, 12); S = QType(7, 12)
+    tags = {"abT": QType(4, 12), "cdT": QType(4, 11), "abcT": P, "cdbT": P, "badT": P, "ABT": S, "BCT": S} if product == "tf" else None
+    lv = [QType(8 + l, 12 - l, True, RND_CONV, SAT_TCPL) for l in range((K - 1).bit_length())]
+    lvi = [QType(9 + l, 11 - l, True, RND_POS_INF, SAT_TCPL) for l in range((K - 1).bit_length())]
+    plan = ops.make_cgemul_plan(t, t, t, t, lv[-1], QType(12, 3), M, N, K, tf_tags=tags, add_re=lv, add_im=lvi, form=TREE_VARIADIC, product=product)
+    batch = 7
+    A = torch.empty(batch * M * K * 2, dtype=torch.int32, device="cuda"); B = torch.empty(batch * K * N * 2, dtype=torch.int32, device="cuda")
+    ops.synth_fill(A, t.raw_min, t.raw_max, 31, 0); ops.synth_fill(B, t.raw_min, t.raw_max, 31, 1)
+    A[:64] = t.raw_min; B[:64] = t.raw_min
+    Cd = torch.empty(batch * M * N * 2, dtype=torch.int32, device="cuda")
+    ops.Qcgemul(Cd, A, B, plan, batch=batch)
+    assert b"tile" in ops.plan_info_cgemul(plan).kernel
+    want = oracle.cgemul_batched(plan, A.cpu().numpy(), B.cpu().numpy(), batch)
+    assert np.array_equal(Cd.cpu().numpy(), want)
+    C2 = torch.empty_like(Cd)
+    ops.Qcgemul(C2, A, B, plan, batch=batch, flags=abi.QB_F_NO_SPECIALIZE)
+    assert torch.equal(Cd, C2)
+    plan.stride_b = 0                                      # one B for all instances
+    ops.Qcgemul(Cd, A, B, plan, batch=batch)
+    want = oracle.cgemul_batched(plan, A.cpu().numpy(), B.cpu().numpy(), batch)
+    assert np.array_equal(Cd.cpu().numpy(), want)
