@@ -227,6 +227,13 @@ std::string emit_cgemul_thread_cfg(const std::string &name, const qb_cgemul_plan
     o << "  static constexpr __host__ __device__ qb::QStage out_im() { return " << emit_qstage(g.out_im) << "; }\n";
     o << emit_levels("lvl_re", g.tree_re, nlev) << emit_levels("lvl_im", g.tree_im, nlev);
     o << emit_flush("flush_re", g.tree_re) << emit_flush("flush_im", g.tree_im);
+    {
+        // TFComplexMul products that are exact as one FFMA (used by the register-tile kernel, qb_fast_cgemul_tile.cuh)
+        CgemulFp f;
+        if (g.kind == QB_CPROD_TF && bits == 32) f = cgemul_fp(p, g);
+        o << "  static constexpr bool FP_A = " << (f.fa ? "true" : "false") << ", FP_B = " << (f.fb ? "true" : "false") << ", FP_C = " << (f.fc ? "true" : "false") << ";\n";
+        o << "  static constexpr int SH_A = " << (f.fa ? (int)g.tf.A.shift : 1) << ", SH_B = " << (f.fb ? (int)g.tf.B.shift : 1) << ", SH_C = " << (f.fc ? (int)g.tf.C.shift : 1) << ";\n";
+    }
     o << "};\n";
     return o.str();
 }

@@ -184,4 +184,160 @@ QB_DEV void cgemul_tile_body(const int2 *__restrict__ A, const int2 *__restrict_
     }
 }
 
+// ---- TFComplexMul with all three products on the FP32 FMA pipe ------------------------------------------------------
+// When Qmul<abcT>, Qmul<badT> and Qmul<cdbT> are exact as one FFMA with a magic constant (qb_codegen.cpp:fp_mul_ok, the
+// same proof as for the mat-vec kernel), the operand-only nodes move out of the inner loop altogether: one pass per staged
+// instance turns A into three float planes (a+b, b, b-a -- the real part a alone is never multiplied) and B into
+// (c, c+d, d), each node computed by its integer quantizer and converted exactly.  The inner loop is then 3 FFMA, the two
+// quantized sums and the two tree merges per complex MAC.  B planes are K-contiguous per column and XOR-swizzled by the
+// column block so that the four column blocks a warp reads fall into different banks.
+template <class Cfg>
+struct CGemulTileFp {
+    typedef CGemulTile<Cfg> T;
+    static constexpr int M = T::M, N = T::N, K = T::K;
+    static constexpr uint32_t RAW_BYTES = T::STAGE_BYTES;                                  // one staging buffer
+    static constexpr uint32_t PLANE_A = (uint32_t)M * K * 4, PLANE_B = (uint32_t)K * N * 4;
+    static constexpr uint32_t SMEM_BYTES = RAW_BYTES + 3 * PLANE_A + 3 * PLANE_B + 64;
+    static_assert(K % 16 == 0, "swizzled B planes need at least four 16-byte chunks per column");
+    static_assert(Cfg::KIND == 0 && Cfg::FP_A && Cfg::FP_B && Cfg::FP_C, "TFComplexMul with three FP-pipe products");
+};
+
+template <class Cfg>
+QB_DEV void cgemul_tile_fp_body(const int2 *__restrict__ A, const int2 *__restrict__ B, int2 *__restrict__ C, uint64_t batch)
+{
+    typedef CGemulTile<Cfg> T;
+    typedef CGemulTileFp<Cfg> F;
+    typedef typename Cfg::I I;
+    constexpr int M = T::M, N = T::N, K = T::K, NTOP = T::NTOP;
+    constexpr TfProg tf = Cfg::tf();
+    constexpr QStage ore = Cfg::out_re(), oim = Cfg::out_im();
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *pab = (float *)(smem_raw + F::RAW_BYTES), *pb = pab + M * K, *pba = pb + M * K;            // A planes [k][i]
+    float *pc = pba + M * K, *pcd = pc + K * N, *pd = pcd + K * N;                                    // B planes [j][k], swizzled
+    uint64_t *bar = (uint64_t *)(smem_raw + F::RAW_BYTES + 3 * F::PLANE_A + 3 * F::PLANE_B);
+
+    const int tid = threadIdx.x;
+    int tx, ty;
+    if constexpr (T::PATCH) {
+        constexpr int WX = (M / 4) / 8;
+        const int wp = tid >> 5;
+        tx = (wp % WX) * 8 + ((tid & 1) | ((tid >> 1) & 2) | ((tid >> 2) & 4));
+        ty = (wp / WX) * 4 + (((tid >> 1) & 1) | ((tid >> 2) & 2));
+    } else {
+        tx = tid % (M / 4); ty = tid / (M / 4);
+    }
+    const int i0 = tx * 4, j0 = ty * 2;
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](uint64_t inst) {
+        mbar_expect_tx(bar, T::STAGE_BYTES);
+        tma_load_1d(smem_raw, A + inst * (uint64_t)Cfg::SA, T::A_BYTES, bar);
+        tma_load_1d(smem_raw + T::A_BYTES, B + inst * (uint64_t)Cfg::SB, T::B_BYTES, bar);
+    };
+    uint64_t inst = blockIdx.x;
+    if (inst < batch && tid == 0) issue(inst);
+
+    // per-thread B chunk offsets (in float4 units): chunk (kc % 4) ^ (column block % 4) within an aligned group of four
+    const int swb = ty & 3;
+    const float4 *bcol[3][2];
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) { bcol[0][jj] = (const float4 *)(pc + (j0 + jj) * K); bcol[1][jj] = (const float4 *)(pcd + (j0 + jj) * K); bcol[2][jj] = (const float4 *)(pd + (j0 + jj) * K); }
+
+    for (uint32_t it = 0; inst < batch; inst += gridDim.x, ++it) {
+        mbar_wait(bar, it & 1);
+        // ---- pass: operand-only nodes as exact floats ----
+        {
+            const int4 *rawA = (const int4 *)smem_raw;                                      // two complex elements per 16 bytes
+            for (int e = tid; e < M * K / 4; e += T::BLOCK) {                              // four consecutive rows of one k
+                const int4 q0 = rawA[2 * e], q1 = rawA[2 * e + 1];
+                const I a[4] = { q0.x, q0.z, q1.x, q1.z }, b[4] = { q0.y, q0.w, q1.y, q1.w };
+                float fab[4], fb[4], fba[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    fab[u] = __int2float_rn((int)add_apply<I, true>(a[u], b[u], tf.ab));    // QuBLAS.h:3524 Qadd<abT>(a, b)
+                    fb[u] = __int2float_rn((int)b[u]);
+                    fba[u] = __int2float_rn((int)add_apply<I, true>(b[u], a[u], tf.ba));    // :3526 Qsub(b, a)
+                }
+                ((float4 *)pab)[e] = make_float4(fab[0], fab[1], fab[2], fab[3]);
+                ((float4 *)pb)[e] = make_float4(fb[0], fb[1], fb[2], fb[3]);
+                ((float4 *)pba)[e] = make_float4(fba[0], fba[1], fba[2], fba[3]);
+            }
+            const int4 *rawB = (const int4 *)(smem_raw + T::A_BYTES);
+            for (int e = tid; e < K * N / 4; e += T::BLOCK) {                              // four consecutive k of one column
+                const int4 q0 = rawB[2 * e], q1 = rawB[2 * e + 1];
+                const I c[4] = { q0.x, q0.z, q1.x, q1.z }, d[4] = { q0.y, q0.w, q1.y, q1.w };
+                float fc[4], fcd[4], fd[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    fc[u] = __int2float_rn((int)c[u]);
+                    fcd[u] = __int2float_rn((int)add_apply<I, true>(c[u], d[u], tf.cd));    // :3525 Qadd<cdT>(c, d)
+                    fd[u] = __int2float_rn((int)d[u]);
+                }
+                const int j = e / (K / 4), ch = e % (K / 4);
+                const int o = j * (K / 4) + (ch ^ ((j >> 1) & 3));                         // swizzle by the column block (two columns per tile)
+                ((float4 *)pc)[o] = make_float4(fc[0], fc[1], fc[2], fc[3]);
+                ((float4 *)pcd)[o] = make_float4(fcd[0], fcd[1], fcd[2], fcd[3]);
+                ((float4 *)pd)[o] = make_float4(fd[0], fd[1], fd[2], fd[3]);
+            }
+        }
+        __syncthreads();
+        const uint64_t next = inst + gridDim.x;
+        if (tid == 0 && next < batch) issue(next);                 // the pass has consumed the staged instance
+
+        I tr[4][2][NTOP > 0 ? NTOP : 1], ti[4][2][NTOP > 0 ? NTOP : 1];
+        I rr[4][2], ri[4][2];
+        constexpr int CHUNK_UNROLL = T::NCH <= 8 ? T::NCH : 1;
+#pragma unroll CHUNK_UNROLL
+        for (uint32_t c = 0; c < (uint32_t)T::NCH; ++c) {
+            I lr[4][2][3], li[4][2][3];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int kc = 2 * (int)c + h;                     // 16-byte chunk of k
+                float4 fcq[2], fcdq[2], fdq[2];
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int o = (kc & ~3) | ((kc & 3) ^ swb);
+                    fcq[jj] = bcol[0][jj][o]; fcdq[jj] = bcol[1][jj][o]; fdq[jj] = bcol[2][jj][o];
+                }
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const int k = 4 * kc + kk, u = 4 * h + kk;
+                    const float4 fab = *(const float4 *)(pab + k * M + i0), fb = *(const float4 *)(pb + k * M + i0), fba = *(const float4 *)(pba + k * M + i0);
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj) {
+                        const float cc = (&fcq[jj].x)[kk], cd = (&fcdq[jj].x)[kk], d = (&fdq[jj].x)[kk];
+#pragma unroll
+                        for (int ii = 0; ii < 4; ++ii) {
+                            const I Av = (I)(fp_mul_apply<Cfg::SH_A, true>((&fab.x)[ii], cc, tf.A) - fp_kbits<Cfg::SH_A>());
+                            const I Bv = (I)(fp_mul_apply<Cfg::SH_B, true>(cd, (&fb.x)[ii], tf.B) - fp_kbits<Cfg::SH_B>());
+                            const I Cv = (I)(fp_mul_apply<Cfg::SH_C, true>((&fba.x)[ii], d, tf.C) - fp_kbits<Cfg::SH_C>());
+                            const I vr = add_apply<I, true>(Av, Bv, tf.re);                  // :3528
+                            const I vi = add_apply<I, true>(Bv, Cv, tf.im);                  // :3529
+                            I nr, ni;
+                            clow_push<Cfg, 0, I>(lr[ii][jj], li[ii][jj], u, vr, vi, nr, ni);
+                            if (u == 7) ctop_push<Cfg, 0, NTOP, I>(tr[ii][jj], ti[ii][jj], c, nr, ni, rr[ii][jj], ri[ii][jj]);
+                        }
+                    }
+                }
+            }
+        }
+        int2 *Ci = C + inst * (uint64_t)Cfg::SC;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                int4 o;
+                o.x = (int)conv_apply<I, true>(rr[2 * h][jj], ore); o.y = (int)conv_apply<I, true>(ri[2 * h][jj], oim);
+                o.z = (int)conv_apply<I, true>(rr[2 * h + 1][jj], ore); o.w = (int)conv_apply<I, true>(ri[2 * h + 1][jj], oim);
+                *(int4 *)(Ci + (size_t)(j0 + jj) * M + i0 + 2 * h) = o;
+            }
+        }
+        __syncthreads();      // the planes are free for the next pass
+    }
+}
+
 }  // namespace qb
