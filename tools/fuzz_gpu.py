@@ -59,6 +59,10 @@ def one_gemul(rng, stats):
 def one_cgemul(rng, stats):
     M, N, K = (int(rng.choice(v)) for v in ([1, 2, 3, 5, 8, 16, 32, 64], [1, 2, 4, 7], [1, 2, 5, 8, 16, 24, 33, 64, 128]))
     kind = str(rng.choice(["tf", "basic", "real_a", "real_b"]))
+    tile_shape = rng.random() < 0.25                      # a quarter of the cases: shapes the register-tile kernels take
+    if tile_shape:
+        M, N, K = (int(rng.choice(v)) for v in ([32, 64, 128], [16, 32, 64], [16, 32, 64]))
+        kind = str(rng.choice(["tf", "basic"]))
     ar, ai, br, bi = rt(rng, 2, 7, 1, 9), rt(rng, 2, 7, 1, 9), rt(rng, 2, 7, 1, 9), rt(rng, 2, 7, 1, 9)
     def tg(names):
         return {k: rt(rng, 5, 12, 2, 10) for k in names if rng.random() < 0.8}
@@ -73,7 +77,7 @@ def one_cgemul(rng, stats):
     lre, lim = levels(rng, leaf[0], int(rng.choice([1, 3, 6]))), levels(rng, leaf[1], int(rng.choice([1, 2, 5])))
     form = TREE_VECTOR if rng.random() < 0.5 else TREE_VARIADIC
     plan = ops.make_cgemul_plan(*args, rt(rng, 8, 12, 2, 6), rt(rng, 8, 12, 2, 6), M, N, K, tf_tags=tags, add_re=lre, add_im=lim, form=form, product=kind,
-                                trans_a=bool(rng.random() < 0.3), trans_b=bool(rng.random() < 0.3))
+                                trans_a=bool(rng.random() < 0.3) and not tile_shape, trans_b=bool(rng.random() < 0.3) and not tile_shape)
     batch = int(rng.integers(1, 5))
     def cw(re_t, im_t, n):
         if im_t is None:
