@@ -230,9 +230,12 @@ std::string emit_cgemul_thread_cfg(const std::string &name, const qb_cgemul_plan
     {
         // TFComplexMul products that are exact as one FFMA (used by the register-tile kernel, qb_fast_cgemul_tile.cuh)
         CgemulFp f;
-        if (g.kind == QB_CPROD_TF && bits == 32) f = cgemul_fp(p, g);
+        if ((g.kind == QB_CPROD_TF || g.kind == QB_CPROD_BASIC) && bits == 32) f = cgemul_fp(p, g);
         o << "  static constexpr bool FP_A = " << (f.fa ? "true" : "false") << ", FP_B = " << (f.fb ? "true" : "false") << ", FP_C = " << (f.fc ? "true" : "false") << ";\n";
         o << "  static constexpr int SH_A = " << (f.fa ? (int)g.tf.A.shift : 1) << ", SH_B = " << (f.fb ? (int)g.tf.B.shift : 1) << ", SH_C = " << (f.fc ? (int)g.tf.C.shift : 1) << ";\n";
+        o << "  static constexpr bool FP_BCM = " << (f.fbcm ? "true" : "false") << ";\n";
+        o << "  static constexpr int SH_AC = " << (f.fbcm ? (int)g.bcm.ac.shift : 1) << ", SH_BD = " << (f.fbcm ? (int)g.bcm.bd.shift : 1) << ", SH_AD = " << (f.fbcm ? (int)g.bcm.ad.shift : 1)
+          << ", SH_BC = " << (f.fbcm ? (int)g.bcm.bc.shift : 1) << ";\n";
     }
     o << "};\n";
     return o.str();
@@ -258,6 +261,12 @@ static bool fp_mul_ok(const QStage &q, const TVal &x, const TVal &y)
 CgemulFp cgemul_fp(const qb_cgemul_plan &p, const CGemulProg &g)
 {
     CgemulFp f;
+    if (g.kind == QB_CPROD_BASIC) {
+        // BasicComplexMul (QuBLAS.h:3437-3445): four products of raw operands
+        const TVal a = { p.a_re, type_range(p.a_re) }, b = { p.a_im, type_range(p.a_im) }, c = { p.b_re, type_range(p.b_re) }, d = { p.b_im, type_range(p.b_im) };
+        f.fbcm = fp_mul_ok(g.bcm.ac, a, c) && fp_mul_ok(g.bcm.bd, b, d) && fp_mul_ok(g.bcm.ad, a, d) && fp_mul_ok(g.bcm.bc, b, c);
+        return f;
+    }
     // FP32-FMA quantizer for the three TF products where it is exact
     Analysis an; TVal re, im, mid[3];
     TVal a = { p.a_re, type_range(p.a_re) }, b = { p.a_im, type_range(p.a_im) }, c = { p.b_re, type_range(p.b_re) }, d = { p.b_im, type_range(p.b_im) };

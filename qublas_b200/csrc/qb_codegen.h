@@ -32,7 +32,8 @@ bool gemul_fp_mul(const qb_gemul_plan &p, const GemulProg &g);
 // dynamic shared memory of the register-tile template for `group` instances per CTA (0: does not fit); *sep: separate 32-bit copy
 uint64_t gemul_tile_smem(const qb_gemul_plan &p, const GemulProg &g, int group, bool *sep);
 void gemul_clamp_thresholds(const GemulProg &g, long long *p_hi, long long *p_lo);
-struct CgemulFp { bool fa = false, fb = false, fc = false, fadd_ab = false, fadd_ba = false; Ival ab, cd, ba; };
+struct CgemulFp { bool fa = false, fb = false, fc = false, fadd_ab = false, fadd_ba = false; Ival ab, cd, ba;
+                  bool fbcm = false; };      // fbcm: all four BasicComplexMul products are exact as one FFMA each
 CgemulFp cgemul_fp(const qb_cgemul_plan &p, const CGemulProg &g);
 
 }  // namespace qb

@@ -197,9 +197,10 @@ struct CGemulTileFp {
     static constexpr int M = T::M, N = T::N, K = T::K;
     static constexpr uint32_t RAW_BYTES = T::STAGE_BYTES;                                  // one staging buffer
     static constexpr uint32_t PLANE_A = (uint32_t)M * K * 4, PLANE_B = (uint32_t)K * N * 4;
-    static constexpr uint32_t SMEM_BYTES = RAW_BYTES + 3 * PLANE_A + 3 * PLANE_B + 64;
+    static constexpr int NP = Cfg::KIND == 0 ? 3 : 2;               // float planes per operand: TF (a+b, b, b-a | c, c+d, d), Basic (a, b | c, d)
+    static constexpr uint32_t SMEM_BYTES = RAW_BYTES + NP * PLANE_A + NP * PLANE_B + 64;
     static_assert(K % 16 == 0, "swizzled B planes need at least four 16-byte chunks per column");
-    static_assert(Cfg::KIND == 0 && Cfg::FP_A && Cfg::FP_B && Cfg::FP_C, "TFComplexMul with three FP-pipe products");
+    static_assert((Cfg::KIND == 0 && Cfg::FP_A && Cfg::FP_B && Cfg::FP_C) || (Cfg::KIND == 1 && Cfg::FP_BCM), "every product on the FP pipe");
 };
 
 template <class Cfg>
@@ -212,9 +213,12 @@ QB_DEV void cgemul_tile_fp_body(const int2 *__restrict__ A, const int2 *__restri
     constexpr TfProg tf = Cfg::tf();
     constexpr QStage ore = Cfg::out_re(), oim = Cfg::out_im();
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *pab = (float *)(smem_raw + F::RAW_BYTES), *pb = pab + M * K, *pba = pb + M * K;            // A planes [k][i]
-    float *pc = pba + M * K, *pcd = pc + K * N, *pd = pcd + K * N;                                    // B planes [j][k], swizzled
-    uint64_t *bar = (uint64_t *)(smem_raw + F::RAW_BYTES + 3 * F::PLANE_A + 3 * F::PLANE_B);
+    constexpr bool TF = Cfg::KIND == 0;
+    constexpr BcmProg bcm = Cfg::bcm();
+    // A planes [k][i]: TF (a+b, b, b-a), Basic (a, b, -);  B planes [j][k], swizzled: TF (c, c+d, d), Basic (c, -, d)
+    float *pab = (float *)(smem_raw + F::RAW_BYTES), *pb = pab + M * K, *pba = TF ? pb + M * K : pb;
+    float *pc = (float *)(smem_raw + F::RAW_BYTES + F::NP * F::PLANE_A), *pcd = TF ? pc + K * N : pc, *pd = TF ? pcd + K * N : pc + K * N;
+    uint64_t *bar = (uint64_t *)(smem_raw + F::RAW_BYTES + F::NP * F::PLANE_A + F::NP * F::PLANE_B);
 
     const int tid = threadIdx.x;
     int tx, ty;
@@ -258,13 +262,13 @@ QB_DEV void cgemul_tile_fp_body(const int2 *__restrict__ A, const int2 *__restri
                 float fab[4], fb[4], fba[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    fab[u] = __int2float_rn((int)add_apply<I, true>(a[u], b[u], tf.ab));    // QuBLAS.h:3524 Qadd<abT>(a, b)
+                    fab[u] = __int2float_rn(TF ? (int)add_apply<I, true>(a[u], b[u], tf.ab) : (int)a[u]);    // QuBLAS.h:3524 Qadd<abT>(a, b)
                     fb[u] = __int2float_rn((int)b[u]);
-                    fba[u] = __int2float_rn((int)add_apply<I, true>(b[u], a[u], tf.ba));    // :3526 Qsub(b, a)
+                    if constexpr (TF) fba[u] = __int2float_rn((int)add_apply<I, true>(b[u], a[u], tf.ba));    // :3526 Qsub(b, a)
                 }
                 ((float4 *)pab)[e] = make_float4(fab[0], fab[1], fab[2], fab[3]);
                 ((float4 *)pb)[e] = make_float4(fb[0], fb[1], fb[2], fb[3]);
-                ((float4 *)pba)[e] = make_float4(fba[0], fba[1], fba[2], fba[3]);
+                if constexpr (TF) ((float4 *)pba)[e] = make_float4(fba[0], fba[1], fba[2], fba[3]);
             }
             const int4 *rawB = (const int4 *)(smem_raw + T::A_BYTES);
             for (int e = tid; e < K * N / 4; e += T::BLOCK) {                              // four consecutive k of one column
@@ -274,13 +278,13 @@ QB_DEV void cgemul_tile_fp_body(const int2 *__restrict__ A, const int2 *__restri
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     fc[u] = __int2float_rn((int)c[u]);
-                    fcd[u] = __int2float_rn((int)add_apply<I, true>(c[u], d[u], tf.cd));    // :3525 Qadd<cdT>(c, d)
+                    if constexpr (TF) fcd[u] = __int2float_rn((int)add_apply<I, true>(c[u], d[u], tf.cd));    // :3525 Qadd<cdT>(c, d)
                     fd[u] = __int2float_rn((int)d[u]);
                 }
                 const int j = e / (K / 4), ch = e % (K / 4);
                 const int o = j * (K / 4) + (ch ^ ((j >> 1) & 3));                         // swizzle by the column block (two columns per tile)
                 ((float4 *)pc)[o] = make_float4(fc[0], fc[1], fc[2], fc[3]);
-                ((float4 *)pcd)[o] = make_float4(fcd[0], fcd[1], fcd[2], fcd[3]);
+                if constexpr (TF) ((float4 *)pcd)[o] = make_float4(fcd[0], fcd[1], fcd[2], fcd[3]);
                 ((float4 *)pd)[o] = make_float4(fd[0], fd[1], fd[2], fd[3]);
             }
         }
@@ -301,22 +305,37 @@ QB_DEV void cgemul_tile_fp_body(const int2 *__restrict__ A, const int2 *__restri
 #pragma unroll
                 for (int jj = 0; jj < 2; ++jj) {
                     const int o = (kc & ~3) | ((kc & 3) ^ swb);
-                    fcq[jj] = bcol[0][jj][o]; fcdq[jj] = bcol[1][jj][o]; fdq[jj] = bcol[2][jj][o];
+                    fcq[jj] = bcol[0][jj][o]; fdq[jj] = bcol[2][jj][o];
+                    if constexpr (TF) fcdq[jj] = bcol[1][jj][o];
                 }
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
                     const int k = 4 * kc + kk, u = 4 * h + kk;
-                    const float4 fab = *(const float4 *)(pab + k * M + i0), fb = *(const float4 *)(pb + k * M + i0), fba = *(const float4 *)(pba + k * M + i0);
+                    const float4 fab = *(const float4 *)(pab + k * M + i0), fb = *(const float4 *)(pb + k * M + i0);
+                    float4 fba = fb;
+                    if constexpr (TF) fba = *(const float4 *)(pba + k * M + i0);
 #pragma unroll
                     for (int jj = 0; jj < 2; ++jj) {
-                        const float cc = (&fcq[jj].x)[kk], cd = (&fcdq[jj].x)[kk], d = (&fdq[jj].x)[kk];
+                        const float cc = (&fcq[jj].x)[kk], d = (&fdq[jj].x)[kk];
+                        float cd = cc;
+                        if constexpr (TF) cd = (&fcdq[jj].x)[kk];
 #pragma unroll
                         for (int ii = 0; ii < 4; ++ii) {
-                            const I Av = (I)(fp_mul_apply<Cfg::SH_A, true>((&fab.x)[ii], cc, tf.A) - fp_kbits<Cfg::SH_A>());
-                            const I Bv = (I)(fp_mul_apply<Cfg::SH_B, true>(cd, (&fb.x)[ii], tf.B) - fp_kbits<Cfg::SH_B>());
-                            const I Cv = (I)(fp_mul_apply<Cfg::SH_C, true>((&fba.x)[ii], d, tf.C) - fp_kbits<Cfg::SH_C>());
-                            const I vr = add_apply<I, true>(Av, Bv, tf.re);                  // :3528
-                            const I vi = add_apply<I, true>(Bv, Cv, tf.im);                  // :3529
+                            I vr, vi;
+                            if constexpr (TF) {
+                                const I Av = (I)(fp_mul_apply<Cfg::SH_A, true>((&fab.x)[ii], cc, tf.A) - fp_kbits<Cfg::SH_A>());
+                                const I Bv = (I)(fp_mul_apply<Cfg::SH_B, true>(cd, (&fb.x)[ii], tf.B) - fp_kbits<Cfg::SH_B>());
+                                const I Cv = (I)(fp_mul_apply<Cfg::SH_C, true>((&fba.x)[ii], d, tf.C) - fp_kbits<Cfg::SH_C>());
+                                vr = add_apply<I, true>(Av, Bv, tf.re);                      // :3528
+                                vi = add_apply<I, true>(Bv, Cv, tf.im);                      // :3529
+                            } else {                                                         // fab = a, fb = b (BasicComplexMul, :3437-3445)
+                                const I ac = (I)(fp_mul_apply<Cfg::SH_AC, true>((&fab.x)[ii], cc, bcm.ac) - fp_kbits<Cfg::SH_AC>());
+                                const I bd = (I)(fp_mul_apply<Cfg::SH_BD, true>((&fb.x)[ii], d, bcm.bd) - fp_kbits<Cfg::SH_BD>());
+                                const I ad = (I)(fp_mul_apply<Cfg::SH_AD, true>((&fab.x)[ii], d, bcm.ad) - fp_kbits<Cfg::SH_AD>());
+                                const I bc = (I)(fp_mul_apply<Cfg::SH_BC, true>((&fb.x)[ii], cc, bcm.bc) - fp_kbits<Cfg::SH_BC>());
+                                vr = add_apply<I, true>(ac, bd, bcm.re);                     // :3439
+                                vi = add_apply<I, true>(ad, bc, bcm.im);                     // :3440
+                            }
                             I nr, ni;
                             clow_push<Cfg, 0, I>(lr[ii][jj], li[ii][jj], u, vr, vi, nr, ni);
                             if (u == 7) ctop_push<Cfg, 0, NTOP, I>(tr[ii][jj], ti[ii][jj], c, nr, ni, rr[ii][jj], ri[ii][jj]);

@@ -256,7 +256,7 @@ struct JitSlots {
     bool built_here() const { const int d = here(); return k[d] && k[d]->ok; }
 };
 struct ReduceC { ReduceProg prog; Analysis an; int bits; const FastReduce *fast; JitSlots jit; };
-struct GemulC  { GemulProg prog; Analysis an; int bits; const FastGemul *fast; bool tc; JitSlots jit; };
+struct GemulC  { GemulProg prog; Analysis an; int bits; const FastGemul *fast; bool tc; JitSlots jit, jit_words; };   // jit_words: word-access kernel for unaligned buffers
 struct CGemulC { CGemulProg prog; Analysis an; int bits; const FastCGemul *fast; JitSlots jit; };
 
 template <class Plan, class Entry, class Build>
@@ -599,10 +599,19 @@ extern "C" int qb200_gemul_batched(const qb_gemul_plan *plan, const void *A, con
             if (e) return fail(QB_ECUDA, std::string(f->name) + " launch failed: " + cudaGetErrorString((cudaError_t)e));
             return QB_OK;
         }
-        if (jk && aligned16 && sa == plan->stride_a && sb == plan->stride_b && sc == plan->stride_c) {
-            int e = jit_launch_gemul(*jk, dA, dB, dC, n, st);
+        if (jk && (aligned16 || jk->outputs_per_unit) && sa == plan->stride_a && sb == plan->stride_b && sc == plan->stride_c) {
+            int e = jit_launch_gemul(*jk, dA, dB, dC, n, st);      // the thread-per-output template reads and writes word by word
             if (e) return fail(QB_ECUDA, jk->name + " launch failed (CUresult " + std::to_string(e) + ")");
             return QB_OK;
+        }
+        if (!aligned16 && !(cx.flags & QB_F_NO_SPECIALIZE) && sa == plan->stride_a && sb == plan->stride_b && sc == plan->stride_c) {
+            // buffers that are only word-aligned: the specialised thread-per-output kernel instead of the register tiles
+            JitKernel *jw = ce->jit_words.get([&] { return jit_gemul_thread(*plan, gp, bits); });
+            if (jw) {
+                int e = jit_launch_gemul(*jw, dA, dB, dC, n, st);
+                if (e) return fail(QB_ECUDA, jw->name + " launch failed (CUresult " + std::to_string(e) + ")");
+                return QB_OK;
+            }
         }
         GemulShape S = shape_of(plan->M, plan->N, plan->K, plan->trans_a, plan->trans_b, gp.a_wb, gp.b_wb, gp.c_wb, sa, sb, sc);
         const uint64_t blocks = (n * ec + 127) / 128;

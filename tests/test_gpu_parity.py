@@ -950,13 +950,16 @@ def test_tile_kernel_deferred_shift_tree_vs_oracle(K, modes, fp):
 
 
 @pytest.mark.parametrize("M,N,K", [(64, 64, 64), (128, 64, 32), (64, 32, 128), (32, 64, 16)])
-@pytest.mark.parametrize("product", ["tf", "basic"])
+@pytest.mark.parametrize("product", ["tf", "basic", "basic_q"])
 def test_complex_gemul_register_tile_kernel_vs_oracle(M, N, K, product):
     """Batched complex Qgemul with N > 1 on the register-tile kernel (qb_fast_cgemul_tile.cuh): TFComplexMul and
     BasicComplexMul products with distinct node types, full-range operands, a shared B operand; same bits as the oracle and as
     the runtime-descriptor kernel."""
     t = QType(3, 12); P = QType(6, 12); S = QType(7, 12)
     tags = {"abT": QType(4, 12), "cdT": QType(4, 11), "abcT": P, "cdbT": P, "badT": P, "ABT": S, "BCT": S} if product == "tf" else None
+    if product == "basic_q":           # quantized BasicComplexMul products (FP pipe); "basic" keeps the full-precision defaults (integer products)
+        tags = {"acT": P, "bdT": QType(6, 11, True, RND_CONV, SAT_TCPL), "adT": P, "bcT": QType(5, 12), "acbdT": S, "adbcT": S}
+        product = "basic"
     lv = [QType(8 + l, 12 - l, True, RND_CONV, SAT_TCPL) for l in range((K - 1).bit_length())]
     lvi = [QType(9 + l, 11 - l, True, RND_POS_INF, SAT_TCPL) for l in range((K - 1).bit_length())]
     plan = ops.make_cgemul_plan(t, t, t, t, lv[-1], QType(12, 3), M, N, K, tf_tags=tags, add_re=lv, add_im=lvi, form=TREE_VARIADIC, product=product)

@@ -20,7 +20,8 @@ def main():
     for (M, N, K) in ((64, 64, 64), (32, 32, 32), (64, 16, 128), (128, 64, 32), (16, 16, 16)):
         for prod in ("tf", "basic"):
             lv = [QType(8 + l, 12 - l, True, RND_CONV, SAT_TCPL) for l in range((K - 1).bit_length())]
-            plan = ops.make_cgemul_plan(t, t, t, t, lv[-1], lv[-1], M, N, K, tf_tags=tags if prod == "tf" else None, add_re=lv, form=TREE_VARIADIC, product=prod)
+            btags = {"acT": P, "bdT": P, "adT": P, "bcT": P, "acbdT": S, "adbcT": S}       # quantized BasicComplexMul products (the defaults keep full precision)
+            plan = ops.make_cgemul_plan(t, t, t, t, lv[-1], lv[-1], M, N, K, tf_tags=tags if prod == "tf" else btags, add_re=lv, form=TREE_VARIADIC, product=prod)
             words = 2 * (M * K + K * N + M * N)
             batch = max(64, min(1 << 18, (1 << 27) // words))
             A = torch.empty(batch * M * K * 2, dtype=torch.int32, device="cuda"); B = torch.empty(batch * K * N * 2, dtype=torch.int32, device="cuda")
