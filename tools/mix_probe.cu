@@ -55,6 +55,48 @@ template <int CH, int ORDER> __global__ void __launch_bounds__(256, 2) k_mix(uin
     out[blockIdx.x * 256 + threadIdx.x] = r;
 }
 
+// Variant B: group sums on the FP pipe.  Products with alternating +-C magic constants make F0 + F1 exact, so a group of
+// four is 4 FFMA + 3 FADD and ONE float->int conversion with the level-1 rounding built in (cvt.rpi: ceil(s / 2)); the
+// level-2 node is one IADD3 (two registers + immediate) per two groups, the levels above cost SHF + LEA.HI per merge
+// (7 merges per 16 groups).
+#define FFMAN(d, a, b) asm volatile("fma.rn.f32 %0, %1, %2, 0fCF400000;" : "=r"(d) : "r"(a), "r"(b))
+#define FADD(d, a, b) asm volatile("add.rn.f32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b))
+#define F2ICEIL(d, a) asm volatile("cvt.rpi.s32.f32 %0, %1;" : "=r"(d) : "r"(a))
+template <int CH> __global__ void __launch_bounds__(256, 2) k_mix_fp(uint32_t *out, const uint32_t *in, int iters)
+{
+    uint32_t a[4], a0[4], b[CH], acc[CH], half[CH];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = a0[i] = in[threadIdx.x + i * 256];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) { b[c] = in[1024 + threadIdx.x + c * 256]; acc[c] = 0; half[c] = 0; }
+    for (int it = 0; it < iters; it += 2) {                 // two groups per chain and trip: one level-2 node
+        uint32_t v[2][CH];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            uint32_t p[CH][4], t01[CH], t23[CH], t[CH];
+#pragma unroll
+            for (int c = 0; c < CH; ++c) { FFMA(p[c][0], a[0], b[c]); FFMAN(p[c][1], a[1], b[c]); FFMA(p[c][2], a[2], b[c]); FFMAN(p[c][3], a[3], b[c]); }
+#pragma unroll
+            for (int c = 0; c < CH; ++c) { FADD(t01[c], p[c][0], p[c][1]); FADD(t23[c], p[c][2], p[c][3]); }
+#pragma unroll
+            for (int c = 0; c < CH; ++c) { FADD(t[c], t01[c], t23[c]); F2ICEIL(v[g][c], t[c]); }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a[k] = a0[k] ^ ((uint32_t)(it + g) << (8 + k));
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            uint32_t s2, tt;
+            ADD2I(s2, v[0][c], v[1][c]);                    // level-2 pre-shift sum with its bias
+            SHR1(tt, half[c]); SHRADD(acc[c], s2, tt);      // one merge above (7 per 8 level-2 nodes in the kernel)
+            half[c] = acc[c];
+        }
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) r ^= acc[c];
+    out[blockIdx.x * 256 + threadIdx.x] = r;
+}
+
 int main()
 {
     int sms = 0, khz = 0;
@@ -77,5 +119,6 @@ int main()
     };
     run("8 chains, by kind", k_mix<8, 0>, 8); run("8 chains, interleaved", k_mix<8, 1>, 8);
     run("16 chains, by kind", k_mix<16, 0>, 16); run("16 chains, interleaved", k_mix<16, 1>, 16);
+    run("FP group sums + F2I, 8 chains", k_mix_fp<8>, 8); run("FP group sums + F2I, 16 chains", k_mix_fp<16>, 16);
     return cudaDeviceSynchronize() != cudaSuccess;
 }

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Small driver for ncu captures: runs one workload's hot kernel a few times on device-resident data.
-usage: python tools/prof.py c2|c3|c4|c5 [iters]"""
+usage: python tools/prof.py c2|c3|c4|c5|cg [iters]"""
 import os
 import sys
 
@@ -39,6 +39,15 @@ elif w == "c4":
     ops.synth_fill(H, -(1 << 14), (1 << 14) - 1, 1, 0); ops.synth_fill(xv, -(1 << 14), (1 << 14) - 1, 1, 1)
     y = torch.empty(batch * 512, dtype=torch.int32, device=dev)
     fn = lambda: ops.Qcgemul(y, H, xv, plan, batch=batch)
+elif w == "cg":                                   # batched complex 64x64x64 TFComplexMul GEMM (register-tile kernel, FP products)
+    t = QType(3, 12); P = QType(6, 12); S = QType(7, 12)
+    tags = {"abT": QType(4, 12), "cdT": QType(4, 11), "abcT": P, "cdbT": P, "badT": P, "ABT": S, "BCT": S}
+    lv = [QType(8 + l, 12 - l, True, RND_CONV, SAT_TCPL) for l in range(6)]
+    plan = ops.make_cgemul_plan(t, t, t, t, lv[-1], lv[-1], 64, 64, 64, tf_tags=tags, add_re=lv, form=TREE_VARIADIC)
+    batch = 4096
+    A = torch.empty(batch * 8192, dtype=torch.int32, device=dev); B = torch.empty_like(A); Cd = torch.empty_like(A)
+    ops.synth_fill(A, -(1 << 14), (1 << 14) - 1, 1, 0); ops.synth_fill(B, -(1 << 14), (1 << 14) - 1, 1, 1)
+    fn = lambda: ops.Qcgemul(Cd, A, B, plan, batch=batch)
 else:
     M = 8192
     a = QType(7, 0); acc = QType(30, 0)
