@@ -775,9 +775,25 @@ def run_secondary(args, embed=False):
         except Exception:
             best = 0.0
         nominal = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
-        roof = {"bound": "tensor", "achieved": value / world, "peak": best if best > 0 else nominal, "unit": "TOP/s", "scope": "per GPU",
-                "peak_source": "torch._int_mm (cuBLASLt int8) 8192^3 on this box" if best > 0 else "2 x measured bf16 (nominal i8:bf16 ratio)",
-                "peak_2x_bf16": nominal}
+        # the library GEMM under the SAME timing discipline as `value` (>= 1.2 s of back-to-back calls: both kernels run into the
+        # power cap there), and the library GEMM fed from the reference's int32 words (torch narrowing passes + cuBLASLt)
+        sus = sus_conv = 0.0
+        try:
+            ms_lib, _, clocks_lib = timed(lambda: torch._int_mm(A8, B8))
+            sus = ops_total / (ms_lib * 1e-3) / 1e12
+            ms_conv, _, _ = timed(lambda: torch._int_mm(A.view(Mm, Kk).to(torch.int8), B.view(Nn, Kk).to(torch.int8).t()))
+            sus_conv = ops_total / (ms_conv * 1e-3) / 1e12
+        except Exception:
+            pass
+        peak = sus if sus > 0 else (best if best > 0 else nominal)
+        roof = {"bound": "tensor", "achieved": value / world, "peak": peak, "unit": "TOP/s", "scope": "per GPU",
+                "peak_source": ("torch._int_mm (cuBLASLt int8, int8 operands) 8192^3 on this box, sustained: the same back-to-back timing loop as `value`" if sus > 0 else
+                                "torch._int_mm (cuBLASLt int8) 8192^3 on this box, best single call" if best > 0 else "2 x measured bf16 (nominal i8:bf16 ratio)"),
+                "peak_burst": best, "peak_burst_note": "best of 5 single cuBLASLt calls from idle (boost clocks, no power cap)",
+                "library_from_int32_words": sus_conv, "library_from_int32_words_note": "torch int32 -> int8 narrowing of both operands + cuBLASLt, same loop: "
+                "the like-for-like library figure for the reference's word format", "peak_2x_bf16": nominal}
+        if sus > 0:
+            roof["peak_clocks"] = clocks_lib
         # the same GEMM with the operands handed over as int8 words, K contiguous: the tensor maps sit on the caller's buffers,
         # no pack kernel runs (one launch per call)
         plan8 = ops.make_gemul_plan(a, a, acc, Mm, Nn, Kk, mul=QType(15, 0), add=[acc], trans_a=True, word_bytes=(1, 1, 0))

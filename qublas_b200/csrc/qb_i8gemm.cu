@@ -123,6 +123,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_i8(int m, int n)
     return (2u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+__device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d)
+{
+    return (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) | ((uint32_t)d << 24);
+}
+
 struct I8Params {
     uint32_t M, N, K;             // M, N: real extents of C (leading dimension M, stores are guarded); K: padded to a multiple of BK
     uint32_t tiles_m, tiles_n;
@@ -330,9 +335,115 @@ __device__ __forceinline__ void bar_wait_cluster(uint64_t *b, uint32_t parity)
         "}\n" ::"r"(s32(b)), "r"(parity) : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1)
-k_i8gemm_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, void *__restrict__ C,
-              const __grid_constant__ I8Params P, const __grid_constant__ QStage outq)
+// ---------------------------------------------------------------------------------------------
+// Fused operand narrowing (FUSE = true, round 2).  The reference keeps W <= 32 raws in int32 words; the tensor maps want
+// int8.  Instead of two pack launches in front of the GEMM (HBM-bound, 2 x 48 us against 337 us of MMA time at 8192^3),
+// eight extra "packer" warps per CTA narrow the words WHILE the tensor cores run: a warp claims a slice (8 operand rows
+// x 512 k = 16 KiB of words) from a global counter, streams it (16-byte loads, 16-byte stores), and bumps the flag of its unit
+// (256 rows x 512 k of the rows of one tile pair / the columns of one n-tile); the TMA producer polls the two flags
+// of the k-chunk it is about to load (acquire + cross-proxy fence: generic-proxy stores, async-proxy reads).  Packers never
+// wait on anything and all CTAs are co-resident (grid <= SM count), so every flag is reached.  Units are claimed in the
+// order the rasterisation needs them: the first wave's panels k-chunk by k-chunk, then the remaining B panels, then the
+// remaining A panels.
+// ---------------------------------------------------------------------------------------------
+static constexpr int PACK_WARPS = 8;
+static constexpr int I8_THREADS_FUSED = I8_THREADS + 32 * PACK_WARPS;
+static constexpr uint32_t PK_ROWS = 256;
+
+struct I8Fuse {
+    const int32_t *srcA, *srcB;   // raw words, K contiguous per operand row; nullptr: that operand is not packed by this kernel
+    int8_t *dstA, *dstB;          // int8 staging the tensor maps sit on
+    uint32_t *sync;               // [0] claim counter, [1 ..] flags of the A units (panel * nkc + kc), then of the B units
+    uint32_t pk_k, slice_rows, slices;   // k extent of a unit (a multiple of BK), operand rows per claimed slice, slices per unit
+    uint32_t nkc;                 // k-chunks of pk_k
+    uint32_t panels_a, panels_b;  // units per k-chunk (0 when the operand is not packed here)
+    uint32_t first_a, first_b;    // panels the first wave of tile pairs touches
+    uint32_t group_a, group_b;    // panels that become live together afterwards: a row group of A, the n-tiles one more wave reaches
+    unsigned long long *stats;    // QB200_I8_STATS=1: [0] first CTA start, [1] last packer done, [2] ns the producers waited for flags, [3] last CTA done (globaltimer)
+};
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
+__device__ __forceinline__ void wait_unit(const uint32_t *flag, uint32_t target, unsigned long long *stats)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v >= target) { asm volatile("fence.proxy.async.global;" ::: "memory"); return; }
+    const unsigned long long t0 = stats ? gtimer() : 0;
+    for (;;) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v >= target) break;
+        __nanosleep(32);
+    }
+    asm volatile("fence.proxy.async.global;" ::: "memory");        // the bytes were written through the generic proxy, TMA reads them through the async proxy
+    if (stats) {
+        const unsigned long long t1 = gtimer();
+        atomicAdd(stats + 2, t1 - t0);
+        const unsigned long long idx = atomicAdd(stats + 4, 1ull);
+        if (idx < 4096) { stats[8 + 2 * idx] = t0; stats[9 + 2 * idx] = t1 - t0; }
+    }
+}
+
+__device__ __forceinline__ void packer_warp(const I8Fuse &F, uint32_t K, int lane)
+{
+    const uint32_t units = (F.panels_a + F.panels_b) * F.nkc, total = units * F.slices;
+    const uint32_t first = F.first_a + F.first_b, n0 = first * F.nkc, n1 = n0 + (F.panels_b - F.first_b) * F.nkc;
+    uint32_t s = 0, s_next = 0;
+    if (lane == 0) s = atomicAdd(F.sync, 1u);
+    s = __shfl_sync(0xffffffffu, s, 0);
+    while (s < total) {
+        if (lane == 0) s_next = atomicAdd(F.sync, 1u);         // claimed now, looked at after this slice: the round trip hides behind the copy
+        const uint32_t u = s / F.slices, slice = s - u * F.slices;
+        // units in the order the rasterisation needs them, k-chunk-major inside every group of panels that becomes live together
+        bool is_a; uint32_t panel, kc;
+        if (u < n0) {                                   // the first wave's A and B panels
+            kc = u / first; const uint32_t j = u - kc * first;
+            is_a = j < F.first_a; panel = is_a ? j : j - F.first_a;
+        } else {
+            is_a = u >= n1;                             // then the B panels wave by wave, then the A panels row group by row group
+            const uint32_t v = is_a ? u - n1 : u - n0, per = is_a ? F.group_a : F.group_b, lim = is_a ? F.panels_a : F.panels_b;
+            const uint32_t g = v / (per * F.nkc), base = (is_a ? F.first_a : F.first_b) + g * per;
+            const uint32_t cnt = (lim - base) < per ? (lim - base) : per, w = v - g * per * F.nkc;
+            kc = w / cnt; panel = base + (w - kc * cnt);
+        }
+        const uint32_t k0 = kc * F.pk_k, klen = (K - k0) < F.pk_k ? (K - k0) : F.pk_k, items = klen / 16;      // K % 128 == 0: items % 8 == 0
+        const uint64_t row0 = (uint64_t)panel * PK_ROWS + slice * F.slice_rows;
+        const int32_t *src = (is_a ? F.srcA : F.srcB) + row0 * K + k0;
+        int8_t *dst = (is_a ? F.dstA : F.dstB) + row0 * K + k0;
+        const uint32_t n_it = F.slice_rows * items;                // 16-word items in this slice, a multiple of 32
+        // four items per lane and trip: sixteen 16-byte loads in flight before the first store
+        for (uint32_t base = lane; base < n_it; base += 128) {
+            int4 v[4][4];
+            uint32_t r[4], t[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t i = base + 32 * j;
+                r[j] = i / items; t[j] = i - r[j] * items;
+                if (i < n_it) {
+                    const int4 *p = (const int4 *)(src + (uint64_t)r[j] * K) + 4 * t[j];
+                    v[j][0] = __ldcs(p); v[j][1] = __ldcs(p + 1); v[j][2] = __ldcs(p + 2); v[j][3] = __ldcs(p + 3);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (base + 32 * j < n_it)
+                    *((uint4 *)(dst + (uint64_t)r[j] * K) + t[j]) =
+                        make_uint4(pack4(v[j][0].x, v[j][0].y, v[j][0].z, v[j][0].w), pack4(v[j][1].x, v[j][1].y, v[j][1].z, v[j][1].w),
+                                   pack4(v[j][2].x, v[j][2].y, v[j][2].z, v[j][2].w), pack4(v[j][3].x, v[j][3].y, v[j][3].z, v[j][3].w));
+        }
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+            uint32_t *flag = F.sync + 1 + (is_a ? 0u : F.panels_a * F.nkc) + panel * F.nkc + kc;
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(flag) : "memory");
+        }
+        s = __shfl_sync(0xffffffffu, s_next, 0);
+    }
+}
+
+template <bool FUSE>
+__device__ __forceinline__ void i8gemm_pair_body(const CUtensorMap &mapA, const CUtensorMap &mapB, void *__restrict__ C, const I8Params &P,
+                                                 const QStage &outq, const I8Fuse &F)
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -379,6 +490,13 @@ k_i8gemm_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             for (uint32_t t = worker; t < nwork; t += n_workers) {
                 uint32_t row, tn; pair_coords(t, row, tn);
                 for (uint32_t kb = 0; kb < nkb; kb++) {
+                    if constexpr (FUSE) {
+                        if (kb % (F.pk_k / BK) == 0) {                                    // a new k-chunk: has it been narrowed yet?
+                            const uint32_t kc = kb / (F.pk_k / BK);
+                            if (F.panels_a) wait_unit(F.sync + 1 + row * F.nkc + kc, F.slices, F.stats);
+                            if (F.panels_b) wait_unit(F.sync + 1 + F.panels_a * F.nkc + tn * F.nkc + kc, F.slices, F.stats);
+                        }
+                    }
                     bar_wait(&empty[stage], phase ^ 1);                                   // released by the pair MMA's multicast commit
                     if (rank == 0) bar_expect_tx(&full[stage], 2 * P2_STAGE_BYTES);       // both CTAs' bytes land on rank 0's barrier
                     tma_load_2d_pair(sA + stage * P2_A_STAGE, &mapA, &full[stage], (int)(kb * BK), (int)((2 * row + rank) * BM));
@@ -411,6 +529,10 @@ k_i8gemm_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
+    } else if (FUSE && warp >= 6) {
+        if (F.stats && lane == 0) atomicMin(F.stats, gtimer());
+        packer_warp(F, P.K, lane);                             // ===== packer warps 6..13 =====
+        if (F.stats && lane == 0) atomicMax(F.stats + 1, gtimer());
     } else {
         // ===== epilogue warps 2..5 of both CTAs: my 128 rows of the pair =====
         const uint32_t quad = warp & 3;
@@ -445,6 +567,21 @@ k_i8gemm_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     __syncthreads();
     cluster_sync_all();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    if constexpr (FUSE) { if (F.stats && threadIdx.x == 0) atomicMax(F.stats + 3, gtimer()); }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1)
+k_i8gemm_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, void *__restrict__ C,
+              const __grid_constant__ I8Params P, const __grid_constant__ QStage outq)
+{
+    i8gemm_pair_body<false>(mapA, mapB, C, P, outq, I8Fuse{});
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS_FUSED, 1)
+k_i8gemm_pair_fused(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, void *__restrict__ C,
+                    const __grid_constant__ I8Params P, const __grid_constant__ QStage outq, const __grid_constant__ I8Fuse F)
+{
+    i8gemm_pair_body<true>(mapA, mapB, C, P, outq, F);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -475,10 +612,6 @@ __global__ void k_pack_i8_transpose(const W *__restrict__ src, int8_t *__restric
 }
 
 // int32 words (the reference's storage for W <= 32), streamed at HBM rate: 16-byte loads, 128-byte row stores.
-__device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d)
-{
-    return (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) | ((uint32_t)d << 24);
-}
 // straight: 4 independent 16-byte loads per thread, one 16-byte store; n % 16 == 0
 __global__ void __launch_bounds__(256)
 k_pack_i8_straight_w4(const int4 *__restrict__ src, uint4 *__restrict__ dst, uint64_t n16)
@@ -631,18 +764,57 @@ bool i8gemm_zero_copy(const void *ptr, int wb, bool k_major, uint32_t K)
 
 // One instance.  A, B: device pointers to raw ABI words (a_wb / b_wb bytes each), column-major as in the plan.
 // Ap / Bp: int8 staging of Mp x Kp and Np x Kp bytes (i8gemm_padded_dims); may be NULL for an operand that is read in place.
+// Which kernel variant runs: QB200_I8_VARIANT = 0 single-CTA kernel, 1 multicast clusters, 2 pair MMA (cta_group::2, default)
+static int i8_variant()
+{
+    static int variant = -1;
+    if (variant < 0) { const char *e = getenv("QB200_I8_VARIANT"); variant = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2; }
+    return variant;
+}
+// Words of the flag buffer the fused narrowing needs (0: this shape / these operands are packed by separate launches).
+// An operand is narrowed inside the GEMM kernel when it holds int32 words with K contiguous on a tile-multiple shape.
+// geometry of the fused narrowing: k extent of a unit and operand rows per claimed slice (QB200_I8_PK="k,rows": experiments)
+static uint32_t g_pk_k = 0, g_pk_rows = 0;
+static void pk_init()
+{
+    if (g_pk_k) return;
+    uint32_t k = 1024, r = 8;
+    if (const char *e = getenv("QB200_I8_PK")) { unsigned a = 0, b = 0; if (sscanf(e, "%u,%u", &a, &b) == 2 && a >= BK && a % BK == 0 && b && PK_ROWS % b == 0) { k = a; r = b; } }
+    g_pk_rows = r; g_pk_k = k;
+}
+static uint32_t pk_k() { pk_init(); return g_pk_k; }
+static uint32_t pk_rows() { pk_init(); return g_pk_rows; }
+static bool fusable(const void *p, int wb, bool k_major, bool zero_copy) { return !zero_copy && wb == 4 && k_major && (((uintptr_t)p) & 15) == 0; }
+size_t i8gemm_sync_words(const void *A, const void *B, uint32_t M, uint32_t N, uint32_t K, bool trans_a, bool trans_b, int a_wb, int b_wb)
+{
+    static int off = -1;                           // QB200_I8_NO_FUSE=1: always pack with separate launches (experiments)
+    if (off < 0) { const char *e = getenv("QB200_I8_NO_FUSE"); off = (e && e[0] == '1') ? 1 : 0; }
+    if (off || i8_variant() != 2 || M % (2 * BM) || N % BN || K % BK) return 0;
+    const bool fa = fusable(A, a_wb, trans_a, i8gemm_zero_copy(A, a_wb, trans_a, K)), fb = fusable(B, b_wb, !trans_b, i8gemm_zero_copy(B, b_wb, !trans_b, K));
+    if (!fa && !fb) return 0;
+    const uint64_t nkc = (K + pk_k() - 1) / pk_k(), units = ((fa ? M / PK_ROWS : 0) + (fb ? N / PK_ROWS : 0)) * nkc;
+    if (units > (1u << 20)) return 0;
+    return (size_t)units + 1;
+}
+
 int i8gemm_run(const void *A, const void *B, void *C, uint32_t M, uint32_t N, uint32_t K, bool trans_a, bool trans_b, int a_wb,
-               int b_wb, int c_wb, const QStage &outq, int8_t *Ap, int8_t *Bp, cudaStream_t s, const char **err)
+               int b_wb, int c_wb, const QStage &outq, int8_t *Ap, int8_t *Bp, uint32_t *sync, cudaStream_t s, const char **err)
 {
     uint32_t Mp, Np, Kp;
     i8gemm_padded_dims(M, N, K, &Mp, &Np, &Kp);
     const bool ragged = Mp != M || Np != N || Kp != K;
-    const bool zc_a = i8gemm_zero_copy(A, a_wb, trans_a, K), zc_b = i8gemm_zero_copy(B, b_wb, !trans_b, K);
+    bool zc_a = i8gemm_zero_copy(A, a_wb, trans_a, K), zc_b = i8gemm_zero_copy(B, b_wb, !trans_b, K);
     if ((!zc_a && !Ap) || (!zc_b && !Bp)) { *err = "missing int8 staging buffer"; return -1; }
     // A operand must become M rows x K (K contiguous).  Stored M x K column-major (M contiguous) unless trans_a (K x M, K contiguous).
     const bool a_tr = !trans_a;
     // B operand must become N rows x K.  Stored K x N column-major (K contiguous) unless trans_b (N x K, N contiguous).
     const bool b_tr = trans_b;
+    // operands narrowed inside the GEMM kernel (k_i8gemm_pair_fused): no pack launch for them
+    const size_t sync_words = sync ? i8gemm_sync_words(A, B, M, N, K, trans_a, trans_b, a_wb, b_wb) : 0;
+    const bool fuse_a = sync_words && fusable(A, a_wb, trans_a, zc_a), fuse_b = sync_words && fusable(B, b_wb, !trans_b, zc_b);
+    const bool real_zc_a = zc_a, real_zc_b = zc_b;
+    if (fuse_a) zc_a = true;                       // skips the separate pack below; the tensor map still sits on the staging buffer
+    if (fuse_b) zc_b = true;
     if (ragged) {
         if (!zc_a) switch (a_wb) {
         case 1: pack_padded<int8_t>(A, Ap, M, K, Mp, Kp, a_tr, s); break;
@@ -672,8 +844,8 @@ int i8gemm_run(const void *A, const void *B, void *C, uint32_t M, uint32_t N, ui
         default: pack_operand<int64_t>(B, Bp, b_r, b_c, b_tr, s); break;
         }
     }
-    static int variant = -1;                       // QB200_I8_VARIANT: 0 single-CTA kernel, 1 multicast clusters, 2 pair MMA (cta_group::2)
-    if (variant < 0) { const char *e = getenv("QB200_I8_VARIANT"); variant = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2; }
+    zc_a = real_zc_a; zc_b = real_zc_b;
+    const int variant = i8_variant();
     const bool pair = variant == 2 && (Mp / BM) % 2 == 0;
     const bool mc = (variant == 1 || pair) && (Mp / BM) % 2 == 0;
     CUtensorMap mapA, mapB;
@@ -686,7 +858,8 @@ int i8gemm_run(const void *A, const void *B, void *C, uint32_t M, uint32_t N, ui
     if (!attr_set[dev & 63]) {
         if (cudaFuncSetAttribute(k_i8gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(k_i8gemm_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(k_i8gemm_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES) != cudaSuccess) { *err = "cannot raise dynamic smem"; return -1; }
+            cudaFuncSetAttribute(k_i8gemm_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(k_i8gemm_pair_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES) != cudaSuccess) { *err = "cannot raise dynamic smem"; return -1; }
         attr_set[dev & 63] = true;
     }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -696,7 +869,47 @@ int i8gemm_run(const void *A, const void *B, void *C, uint32_t M, uint32_t N, ui
     if (mc) {
         P.group_m = 8;                                                     // 8 tile pairs = 16 m-tiles per group
         const uint32_t npairs = ntiles / 2, clusters = npairs < (uint32_t)(sms / 2) ? npairs : (uint32_t)(sms / 2);
-        if (pair) k_i8gemm_pair<<<clusters * 2, I8_THREADS, P2_SMEM_BYTES, s>>>(mapA, mapB, C, P, outq);
+        if (pair && (fuse_a || fuse_b)) {
+            I8Fuse F;
+            F.srcA = fuse_a ? (const int32_t *)A : nullptr; F.srcB = fuse_b ? (const int32_t *)B : nullptr;
+            F.dstA = Ap; F.dstB = Bp; F.sync = sync;
+            F.pk_k = pk_k(); F.slice_rows = pk_rows(); F.slices = PK_ROWS / F.slice_rows;
+            F.nkc = (K + F.pk_k - 1) / F.pk_k;
+            F.panels_a = fuse_a ? M / PK_ROWS : 0; F.panels_b = fuse_b ? N / PK_ROWS : 0;
+            const uint32_t rows = P.tiles_m / 2, gm = rows < P.group_m ? rows : P.group_m;
+            const uint32_t wave_n = (clusters + gm - 1) / gm + 1;                  // n-tiles the first wave of tile pairs reaches
+            F.first_a = fuse_a ? gm : 0;
+            F.first_b = fuse_b ? (wave_n < P.tiles_n ? wave_n : P.tiles_n) : 0;
+            F.group_a = gm; F.group_b = wave_n > 1 ? wave_n - 1 : 1;
+            if (cudaMemsetAsync(sync, 0, sync_words * sizeof(uint32_t), s) != cudaSuccess) { *err = "cudaMemsetAsync failed"; return -1; }
+            static int want_stats = -1;            // QB200_I8_STATS=1: per-call timeline of the fused kernel on stderr (synchronises; experiments only)
+            if (want_stats < 0) { const char *e = getenv("QB200_I8_STATS"); want_stats = (e && e[0] == '1') ? 1 : 0; }
+            F.stats = nullptr;
+            if (want_stats) {
+                const unsigned long long init[8] = { ~0ull, 0, 0, 0, 0, 0, 0, 0 };
+                if (cudaMalloc(&F.stats, (8 + 2 * 4096) * sizeof(unsigned long long)) != cudaSuccess) { *err = "cudaMalloc failed"; return -1; }
+                cudaMemcpyAsync(F.stats, init, sizeof init, cudaMemcpyHostToDevice, s);
+            }
+            k_i8gemm_pair_fused<<<clusters * 2, I8_THREADS_FUSED, P2_SMEM_BYTES, s>>>(mapA, mapB, C, P, outq, F);
+            if (want_stats) {
+                static unsigned long long st[8 + 2 * 4096];
+                cudaMemcpyAsync(st, F.stats, sizeof st, cudaMemcpyDeviceToHost, s);
+                cudaStreamSynchronize(s);
+                cudaFree(F.stats);
+                {   // histogram of the waits over the kernel's timeline (20 us bins): when do the producers starve?
+                    double bins[64] = { 0 }; unsigned cnt[64] = { 0 };
+                    const unsigned long long n = st[4] < 4096 ? st[4] : 4096;
+                    for (unsigned long long i = 0; i < n; i++) {
+                        unsigned b = (unsigned)((st[8 + 2 * i] - st[0]) / 20000); if (b > 63) b = 63;
+                        bins[b] += st[9 + 2 * i] * 1e-3; cnt[b]++;
+                    }
+                    for (int b = 0; b < 64; b++) if (cnt[b]) fprintf(stderr, "  waits starting in [%d, %d) us: %u, %.1f us in total\n", b * 20, b * 20 + 20, cnt[b], bins[b]);
+                }
+                fprintf(stderr, "k_i8gemm_pair_fused: packers done after %.1f us, kernel %.1f us, producers waited %.1f us in total (%u producers)\n",
+                        (st[1] - st[0]) * 1e-3, (st[3] - st[0]) * 1e-3, st[2] * 1e-3, clusters * 2);
+            }
+        }
+        else if (pair) k_i8gemm_pair<<<clusters * 2, I8_THREADS, P2_SMEM_BYTES, s>>>(mapA, mapB, C, P, outq);
         else      k_i8gemm_mc<<<clusters * 2, I8_THREADS, SMEM_BYTES, s>>>(mapA, mapB, C, P, outq);
     } else {
         const unsigned grid = ntiles < (uint32_t)sms ? ntiles : (unsigned)sms;

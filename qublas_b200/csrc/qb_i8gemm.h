@@ -8,6 +8,8 @@ namespace qb {
 bool i8gemm_shape_ok(uint32_t M, uint32_t N, uint32_t K);
 void i8gemm_padded_dims(uint32_t M, uint32_t N, uint32_t K, uint32_t *Mp, uint32_t *Np, uint32_t *Kp);   // staging: Mp x Kp and Np x Kp bytes
 bool i8gemm_zero_copy(const void *ptr, int word_bytes, bool k_major, uint32_t K);   // operand read in place, no pack launch
+// words of the flag buffer of the fused operand narrowing (k_i8gemm_pair_fused); 0 = separate pack launches
+size_t i8gemm_sync_words(const void *A, const void *B, uint32_t M, uint32_t N, uint32_t K, bool trans_a, bool trans_b, int a_wb, int b_wb);
 int  i8gemm_run(const void *A, const void *B, void *C, uint32_t M, uint32_t N, uint32_t K, bool trans_a, bool trans_b, int a_wb,
-                int b_wb, int c_wb, const QStage &outq, int8_t *Ap, int8_t *Bp, cudaStream_t s, const char **err);
+                int b_wb, int c_wb, const QStage &outq, int8_t *Ap, int8_t *Bp, uint32_t *sync, cudaStream_t s, const char **err);
 }

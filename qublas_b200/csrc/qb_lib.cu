@@ -11,6 +11,7 @@
 #include <thread>
 #include <unordered_map>
 #include <vector>
+#include <algorithm>
 
 #include "../../include/qb200.h"
 #include "qb_plan.h"
@@ -637,11 +638,18 @@ extern "C" int qb200_gemul_batched(const qb_gemul_plan *plan, const void *A, con
         }
         Ap = Bp = nullptr;
         if ((need_a && (rc = cx.alloc(&Ap, (size_t)Mp * Kp))) || (need_b && (rc = cx.alloc(&Bp, (size_t)Np * Kp)))) return rc;
+        // flags of the operand narrowing fused into the GEMM kernel (int32 words, K contiguous, tile-multiple shapes)
+        size_t sync_words = 0;
+        for (uint64_t i = 0; i < batch; i++)
+            sync_words = std::max(sync_words, i8gemm_sync_words((const char *)dA + i * plan->stride_a * gp.a_wb, (const char *)dB + i * plan->stride_b * gp.b_wb,
+                                                                plan->M, plan->N, plan->K, plan->trans_a, plan->trans_b, gp.a_wb, gp.b_wb));
+        void *sync = nullptr;
+        if (sync_words && (rc = cx.alloc(&sync, sync_words * sizeof(uint32_t)))) return rc;
         for (uint64_t i = 0; i < batch; i++) {
             const char *err = "";
             if (i8gemm_run((const char *)dA + i * plan->stride_a * gp.a_wb, (const char *)dB + i * plan->stride_b * gp.b_wb,
                            (char *)dC + i * plan->stride_c * gp.c_wb, plan->M, plan->N, plan->K, plan->trans_a, plan->trans_b, gp.a_wb, gp.b_wb,
-                           gp.c_wb, gp.out, (int8_t *)Ap, (int8_t *)Bp, cx.stream, &err))
+                           gp.c_wb, gp.out, (int8_t *)Ap, (int8_t *)Bp, (uint32_t *)sync, cx.stream, &err))
                 return fail(QB_ECUDA, std::string("k_i8gemm: ") + err);
         }
         if ((rc = cx.out_done(C, bytes_c, dC))) return rc;

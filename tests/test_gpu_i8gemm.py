@@ -127,7 +127,8 @@ def test_i8_operands_handed_over_k_major_are_read_in_place(M, N, K):
     lib.qb200_launch_count_reset()
     ops.Qgemul(C32, dA.to(torch.int32), dB.to(torch.int32), plan32)
     torch.cuda.synchronize()
-    assert lib.qb200_launch_count() == 3 and torch.equal(Cd, C32)
+    fused = M % 256 == 0 and N % 256 == 0 and K % 128 == 0       # int32 words, K contiguous: narrowed inside the GEMM kernel
+    assert lib.qb200_launch_count() == (1 if fused else 3) and torch.equal(Cd, C32)
     if M * N * K <= 1 << 26:
         assert np.array_equal(Cd.cpu().numpy(), oracle.gemul_batched(plan8, A, B, 1))
     else:
@@ -139,3 +140,35 @@ def test_i8_operands_handed_over_k_major_are_read_in_place(M, N, K):
     C3 = torch.empty_like(Cd)
     ops.Qgemul(C3, bufA[1:1 + M * K], dB, plan8)
     assert torch.equal(C3, Cd)
+
+
+@pytest.mark.parametrize("M,N,K,ta", [(256, 256, 128, True), (512, 768, 2176, True), (1024, 512, 1024, False), (4096, 2048, 3072, True)])
+def test_i8_int32_words_are_narrowed_inside_the_gemm_kernel(M, N, K, ta):
+    """VERDICT r1 task 5: the reference's int32 words with K contiguous are narrowed to int8 by packer warps of the GEMM
+    kernel while the tensor cores run (k_i8gemm_pair_fused): ONE launch when both operands qualify (A stored K x M), two
+    when A is stored M x K and goes through the transposing pack.  K = 2176 ends in a partial k-chunk; the call is repeated
+    (the flags are cleared per call) and also run on a batch of two instances."""
+    rng = np.random.default_rng(M + 5 * N + K)
+    a = QType(7, 0); acc = QType(30, 0)
+    plan = ops.make_gemul_plan(a, a, acc, M, N, K, mul=QType(15, 0), add=[acc], trans_a=ta)
+    assert ops.plan_info_gemul(plan).tensor_core == 1
+    nb = 2
+    A = rng.integers(-128, 128, size=nb * M * K).astype(np.int32); B = rng.integers(-128, 128, size=nb * K * N).astype(np.int32)
+    A[:9] = -128; B[:9] = -128
+    dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    Cd = torch.empty(nb * M * N, dtype=torch.int32, device="cuda")
+    lib = abi.load()
+    ops.Qgemul(Cd[:M * N], dA[:M * K], dB[:K * N], plan)
+    torch.cuda.synchronize(); lib.qb200_launch_count_reset()
+    for _ in range(3):
+        Cd.zero_()
+        ops.Qgemul(Cd, dA, dB, plan, batch=nb)
+    torch.cuda.synchronize()
+    assert lib.qb200_launch_count() == 3 * nb * (1 if ta else 2)
+    for i in range(nb):
+        Ai, Bi = dA[i * M * K:(i + 1) * M * K], dB[i * K * N:(i + 1) * K * N]
+        Am = (Ai.view(M, K) if ta else Ai.view(K, M).t()).double()
+        ref = (Am @ Bi.view(N, K).t().double()).t().contiguous().view(-1)           # exact: every partial sum < 2^53
+        assert torch.equal(Cd[i * M * N:(i + 1) * M * N].double(), ref)
+    if M * N * K <= 1 << 25:
+        assert np.array_equal(Cd[:M * N].cpu().numpy(), oracle.gemul_batched(plan, A[:M * K], B[:K * N], 1))

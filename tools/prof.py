@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Small driver for ncu captures: runs one workload's hot kernel a few times on device-resident data.
-usage: python tools/prof.py c2|c3|c4|c5|cg [iters]"""
+usage: python tools/prof.py c2|c3|c4|c5|c5t|cg [iters]"""
 import os
 import sys
 
@@ -51,7 +51,7 @@ elif w == "cg":                                   # batched complex 64x64x64 TFC
 else:
     M = 8192
     a = QType(7, 0); acc = QType(30, 0)
-    plan = ops.make_gemul_plan(a, a, acc, M, M, M, mul=QType(15, 0), add=[acc])
+    plan = ops.make_gemul_plan(a, a, acc, M, M, M, mul=QType(15, 0), add=[acc], trans_a=(w == "c5t"))     # c5t: A stored K x M as in bench.py
     A = torch.empty(M * M, dtype=torch.int32, device=dev); B = torch.empty_like(A); Cd = torch.empty_like(A)
     ops.synth_fill(A, -128, 127, 1, 0); ops.synth_fill(B, -128, 127, 1, 1)
     fn = lambda: ops.Qgemul(Cd, A, B, plan)
