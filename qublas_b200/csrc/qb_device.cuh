@@ -222,6 +222,44 @@ template <int S, bool CT> QB_DEV int fp_mul_apply(float a, float b, const QStage
     return bits;
 }
 
+// Saturation by operand substitution (round 2).  When the ONLY product that Qmul's SAT clamp can touch is min x min of two
+// full-range signed operands (a = -2^pa, b = -2^pb, RND::CONV, shift S <= pa, pb; the product quantizes to hi + 1 exactly),
+// replacing every operand that equals its type's minimum by
+//     a' = -(2^pa - 2^(S-pb-1)),   b' = -(2^pb - 2^(S-pa-1))
+// in the float copy makes the plain FMA deliver the CLAMPED result, and no clamp instruction is left:
+//   * a' * b' / 2^S = hi + 1 - 1 + 2^(S-pa-pb-2): rounds to hi, the saturated value;
+//   * a' * y / 2^S for any other y (|y| <= 2^pb - 1) = -2^(pa-S) y + y / 2^(pb+1): an integer plus less than half, so it
+//     rounds to -2^(pa-S) y, the exact (unclamped, untouched) product quantized; likewise x * b';
+//   * a' and b' are exact floats (pa + pb - S + 1 <= 24 significant bits).
+// The FMA sees exact real arithmetic and rounds once, so these three statements are the whole proof; qb200_selftest_fp
+// additionally sweeps every operand pair on the GPU (mode 2).  Config 3: pa = pb = 15, S = 8, a' = b' = -32767.99609375.
+struct FpSubst { bool ok; float a_sub, b_sub; };
+__host__ __device__ constexpr int qb_log2_exact(long long v)
+{
+    if (v <= 0) return -1;
+    int p = 0;
+    while ((v & 1) == 0) { v >>= 1; ++p; }
+    return v == 1 ? p : -1;
+}
+__host__ __device__ constexpr FpSubst fp_subst(bool fp_mul, int S, const QStage &m, long long a_lo, long long a_hi, long long b_lo, long long b_hi)
+{
+    FpSubst r = { false, 0.f, 0.f };
+#ifdef QB_NO_SUBST                                             // experiments: keep the per-instance choice between a clamped and a clamp-free loop
+    return r;
+#endif
+    if (!fp_mul || m.qu != RND_CONV || !m.need_hi || m.need_lo || !(m.of == SAT_TCPL || m.of == SAT_SMGN)) return r;
+    const int pa = qb_log2_exact(-a_lo), pb = qb_log2_exact(-b_lo);
+    if (pa < 0 || pb < 0 || a_hi != -a_lo - 1 || b_hi != -b_lo - 1 || S < 1 || pa < S || pb < S || pa + pb - S + 1 > 24) return r;
+    if (m.hi != (1LL << (pa + pb - S)) - 1) return r;
+    // no other product reaches past hi: the next largest ones are a_lo * (b_lo + 1) and (a_lo + 1) * b_lo
+    const long long p1 = a_lo * (b_lo + 1), p2 = (a_lo + 1) * b_lo, half = 1LL << (S - 1);
+    if (((p1 + half) >> S) > m.hi || ((p2 + half) >> S) > m.hi) return r;
+    r.ok = true;
+    r.a_sub = -((float)(1LL << pa) - 1.0f / (float)(1LL << (pb + 1 - S)));
+    r.b_sub = -((float)(1LL << pb) - 1.0f / (float)(1LL << (pa + 1 - S)));
+    return r;
+}
+
 // Non-power-of-two counts: run the host-built flush program over the pending stack entries
 // (vector form QuBLAS.h:4977-4980, variadic form :4942-4949).
 template <typename I, bool CT>

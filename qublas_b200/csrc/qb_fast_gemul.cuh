@@ -64,7 +64,11 @@ struct GemulTile {
     static constexpr bool NARROW = WORD == 2;
     // One pass over each staged instance (gemul_tile_body): exact int->float conversion for the FP32-FMA product quantizer,
     // the per-instance operand ranges of the dynamic clamp elision, widening of packed words.
-    static constexpr bool DYN = (Cfg::mul().need_lo || Cfg::mul().need_hi) && (Cfg::mul().of == SAT_TCPL || Cfg::mul().of == SAT_SMGN);
+    // SUBST: the surviving clamp is min x min only and the conversion pass folds it into the operands (qb_device.cuh:fp_subst):
+    // one clamp-free loop serves every instance.  Otherwise DYN: per-instance ranges pick the clamped or the clamp-free loop.
+    static constexpr FpSubst SUB = fp_subst(Cfg::FP_MUL, Cfg::FP_SHIFT, Cfg::mul(), Cfg::A_LO, Cfg::A_HI, Cfg::B_LO, Cfg::B_HI);
+    static constexpr bool SUBST = SUB.ok;
+    static constexpr bool DYN = !SUBST && (Cfg::mul().need_lo || Cfg::mul().need_hi) && (Cfg::mul().of == SAT_TCPL || Cfg::mul().of == SAT_SMGN);
     static constexpr bool PASS = DYN || Cfg::FP_MUL || NARROW;
     // SEP: the pass writes a separate single-buffered 32-bit copy (the host grants it when shared memory allows) instead of
     // converting in place; only then can the copy be laid out differently from the staged instance (swizzles below).
@@ -483,7 +487,10 @@ QB_DEV void gemul_tile_body(const typename Cfg::WA *__restrict__ A, const typena
             auto put4 = [&](int part, int4 *w, int i, const int4 &v) {          // i = 16-byte chunk index within the part
                 const bool swz = part ? T::SWZ_B : T::SWZ_A;
                 const int o = swz ? i ^ ((i / T::K) & 3) : i;                    // chunk ^ (row / 4) % 4, row = i / (K / 4)
-                if constexpr (Cfg::FP_MUL) ((float4 *)w)[o] = make_float4(__int2float_rn(v.x), __int2float_rn(v.y), __int2float_rn(v.z), __int2float_rn(v.w));
+                if constexpr (T::SUBST) {                                        // an operand at its type's minimum -> the substitute that saturates min x min
+                    const float sub = part ? T::SUB.b_sub : T::SUB.a_sub;
+                    ((float4 *)w)[o] = make_float4(fmaxf(__int2float_rn(v.x), sub), fmaxf(__int2float_rn(v.y), sub), fmaxf(__int2float_rn(v.z), sub), fmaxf(__int2float_rn(v.w), sub));
+                } else if constexpr (Cfg::FP_MUL) ((float4 *)w)[o] = make_float4(__int2float_rn(v.x), __int2float_rn(v.y), __int2float_rn(v.z), __int2float_rn(v.w));
                 else w[o] = v;
             };
 #pragma unroll
@@ -570,7 +577,9 @@ QB_DEV void gemul_tile_body(const typename Cfg::WA *__restrict__ A, const typena
                 *(int4 *)(Ci + (j0 + jj) * M + i0) = o;
             };
             if constexpr (s_form_ok<Cfg>()) {
-                if constexpr (DYN) {
+                if constexpr (T::SUBST) {
+                    tile_compute_s<Cfg, false, QB_SFORM_JW>(Ag, Bg, i0, j0, store_col);
+                } else if constexpr (DYN) {
                     if (clamp) tile_compute_s<Cfg, true, QB_SFORM_JW>(Ag, Bg, i0, j0, store_col);
                     else       tile_compute_s<Cfg, false, QB_SFORM_JW>(Ag, Bg, i0, j0, store_col);
                 } else {
@@ -578,7 +587,9 @@ QB_DEV void gemul_tile_body(const typename Cfg::WA *__restrict__ A, const typena
                 }
             } else {
                 I res[4][4];
-                if constexpr (DYN) {
+                if constexpr (T::SUBST) {
+                    tile_compute<Cfg, false>(Ag, Bg, i0, j0, res);
+                } else if constexpr (DYN) {
                     if (clamp) tile_compute<Cfg, true>(Ag, Bg, i0, j0, res);
                     else       tile_compute<Cfg, false>(Ag, Bg, i0, j0, res);
                 } else {

@@ -1365,22 +1365,23 @@ extern "C" int qb200_table_batched(const qb_qdesc *x, const qb_qdesc *out_type, 
 // qb_fast_cgemv.cuh:fadd_stage).  These kernels run the SAME device functions over every operand pair the plan's types
 // admit and compare with the integer form (mul_apply / add_apply, the restatement of QuBLAS.h:3146-3235).
 // mode 0: clamps as the plan has them; mode 1: clamp-free variant, counted only where the product lies inside [p_lo, p_hi]
-// (the per-instance clamp elision of qb_fast_gemul.cuh).
+// (the per-instance clamp elision of qb_fast_gemul.cuh); mode 2: clamp-free variant on operands whose minima were replaced by
+// the substitutes xs / ys (saturation by operand substitution, qb_device.cuh:fp_subst), every pair counted.
 template <int S>
 __global__ void __launch_bounds__(256) k_selftest_fpmul(long long xlo, unsigned long long nx, long long ylo, unsigned long long ny,
                                                         const __grid_constant__ QStage q, int mode, long long p_lo, long long p_hi,
-                                                        unsigned long long *counts)
+                                                        float xs, float ys, unsigned long long *counts)
 {
     unsigned long long bad = 0, seen = 0;
     QStage qq = q;
-    if (mode == 1) { qq.need_lo = 0; qq.need_hi = 0; }
+    if (mode != 0) { qq.need_lo = 0; qq.need_hi = 0; }
     for (unsigned long long iy = blockIdx.x; iy < ny; iy += gridDim.x) {
         const int y = (int)(ylo + (long long)iy);
-        const float yf = __int2float_rn(y);
+        const float yf = mode == 2 ? fmaxf(__int2float_rn(y), ys) : __int2float_rn(y);
         for (unsigned long long ix = threadIdx.x; ix < nx; ix += blockDim.x) {
             const int x = (int)(xlo + (long long)ix);
             if (mode == 1) { const long long p = (long long)x * y; if (p < p_lo || p > p_hi) continue; }
-            const int got = fp_mul_apply<S, true>(__int2float_rn(x), yf, qq) - fp_kbits<S>();
+            const int got = fp_mul_apply<S, true>(mode == 2 ? fmaxf(__int2float_rn(x), xs) : __int2float_rn(x), yf, qq) - fp_kbits<S>();
             const int want = mul_apply<int32_t, false>(x, y, q);
             bad += got != want; ++seen;
         }
@@ -1414,11 +1415,11 @@ __global__ void __launch_bounds__(256) k_selftest_fadd(long long xlo, unsigned l
 }
 
 static int launch_selftest_fpmul(int S, const Ival &x, const Ival &y, const QStage &q, int mode, long long p_lo, long long p_hi,
-                                 unsigned long long *counts, cudaStream_t st)
+                                 unsigned long long *counts, cudaStream_t st, float xs = 0.f, float ys = 0.f)
 {
     const unsigned long long nx = (unsigned long long)(x.hi - x.lo + 1), ny = (unsigned long long)(y.hi - y.lo + 1);
     const unsigned grid = (unsigned)std::min<unsigned long long>(ny, 148ull * 32);
-#define QB_ST(SV) case SV: k_selftest_fpmul<SV><<<grid, 256, 0, st>>>((long long)x.lo, nx, (long long)y.lo, ny, q, mode, p_lo, p_hi, counts); break;
+#define QB_ST(SV) case SV: k_selftest_fpmul<SV><<<grid, 256, 0, st>>>((long long)x.lo, nx, (long long)y.lo, ny, q, mode, p_lo, p_hi, xs, ys, counts); break;
     switch (S) {
         QB_ST(1) QB_ST(2) QB_ST(3) QB_ST(4) QB_ST(5) QB_ST(6) QB_ST(7) QB_ST(8) QB_ST(9) QB_ST(10) QB_ST(11) QB_ST(12) QB_ST(13) QB_ST(14) QB_ST(15)
         QB_ST(16) QB_ST(17) QB_ST(18) QB_ST(19) QB_ST(20) QB_ST(21) QB_ST(22) QB_ST(23) QB_ST(24) QB_ST(25) QB_ST(26) QB_ST(27) QB_ST(28) QB_ST(29) QB_ST(30)
@@ -1451,6 +1452,8 @@ extern "C" int qb200_selftest_fp(int what, const void *plan, uint64_t *checked, 
             const QStage &m = ce->prog.mul;
             if ((m.need_lo || m.need_hi) && (m.of == SAT_TCPL || m.of == SAT_SMGN))
                 if ((rc = launch_selftest_fpmul(m.shift, ra, rb, m, 1, p_lo, p_hi, counts, cx.stream))) return rc;
+            const FpSubst sub = fp_subst(true, m.shift, m, (long long)ra.lo, (long long)ra.hi, (long long)rb.lo, (long long)rb.hi);
+            if (sub.ok && (rc = launch_selftest_fpmul(m.shift, ra, rb, m, 2, 0, 0, counts, cx.stream, sub.a_sub, sub.b_sub))) return rc;
         }
     } else if (what == 1) {
         const qb_cgemul_plan &p = *(const qb_cgemul_plan *)plan;
