@@ -134,9 +134,11 @@ QB_DEV void pstack_push(I (&st)[NTOP + 1], bool (&sp)[NTOP + 1], uint32_t j, I c
     }
 }
 
-// x: batch vectors of n_in words; out: ceil(n_in / 2^PW) nodes per vector.
+// x: batch vectors of n_in words, in_stride words apart; out: ceil(n_in / 2^PW) nodes per vector, out_stride words apart.
+// (The variadic form of a non-power-of-two length hands over only the whole chunks of each vector: n_in < in_stride.)
 template <class Cfg, int LEV0, int PW, int RMAX>
-QB_DEV void reduce_any_body(const int32_t *__restrict__ x, int32_t *__restrict__ out, uint64_t n_in, uint64_t batch, int vec_ok)
+QB_DEV void reduce_any_body(const int32_t *__restrict__ x, int32_t *__restrict__ out, uint64_t n_in, uint64_t batch, int vec_ok,
+                            uint64_t in_stride, uint64_t out_stride)
 {
     typedef typename Cfg::I I;
     constexpr int NSUB = 1 << (PW - 8), NTOP = PW - 8, U = NSUB < 4 ? NSUB : 4;
@@ -145,7 +147,7 @@ QB_DEV void reduce_any_body(const int32_t *__restrict__ x, int32_t *__restrict__
     const uint64_t per_vec = (n_in + ((uint64_t)1 << PW) - 1) >> PW;
     if (warp >= batch * per_vec) return;
     const uint64_t b = warp / per_vec, c = warp - b * per_vec;
-    const int32_t *xv = x + b * n_in;
+    const int32_t *xv = x + b * in_stride;
     const uint64_t e_begin = c << PW;
     const uint64_t e_end = (e_begin + ((uint64_t)1 << PW)) < n_in ? e_begin + ((uint64_t)1 << PW) : n_in;
     I result = 0;
@@ -205,7 +207,7 @@ QB_DEV void reduce_any_body(const int32_t *__restrict__ x, int32_t *__restrict__
         }
         result = st[NTOP];
     }
-    if (lane == 0) out[warp] = (int32_t)result;
+    if (lane == 0) out[b * out_stride + c] = (int32_t)result;
 }
 
 #ifndef QB_JIT

@@ -19,6 +19,7 @@ struct JitKernel {
     void *module = nullptr;        // CUmodule
     void *func[4] = { nullptr, nullptr, nullptr, nullptr };   // CUfunction(s)
     int npass = 0;                                             // > 0: any-length reduction, one entry point per pass
+    bool variadic = false;                                     // the passes reduce whole chunks only; k_reduce_var_finish completes the tree
     struct { uint64_t n_in, n_out; } pass[4] = {};
     unsigned threads = 0, smem = 0;
     int blocks_per_sm = 1, sms = 0;
@@ -52,5 +53,7 @@ int jit_launch_gemul(const JitKernel &k, const void *A, const void *B, void *C, 
 int jit_launch_reduce(const JitKernel &k, unsigned logn, const void *x, void *out, void *scratch, uint64_t batch, cudaStream_t s);
 // any-length variant: scratch must hold 2 * batch * pass[0].n_out words (two ping-pong halves)
 int jit_launch_reduce_any(const JitKernel &k, const void *x, void *out, void *scratch, uint64_t batch, cudaStream_t s);
+// variadic form, length not a power of two: whole 256-node chunks per pass; roots_of[i] = where pass i wrote its batch * n_out roots
+int jit_launch_reduce_var(const JitKernel &k, const void *x, void *roots, uint64_t batch, cudaStream_t s, const int32_t **roots_of);
 
 }  // namespace qb

@@ -153,6 +153,34 @@ k_reduce_thread(const void *__restrict__ x, int in_wb, void *__restrict__ out, i
     store_word<I>(out, b, out_wb, r);
 }
 
+// Variadic form of a non-power-of-two length, last step (qb_jit.cpp:jit_reduce_var): the passes before it reduced every
+// whole 256-node chunk; what is left are runs of nodes at different levels -- the roots of the last pass, then the trailing
+// nodes of each pass, highest level first, i.e. in leaf order.  One thread per vector pushes them through the level-indexed
+// stack (a node of level L with index idx among the level-L nodes merges while the low bits of idx are set) and runs the
+// variadic flush program (QuBLAS.h:4942-4949).
+struct VarRun { const int32_t *ptr; uint64_t stride, start, count; uint32_t level, pad; };
+struct VarRuns { int n, pad; VarRun r[6]; };
+template <typename I>
+__global__ void __launch_bounds__(128)
+k_reduce_var_finish(const __grid_constant__ VarRuns R, void *__restrict__ out, int out_wb, uint64_t batch, const __grid_constant__ TreeProg P)
+{
+    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    I st[QBP_MAX_LEVELS];
+    for (int i = 0; i < R.n; i++) {
+        const VarRun &q = R.r[i];
+        const int32_t *p = q.ptr + b * q.stride;
+        for (uint64_t idx = q.start; idx < q.start + q.count; ++idx) {
+            I v = (I)p[idx];
+            unsigned l = q.level;
+            uint64_t m = idx;
+            while (m & 1) { v = merge_apply<I, false>(st[l], v, P.lvl[l]); ++l; m >>= 1; }
+            st[l] = v;
+        }
+    }
+    store_word<I>(out, b, out_wb, flush_apply<I, false>(P, st));
+}
+
 // ----------------------------------------------------------------------------------------------
 // Qgemul, one thread per output element (any shape, transposes, both tree forms).
 // C[i,j] = conv_C( tree_k( Qmul<mul>(opA(i,k), opB(k,j)) ) )      readme.md:80-87

@@ -513,6 +513,26 @@ extern "C" int qb200_reduce_batched(const qb_reduce_plan *plan_in, const void *x
         if ((rc = cx.alloc(&scratch, batch * 4096 * sizeof(int32_t)))) return rc;
         int e = fr->launch(dx, dout, scratch, batch, cx.stream);
         rc = e ? fail(QB_ECUDA, std::string(fr->name) + " launch failed: " + cudaGetErrorString((cudaError_t)e)) : QB_OK;
+    } else if (jk && jk->npass > 0 && jk->variadic) {
+        // whole 256-node chunks pass by pass, then one thread per vector for the < 256 trailing nodes of every pass
+        uint64_t roots_words = 0;
+        for (int i = 0; i < jk->npass; i++) roots_words += batch * jk->pass[i].n_out;
+        void *roots;
+        if ((rc = cx.alloc(&roots, roots_words * sizeof(int32_t)))) return rc;
+        const int32_t *roots_of[4] = { nullptr, nullptr, nullptr, nullptr };
+        int e = jit_launch_reduce_var(*jk, dx, roots, batch, cx.stream, roots_of);
+        if (e) return fail(QB_ECUDA, "k_reduce_var<jit> launch failed (CUresult " + std::to_string(e) + ")");
+        VarRuns R; memset(&R, 0, sizeof(R));
+        const int np = jk->npass;
+        R.r[R.n++] = { roots_of[np - 1], jk->pass[np - 1].n_out, 0, jk->pass[np - 1].n_out, (uint32_t)(8 * np), 0 };      // every root of the last pass
+        for (int i = np - 1; i >= 0; i--) {                                                                             // then the nodes each pass left behind
+            const uint64_t n_i = jk->pass[i].n_in, done = jk->pass[i].n_out << 8;
+            if (n_i > done) R.r[R.n++] = { i ? roots_of[i - 1] : (const int32_t *)dx, n_i, done, n_i - done, (uint32_t)(8 * i), 0 };
+        }
+        const uint64_t blocks = (batch + 127) / 128;
+        if (blocks > 0x7fffffffull) return fail(QB_EINVAL, "too many vectors for one launch");
+        k_reduce_var_finish<int32_t><<<(unsigned)blocks, 128, 0, cx.stream>>>(R, dout, rp.out_wb, batch, rp.tree);
+        rc = post_launch("k_reduce_var_finish");
     } else if (jk && jk->npass > 0) {
         void *scratch = nullptr;
         if (jk->npass > 1 && (rc = cx.alloc(&scratch, 2 * batch * jk->pass[0].n_out * sizeof(int32_t)))) return rc;

@@ -175,7 +175,9 @@ def test_every_jit_template_compiles_without_a_device():
         check(1, ops.make_cgemul_plan(*args, out, out, 5, 3, 12, tf_tags=tags, add_re=lv, form=TREE_VECTOR, product=kind, trans_a=True))
     # Qreduce: power-of-two two-pass template, any-length template, variadic power of two routed to the vector kernels
     elem = QType(8, 8); rl = [QType(9 + l, 8 - l, True, 0, 0) for l in range(8)]
-    for n, form in ((1 << 16, TREE_VECTOR), (100000, TREE_VECTOR), (64, TREE_VECTOR), (4097, TREE_VECTOR), (1 << 12, TREE_VARIADIC)):
+    # ... and the variadic form of lengths that are not a power of two (whole 256-node chunks per pass + finishing kernel)
+    for n, form in ((1 << 16, TREE_VECTOR), (100000, TREE_VECTOR), (64, TREE_VECTOR), (4097, TREE_VECTOR), (1 << 12, TREE_VARIADIC),
+                    (100000, TREE_VARIADIC), (3 << 20, TREE_VARIADIC), (513, TREE_VARIADIC)):
         check(2, ops.make_reduce_plan(elem, rl, n, form=form))
     # element-wise: complex products, real ops, converting assignment
     for kind, tags, args in (("tf", tf, (t, t, t, t)), ("basic", bc, (t, t, t, t)), ("real_a", rc_tags, (t, None, t, t))):

@@ -715,6 +715,30 @@ def test_jit_any_length_reduce_vs_oracle(seed):
     assert np.array_equal(out.cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("n,batch", [(513, 7), (1000, 5), (65535, 3), (65537, 3), (100000, 4), (3 << 20, 2), ((1 << 24) - 1, 1), (256 * 257 + 255, 2)])
+def test_variadic_qreduce_of_lengths_that_are_not_a_power_of_two(n, batch):
+    """the variadic form (QuBLAS.h:4942-4949: the odd node of a level is added after the levels above
+    it) on long vectors: whole 256-node chunks are reduced pass by pass by the warp kernels, k_reduce_var_finish streams
+    what is left through the level-indexed stack.  Bit-exact against the oracle and the one-thread-per-vector kernel."""
+    rng = np.random.default_rng(n)
+    for mode in (RND_POS_INF, RND_CONV):
+        elem = QType(8, 8)
+        lv = [QType(9 + l, 8 - l, True, mode, SAT_TCPL) for l in range(8)] + [QType(17 + (l - 6) // 2, 0, True, mode, SAT_TCPL) for l in range(8, 24)]
+        plan = reduce_plan(elem, lv, n, form=TREE_VARIADIC)
+        x = rand_words(rng, elem, batch * n).astype(np.int32)
+        out, _ = ops.Qreduce(dev(x), elem, lv, length=n, batch=batch, form=TREE_VARIADIC)
+        assert ops.plan_info_reduce(plan).kernel == b"k_reduce_var<jit>", ops.plan_info_reduce(plan).kernel
+        want, _ = oracle.reduce_batched(plan, x, batch)
+        assert np.array_equal(out.cpu().numpy(), want), (n, mode)
+        if n <= 100000:
+            gen, _ = ops.Qreduce(dev(x), elem, lv, length=n, batch=batch, form=TREE_VARIADIC, flags=abi.QB_F_NO_SPECIALIZE)
+            assert torch.equal(out, gen)
+            # a buffer that does not start on a 16-byte boundary stays on the one-thread-per-vector kernel: same bits
+            buf = dev(np.concatenate([np.zeros(1, np.int32), x]))
+            out2, _ = ops.Qreduce(buf[1:], elem, lv, length=n, batch=batch, form=TREE_VARIADIC)
+            assert np.array_equal(out2.cpu().numpy(), want), (n, mode, "unaligned")
+
+
 def test_jit_elementwise_kernels_vs_runtime_descriptor_and_oracle():
     """The NVRTC-specialised element-wise kernels (complex products of all four kinds, real Qmul/Qadd/Qsub, converting
     assignment) on odd lengths (ragged tail of the 4-way unrolled loop), 32- and 64-bit register classes: identical to the
