@@ -192,14 +192,38 @@ template <class Cfg> __host__ __device__ constexpr bool s_form_ok()
     }
     return true;
 }
+// Negated S form (round 2).  ceil(x / 2) = -floor(-x / 2): if every node is carried NEGATED, a RND::POS_INF halving needs no
+// bias at all (and a round-down level needs the +1 instead).  The negation is free -- the conversion pass negates the float
+// copy of A, RND::CONV products are odd-symmetric -- and with level 1 rounding half-up the additive constant of every group
+// but the few that inherit a bias from a round-down level above is ZERO.  The FFMA magic-constant bias (4 * fp_kbits per
+// group, an even number at every level: ((S + D) >> 1) + ((S' + D) >> 1) = (S >> 1) + (S' >> 1) + D) is not removed per group
+// any more but once per output at the root.  A group is then IADD3(p0, p1, p2) + one plain two-input add without an
+// immediate (config 3: 11.4 -> 11.9 TMAC/s).  Issuing that add as IMAD (x * 1 + y, the 1 in a register) on the FMA pipe gains
+// 5 % from registers (tools/mix_probe.cu) but loses 1 % in the kernel (QB_IMAD_ADD).
+template <class Cfg> __host__ __device__ constexpr bool s_form_neg()
+{
+#ifdef QB_NO_NEG
+    return false;
+#else
+    return GemulTile<Cfg, 4, 4>::SUBST && s_form_ok<Cfg>() && Cfg::lvl(1).q.qu == RND_POS_INF;
+#endif
+}
 // additive constant of 4-product group g (0 .. K/4-1): the level-1 bias plus every bias pushed down from the levels above
 template <class Cfg> __host__ __device__ constexpr int s_form_const(int g)
 {
-    int c = Cfg::lvl(1).q.qu == RND_POS_INF ? 1 : 0;
+    const bool neg = s_form_neg<Cfg>();
+    int c = ((Cfg::lvl(1).q.qu == RND_POS_INF) != neg) ? 1 : 0;
     for (int l = 2; l < Cfg::NLEV; ++l)
-        if (g % (1 << (l - 1)) == 0 && Cfg::lvl(l).q.qu == RND_POS_INF) c += 1 << (l - 1);
+        if (g % (1 << (l - 1)) == 0 && ((Cfg::lvl(l).q.qu == RND_POS_INF) != neg)) c += 1 << (l - 1);
     return c;
 }
+template <class Cfg> __host__ __device__ constexpr bool s_form_no_consts()
+{
+    for (int g = 0; g < Cfg::K / 4; ++g) if (s_form_const<Cfg>(g) != 0) return false;
+    return true;
+}
+// the 1 of the IMAD adds: read from memory so that the compiler cannot fold the multiply away
+static __device__ uint32_t qb_opaque_one = 1u;
 // level-indexed stack of pre-shift sums; slot L holds a pending node of level 2 + L
 template <class Cfg, int L, int NTOP, typename I>
 QB_DEV void s_push(I (&st)[NTOP > 0 ? NTOP : 1], uint32_t c, I S, I &result)
@@ -330,8 +354,10 @@ QB_DEV void tile_compute(const int32_t *As, const int32_t *Bs, int i0, int j0, t
 #define QB_SFORM_JW 2
 #endif
 template <class Cfg, bool CLAMP, int JW, class Out>
-QB_DEV void tile_compute_s(const int32_t *As, const int32_t *Bs, int i0, int j0, Out out)
+QB_DEV void tile_compute_s(const int32_t *As, const int32_t *Bs, int i0, int j0, uint32_t one, Out out)
 {
+    constexpr bool NEG = s_form_neg<Cfg>();
+    static_assert(!NEG || (!CLAMP && Cfg::FP_MUL), "the negated form runs on substituted operands");
     typedef GemulTile<Cfg, 4, 4> T;
     typedef typename T::I I;
     constexpr int NTOP = T::NTOP;
@@ -369,7 +395,24 @@ QB_DEV void tile_compute_s(const int32_t *As, const int32_t *Bs, int i0, int j0,
                         // four products -> the pre-shift level-1 sum (two IADD3): level 0 is exact, the constant removes the
                         // FFMA bias and carries every rounding bias that belongs to this group
                         uint32_t sum;
-                        if constexpr (Cfg::FP_MUL) {
+                        if constexpr (NEG) {
+                            // negated products, biased by fp_kbits each (removed at the root); level 0 is exact
+                            constexpr int S = Cfg::FP_SHIFT;
+                            const int KG = s_form_const<Cfg>(2 * (int)c + h);      // a constant once the chunk loop is unrolled
+                            const uint32_t p3 = (uint32_t)fp_mul_apply<S, true>(__int_as_float(a3), __int_as_float(b3), mulq);
+                            sum = (uint32_t)fp_mul_apply<S, true>(__int_as_float(a0), __int_as_float(b0), mulq) + (uint32_t)fp_mul_apply<S, true>(__int_as_float(a1), __int_as_float(b1), mulq) +
+                                  (uint32_t)fp_mul_apply<S, true>(__int_as_float(a2), __int_as_float(b2), mulq);
+#ifdef QB_IMAD_ADD                                            // experiment: the plain add as IMAD (x * 1 + y) on the FMA pipe; measured -1 % in the kernel
+                            if constexpr (s_form_no_consts<Cfg>()) sum = sum * one + p3;
+                            else sum = sum + p3 + (uint32_t)KG;
+#else
+                            sum = sum + p3 + (uint32_t)KG;
+#endif
+                            const I S1 = (I)sum;
+                            if (h == 0) half0[ii][jj] = S1;
+                            else s_push<Cfg, 0, NTOP, I>(st[ii][jj], c, (I)((half0[ii][jj] >> 1) + (S1 >> 1)), res[ii][jj]);
+                            continue;
+                        } else if constexpr (Cfg::FP_MUL) {
                             constexpr int S = Cfg::FP_SHIFT;
                             sum = (uint32_t)fp_mul_apply<S, true>(__int_as_float(a0), __int_as_float(b0), mulq) + (uint32_t)fp_mul_apply<S, true>(__int_as_float(a1), __int_as_float(b1), mulq) +
                                   (uint32_t)fp_mul_apply<S, true>(__int_as_float(a2), __int_as_float(b2), mulq) + (uint32_t)fp_mul_apply<S, true>(__int_as_float(a3), __int_as_float(b3), mulq) -
@@ -385,7 +428,14 @@ QB_DEV void tile_compute_s(const int32_t *As, const int32_t *Bs, int i0, int j0,
             }
         }
 #pragma unroll
-        for (int jj = 0; jj < JW; ++jj) out(jp + jj, (I)(res[0][jj] >> 1), (I)(res[1][jj] >> 1), (I)(res[2][jj] >> 1), (I)(res[3][jj] >> 1));   // root: pre-shift sum -> value
+        for (int jj = 0; jj < JW; ++jj) {
+            if constexpr (NEG) {                              // root: offset, negated pre-shift sum -> value
+                constexpr I DH = (I)((int32_t)(4u * (uint32_t)fp_kbits<Cfg::FP_SHIFT>()) >> 1);
+                out(jp + jj, (I)(DH - (res[0][jj] >> 1)), (I)(DH - (res[1][jj] >> 1)), (I)(DH - (res[2][jj] >> 1)), (I)(DH - (res[3][jj] >> 1)));
+            } else {
+                out(jp + jj, (I)(res[0][jj] >> 1), (I)(res[1][jj] >> 1), (I)(res[2][jj] >> 1), (I)(res[3][jj] >> 1));   // root: pre-shift sum -> value
+            }
+        }
     }
 }
 
@@ -455,6 +505,7 @@ QB_DEV void gemul_tile_body(const typename Cfg::WA *__restrict__ A, const typena
 
     constexpr QStage mulq = Cfg::mul();
     constexpr QStage outq = Cfg::out();
+    const uint32_t one = *(const volatile uint32_t *)&qb_opaque_one;
     // Dynamic clamp elision: Qmul's SAT clamp survives the static interval analysis only because of extreme
     // operand values (config 3: min x min).  One pass over the staged instance finds its actual operand
     // ranges; if even the extreme corner products stay inside [P_LO, P_HI] (host-computed, conservative),
@@ -489,7 +540,10 @@ QB_DEV void gemul_tile_body(const typename Cfg::WA *__restrict__ A, const typena
                 const int o = swz ? i ^ ((i / T::K) & 3) : i;                    // chunk ^ (row / 4) % 4, row = i / (K / 4)
                 if constexpr (T::SUBST) {                                        // an operand at its type's minimum -> the substitute that saturates min x min
                     const float sub = part ? T::SUB.b_sub : T::SUB.a_sub;
-                    ((float4 *)w)[o] = make_float4(fmaxf(__int2float_rn(v.x), sub), fmaxf(__int2float_rn(v.y), sub), fmaxf(__int2float_rn(v.z), sub), fmaxf(__int2float_rn(v.w), sub));
+                    if (s_form_neg<Cfg>() && part == 0)                           // negated S form: A enters negated (FMNMX negates its inputs for free)
+                        ((float4 *)w)[o] = make_float4(fminf(-__int2float_rn(v.x), -sub), fminf(-__int2float_rn(v.y), -sub), fminf(-__int2float_rn(v.z), -sub), fminf(-__int2float_rn(v.w), -sub));
+                    else
+                        ((float4 *)w)[o] = make_float4(fmaxf(__int2float_rn(v.x), sub), fmaxf(__int2float_rn(v.y), sub), fmaxf(__int2float_rn(v.z), sub), fmaxf(__int2float_rn(v.w), sub));
                 } else if constexpr (Cfg::FP_MUL) ((float4 *)w)[o] = make_float4(__int2float_rn(v.x), __int2float_rn(v.y), __int2float_rn(v.z), __int2float_rn(v.w));
                 else w[o] = v;
             };
@@ -578,12 +632,12 @@ QB_DEV void gemul_tile_body(const typename Cfg::WA *__restrict__ A, const typena
             };
             if constexpr (s_form_ok<Cfg>()) {
                 if constexpr (T::SUBST) {
-                    tile_compute_s<Cfg, false, QB_SFORM_JW>(Ag, Bg, i0, j0, store_col);
+                    tile_compute_s<Cfg, false, QB_SFORM_JW>(Ag, Bg, i0, j0, one, store_col);
                 } else if constexpr (DYN) {
-                    if (clamp) tile_compute_s<Cfg, true, QB_SFORM_JW>(Ag, Bg, i0, j0, store_col);
-                    else       tile_compute_s<Cfg, false, QB_SFORM_JW>(Ag, Bg, i0, j0, store_col);
+                    if (clamp) tile_compute_s<Cfg, true, QB_SFORM_JW>(Ag, Bg, i0, j0, one, store_col);
+                    else       tile_compute_s<Cfg, false, QB_SFORM_JW>(Ag, Bg, i0, j0, one, store_col);
                 } else {
-                    tile_compute_s<Cfg, true, QB_SFORM_JW>(Ag, Bg, i0, j0, store_col);
+                    tile_compute_s<Cfg, true, QB_SFORM_JW>(Ag, Bg, i0, j0, one, store_col);
                 }
             } else {
                 I res[4][4];
