@@ -369,6 +369,13 @@ QB_DEV void tile_compute_s(const int32_t *As, const int32_t *Bs, int i0, int j0,
         asm volatile("" ::: "memory");                        // keep the (pass-invariant) A fragment loads inside their pass
         const TileFrag<Cfg> fr(As, Bs + (Cfg::TRANS_B ? 0 : jp * T::K), i0, j0);      // plain B: the pass starts at column j0 + jp (same row block: same swizzle)
         I st[4][JW][NTOP > 0 ? NTOP : 1], res[4][JW];
+#ifdef QB_SFORM_PREFETCH                                      // experiment: fragments of the next four k in flight behind the current group
+        int4 bqn[4], aqn[4];
+#pragma unroll
+        for (int u = 0; u < (Cfg::TRANS_B ? 4 : JW); ++u) bqn[u] = fr.ldb(u, 0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) aqn[u] = fr.lda(u, 0);
+#endif
 #pragma unroll
         for (uint32_t c = 0; c < (uint32_t)T::NCH; ++c) {
             I half0[4][JW];
@@ -376,10 +383,21 @@ QB_DEV void tile_compute_s(const int32_t *As, const int32_t *Bs, int i0, int j0,
             for (int h = 0; h < 2; ++h) {
                 const int kc = 2 * (int)c + h;
                 int4 bq[4], aq[4];
+#ifdef QB_SFORM_PREFETCH
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { bq[u] = bqn[u]; aq[u] = aqn[u]; }
+                if (kc + 1 < 2 * T::NCH) {
+#pragma unroll
+                    for (int u = 0; u < (Cfg::TRANS_B ? 4 : JW); ++u) bqn[u] = fr.ldb(u, kc + 1);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) aqn[u] = fr.lda(u, kc + 1);
+                }
+#else
 #pragma unroll
                 for (int u = 0; u < (Cfg::TRANS_B ? 4 : JW); ++u) bq[u] = fr.ldb(u, kc);            // stored transposed: j contiguous, all four columns come along
 #pragma unroll
                 for (int u = 0; u < 4; ++u) aq[u] = fr.lda(u, kc);
+#endif
                 auto a_at = [&](int ii, int kk) -> I { return Cfg::TRANS_A ? (&aq[ii].x)[kk] : (&aq[kk].x)[ii]; };
                 auto b_at = [&](int kk, int jj) -> I {
                     if constexpr (!Cfg::TRANS_B) return (&bq[jj].x)[kk];

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Small driver for ncu captures: runs one workload's hot kernel a few times on device-resident data.
-usage: python tools/prof.py c2|c3|c4|c5|c5t|cg [iters]"""
+usage: python tools/prof.py c2|c3|c4|c5|c5t|c5i8|cg [iters]"""
 import os
 import sys
 
@@ -55,6 +55,10 @@ else:
     A = torch.empty(M * M, dtype=torch.int32, device=dev); B = torch.empty_like(A); Cd = torch.empty_like(A)
     ops.synth_fill(A, -128, 127, 1, 0); ops.synth_fill(B, -128, 127, 1, 1)
     fn = lambda: ops.Qgemul(Cd, A, B, plan)
+    if w == "c5i8":                               # int8 words, K contiguous: read in place by TMA (no narrowing at all)
+        plan = ops.make_gemul_plan(a, a, acc, M, M, M, mul=QType(15, 0), add=[acc], trans_a=True, word_bytes=(1, 1, 0))
+        A8, B8 = A.to(torch.int8), B.to(torch.int8)
+        fn = lambda: ops.Qgemul(Cd, A8, B8, plan)
 for _ in range(iters):
     fn()
 torch.cuda.synchronize()

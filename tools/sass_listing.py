@@ -14,7 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "qublas_b200", "libqb200.so")
 KERNELS = {                               # tag -> substring of the mangled name
     "c3_k_gemul_tile": "k_gemul_tileI5CfgC3",
-    "c5_k_i8gemm_pair": "k_i8gemm_pair",
+    "c5_k_i8gemm_pair": "k_i8gemm_pairE",
+    "c5_k_i8gemm_pair_fused": "k_i8gemm_pair_fusedE",
     "c2_k_reduce_ct_pass1": "k_reduce_ctI7CfgC2b0Li0ELi12E",
     "c4_k_cgemv_rows": "k_cgemv_rowsI5CfgC4",
 }
