@@ -222,8 +222,10 @@ template <class Cfg> __host__ __device__ constexpr bool s_form_no_consts()
     for (int g = 0; g < Cfg::K / 4; ++g) if (s_form_const<Cfg>(g) != 0) return false;
     return true;
 }
+#ifdef QB_IMAD_ADD
 // the 1 of the IMAD adds: read from memory so that the compiler cannot fold the multiply away
 static __device__ uint32_t qb_opaque_one = 1u;
+#endif
 // level-indexed stack of pre-shift sums; slot L holds a pending node of level 2 + L
 template <class Cfg, int L, int NTOP, typename I>
 QB_DEV void s_push(I (&st)[NTOP > 0 ? NTOP : 1], uint32_t c, I S, I &result)
@@ -523,7 +525,11 @@ QB_DEV void gemul_tile_body(const typename Cfg::WA *__restrict__ A, const typena
 
     constexpr QStage mulq = Cfg::mul();
     constexpr QStage outq = Cfg::out();
+#ifdef QB_IMAD_ADD
     const uint32_t one = *(const volatile uint32_t *)&qb_opaque_one;
+#else
+    const uint32_t one = 1u;
+#endif
     // Dynamic clamp elision: Qmul's SAT clamp survives the static interval analysis only because of extreme
     // operand values (config 3: min x min).  One pass over the staged instance finds its actual operand
     // ranges; if even the extreme corner products stay inside [P_LO, P_HI] (host-computed, conservative),

@@ -945,6 +945,48 @@ def test_fp_pipe_quantizers_exhaustive_sweep():
     assert checked.value >= 2 * (1 << 32) + (1 << 33) + 2 * (1 << 32) - (1 << 20) and bad.value == 0, (checked.value, bad.value)
 
 
+@pytest.mark.parametrize("a,b,mul,sform", [
+    (QType(3, 4), QType(5, 6), QType(8, 6, True, RND_CONV, SAT_TCPL), False),        # 8 x 12 bits, shift 4
+    (QType(7, 8), QType(7, 8), QType(14, 4, True, RND_CONV, SAT_TCPL), True),        # 16 x 16 bits, shift 12, deferred-shift tree
+    (QType(9, 2), QType(2, 9), QType(11, 0, True, RND_CONV, SAT_TCPL), False),       # 12 x 12 bits, shift 11 = log2(-min)
+    (QType(7, 8), QType(3, 4), QType(14, 2, True, RND_CONV, SAT_TCPL), True)])       # 16 x 8 bits, shift 10 > log2(-min(b)): not substitutable
+def test_saturation_by_operand_substitution_other_widths(a, b, mul, sform):
+    """qb_device.cuh:fp_subst -- when the only product Qmul's SAT clamp can touch is min x min, the conversion pass replaces
+    operands at their type's minimum by a nearby float that makes the plain FMA deliver the saturated value; the register
+    tiles then run ONE clamp-free loop.  Other operand widths and shifts than config 3's: the exhaustive GPU sweep of the
+    substituted form (third pass of qb200_selftest_fp) and the tile kernel on batches full of minima against the oracle."""
+    import ctypes
+    lib = abi.load()
+    K = 16
+    if sform:
+        lv = [QType(mul.i + 1, mul.f, True, RND_POS_INF, SAT_TCPL)] + [QType(mul.i + 1 + l, mul.f - l, True, RND_POS_INF, SAT_TCPL) for l in range(1, 4)]
+    else:
+        lv = [QType(mul.i + 1 + l, mul.f, True, RND_POS_INF, SAT_TCPL) for l in range(4)]
+    c = QType(lv[-1].i, lv[-1].f, True, RND_POS_INF, SAT_TCPL)
+    plan = ops.make_gemul_plan(a, b, c, 32, 32, K, mul=mul, add=lv)
+    info = ops.plan_info_gemul(plan)
+    pa, pb, S = (-a.raw_min).bit_length() - 1, (-b.raw_min).bit_length() - 1, a.f + b.f - mul.f
+    subst = pa >= S and pb >= S
+    ex = abi.qb_exec(abi.QB_MEM_DEVICE, 0, None, 0, 0)
+    checked, bad = ctypes.c_uint64(), ctypes.c_uint64()
+    abi.check(lib.qb200_selftest_fp(0, ctypes.cast(ctypes.byref(plan), ctypes.c_void_p), ctypes.byref(checked), ctypes.byref(bad), ctypes.byref(ex)))
+    pairs = (a.raw_max - a.raw_min + 1) * (b.raw_max - b.raw_min + 1)
+    assert bad.value == 0 and (checked.value > 2.5 * pairs) == subst, (checked.value, pairs, bad.value)
+    rng = np.random.default_rng(mul.f * 7 + a.i)
+    batch = 9
+    A = rand_words(rng, a, batch * 32 * K).astype(np.int32); B = rand_words(rng, b, batch * K * 32).astype(np.int32)
+    A[rng.random(A.size) < 0.15] = a.raw_min; B[rng.random(B.size) < 0.15] = b.raw_min          # min x min products all over the place
+    A[:32 * K] = a.raw_min; B[:K * 32] = b.raw_min                                               # instance 0: nothing but
+    Cd = torch.empty(batch * 32 * 32, dtype=torch.int32, device="cuda")
+    ops.Qgemul(Cd, dev(A), dev(B), plan, batch=batch)
+    assert b"tile" in ops.plan_info_gemul(plan).kernel, info.kernel
+    want = oracle.gemul_batched(plan, A, B, batch)
+    assert np.array_equal(Cd.cpu().numpy(), want)
+    C2 = torch.empty_like(Cd)
+    ops.Qgemul(C2, dev(A), dev(B), plan, batch=batch, flags=abi.QB_F_NO_SPECIALIZE)
+    assert torch.equal(Cd, C2)
+
+
 @pytest.mark.parametrize("K,modes,fp", [(64, "PPPPP", True), (64, "PNTPN", True), (32, "TTTT", False), (16, "NPP", True), (8, "PP", False), (64, "PPPPP", False)])
 def test_tile_kernel_deferred_shift_tree_vs_oracle(K, modes, fp):
     """The S form of the register-tile kernel (qb_fast_gemul.cuh: exact level 0, clamp-free halving levels with a
