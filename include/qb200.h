@@ -281,6 +281,12 @@ int qb200_error_stats(const qb_qdesc *type, const void *words, const double *ref
 /* float64 GEMM of the dequantized operands of a real Qgemul plan (same shapes, transposes and batch strides; C64 is
  * batch x M x N doubles, column-major): the yardstick qb200_error_stats compares a quantized result with. */
 int qb200_gemul_f64_batched(const qb_gemul_plan *plan, const void *A, const void *B, double *C64, uint64_t batch, const qb_exec *exec);
+/* The two steps above in one pass over a batch: error statistics of the quantized results C (the plan's C type) against the
+ * float64 GEMM of the dequantized operands, without materialising the float64 matrices (the accuracy sweep of a Monte-Carlo
+ * run: Qu -> double on either side of the path, QuBLAS.h:2413-2416).  Same reference values as qb200_gemul_f64_batched; the
+ * sums are reduced in a fixed order (reproducible), which differs from qb200_error_stats' order in the last bits. */
+int qb200_gemul_error_batched(const qb_gemul_plan *plan, const void *A, const void *B, const void *C, uint64_t batch,
+                              qb_err_stats *stats, const qb_exec *exec);
 
 /* Memory helpers for the host bindings.  Pinned (page-locked) host buffers make the copies of QB_MEM_HOST calls truly
  * asynchronous, so that the library's internal H2D / kernel / D2H pipeline overlaps; device buffers keep a whole

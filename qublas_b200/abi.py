@@ -147,7 +147,7 @@ ABI_SYMBOLS = [
     "qb200_launch_count_reset", "qb200_reduce_plan_info", "qb200_gemul_plan_info", "qb200_cgemul_plan_info",
     "qb200_reduce_batched", "qb200_gemul_batched", "qb200_cgemul_batched", "qb200_tfcmul_batched",
     "qb200_convert_batched", "qb200_elementwise_batched", "qb200_synth_fill", "qb200_shard_range", "qb200_measure_int_peak", "qb200_jit_check_gemul", "qb200_jit_check", "qb200_quantize_f64", "qb200_dequantize_f64", "qb200_error_stats",
-    "qb200_selftest_fp", "qb200_gemul_f64_batched", "qb200_host_alloc", "qb200_host_free", "qb200_device_alloc", "qb200_device_free", "qb200_memcpy", "qb200_gemul_sharded", "qb200_allgather",
+    "qb200_selftest_fp", "qb200_gemul_f64_batched", "qb200_gemul_error_batched", "qb200_host_alloc", "qb200_host_free", "qb200_device_alloc", "qb200_device_free", "qb200_memcpy", "qb200_gemul_sharded", "qb200_allgather",
     "qb200_poly_plan_info", "qb200_poly_batched", "qb200_gemul_poly_batched", "qb200_table_batched",
 ]
 
@@ -192,6 +192,7 @@ def load() -> C.CDLL:
     L.qb200_jit_check.argtypes = [C.c_int, C.c_void_p, C.c_char_p, u64]
     L.qb200_measure_int_peak.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(qb_exec)]
     L.qb200_gemul_f64_batched.argtypes = [C.POINTER(qb_gemul_plan), vp, vp, vp, u64, C.POINTER(qb_exec)]
+    L.qb200_gemul_error_batched.argtypes = [C.POINTER(qb_gemul_plan), vp, vp, vp, u64, C.POINTER(qb_err_stats), C.POINTER(qb_exec)]
     L.qb200_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t, u32]
     L.qb200_host_free.argtypes = [vp]
     L.qb200_device_alloc.argtypes = [C.POINTER(vp), C.c_size_t, C.c_int]

@@ -1600,6 +1600,131 @@ extern "C" int qb200_gemul_f64_batched(const qb_gemul_plan *plan, const void *A,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Accuracy of a quantized batch in ONE pass (the Monte-Carlo sweep of north_star: Qgemul -> error against float64): the
+// float64 reference of every instance is formed in registers and compared with the quantized result on the spot, so neither
+// the batch x M x N doubles nor a second pass over them exist.  One CTA per instance at a time: the operands are converted to
+// double ONCE into shared memory (A as [k][i], B as [k][j]), every thread owns 4 x 4 outputs and runs the same k-ascending FMA
+// chain per output as k_gemul_f64 (bit-identical reference values); the sums are reduced in a fixed order (fixed grid, fixed
+// instance -> CTA mapping, fixed tree), i.e. reproducible run to run.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gemul_err_f64(const void *__restrict__ A, const void *__restrict__ B, const void *__restrict__ C, uint64_t batch,
+                                                       const __grid_constant__ GemulShape S, int frac_a, int frac_b, int frac_c, double *__restrict__ part)
+{
+    extern __shared__ double err_sm[];
+    double *As = err_sm, *Bt = err_sm + (size_t)S.K * S.M;
+    __shared__ double s0[256], s1[256], s2[256];
+    const uint32_t M = S.M, N = S.N, K = S.K, tid = threadIdx.x;
+    const uint32_t tm = M / 4, ntiles = tm * (N / 4);
+    const double sc = pow2_neg(frac_a + frac_b), scc = pow2_neg(frac_c);
+    double se = 0, sr = 0, mx = 0;
+    for (uint64_t inst = blockIdx.x; inst < batch; inst += gridDim.x) {
+        __syncthreads();                                        // the previous instance's tiles are done with shared memory
+        const uint64_t oa = inst * (uint64_t)S.stride_a, ob = inst * (uint64_t)S.stride_b;
+        for (uint32_t r = tid; r < M * K; r += blockDim.x) {    // stored order (coalesced); As[k][i]
+            const double v = (double)load_word<int64_t>(A, oa + r, S.a_wb);
+            if (S.trans_a) { const uint32_t i = r / K, k = r - i * K; As[k * M + i] = v; } else As[r] = v;
+        }
+        for (uint32_t r = tid; r < K * N; r += blockDim.x) {    // Bt[k][j]
+            const double v = (double)load_word<int64_t>(B, ob + r, S.b_wb);
+            if (S.trans_b) Bt[r] = v; else { const uint32_t j = r / K, k = r - j * K; Bt[k * N + j] = v; }
+        }
+        __syncthreads();
+        for (uint32_t t = tid; t < ntiles; t += blockDim.x) {
+            const uint32_t i0 = (t % tm) * 4, j0 = (t / tm) * 4;
+            double acc[4][4];
+#pragma unroll
+            for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+                for (int jj = 0; jj < 4; jj++) acc[ii][jj] = 0.0;
+#pragma unroll 4
+            for (uint32_t k = 0; k < K; ++k) {
+                const double2 a01 = *(const double2 *)(As + k * M + i0), a23 = *(const double2 *)(As + k * M + i0 + 2);
+                const double2 b01 = *(const double2 *)(Bt + k * N + j0), b23 = *(const double2 *)(Bt + k * N + j0 + 2);
+                const double a[4] = { a01.x, a01.y, a23.x, a23.y }, b[4] = { b01.x, b01.y, b23.x, b23.y };
+#pragma unroll
+                for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+                    for (int jj = 0; jj < 4; jj++) acc[ii][jj] = fma(a[ii], b[jj], acc[ii][jj]);
+            }
+            const uint64_t oc = inst * (uint64_t)S.stride_c;
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++)
+#pragma unroll
+                for (int ii = 0; ii < 4; ii++) {
+                    const double ref = acc[ii][jj] * sc;
+                    const double d = (double)load_word<int64_t>(C, oc + (uint64_t)(j0 + jj) * M + i0 + ii, S.c_wb) * scc - ref;
+                    se += d * d; sr += ref * ref; mx = fmax(mx, fabs(d));
+                }
+        }
+    }
+    s0[tid] = se; s1[tid] = sr; s2[tid] = mx;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)tid < o) { s0[tid] += s0[tid + o]; s1[tid] += s1[tid + o]; s2[tid] = fmax(s2[tid], s2[tid + o]); }
+        __syncthreads();
+    }
+    if (tid == 0) { part[3 * blockIdx.x] = s0[0]; part[3 * blockIdx.x + 1] = s1[0]; part[3 * blockIdx.x + 2] = s2[0]; }
+}
+
+extern "C" int qb200_gemul_error_batched(const qb_gemul_plan *plan, const void *A, const void *B, const void *C, uint64_t batch,
+                                         qb_err_stats *stats, const qb_exec *exec)
+{
+    if (!plan || !A || !B || !C || !stats) return fail(QB_EINVAL, "null argument");
+    if (wants_all_devices(exec)) return fail(QB_EINVAL, "error statistics run on one device (reduce per device and add the sums)");
+    auto ce = get_gemul(*plan);
+    if (ce->an.status) return fail(ce->an.status, ce->an.err);
+    const GemulProg &gp = ce->prog;
+    if (width(plan->a) + width(plan->b) > 53) return fail(QB_EDOMAIN, "operand products do not fit a float64 mantissa");
+    if (plan->stride_a < 0 || plan->stride_b < 0 || plan->stride_c < (int64_t)((uint64_t)plan->M * plan->N)) return fail(QB_EINVAL, "bad batch strides");
+    const uint64_t ea = (uint64_t)plan->M * plan->K, eb = (uint64_t)plan->K * plan->N, ec = (uint64_t)plan->M * plan->N;
+    memset(stats, 0, sizeof(*stats));
+    stats->n = batch * ec;
+    if (batch == 0) return QB_OK;
+    Ctx cx; int rc = cx.init(exec); if (rc) return rc;
+    const size_t bytes_a = span_elems(batch, plan->stride_a, ea) * gp.a_wb, bytes_b = span_elems(batch, plan->stride_b, eb) * gp.b_wb,
+                 bytes_c = span_elems(batch, plan->stride_c, ec) * gp.c_wb;
+    const void *dA, *dB, *dC;
+    if ((rc = cx.in(A, bytes_a, &dA)) || (rc = cx.in(B, bytes_b, &dB)) || (rc = cx.in(C, bytes_c, &dC))) return rc;
+    GemulShape S = shape_of(plan->M, plan->N, plan->K, plan->trans_a, plan->trans_b, gp.a_wb, gp.b_wb, gp.c_wb, plan->stride_a, plan->stride_b, plan->stride_c);
+    const size_t smem = (ea + eb) * sizeof(double);
+    void *part, *res;
+    if ((rc = cx.alloc(&res, 3 * 8))) return rc;
+    int nblocks = 0;
+    if (plan->M % 4 == 0 && plan->N % 4 == 0 && smem <= 200 * 1024) {
+        int dev = 0, sms = 0, per_sm = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        CUDA_TRY(cudaFuncSetAttribute(k_gemul_err_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gemul_err_f64, 256, smem));
+        const uint64_t cap = (uint64_t)sms * (per_sm > 0 ? per_sm : 1);
+        nblocks = (int)(batch < cap ? batch : cap);
+        if ((rc = cx.alloc(&part, 3 * (size_t)nblocks * 8))) return rc;
+        k_gemul_err_f64<<<nblocks, 256, smem, cx.stream>>>(dA, dB, dC, batch, S, plan->a.frac_bits, plan->b.frac_bits, plan->c.frac_bits, (double *)part);
+        if ((rc = post_launch("k_gemul_err_f64"))) return rc;
+    } else {
+        // other shapes: the float64 reference through the one-thread-per-output kernel, then the streaming comparison
+        void *ref;
+        nblocks = 1184;
+        if (plan->stride_c != (int64_t)ec) return fail(QB_EINVAL, "padded C batches need M, N multiples of 4 here");
+        if ((rc = cx.alloc(&ref, batch * ec * sizeof(double))) || (rc = cx.alloc(&part, 3 * (size_t)nblocks * 8))) return rc;
+        GemulShape S64 = S; S64.c_wb = 8;
+        const uint64_t blocks = (batch * ec + 127) / 128;
+        if (blocks > 0x7fffffffull) return fail(QB_EINVAL, "too many outputs for one launch");
+        k_gemul_f64<<<(unsigned)blocks, 128, 0, cx.stream>>>(dA, dB, (double *)ref, batch, S64, plan->a.frac_bits, plan->b.frac_bits);
+        if ((rc = post_launch("k_gemul_f64"))) return rc;
+        k_err_stats<<<nblocks, 256, 0, cx.stream>>>(dC, (const double *)ref, batch * ec, gp.c_wb, plan->c.frac_bits, (double *)part);
+        if ((rc = post_launch("k_err_stats"))) return rc;
+    }
+    k_err_final<<<1, 256, 0, cx.stream>>>((const double *)part, nblocks, (double *)res);
+    if ((rc = post_launch("k_err_final"))) return rc;
+    double h[3];
+    CUDA_TRY(cudaMemcpyAsync(h, res, sizeof(h), cudaMemcpyDeviceToHost, cx.stream));
+    CUDA_TRY(cudaStreamSynchronize(cx.stream));
+    stats->sum_sq_err = h[0]; stats->sum_sq_ref = h[1]; stats->max_abs_err = h[2];
+    return cx.finish();
+}
+
+// ---------------------------------------------------------------------------------------------
 // device-resident shards on several GPUs in one call, and the optional output all-gather over NVLink
 // ---------------------------------------------------------------------------------------------
 extern "C" int qb200_gemul_sharded(const qb_gemul_plan *plan, const qb_shard *shards, uint32_t n_shards, const qb_exec *exec)

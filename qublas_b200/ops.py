@@ -377,6 +377,30 @@ def error_stats(w, ref, t: QType):
     return {"sqnr_db": sqnr, "max_abs_err": st.max_abs_err, "sum_sq_err": st.sum_sq_err, "sum_sq_ref": st.sum_sq_ref, "n": st.n}
 
 
+def gemul_f64(A, B, plan: abi.qb_gemul_plan, batch: int = 1):
+    """float64 GEMM of the dequantized operands of a real Qgemul plan (batch x M x N doubles, column-major)."""
+    n = batch * plan.M * plan.N
+    if _is_torch(A):
+        import torch
+        out = torch.empty(n, dtype=torch.float64, device=A.device)
+    else:
+        out = np.empty(n, dtype=np.float64)
+    ex = _exec_for(A, B, out)
+    abi.check(abi.load().qb200_gemul_f64_batched(C.byref(plan), _ptr(A), _ptr(B), _ptr(out), batch, C.byref(ex)))
+    return out
+
+
+def gemul_error(Cbuf, A, B, plan: abi.qb_gemul_plan, batch: int = 1):
+    """Error statistics of quantized results against the float64 GEMM of the dequantized operands, in one pass on the device
+    (qb200_gemul_error_batched): nothing but the sums comes back."""
+    import math
+    st = abi.qb_err_stats()
+    ex = _exec_for(Cbuf, A, B)
+    abi.check(abi.load().qb200_gemul_error_batched(C.byref(plan), _ptr(A), _ptr(B), _ptr(Cbuf), batch, C.byref(st), C.byref(ex)))
+    sqnr = float("inf") if st.sum_sq_err == 0 else 10.0 * math.log10(st.sum_sq_ref / st.sum_sq_err)
+    return {"sqnr_db": sqnr, "max_abs_err": st.max_abs_err, "sum_sq_err": st.sum_sq_err, "sum_sq_ref": st.sum_sq_ref, "n": st.n}
+
+
 def synth_fill(out, lo: int, hi: int, seed: int, stream_id: int, first_index: int = 0):
     """Counter-based synthetic raw words, uniform over [lo, hi]."""
     n = out.numel() if _is_torch(out) else out.size

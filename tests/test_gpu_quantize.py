@@ -91,3 +91,39 @@ def test_error_stats_of_a_quantized_gemul_vs_float64():
     assert 40.0 < st["sqnr_db"] < 120.0 and st["n"] == batch * 4096
     again = ops.error_stats(Cq, ref, c)
     assert again["sum_sq_err"] == st["sum_sq_err"]                         # fixed reduction order: reproducible
+
+
+@pytest.mark.parametrize("M,N,K,ta,tb,wb", [(64, 64, 64, False, False, 0), (32, 48, 40, True, False, 0), (16, 8, 24, False, True, 2), (10, 6, 12, False, False, 0),
+                                             (64, 64, 64, True, True, 2)])
+def test_gemul_error_in_one_pass_equals_reference_gemm_plus_error_stats(M, N, K, ta, tb, wb):
+    """qb200_gemul_error_batched (the accuracy sweep in one pass: the float64 reference of each instance lives in registers)
+    against the two-step path -- qb200_gemul_f64_batched + qb200_error_stats -- and against numpy: the same reference values
+    (same k-ascending FMA chain), sums equal up to the summation order, the maximum error exactly; host and device memory;
+    int16 words; a shape that is not a multiple of 4 (falls back to the two kernels inside the same call)."""
+    from qublas_b200.qtypes import RND_CONV, RND_POS_INF
+    a = QType(7, 8); mul = QType(14, 8, True, RND_CONV, SAT_TCPL)
+    nl = max(1, (K - 1).bit_length())
+    lv = [QType(15 + l, 8, True, RND_POS_INF, SAT_TCPL) for l in range(nl)]
+    c = QType(17, 4, True, RND_POS_INF, SAT_TCPL)
+    plan = ops.make_gemul_plan(a, a, c, M, N, K, mul=mul, add=lv, trans_a=ta, trans_b=tb, word_bytes=(wb, wb, 0))
+    batch = 37
+    rng = np.random.default_rng(M * N + K)
+    dt = np.int16 if wb == 2 else np.int32
+    A = rng.integers(a.raw_min, a.raw_max + 1, size=batch * M * K).astype(dt); B = rng.integers(a.raw_min, a.raw_max + 1, size=batch * K * N).astype(dt)
+    dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    Cq = torch.empty(batch * M * N, dtype=torch.int32, device="cuda")
+    ops.Qgemul(Cq, dA, dB, plan, batch=batch)
+    one = ops.gemul_error(Cq, dA, dB, plan, batch=batch)
+    ref = ops.gemul_f64(dA, dB, plan, batch=batch)
+    two = ops.error_stats(Cq, ref, c)
+    assert one["n"] == batch * M * N and one["max_abs_err"] == two["max_abs_err"]
+    assert abs(one["sum_sq_err"] - two["sum_sq_err"]) <= 1e-12 * two["sum_sq_err"] and abs(one["sum_sq_ref"] - two["sum_sq_ref"]) <= 1e-12 * two["sum_sq_ref"]
+    # numpy yardstick (exact: every partial sum is far below 2^53)
+    Am = A.astype(np.float64).reshape(batch, M, K) if ta else A.astype(np.float64).reshape(batch, K, M).transpose(0, 2, 1)
+    Bm = B.astype(np.float64).reshape(batch, K, N) if tb else B.astype(np.float64).reshape(batch, N, K).transpose(0, 2, 1)
+    want = (Am @ Bm).transpose(0, 2, 1).reshape(-1) * 2.0 ** (-2 * a.f)
+    err = Cq.cpu().numpy().astype(np.float64) * 2.0 ** (-c.f) - want
+    assert one["max_abs_err"] == np.abs(err).max() and abs(one["sum_sq_err"] - (err * err).sum()) <= 1e-11 * (err * err).sum()
+    # reproducible, and the same from host memory
+    assert ops.gemul_error(Cq, dA, dB, plan, batch=batch) == one
+    assert ops.gemul_error(Cq.cpu().numpy(), A, B, plan, batch=batch) == one
