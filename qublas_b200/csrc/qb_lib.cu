@@ -131,13 +131,19 @@ struct Ctx {
 // asynchronous; with pageable memory the runtime stages them and the overlap is partial.
 // ---------------------------------------------------------------------------------------------
 struct HostPipe {
-    static constexpr int NS = 3;
+    static constexpr int NS = 6;           // slots created; slots() of them are used (QB200_PIPE_SLOTS, default 3)
     std::mutex mu;
     bool ready = false;
     cudaStream_t st[NS];
     cudaEvent_t done[NS];
-    char *buf[NS] = { nullptr, nullptr, nullptr };
-    size_t cap[NS] = { 0, 0, 0 };
+    char *buf[NS] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    size_t cap[NS] = { 0, 0, 0, 0, 0, 0 };
+    static int slots()
+    {
+        static int n = 0;
+        if (!n) { const char *e = getenv("QB200_PIPE_SLOTS"); const int v = e ? atoi(e) : 0; n = (v >= 2 && v <= NS) ? v : 3; }
+        return n;
+    }
     char *shared = nullptr; size_t shared_cap = 0;
     int init()
     {
@@ -189,7 +195,7 @@ static int host_pipeline(int nin, const PipeIn *ins, char *out, size_t out_unit_
     if (cu > units) cu = units;
     size_t slot_bytes = al(cu * out_unit_bytes);
     for (int i = 0; i < nin; i++) if (!ins[i].shared) slot_bytes += al(cu * ins[i].unit_bytes);
-    for (int s = 0; s < HostPipe::NS; s++) if ((rc = hp.ensure(&hp.buf[s], &hp.cap[s], slot_bytes))) return rc;
+    for (int s = 0; s < HostPipe::slots(); s++) if ((rc = hp.ensure(&hp.buf[s], &hp.cap[s], slot_bytes))) return rc;
     const void *dins[8];
     if (shared_total) {
         if ((rc = hp.ensure(&hp.shared, &hp.shared_cap, shared_total))) return rc;
@@ -202,7 +208,7 @@ static int host_pipeline(int nin, const PipeIn *ins, char *out, size_t out_unit_
     }
     uint64_t first = 0;
     for (uint64_t it = 0; first < units; ++it, first += cu) {
-        const int s = (int)(it % HostPipe::NS);
+        const int s = (int)(it % HostPipe::slots());
         const uint64_t n = units - first < cu ? units - first : cu;
         cudaStream_t st = hp.st[s];
         size_t off = 0;
@@ -214,7 +220,7 @@ static int host_pipeline(int nin, const PipeIn *ins, char *out, size_t out_unit_
         if ((rc = launch(dins, dout, n, st))) return rc;
         CUDA_TRY(cudaMemcpyAsync(out + first * out_unit_bytes, dout, n * out_unit_bytes, cudaMemcpyDeviceToHost, st));
     }
-    for (int s = 0; s < HostPipe::NS; s++) CUDA_TRY(cudaStreamSynchronize(hp.st[s]));
+    for (int s = 0; s < HostPipe::slots(); s++) CUDA_TRY(cudaStreamSynchronize(hp.st[s]));
     return QB_OK;
 }
 
