@@ -262,6 +262,12 @@ int qb200_poly_plan_info(const qb_poly_plan *plan, qb_plan_info *info);
 int qb200_poly_batched(const qb_poly_plan *plan, const void *x, void *out, uint64_t batch, const qb_exec *exec);
 int qb200_gemul_poly_batched(const qb_gemul_plan *gemul, const qb_poly_plan *poly, const void *A, const void *B, void *C,
                              uint64_t batch, const qb_exec *exec);
+/* The polynomial as a PROLOGUE: applied to the elements of operand A and / or B before the products
+ * (Qgemul(C, ANUS::Qapprox<...>(A), B) evaluated without materialising the operand).  poly_a / poly_b may be NULL; a
+ * polynomial's result type must equal the plan's operand type, its x words have the operand's word size.  One launch with the
+ * run-time specialised kernels (the polynomial runs as the operand is staged), otherwise the polynomial runs into a scratch copy. */
+int qb200_gemul_prologue_batched(const qb_gemul_plan *gemul, const qb_poly_plan *poly_a, const qb_poly_plan *poly_b, const void *A, const void *B,
+                                 void *C, uint64_t batch, const qb_exec *exec);
 int qb200_table_batched(const qb_qdesc *x, const qb_qdesc *out_type, const void *table, const void *in, void *out, uint64_t n,
                         const qb_exec *exec);
 
@@ -318,7 +324,8 @@ int qb200_measure_int_peak(double fma_share, double *tera_ops_per_s, const qb_ex
 int qb200_jit_check_gemul(const qb_gemul_plan *plan, char *log, uint64_t log_cap);
 /* The same check for the other run-time specialised kernel templates (no device needed).
  * what: 1 = qb_cgemul_plan, 2 = qb_reduce_plan, 3 = qb_tfcmul_plan, 4 = qb_ew_plan, 5 = qb_convert_plan, 6 = qb_poly_plan,
- * 7 = struct { qb_gemul_plan; qb_poly_plan; } (Qgemul with the polynomial fused into its store).
+ * 7 = struct { qb_gemul_plan; qb_poly_plan; } (Qgemul with the polynomial fused into its store), 8 = the same pair with the
+ * polynomial fused into the loads of both operands.
  * Returns 0 = cubin produced, 1 = no template applies to this plan, -1 = NVRTC failed (log filled), < -1 = plan error. */
 int qb200_jit_check(int what, const void *plan, char *log, uint64_t log_cap);
 

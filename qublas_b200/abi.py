@@ -147,7 +147,7 @@ ABI_SYMBOLS = [
     "qb200_launch_count_reset", "qb200_reduce_plan_info", "qb200_gemul_plan_info", "qb200_cgemul_plan_info",
     "qb200_reduce_batched", "qb200_gemul_batched", "qb200_cgemul_batched", "qb200_tfcmul_batched",
     "qb200_convert_batched", "qb200_elementwise_batched", "qb200_synth_fill", "qb200_shard_range", "qb200_measure_int_peak", "qb200_jit_check_gemul", "qb200_jit_check", "qb200_quantize_f64", "qb200_dequantize_f64", "qb200_error_stats",
-    "qb200_selftest_fp", "qb200_gemul_f64_batched", "qb200_gemul_error_batched", "qb200_host_alloc", "qb200_host_free", "qb200_device_alloc", "qb200_device_free", "qb200_memcpy", "qb200_gemul_sharded", "qb200_allgather",
+    "qb200_selftest_fp", "qb200_gemul_f64_batched", "qb200_gemul_error_batched", "qb200_gemul_prologue_batched", "qb200_host_alloc", "qb200_host_free", "qb200_device_alloc", "qb200_device_free", "qb200_memcpy", "qb200_gemul_sharded", "qb200_allgather",
     "qb200_poly_plan_info", "qb200_poly_batched", "qb200_gemul_poly_batched", "qb200_table_batched",
 ]
 
@@ -203,6 +203,7 @@ def load() -> C.CDLL:
     L.qb200_poly_plan_info.argtypes = [C.POINTER(qb_poly_plan), C.POINTER(qb_plan_info)]
     L.qb200_poly_batched.argtypes = [C.POINTER(qb_poly_plan), vp, vp, u64, C.POINTER(qb_exec)]
     L.qb200_gemul_poly_batched.argtypes = [C.POINTER(qb_gemul_plan), C.POINTER(qb_poly_plan), vp, vp, vp, u64, C.POINTER(qb_exec)]
+    L.qb200_gemul_prologue_batched.argtypes = [C.POINTER(qb_gemul_plan), C.POINTER(qb_poly_plan), C.POINTER(qb_poly_plan), vp, vp, vp, u64, C.POINTER(qb_exec)]
     L.qb200_table_batched.argtypes = [C.POINTER(qb_qdesc), C.POINTER(qb_qdesc), vp, vp, vp, u64, C.POINTER(qb_exec)]
     L.qb200_selftest_fp.argtypes = [C.c_int, C.c_void_p, C.POINTER(u64), C.POINTER(u64), C.POINTER(qb_exec)]
     for name in ABI_SYMBOLS:

@@ -52,12 +52,14 @@ std::string emit_polyprog(const PolyProg &P)
     o << "    }}";
     return o.str();
 }
-static std::string emit_epilogue(const PolyProg *epi)
+static std::string emit_epilogue(const PolyProg *epi, const PolyProg *pro_a = nullptr, const PolyProg *pro_b = nullptr)
 {
     PolyProg z; memset(&z, 0, sizeof(z));
     std::ostringstream o;
-    o << "  static constexpr bool EPI = " << (epi ? "true" : "false") << ";\n";
+    o << "  static constexpr bool EPI = " << (epi ? "true" : "false") << ", PRO_A = " << (pro_a ? "true" : "false") << ", PRO_B = " << (pro_b ? "true" : "false") << ";\n";
     o << "  static constexpr __host__ __device__ qb::PolyProg poly() { return " << emit_polyprog(epi ? *epi : z) << "; }\n";
+    o << "  static constexpr __host__ __device__ qb::PolyProg poly_a() { return " << emit_polyprog(pro_a ? *pro_a : z) << "; }\n";
+    o << "  static constexpr __host__ __device__ qb::PolyProg poly_b() { return " << emit_polyprog(pro_b ? *pro_b : z) << "; }\n";
     return o.str();
 }
 // batch strides of the plan (in elements), baked into the tag: a kernel is specialised per plan anyway
@@ -116,7 +118,7 @@ uint64_t gemul_tile_smem(const qb_gemul_plan &p, const GemulProg &g, int group, 
     return total <= limit ? total : 0;
 }
 
-std::string emit_gemul_cfg(const std::string &name, const qb_gemul_plan &p, const GemulProg &g, int group, const PolyProg *epi)
+std::string emit_gemul_cfg(const std::string &name, const qb_gemul_plan &p, const GemulProg &g, int group, const PolyProg *epi, const PolyProg *pro_a, const PolyProg *pro_b)
 {
     std::ostringstream o;
     o << "struct " << name << " {\n";
@@ -151,13 +153,13 @@ std::string emit_gemul_cfg(const std::string &name, const qb_gemul_plan &p, cons
         const Ival ra = type_range(p.a), rb = type_range(p.b);           // operand types' own bounds (32-bit register class: they fit)
         o << "  static constexpr long long A_LO = " << (long long)ra.lo << "LL, A_HI = " << (long long)ra.hi << "LL, B_LO = " << (long long)rb.lo << "LL, B_HI = " << (long long)rb.hi << "LL;\n";
     }
-    o << emit_epilogue(epi);
+    o << emit_epilogue(epi, pro_a, pro_b);
     o << "};\n";
     return o.str();
 }
 
 // Tag struct for the thread-per-output template (qb_fast_gemul_thread.cuh): any shape, both forms, transposes.
-std::string emit_gemul_thread_cfg(const std::string &name, const qb_gemul_plan &p, const GemulProg &g, int bits, const PolyProg *epi)
+std::string emit_gemul_thread_cfg(const std::string &name, const qb_gemul_plan &p, const GemulProg &g, int bits, const PolyProg *epi, const PolyProg *pro_a, const PolyProg *pro_b)
 {
     std::ostringstream o;
     unsigned nlev = 0;
@@ -178,7 +180,7 @@ std::string emit_gemul_thread_cfg(const std::string &name, const qb_gemul_plan &
         o << "      qb::FlushStep{" << (unsigned)f.kind << "," << (unsigned)f.slot << ",{0,0,0,0,0,0}," << emit_addstage(f.a) << "},\n";
     }
     o << "    };\n    return t[i];\n  }\n";
-    o << emit_epilogue(epi);
+    o << emit_epilogue(epi, pro_a, pro_b);
     o << "};\n";
     return o.str();
 }

@@ -14,8 +14,8 @@ std::string emit_qstage(const QStage &q);
 std::string emit_addstage(const AddStage &a);
 // group = instances a CTA of the register-tile template works on at a time (1 unless the instance is small)
 // epi: ANUS polynomial applied to every result element before it is stored (fused epilogue), or nullptr
-std::string emit_gemul_cfg(const std::string &name, const qb_gemul_plan &p, const GemulProg &g, int group = 1, const PolyProg *epi = nullptr);
-std::string emit_gemul_thread_cfg(const std::string &name, const qb_gemul_plan &p, const GemulProg &g, int arith_bits, const PolyProg *epi = nullptr);
+std::string emit_gemul_cfg(const std::string &name, const qb_gemul_plan &p, const GemulProg &g, int group = 1, const PolyProg *epi = nullptr, const PolyProg *pro_a = nullptr, const PolyProg *pro_b = nullptr);
+std::string emit_gemul_thread_cfg(const std::string &name, const qb_gemul_plan &p, const GemulProg &g, int arith_bits, const PolyProg *epi = nullptr, const PolyProg *pro_a = nullptr, const PolyProg *pro_b = nullptr);
 std::string emit_polyprog(const PolyProg &P);
 std::string emit_poly_cfg(const std::string &name, const PolyProg &prog, int xw, int ow, int arith_bits);
 std::string emit_reduce_cfg(const std::string &name, const qb_reduce_plan &p, const ReduceProg &r);

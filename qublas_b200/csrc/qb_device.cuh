@@ -207,6 +207,11 @@ QB_DEV I poly_ct(I x)
     else return (int64_t)x < Cfg::poly().seg[S].below ? poly_seg_ct<Cfg, I, S>(x) : poly_ct<Cfg, I, S + 1>(x);
 }
 
+// the polynomial fused into the LOADS of a Qgemul operand (Cfg::PRO_A / PRO_B: ANUS::Qpoly / Qapprox as a prologue)
+template <class Cfg, int WHICH> struct PolySel {
+    static constexpr __host__ __device__ PolyProg poly() { if constexpr (WHICH == 1) return Cfg::poly_a(); else return Cfg::poly_b(); }
+};
+
 // Qmul through the FP32 FMA pipe (see qb_codegen.cpp:fp_mul_ok): fma(a, b, 1.5 * 2^(23+S)) is the exact product
 // plus ONE IEEE rounding at ulp 2^S, i.e. the rounded right shift by S (round-to-nearest-even == RND::CONV,
 // round toward -inf == TRN::TCPL).  Returns the quantized product BIASED by the constant's bit pattern

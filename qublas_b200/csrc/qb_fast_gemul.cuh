@@ -69,7 +69,8 @@ struct GemulTile {
     static constexpr FpSubst SUB = fp_subst(Cfg::FP_MUL, Cfg::FP_SHIFT, Cfg::mul(), Cfg::A_LO, Cfg::A_HI, Cfg::B_LO, Cfg::B_HI);
     static constexpr bool SUBST = SUB.ok;
     static constexpr bool DYN = !SUBST && (Cfg::mul().need_lo || Cfg::mul().need_hi) && (Cfg::mul().of == SAT_TCPL || Cfg::mul().of == SAT_SMGN);
-    static constexpr bool PASS = DYN || Cfg::FP_MUL || NARROW;
+    static constexpr bool PRO = Cfg::PRO_A || Cfg::PRO_B;       // ANUS polynomial applied to an operand as it is staged (prologue)
+    static constexpr bool PASS = DYN || Cfg::FP_MUL || NARROW || PRO;
     // SEP: the pass writes a separate single-buffered 32-bit copy (the host grants it when shared memory allows) instead of
     // converting in place; only then can the copy be laid out differently from the staged instance (swizzles below).
     static constexpr bool SEP = PASS && Cfg::SEP;
@@ -542,7 +543,7 @@ QB_DEV void gemul_tile_body(const typename Cfg::WA *__restrict__ A, const typena
         const uint64_t next = inst + gridDim.x;
         if constexpr (T::NSTAGE == 2) {
             if (tid == 0 && next < ngroups) {
-                if constexpr (PASS && Cfg::FP_MUL) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // in-place int->float writes (generic proxy) before the TMA refill
+                if constexpr (PASS && (Cfg::FP_MUL || T::PRO)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // in-place int->float / prologue writes (generic proxy) before the TMA refill
                 issue(next, s ^ 1);                               // stage s^1 was released by the barrier that ended the previous iteration
             }
         }
@@ -558,6 +559,16 @@ QB_DEV void gemul_tile_body(const typename Cfg::WA *__restrict__ A, const typena
             auto scan4 = [&](int part, const int4 &v) {
                 if constexpr (TRACK_LO) lo[part] = min3i(min3i(lo[part], v.x, v.y), v.z, v.w);      // two VIMNMX3 per four words
                 if constexpr (TRACK_HI) hi[part] = max3i(max3i(hi[part], v.x, v.y), v.z, v.w);
+            };
+            auto pro4 = [&](int part, int4 &v) {                                 // fused ANUS prologue on the raw words of an operand
+                if constexpr (Cfg::PRO_A) if (part == 0) {
+                    v.x = (int)poly_ct<PolySel<Cfg, 1>, I>((I)v.x); v.y = (int)poly_ct<PolySel<Cfg, 1>, I>((I)v.y);
+                    v.z = (int)poly_ct<PolySel<Cfg, 1>, I>((I)v.z); v.w = (int)poly_ct<PolySel<Cfg, 1>, I>((I)v.w);
+                }
+                if constexpr (Cfg::PRO_B) if (part == 1) {
+                    v.x = (int)poly_ct<PolySel<Cfg, 2>, I>((I)v.x); v.y = (int)poly_ct<PolySel<Cfg, 2>, I>((I)v.y);
+                    v.z = (int)poly_ct<PolySel<Cfg, 2>, I>((I)v.z); v.w = (int)poly_ct<PolySel<Cfg, 2>, I>((I)v.w);
+                }
             };
             auto put4 = [&](int part, int4 *w, int i, const int4 &v) {          // i = 16-byte chunk index within the part
                 const bool swz = part ? T::SWZ_B : T::SWZ_A;
@@ -580,8 +591,9 @@ QB_DEV void gemul_tile_body(const typename Cfg::WA *__restrict__ A, const typena
                     const int n8 = (part ? T::G * T::B_WORDS : T::G * T::A_WORDS) / 8;
                     for (int i = tid; i < n8; i += T::BLOCK) {
                         const int4 v = raw[i];
-                        const int4 e0 = make_int4((int)(short)(v.x & 0xffff), v.x >> 16, (int)(short)(v.y & 0xffff), v.y >> 16);
-                        const int4 e1 = make_int4((int)(short)(v.z & 0xffff), v.z >> 16, (int)(short)(v.w & 0xffff), v.w >> 16);
+                        int4 e0 = make_int4((int)(short)(v.x & 0xffff), v.x >> 16, (int)(short)(v.y & 0xffff), v.y >> 16);
+                        int4 e1 = make_int4((int)(short)(v.z & 0xffff), v.z >> 16, (int)(short)(v.w & 0xffff), v.w >> 16);
+                        pro4(part, e0); pro4(part, e1);
                         scan4(part, e0); scan4(part, e1);
                         put4(part, w, 2 * i, e0); put4(part, w, 2 * i + 1, e1);
                     }
@@ -598,13 +610,14 @@ QB_DEV void gemul_tile_body(const typename Cfg::WA *__restrict__ A, const typena
 #pragma unroll
                         for (int u = 0; u < PER; ++u) {
                             const int i = tid + u * T::BLOCK;
-                            if (i < n4) { scan4(part, v[u]); if constexpr (T::SEP || Cfg::FP_MUL) put4(part, w, i, v[u]); }
+                            if (i < n4) { pro4(part, v[u]); scan4(part, v[u]); if constexpr (T::SEP || Cfg::FP_MUL || T::PRO) put4(part, w, i, v[u]); }
                         }
                     } else {
                         for (int i = tid; i < n4; i += T::BLOCK) {
-                            const int4 v = raw[i];
+                            int4 v = raw[i];
+                            pro4(part, v);
                             scan4(part, v);
-                            if constexpr (T::SEP || Cfg::FP_MUL) put4(part, w, i, v);
+                            if constexpr (T::SEP || Cfg::FP_MUL || T::PRO) put4(part, w, i, v);
                         }
                     }
                 }

@@ -60,7 +60,10 @@ QB_DEV void gemul_thread_body(const typename Cfg::WA *__restrict__ A, const type
     auto leaf = [&](uint32_t k) -> I {
         const uint32_t ia = Cfg::TRANS_A ? (k + i * K) : (i + k * M);                 // column-major, QuBLAS.h:2680-2692
         const uint32_t ib = Cfg::TRANS_B ? (j + k * N) : (k + j * K);
-        return mul_apply<I, true>((I)__ldg(a + ia), (I)__ldg(b + ib), mulq);
+        I av = (I)__ldg(a + ia), bv = (I)__ldg(b + ib);
+        if constexpr (Cfg::PRO_A) av = poly_ct<PolySel<Cfg, 1>, I>(av);      // fused ANUS prologue (qb200_gemul_prologue_batched)
+        if constexpr (Cfg::PRO_B) bv = poly_ct<PolySel<Cfg, 2>, I>(bv);
+        return mul_apply<I, true>(av, bv, mulq);
     };
     I st[Cfg::NLEV + 1];
     if constexpr (K <= 64) {

@@ -32,7 +32,9 @@ struct JitKernel {
 bool jit_enabled();
 // Each returns nullptr when the plan does not fit the template or when compilation fails.
 // epi: ANUS polynomial fused into the store of every result element (nullptr: none)
-std::shared_ptr<JitKernel> jit_gemul(const qb_gemul_plan &p, const GemulProg &g, int arith_bits, const PolyProg *epi = nullptr);
+// pro_a / pro_b: ANUS polynomial fused into the loads of operand A / B (nullptr: none)
+std::shared_ptr<JitKernel> jit_gemul(const qb_gemul_plan &p, const GemulProg &g, int arith_bits, const PolyProg *epi = nullptr, const PolyProg *pro_a = nullptr,
+                                     const PolyProg *pro_b = nullptr);
 std::shared_ptr<JitKernel> jit_gemul_thread(const qb_gemul_plan &p, const GemulProg &g, int arith_bits);   // thread-per-output template only
 std::shared_ptr<JitKernel> jit_poly(const PolyProg &prog, int xw, int ow, int arith_bits);
 std::shared_ptr<JitKernel> jit_cgemul(const qb_cgemul_plan &p, const CGemulProg &g, int arith_bits);

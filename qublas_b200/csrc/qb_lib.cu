@@ -1013,6 +1013,19 @@ extern "C" int qb200_jit_check(int what, const void *plan, char *log, uint64_t l
             if (ce->bits == 32) sanitize32(prog);
             run([&] { jit_gemul(pr.g, ce->prog, ce->bits, &prog); });
         }
+    } else if (what == 8) {
+        // Qgemul with the polynomial fused into the loads of both operands: plan = { qb_gemul_plan, qb_poly_plan } back to back
+        struct Pair { qb_gemul_plan g; qb_poly_plan p; };
+        const Pair &pr = *(const Pair *)plan;
+        PolyProg prog; qb_qdesc ot; Analysis an;
+        if (compile_poly(pr.p, &prog, &ot, an)) return fail(an.status, an.err);
+        auto ce = get_gemul(pr.g);
+        if (ce->an.status) return fail(ce->an.status, ce->an.err);
+        if (arith_bits(an) > ce->bits) { rc = 1; }
+        else {
+            if (ce->bits == 32) sanitize32(prog);
+            run([&] { jit_gemul(pr.g, ce->prog, ce->bits, nullptr, &prog, &prog); });
+        }
     } else {
         return fail(QB_EINVAL, "unknown plan kind");
     }
@@ -1361,6 +1374,73 @@ extern "C" int qb200_gemul_poly_batched(const qb_gemul_plan *gemul, const qb_pol
             if ((rc = launch_poly(prog, arith_bits(an), ci, ci, ec, xw, ow, cx.stream))) return rc;
         }
     }
+    if ((rc = cx.out_done(C, bytes_c, dC))) return rc;
+    return cx.finish();
+}
+
+// The polynomial applied to an OPERAND of Qgemul before the products (Qgemul(C, Qapprox(A), B): the reference evaluates the
+// tensor expression element by element, QuBLAS.h:4829-4897 into :3146-3171).  poly_a / poly_b may be NULL; a polynomial's
+// result type must be the operand type of the plan (gemul->a / gemul->b), the caller's buffer holds raw words of the
+// polynomial's x type in words of the same size.  Fused: the run-time specialised Qgemul kernels apply it as the operand is
+// staged (register tiles: once per element, in the conversion pass) or loaded (thread per output); otherwise the polynomial
+// runs as its own launch into a scratch copy of the operand.
+extern "C" int qb200_gemul_prologue_batched(const qb_gemul_plan *gemul, const qb_poly_plan *poly_a, const qb_poly_plan *poly_b, const void *A, const void *B,
+                                            void *C, uint64_t batch, const qb_exec *exec)
+{
+    if (!gemul || !A || !B || !C) return fail(QB_EINVAL, "null argument");
+    if (!poly_a && !poly_b) return qb200_gemul_batched(gemul, A, B, C, batch, exec);
+    if (exec && exec->device == QB_DEVICE_ALL) return fail(QB_EINVAL, "QB_DEVICE_ALL is not supported by the fused call: shard the batch and pass one device per call");
+    auto ce = get_gemul(*gemul);
+    if (ce->an.status) return fail(ce->an.status, ce->an.err);
+    const GemulProg &gp = ce->prog;
+    PolyProg prog[2]; Analysis an[2]; int pbits = 32;
+    const qb_poly_plan *pp[2] = { poly_a, poly_b };
+    const qb_qdesc *want[2] = { &gemul->a, &gemul->b };
+    const int wb[2] = { gp.a_wb, gp.b_wb };
+    int rc;
+    for (int i = 0; i < 2; i++) if (pp[i]) {
+        qb_qdesc ot;
+        if ((rc = poly_setup(pp[i], &prog[i], &ot, an[i]))) return rc;
+        if (ot.int_bits != want[i]->int_bits || ot.frac_bits != want[i]->frac_bits || ot.is_signed != want[i]->is_signed)
+            return fail(QB_EINVAL, "the polynomial's result type must be the operand type of the Qgemul plan");
+        if (word_bytes(pp[i]->x) != wb[i] || word_bytes(ot) != wb[i]) return fail(QB_EINVAL, "the polynomial's x words and the operand words must have the same size");
+        pbits = std::max(pbits, arith_bits(an[i]));
+    }
+    if (gemul->stride_a < 0 || gemul->stride_b < 0 || gemul->stride_c < (int64_t)((uint64_t)gemul->M * gemul->N)) return fail(QB_EINVAL, "bad batch strides");
+    if (batch == 0) return QB_OK;
+    Ctx cx; if ((rc = cx.init(exec))) return rc;
+    const uint64_t ea = (uint64_t)gemul->M * gemul->K, eb = (uint64_t)gemul->K * gemul->N, ec = (uint64_t)gemul->M * gemul->N;
+    const uint64_t na = span_elems(batch, gemul->stride_a, ea), nb = span_elems(batch, gemul->stride_b, eb);
+    const size_t bytes_c = span_elems(batch, gemul->stride_c, ec) * gp.c_wb;
+    const void *dA, *dB; void *dC;
+    if ((rc = cx.in(A, na * gp.a_wb, &dA)) || (rc = cx.in(B, nb * gp.b_wb, &dB)) || (rc = cx.out(C, bytes_c, &dC))) return rc;
+    const bool tc = !(cx.flags & QB_F_NO_TENSOR_CORE) && ce->tc;
+    const bool aligned16 = !(((uintptr_t)dA | (uintptr_t)dB | (uintptr_t)dC) & 15);
+    if (!tc && !(cx.flags & QB_F_NO_SPECIALIZE) && aligned16 && pbits <= ce->bits) {
+        struct Key { qb_gemul_plan g; qb_poly_plan a, b; uint32_t has_a, has_b; } key;
+        memset(&key, 0, sizeof(key)); key.g = *gemul; key.has_a = poly_a != nullptr; key.has_b = poly_b != nullptr;
+        if (poly_a) { key.a = *poly_a; key.a.len = 0; }
+        if (poly_b) { key.b = *poly_b; key.b.len = 0; }
+        PolyProg pe[2] = { prog[0], prog[1] };
+        if (ce->bits == 32) { if (poly_a) sanitize32(pe[0]); if (poly_b) sanitize32(pe[1]); }
+        JitKernel *jk = cached<Key, EwC>(key, [](EwC &) {})->jit.get([&] { return jit_gemul(*gemul, gp, ce->bits, nullptr, poly_a ? &pe[0] : nullptr, poly_b ? &pe[1] : nullptr); });
+        if (jk) {
+            int e = jit_launch_gemul(*jk, dA, dB, dC, batch, cx.stream);
+            if (e) return fail(QB_ECUDA, jk->name + " launch failed (CUresult " + std::to_string(e) + ")");
+            if ((rc = cx.out_done(C, bytes_c, dC))) return rc;
+            return cx.finish();
+        }
+    }
+    // not fused: the polynomial into a scratch copy of the operand, then the plain call on device memory
+    const void *src[2] = { dA, dB }; const uint64_t n[2] = { na, nb };
+    for (int i = 0; i < 2; i++) if (pp[i]) {
+        void *tmp;
+        if ((rc = cx.alloc(&tmp, n[i] * wb[i])) || (rc = launch_poly(prog[i], arith_bits(an[i]), src[i], tmp, n[i], wb[i], wb[i], cx.stream))) return rc;
+        src[i] = tmp;
+    }
+    int dev = 0; cudaGetDevice(&dev);
+    qb_exec ex = { QB_MEM_DEVICE, dev, (void *)cx.stream, cx.flags, 0 };
+    if ((rc = qb200_gemul_batched(gemul, src[0], src[1], dC, batch, &ex))) return rc;
     if ((rc = cx.out_done(C, bytes_c, dC))) return rc;
     return cx.finish();
 }

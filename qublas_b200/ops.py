@@ -325,6 +325,15 @@ def Qgemul_poly(Cbuf, A, B, plan: abi.qb_gemul_plan, poly: abi.qb_poly_plan, bat
     return Cbuf
 
 
+def Qgemul_prologue(Cbuf, A, B, plan: abi.qb_gemul_plan, poly_a=None, poly_b=None, batch: int = 1, flags: int = 0):
+    """Qgemul(C, poly_a(A), poly_b(B)): the polynomial(s) applied to the operand elements as they are staged (one launch).
+    A polynomial's result type must be the plan's operand type; None = that operand is used as it is."""
+    ex = _exec_for(A, B, Cbuf, flags=flags)
+    abi.check(abi.load().qb200_gemul_prologue_batched(C.byref(plan), C.byref(poly_a) if poly_a is not None else None,
+                                                      C.byref(poly_b) if poly_b is not None else None, _ptr(A), _ptr(B), _ptr(Cbuf), batch, C.byref(ex)))
+    return Cbuf
+
+
 def Qtable(x, x_t: QType, out_t: QType, func):
     """ANUS::Qtable<func>(x) (reference readme.md:66-78; not in the header): out = out_t(func(x.toDouble())), through a
     table over every raw value of x_t built here with the library's own double -> Qu quantizer."""

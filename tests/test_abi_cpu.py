@@ -284,3 +284,7 @@ def test_poly_kernels_specialise_with_nvrtc_without_a_gpu():
         pair = Pair(ops.make_gemul_plan(a, a, c, M, N, K, mul=mul, add=lv), poly)
         rc = lib.qb200_jit_check(7, ctypes.cast(ctypes.byref(pair), ctypes.c_void_p), log, 16384)
         assert rc == 0, log.value.decode()
+        # the polynomial as a prologue of both operands (its x type = its result type = the operand type)
+        pro = Pair(pair.g, ops.make_poly_plan(a, segs, 64, True))
+        rc = lib.qb200_jit_check(8, ctypes.cast(ctypes.byref(pro), ctypes.c_void_p), log, 16384)
+        assert rc == 0, log.value.decode()

@@ -113,6 +113,51 @@ def test_fused_epilogue_is_one_launch():
     assert lib.qb200_launch_count() == 1
 
 
+@pytest.mark.parametrize("which", ["a", "b", "ab"])
+def test_gemul_with_polynomial_prologue_vs_oracle(which):
+    """SURVEY 8(f) rank 3, the prologue side: Qgemul(C, Qapprox(A), Qapprox(B)) with the piecewise polynomial applied to the
+    operand elements as they are staged (register tiles: in the conversion pass, once per element; thread per output: on
+    load).  Same bits as the oracle's Qapprox over the operand followed by the oracle's Qgemul; device and host buffers, the
+    config-3 types at 64x64x64 (one launch), a ragged shape, and the unfused runtime-descriptor path."""
+    a = QType(7, 8); mul = QType(14, 8, True, RND_CONV, SAT_TCPL)
+    c = QType(17, 4, True, RND_POS_INF, SAT_TCPL)
+    k_t = QType(1, 14, True, RND_POS_INF, SAT_TCPL)
+    segs = [(-20.0, [(k_t, 1 << 10)]), (0.0, [(k_t, 0), (k_t, 1 << 12)]), (1e9, [(k_t, 0), (k_t, 1 << 14), (k_t, -5)])]
+    lib = abi.load()
+    for M, N, K, batch in ((64, 64, 64, 9), (10, 6, 12, 5)):
+        nlev = max(1, (K - 1).bit_length())
+        lv = [QType(15 + l, 8 - min(l, 8), True, RND_POS_INF, SAT_TCPL) for l in range(nlev)]
+        plan = ops.make_gemul_plan(a, a, c, M, N, K, mul=mul, add=lv)
+        pa = ops.make_poly_plan(a, segs, 0, True) if "a" in which else None
+        pb = ops.make_poly_plan(a, segs[1:], 0, True) if "b" in which else None
+        A = torch.empty(batch * M * K, dtype=torch.int32, device="cuda"); B = torch.empty(batch * K * N, dtype=torch.int32, device="cuda")
+        ops.synth_fill(A, a.raw_min, a.raw_max, 6, 0); ops.synth_fill(B, a.raw_min, a.raw_max, 6, 1)
+        A[:7] = a.raw_min; B[:7] = a.raw_min; A[7:14] = a.raw_max
+        An, Bn = A.cpu().numpy(), B.cpu().numpy()
+        Ap, Bp = An, Bn
+        if pa is not None:
+            pa.len = An.size; Ap = oracle.poly_batched(pa, An)
+        if pb is not None:
+            pb.len = Bn.size; Bp = oracle.poly_batched(pb, Bn)
+        want = oracle.gemul_batched(plan, Ap, Bp, batch)
+        Cd = torch.empty(batch * M * N, dtype=torch.int32, device="cuda")
+        ops.Qgemul_prologue(Cd, A, B, plan, pa, pb, batch=batch)
+        assert np.array_equal(Cd.cpu().numpy(), want), (M, which)
+        lib.qb200_launch_count_reset()
+        ops.Qgemul_prologue(Cd, A, B, plan, pa, pb, batch=batch)
+        assert lib.qb200_launch_count() == 1 and np.array_equal(Cd.cpu().numpy(), want)
+        Ch = np.empty(batch * M * N, dtype=np.int32)
+        ops.Qgemul_prologue(Ch, An, Bn, plan, pa, pb, batch=batch)
+        assert np.array_equal(Ch, want)
+        C2 = torch.empty_like(Cd)                                                     # polynomial into a scratch operand, then the runtime-descriptor Qgemul
+        ops.Qgemul_prologue(C2, A, B, plan, pa, pb, batch=batch, flags=abi.QB_F_NO_SPECIALIZE)
+        assert torch.equal(Cd, C2)
+    # a polynomial whose result type is not the operand type is refused
+    bad = ops.make_poly_plan(QType(6, 8), segs, 0, True)
+    with pytest.raises(Exception):
+        ops.Qgemul_prologue(Cd, A, B, plan, bad, None, batch=batch)
+
+
 def test_table_lookup_matches_quantized_function():
     """ANUS::Qtable<func>(x) (readme.md:66-78): out = out_t(func(x.toDouble())) for the three predefined tables."""
     x_t = QType(4, 8, True)
