@@ -359,6 +359,7 @@ struct I8Fuse {
     uint32_t panels_a, panels_b;  // units per k-chunk (0 when the operand is not packed here)
     uint32_t first_a, first_b;    // panels the first wave of tile pairs touches
     uint32_t group_a, group_b;    // panels that become live together afterwards: a row group of A, the n-tiles one more wave reaches
+    uint32_t sleep_ns;            // experiment (QB200_I8_PACK_SLEEP): pause per slice once the first wave's panels are done
     unsigned long long *stats;    // QB200_I8_STATS=1: [0] first CTA start, [1] last packer done, [2] ns the producers waited for flags, [3] last CTA done (globaltimer)
 };
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
@@ -405,6 +406,7 @@ __device__ __forceinline__ void packer_warp(const I8Fuse &F, uint32_t K, int lan
             const uint32_t cnt = (lim - base) < per ? (lim - base) : per, w = v - g * per * F.nkc;
             kc = w / cnt; panel = base + (w - kc * cnt);
         }
+        if (F.sleep_ns && u >= n0) __nanosleep(F.sleep_ns);
         const uint32_t k0 = kc * F.pk_k, klen = (K - k0) < F.pk_k ? (K - k0) : F.pk_k, items = klen / 16;      // K % 128 == 0: items % 8 == 0
         const uint64_t row0 = (uint64_t)panel * PK_ROWS + slice * F.slice_rows;
         const int32_t *src = (is_a ? F.srcA : F.srcB) + row0 * K + k0;
@@ -881,6 +883,11 @@ int i8gemm_run(const void *A, const void *B, void *C, uint32_t M, uint32_t N, ui
             F.first_a = fuse_a ? gm : 0;
             F.first_b = fuse_b ? (wave_n < P.tiles_n ? wave_n : P.tiles_n) : 0;
             F.group_a = gm; F.group_b = wave_n > 1 ? wave_n - 1 : 1;
+            static int packers = 0, sleep_ns = -1;  // experiments: QB200_I8_PACKERS = packer warps per CTA (1..8), QB200_I8_PACK_SLEEP = ns per slice after the first wave
+            if (!packers) { const char *e = getenv("QB200_I8_PACKERS"); const int v = e ? atoi(e) : 0; packers = (v >= 1 && v <= PACK_WARPS) ? v : PACK_WARPS; }
+            if (sleep_ns < 0) { const char *e = getenv("QB200_I8_PACK_SLEEP"); const int v = e ? atoi(e) : 0; sleep_ns = v > 0 ? v : 0; }
+            F.sleep_ns = (uint32_t)sleep_ns;
+            const unsigned fused_threads = I8_THREADS + 32 * packers;
             if (cudaMemsetAsync(sync, 0, sync_words * sizeof(uint32_t), s) != cudaSuccess) { *err = "cudaMemsetAsync failed"; return -1; }
             static int want_stats = -1;            // QB200_I8_STATS=1: per-call timeline of the fused kernel on stderr (synchronises; experiments only)
             if (want_stats < 0) { const char *e = getenv("QB200_I8_STATS"); want_stats = (e && e[0] == '1') ? 1 : 0; }
@@ -890,7 +897,7 @@ int i8gemm_run(const void *A, const void *B, void *C, uint32_t M, uint32_t N, ui
                 if (cudaMalloc(&F.stats, (8 + 2 * 4096) * sizeof(unsigned long long)) != cudaSuccess) { *err = "cudaMalloc failed"; return -1; }
                 cudaMemcpyAsync(F.stats, init, sizeof init, cudaMemcpyHostToDevice, s);
             }
-            k_i8gemm_pair_fused<<<clusters * 2, I8_THREADS_FUSED, P2_SMEM_BYTES, s>>>(mapA, mapB, C, P, outq, F);
+            k_i8gemm_pair_fused<<<clusters * 2, fused_threads, P2_SMEM_BYTES, s>>>(mapA, mapB, C, P, outq, F);
             if (want_stats) {
                 static unsigned long long st[8 + 2 * 4096];
                 cudaMemcpyAsync(st, F.stats, sizeof st, cudaMemcpyDeviceToHost, s);
