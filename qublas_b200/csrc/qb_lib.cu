@@ -1696,7 +1696,7 @@ extern "C" int qb200_gemul_f64_batched(const qb_gemul_plan *plan, const void *A,
 __global__ void __launch_bounds__(256) k_gemul_err_f64(const void *__restrict__ A, const void *__restrict__ B, const void *__restrict__ C, uint64_t batch,
                                                        const __grid_constant__ GemulShape S, int frac_a, int frac_b, int frac_c, double *__restrict__ part)
 {
-    extern __shared__ double err_sm[];
+    extern __shared__ __align__(16) double err_sm[];          // 16-byte loads of four consecutive rows / columns
     double *As = err_sm, *Bt = err_sm + (size_t)S.K * S.M;
     __shared__ double s0[256], s1[256], s2[256];
     const uint32_t M = S.M, N = S.N, K = S.K, tid = threadIdx.x;
