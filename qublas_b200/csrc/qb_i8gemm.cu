@@ -336,7 +336,8 @@ __device__ __forceinline__ void bar_wait_cluster(uint64_t *b, uint32_t parity)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fused operand narrowing (FUSE = true, round 2).  The reference keeps W <= 32 raws in int32 words; the tensor maps want
+// Fused operand narrowing (FUSE = true, round 2).  (An operand stored with its rows contiguous -- A as M x K, the
+// reference's natural layout -- is transposed in registers by the same warps: see packer_warp.)  The reference keeps W <= 32 raws in int32 words; the tensor maps want
 // int8.  Instead of two pack launches in front of the GEMM (HBM-bound, 2 x 48 us against 337 us of MMA time at 8192^3),
 // eight extra "packer" warps per CTA narrow the words WHILE the tensor cores run: a warp claims a slice (8 operand rows
 // x 512 k = 16 KiB of words) from a global counter, streams it (16-byte loads, 16-byte stores), and bumps the flag of its unit
@@ -360,6 +361,8 @@ struct I8Fuse {
     uint32_t first_a, first_b;    // panels the first wave of tile pairs touches
     uint32_t group_a, group_b;    // panels that become live together afterwards: a row group of A, the n-tiles one more wave reaches
     uint32_t sleep_ns;            // experiment (QB200_I8_PACK_SLEEP): pause per slice once the first wave's panels are done
+    uint32_t tr_a, tr_b;          // operand stored with its ROWS contiguous (A as M x K, B as N x K): the slice is transposed in registers
+    uint32_t ld_a, ld_b;          // ... and its leading dimension (M resp. N)
     unsigned long long *stats;    // QB200_I8_STATS=1: [0] first CTA start, [1] last packer done, [2] ns the producers waited for flags, [3] last CTA done (globaltimer)
 };
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
@@ -408,6 +411,32 @@ __device__ __forceinline__ void packer_warp(const I8Fuse &F, uint32_t K, int lan
         }
         if (F.sleep_ns && u >= n0) __nanosleep(F.sleep_ns);
         const uint32_t k0 = kc * F.pk_k, klen = (K - k0) < F.pk_k ? (K - k0) : F.pk_k, items = klen / 16;      // K % 128 == 0: items % 8 == 0
+        if (is_a ? F.tr_a : F.tr_b) {
+            // rows contiguous in memory: a lane owns one operand row, reads it k by k (the warp's 32 rows are 128 contiguous
+            // bytes per k) and stores 32 narrowed k at a time (two 16-byte stores = one full sector of its K-major row).
+            // The unit's slices are 8 blocks of 32 rows x (slices / 8) parts of the k-chunk.
+            const uint32_t nsub = F.slices / 8, rb = slice % 8, ks = slice / 8, sub = klen / nsub;      // sub % 32 == 0 (host)
+            const uint64_t ld = is_a ? F.ld_a : F.ld_b, row = (uint64_t)panel * PK_ROWS + rb * 32 + lane;
+            const int32_t *src = (is_a ? F.srcA : F.srcB) + row + (uint64_t)(k0 + ks * sub) * ld;
+            int8_t *dst = (is_a ? F.dstA : F.dstB) + row * K + k0 + ks * sub;
+            for (uint32_t kk = 0; kk < sub; kk += 32) {
+                int v[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j] = __ldcs(src + (uint64_t)(kk + j) * ld);
+                uint4 *d = (uint4 *)(dst + kk);
+                d[0] = make_uint4(pack4(v[0], v[1], v[2], v[3]), pack4(v[4], v[5], v[6], v[7]), pack4(v[8], v[9], v[10], v[11]), pack4(v[12], v[13], v[14], v[15]));
+                d[1] = make_uint4(pack4(v[16], v[17], v[18], v[19]), pack4(v[20], v[21], v[22], v[23]), pack4(v[24], v[25], v[26], v[27]), pack4(v[28], v[29], v[30], v[31]));
+            }
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) {
+                uint32_t *flag = F.sync + 1 + (is_a ? 0u : F.panels_a * F.nkc) + panel * F.nkc + kc;
+                asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(flag) : "memory");
+            }
+            s = __shfl_sync(0xffffffffu, s_next, 0);
+            continue;
+        }
         const uint64_t row0 = (uint64_t)panel * PK_ROWS + slice * F.slice_rows;
         const int32_t *src = (is_a ? F.srcA : F.srcB) + row0 * K + k0;
         int8_t *dst = (is_a ? F.dstA : F.dstB) + row0 * K + k0;
@@ -786,7 +815,14 @@ static void pk_init()
 }
 static uint32_t pk_k() { pk_init(); return g_pk_k; }
 static uint32_t pk_rows() { pk_init(); return g_pk_rows; }
-static bool fusable(const void *p, int wb, bool k_major, bool zero_copy) { return !zero_copy && wb == 4 && k_major && (((uintptr_t)p) & 15) == 0; }
+// rows contiguous (k_major == false): transposed in registers by the packers, needs slices in 8 row blocks x parts of >= 32 k
+static bool fusable(const void *p, int wb, bool k_major, bool zero_copy)
+{
+    if (zero_copy || wb != 4) return false;
+    if (k_major) return (((uintptr_t)p) & 15) == 0;
+    const uint32_t slices = PK_ROWS / pk_rows();
+    return (((uintptr_t)p) & 3) == 0 && slices % 8 == 0 && (BK / (slices / 8)) % 32 == 0 && !getenv("QB200_I8_NO_FUSE_T");
+}
 size_t i8gemm_sync_words(const void *A, const void *B, uint32_t M, uint32_t N, uint32_t K, bool trans_a, bool trans_b, int a_wb, int b_wb)
 {
     static int off = -1;                           // QB200_I8_NO_FUSE=1: always pack with separate launches (experiments)
@@ -883,6 +919,7 @@ int i8gemm_run(const void *A, const void *B, void *C, uint32_t M, uint32_t N, ui
             F.first_a = fuse_a ? gm : 0;
             F.first_b = fuse_b ? (wave_n < P.tiles_n ? wave_n : P.tiles_n) : 0;
             F.group_a = gm; F.group_b = wave_n > 1 ? wave_n - 1 : 1;
+            F.tr_a = a_tr ? 1u : 0u; F.tr_b = b_tr ? 1u : 0u; F.ld_a = M; F.ld_b = N;
             static int packers = 0, sleep_ns = -1;  // experiments: QB200_I8_PACKERS = packer warps per CTA (1..8), QB200_I8_PACK_SLEEP = ns per slice after the first wave
             if (!packers) { const char *e = getenv("QB200_I8_PACKERS"); const int v = e ? atoi(e) : 0; packers = (v >= 1 && v <= PACK_WARPS) ? v : PACK_WARPS; }
             if (sleep_ns < 0) { const char *e = getenv("QB200_I8_PACK_SLEEP"); const int v = e ? atoi(e) : 0; sleep_ns = v > 0 ? v : 0; }
