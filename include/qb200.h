@@ -356,6 +356,13 @@ int qb200_gemul_sharded(const qb_gemul_plan *plan, const qb_shard *shards, uint3
 int qb200_allgather(void *const *dst, const void *const *src, const int32_t *devices, uint32_t n, uint64_t rows, uint64_t dst_pitch,
                     const uint64_t *dst_off, const uint64_t *src_pitch, const uint64_t *width, double *seconds);
 
+/* GEMM -> all-gather in ONE kernel per GPU: shard r (shards[r].device, .A = its M-row panel of op(A), .B = all of B; .C and
+ * .batch are ignored) computes rows [r * plan->M, (r + 1) * plan->M) of a (n * plan->M) x N column-major C, and the
+ * tensor-core epilogue stores every element into c_full[j] on EVERY device j (its own through local stores, the others'
+ * through peer stores over NVLink / NVSwitch), tile by tile behind the MMAs of the next tile.  No copy pass afterwards.
+ * Tensor-core plans only (lossless int8-range accumulation, plan->M a multiple of 256), n <= 8; complete on return. */
+int qb200_gemul_panels_gathered(const qb_gemul_plan *plan, const qb_shard *shards, uint32_t n, void *const *c_full, const qb_exec *exec);
+
 /* Contiguous shard [first, first+count) of `total` units for `rank` of `world` (batch or M-panel). */
 int qb200_shard_range(uint64_t total, uint32_t world, uint32_t rank, uint64_t *first, uint64_t *count);
 

@@ -147,7 +147,7 @@ ABI_SYMBOLS = [
     "qb200_launch_count_reset", "qb200_reduce_plan_info", "qb200_gemul_plan_info", "qb200_cgemul_plan_info",
     "qb200_reduce_batched", "qb200_gemul_batched", "qb200_cgemul_batched", "qb200_tfcmul_batched",
     "qb200_convert_batched", "qb200_elementwise_batched", "qb200_synth_fill", "qb200_shard_range", "qb200_measure_int_peak", "qb200_jit_check_gemul", "qb200_jit_check", "qb200_quantize_f64", "qb200_dequantize_f64", "qb200_error_stats",
-    "qb200_selftest_fp", "qb200_gemul_f64_batched", "qb200_gemul_error_batched", "qb200_gemul_prologue_batched", "qb200_host_alloc", "qb200_host_free", "qb200_device_alloc", "qb200_device_free", "qb200_memcpy", "qb200_gemul_sharded", "qb200_allgather",
+    "qb200_selftest_fp", "qb200_gemul_f64_batched", "qb200_gemul_error_batched", "qb200_gemul_prologue_batched", "qb200_host_alloc", "qb200_host_free", "qb200_device_alloc", "qb200_device_free", "qb200_memcpy", "qb200_gemul_sharded", "qb200_gemul_panels_gathered", "qb200_allgather",
     "qb200_poly_plan_info", "qb200_poly_batched", "qb200_gemul_poly_batched", "qb200_table_batched",
 ]
 
@@ -199,6 +199,7 @@ def load() -> C.CDLL:
     L.qb200_device_free.argtypes = [vp, C.c_int]
     L.qb200_memcpy.argtypes = [vp, vp, C.c_size_t, C.c_int]
     L.qb200_gemul_sharded.argtypes = [C.POINTER(qb_gemul_plan), C.POINTER(qb_shard), u32, C.POINTER(qb_exec)]
+    L.qb200_gemul_panels_gathered.argtypes = [C.POINTER(qb_gemul_plan), C.POINTER(qb_shard), u32, C.POINTER(vp), C.POINTER(qb_exec)]
     L.qb200_allgather.argtypes = [C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int32), u32, u64, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_double)]
     L.qb200_poly_plan_info.argtypes = [C.POINTER(qb_poly_plan), C.POINTER(qb_plan_info)]
     L.qb200_poly_batched.argtypes = [C.POINTER(qb_poly_plan), vp, vp, u64, C.POINTER(qb_exec)]

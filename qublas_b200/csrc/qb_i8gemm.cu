@@ -133,6 +133,9 @@ struct I8Params {
     uint32_t tiles_m, tiles_n;
     int32_t  c_wb;
     uint32_t group_m;             // rasterisation: group_m m-tiles share each B panel while it is hot in L2
+    uint32_t n_out, row0;         // n_out > 0 (pair kernels): fan the result out into outs[0 .. n_out), rows starting at row0, leading dimension ldc
+    uint64_t ldc;
+    void    *outs[8];
 };
 
 // MC = false: one CTA per tile, plain TMA.
@@ -583,8 +586,12 @@ __device__ __forceinline__ void i8gemm_pair_body(const CUtensorMap &mapA, const 
                     const uint64_t col = (uint64_t)tn * BN + c0 + c;
                     const int32_t q = plain ? (int32_t)v[c] : conv_apply<int32_t, false>((int32_t)v[c], outq);
                     if (row < P.M && col < P.N) {
-                        if (P.c_wb == 4) ((int32_t *)C)[col * P.M + row] = q;
-                        else             ((int64_t *)C)[col * P.M + row] = (int64_t)q;
+                        if (P.n_out) {                                      // GEMM -> all-gather: local and peer stores, 128 contiguous bytes per warp and column
+                            const uint64_t e = col * P.ldc + P.row0 + row;
+                            for (uint32_t o = 0; o < P.n_out; o++) ((int32_t *)P.outs[o])[e] = q;
+                        }
+                        else if (P.c_wb == 4) ((int32_t *)C)[col * P.M + row] = q;
+                        else                  ((int64_t *)C)[col * P.M + row] = (int64_t)q;
                     }
                 }
             }
@@ -836,7 +843,7 @@ size_t i8gemm_sync_words(const void *A, const void *B, uint32_t M, uint32_t N, u
 }
 
 int i8gemm_run(const void *A, const void *B, void *C, uint32_t M, uint32_t N, uint32_t K, bool trans_a, bool trans_b, int a_wb,
-               int b_wb, int c_wb, const QStage &outq, int8_t *Ap, int8_t *Bp, uint32_t *sync, cudaStream_t s, const char **err)
+               int b_wb, int c_wb, const QStage &outq, int8_t *Ap, int8_t *Bp, uint32_t *sync, cudaStream_t s, const char **err, const I8FanOut *fan)
 {
     uint32_t Mp, Np, Kp;
     i8gemm_padded_dims(M, N, K, &Mp, &Np, &Kp);
@@ -903,6 +910,13 @@ int i8gemm_run(const void *A, const void *B, void *C, uint32_t M, uint32_t N, ui
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     I8Params P;
     P.M = M; P.N = N; P.K = Kp; P.tiles_m = Mp / BM; P.tiles_n = Np / BN; P.c_wb = c_wb; P.group_m = 16;
+    P.n_out = 0; P.row0 = 0; P.ldc = M;
+    for (int o = 0; o < 8; o++) P.outs[o] = nullptr;
+    if (fan) {
+        if (!pair || c_wb != 4 || fan->n == 0 || fan->n > 8) { *err = "the fused all-gather needs the pair kernel (M a multiple of 256), int32 results and at most 8 destinations"; return -1; }
+        P.n_out = fan->n; P.row0 = fan->row0; P.ldc = fan->ldc;
+        for (uint32_t o = 0; o < fan->n; o++) P.outs[o] = fan->out[o];
+    }
     const uint32_t ntiles = P.tiles_m * P.tiles_n;
     if (mc) {
         P.group_m = 8;                                                     // 8 tile pairs = 16 m-tiles per group

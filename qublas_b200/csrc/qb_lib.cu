@@ -590,6 +590,9 @@ extern "C" int qb200_gemul_plan_info(const qb_gemul_plan *plan, qb_plan_info *in
     return QB_OK;
 }
 
+// set by qb200_gemul_panels_gathered around its per-shard call: the tensor-core epilogue stores into every device's C
+static thread_local const I8FanOut *tl_fanout = nullptr;
+
 extern "C" int qb200_gemul_batched(const qb_gemul_plan *plan, const void *A, const void *B, void *C, uint64_t batch,
                                    const qb_exec *exec)
 {
@@ -648,6 +651,7 @@ extern "C" int qb200_gemul_batched(const qb_gemul_plan *plan, const void *A, con
         return post_launch("k_gemul_thread");
     };
     const bool tc = !(cx.flags & QB_F_NO_TENSOR_CORE) && ce->tc;
+    if (tl_fanout && (!tc || batch != 1 || cx.host)) return fail(QB_EINVAL, "the fused all-gather needs one device-resident instance on the tensor-core path");
     if (tc) {
         // lossless accumulation: exact int8 x int8 -> int32 dot products on the tensor cores, C's quantizer in the epilogue
         const size_t bytes_a = span_elems(batch, plan->stride_a, ea) * gp.a_wb, bytes_b = span_elems(batch, plan->stride_b, eb) * gp.b_wb,
@@ -675,7 +679,7 @@ extern "C" int qb200_gemul_batched(const qb_gemul_plan *plan, const void *A, con
             const char *err = "";
             if (i8gemm_run((const char *)dA + i * plan->stride_a * gp.a_wb, (const char *)dB + i * plan->stride_b * gp.b_wb,
                            (char *)dC + i * plan->stride_c * gp.c_wb, plan->M, plan->N, plan->K, plan->trans_a, plan->trans_b, gp.a_wb, gp.b_wb,
-                           gp.c_wb, gp.out, (int8_t *)Ap, (int8_t *)Bp, (uint32_t *)sync, cx.stream, &err))
+                           gp.c_wb, gp.out, (int8_t *)Ap, (int8_t *)Bp, (uint32_t *)sync, cx.stream, &err, tl_fanout))
                 return fail(QB_ECUDA, std::string("k_i8gemm: ") + err);
         }
         if ((rc = cx.out_done(C, bytes_c, dC))) return rc;
@@ -1846,6 +1850,70 @@ extern "C" int qb200_gemul_sharded(const qb_gemul_plan *plan, const qb_shard *sh
 // dependency: it is optional and separate from the kernels).  Shard i is `rows` rows of width[i] bytes with pitch
 // src_pitch[i] on devices[i]; it lands at byte offset dst_off[i] of every row of dst[j] (pitch dst_pitch) on every device j.
 // rows == 1 is the contiguous case (batch shards); rows = N with column-major M x N matrices gathers M-row panels.
+static int enable_peers(const int32_t *devices, uint32_t n)
+{
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (uint32_t i = 0; i < n; i++) {
+        CUDA_TRY(cudaSetDevice(devices[i]));
+        for (uint32_t j = 0; j < n; j++) {
+            if (devices[j] == devices[i]) continue;
+            int can = 0;
+            CUDA_TRY(cudaDeviceCanAccessPeer(&can, devices[i], devices[j]));
+            if (!can) { cudaSetDevice(prev); return fail(QB_ECUDA, "no peer access between devices " + std::to_string(devices[i]) + " and " + std::to_string(devices[j])); }
+            cudaError_t e = cudaDeviceEnablePeerAccess(devices[j], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaSetDevice(prev); return fail(QB_ECUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)); }
+            cudaGetLastError();
+        }
+    }
+    cudaSetDevice(prev);
+    return QB_OK;
+}
+
+// GEMM -> all-gather in ONE kernel per GPU (the optional output all-gather of SURVEY.md 8(e), fused): shard r computes the
+// M-row panel r of a (n * M) x N column-major C and its tensor-core epilogue stores every element into the C of EVERY
+// device -- its own through local stores, the others' through peer stores over NVLink / NVSwitch (128 contiguous bytes per
+// warp and column), overlapped tile by tile with the MMAs of the next tile through the second TMEM accumulator.  No
+// separate copy pass, no staging of the panel.  plan describes ONE panel (plan->M rows); c_full[j] is the whole C on
+// shards[j].device (leading dimension n * M); shards[r].C is ignored.  Tensor-core plans only (lossless int8-range
+// accumulation, M a multiple of 256); n <= 8.  Complete on return.
+extern "C" int qb200_gemul_panels_gathered(const qb_gemul_plan *plan, const qb_shard *shards, uint32_t n, void *const *c_full, const qb_exec *exec)
+{
+    if (!plan || !shards || !c_full) return fail(QB_EINVAL, "null argument");
+    if (n == 0) return QB_OK;
+    if (n > 8) return fail(QB_EINVAL, "at most 8 panels");
+    if (exec && (exec->stream || exec->mem_kind != QB_MEM_DEVICE)) return fail(QB_EINVAL, "device-resident panels on the library's own streams");
+    int32_t devs[8];
+    for (uint32_t r = 0; r < n; r++) { devs[r] = shards[r].device; if (!shards[r].A || !shards[r].B || !c_full[r]) return fail(QB_EINVAL, "null shard pointer"); }
+    int rc = enable_peers(devs, n); if (rc) return rc;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    std::vector<int> rcs(n, QB_OK);
+    std::vector<std::string> errs(n);
+    std::vector<std::thread> th;
+    for (uint32_t r = 0; r < n; r++) {
+        th.emplace_back([&, r] {
+            I8FanOut fan;
+            fan.n = n; fan.row0 = r * plan->M; fan.ldc = (uint64_t)n * plan->M;
+            for (uint32_t j = 0; j < 8; j++) fan.out[j] = j < n ? c_full[j] : nullptr;
+            qb_exec ex = { (int32_t)QB_MEM_DEVICE, shards[r].device, nullptr, exec ? exec->flags : 0u, 0 };
+            tl_fanout = &fan;
+            int e = qb200_gemul_batched(plan, shards[r].A, shards[r].B, c_full[r], 1, &ex);
+            tl_fanout = nullptr;
+            if (!e) {
+                cudaError_t ce = cudaStreamSynchronize(nullptr);
+                if (ce != cudaSuccess) e = fail(QB_ECUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(ce));
+            }
+            rcs[r] = e;
+            if (e) errs[r] = g_err;
+        });
+    }
+    for (auto &t : th) t.join();
+    cudaSetDevice(prev);
+    for (uint32_t r = 0; r < n; r++) if (rcs[r]) return fail(rcs[r], "panel " + std::to_string(r) + " (device " + std::to_string(shards[r].device) + "): " + errs[r]);
+    return QB_OK;
+}
+
 extern "C" int qb200_allgather(void *const *dst, const void *const *src, const int32_t *devices, uint32_t n, uint64_t rows, uint64_t dst_pitch,
                                const uint64_t *dst_off, const uint64_t *src_pitch, const uint64_t *width, double *seconds)
 {

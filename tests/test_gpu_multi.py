@@ -112,3 +112,38 @@ def test_allgather_of_row_panels_into_column_major_matrices():
     abi.check(lib.qb200_allgather(dst, src, dv, n, N, M * 4, off, sp, wid, None))
     for r in range(n):
         assert np.array_equal(Cg[r].cpu().numpy(), full), r
+
+
+@pytest.mark.parametrize("n,words", [(2, 4), (3, 4), (2, 1)])
+def test_gemm_and_allgather_in_one_kernel_per_gpu(n, words):
+    """qb200_gemul_panels_gathered: panel r of a (n * M) x N Qgemul on the tensor-core path, whose epilogue stores every
+    element into the column-major C of EVERY device (local + peer stores) -- no copy pass.  Every device's C equals the exact
+    float64 GEMM of the whole problem; int32 words (narrowed inside the same kernel) and int8 operands read in place."""
+    lib = abi.load()
+    devs = _devices(n)
+    M, N, K = 256, 512, 384
+    t = QType(7, 0); acc = QType(30, 0)
+    plan = ops.make_gemul_plan(t, t, acc, M, N, K, mul=QType(15, 0), add=[acc], trans_a=True, word_bytes=(words if words == 1 else 0, words if words == 1 else 0, 0))
+    assert ops.plan_info_gemul(plan).tensor_core == 1
+    rng = np.random.default_rng(n + words)
+    dt = np.int8 if words == 1 else np.int32
+    Afull = rng.integers(-128, 128, size=(n * M, K)).astype(dt)                 # op(A) row-major = stored K-major
+    Bm = rng.integers(-128, 128, size=(N, K)).astype(dt)                        # B stored K x N column-major = [j][k]
+    want = (Afull.astype(np.float64) @ Bm.astype(np.float64).T).T               # [j][i] = column-major (n * M) x N
+    A, B, Cf = [], [], []
+    for r, d in enumerate(devs):
+        dev = torch.device("cuda", d)
+        A.append(torch.from_numpy(np.ascontiguousarray(Afull[r * M:(r + 1) * M])).to(dev)); B.append(torch.from_numpy(Bm).to(dev))
+        Cf.append(torch.full((N, n * M), -7, dtype=torch.int32, device=dev))
+    shards = (abi.qb_shard * n)(*[abi.qb_shard(devs[r], 0, A[r].data_ptr(), B[r].data_ptr(), 0, 1) for r in range(n)])
+    cf = (C.c_void_p * n)(*[x.data_ptr() for x in Cf])
+    for d in set(devs):
+        torch.cuda.synchronize(d)
+    ex = abi.qb_exec(abi.QB_MEM_DEVICE, -1, None, 0, 0)
+    for _ in range(2):                                                          # twice: flags of the fused narrowing are per call
+        abi.check(lib.qb200_gemul_panels_gathered(C.byref(plan), shards, n, cf, C.byref(ex)))
+    for r in range(n):
+        assert np.array_equal(Cf[r].cpu().numpy().astype(np.float64), want), r
+    # plans off the tensor-core path are refused
+    a3, p3 = c3_plan()
+    assert lib.qb200_gemul_panels_gathered(C.byref(p3), shards, n, cf, C.byref(ex)) == abi.QB_EINVAL
