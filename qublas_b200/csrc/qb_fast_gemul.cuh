@@ -182,7 +182,10 @@ constexpr QStage stage_without_clamps(QStage q) { q.need_lo = 0; q.need_hi = 0; 
 template <class Cfg> __host__ __device__ constexpr bool s_form_ok()
 {
     typedef GemulTile<Cfg, 4, 4> T;
-    if (!T::K_POW2 || Cfg::NLEV < 3 || T::NCH > 8 || T::BLOCK > 512) return false;       // needs the fully unrolled chunk loop
+#ifndef QB_SFORM_MAX_NCH
+#define QB_SFORM_MAX_NCH 16                                     // K <= 128: 64x64x128 runs at 10.3 TMAC/s in this form, 9.0 without
+#endif
+    if (!T::K_POW2 || Cfg::NLEV < 3 || T::NCH > QB_SFORM_MAX_NCH || T::BLOCK > 512) return false;       // needs the fully unrolled chunk loop
     constexpr AddStage l0 = Cfg::lvl(0);
     if (l0.q.shift != 0 || l0.q.need_lo || l0.q.need_hi || l0.q.wide || l0.shl_a || l0.shl_b || l0.sub) return false;
     if (l0.q.of == WRP_TCPL && (l0.q.need_lo || l0.q.need_hi)) return false;

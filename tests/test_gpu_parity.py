@@ -987,7 +987,8 @@ def test_saturation_by_operand_substitution_other_widths(a, b, mul, sform):
     assert torch.equal(Cd, C2)
 
 
-@pytest.mark.parametrize("K,modes,fp", [(64, "PPPPP", True), (64, "PNTPN", True), (32, "TTTT", False), (16, "NPP", True), (8, "PP", False), (64, "PPPPP", False)])
+@pytest.mark.parametrize("K,modes,fp", [(64, "PPPPP", True), (64, "PNTPN", True), (32, "TTTT", False), (16, "NPP", True), (8, "PP", False), (64, "PPPPP", False),
+                                        (128, "PPPPPP", True), (128, "PNPTPN", True)])
 def test_tile_kernel_deferred_shift_tree_vs_oracle(K, modes, fp):
     """The S form of the register-tile kernel (qb_fast_gemul.cuh: exact level 0, clamp-free halving levels with a
     data-independent bias -- RND::POS_INF, RND::NEG_INF, TRN::TCPL at a 1-bit shift -- carried as pre-shift sums with the
