@@ -475,7 +475,7 @@ __device__ __forceinline__ void packer_warp(const I8Fuse &F, uint32_t K, int lan
     }
 }
 
-template <bool FUSE>
+template <bool FUSE, bool FAN>
 __device__ __forceinline__ void i8gemm_pair_body(const CUtensorMap &mapA, const CUtensorMap &mapB, void *__restrict__ C, const I8Params &P,
                                                  const QStage &outq, const I8Fuse &F)
 {
@@ -586,12 +586,13 @@ __device__ __forceinline__ void i8gemm_pair_body(const CUtensorMap &mapA, const 
                     const uint64_t col = (uint64_t)tn * BN + c0 + c;
                     const int32_t q = plain ? (int32_t)v[c] : conv_apply<int32_t, false>((int32_t)v[c], outq);
                     if (row < P.M && col < P.N) {
-                        if (P.n_out) {                                      // GEMM -> all-gather: local and peer stores, 128 contiguous bytes per warp and column
+                        if constexpr (FAN) {                                // GEMM -> all-gather: local and peer stores, 128 contiguous bytes per warp and column
                             const uint64_t e = col * P.ldc + P.row0 + row;
                             for (uint32_t o = 0; o < P.n_out; o++) ((int32_t *)P.outs[o])[e] = q;
+                        } else {
+                            if (P.c_wb == 4) ((int32_t *)C)[col * P.M + row] = q;
+                            else             ((int64_t *)C)[col * P.M + row] = (int64_t)q;
                         }
-                        else if (P.c_wb == 4) ((int32_t *)C)[col * P.M + row] = q;
-                        else                  ((int64_t *)C)[col * P.M + row] = (int64_t)q;
                     }
                 }
             }
@@ -612,14 +613,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1)
 k_i8gemm_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, void *__restrict__ C,
               const __grid_constant__ I8Params P, const __grid_constant__ QStage outq)
 {
-    i8gemm_pair_body<false>(mapA, mapB, C, P, outq, I8Fuse{});
+    i8gemm_pair_body<false, false>(mapA, mapB, C, P, outq, I8Fuse{});
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS_FUSED, 1)
 k_i8gemm_pair_fused(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, void *__restrict__ C,
                     const __grid_constant__ I8Params P, const __grid_constant__ QStage outq, const __grid_constant__ I8Fuse F)
 {
-    i8gemm_pair_body<true>(mapA, mapB, C, P, outq, F);
+    i8gemm_pair_body<true, false>(mapA, mapB, C, P, outq, F);
+}
+
+// the same two kernels with the result fanned out into the C of every device (qb200_gemul_panels_gathered): separate
+// instantiations, so that the plain epilogue keeps its code
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1)
+k_i8gemm_pair_fan(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, void *__restrict__ C,
+                  const __grid_constant__ I8Params P, const __grid_constant__ QStage outq)
+{
+    i8gemm_pair_body<false, true>(mapA, mapB, C, P, outq, I8Fuse{});
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS_FUSED, 1)
+k_i8gemm_pair_fused_fan(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, void *__restrict__ C,
+                        const __grid_constant__ I8Params P, const __grid_constant__ QStage outq, const __grid_constant__ I8Fuse F)
+{
+    i8gemm_pair_body<true, true>(mapA, mapB, C, P, outq, F);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -904,7 +920,9 @@ int i8gemm_run(const void *A, const void *B, void *C, uint32_t M, uint32_t N, ui
         if (cudaFuncSetAttribute(k_i8gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(k_i8gemm_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(k_i8gemm_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(k_i8gemm_pair_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES) != cudaSuccess) { *err = "cannot raise dynamic smem"; return -1; }
+            cudaFuncSetAttribute(k_i8gemm_pair_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(k_i8gemm_pair_fan, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(k_i8gemm_pair_fused_fan, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES) != cudaSuccess) { *err = "cannot raise dynamic smem"; return -1; }
         attr_set[dev & 63] = true;
     }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -948,7 +966,8 @@ int i8gemm_run(const void *A, const void *B, void *C, uint32_t M, uint32_t N, ui
                 if (cudaMalloc(&F.stats, (8 + 2 * 4096) * sizeof(unsigned long long)) != cudaSuccess) { *err = "cudaMalloc failed"; return -1; }
                 cudaMemcpyAsync(F.stats, init, sizeof init, cudaMemcpyHostToDevice, s);
             }
-            k_i8gemm_pair_fused<<<clusters * 2, fused_threads, P2_SMEM_BYTES, s>>>(mapA, mapB, C, P, outq, F);
+            if (P.n_out) k_i8gemm_pair_fused_fan<<<clusters * 2, fused_threads, P2_SMEM_BYTES, s>>>(mapA, mapB, C, P, outq, F);
+            else         k_i8gemm_pair_fused<<<clusters * 2, fused_threads, P2_SMEM_BYTES, s>>>(mapA, mapB, C, P, outq, F);
             if (want_stats) {
                 static unsigned long long st[8 + 2 * 4096];
                 cudaMemcpyAsync(st, F.stats, sizeof st, cudaMemcpyDeviceToHost, s);
@@ -967,6 +986,7 @@ int i8gemm_run(const void *A, const void *B, void *C, uint32_t M, uint32_t N, ui
                         (st[1] - st[0]) * 1e-3, (st[3] - st[0]) * 1e-3, st[2] * 1e-3, clusters * 2);
             }
         }
+        else if (pair && P.n_out) k_i8gemm_pair_fan<<<clusters * 2, I8_THREADS, P2_SMEM_BYTES, s>>>(mapA, mapB, C, P, outq);
         else if (pair) k_i8gemm_pair<<<clusters * 2, I8_THREADS, P2_SMEM_BYTES, s>>>(mapA, mapB, C, P, outq);
         else      k_i8gemm_mc<<<clusters * 2, I8_THREADS, SMEM_BYTES, s>>>(mapA, mapB, C, P, outq);
     } else {
