@@ -989,7 +989,8 @@ def test_saturation_by_operand_substitution_other_widths(a, b, mul, sform):
 
 @pytest.mark.parametrize("K,modes,fp", [(64, "PPPPP", True), (64, "PNTPN", True), (32, "TTTT", False), (16, "NPP", True), (8, "PP", False), (64, "PPPPP", False),
                                         (128, "PPPPPP", True), (128, "PNPTPN", True)])
-def test_tile_kernel_deferred_shift_tree_vs_oracle(K, modes, fp):
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
+def test_tile_kernel_deferred_shift_tree_vs_oracle(K, modes, fp, ta, tb):
     """The S form of the register-tile kernel (qb_fast_gemul.cuh: exact level 0, clamp-free halving levels with a
     data-independent bias -- RND::POS_INF, RND::NEG_INF, TRN::TCPL at a 1-bit shift -- carried as pre-shift sums with the
     biases folded into compile-time constants) against the oracle and the runtime-descriptor kernel, full-range operands,
@@ -1001,7 +1002,9 @@ def test_tile_kernel_deferred_shift_tree_vs_oracle(K, modes, fp):
     lv = [QType(15, 8, True, RND_POS_INF, SAT_TCPL)] + [QType(15 + l, 8 - l, True, m[modes[l - 1]], SAT_TCPL) for l in range(1, len(modes) + 1)]
     assert len(lv) == K.bit_length() - 1
     c = QType(17, 4, True, RND_POS_INF, SAT_TCPL)
-    plan = ops.make_gemul_plan(a, a, c, 64, 32, K, mul=mul, add=lv)
+    if (ta or tb) and not (fp and K in (64, 128)):
+        pytest.skip("transposed operands: the substituted / negated forms only")
+    plan = ops.make_gemul_plan(a, a, c, 64, 32, K, mul=mul, add=lv, trans_a=ta, trans_b=tb)
     batch = 11
     A = torch.empty(batch * 64 * K, dtype=torch.int32, device="cuda"); B = torch.empty(batch * K * 32, dtype=torch.int32, device="cuda")
     ops.synth_fill(A, a.raw_min, a.raw_max, 21, 0); ops.synth_fill(B, a.raw_min, a.raw_max, 21, 1)
