@@ -150,6 +150,37 @@ def test_jit_specialisation_compiles_without_a_device():
         assert rc == 0, (M, N, K, log.value.decode())
 
 
+def test_register_tile_variants_compile_without_a_device():
+    """The register-tile template in the forms its compile-time predicates select (qb_fast_gemul.cuh): substituted operands
+    (fp_subst) with the negated deferred-shift tree (all levels RND::POS_INF), with group constants (mixed level modes), without
+    the deferred-shift form (wide levels), at K = 128, with packed int16 words, with groups of small instances per CTA, with
+    transposed operands; and the per-instance clamp elision where the substitution does not apply (TRN::TCPL product)."""
+    import ctypes
+    from qublas_b200.qtypes import RND_CONV, RND_NEG_INF, RND_POS_INF, SAT_TCPL, TRN_TCPL
+    lib = abi.load()
+    log = ctypes.create_string_buffer(16384)
+    a = QType(7, 8); c = QType(17, 4, True, RND_POS_INF, SAT_TCPL)
+    conv = QType(14, 8, True, RND_CONV, SAT_TCPL); trn = QType(14, 8, True, TRN_TCPL, SAT_TCPL)
+
+    def halving(K, modes):
+        return [QType(15, 8, True, RND_POS_INF, SAT_TCPL)] + [QType(15 + l, 8 - l, True, modes[(l - 1) % len(modes)], SAT_TCPL) for l in range(1, K.bit_length() - 1)]
+
+    cases = [
+        (64, 64, 64, conv, halving(64, [RND_POS_INF]), {}),
+        (64, 64, 64, conv, halving(64, [RND_POS_INF, RND_NEG_INF, TRN_TCPL]), {}),
+        (64, 64, 64, conv, [QType(16 + l, 8, True, RND_POS_INF, SAT_TCPL) for l in range(6)], {}),
+        (64, 64, 128, conv, halving(128, [RND_POS_INF]), {}),
+        (64, 64, 64, conv, halving(64, [RND_POS_INF]), {"word_bytes": (2, 2, 0)}),
+        (16, 16, 16, conv, halving(16, [RND_POS_INF]), {}),
+        (64, 32, 64, conv, halving(64, [RND_POS_INF]), {"trans_a": True, "trans_b": True}),
+        (64, 64, 64, trn, halving(64, [RND_POS_INF]), {}),
+    ]
+    for (M, N, K, mul, lv, kw) in cases:
+        plan = ops.make_gemul_plan(a, a, c, M, N, K, mul=mul, add=lv, **kw)
+        rc = lib.qb200_jit_check_gemul(ctypes.byref(plan), log, 16384)
+        assert rc == 0, (M, N, K, kw, log.value.decode()[:1500])
+
+
 def test_every_jit_template_compiles_without_a_device():
     """qb200_jit_check: the complex thread-per-output template (all four product kinds), the mat-vec rows template, both
     Qreduce templates, and the element-wise templates (complex products, real ops, convert) go through codegen + NVRTC
